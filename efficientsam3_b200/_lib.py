@@ -1,0 +1,84 @@
+"""ctypes binding of libes3.so (the C ABI declared in include/es3.h).
+
+The product path has NO fallback: if the shared library is missing, or the device is not a CC 10.x
+GPU, importing/using the ops raises.  Nothing in this package imports `oracle/`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libes3.so"
+
+_vp, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+
+# name -> argtypes  (restype is always int unless noted)
+SIGNATURES: dict[str, list] = {
+    "es3_init": [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
+    "es3_gemm_bf16": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _i, _vp],
+    "es3_conv3x3_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp],
+    "es3_gemm_simt": [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _i, _vp],
+    "es3_stem_conv3x3_s2": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "es3_dwconv_bf16": [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "es3_dsconv_res_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "es3_bilinear_nhwc_to_nchw": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "es3_nhwc_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],
+    "es3_nchw_f32_to_nhwc": [_vp, _vp, _i, _i, _i, _vp],
+    "es3_litemla_aggreg": [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp],
+    "es3_litemla_attn": [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _f, _vp],
+}
+
+_lib = None
+
+
+class Es3Error(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load libes3.so, building it in-tree first if it is absent (nvcc needs no GPU)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if not build_if_missing:
+            raise Es3Error(f"{LIB_PATH} not built; run `python -m efficientsam3_b200.build`")
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(str(LIB_PATH))
+    lib.es3_last_error.restype = C.c_char_p
+    lib.es3_last_error.argtypes = []
+    lib.es3_version.restype = _i
+    lib.es3_version.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+        fn.restype = _i
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().es3_last_error().decode("utf-8", "replace")
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise Es3Error(f"{name} failed ({rc}): {last_error()}")
+
+
+_inited: dict[int, tuple[int, int, int]] = {}
+
+
+def init(device: int = 0) -> tuple[int, int, int]:
+    """Validate the device (CC 10.x required).  Returns (sm_count, cc_major, cc_minor)."""
+    if device in _inited:
+        return _inited[device]
+    sm, ma, mi = _i(0), _i(0), _i(0)
+    call("es3_init", device, C.byref(sm), C.byref(ma), C.byref(mi))
+    _inited[device] = (sm.value, ma.value, mi.value)
+    return _inited[device]

@@ -1,0 +1,93 @@
+// Shared device/host helpers for the es3 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------ error state
+// Every C-ABI export returns 0 on success; the message is read through es3_last_error().
+namespace es3 {
+void set_error(const char* fmt, ...);
+int cuda_status(cudaError_t e, const char* what);
+}  // namespace es3
+
+#define ES3_CHECK_CUDA(expr)                                   \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return es3::cuda_status(_e, #expr); \
+  } while (0)
+
+#define ES3_REQUIRE(cond, ...)     \
+  do {                             \
+    if (!(cond)) {                 \
+      es3::set_error(__VA_ARGS__); \
+      return 1;                    \
+    }                              \
+  } while (0)
+
+#define ES3_LAUNCH_CHECK(name)                                 \
+  do {                                                         \
+    cudaError_t _e = cudaGetLastError();                       \
+    if (_e != cudaSuccess) return es3::cuda_status(_e, name);  \
+  } while (0)
+
+// ------------------------------------------------------------------------------------ activations
+// Codes shared with the Python side (efficientsam3_b200/ops.py).
+enum Es3Act { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_GELU = 3, ACT_GELU_TANH = 4, ACT_RELU6 = 5, ACT_SIGMOID = 6 };
+
+__device__ __forceinline__ float es3_act(float x, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(x, 0.f);
+    case ACT_HSWISH: return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    case ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    case ACT_GELU_TANH: {
+      float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+      return 0.5f * x * (1.f + tanhf(u));
+    }
+    case ACT_RELU6: return fminf(fmaxf(x, 0.f), 6.f);
+    case ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+    default: return x;
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ float es3_act_t(float x) { return es3_act(x, ACT); }
+
+// ------------------------------------------------------------------------------------ bf16 packing
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+// 8 bf16 (one 16-byte vector) <-> 8 floats
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,374 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a with a fused per-channel epilogue.
+//
+//   out[m, n] = act(scale[n] * sum_k A[m, k] * W[n, k] + bias[n]) (+ residual[m, n])
+//
+// A: bf16 activations, K contiguous (NHWC pixels x channels, or tokens x features)
+// W: bf16 weights [N][K], K contiguous (nn.Linear / 1x1 nn.Conv2d weight layout)
+// accumulation: fp32 in tensor memory; out: bf16 or fp32.
+//
+// This one kernel serves every dense contraction on the hot path:
+//   * pointwise (1x1) convs of EfficientViT / RepViT / TinyViT MBConv + the student head
+//     (reference: efficientvit/nn/ops.py:39-80 ConvLayer with kernel_size=1, stage1/model.py:194-199)
+//   * nn.Linear of the ViT teacher / TinyViT / TwoWayTransformer (vitdet.py:466-515, timm Mlp)
+//   * dense 3x3 conv as an implicit GEMM (head.3: stage1/model.py:198; FPN neck necks.py) -- the A tile
+//     of tap (dy, dx) is a 4-D TMA box at coordinate (c, w0+dx-1, h0+dy-1, b); TMA zero-fills the halo.
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor into a STAGES-deep 128B-swizzled smem ring
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16)
+//   warps 2-5: epilogue       -- tcgen05.ld 32x32b -> registers -> scale/bias/act/residual -> global
+// Pipelines: full[s]/empty[s] mbarriers (TMA <-> MMA), tmem_full (MMA -> epilogue).
+#include "ptx.cuh"
+
+namespace es3 {
+
+struct GemmArgs {
+  int M, N;
+  int num_kb;      // total K iterations (64 elements each); conv: 9 * kb_per_tap
+  int kb_per_tap;  // conv: C / 64 rounded up
+  int tiles_n;
+  int conv;  // 0: plain [M,K] A map (2-D); 1: 3x3 implicit GEMM, A map is 4-D (C, W, H, B)
+  int H, W, TW, TH, tiles_w, tiles_h;
+  int Ctap;  // conv: channels per tap (K offset of tap t in W is t * Ctap)
+  const float* scale;
+  const float* bias;
+  int act;
+  const bf16* residual;
+  long long ldr;
+  void* out;
+  long long ldo;
+  int out_f32;
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_holder;
+  __shared__ float s_scale[BN];
+  __shared__ float s_bias[BN];
+
+  using L = GemmSmem<BN, STAGES>;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_tile = blockIdx.x % args.tiles_n;
+  const int m_tile = blockIdx.x / args.tiles_n;
+  const int n0 = n_tile * BN;
+
+  // conv tile decomposition
+  int img = 0, h0 = 0, w0 = 0;
+  if (args.conv) {
+    const int per_img = args.tiles_w * args.tiles_h;
+    img = m_tile / per_img;
+    const int t = m_tile % per_img;
+    h0 = (t / args.tiles_w) * args.TH;
+    w0 = (t % args.tiles_w) * args.TW;
+  }
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(&tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(&tmem_base_holder, BN);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < args.num_kb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+        if (args.conv) {
+          const int tap = kb / args.kb_per_tap;
+          const int kc = kb - tap * args.kb_per_tap;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          ptx::tma_load_4d(&tmA, &full_bar[stage], sa, kc * BK, w0 + dx, h0 + dy, img);
+          ptx::tma_load_2d(&tmB, &full_bar[stage], sb, tap * args.Ctap + kc * BK, n0);
+        } else {
+          ptx::tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_tile * BM);
+          ptx::tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < args.num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint32_t sb = sa + L::A_BYTES;
+        const uint64_t da = ptx::make_desc_sw128(sa);
+        const uint64_t db = ptx::make_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the >>4 address field
+          ptx::umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      ptx::umma_commit(&tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int et = threadIdx.x - 64;  // 0..127
+    for (int i = et; i < BN; i += 128) {
+      const int n = n0 + i;
+      s_scale[i] = (args.scale != nullptr && n < args.N) ? args.scale[n] : 1.f;
+      s_bias[i] = (args.bias != nullptr && n < args.N) ? args.bias[n] : 0.f;
+    }
+    // named barrier among the 128 epilogue threads only
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;     // row inside the tile
+    bool valid;
+    long long row_off;
+    if (args.conv) {
+      const int dy = r / args.TW, dx = r - dy * args.TW;
+      const int h = h0 + dy, w = w0 + dx;
+      valid = (h < args.H) && (w < args.W);
+      row_off = ((long long)img * args.H + h) * args.W + w;
+    } else {
+      const long long m = (long long)m_tile * BM + r;
+      valid = m < args.M;
+      row_off = m;
+    }
+
+    ptx::mbar_wait(&tmem_full_bar, 0);
+    ptx::tc_fence_after();
+
+    const int act = args.act;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      ptx::tmem_ld_wait();
+      const int nb = n0 + c * 32;
+      if (valid && nb < args.N) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = es3_act(__uint_as_float(v[j]) * s_scale[c * 32 + j] + s_bias[c * 32 + j], act);
+        if (args.residual != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(args.residual + row_off * args.ldr + nb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float rf[8];
+            unpack8(__ldg(rp + j), rf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[j * 8 + e] += rf[e];
+          }
+        }
+        if (args.out_f32) {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + row_off * args.ldo + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(args.out) + row_off * args.ldo + nb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) op[j] = pack8(f + 8 * j);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// rank-N bf16 tensor map, 128B swizzle, zero OOB fill. dims/strides innermost first; strides in BYTES for dims 1..
+static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                      const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return 1;
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_b[i];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,..] box=[%u,%u,..]", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
+    return 1;
+  }
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int tiles_m,
+                  cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        L::TOTAL));
+    configured = true;
+  }
+  dim3 grid((unsigned)(tiles_m * args.tiles_n));
+  gemm_tc_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, args);
+  ES3_LAUNCH_CHECK("gemm_tc_kernel");
+  return 0;
+}
+
+static int pick_bn(int N, int bn_hint) {
+  if (bn_hint == 32 || bn_hint == 64 || bn_hint == 128 || bn_hint == 256) return bn_hint;
+  if (N % 256 == 0 && N >= 512) return 256;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  return 32;
+}
+
+static int dispatch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int tiles_m,
+                    cudaStream_t stream) {
+  switch (bn) {
+    case 256: return launch<256, 4>(tmA, tmB, args, tiles_m, stream);
+    case 128: return launch<128, 3>(tmA, tmB, args, tiles_m, stream);
+    case 64: return launch<64, 4>(tmA, tmB, args, tiles_m, stream);
+    default: return launch<32, 4>(tmA, tmB, args, tiles_m, stream);
+  }
+}
+
+}  // namespace es3
+
+using namespace es3;
+
+extern "C" int es3_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
+                             int out_f32, int M, int N, int K, const float* scale, const float* bias, int act,
+                             const void* residual, long long ldr, int bn_hint, void* stream) {
+  ES3_REQUIRE(M > 0 && N > 0 && K > 0, "es3_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+  ES3_REQUIRE(N % 32 == 0, "es3_gemm_bf16: N=%d must be a multiple of 32", N);
+  ES3_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "es3_gemm_bf16: K/lda/ldw must be multiples of 8 (16-byte TMA strides)");
+  ES3_REQUIRE(ldo % 8 == 0 && (residual == nullptr || ldr % 8 == 0), "es3_gemm_bf16: ldo/ldr must be multiples of 8");
+  ES3_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
+              "es3_gemm_bf16: pointers must be 16-byte aligned");
+  const int bn = pick_bn(N, bn_hint);
+  ES3_REQUIRE(N % bn == 0, "es3_gemm_bf16: N=%d not a multiple of tile %d", N, bn);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+    if (encode_map(&tmA, A, 2, dims, str, box)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)bn};
+    if (encode_map(&tmB, W, 2, dims, str, box)) return 1;
+  }
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M; a.N = N;
+  a.num_kb = ceil_div(K, BK);
+  a.kb_per_tap = a.num_kb;
+  a.tiles_n = N / bn;
+  a.conv = 0;
+  a.scale = scale; a.bias = bias; a.act = act;
+  a.residual = (const bf16*)residual; a.ldr = ldr;
+  a.out = out; a.ldo = ldo; a.out_f32 = out_f32;
+  return dispatch(bn, tmA, tmB, a, ceil_div(M, BM), (cudaStream_t)stream);
+}
+
+// Dense 3x3, stride 1, pad 1 conv on NHWC bf16 as an implicit GEMM.  x: [B,H,Wd,C]; W: [N][9*C] with
+// k = (ky*3+kx)*C + c (repacked from the nn.Conv2d [N,C,3,3] weight by the Python side); out: [B,H,Wd,N].
+extern "C" int es3_conv3x3_bf16(const void* x, const void* W, void* out, int out_f32, int B, int H, int Wd, int C,
+                                int N, const float* scale, const float* bias, int act, const void* residual,
+                                int bn_hint, void* stream) {
+  ES3_REQUIRE(B > 0 && H > 0 && Wd > 0, "es3_conv3x3_bf16: bad shape");
+  ES3_REQUIRE(C % 8 == 0 && N % 32 == 0, "es3_conv3x3_bf16: need C %% 8 == 0 and N %% 32 == 0 (C=%d N=%d)", C, N);
+  const int bn = pick_bn(N, bn_hint);
+  ES3_REQUIRE(N % bn == 0, "es3_conv3x3_bf16: N=%d not a multiple of tile %d", N, bn);
+  int TW = 8;
+  if (Wd % 32 == 0) TW = 32; else if (Wd % 16 == 0) TW = 16;
+  const int TH = BM / TW;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wd, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)Wd * C * 2, (uint64_t)H * Wd * C * 2};
+    uint32_t box[4] = {(uint32_t)BK, (uint32_t)TW, (uint32_t)TH, 1u};
+    if (encode_map(&tmA, x, 4, dims, str, box)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)9 * C, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)9 * C * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)bn};
+    if (encode_map(&tmB, W, 2, dims, str, box)) return 1;
+  }
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = B * H * Wd; a.N = N;
+  a.kb_per_tap = ceil_div(C, BK);
+  a.num_kb = 9 * a.kb_per_tap;
+  a.tiles_n = N / bn;
+  a.conv = 1;
+  a.H = H; a.W = Wd; a.TW = TW; a.TH = TH;
+  a.tiles_w = ceil_div(Wd, TW); a.tiles_h = ceil_div(H, TH);
+  a.Ctap = C;
+  a.scale = scale; a.bias = bias; a.act = act;
+  a.residual = (const bf16*)residual; a.ldr = N;
+  a.out = out; a.ldo = N; a.out_f32 = out_f32;
+  // NOTE: when C is not a multiple of 64 the last K block of a tap would read the next tap's weights
+  // from W; the A side is zero-filled by TMA (channel coordinate beyond C), so the product is still 0.
+  return dispatch(bn, tmA, tmB, a, B * a.tiles_w * a.tiles_h, (cudaStream_t)stream);
+}

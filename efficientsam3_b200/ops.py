@@ -1,0 +1,175 @@
+"""Tensor-level wrappers over the C ABI.  torch is used for device memory and streams only.
+
+Activations are channels-last bf16 2-D/4-D tensors on a CUDA device; every wrapper validates device /
+dtype / contiguity and raises (no CPU fallback -- a CPU tensor is an error).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+ACT = {None: 0, "none": 0, "relu": 1, "hswish": 2, "gelu": 3, "gelu_tanh": 4, "relu6": 5, "sigmoid": 6}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _lib.Es3Error(f"{name}: expected a CUDA tensor (the native path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.Es3Error(f"{name}: expected {dtype}, got {t.dtype}")
+    return t
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _ensure_init(t: torch.Tensor):
+    _lib.init(t.device.index or 0)
+
+
+def gemm(a, w, *, scale=None, bias=None, act=None, residual=None, out=None, out_dtype=torch.bfloat16, bn_hint=0):
+    """out[m,n] = act(scale[n]*sum_k a[m,k] w[n,k] + bias[n]) (+residual).  a: [M,K] (row stride allowed),
+    w: [N,K] bf16, scale/bias fp32 [N]."""
+    _chk(a, torch.bfloat16, "a"); _chk(w, torch.bfloat16, "w")
+    _ensure_init(a)
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, (a.shape, w.shape)
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    assert out.stride(1) == 1 and out.shape == (M, N)
+    if residual is not None:
+        _chk(residual, torch.bfloat16, "residual")
+        assert residual.stride(1) == 1 and residual.shape == (M, N)
+    _lib.call("es3_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
+              int(out.dtype == torch.float32), M, N, K, _ptr(scale), _ptr(bias), ACT[act], _ptr(residual),
+              residual.stride(0) if residual is not None else 0, bn_hint, _stream())
+    return out
+
+
+def gemm_simt(a, w, *, scale=None, bias=None, act=None, residual=None, out=None, out_dtype=torch.bfloat16):
+    _ensure_init(a)
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    res_f32 = int(residual is not None and residual.dtype == torch.float32)
+    _lib.call("es3_gemm_simt", a.data_ptr(), a.stride(0), int(a.dtype == torch.float32), w.data_ptr(), w.stride(0),
+              int(w.dtype == torch.float32), out.data_ptr(), out.stride(0), int(out.dtype == torch.float32), M, N, K,
+              _ptr(scale), _ptr(bias), ACT[act], _ptr(residual), residual.stride(0) if residual is not None else 0,
+              res_f32, _stream())
+    return out
+
+
+def conv3x3(x, w9, *, scale=None, bias=None, act=None, residual=None, out_dtype=torch.bfloat16, bn_hint=0):
+    """x: [B,H,W,C] bf16 NHWC contiguous; w9: [N, 9*C] bf16 (tap-major k)."""
+    _chk(x, torch.bfloat16, "x"); _chk(w9, torch.bfloat16, "w9")
+    _ensure_init(x)
+    assert x.is_contiguous() and w9.is_contiguous()
+    B, H, W, Cc = x.shape
+    N = w9.shape[0]
+    assert w9.shape[1] == 9 * Cc
+    out = torch.empty((B, H, W, N), device=x.device, dtype=out_dtype)
+    _lib.call("es3_conv3x3_bf16", x.data_ptr(), w9.data_ptr(), out.data_ptr(), int(out_dtype == torch.float32),
+              B, H, W, Cc, N, _ptr(scale), _ptr(bias), ACT[act], _ptr(residual), bn_hint, _stream())
+    return out
+
+
+def stem_conv3x3_s2(x, w27, bias, act):
+    """x: [B,3,H,W] fp32 NCHW -> [B,Ho,Wo,Cout] bf16 NHWC.  w27: [27,Cout] fp32."""
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    x = x.contiguous()
+    B, _, H, W = x.shape
+    Cout = w27.shape[1]
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
+    _lib.call("es3_stem_conv3x3_s2", x.data_ptr(), w27.data_ptr(), _ptr(bias), out.data_ptr(), B, H, W, Cout,
+              ACT[act], _stream())
+    return out
+
+
+def dwconv(x, w, bias, ks, stride, act, out=None):
+    """x: [B,H,W,C] bf16 (channel-sliced views allowed); w: [ks*ks, C] fp32."""
+    _chk(x, torch.bfloat16, "x")
+    _ensure_init(x)
+    B, H, W, Cc = x.shape
+    assert x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1)
+    pad = ks // 2
+    Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cc), device=x.device, dtype=torch.bfloat16)
+    _lib.call("es3_dwconv_bf16", x.data_ptr(), x.stride(2), w.data_ptr(), _ptr(bias), out.data_ptr(), out.stride(2),
+              B, H, W, Cc, ks, stride, ACT[act], _stream())
+    return out
+
+
+def dsconv_res(x, wdw, bdw, wpw, bpw, act):
+    _chk(x, torch.bfloat16, "x")
+    _ensure_init(x)
+    assert x.is_contiguous()
+    B, H, W, Cc = x.shape
+    out = torch.empty_like(x)
+    _lib.call("es3_dsconv_res_bf16", x.data_ptr(), wdw.data_ptr(), _ptr(bdw), wpw.data_ptr(), _ptr(bpw),
+              out.data_ptr(), B, H, W, Cc, ACT[act], _stream())
+    return out
+
+
+def bilinear_nhwc_to_nchw(x, Ho, Wo):
+    _chk(x, torch.bfloat16, "x")
+    _ensure_init(x)
+    assert x.is_contiguous()
+    B, Hi, Wi, Cc = x.shape
+    out = torch.empty((B, Cc, Ho, Wo), device=x.device, dtype=torch.float32)
+    _lib.call("es3_bilinear_nhwc_to_nchw", x.data_ptr(), out.data_ptr(), B, Hi, Wi, Cc, Ho, Wo, _stream())
+    return out
+
+
+def nhwc_to_nchw_f32(x):
+    _chk(x, torch.bfloat16, "x")
+    _ensure_init(x)
+    assert x.is_contiguous()
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, Cc, H, W), device=x.device, dtype=torch.float32)
+    _lib.call("es3_nhwc_to_nchw_f32", x.data_ptr(), out.data_ptr(), B, H * W, Cc, _stream())
+    return out
+
+
+def nchw_f32_to_nhwc(x):
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    x = x.contiguous()
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, H, W, Cc), device=x.device, dtype=torch.bfloat16)
+    _lib.call("es3_nchw_f32_to_nhwc", x.data_ptr(), out.data_ptr(), B, H * W, Cc, _stream())
+    return out
+
+
+def litemla_aggreg(ms, wdw, wpw, C3):
+    """ms: [B,H,W,2*C3] bf16; fills channels [C3, 2*C3) in place."""
+    _chk(ms, torch.bfloat16, "ms")
+    _ensure_init(ms)
+    assert ms.is_contiguous()
+    B, H, W, ld = ms.shape
+    _lib.call("es3_litemla_aggreg", ms.data_ptr(), ld, wdw.data_ptr(), wpw.data_ptr(), B, H, W, C3, _stream())
+    return ms
+
+
+def litemla_attn(ms, heads2, eps=1e-15):
+    """ms: [B,H,W,48*heads2] bf16 -> att [B,H,W,16*heads2] bf16."""
+    _chk(ms, torch.bfloat16, "ms")
+    _ensure_init(ms)
+    assert ms.is_contiguous()
+    B, H, W, ld = ms.shape
+    att = torch.empty((B, H, W, 16 * heads2), device=ms.device, dtype=torch.bfloat16)
+    kv = torch.empty((B, heads2, 17, 16), device=ms.device, dtype=torch.float32)
+    _lib.call("es3_litemla_attn", ms.data_ptr(), ld, kv.data_ptr(), att.data_ptr(), att.shape[3], B, H * W, heads2,
+              float(eps), _stream())
+    return att

@@ -1,0 +1,86 @@
+/* es3.h -- C ABI of libes3.so: hand-written sm_100a kernels for the EfficientSAM3 hot path.
+ *
+ * The reference (SimonZeng7108/efficientsam3) has no FFI of its own: its hot path bottoms out in
+ * torch.nn.functional calls.  Each entry point below therefore names the reference
+ * Python call site whose device work it replaces; the Python module shells in efficientsam3_b200/
+ * (same class names / state_dict keys as the reference) are the only callers.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; es3_last_error() gives the message
+ *     (thread-local).  There is no CPU fallback: non-Blackwell devices fail in es3_init().
+ *   - all pointers are DEVICE pointers unless stated; `stream` is a cudaStream_t passed as void*.
+ *   - activations are NHWC (pixels x channels) / tokens x features, bf16, 16-byte aligned; `ld*` are
+ *     row strides in ELEMENTS.  fp32 vectors (scale / bias / folded BN) are per output channel.
+ *   - act codes: 0 none, 1 relu, 2 hardswish, 3 gelu(erf), 4 gelu(tanh), 5 relu6, 6 sigmoid.
+ */
+#ifndef ES3_H_
+#define ES3_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ runtime */
+const char* es3_last_error(void);
+int es3_version(void);
+/* Queries `device`; fails unless it is compute capability 10.x. */
+int es3_init(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------ GEMMs */
+/* out[m,n] = act(scale[n] * sum_k A[m,k] W[n,k] + bias[n]) (+ residual[m,n]);  tcgen05 + TMEM + TMA.
+ * Replaces nn.Conv2d(k=1)+BatchNorm2d+act of ConvLayer (sam3/sam3/backbones/efficientvit/nn/ops.py:39-80),
+ * the student head 1x1 (stage1/model.py:194-197) and every nn.Linear on the path (vitdet.py:466-515,
+ * sam/transformer.py:185-264).  N % 32 == 0, K % 8 == 0; bn_hint in {0 (auto), 32, 64, 128, 256}. */
+int es3_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_f32,
+                  int M, int N, int K, const float* scale, const float* bias, int act, const void* residual,
+                  long long ldr, int bn_hint, void* stream);
+
+/* Dense 3x3 / stride 1 / pad 1 conv as an implicit tcgen05 GEMM (halo via TMA zero fill).
+ * x [B,H,W,C] bf16 NHWC; W [N][9*C] with k = (ky*3+kx)*C + c; out [B,H,W,N].
+ * Replaces head.3 = nn.Conv2d(1024,1024,3,padding=1) (stage1/model.py:198) and the FPN 3x3s (necks.py). */
+int es3_conv3x3_bf16(const void* x, const void* W, void* out, int out_f32, int B, int H, int Wd, int C, int N,
+                     const float* scale, const float* bias, int act, const void* residual, int bn_hint, void* stream);
+
+/* CUDA-core GEMM, same epilogue; for tiny M (decoder tokens, SE MLPs) and as the on-device cross-check
+ * of the tensor-core kernel.  a_f32 / w_f32 / res_f32 select fp32 (1) or bf16 (0) operands. */
+int es3_gemm_simt(const void* A, long long lda, int a_f32, const void* W, long long ldw, int w_f32, void* out,
+                  long long ldo, int out_f32, int M, int N, int K, const float* scale, const float* bias, int act,
+                  const void* residual, long long ldr, int res_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------------ convs */
+/* 3x3 stride-2 pad-1 conv from the NCHW fp32 image to NHWC bf16, folded BN + act.
+ * w [27][Cout] fp32 tap-major ((ci*9+ky*3+kx)), Cout in {8,16,24,32}.
+ * Replaces EfficientViT input_stem op 0 (efficientvit/backbone.py:49-57). */
+int es3_stem_conv3x3_s2(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int Cout,
+                        int act, void* stream);
+
+/* Depthwise ks x ks (3|5), stride 1|2, pad ks/2.  w [ks*ks][C] fp32 tap-major (BN scale folded), bias [C]|NULL.
+ * Replaces ConvLayer(groups=C) in DSConv / MBConv (efficientvit/nn/ops.py:273-367). */
+int es3_dwconv_bf16(const void* x, long long ldx, const float* w, const float* bias, void* out, long long ldo, int B,
+                    int H, int W, int C, int ks, int stride, int act, void* stream);
+
+/* y = x + BN(pw(act(BN(dw3x3(x))))) in one pass; C in {8,16,24,32}.
+ * Replaces the stem ResidualBlock(DSConv) (efficientvit/backbone.py:58-67). */
+int es3_dsconv_res_bf16(const void* x, const float* wdw, const float* bdw, const float* wpw, const float* bpw,
+                        void* out, int B, int H, int W, int C, int act, void* stream);
+
+/* Bilinear (align_corners=False) NHWC bf16 -> NCHW fp32.  Replaces F.interpolate at stage1/model.py:204-210. */
+int es3_bilinear_nhwc_to_nchw(const void* in, float* out, int B, int Hi, int Wi, int C, int Ho, int Wo, void* stream);
+/* Layout conversions at the module boundary. */
+int es3_nhwc_to_nchw_f32(const void* in, float* out, int B, int HW, int C, void* stream);
+int es3_nchw_f32_to_nhwc(const float* in, void* out, int B, int HW, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------ LiteMLA */
+/* ms [B,H,W,ld] bf16: reads qkv in channels [0,C3), writes aggreg(qkv) = grouped1x1(dw5x5(qkv)) into
+ * channels [C3,2*C3).  wdw [25][C3] fp32, wpw [C3][16] fp32.  Replaces LiteMLA.aggreg (ops.py:560-575,655-660). */
+int es3_litemla_aggreg(void* ms, long long ld, const float* wdw, const float* wpw, int B, int H, int W, int C3,
+                       void* stream);
+/* ReLU linear attention over the multi-scale qkv buffer (head h = channels [48h,48h+48) = q|k|v, dim 16).
+ * kv_ws: B*heads2*17*16 floats of scratch.  att [B,HW,ldo] bf16.  Replaces relu_linear_att (ops.py:584-621). */
+int es3_litemla_attn(const void* ms, long long ld, float* kv_ws, void* att, long long ldo, int B, int HW, int heads2,
+                     float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ES3_H_ */

@@ -1,0 +1,190 @@
+"""Kernel-level numerics: every C-ABI op against a plain PyTorch fp32 statement of the same op.
+
+Inputs are rounded to bf16 first so the comparison isolates the kernel's arithmetic (fp32 accumulation,
+bf16 output rounding) from input quantisation.  Tolerances: outputs are bf16 (rel. step 2^-8), so
+atol/rtol = 1e-2 relative to the tensor's scale; fp32 outputs use 2e-3 (fp32 accumulation-order noise
+on bf16 products).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def _close(got, ref, tol, what=""):
+    got = got.float()
+    scale = ref.abs().max().item() + 1e-12
+    err = (got - ref).abs().max().item() / scale
+    assert err <= tol, f"{what}: max err / scale = {err:.3e} > {tol}"
+
+
+def _act(x, act):
+    if act is None:
+        return x
+    return {"relu": F.relu, "hswish": F.hardswish, "gelu": F.gelu, "gelu_tanh": lambda v: F.gelu(v, approximate="tanh"),
+            "relu6": F.relu6, "sigmoid": torch.sigmoid}[act](x)
+
+
+GEMM_CASES = [
+    # M, N, K, act, residual, out_f32, bn_hint
+    (128, 32, 64, None, False, False, 0),
+    (256, 64, 16, "hswish", False, False, 0),
+    (300, 128, 128, "gelu", True, False, 0),
+    (1000, 256, 256, None, True, False, 0),
+    (127, 1024, 256, "gelu", False, False, 0),
+    (5184, 1024, 1024, None, True, True, 256),
+    (640, 3072, 1024, None, False, False, 256),
+    (513, 4736, 1024, "gelu", False, False, 128),
+    (384, 1024, 4736, None, True, False, 0),
+    (3969, 384, 128, None, False, False, 0),
+    (2048, 512, 128, "hswish", False, False, 64),
+    (2048, 128, 512, None, True, False, 32),
+]
+
+
+@pytest.mark.parametrize("M,N,K,act,res,out_f32,bn", GEMM_CASES)
+def test_gemm_tc(cuda, M, N, K, act, res, out_f32, bn):
+    from efficientsam3_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = _bf(torch.randn(M, K, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda)
+    scale = (torch.rand(N, generator=g) + 0.5).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    r = _bf(torch.randn(M, N, generator=g)).to(cuda) if res else None
+    out = ops.gemm(a, w, scale=scale, bias=bias, act=act, residual=r,
+                   out_dtype=torch.float32 if out_f32 else torch.bfloat16, bn_hint=bn)
+    ref = _act((a.float() @ w.float().t()) * scale + bias, act)
+    if res:
+        ref = ref + r.float()
+    _close(out, ref, 2e-3 if out_f32 else 1e-2, f"gemm {M}x{N}x{K}")
+    # independent on-device cross-check with the CUDA-core kernel
+    out2 = ops.gemm_simt(a, w, scale=scale, bias=bias, act=act, residual=r, out_dtype=torch.float32)
+    _close(out2, ref, 2e-3, "gemm_simt")
+
+
+def test_gemm_strided_views(cuda):
+    """A is a channel slice of a wider buffer; out is written into a slice (the LiteMLA qkv layout)."""
+    from efficientsam3_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    big = _bf(torch.randn(777, 256, generator=g)).to(cuda)
+    a = big[:, 64:192]
+    w = _bf(torch.randn(384, 128, generator=g) / 11).to(cuda)
+    outbuf = torch.zeros(777, 768, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(a, w, out=outbuf[:, :384])
+    ref = a.float() @ w.float().t()
+    _close(outbuf[:, :384], ref, 1e-2, "strided gemm")
+    assert outbuf[:, 384:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 32, 32, 1024, 1024), (1, 8, 8, 64, 32), (2, 17, 23, 128, 64), (1, 72, 72, 256, 256)])
+def test_conv3x3(cuda, B, H, W, C, N):
+    from efficientsam3_b200 import ops
+    g = torch.Generator().manual_seed(B + H + C)
+    x = _bf(torch.randn(B, H, W, C, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, C, 3, 3, generator=g) / math.sqrt(9 * C)).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    w9 = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = ops.conv3x3(x, w9, bias=bias)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    _close(out, ref, 1e-2, "conv3x3")
+
+
+@pytest.mark.parametrize("H,W,Cout", [(64, 64, 16), (63, 65, 32)])
+def test_stem(cuda, H, W, Cout):
+    from efficientsam3_b200 import ops
+    g = torch.Generator().manual_seed(H)
+    x = torch.randn(2, 3, H, W, generator=g).to(cuda)
+    w = (torch.randn(Cout, 3, 3, 3, generator=g) / 5).to(cuda)
+    b = torch.randn(Cout, generator=g).to(cuda)
+    w27 = w.reshape(Cout, 27).t().contiguous()
+    out = ops.stem_conv3x3_s2(x, w27, b, "hswish")
+    ref = F.hardswish(F.conv2d(x, w, b, stride=2, padding=1)).permute(0, 2, 3, 1)
+    _close(out, ref, 1e-2, "stem")
+
+
+@pytest.mark.parametrize("ks,stride,H,W,C", [(3, 1, 20, 20, 64), (3, 2, 21, 19, 32), (5, 1, 16, 16, 48), (3, 2, 63, 63, 512)])
+def test_dwconv(cuda, ks, stride, H, W, C):
+    from efficientsam3_b200 import ops
+    g = torch.Generator().manual_seed(ks * 10 + stride)
+    x = _bf(torch.randn(2, H, W, C, generator=g)).to(cuda)
+    w = (torch.randn(C, 1, ks, ks, generator=g) / ks).to(cuda)
+    b = torch.randn(C, generator=g).to(cuda)
+    wt = w.reshape(C, ks * ks).t().contiguous()
+    out = ops.dwconv(x, wt, b, ks, stride, "hswish")
+    ref = F.hardswish(F.conv2d(x.float().permute(0, 3, 1, 2), w, b, stride=stride, padding=ks // 2, groups=C)).permute(0, 2, 3, 1)
+    _close(out, ref, 1e-2, "dwconv")
+
+
+def test_dsconv_res(cuda):
+    from efficientsam3_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    C = 16
+    x = _bf(torch.randn(2, 30, 34, C, generator=g)).to(cuda)
+    wdw = (torch.randn(C, 1, 3, 3, generator=g) / 3).to(cuda)
+    bdw = torch.randn(C, generator=g).to(cuda)
+    wpw = (torch.randn(C, C, generator=g) / 4).to(cuda)
+    bpw = torch.randn(C, generator=g).to(cuda)
+    out = ops.dsconv_res(x, wdw.reshape(C, 9).t().contiguous(), bdw, wpw.contiguous(), bpw, "hswish")
+    xn = x.float().permute(0, 3, 1, 2)
+    mid = F.hardswish(F.conv2d(xn, wdw, bdw, padding=1, groups=C)).to(torch.bfloat16).float()
+    ref = (F.conv2d(mid, wpw[:, :, None, None], bpw) + xn).permute(0, 2, 3, 1)
+    _close(out, ref, 1e-2, "dsconv_res")
+
+
+@pytest.mark.parametrize("Hi,Wi,Ho,Wo", [(32, 32, 72, 72), (32, 32, 64, 64), (8, 8, 18, 18), (16, 16, 16, 16)])
+def test_bilinear(cuda, Hi, Wi, Ho, Wo):
+    from efficientsam3_b200 import ops
+    x = _bf(torch.randn(2, Hi, Wi, 128, generator=torch.Generator().manual_seed(1))).to(cuda)
+    out = ops.bilinear_nhwc_to_nchw(x, Ho, Wo)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=False)
+    _close(out, ref, 1e-5, "bilinear")
+
+
+def test_layout_roundtrip(cuda):
+    from efficientsam3_b200 import ops
+    x = torch.randn(2, 48, 9, 11, device=cuda)
+    y = ops.nchw_f32_to_nhwc(x)
+    assert torch.equal(y, x.permute(0, 2, 3, 1).to(torch.bfloat16))
+    z = ops.nhwc_to_nchw_f32(y)
+    assert torch.equal(z, x.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("H,W,heads,B", [(32, 32, 16, 2), (63, 63, 8, 1)])
+def test_litemla(cuda, H, W, heads, B):
+    """aggreg + ReLU linear attention vs the textbook formulation (efficientvit/nn/ops.py:584-621)."""
+    from efficientsam3_b200 import ops
+    dim = 16
+    td = heads * dim
+    C3 = 3 * td
+    g = torch.Generator().manual_seed(H)
+    qkv = _bf(torch.randn(B, H, W, C3, generator=g)).to(cuda)
+    wdw = (torch.randn(C3, 1, 5, 5, generator=g) / 5).to(cuda)
+    wpw = (torch.randn(C3, 16, 1, 1, generator=g) / 4).to(cuda)
+    ms = torch.zeros(B, H, W, 2 * C3, device=cuda, dtype=torch.bfloat16)
+    ms[..., :C3] = qkv
+    ops.litemla_aggreg(ms, wdw.reshape(C3, 25).t().contiguous(), wpw.reshape(C3, 16).contiguous(), C3)
+    x = qkv.float().permute(0, 3, 1, 2)
+    dw = F.conv2d(x, wdw, padding=2, groups=C3).to(torch.bfloat16).float()
+    agg = F.conv2d(dw, wpw, groups=3 * heads)
+    _close(ms[..., C3:], agg.permute(0, 2, 3, 1), 1e-2, "aggreg")
+    att = ops.litemla_attn(ms, 2 * heads)
+    full = ms.float().permute(0, 3, 1, 2).reshape(B, -1, 3 * dim, H * W)
+    q, k, v = F.relu(full[:, :, :dim]), F.relu(full[:, :, dim:2 * dim]), full[:, :, 2 * dim:]
+    v = F.pad(v, (0, 0, 0, 1), value=1.0)
+    out = (v @ k.transpose(-1, -2)) @ q
+    out = out[:, :, :-1] / (out[:, :, -1:] + 1e-15)
+    ref = out.reshape(B, -1, H, W).permute(0, 2, 3, 1)
+    _close(att, ref, 1e-2, "litemla attn")
+
+
+def test_cpu_tensor_is_an_error():
+    from efficientsam3_b200 import _lib, ops
+    with pytest.raises(_lib.Es3Error):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(32, 8, dtype=torch.bfloat16))
