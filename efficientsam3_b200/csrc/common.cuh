@@ -55,8 +55,33 @@ __device__ __forceinline__ float es3_act(float x, int act) {
   }
 }
 
+// Compile-time activation: a runtime `switch` inside an unrolled epilogue costs a BRX per element
+// (measured: 67% of gemm_tc stall samples, profiles/r1_gemm_epilogue_switch.md) -- kernels are
+// templated on ACT and dispatched on the host with ES3_DISPATCH_ACT.
 template <int ACT>
-__device__ __forceinline__ float es3_act_t(float x) { return es3_act(x, ACT); }
+__device__ __forceinline__ float es3_act_t(float x) {
+  if constexpr (ACT == ACT_RELU) return fmaxf(x, 0.f);
+  else if constexpr (ACT == ACT_HSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  else if constexpr (ACT == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+  else if constexpr (ACT == ACT_GELU_TANH) {
+    float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    return 0.5f * x * (1.f + tanhf(u));
+  } else if constexpr (ACT == ACT_RELU6) return fminf(fmaxf(x, 0.f), 6.f);
+  else if constexpr (ACT == ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+  else return x;
+}
+
+#define ES3_DISPATCH_ACT(act, ACT_CONST, ...)                                            \
+  switch (act) {                                                                         \
+    case ACT_NONE: { constexpr int ACT_CONST = ACT_NONE; __VA_ARGS__; } break;           \
+    case ACT_RELU: { constexpr int ACT_CONST = ACT_RELU; __VA_ARGS__; } break;           \
+    case ACT_HSWISH: { constexpr int ACT_CONST = ACT_HSWISH; __VA_ARGS__; } break;       \
+    case ACT_GELU: { constexpr int ACT_CONST = ACT_GELU; __VA_ARGS__; } break;           \
+    case ACT_GELU_TANH: { constexpr int ACT_CONST = ACT_GELU_TANH; __VA_ARGS__; } break; \
+    case ACT_RELU6: { constexpr int ACT_CONST = ACT_RELU6; __VA_ARGS__; } break;         \
+    case ACT_SIGMOID: { constexpr int ACT_CONST = ACT_SIGMOID; __VA_ARGS__; } break;     \
+    default: es3::set_error("unknown activation code %d", act); return 1;                \
+  }
 
 // ------------------------------------------------------------------------------------ bf16 packing
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

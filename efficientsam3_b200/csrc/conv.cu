@@ -13,10 +13,10 @@ namespace es3 {
 // ------------------------------------------------------------------------------------------ stem
 // x: [B,3,H,W] fp32 NCHW.  w: [27][COUT] fp32 (tap-major: (ci*9 + ky*3 + kx), BN scale pre-folded).
 // out: [B,Ho,Wo,COUT] bf16.  One thread per output pixel, COUT accumulators.
-template <int COUT>
+template <int COUT, int ACT>
 __global__ void stem_conv3x3_s2_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                        const float* __restrict__ bias, bf16* __restrict__ out, int B, int H, int W,
-                                       int Ho, int Wo, int act) {
+                                       int Ho, int Wo) {
   __shared__ float sw[27 * COUT];
   __shared__ float sb[COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
@@ -50,7 +50,7 @@ __global__ void stem_conv3x3_s2_kernel(const float* __restrict__ x, const float*
     }
   }
 #pragma unroll
-  for (int c = 0; c < COUT; ++c) acc[c] = es3_act(acc[c], act);
+  for (int c = 0; c < COUT; ++c) acc[c] = es3_act_t<ACT>(acc[c]);
   uint4* op = reinterpret_cast<uint4*>(out + p * COUT);
 #pragma unroll
   for (int j = 0; j < COUT / 8; ++j) op[j] = pack8(acc + 8 * j);
@@ -59,10 +59,10 @@ __global__ void stem_conv3x3_s2_kernel(const float* __restrict__ x, const float*
 // ------------------------------------------------------------------------------------- depthwise
 // x: [B,H,W,C] bf16 (pixel stride ldx elements), w: [KS*KS][C] fp32 (tap-major, BN scale pre-folded),
 // bias: [C] fp32 or null, out: [B,Ho,Wo,C] bf16 (pixel stride ldo).  pad = KS/2.
-template <int KS, int STRIDE>
+template <int KS, int STRIDE, int ACT>
 __global__ void dwconv_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ w,
                               const float* __restrict__ bias, bf16* __restrict__ out, long long ldo, int B, int H,
-                              int W, int C, int Ho, int Wo, int act) {
+                              int W, int C, int Ho, int Wo) {
   const int cg = C >> 3;  // 8-channel groups
   const long long total = (long long)B * Ho * Wo * cg;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,7 +105,7 @@ __global__ void dwconv_kernel(const bf16* __restrict__ x, long long ldx, const f
     }
   }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = es3_act(acc[e], act);
+  for (int e = 0; e < 8; ++e) acc[e] = es3_act_t<ACT>(acc[e]);
   *reinterpret_cast<uint4*>(out + p * ldo + c0) = pack8(acc);
 }
 
@@ -113,10 +113,10 @@ __global__ void dwconv_kernel(const bf16* __restrict__ x, long long ldx, const f
 // EfficientViT stem block (backbone.py:58-67 with expand_ratio=1 -> DSConv, ops.py:273-312):
 //   y = x + BN2(pw(act(BN1(dw3x3(x)))))       C == 16 (b1) / 8 (b0) / 24 (b2) / 32 (b3)
 // One thread per pixel, all C channels in registers; pw weights [C][C] in shared memory.
-template <int C>
+template <int C, int ACT>
 __global__ void dsconv_res_kernel(const bf16* __restrict__ x, const float* __restrict__ wdw /*[9][C]*/,
                                   const float* __restrict__ bdw, const float* __restrict__ wpw /*[Cout][Cin]*/,
-                                  const float* __restrict__ bpw, bf16* __restrict__ out, int B, int H, int W, int act) {
+                                  const float* __restrict__ bpw, bf16* __restrict__ out, int B, int H, int W) {
   __shared__ float s_wdw[9 * C];
   __shared__ float s_wpw[C * C];
   __shared__ float s_bdw[C];
@@ -162,7 +162,7 @@ __global__ void dsconv_res_kernel(const bf16* __restrict__ x, const float* __res
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     // the reference materialises the dw output in the activation dtype; round like the unfused path would
-    mid[c] = __bfloat162float(__float2bfloat16(es3_act(mid[c], act)));
+    mid[c] = __bfloat162float(__float2bfloat16(es3_act_t<ACT>(mid[c])));
   }
   float o[C];
 #pragma unroll
@@ -270,13 +270,15 @@ extern "C" int es3_stem_conv3x3_s2(const float* x, const float* w, const float* 
   const int threads = 128;
   const unsigned blocks = (unsigned)ceil_div(total, threads);
   cudaStream_t st = (cudaStream_t)stream;
-  switch (Cout) {
-    case 8: stem_conv3x3_s2_kernel<8><<<blocks, threads, 0, st>>>(x, w, bias, (bf16*)out, B, H, W, Ho, Wo, act); break;
-    case 16: stem_conv3x3_s2_kernel<16><<<blocks, threads, 0, st>>>(x, w, bias, (bf16*)out, B, H, W, Ho, Wo, act); break;
-    case 24: stem_conv3x3_s2_kernel<24><<<blocks, threads, 0, st>>>(x, w, bias, (bf16*)out, B, H, W, Ho, Wo, act); break;
-    case 32: stem_conv3x3_s2_kernel<32><<<blocks, threads, 0, st>>>(x, w, bias, (bf16*)out, B, H, W, Ho, Wo, act); break;
-    default: ES3_REQUIRE(false, "es3_stem_conv3x3_s2: unsupported Cout=%d (8/16/24/32)", Cout);
-  }
+  ES3_DISPATCH_ACT(act, A, {
+    switch (Cout) {
+      case 8: stem_conv3x3_s2_kernel<8, A><<<blocks, threads, 0, st>>>(x, w, bias, (bf16*)out, B, H, W, Ho, Wo); break;
+      case 16: stem_conv3x3_s2_kernel<16, A><<<blocks, threads, 0, st>>>(x, w, bias, (bf16*)out, B, H, W, Ho, Wo); break;
+      case 24: stem_conv3x3_s2_kernel<24, A><<<blocks, threads, 0, st>>>(x, w, bias, (bf16*)out, B, H, W, Ho, Wo); break;
+      case 32: stem_conv3x3_s2_kernel<32, A><<<blocks, threads, 0, st>>>(x, w, bias, (bf16*)out, B, H, W, Ho, Wo); break;
+      default: ES3_REQUIRE(false, "es3_stem_conv3x3_s2: unsupported Cout=%d (8/16/24/32)", Cout);
+    }
+  })
   ES3_LAUNCH_CHECK("stem_conv3x3_s2_kernel");
   return 0;
 }
@@ -293,10 +295,12 @@ extern "C" int es3_dwconv_bf16(const void* x, long long ldx, const float* w, con
   cudaStream_t st = (cudaStream_t)stream;
   const bf16* xi = (const bf16*)x;
   bf16* o = (bf16*)out;
-  if (ks == 3 && stride == 1) dwconv_kernel<3, 1><<<blocks, threads, 0, st>>>(xi, ldx, w, bias, o, ldo, B, H, W, C, Ho, Wo, act);
-  else if (ks == 3 && stride == 2) dwconv_kernel<3, 2><<<blocks, threads, 0, st>>>(xi, ldx, w, bias, o, ldo, B, H, W, C, Ho, Wo, act);
-  else if (ks == 5 && stride == 1) dwconv_kernel<5, 1><<<blocks, threads, 0, st>>>(xi, ldx, w, bias, o, ldo, B, H, W, C, Ho, Wo, act);
-  else dwconv_kernel<5, 2><<<blocks, threads, 0, st>>>(xi, ldx, w, bias, o, ldo, B, H, W, C, Ho, Wo, act);
+  ES3_DISPATCH_ACT(act, A, {
+    if (ks == 3 && stride == 1) dwconv_kernel<3, 1, A><<<blocks, threads, 0, st>>>(xi, ldx, w, bias, o, ldo, B, H, W, C, Ho, Wo);
+    else if (ks == 3 && stride == 2) dwconv_kernel<3, 2, A><<<blocks, threads, 0, st>>>(xi, ldx, w, bias, o, ldo, B, H, W, C, Ho, Wo);
+    else if (ks == 5 && stride == 1) dwconv_kernel<5, 1, A><<<blocks, threads, 0, st>>>(xi, ldx, w, bias, o, ldo, B, H, W, C, Ho, Wo);
+    else dwconv_kernel<5, 2, A><<<blocks, threads, 0, st>>>(xi, ldx, w, bias, o, ldo, B, H, W, C, Ho, Wo);
+  })
   ES3_LAUNCH_CHECK("dwconv_kernel");
   return 0;
 }
@@ -307,13 +311,15 @@ extern "C" int es3_dsconv_res_bf16(const void* x, const float* wdw, const float*
   const int threads = 128;
   const unsigned blocks = (unsigned)ceil_div(total, threads);
   cudaStream_t st = (cudaStream_t)stream;
-  switch (C) {
-    case 8: dsconv_res_kernel<8><<<blocks, threads, 0, st>>>((const bf16*)x, wdw, bdw, wpw, bpw, (bf16*)out, B, H, W, act); break;
-    case 16: dsconv_res_kernel<16><<<blocks, threads, 0, st>>>((const bf16*)x, wdw, bdw, wpw, bpw, (bf16*)out, B, H, W, act); break;
-    case 24: dsconv_res_kernel<24><<<blocks, threads, 0, st>>>((const bf16*)x, wdw, bdw, wpw, bpw, (bf16*)out, B, H, W, act); break;
-    case 32: dsconv_res_kernel<32><<<blocks, threads, 0, st>>>((const bf16*)x, wdw, bdw, wpw, bpw, (bf16*)out, B, H, W, act); break;
-    default: ES3_REQUIRE(false, "es3_dsconv_res_bf16: unsupported C=%d (8/16/24/32)", C);
-  }
+  ES3_DISPATCH_ACT(act, A, {
+    switch (C) {
+      case 8: dsconv_res_kernel<8, A><<<blocks, threads, 0, st>>>((const bf16*)x, wdw, bdw, wpw, bpw, (bf16*)out, B, H, W); break;
+      case 16: dsconv_res_kernel<16, A><<<blocks, threads, 0, st>>>((const bf16*)x, wdw, bdw, wpw, bpw, (bf16*)out, B, H, W); break;
+      case 24: dsconv_res_kernel<24, A><<<blocks, threads, 0, st>>>((const bf16*)x, wdw, bdw, wpw, bpw, (bf16*)out, B, H, W); break;
+      case 32: dsconv_res_kernel<32, A><<<blocks, threads, 0, st>>>((const bf16*)x, wdw, bdw, wpw, bpw, (bf16*)out, B, H, W); break;
+      default: ES3_REQUIRE(false, "es3_dsconv_res_bf16: unsupported C=%d (8/16/24/32)", C);
+    }
+  })
   ES3_LAUNCH_CHECK("dsconv_res_kernel");
   return 0;
 }

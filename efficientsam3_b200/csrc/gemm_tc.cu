@@ -51,7 +51,7 @@ struct GemmSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int ACT>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_holder;
-  __shared__ float s_scale[BN];
-  __shared__ float s_bias[BN];
+  __shared__ __align__(16) float s_scale[BN];
+  __shared__ __align__(16) float s_bias[BN];
 
   using L = GemmSmem<BN, STAGES>;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -174,7 +174,6 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     ptx::mbar_wait(&tmem_full_bar, 0);
     ptx::tc_fence_after();
 
-    const int act = args.act;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
@@ -183,8 +182,16 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       const int nb = n0 + c * 32;
       if (valid && nb < args.N) {
         float f[32];
+        const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);
+        const float4* bi4 = reinterpret_cast<const float4*>(s_bias + c * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = es3_act(__uint_as_float(v[j]) * s_scale[c * 32 + j] + s_bias[c * 32 + j], act);
+        for (int j = 0; j < 8; ++j) {
+          const float4 sc = sc4[j], bi = bi4[j];
+          f[4 * j + 0] = es3_act_t<ACT>(fmaf(__uint_as_float(v[4 * j + 0]), sc.x, bi.x));
+          f[4 * j + 1] = es3_act_t<ACT>(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, bi.y));
+          f[4 * j + 2] = es3_act_t<ACT>(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, bi.z));
+          f[4 * j + 3] = es3_act_t<ACT>(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, bi.w));
+        }
         if (args.residual != nullptr) {
           const uint4* rp = reinterpret_cast<const uint4*>(args.residual + row_off * args.ldr + nb);
 #pragma unroll
@@ -255,20 +262,32 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64
   return 0;
 }
 
-template <int BN, int STAGES>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int tiles_m,
-                  cudaStream_t stream) {
+template <int BN, int STAGES, int ACT>
+static int launch_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int tiles_m,
+                      cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    ES3_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         L::TOTAL));
     configured = true;
   }
   dim3 grid((unsigned)(tiles_m * args.tiles_n));
-  gemm_tc_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, args);
+  gemm_tc_kernel<BN, STAGES, ACT><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, args);
   ES3_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
+}
+
+template <int BN, int STAGES>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int tiles_m,
+                  cudaStream_t stream) {
+  switch (args.act) {
+    case ACT_NONE: return launch_act<BN, STAGES, ACT_NONE>(tmA, tmB, args, tiles_m, stream);
+    case ACT_RELU: return launch_act<BN, STAGES, ACT_RELU>(tmA, tmB, args, tiles_m, stream);
+    case ACT_HSWISH: return launch_act<BN, STAGES, ACT_HSWISH>(tmA, tmB, args, tiles_m, stream);
+    case ACT_GELU: return launch_act<BN, STAGES, ACT_GELU>(tmA, tmB, args, tiles_m, stream);
+    default: set_error("gemm_tc: activation code %d not instantiated (0,1,2,3)", args.act); return 1;
+  }
 }
 
 static int pick_bn(int N, int bn_hint) {

@@ -1,0 +1,71 @@
+"""Host-side helpers shared by the module shells: BN folding, weight packing, plan caching.
+
+The shells (`backbones/*.py`, `stage1/model.py`, ...) keep the reference's class names, constructor
+signatures and state_dict keys; torch.nn.Conv2d / BatchNorm2d / Linear objects inside them are used
+ONLY as parameter containers (their forward is never called) -- all device work goes through
+`efficientsam3_b200.ops` -> libes3.so.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+
+def bn_scale_bias(norm: nn.BatchNorm2d | None, conv_bias: torch.Tensor | None, cout: int, device):
+    """Eval-mode BatchNorm folded to per-channel (scale, bias) in fp32; conv bias merged.
+    Returns (scale|None, bias|None)."""
+    if norm is None:
+        return None, (conv_bias.detach().float().contiguous() if conv_bias is not None else None)
+    s = (norm.weight.detach().float() / torch.sqrt(norm.running_var.detach().float() + norm.eps))
+    b = norm.bias.detach().float() - norm.running_mean.detach().float() * s
+    if conv_bias is not None:
+        b = b + conv_bias.detach().float() * s
+    return s.contiguous(), b.contiguous()
+
+
+def pw_weight(conv: nn.Conv2d) -> torch.Tensor:
+    """1x1 conv weight [N,C,1,1] -> bf16 [N,C] (K-major GEMM B operand)."""
+    w = conv.weight.detach()
+    return w.reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+
+
+def dw_weight(conv: nn.Conv2d, scale: torch.Tensor | None) -> torch.Tensor:
+    """depthwise weight [C,1,k,k] (x folded BN scale) -> fp32 [k*k, C] tap-major."""
+    w = conv.weight.detach().float()
+    c, _, k, _ = w.shape
+    if scale is not None:
+        w = w * scale.view(-1, 1, 1, 1)
+    return w.reshape(c, k * k).t().contiguous()
+
+
+def conv3x3_weight(conv: nn.Conv2d) -> torch.Tensor:
+    """dense 3x3 weight [N,C,3,3] -> bf16 [N, 9*C] with k = (ky*3+kx)*C + c."""
+    w = conv.weight.detach()
+    n, c = w.shape[:2]
+    return w.permute(0, 2, 3, 1).reshape(n, 9 * c).to(torch.bfloat16).contiguous()
+
+
+def params_fingerprint(module: nn.Module):
+    """Cheap change detector for cached packed weights: (data_ptr, _version) of every tensor."""
+    fp = []
+    for t in list(module.parameters()) + list(module.buffers()):
+        fp.append((t.data_ptr(), t._version))
+    return tuple(fp)
+
+
+class NativePlanMixin:
+    """Caches packed / folded weights; rebuilds when parameters, device or mode change."""
+
+    def _plan(self):
+        key = (params_fingerprint(self), self.training)
+        if getattr(self, "_plan_key", None) != key:
+            self._plan_cache = self._build_plan()
+            self._plan_key = key
+        return self._plan_cache
+
+    def _require_eval(self, what: str):
+        if self.training:
+            raise NotImplementedError(
+                f"{what}: the native sm_100a path implements eval-mode forward only in this round "
+                "(BatchNorm batch statistics + backward are the next scope row; see DESIGN.md). "
+                "Call .eval() first.")

@@ -96,7 +96,7 @@ def stem_conv3x3_s2(x, w27, bias, act):
     return out
 
 
-def dwconv(x, w, bias, ks, stride, act, out=None):
+def dwconv(x, w, bias, ks, stride, act, out=None, force_simple=False):
     """x: [B,H,W,C] bf16 (channel-sliced views allowed); w: [ks*ks, C] fp32."""
     _chk(x, torch.bfloat16, "x")
     _ensure_init(x)
@@ -106,7 +106,8 @@ def dwconv(x, w, bias, ks, stride, act, out=None):
     Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
     if out is None:
         out = torch.empty((B, Ho, Wo, Cc), device=x.device, dtype=torch.bfloat16)
-    _lib.call("es3_dwconv_bf16", x.data_ptr(), x.stride(2), w.data_ptr(), _ptr(bias), out.data_ptr(), out.stride(2),
+    fn = "es3_dwconv_tiled_bf16" if (Cc % 32 == 0 and not force_simple) else "es3_dwconv_bf16"
+    _lib.call(fn, x.data_ptr(), x.stride(2), w.data_ptr(), _ptr(bias), out.data_ptr(), out.stride(2),
               B, H, W, Cc, ks, stride, ACT[act], _stream())
     return out
 
@@ -152,13 +153,14 @@ def nchw_f32_to_nhwc(x):
     return out
 
 
-def litemla_aggreg(ms, wdw, wpw, C3):
+def litemla_aggreg(ms, wdw, wpw, C3, force_simple=False):
     """ms: [B,H,W,2*C3] bf16; fills channels [C3, 2*C3) in place."""
     _chk(ms, torch.bfloat16, "ms")
     _ensure_init(ms)
     assert ms.is_contiguous()
     B, H, W, ld = ms.shape
-    _lib.call("es3_litemla_aggreg", ms.data_ptr(), ld, wdw.data_ptr(), wpw.data_ptr(), B, H, W, C3, _stream())
+    fn = "es3_litemla_aggreg_tiled" if (C3 % 64 == 0 and not force_simple) else "es3_litemla_aggreg"
+    _lib.call(fn, ms.data_ptr(), ld, wdw.data_ptr(), wpw.data_ptr(), B, H, W, C3, _stream())
     return ms
 
 

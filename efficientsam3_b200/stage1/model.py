@@ -1,0 +1,84 @@
+"""Drop-in for the reference `stage1/model.py` (image path): same builder / class names, same
+state_dict keys, forward on libes3.so.
+
+  build_image_student_model(config)   stage1/model.py:30-39
+  ImageStudentEncoder                 stage1/model.py:188-211   (head.0/1/3 keys preserved)
+  EfficientViTAdapter                 stage1/model.py:327-335
+  _build_backbone                     stage1/model.py:386-417
+
+`config` needs MODEL.BACKBONE, DATA.IMG_SIZE, DISTILL.EMBED_DIM, DISTILL.EMBED_SIZE (yacs CfgNode or any
+attribute namespace).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..backbones.efficientvit import (efficientvit_backbone_b0, efficientvit_backbone_b1,
+                                      efficientvit_backbone_b2)
+from ..nn_utils import NativePlanMixin, bn_scale_bias, conv3x3_weight, pw_weight
+
+
+def build_image_student_model(config):
+    backbone_name = config.MODEL.BACKBONE.lower()
+    backbone, out_channels = _build_backbone(backbone_name, config.DATA.IMG_SIZE)
+    return ImageStudentEncoder(backbone=backbone, in_channels=out_channels, embed_dim=config.DISTILL.EMBED_DIM,
+                               embed_size=config.DISTILL.EMBED_SIZE, img_size=config.DATA.IMG_SIZE)
+
+
+class ImageStudentEncoder(nn.Module, NativePlanMixin):
+    def __init__(self, backbone, in_channels, embed_dim, embed_size, img_size):
+        super().__init__()
+        self.backbone = backbone
+        self.embed_size = embed_size
+        self.img_size = img_size
+        # parameter containers; keys head.0.weight, head.1.{weight,bias,running_*}, head.3.{weight,bias}
+        self.head = nn.Sequential(
+            nn.Conv2d(in_channels, embed_dim, kernel_size=1, bias=False),
+            nn.BatchNorm2d(embed_dim),
+            nn.GELU(),
+            nn.Conv2d(embed_dim, embed_dim, kernel_size=3, padding=1),
+        )
+
+    def _build_plan(self):
+        dev = self.head[0].weight.device
+        s, b = bn_scale_bias(self.head[1], None, self.head[0].out_channels, dev)
+        return dict(w0=pw_weight(self.head[0]), s0=s, b0=b, w3=conv3x3_weight(self.head[3]),
+                    b3=self.head[3].bias.detach().float().contiguous())
+
+    @torch.no_grad()
+    def forward(self, x):
+        self._require_eval("ImageStudentEncoder.forward")
+        feats = self.backbone.forward_nhwc(x)          # [B,h,w,Cin] bf16
+        p = self._plan()
+        B, h, w, cin = feats.shape
+        y = ops.gemm(feats.view(-1, cin), p["w0"], scale=p["s0"], bias=p["b0"], act="gelu")
+        y = ops.conv3x3(y.view(B, h, w, -1), p["w3"], bias=p["b3"])
+        if h != self.embed_size or w != self.embed_size:
+            return ops.bilinear_nhwc_to_nchw(y, self.embed_size, self.embed_size)
+        return ops.nhwc_to_nchw_f32(y)
+
+
+class EfficientViTAdapter(nn.Module):
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+        self.out_channels = self.model.width_list[-1]
+
+    def forward(self, x):
+        return self.model(x)["stage_final"]
+
+    def forward_nhwc(self, x):
+        return self.model.forward_nhwc(x)
+
+
+def _build_backbone(name, img_size):
+    if name.startswith("efficientvit"):
+        fn = {"efficientvit_b0": efficientvit_backbone_b0, "efficientvit_b1": efficientvit_backbone_b1,
+              "efficientvit_b2": efficientvit_backbone_b2}[name]
+        adapter = EfficientViTAdapter(fn())
+        return adapter, adapter.out_channels
+    if name.startswith("repvit") or name.startswith("tiny_vit"):
+        raise NotImplementedError(f"{name}: native student backbone not built yet (see DESIGN.md scope table)")
+    raise ValueError(f"Unsupported backbone {name}")

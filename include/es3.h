@@ -59,6 +59,10 @@ int es3_stem_conv3x3_s2(const float* x, const float* w, const float* bias, void*
 int es3_dwconv_bf16(const void* x, long long ldx, const float* w, const float* bias, void* out, long long ldo, int B,
                     int H, int W, int C, int ks, int stride, int act, void* stream);
 
+/* Same contract as es3_dwconv_bf16 (C % 32 == 0): shared-memory tiled, 4-pixel register strips. */
+int es3_dwconv_tiled_bf16(const void* x, long long ldx, const float* w, const float* bias, void* out, long long ldo,
+                          int B, int H, int W, int C, int ks, int stride, int act, void* stream);
+
 /* y = x + BN(pw(act(BN(dw3x3(x))))) in one pass; C in {8,16,24,32}.
  * Replaces the stem ResidualBlock(DSConv) (efficientvit/backbone.py:58-67). */
 int es3_dsconv_res_bf16(const void* x, const float* wdw, const float* bdw, const float* wpw, const float* bpw,
@@ -75,6 +79,9 @@ int es3_nchw_f32_to_nhwc(const float* in, void* out, int B, int HW, int C, void*
  * channels [C3,2*C3).  wdw [25][C3] fp32, wpw [C3][16] fp32.  Replaces LiteMLA.aggreg (ops.py:560-575,655-660). */
 int es3_litemla_aggreg(void* ms, long long ld, const float* wdw, const float* wpw, int B, int H, int W, int C3,
                        void* stream);
+/* Same contract as es3_litemla_aggreg (C3 % 64 == 0): tiled dw5x5 with the grouped 1x1 fused in registers. */
+int es3_litemla_aggreg_tiled(void* ms, long long ld, const float* wdw, const float* wpw, int B, int H, int W, int C3,
+                             void* stream);
 /* ReLU linear attention over the multi-scale qkv buffer (head h = channels [48h,48h+48) = q|k|v, dim 16).
  * kv_ws: B*heads2*17*16 floats of scratch.  att [B,HW,ldo] bf16.  Replaces relu_linear_att (ops.py:584-621). */
 int es3_litemla_attn(const void* ms, long long ld, float* kv_ws, void* att, long long ldo, int B, int HW, int heads2,

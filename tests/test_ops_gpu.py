@@ -109,15 +109,17 @@ def test_stem(cuda, H, W, Cout):
     _close(out, ref, 1e-2, "stem")
 
 
-@pytest.mark.parametrize("ks,stride,H,W,C", [(3, 1, 20, 20, 64), (3, 2, 21, 19, 32), (5, 1, 16, 16, 48), (3, 2, 63, 63, 512)])
-def test_dwconv(cuda, ks, stride, H, W, C):
+@pytest.mark.parametrize("simple", [False, True])
+@pytest.mark.parametrize("ks,stride,H,W,C", [(3, 1, 20, 20, 64), (3, 2, 21, 19, 32), (5, 1, 16, 16, 48), (3, 2, 63, 63, 512),
+                                             (3, 1, 64, 64, 128), (5, 1, 33, 70, 96), (3, 2, 128, 128, 64), (3, 1, 7, 5, 32)])
+def test_dwconv(cuda, ks, stride, H, W, C, simple):
     from efficientsam3_b200 import ops
     g = torch.Generator().manual_seed(ks * 10 + stride)
     x = _bf(torch.randn(2, H, W, C, generator=g)).to(cuda)
     w = (torch.randn(C, 1, ks, ks, generator=g) / ks).to(cuda)
     b = torch.randn(C, generator=g).to(cuda)
     wt = w.reshape(C, ks * ks).t().contiguous()
-    out = ops.dwconv(x, wt, b, ks, stride, "hswish")
+    out = ops.dwconv(x, wt, b, ks, stride, "hswish", force_simple=simple)
     ref = F.hardswish(F.conv2d(x.float().permute(0, 3, 1, 2), w, b, stride=stride, padding=ks // 2, groups=C)).permute(0, 2, 3, 1)
     _close(out, ref, 1e-2, "dwconv")
 
@@ -156,8 +158,9 @@ def test_layout_roundtrip(cuda):
     assert torch.equal(z, x.to(torch.bfloat16).float())
 
 
-@pytest.mark.parametrize("H,W,heads,B", [(32, 32, 16, 2), (63, 63, 8, 1)])
-def test_litemla(cuda, H, W, heads, B):
+@pytest.mark.parametrize("simple", [False, True])
+@pytest.mark.parametrize("H,W,heads,B", [(32, 32, 16, 2), (63, 63, 8, 1), (64, 64, 8, 2)])
+def test_litemla(cuda, H, W, heads, B, simple):
     """aggreg + ReLU linear attention vs the textbook formulation (efficientvit/nn/ops.py:584-621)."""
     from efficientsam3_b200 import ops
     dim = 16
@@ -169,7 +172,7 @@ def test_litemla(cuda, H, W, heads, B):
     wpw = (torch.randn(C3, 16, 1, 1, generator=g) / 4).to(cuda)
     ms = torch.zeros(B, H, W, 2 * C3, device=cuda, dtype=torch.bfloat16)
     ms[..., :C3] = qkv
-    ops.litemla_aggreg(ms, wdw.reshape(C3, 25).t().contiguous(), wpw.reshape(C3, 16).contiguous(), C3)
+    ops.litemla_aggreg(ms, wdw.reshape(C3, 25).t().contiguous(), wpw.reshape(C3, 16).contiguous(), C3, force_simple=simple)
     x = qkv.float().permute(0, 3, 1, 2)
     dw = F.conv2d(x, wdw, padding=2, groups=C3).to(torch.bfloat16).float()
     agg = F.conv2d(dw, wpw, groups=3 * heads)

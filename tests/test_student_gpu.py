@@ -1,0 +1,80 @@
+"""GPU parity of the native EV-M student encoder (through the reference-shaped module API, which calls
+the C ABI) against (a) the committed reference fixture and (b) the CPU oracle on larger seeded inputs.
+
+Stated tolerance (bf16 activations/weights in HBM, fp32 accumulation -- DESIGN.md "Precision"):
+  relative L2 error of the embedding <= 2e-2, max|err| / max|ref| <= 1e-1, cosine >= 0.9995.
+(The north-star's rtol 1e-4 is an fp32-class figure; the reference's own GPU path runs fp16 autocast + TF32,
+SURVEY.md D7.  The fp32-accurate split-bf16 mode is a later scope row.)
+"""
+from types import SimpleNamespace as NS
+
+import pytest
+import torch
+
+from helpers import cosine, load_golden, max_err_over_scale, rel_l2, sd_from_keys
+
+pytestmark = pytest.mark.gpu
+
+TOL_L2, TOL_MAX, TOL_COS = 2e-2, 1e-1, 0.9995
+
+
+def _build(img, embed, sd, dev):
+    from efficientsam3_b200.stage1.model import build_image_student_model
+    cfg = NS(MODEL=NS(BACKBONE="efficientvit_b1"), DATA=NS(IMG_SIZE=img), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=embed))
+    m = build_image_student_model(cfg)
+    m.load_state_dict(sd)
+    return m.to(dev).eval()
+
+
+def _check(got, ref, what):
+    l2, mx, cs = rel_l2(got, ref), max_err_over_scale(got, ref), cosine(got, ref)
+    print(f"{what}: rel_l2={l2:.3e} max/scale={mx:.3e} cos={cs:.6f}")
+    assert l2 <= TOL_L2 and mx <= TOL_MAX and cs >= TOL_COS, (what, l2, mx, cs)
+
+
+def test_evm_matches_reference_fixture(cuda):
+    g = load_golden("evm_160")
+    sd = sd_from_keys(g["keys"], int(g["seed_w"]))
+    img, embed = int(g["img"]), int(g["embed"])
+    m = _build(img, embed, sd, cuda)
+    x = torch.randn(int(g["batch"]), 3, img, img, generator=torch.Generator().manual_seed(int(g["seed_x"])))
+    out = m(x.to(cuda)).cpu()
+    assert out.shape == tuple(g["out"].shape) and out.dtype == torch.float32
+    _check(out, g["out"], "evm_160 vs reference fixture")
+
+
+@pytest.mark.parametrize("img,embed,batch", [(256, 18, 2), (224, 7, 3)])
+def test_evm_matches_oracle(cuda, img, embed, batch):
+    from oracle import efficientvit as O
+    g = load_golden("evm_160")
+    sd = sd_from_keys(g["keys"], 101)
+    x = torch.randn(batch, 3, img, img, generator=torch.Generator().manual_seed(7))
+    with torch.no_grad():
+        ref, stages = O.image_student_encoder(sd, x, embed, "b1", return_stages=True)
+    m = _build(img, embed, sd, cuda)
+    out = m(x.to(cuda)).cpu()
+    _check(out, ref, f"evm {img} vs oracle")
+    # per-stage parity through the reference-shaped backbone API (dict of NCHW fp32 maps)
+    feats = m.backbone.model(x.to(cuda))
+    for k, v in stages.items():
+        _check(feats[k].cpu(), v, f"{k}")
+
+
+def test_evm_full_size_properties(cuda):
+    """1024^2 (BASELINE size): shape/dtype, finiteness, batch-composition invariance (each image's
+    embedding must not depend on its batch neighbours -- eval-mode BN, per-image LiteMLA state)."""
+    g = load_golden("evm_160")
+    sd = sd_from_keys(g["keys"], 5)
+    m = _build(1024, 64, sd, cuda)
+    x = torch.randn(3, 3, 1024, 1024, generator=torch.Generator().manual_seed(3)).to(cuda)
+    out = m(x)
+    assert out.shape == (3, 1024, 64, 64) and torch.isfinite(out).all()
+    solo = m(x[1:2])
+    assert torch.equal(solo[0], out[1]), "embedding depends on batch neighbours"
+
+
+def test_train_mode_is_refused(cuda):
+    g = load_golden("evm_160")
+    m = _build(160, 12, sd_from_keys(g["keys"], 1), cuda).train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 160, 160, device=cuda))
