@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- encoder images/sec at 1024^2 for the EV-M student (BASELINE.json metric), B200-native path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--batch B] [--img S]
+
+One "step" = one forward pass of the hot path over one synthetic batch (per GPU):
+  ImageStudentEncoder(efficientvit_b1) : [B,3,S,S] fp32 NCHW -> [B,1024,E,E] fp32   (stage1/model.py:188-211)
+N > 1 (torchrun): images are sharded across ranks, no data-path collective (inference is embarrassingly
+parallel) -> "scaling": "weak"; timing = max over ranks of device time.
+
+Keys beyond the base contract: `roofline` (dominant kernel family, measured live with CUDA events on the
+launch stream), `cpu_baseline` (the oracle port timed on this box's host cores, rank 0, N=1), `e2e`
+(pinned host batch -> H2D -> module forward -> D2H of the step's scalar metric, every step).
+`--impl reference` times the CPU oracle port (the reference is Python/PyTorch; /root/reference does not
+exist on the GPU box, and the oracle is pinned to it by tests/golden) with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace as NS
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "encoder images/sec @1024^2 (EV-M student forward)"
+UNIT = "images/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_student(img, embed, device):
+    from efficientsam3_b200.stage1.model import build_image_student_model
+    cfg = NS(MODEL=NS(BACKBONE="efficientvit_b1"), DATA=NS(IMG_SIZE=img), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=embed))
+    torch.manual_seed(0)
+    m = build_image_student_model(cfg)
+    with torch.no_grad():  # random-init weights of the named architecture + non-trivial BN statistics
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.running_mean.normal_(0, 0.1)
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.normal_(0, 0.1)
+    return m.to(device).eval()
+
+
+def run_native(args):
+    from efficientsam3_b200 import ops
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, S, E = args.batch, args.img, args.embed
+    model = build_student(S, E, dev)
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = [torch.randn(B, 3, S, S, generator=g).pin_memory() for _ in range(2)]
+    x_dev = [h.to(dev) for h in host]  # 2 x 403 MB at B=32,S=1024: each larger than the 126 MB L2
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident throughput
+    for i in range(args.warmup):
+        out = model(x_dev[i % 2])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = model(x_dev[i % 2])
+    e1.record()
+    barrier()
+    launches = ops.launch_count - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---------------------------------------------------------------- end-to-end (host buffers)
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [torch.empty_like(x_dev[0]) for _ in range(2)]
+    metric_host = torch.zeros(1).pin_memory()
+
+    def e2e_pass(nsteps):
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        with torch.cuda.stream(copy_stream):
+            stage[0].copy_(host[0], non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(nsteps):
+            cur, nxt = i % 2, (i + 1) % 2
+            if i + 1 < nsteps:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(freed[nxt])
+                    stage[nxt].copy_(host[nxt], non_blocking=True)
+                    ready[nxt].record(copy_stream)
+            torch.cuda.current_stream().wait_event(ready[cur])
+            y = model(stage[cur])
+            freed[cur].record()
+            metric_host.copy_(y[:, :, ::8, ::8].abs().mean().reshape(1), non_blocking=True)  # step metric, 4 bytes D2H
+            torch.cuda.current_stream().synchronize()  # the caller consumes the metric every step
+
+    e2e_pass(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_pass(args.steps)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (t.item() / 1e3)
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    roofline, kernel_table = None, None
+    if rank == 0:
+        prof = ops.Profiler()
+        ops.set_profiler(prof)
+        for i in range(3):
+            model(x_dev[i % 2])
+        ops.set_profiler(None)
+        agg = prof.summary()
+        kernel_table = sorted(((k, v["ms"] / 3, v["calls"] // 3, v["bytes"] / 3, v["flops"] / 3) for k, v in agg.items()),
+                              key=lambda r: -r[1])
+        name, kms, calls, kbytes, kflops = kernel_table[0]
+        pk = _peaks()
+        gbs = kbytes / 1e9 / (kms / 1e3)
+        tfs = kflops / 1e12 / (kms / 1e3)
+        frac_hbm, frac_tc = gbs / pk["hbm"], tfs / pk["tf_sustained"]
+        if frac_tc > frac_hbm:
+            roofline = {"bound": "tensor", "achieved": round(tfs, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                        "frac": round(frac_tc, 4), "traffic": None}
+        else:
+            roofline = {"bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": round(frac_hbm, 4), "traffic": None}
+        roofline.update(kernel=name, launches_per_step=calls, ms_per_step=round(kms, 4),
+                        share_of_step=round(kms / sum(r[1] for r in kernel_table), 4), peak_source=pk["src"])
+        # whole-step figures against SURVEY section 8d's per-image algorithmic bytes / flops
+        alg_bytes = 110e6 * (S / 1008.0) ** 2 * B
+        alg_flops = 40.2e9 * (S / 1008.0) ** 2 * B
+        roofline["step"] = {"alg_GB_per_step": round(alg_bytes / 1e9, 3), "hbm_frac": round(alg_bytes / 1e9 / (ms_step / 1e3) / pk["hbm"], 4),
+                            "alg_TFLOP_per_step": round(alg_flops / 1e12, 3),
+                            "tensor_frac": round(alg_flops / 1e12 / (ms_step / 1e3) / pk["tf_sustained"], 4)}
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_oracle_throughput(S, E, batch=min(B, 2), steps=3, warmup=1)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"EV-M student encoder forward (efficientvit_b1 + 1024-ch head, eval), batch {B}/GPU x "
+                                   f"3x{S}x{S} fp32 NCHW -> 1024x{E}x{E} fp32; random-init weights",
+                       "batch_per_gpu": B, "global_batch": B * world, "img": S, "embed": E, "parallelism": f"dp{world}",
+                       "l2_policy": f"inputs alternate between two {x_dev[0].numel()*4/1e6:.0f} MB buffers (> 126 MB L2)"},
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": host[0].numel() * 4,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        if kernel_table is not None and args.table:
+            with open(args.table, "w") as f:
+                f.write("| kernel family | launches/step | ms/step | alg GB/s | alg TFLOP/s |\n|---|---|---|---|---|\n")
+                for k, kms, c, kb, kf in kernel_table:
+                    f.write(f"| `{k}` | {c} | {kms:.4f} | {kb/1e9/(kms/1e3):.0f} | {kf/1e12/(kms/1e3):.1f} |\n")
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_oracle_throughput(S, E, batch, steps, warmup):
+    """Times the CPU oracle port (oracle/efficientvit.py; pinned to the reference by tests/golden) on all host
+    threads.  The only place bench.py touches oracle/ -- as a baseline, never as the product path."""
+    from oracle import efficientvit as O
+    from oracle.weights import fill_state_dict
+    from efficientsam3_b200.stage1.model import build_image_student_model
+    cfg = NS(MODEL=NS(BACKBONE="efficientvit_b1"), DATA=NS(IMG_SIZE=S), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=E))
+    sd = fill_state_dict(build_image_student_model(cfg).state_dict(), 7)
+    x = torch.randn(batch, 3, S, S, generator=torch.Generator().manual_seed(1))
+    cores = torch.get_num_threads()
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.image_student_encoder(sd, x, E, "b1")
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            O.image_student_encoder(sd, x, E, "b1")
+            ts.append(time.perf_counter() - t0)
+    sec = statistics.median(ts)
+    return {"value": round(batch / sec, 3), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} timed passes of batch {batch} x 3x{S}x{S} (median), PyTorch-CPU fp32 eager oracle port, "
+                      f"torch threads={cores}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    S, E = args.img, args.embed
+    batch = min(args.batch, 2)
+    t0 = time.perf_counter()
+    cpu = cpu_oracle_throughput(S, E, batch=batch, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(batch / cpu["value"] * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"EV-M student encoder forward on host CPU (oracle port of the reference modules), "
+                               f"bounded sample: batch {batch} x 3x{S}x{S}", "img": S, "embed": E},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": round(time.perf_counter() - t0, 1),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--img", type=int, default=1024)
+    ap.add_argument("--embed", type=int, default=64, help="stage1/config.py:21,50 pair IMG_SIZE 1024 with EMBED_SIZE 64")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--table", default=None, help="write the per-kernel-family table (markdown) here")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

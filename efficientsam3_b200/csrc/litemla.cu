@@ -7,6 +7,7 @@
 // (B, 2*heads, 3*dim, HW), head h owns channels [48h, 48h+48): q | k | v (ops.py:590-606, dim = 16).
 //
 //   kv kernel   : KV[b,h] (17x16) = sum_p [v_p ; 1] relu(k_p)^T        (ops.py:609-616, the padded ones row)
+//                 two-stage, fixed summation order -> bit-reproducible
 //   apply kernel: out_p = KV[:16] relu(q_p) / (KV[16] . relu(q_p) + eps) (ops.py:617-620)
 // All arithmetic fp32 (the reference forces fp32 here, ops.py:586-589).
 #include "common.cuh"
@@ -79,52 +80,65 @@ __global__ void litemla_aggreg_kernel(const bf16* ms_in, bf16* ms_out, long long
   op[1] = pack8(o + 8);
 }
 
-// grid (chunks of 128 pixels, heads2, B), block 256.  kv: [B][heads2][17][16] fp32, pre-zeroed.
-__global__ void litemla_kv_kernel(const bf16* __restrict__ ms, long long ld, float* __restrict__ kv, int HW) {
+// Deterministic two-stage reduction (no atomics: results must not depend on scheduling, the
+// reference's masks are compared bit-for-bit downstream).
+// Stage 1: grid (chunks of KV_CHUNK pixels, heads2, B), block 256.
+//          part: [B][heads2][nchunk][17][16] fp32 partial sums.
+constexpr int KV_CHUNK = 512;
+__global__ void litemla_kv_kernel(const bf16* __restrict__ ms, long long ld, float* __restrict__ part, int HW) {
   __shared__ float sk[128][LDIM];
   __shared__ float sv[128][LDIM + 1];
-  const int h = blockIdx.y, b = blockIdx.z, heads2 = gridDim.y;
-  const int p0 = blockIdx.x * 128;
-  // 128 pixels x 4 uint4 (k: 2, v: 2)
-  for (int i = threadIdx.x; i < 128 * 4; i += blockDim.x) {
-    const int pl = i >> 2, v = i & 3;
-    const int p = p0 + pl;
-    float f[8];
-    if (p < HW) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(ms + ((long long)b * HW + p) * ld + h * 48 + 16 + v * 8)), f);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = 0.f;
-    }
-    if (v < 2) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sk[pl][v * 8 + e] = fmaxf(f[e], 0.f);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sv[pl][(v - 2) * 8 + e] = f[e];
-    }
-  }
-  __syncthreads();
+  const int h = blockIdx.y, b = blockIdx.z, heads2 = gridDim.y, nchunk = gridDim.x;
   const int i = threadIdx.x >> 4, j = threadIdx.x & 15;
   float acc = 0.f, ones = 0.f;
+  for (int sub = 0; sub < KV_CHUNK / 128; ++sub) {
+    const int p0 = blockIdx.x * KV_CHUNK + sub * 128;
+    if (p0 >= HW) break;
+    // 128 pixels x 4 uint4 (k: 2, v: 2)
+    for (int t = threadIdx.x; t < 128 * 4; t += blockDim.x) {
+      const int pl = t >> 2, v = t & 3;
+      const int p = p0 + pl;
+      float f[8];
+      if (p < HW) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(ms + ((long long)b * HW + p) * ld + h * 48 + 16 + v * 8)), f);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = 0.f;
+      }
+      if (v < 2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sk[pl][v * 8 + e] = fmaxf(f[e], 0.f);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sv[pl][(v - 2) * 8 + e] = f[e];
+      }
+    }
+    __syncthreads();
 #pragma unroll 8
-  for (int p = 0; p < 128; ++p) {
-    const float kk = sk[p][j];
-    acc = fmaf(sv[p][i], kk, acc);
-    ones += kk;  // rows beyond HW hold k = 0
+    for (int p = 0; p < 128; ++p) {
+      const float kk = sk[p][j];
+      acc = fmaf(sv[p][i], kk, acc);
+      ones += kk;  // rows beyond HW hold k = 0
+    }
+    __syncthreads();
   }
-  float* dst = kv + ((long long)b * heads2 + h) * 17 * LDIM;
-  atomicAdd(dst + i * LDIM + j, acc);
-  if (i == 0) atomicAdd(dst + 16 * LDIM + j, ones);
+  float* dst = part + (((long long)b * heads2 + h) * nchunk + blockIdx.x) * 17 * LDIM;
+  dst[i * LDIM + j] = acc;
+  if (i == 0) dst[16 * LDIM + j] = ones;
 }
 
-// grid (chunks of 128 pixels, heads2, B), block 128.  att: [B][HW][ldo] bf16, head h -> channels [16h, 16h+16).
-__global__ void litemla_apply_kernel(const bf16* __restrict__ ms, long long ld, const float* __restrict__ kv,
-                                     bf16* __restrict__ att, long long ldo, int HW, float eps) {
+// Stage 2 + apply: grid (chunks of 128 pixels, heads2, B), block 128.  Sums the partials in fixed order.
+// att: [B][HW][ldo] bf16, head h -> channels [16h, 16h+16).
+__global__ void litemla_apply_kernel(const bf16* __restrict__ ms, long long ld, const float* __restrict__ part,
+                                     int nchunk, bf16* __restrict__ att, long long ldo, int HW, float eps) {
   __shared__ float skv[17 * LDIM];
   const int h = blockIdx.y, b = blockIdx.z, heads2 = gridDim.y;
-  const float* src = kv + ((long long)b * heads2 + h) * 17 * LDIM;
-  for (int i = threadIdx.x; i < 17 * LDIM; i += blockDim.x) skv[i] = src[i];
+  const float* src = part + ((long long)b * heads2 + h) * nchunk * 17 * LDIM;
+  for (int i = threadIdx.x; i < 17 * LDIM; i += blockDim.x) {
+    float a = 0.f;
+    for (int c = 0; c < nchunk; ++c) a += src[c * 17 * LDIM + i];
+    skv[i] = a;
+  }
   __syncthreads();
   const int p = blockIdx.x * 128 + threadIdx.x;
   if (p >= HW) return;
@@ -167,17 +181,22 @@ extern "C" int es3_litemla_aggreg(void* ms, long long ld, const float* wdw, cons
   return 0;
 }
 
-// ms: [B,HW,ld] bf16 (ld = 48*heads2), kv_ws: fp32 workspace of B*heads2*17*16 floats,
-// att: [B,HW,ldo] bf16 output (ldo >= 16*heads2).
+// ms: [B,HW,ld] bf16 (ld = 48*heads2), kv_ws: fp32 workspace of B*heads2*ceil(HW/512)*17*16 floats
+// (es3_litemla_ws_floats), att: [B,HW,ldo] bf16 output (ldo >= 16*heads2).
+extern "C" long long es3_litemla_ws_floats(int B, int HW, int heads2) {
+  return (long long)B * heads2 * ceil_div(HW, KV_CHUNK) * 17 * LDIM;
+}
+
 extern "C" int es3_litemla_attn(const void* ms, long long ld, float* kv_ws, void* att, long long ldo, int B, int HW,
                                 int heads2, float eps, void* stream) {
   ES3_REQUIRE(ld >= 48 * heads2 && ld % 8 == 0 && ldo % 8 == 0, "es3_litemla_attn: bad ld=%lld ldo=%lld heads2=%d", ld, ldo, heads2);
   cudaStream_t st = (cudaStream_t)stream;
-  ES3_CHECK_CUDA(cudaMemsetAsync(kv_ws, 0, (size_t)B * heads2 * 17 * LDIM * sizeof(float), st));
-  dim3 grid(ceil_div(HW, 128), heads2, B);
-  litemla_kv_kernel<<<grid, 256, 0, st>>>((const bf16*)ms, ld, kv_ws, HW);
+  const int nchunk = ceil_div(HW, KV_CHUNK);
+  dim3 grid1(nchunk, heads2, B);
+  litemla_kv_kernel<<<grid1, 256, 0, st>>>((const bf16*)ms, ld, kv_ws, HW);
   ES3_LAUNCH_CHECK("litemla_kv_kernel");
-  litemla_apply_kernel<<<grid, 128, 0, st>>>((const bf16*)ms, ld, kv_ws, (bf16*)att, ldo, HW, eps);
+  dim3 grid(ceil_div(HW, 128), heads2, B);
+  litemla_apply_kernel<<<grid, 128, 0, st>>>((const bf16*)ms, ld, kv_ws, nchunk, (bf16*)att, ldo, HW, eps);
   ES3_LAUNCH_CHECK("litemla_apply_kernel");
   return 0;
 }

@@ -16,6 +16,57 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ------------------------------------------------------------------------------------ accounting
+# kernels launched per C-ABI call (memsets excluded) -- bench.py reports the sum as `gpu_launches`.
+KERNELS_PER_CALL = {"es3_litemla_attn": 2}
+launch_count = 0
+
+
+class Profiler:
+    """Optional per-call CUDA-event timing with algorithmic bytes / flops (bench.py roofline leg).
+    Events are recorded on the current stream, which is the stream the kernels are launched on."""
+
+    def __init__(self):
+        self.records = []  # (name, start_event, end_event, bytes, flops)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, nbytes, flops in self.records:
+            a = agg.setdefault(name, dict(calls=0, ms=0.0, bytes=0, flops=0))
+            a["calls"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["bytes"] += nbytes
+            a["flops"] += flops
+        return agg
+
+
+_profiler: Profiler | None = None
+
+
+def set_profiler(p: Profiler | None):
+    global _profiler
+    _profiler = p
+
+
+def _nb(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
+def _call(name, tag, nbytes, flops, *args):
+    """Launch one C-ABI op; `tag` names the kernel family for the profiler."""
+    global launch_count
+    launch_count += KERNELS_PER_CALL.get(name, 1)
+    if _profiler is None:
+        _lib.call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.call(name, *args)
+    e1.record()
+    _profiler.records.append((tag, e0, e1, nbytes, flops))
+
+
 def _chk(t: torch.Tensor, dtype, name: str):
     if not t.is_cuda:
         raise _lib.Es3Error(f"{name}: expected a CUDA tensor (the native path has no CPU fallback)")
@@ -47,7 +98,8 @@ def gemm(a, w, *, scale=None, bias=None, act=None, residual=None, out=None, out_
     if residual is not None:
         _chk(residual, torch.bfloat16, "residual")
         assert residual.stride(1) == 1 and residual.shape == (M, N)
-    _lib.call("es3_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
+    _call("es3_gemm_bf16", f"gemm_tc[K={K},N={N}]", M * K * 2 + M * N * out.element_size() + _nb(w, residual),
+          2 * M * N * K, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
               int(out.dtype == torch.float32), M, N, K, _ptr(scale), _ptr(bias), ACT[act], _ptr(residual),
               residual.stride(0) if residual is not None else 0, bn_hint, _stream())
     return out
@@ -61,7 +113,7 @@ def gemm_simt(a, w, *, scale=None, bias=None, act=None, residual=None, out=None,
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype)
     res_f32 = int(residual is not None and residual.dtype == torch.float32)
-    _lib.call("es3_gemm_simt", a.data_ptr(), a.stride(0), int(a.dtype == torch.float32), w.data_ptr(), w.stride(0),
+    _call("es3_gemm_simt", "gemm_simt", _nb(a, w, out, residual), 2 * M * N * K, a.data_ptr(), a.stride(0), int(a.dtype == torch.float32), w.data_ptr(), w.stride(0),
               int(w.dtype == torch.float32), out.data_ptr(), out.stride(0), int(out.dtype == torch.float32), M, N, K,
               _ptr(scale), _ptr(bias), ACT[act], _ptr(residual), residual.stride(0) if residual is not None else 0,
               res_f32, _stream())
@@ -77,7 +129,8 @@ def conv3x3(x, w9, *, scale=None, bias=None, act=None, residual=None, out_dtype=
     N = w9.shape[0]
     assert w9.shape[1] == 9 * Cc
     out = torch.empty((B, H, W, N), device=x.device, dtype=out_dtype)
-    _lib.call("es3_conv3x3_bf16", x.data_ptr(), w9.data_ptr(), out.data_ptr(), int(out_dtype == torch.float32),
+    _call("es3_conv3x3_bf16", f"conv3x3_tc[C={Cc},N={N}]", _nb(x, w9, out, residual), 2 * B * H * W * N * 9 * Cc,
+          x.data_ptr(), w9.data_ptr(), out.data_ptr(), int(out_dtype == torch.float32),
               B, H, W, Cc, N, _ptr(scale), _ptr(bias), ACT[act], _ptr(residual), bn_hint, _stream())
     return out
 
@@ -91,7 +144,7 @@ def stem_conv3x3_s2(x, w27, bias, act):
     Cout = w27.shape[1]
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     out = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
-    _lib.call("es3_stem_conv3x3_s2", x.data_ptr(), w27.data_ptr(), _ptr(bias), out.data_ptr(), B, H, W, Cout,
+    _call("es3_stem_conv3x3_s2", "stem_conv3x3_s2", _nb(x, out), 2 * B * Ho * Wo * Cout * 27, x.data_ptr(), w27.data_ptr(), _ptr(bias), out.data_ptr(), B, H, W, Cout,
               ACT[act], _stream())
     return out
 
@@ -107,7 +160,8 @@ def dwconv(x, w, bias, ks, stride, act, out=None, force_simple=False):
     if out is None:
         out = torch.empty((B, Ho, Wo, Cc), device=x.device, dtype=torch.bfloat16)
     fn = "es3_dwconv_tiled_bf16" if (Cc % 32 == 0 and not force_simple) else "es3_dwconv_bf16"
-    _lib.call(fn, x.data_ptr(), x.stride(2), w.data_ptr(), _ptr(bias), out.data_ptr(), out.stride(2),
+    _call(fn, f"dwconv{ks}x{ks}s{stride}", B * H * W * Cc * 2 + B * Ho * Wo * Cc * 2, 2 * B * Ho * Wo * Cc * ks * ks,
+          x.data_ptr(), x.stride(2), w.data_ptr(), _ptr(bias), out.data_ptr(), out.stride(2),
               B, H, W, Cc, ks, stride, ACT[act], _stream())
     return out
 
@@ -118,7 +172,7 @@ def dsconv_res(x, wdw, bdw, wpw, bpw, act):
     assert x.is_contiguous()
     B, H, W, Cc = x.shape
     out = torch.empty_like(x)
-    _lib.call("es3_dsconv_res_bf16", x.data_ptr(), wdw.data_ptr(), _ptr(bdw), wpw.data_ptr(), _ptr(bpw),
+    _call("es3_dsconv_res_bf16", "dsconv_res", _nb(x, out), 2 * B * H * W * Cc * (9 + Cc), x.data_ptr(), wdw.data_ptr(), _ptr(bdw), wpw.data_ptr(), _ptr(bpw),
               out.data_ptr(), B, H, W, Cc, ACT[act], _stream())
     return out
 
@@ -129,7 +183,7 @@ def bilinear_nhwc_to_nchw(x, Ho, Wo):
     assert x.is_contiguous()
     B, Hi, Wi, Cc = x.shape
     out = torch.empty((B, Cc, Ho, Wo), device=x.device, dtype=torch.float32)
-    _lib.call("es3_bilinear_nhwc_to_nchw", x.data_ptr(), out.data_ptr(), B, Hi, Wi, Cc, Ho, Wo, _stream())
+    _call("es3_bilinear_nhwc_to_nchw", "bilinear_nhwc_to_nchw", _nb(x, out), 8 * out.numel(), x.data_ptr(), out.data_ptr(), B, Hi, Wi, Cc, Ho, Wo, _stream())
     return out
 
 
@@ -139,7 +193,7 @@ def nhwc_to_nchw_f32(x):
     assert x.is_contiguous()
     B, H, W, Cc = x.shape
     out = torch.empty((B, Cc, H, W), device=x.device, dtype=torch.float32)
-    _lib.call("es3_nhwc_to_nchw_f32", x.data_ptr(), out.data_ptr(), B, H * W, Cc, _stream())
+    _call("es3_nhwc_to_nchw_f32", "nhwc_to_nchw", _nb(x, out), 0, x.data_ptr(), out.data_ptr(), B, H * W, Cc, _stream())
     return out
 
 
@@ -149,7 +203,7 @@ def nchw_f32_to_nhwc(x):
     x = x.contiguous()
     B, Cc, H, W = x.shape
     out = torch.empty((B, H, W, Cc), device=x.device, dtype=torch.bfloat16)
-    _lib.call("es3_nchw_f32_to_nhwc", x.data_ptr(), out.data_ptr(), B, H * W, Cc, _stream())
+    _call("es3_nchw_f32_to_nhwc", "nchw_to_nhwc", _nb(x, out), 0, x.data_ptr(), out.data_ptr(), B, H * W, Cc, _stream())
     return out
 
 
@@ -160,7 +214,7 @@ def litemla_aggreg(ms, wdw, wpw, C3, force_simple=False):
     assert ms.is_contiguous()
     B, H, W, ld = ms.shape
     fn = "es3_litemla_aggreg_tiled" if (C3 % 64 == 0 and not force_simple) else "es3_litemla_aggreg"
-    _lib.call(fn, ms.data_ptr(), ld, wdw.data_ptr(), wpw.data_ptr(), B, H, W, C3, _stream())
+    _call(fn, "litemla_aggreg", 2 * B * H * W * C3 * 2, 2 * B * H * W * C3 * (25 + 16), ms.data_ptr(), ld, wdw.data_ptr(), wpw.data_ptr(), B, H, W, C3, _stream())
     return ms
 
 
@@ -171,7 +225,8 @@ def litemla_attn(ms, heads2, eps=1e-15):
     assert ms.is_contiguous()
     B, H, W, ld = ms.shape
     att = torch.empty((B, H, W, 16 * heads2), device=ms.device, dtype=torch.bfloat16)
-    kv = torch.empty((B, heads2, 17, 16), device=ms.device, dtype=torch.float32)
-    _lib.call("es3_litemla_attn", ms.data_ptr(), ld, kv.data_ptr(), att.data_ptr(), att.shape[3], B, H * W, heads2,
+    kv = torch.empty((B * heads2 * ((H * W + 511) // 512) * 17 * 16,), device=ms.device, dtype=torch.float32)
+    _call("es3_litemla_attn", "litemla_attn", _nb(ms) * 2 // 3 + _nb(ms) // 3 + _nb(att), 2 * B * H * W * heads2 * 17 * 16 * 2,
+          ms.data_ptr(), ld, kv.data_ptr(), att.data_ptr(), att.shape[3], B, H * W, heads2,
               float(eps), _stream())
     return att

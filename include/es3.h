@@ -83,7 +83,8 @@ int es3_litemla_aggreg(void* ms, long long ld, const float* wdw, const float* wp
 int es3_litemla_aggreg_tiled(void* ms, long long ld, const float* wdw, const float* wpw, int B, int H, int W, int C3,
                              void* stream);
 /* ReLU linear attention over the multi-scale qkv buffer (head h = channels [48h,48h+48) = q|k|v, dim 16).
- * kv_ws: B*heads2*17*16 floats of scratch.  att [B,HW,ldo] bf16.  Replaces relu_linear_att (ops.py:584-621). */
+ * kv_ws: es3_litemla_ws_floats(B,HW,heads2) floats of scratch (two-stage deterministic reduction, no atomics).  att [B,HW,ldo] bf16.  Replaces relu_linear_att (ops.py:584-621). */
+long long es3_litemla_ws_floats(int B, int HW, int heads2);
 int es3_litemla_attn(const void* ms, long long ld, float* kv_ws, void* att, long long ldo, int B, int HW, int heads2,
                      float eps, void* stream);
 
