@@ -24,6 +24,7 @@ SIGNATURES: dict[str, list] = {
     "es3_dwconv_bf16": [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "es3_dwconv_tiled_bf16": [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "es3_litemla_aggreg_tiled": [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp],
+    "es3_mbconv_fused_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "es3_dsconv_res_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "es3_bilinear_nhwc_to_nchw": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_nhwc_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],
@@ -71,6 +72,14 @@ def call(name: str, *args) -> None:
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise Es3Error(f"{name} failed ({rc}): {last_error()}")
+
+
+def call_rc(name: str, *args) -> int:
+    """For entry points with a documented negative 'not applicable' return (no error raised for rc < 0)."""
+    rc = getattr(load(), name)(*args)
+    if rc > 0:
+        raise Es3Error(f"{name} failed ({rc}): {last_error()}")
+    return rc
 
 
 _inited: dict[int, tuple[int, int, int]] = {}

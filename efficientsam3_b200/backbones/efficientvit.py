@@ -150,12 +150,36 @@ class _DW:
         return ops.dwconv(x4d, self.w, self.bias, self.ks, self.stride, self.act)
 
 
+def _ones(n, dev):
+    return torch.ones(n, device=dev, dtype=torch.float32)
+
+
+def _zeros(n, dev):
+    return torch.zeros(n, device=dev, dtype=torch.float32)
+
+
 class _MBConvPlan:
+    """MBConv (+ identity shortcut).  Tries the single-kernel fused path (es3_mbconv_fused_bf16) and falls
+    back to gemm_tc -> dwconv -> gemm_tc (all native kernels) for shapes it is not instantiated for."""
+
     def __init__(self, m: MBConv, residual: bool, device):
         self.inv, self.dw, self.pt = _PW(m.inverted_conv, device), _DW(m.depth_conv, device), _PW(m.point_conv, device)
         self.residual = residual
+        mid, cout = self.inv.w.shape[0], self.pt.w.shape[0]
+        self.f = dict(
+            w1=self.inv.w, s1=self.inv.scale if self.inv.scale is not None else _ones(mid, device),
+            b1=self.inv.bias if self.inv.bias is not None else _zeros(mid, device),
+            wdw=self.dw.w, b2=self.dw.bias if self.dw.bias is not None else _zeros(mid, device),
+            w3=self.pt.w, s3=self.pt.scale if self.pt.scale is not None else _ones(cout, device),
+            b3=self.pt.bias if self.pt.bias is not None else _zeros(cout, device))
+        self.fusable = (self.dw.ks == 3 and self.inv.act == self.dw.act == "hswish" and self.pt.act is None)
 
     def __call__(self, x):  # x: [B,H,W,C] bf16
+        if self.fusable:
+            y = ops.mbconv_fused(x, stride=self.dw.stride, residual=self.residual, act="hswish", **self.f)
+            if y is not None:
+                return y
+            self.fusable = False  # shape not instantiated: remember and use the unfused native path
         B, H, W, C = x.shape
         mid = self.inv(x.view(-1, C)).view(B, H, W, -1)
         mid = self.dw(mid)

@@ -230,3 +230,31 @@ def litemla_attn(ms, heads2, eps=1e-15):
           ms.data_ptr(), ld, kv.data_ptr(), att.data_ptr(), att.shape[3], B, H * W, heads2,
               float(eps), _stream())
     return att
+
+
+def mbconv_fused(x, w1, s1, b1, wdw, b2, w3, s3, b3, stride, residual, act):
+    """Fused MBConv (expand -> dw3x3 -> project [+x]); returns None when the shape is not instantiated."""
+    global launch_count
+    _chk(x, torch.bfloat16, "x")
+    _ensure_init(x)
+    assert x.is_contiguous()
+    B, H, W, Cin = x.shape
+    Mid, Cout = w1.shape[0], w3.shape[0]
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
+    args = (x.data_ptr(), y.data_ptr(), w1.data_ptr(), s1.data_ptr(), b1.data_ptr(), wdw.data_ptr(), b2.data_ptr(),
+            w3.data_ptr(), s3.data_ptr(), b3.data_ptr(), B, H, W, Cin, Mid, Cout, stride, int(residual), ACT[act],
+            _stream())
+    prof = _profiler
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = _lib.call_rc("es3_mbconv_fused_bf16", *args)
+    if rc < 0:
+        return None
+    launch_count += 1
+    if prof is not None:
+        e1.record()
+        flops = 2 * B * (H * W * Cin * Mid + Ho * Wo * Mid * (9 + Cout))
+        prof.records.append((f"mbconv_fused[{Cin}-{Mid}-{Cout},s{stride}]", e0, e1, _nb(x, y), flops))
+    return y

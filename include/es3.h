@@ -68,6 +68,16 @@ int es3_dwconv_tiled_bf16(const void* x, long long ldx, const float* w, const fl
 int es3_dsconv_res_bf16(const void* x, const float* wdw, const float* bdw, const float* wpw, const float* bpw,
                         void* out, int B, int H, int W, int C, int act, void* stream);
 
+/* Whole MBConv block in one kernel: y = [x +] BN3(pw2(act(BN2(dw3x3_s(act(BN1(pw1(x)))))))) with the 4x-expanded
+ * tensor kept in shared memory (mma.sync expand/project around an fp32 depthwise).  w1 [Mid][Cin], w3 [Cout][Mid]
+ * bf16; s1,b1,b2 [Mid], s3,b3 [Cout] fp32 (BN folded; ones/zeros where the reference has bias-only convs);
+ * wdw [9][Mid] fp32.  Returns -1 (no error set) when the shape is not instantiated -- the caller then runs
+ * es3_gemm_bf16 + es3_dwconv_tiled_bf16.  Replaces MBConv inside ResidualBlock (efficientvit/nn/ops.py:315-367,
+ * 740-770) for efficientvit_b1 stages 1-3 heads. */
+int es3_mbconv_fused_bf16(const void* x, void* y, const void* w1, const float* s1, const float* b1, const float* wdw,
+                          const float* b2, const void* w3, const float* s3, const float* b3, int B, int H, int W,
+                          int Cin, int Mid, int Cout, int stride, int residual, int act, void* stream);
+
 /* Bilinear (align_corners=False) NHWC bf16 -> NCHW fp32.  Replaces F.interpolate at stage1/model.py:204-210. */
 int es3_bilinear_nhwc_to_nchw(const void* in, float* out, int B, int Hi, int Wi, int C, int Ho, int Wo, void* stream);
 /* Layout conversions at the module boundary. */

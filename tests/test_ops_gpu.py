@@ -191,3 +191,39 @@ def test_cpu_tensor_is_an_error():
     from efficientsam3_b200 import _lib, ops
     with pytest.raises(_lib.Es3Error):
         ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(32, 8, dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("cin,mid,cout,stride,res,H,W", [
+    (16, 64, 32, 2, False, 64, 64), (32, 128, 32, 1, True, 40, 48), (32, 128, 64, 2, False, 33, 47),
+    (64, 256, 64, 1, True, 31, 17), (64, 256, 128, 2, False, 64, 64), (16, 64, 32, 2, False, 63, 65)])
+def test_mbconv_fused(cuda, cin, mid, cout, stride, res, H, W):
+    """One-kernel MBConv vs the op-by-op fp32 statement (intermediates rounded to bf16 where the unfused
+    native path would materialise them)."""
+    from efficientsam3_b200 import ops
+    g = torch.Generator().manual_seed(cin + mid + H)
+    B = 2
+    x = _bf(torch.randn(B, H, W, cin, generator=g)).to(cuda)
+    w1 = _bf(torch.randn(mid, cin, generator=g) / math.sqrt(cin)).to(cuda)
+    s1 = (torch.rand(mid, generator=g) + 0.5).to(cuda); b1 = (torch.randn(mid, generator=g) * 0.2).to(cuda)
+    wdw = (torch.randn(mid, 1, 3, 3, generator=g) / 3).to(cuda); b2 = (torch.randn(mid, generator=g) * 0.2).to(cuda)
+    w3 = _bf(torch.randn(cout, mid, generator=g) / math.sqrt(mid)).to(cuda)
+    s3 = (torch.rand(cout, generator=g) + 0.5).to(cuda); b3 = (torch.randn(cout, generator=g) * 0.2).to(cuda)
+    y = ops.mbconv_fused(x, w1, s1, b1, wdw.reshape(mid, 9).t().contiguous(), b2, w3, s3, b3, stride, res, "hswish")
+    assert y is not None
+    xn = x.float().permute(0, 3, 1, 2)
+    e = F.hardswish(F.conv2d(xn, w1.float()[:, :, None, None]) * s1.view(1, -1, 1, 1) + b1.view(1, -1, 1, 1))
+    e = e.to(torch.bfloat16).float()
+    d = F.hardswish(F.conv2d(e, wdw, b2, stride=stride, padding=1, groups=mid)).to(torch.bfloat16).float()
+    ref = F.conv2d(d, w3.float()[:, :, None, None]) * s3.view(1, -1, 1, 1) + b3.view(1, -1, 1, 1)
+    if res:
+        ref = ref + xn
+    _close(y, ref.permute(0, 2, 3, 1), 1e-2, "mbconv_fused")
+
+
+def test_mbconv_fused_uninstantiated_shape_returns_none(cuda):
+    from efficientsam3_b200 import ops
+    x = torch.zeros(1, 8, 8, 48, device=cuda, dtype=torch.bfloat16)
+    z = lambda *s: torch.zeros(*s, device=cuda)
+    y = ops.mbconv_fused(x, z(192, 48).bfloat16(), z(192), z(192), z(9, 192), z(192), z(48, 192).bfloat16(), z(48), z(48),
+                         1, True, "hswish")
+    assert y is None
