@@ -38,6 +38,11 @@ struct GemmArgs {
   void* out;
   long long ldo;
   int out_f32;
+  int res_f32;          // residual is fp32 (the ViT residual stream) instead of bf16
+  // 2-D axial RoPE fused into the QKV projection epilogue (vitdet.py:68-90, 421-457): columns
+  // [0, rope_cols) are (q | k) heads of 64 dims = 32 complex pairs; rope: [positions][32] (cos, sin).
+  const float2* rope;
+  int rope_cols, rope_H, rope_W, rope_win;
 };
 
 constexpr int BM = 128;
@@ -192,7 +197,29 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
           f[4 * j + 2] = es3_act_t<ACT>(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, bi.z));
           f[4 * j + 3] = es3_act_t<ACT>(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, bi.w));
         }
-        if (args.residual != nullptr) {
+        if (args.rope != nullptr && nb < args.rope_cols) {
+          const int t = (int)(row_off % ((long long)args.rope_H * args.rope_W));
+          const int h = t / args.rope_W, w = t - h * args.rope_W;
+          const int pidx = args.rope_win ? (h % args.rope_win) * args.rope_win + (w % args.rope_win) : t;
+          const float4* tp = reinterpret_cast<const float4*>(args.rope + (long long)pidx * 32 + ((nb & 63) >> 1));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 cs = __ldg(tp + j);  // (cos, sin) of two consecutive pairs
+            const float x0 = f[4 * j], x1 = f[4 * j + 1], x2 = f[4 * j + 2], x3 = f[4 * j + 3];
+            f[4 * j] = x0 * cs.x - x1 * cs.y;
+            f[4 * j + 1] = x0 * cs.y + x1 * cs.x;
+            f[4 * j + 2] = x2 * cs.z - x3 * cs.w;
+            f[4 * j + 3] = x2 * cs.w + x3 * cs.z;
+          }
+        }
+        if (args.residual != nullptr && args.res_f32) {
+          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(args.residual) + row_off * args.ldr + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r4 = __ldg(rp + j);
+            f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+          }
+        } else if (args.residual != nullptr) {
           const uint4* rp = reinterpret_cast<const uint4*>(args.residual + row_off * args.ldr + nb);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -312,13 +339,30 @@ static int dispatch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 
 using namespace es3;
 
+extern "C" int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
+                                int out_f32, int M, int N, int K, const float* scale, const float* bias, int act,
+                                const void* residual, long long ldr, int res_f32, const float* rope, int rope_cols,
+                                int rope_H, int rope_W, int rope_win, int bn_hint, void* stream);
+
 extern "C" int es3_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
                              int out_f32, int M, int N, int K, const float* scale, const float* bias, int act,
                              const void* residual, long long ldr, int bn_hint, void* stream) {
+  return es3_gemm_bf16_ex(A, lda, W, ldw, out, ldo, out_f32, M, N, K, scale, bias, act, residual, ldr, 0, nullptr, 0, 0,
+                          0, 0, bn_hint, stream);
+}
+
+extern "C" int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
+                                int out_f32, int M, int N, int K, const float* scale, const float* bias, int act,
+                                const void* residual, long long ldr, int res_f32, const float* rope, int rope_cols,
+                                int rope_H, int rope_W, int rope_win, int bn_hint, void* stream) {
   ES3_REQUIRE(M > 0 && N > 0 && K > 0, "es3_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+  ES3_REQUIRE(rope == nullptr || (rope_cols % 64 == 0 && rope_cols <= N && rope_H > 0 && rope_W > 0 &&
+                                  M % (rope_H * rope_W) == 0 && ((uintptr_t)rope & 15) == 0),
+              "es3_gemm_bf16_ex: bad rope arguments");
   ES3_REQUIRE(N % 32 == 0, "es3_gemm_bf16: N=%d must be a multiple of 32", N);
   ES3_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "es3_gemm_bf16: K/lda/ldw must be multiples of 8 (16-byte TMA strides)");
   ES3_REQUIRE(ldo % 8 == 0 && (residual == nullptr || ldr % 8 == 0), "es3_gemm_bf16: ldo/ldr must be multiples of 8");
+  ES3_REQUIRE(rope == nullptr || act == ACT_NONE, "es3_gemm_bf16_ex: rope epilogue expects act = none");
   ES3_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
               "es3_gemm_bf16: pointers must be 16-byte aligned");
   const int bn = pick_bn(N, bn_hint);
@@ -344,7 +388,8 @@ extern "C" int es3_gemm_bf16(const void* A, long long lda, const void* W, long l
   a.tiles_n = N / bn;
   a.conv = 0;
   a.scale = scale; a.bias = bias; a.act = act;
-  a.residual = (const bf16*)residual; a.ldr = ldr;
+  a.residual = (const bf16*)residual; a.ldr = ldr; a.res_f32 = res_f32;
+  a.rope = (const float2*)rope; a.rope_cols = rope_cols; a.rope_H = rope_H; a.rope_W = rope_W; a.rope_win = rope_win;
   a.out = out; a.ldo = ldo; a.out_f32 = out_f32;
   return dispatch(bn, tmA, tmB, a, ceil_div(M, BM), (cudaStream_t)stream);
 }

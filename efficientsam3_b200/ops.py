@@ -83,9 +83,11 @@ def _ensure_init(t: torch.Tensor):
     _lib.init(t.device.index or 0)
 
 
-def gemm(a, w, *, scale=None, bias=None, act=None, residual=None, out=None, out_dtype=torch.bfloat16, bn_hint=0):
+def gemm(a, w, *, scale=None, bias=None, act=None, residual=None, out=None, out_dtype=torch.bfloat16, bn_hint=0,
+         rope=None):
     """out[m,n] = act(scale[n]*sum_k a[m,k] w[n,k] + bias[n]) (+residual).  a: [M,K] (row stride allowed),
-    w: [N,K] bf16, scale/bias fp32 [N]."""
+    w: [N,K] bf16, scale/bias fp32 [N]; residual bf16 or fp32 [M,N].
+    rope = (table[P,32,2] fp32, rope_cols, H, W, win): rotate columns [0, rope_cols) (see es3_gemm_bf16_ex)."""
     _chk(a, torch.bfloat16, "a"); _chk(w, torch.bfloat16, "w")
     _ensure_init(a)
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
@@ -258,3 +260,49 @@ def mbconv_fused(x, w1, s1, b1, wdw, b2, w3, s3, b3, stride, residual, act):
         flops = 2 * B * (H * W * Cin * Mid + Ho * Wo * Mid * (9 + Cout))
         prof.records.append((f"mbconv_fused[{Cin}-{Mid}-{Cout},s{stride}]", e0, e1, _nb(x, y), flops))
     return y
+
+
+def layernorm(x, gamma, beta, eps=1e-5, *, pos=None, pos_size=0, H=0, W=0, out_bf16=True, out_f32=False):
+    """x: [M, C] fp32 -> (bf16 [M,C] | None, fp32 [M,C] | None); optional tiled abs-pos add before the norm."""
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    assert x.dim() == 2 and x.is_contiguous()
+    M, C = x.shape
+    yb = torch.empty((M, C), device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    yf = torch.empty((M, C), device=x.device, dtype=torch.float32) if out_f32 else None
+    _call("es3_layernorm_f32", "layernorm", _nb(x, yb, yf), 8 * M * C, x.data_ptr(), _ptr(pos), pos_size, H, W,
+          gamma.data_ptr(), beta.data_ptr(), float(eps), _ptr(yb), _ptr(yf), M, C, _stream())
+    return yb, yf
+
+
+def im2col_patch(x, P, Kp):
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    x = x.contiguous()
+    B, _, S, _ = x.shape
+    n = (S // P) ** 2
+    cols = torch.empty((B * n, Kp), device=x.device, dtype=torch.bfloat16)
+    _call("es3_im2col_patch", "im2col_patch", _nb(x, cols), 0, x.data_ptr(), cols.data_ptr(), B, S, P, Kp, _stream())
+    return cols
+
+
+def attention(qkv, B, H, W, C, num_heads, win, scale):
+    """qkv: [B*H*W, 3C] bf16 -> [B*H*W, C] bf16."""
+    _chk(qkv, torch.bfloat16, "qkv")
+    _ensure_init(qkv)
+    assert qkv.is_contiguous() and qkv.shape == (B * H * W, 3 * C)
+    out = torch.empty((B * H * W, C), device=qkv.device, dtype=torch.bfloat16)
+    L = win * win if win else H * W
+    _call("es3_attention_bf16", f"attention[L={L}]", _nb(qkv, out), 4 * B * H * W * L * C, qkv.data_ptr(), out.data_ptr(),
+          B, H, W, C, num_heads, win, float(scale), _stream())
+    return out
+
+
+def tokens_f32_to_nchw(x, B, H, W):
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    out = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
+    _call("es3_tokens_f32_to_nchw", "tokens_to_nchw", _nb(x, out), 0, x.data_ptr(), out.data_ptr(), B, H * W, C, _stream())
+    return out

@@ -60,6 +60,55 @@ class ImageStudentEncoder(nn.Module, NativePlanMixin):
         return ops.nhwc_to_nchw_f32(y)
 
 
+def build_image_teacher_model(config):
+    """stage1/model.py:168-175.  `config.MODEL.RESUME` (optional) is a reference SAM3 checkpoint."""
+    checkpoint = getattr(config.MODEL, "RESUME", None) or None
+    teacher = SAM3ImageTeacherEncoder(checkpoint_path=checkpoint, embed_size=config.DISTILL.EMBED_SIZE)
+    teacher.img_size = config.DATA.IMG_SIZE
+    return teacher
+
+
+class _Holder(nn.Module):
+    """Attribute container that reproduces the reference's key prefix `sam3.backbone.vision_backbone.trunk.`"""
+
+
+class SAM3ImageTeacherEncoder(nn.Module):
+    """stage1/model.py:214-249: frozen SAM3 ViT trunk -> [B,1024,72,72].  Only the trunk is instantiated (the
+    reference builds the whole SAM3 model and then uses nothing else on this path); a full reference checkpoint
+    loads with strict=False through the preserved key prefix."""
+
+    def __init__(self, checkpoint_path=None, embed_size=64, vit_overrides=None):
+        super().__init__()
+        from ..model.vitdet import create_sam3_vit_backbone
+        self.embed_size = embed_size
+        self.sam3 = _Holder()
+        self.sam3.backbone = _Holder()
+        self.sam3.backbone.vision_backbone = _Holder()
+        self.sam3.backbone.vision_backbone.trunk = create_sam3_vit_backbone(**(vit_overrides or {}))
+        if checkpoint_path:
+            sd = torch.load(checkpoint_path, map_location="cpu")
+            sd = sd.get("model", sd)
+            # reference checkpoints prefix the image model with "detector." (model_builder.py:584-630)
+            sd = {("sam3." + k[len("detector."):] if k.startswith("detector.") else k): v for k, v in sd.items()}
+            own = set(self.state_dict().keys())
+            self.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+        for p in self.parameters():
+            p.requires_grad = False
+        self.eval()
+        self.img_size = 1008
+
+    def train(self, mode: bool = True):  # frozen teacher: always eval (stage1/model.py:226-227)
+        return super().train(False)
+
+    @torch.no_grad()
+    def forward(self, x):
+        feats = self.sam3.backbone.vision_backbone.trunk(x)[-1]
+        if feats.shape[-1] != self.embed_size or feats.shape[-2] != self.embed_size:
+            raise NotImplementedError("teacher output resize (stage1/model.py:241-248) is not built: the shipped "
+                                      "configs use EMBED_SIZE 72 with 1008px inputs, where it is a no-op")
+        return feats
+
+
 class EfficientViTAdapter(nn.Module):
     def __init__(self, model):
         super().__init__()

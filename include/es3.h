@@ -35,6 +35,16 @@ int es3_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, vo
                   int M, int N, int K, const float* scale, const float* bias, int act, const void* residual,
                   long long ldr, int bn_hint, void* stream);
 
+/* Extended epilogue: fp32 residual (res_f32 = 1: the ViT residual stream stays fp32), and 2-D axial RoPE applied to
+ * columns [0, rope_cols) (the q|k part of a fused QKV projection, heads of 64) before rounding -- rope is a
+ * [positions][32] table of (cos, sin) float pairs, position = raster index of the token inside its
+ * rope_win x rope_win window (rope_win > 0) or inside the rope_H x rope_W map (rope_win = 0).
+ * Replaces Attention.qkv + apply_rotary_enc (vitdet.py:68-90, 480-486). */
+int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_f32,
+                     int M, int N, int K, const float* scale, const float* bias, int act, const void* residual,
+                     long long ldr, int res_f32, const float* rope, int rope_cols, int rope_H, int rope_W, int rope_win,
+                     int bn_hint, void* stream);
+
 /* Dense 3x3 / stride 1 / pad 1 conv as an implicit tcgen05 GEMM (halo via TMA zero fill).
  * x [B,H,W,C] bf16 NHWC; W [N][9*C] with k = (ky*3+kx)*C + c; out [B,H,W,N].
  * Replaces head.3 = nn.Conv2d(1024,1024,3,padding=1) (stage1/model.py:198) and the FPN 3x3s (necks.py). */
@@ -97,6 +107,23 @@ int es3_litemla_aggreg_tiled(void* ms, long long ld, const float* wdw, const flo
 long long es3_litemla_ws_floats(int B, int HW, int heads2);
 int es3_litemla_attn(const void* ms, long long ld, float* kv_ws, void* att, long long ldo, int B, int HW, int heads2,
                      float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------ ViT trunk */
+/* LayerNorm over C (C % 128 == 0) of fp32 rows, optional tiled abs-pos add first (pos [pos_size^2, C], token
+ * (h, w) uses entry (h % pos_size, w % pos_size)); writes bf16 and/or fp32.  Replaces nn.LayerNorm in Block
+ * (vitdet.py:597-613) and get_abs_pos(tiling) + ln_pre (vitdet.py:205-214, 820-828). */
+int es3_layernorm_f32(const float* x, const float* pos, int pos_size, int H, int W, const float* gamma,
+                      const float* beta, float eps, void* y_bf16, float* y_f32, long long M, int C, void* stream);
+/* Patch-embedding im2col: x [B,3,S,S] fp32 -> [B*(S/P)^2, Kp] bf16, column = c*P*P + ky*P + kx, zero padded to Kp.
+ * With es3_gemm_bf16 this replaces PatchEmbed.proj (vitdet.py:299-336). */
+int es3_im2col_patch(const float* x, void* cols, int B, int S, int P, int Kp, void* stream);
+/* Softmax attention, head_dim 64, inside win x win windows (win > 0) or global (win = 0), on the fused qkv
+ * activation [B*H*W, 3C] bf16 -> [B*H*W, C] bf16; windows are gathered in place (no partition copies).
+ * Replaces window_partition + F.scaled_dot_product_attention + window_unpartition (vitdet.py:93-139, 502). */
+int es3_attention_bf16(const void* qkv, void* out, int B, int H, int W, int C, int num_heads, int win, float scale,
+                       void* stream);
+/* [B, HW, C] fp32 tokens -> [B, C, HW] fp32 (the NCHW map ViT.forward returns, vitdet.py:846-857). */
+int es3_tokens_f32_to_nchw(const float* in, float* out, int B, int HW, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,31 @@ def gen_student(backbone, tag, img, embed, seed_w, seed_x, batch=1):
           "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+VIT_SMALL = dict(img_size=112, pretrain_img_size=56, patch_size=14, embed_dim=256, depth=4, num_heads=4, mlp_ratio=4.625,
+                 window_size=4, global_att_blocks=(1, 3))
+
+
+def gen_vit(tag, cfg, seed_w, seed_x, batch):
+    """Reference ViT class (sam3/sam3/model/vitdet.py) in the SAM3 configuration family, small dims."""
+    from sam3.model.vitdet import ViT
+
+    m = ViT(norm_layer="LayerNorm", drop_path_rate=0.1, qkv_bias=True, use_abs_pos=True, tile_abs_pos=True,
+            rel_pos_blocks=(), use_rope=True, use_interp_rope=True, pretrain_use_cls_token=True, retain_cls_token=False,
+            ln_pre=True, ln_post=False, return_interm_layers=False, bias_patch_embed=False, **cfg).eval()
+    sd = fill_state_dict(m.state_dict(), seed_w)
+    m.load_state_dict(sd)
+    x = torch.randn(batch, 3, cfg["img_size"], cfg["img_size"], generator=torch.Generator().manual_seed(seed_x))
+    out = m(x)[-1]
+    path = os.path.join(HERE, f"{tag}.npz")
+    np.savez_compressed(path, out=out.numpy(), keys=keyshapes(m.state_dict()), seed_w=seed_w, seed_x=seed_x, batch=batch,
+                        n_params=sum(p.numel() for p in m.parameters()), cfg=np.array(repr(cfg)))
+    print(tag, "out", tuple(out.shape), "absmean %.4f" % out.abs().mean().item(), "->", path,
+          "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 def main(which):
+    if which in ("vit", "all"):
+        gen_vit("vit_small_112", VIT_SMALL, seed_w=21, seed_x=3, batch=2)
     if which in ("evm", "all"):
         # 160x160: stage3 10x10, stage4 5x5 (> dim=16 pixels so the linear-attention branch runs, odd size
         # exercises the stride-2 padding), head 5x5 -> bilinear to 12x12.

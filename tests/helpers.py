@@ -19,7 +19,9 @@ def sd_from_keys(keys, seed):
         k, shp, dt = str(rec).split("|")
         shape = tuple(int(s) for s in shp.split(",")) if shp else ()
         sd[k] = torch.zeros(shape, dtype=getattr(torch, dt))
-    return fill_state_dict(sd, seed)
+    sd = fill_state_dict(sd, seed)
+    # complex buffers (ViT freqs_cis) are derived constants, not weights: the modules compute them
+    return {k: v for k, v in sd.items() if not v.is_complex()}
 
 
 def rel_l2(got, ref):

@@ -15,13 +15,7 @@ def _load(name):
     return np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)
 
 
-def _sd_from_keys(keys, seed):
-    sd = {}
-    for rec in keys:
-        k, shp, dt = str(rec).split("|")
-        shape = tuple(int(s) for s in shp.split(",")) if shp else ()
-        sd[k] = torch.zeros(shape, dtype=getattr(torch, dt))
-    return fill_state_dict(sd, seed)
+from helpers import sd_from_keys as _sd_from_keys
 
 
 def _assert_close(got, ref, rtol=1e-5):
@@ -47,3 +41,14 @@ def test_efficientvit_oracle_matches_reference(name):
         np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-6)
     n_params = sum(v.numel() for k, v in sd.items() if "running_" not in k and "num_batches" not in k)
     assert n_params == int(g["n_params"])
+
+
+def test_vit_oracle_matches_reference():
+    from oracle import vitdet as O
+    g = _load("vit_small_112")
+    cfg = eval(str(g["cfg"]))
+    sd = _sd_from_keys(g["keys"], int(g["seed_w"]))
+    x = torch.randn(int(g["batch"]), 3, cfg["img_size"], cfg["img_size"], generator=torch.Generator().manual_seed(int(g["seed_x"])))
+    with torch.no_grad():
+        out = O.vit_trunk(sd, "", x, cfg)
+    _assert_close(out.numpy(), g["out"], rtol=2e-5)
