@@ -13,11 +13,12 @@
 //   * dense 3x3 conv as an implicit GEMM (head.3: stage1/model.py:198; FPN neck necks.py) -- the A tile
 //     of tap (dy, dx) is a 4-D TMA box at coordinate (c, w0+dx-1, h0+dy-1, b); TMA zero-fills the halo.
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Structure (persistent CTAs, 128 x BN output tiles, 320 threads):
 //   warp 0   : TMA producer   -- cp.async.bulk.tensor into a STAGES-deep 128B-swizzled smem ring
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16)
-//   warps 2-5: epilogue       -- tcgen05.ld 32x32b -> registers -> scale/bias/act/residual -> global
-// Pipelines: full[s]/empty[s] mbarriers (TMA <-> MMA), tmem_full (MMA -> epilogue).
+//   warps 2-9: epilogue       -- tcgen05.ld 32x32b -> registers -> scale/bias/act/rope/residual -> global
+// Pipelines: full[s]/empty[s] mbarriers (TMA <-> MMA), tmem_full[2]/tmem_empty[2] (MMA <-> epilogue) over a
+// double-buffered TMEM accumulator, so the epilogue of one tile overlaps the main loop of the next.
 #include "ptx.cuh"
 
 namespace es3 {
@@ -56,36 +57,28 @@ struct GemmSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 };
 
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, splitting the column chunks
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
+
+// Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so CTAs that
+// run together share the A row-block in L2).  The accumulator is double-buffered in TMEM (2 x BN columns):
+// the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
 template <int BN, int STAGES, int ACT>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const GemmArgs args, const int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_holder;
-  __shared__ __align__(16) float s_scale[BN];
-  __shared__ __align__(16) float s_bias[BN];
 
   using L = GemmSmem<BN, STAGES>;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  const int n_tile = blockIdx.x % args.tiles_n;
-  const int m_tile = blockIdx.x / args.tiles_n;
-  const int n0 = n_tile * BN;
-
-  // conv tile decomposition
-  int img = 0, h0 = 0, w0 = 0;
-  if (args.conv) {
-    const int per_img = args.tiles_w * args.tiles_h;
-    img = m_tile / per_img;
-    const int t = m_tile % per_img;
-    h0 = (t / args.tiles_w) * args.TH;
-    w0 = (t % args.tiles_w) * args.TW;
-  }
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -95,36 +88,52 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(&tmem_full_bar, 1);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full_bar[s], 1);
+      ptx::mbar_init(&tmem_empty_bar[s], EPI_WARPS);
+    }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(&tmem_base_holder, BN);
+  if (warp == 1) ptx::tmem_alloc(&tmem_base_holder, 2 * BN);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
+  const int per_img = args.tiles_w * args.tiles_h;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < args.num_kb; ++kb) {
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * L::STAGE_BYTES;
-        uint8_t* sb = sa + L::A_BYTES;
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % args.tiles_n) * BN;
+        const int m_tile = tile / args.tiles_n;
+        int img = 0, h0 = 0, w0 = 0;
         if (args.conv) {
-          const int tap = kb / args.kb_per_tap;
-          const int kc = kb - tap * args.kb_per_tap;
-          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-          ptx::tma_load_4d(&tmA, &full_bar[stage], sa, kc * BK, w0 + dx, h0 + dy, img);
-          ptx::tma_load_2d(&tmB, &full_bar[stage], sb, tap * args.Ctap + kc * BK, n0);
-        } else {
-          ptx::tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_tile * BM);
-          ptx::tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+          img = m_tile / per_img;
+          const int t = m_tile % per_img;
+          h0 = (t / args.tiles_w) * args.TH;
+          w0 = (t % args.tiles_w) * args.TW;
         }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if (args.conv) {
+            const int tap = kb / args.kb_per_tap;
+            const int kc = kb - tap * args.kb_per_tap;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            ptx::tma_load_4d(&tmA, &full_bar[stage], sa, kc * BK, w0 + dx, h0 + dy, img);
+            ptx::tma_load_2d(&tmB, &full_bar[stage], sb, tap * args.Ctap + kc * BK, n0);
+          } else {
+            ptx::tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_tile * BM);
+            ptx::tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -133,112 +142,141 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < args.num_kb; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + stage * L::STAGE_BYTES);
-        const uint32_t sb = sa + L::A_BYTES;
-        const uint64_t da = ptx::make_desc_sw128(sa);
-        const uint64_t db = ptx::make_desc_sw128(sb);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+          const uint64_t da = ptx::make_desc_sw128(sa);
+          const uint64_t db = ptx::make_desc_sw128(sb);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the >>4 address field
-          ptx::umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the >>4 address field
+            ptx::umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      ptx::umma_commit(&tmem_full_bar);  // accumulator complete
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int et = threadIdx.x - 64;  // 0..127
-    for (int i = et; i < BN; i += 128) {
-      const int n = n0 + i;
-      s_scale[i] = (args.scale != nullptr && n < args.N) ? args.scale[n] : 1.f;
-      s_bias[i] = (args.bias != nullptr && n < args.N) ? args.bias[n] : 0.f;
-    }
-    // named barrier among the 128 epilogue threads only
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which of the two warps of the quarter: interleaved column chunks
+    const int r = q * 32 + lane;            // row inside the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n0 = (tile % args.tiles_n) * BN;
+      const int m_tile = tile / args.tiles_n;
+      bool valid;
+      long long row_off;
+      if (args.conv) {
+        const int img = m_tile / per_img;
+        const int t = m_tile % per_img;
+        const int h0 = (t / args.tiles_w) * args.TH, w0 = (t % args.tiles_w) * args.TW;
+        const int dy = r / args.TW, dx = r - dy * args.TW;
+        const int h = h0 + dy, w = w0 + dx;
+        valid = (h < args.H) && (w < args.W);
+        row_off = ((long long)img * args.H + h) * args.W + w;
+      } else {
+        const long long m = (long long)m_tile * BM + r;
+        valid = m < args.M;
+        row_off = m;
+      }
 
-    const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;     // row inside the tile
-    bool valid;
-    long long row_off;
-    if (args.conv) {
-      const int dy = r / args.TW, dx = r - dy * args.TW;
-      const int h = h0 + dy, w = w0 + dx;
-      valid = (h < args.H) && (w < args.W);
-      row_off = ((long long)img * args.H + h) * args.W + w;
-    } else {
-      const long long m = (long long)m_tile * BM + r;
-      valid = m < args.M;
-      row_off = m;
-    }
-
-    ptx::mbar_wait(&tmem_full_bar, 0);
-    ptx::tc_fence_after();
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
 
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      ptx::tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (valid && nb < args.N) {
-        float f[32];
-        const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c * 32);
-        const float4* bi4 = reinterpret_cast<const float4*>(s_bias + c * 32);
+      for (int c = half; c < BN / 32; c += 2) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        ptx::tmem_ld_wait();
+        const int nb = n0 + c * 32;
+        if (valid && nb < args.N) {
+          float f[32];
+          if (args.scale != nullptr) {
+            const float4* sc4 = reinterpret_cast<const float4*>(args.scale + nb);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 sc = sc4[j], bi = bi4[j];
-          f[4 * j + 0] = es3_act_t<ACT>(fmaf(__uint_as_float(v[4 * j + 0]), sc.x, bi.x));
-          f[4 * j + 1] = es3_act_t<ACT>(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, bi.y));
-          f[4 * j + 2] = es3_act_t<ACT>(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, bi.z));
-          f[4 * j + 3] = es3_act_t<ACT>(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, bi.w));
-        }
-        if (args.rope != nullptr && nb < args.rope_cols) {
-          const int t = (int)(row_off % ((long long)args.rope_H * args.rope_W));
-          const int h = t / args.rope_W, w = t - h * args.rope_W;
-          const int pidx = args.rope_win ? (h % args.rope_win) * args.rope_win + (w % args.rope_win) : t;
-          const float4* tp = reinterpret_cast<const float4*>(args.rope + (long long)pidx * 32 + ((nb & 63) >> 1));
+            for (int j = 0; j < 8; ++j) {
+              const float4 sc = __ldg(sc4 + j);
+              f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) * sc.x;
+              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) * sc.y;
+              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) * sc.z;
+              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) * sc.w;
+            }
+          } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 cs = __ldg(tp + j);  // (cos, sin) of two consecutive pairs
-            const float x0 = f[4 * j], x1 = f[4 * j + 1], x2 = f[4 * j + 2], x3 = f[4 * j + 3];
-            f[4 * j] = x0 * cs.x - x1 * cs.y;
-            f[4 * j + 1] = x0 * cs.y + x1 * cs.x;
-            f[4 * j + 2] = x2 * cs.z - x3 * cs.w;
-            f[4 * j + 3] = x2 * cs.w + x3 * cs.z;
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           }
-        }
-        if (args.residual != nullptr && args.res_f32) {
-          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(args.residual) + row_off * args.ldr + nb);
+          if (args.bias != nullptr) {
+            const float4* bi4 = reinterpret_cast<const float4*>(args.bias + nb);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 r4 = __ldg(rp + j);
-            f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+            for (int j = 0; j < 8; ++j) {
+              const float4 bi = __ldg(bi4 + j);
+              f[4 * j + 0] += bi.x; f[4 * j + 1] += bi.y; f[4 * j + 2] += bi.z; f[4 * j + 3] += bi.w;
+            }
           }
-        } else if (args.residual != nullptr) {
-          const uint4* rp = reinterpret_cast<const uint4*>(args.residual + row_off * args.ldr + nb);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float rf[8];
-            unpack8(__ldg(rp + j), rf);
+          for (int j = 0; j < 32; ++j) f[j] = es3_act_t<ACT>(f[j]);
+          if (args.rope != nullptr && nb < args.rope_cols) {
+            const int t = (int)(row_off % ((long long)args.rope_H * args.rope_W));
+            const int h = t / args.rope_W, w = t - h * args.rope_W;
+            const int pidx = args.rope_win ? (h % args.rope_win) * args.rope_win + (w % args.rope_win) : t;
+            const float4* tp = reinterpret_cast<const float4*>(args.rope + (long long)pidx * 32 + ((nb & 63) >> 1));
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[j * 8 + e] += rf[e];
+            for (int j = 0; j < 8; ++j) {
+              const float4 cs = __ldg(tp + j);  // (cos, sin) of two consecutive pairs
+              const float x0 = f[4 * j], x1 = f[4 * j + 1], x2 = f[4 * j + 2], x3 = f[4 * j + 3];
+              f[4 * j] = x0 * cs.x - x1 * cs.y;
+              f[4 * j + 1] = x0 * cs.y + x1 * cs.x;
+              f[4 * j + 2] = x2 * cs.z - x3 * cs.w;
+              f[4 * j + 3] = x2 * cs.w + x3 * cs.z;
+            }
           }
-        }
-        if (args.out_f32) {
-          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + row_off * args.ldo + nb);
+          if (args.residual != nullptr && args.res_f32) {
+            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(args.residual) + row_off * args.ldr + nb);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(args.out) + row_off * args.ldo + nb);
+            for (int j = 0; j < 8; ++j) {
+              const float4 r4 = __ldg(rp + j);
+              f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+            }
+          } else if (args.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(args.residual + row_off * args.ldr + nb);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) op[j] = pack8(f + 8 * j);
+            for (int j = 0; j < 4; ++j) {
+              float rf[8];
+              unpack8(__ldg(rp + j), rf);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[j * 8 + e] += rf[e];
+            }
+          }
+          if (args.out_f32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + row_off * args.ldo + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(args.out) + row_off * args.ldo + nb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = pack8(f + 8 * j);
+          }
+
         }
       }
+      // this warp is done reading the accumulator: hand it back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -246,7 +284,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, BN);
+    ptx::tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -299,8 +337,17 @@ static int launch_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
                                         L::TOTAL));
     configured = true;
   }
-  dim3 grid((unsigned)(tiles_m * args.tiles_n));
-  gemm_tc_kernel<BN, STAGES, ACT><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, args);
+  const int num_tiles = tiles_m * args.tiles_n;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    ES3_CHECK_CUDA(cudaGetDevice(&dev));
+    ES3_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // BN = 256 uses all 512 TMEM columns and ~193 KB of smem: one CTA per SM.  Narrower tiles fit two.
+  const int ctas = sm_count * (BN == 256 ? 1 : 2);
+  dim3 grid((unsigned)(num_tiles < ctas ? num_tiles : ctas));
+  gemm_tc_kernel<BN, STAGES, ACT><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, args, num_tiles);
   ES3_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -317,12 +364,14 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs
   }
 }
 
+// Tile width: N need not be a multiple of BN (TMA zero-fills weight rows >= N, the epilogue masks 32-column
+// chunks), so take 256 whenever the padding waste is small -- it halves the smem operand traffic per MMA.
 static int pick_bn(int N, int bn_hint) {
   if (bn_hint == 32 || bn_hint == 64 || bn_hint == 128 || bn_hint == 256) return bn_hint;
-  if (N % 256 == 0 && N >= 512) return 256;
-  if (N % 128 == 0) return 128;
+  if (N >= 512 && (ceil_div(N, 256) * 256 - N) * 16 <= N) return 256;   // <= 6.25 % padded columns
+  if (N % 128 == 0 || N > 1024) return 128;
   if (N % 64 == 0) return 64;
-  return 32;
+  return N >= 128 ? 128 : 32;
 }
 
 static int dispatch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int tiles_m,
@@ -366,7 +415,6 @@ extern "C" int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, lon
   ES3_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
               "es3_gemm_bf16: pointers must be 16-byte aligned");
   const int bn = pick_bn(N, bn_hint);
-  ES3_REQUIRE(N % bn == 0, "es3_gemm_bf16: N=%d not a multiple of tile %d", N, bn);
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -385,7 +433,7 @@ extern "C" int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, lon
   a.M = M; a.N = N;
   a.num_kb = ceil_div(K, BK);
   a.kb_per_tap = a.num_kb;
-  a.tiles_n = N / bn;
+  a.tiles_n = ceil_div(N, bn);
   a.conv = 0;
   a.scale = scale; a.bias = bias; a.act = act;
   a.residual = (const bf16*)residual; a.ldr = ldr; a.res_f32 = res_f32;
@@ -402,7 +450,6 @@ extern "C" int es3_conv3x3_bf16(const void* x, const void* W, void* out, int out
   ES3_REQUIRE(B > 0 && H > 0 && Wd > 0, "es3_conv3x3_bf16: bad shape");
   ES3_REQUIRE(C % 8 == 0 && N % 32 == 0, "es3_conv3x3_bf16: need C %% 8 == 0 and N %% 32 == 0 (C=%d N=%d)", C, N);
   const int bn = pick_bn(N, bn_hint);
-  ES3_REQUIRE(N % bn == 0, "es3_conv3x3_bf16: N=%d not a multiple of tile %d", N, bn);
   int TW = 8;
   if (Wd % 32 == 0) TW = 32; else if (Wd % 16 == 0) TW = 16;
   const int TH = BM / TW;
@@ -424,7 +471,7 @@ extern "C" int es3_conv3x3_bf16(const void* x, const void* W, void* out, int out
   a.M = B * H * Wd; a.N = N;
   a.kb_per_tap = ceil_div(C, BK);
   a.num_kb = 9 * a.kb_per_tap;
-  a.tiles_n = N / bn;
+  a.tiles_n = ceil_div(N, bn);
   a.conv = 1;
   a.H = H; a.W = Wd; a.TW = TW; a.TH = TH;
   a.tiles_w = ceil_div(Wd, TW); a.tiles_h = ceil_div(H, TH);

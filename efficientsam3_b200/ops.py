@@ -97,13 +97,22 @@ def gemm(a, w, *, scale=None, bias=None, act=None, residual=None, out=None, out_
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype)
     assert out.stride(1) == 1 and out.shape == (M, N)
+    res_f32 = 0
     if residual is not None:
-        _chk(residual, torch.bfloat16, "residual")
+        assert residual.is_cuda and residual.dtype in (torch.bfloat16, torch.float32)
         assert residual.stride(1) == 1 and residual.shape == (M, N)
-    _call("es3_gemm_bf16", f"gemm_tc[K={K},N={N}]", M * K * 2 + M * N * out.element_size() + _nb(w, residual),
+        res_f32 = int(residual.dtype == torch.float32)
+    if rope is not None:
+        tab, rcols, rH, rW, rwin = rope
+        _chk(tab, torch.float32, "rope table")
+        assert tab.is_contiguous() and tab.shape[1:] == (32, 2)
+        rargs = (tab.data_ptr(), rcols, rH, rW, rwin)
+    else:
+        rargs = (0, 0, 0, 0, 0)
+    _call("es3_gemm_bf16_ex", f"gemm_tc[K={K},N={N}]", M * K * 2 + M * N * out.element_size() + _nb(w, residual),
           2 * M * N * K, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
-              int(out.dtype == torch.float32), M, N, K, _ptr(scale), _ptr(bias), ACT[act], _ptr(residual),
-              residual.stride(0) if residual is not None else 0, bn_hint, _stream())
+          int(out.dtype == torch.float32), M, N, K, _ptr(scale), _ptr(bias), ACT[act], _ptr(residual),
+          residual.stride(0) if residual is not None else 0, res_f32, *rargs, bn_hint, _stream())
     return out
 
 
