@@ -1,0 +1,46 @@
+"""CPU, world_size 2, gloo: the N>1 host logic of bench.py -- rank-sharded synthetic inputs, barrier, and the
+max-over-ranks reduction of the timed region.  (The data path itself has no collective: SURVEY.md section 8e.)"""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(1234 + rank)                  # bench.py: per-rank input seed
+    x = torch.randn(2, 3, 8, 8, generator=g)
+    ms = torch.tensor([10.0 + 5.0 * rank])                          # pretend device time of this rank
+    dist.barrier()
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    chk = torch.tensor([x.sum().item()])
+    allc = [torch.zeros(1) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    q.put((rank, ms.item(), [c.item() for c in allc]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_max_time_and_distinct_shards():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in ps]
+    assert all(r[1] == 15.0 for r in res)                           # max over ranks
+    assert res[0][2] == res[1][2] and res[0][2][0] != res[0][2][1]  # ranks hold different images
+    B, steps = 32, 20
+    value = world * B * steps / (res[0][1] * steps / 1e3)           # whole-job images/s as bench.py computes it
+    assert abs(value - world * B / 15e-3) < 1e-6
