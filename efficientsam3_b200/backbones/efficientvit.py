@@ -198,6 +198,7 @@ class _LiteMLAPlan:
         dw, pw = m.aggreg[0][0], m.aggreg[0][1]
         self.agg_dw = dw_weight(dw, None)                                         # [25, C3] fp32
         self.agg_pw = pw.weight.detach().float().reshape(self.c3, 16).contiguous()  # [C3, 16] fp32
+        self.wcomb = ops.litemla_wcomb(self.agg_dw, self.agg_pw)                    # [C3/16, 25, 16, 16] bf16
         self.proj = _PW(m.proj, device)
         self.heads2 = 2 * m.heads
         self.eps = m.eps
@@ -210,7 +211,7 @@ class _LiteMLAPlan:
         ms = torch.empty((B, H, W, 2 * self.c3), device=x.device, dtype=torch.bfloat16)
         ms2d = ms.view(-1, 2 * self.c3)
         ops.gemm(x.view(-1, C), self.qkv_w, out=ms2d[:, : self.c3])
-        ops.litemla_aggreg(ms, self.agg_dw, self.agg_pw, self.c3)
+        ops.litemla_aggreg_tc(ms, self.wcomb, self.c3)
         att = ops.litemla_attn(ms, self.heads2, self.eps)
         out = self.proj(att.view(-1, att.shape[-1]), residual=x.view(-1, C))
         return out.view(B, H, W, C)

@@ -18,7 +18,7 @@ def _stream() -> int:
 
 # ------------------------------------------------------------------------------------ accounting
 # kernels launched per C-ABI call (memsets excluded) -- bench.py reports the sum as `gpu_launches`.
-KERNELS_PER_CALL = {"es3_litemla_attn": 2}
+KERNELS_PER_CALL = {"es3_litemla_attn": 2, "es3_litemla_attn_tc": 2}
 launch_count = 0
 
 
@@ -229,7 +229,27 @@ def litemla_aggreg(ms, wdw, wpw, C3, force_simple=False):
     return ms
 
 
-def litemla_attn(ms, heads2, eps=1e-15):
+def litemla_wcomb(wdw, wpw):
+    """Combined aggreg weights: wdw [25, C3] fp32 (tap-major), wpw [C3, 16] fp32 -> [C3/16, 25, 16, 16] bf16."""
+    C3 = wpw.shape[0]
+    G = C3 // 16
+    d = wdw.t().reshape(G, 16, 25)                     # [g][i][tap]
+    w = wpw.reshape(G, 16, 16)                         # [g][n][i]
+    comb = w.unsqueeze(1) * d.permute(0, 2, 1).unsqueeze(2)   # [g][tap][n][i]
+    return comb.to(torch.bfloat16).contiguous()
+
+
+def litemla_aggreg_tc(ms, wcomb, C3):
+    _chk(ms, torch.bfloat16, "ms"); _chk(wcomb, torch.bfloat16, "wcomb")
+    _ensure_init(ms)
+    assert ms.is_contiguous() and wcomb.is_contiguous() and wcomb.shape == (C3 // 16, 25, 16, 16)
+    B, H, W, ld = ms.shape
+    _call("es3_litemla_aggreg_tc", "litemla_aggreg_tc", 2 * B * H * W * C3 * 2, 2 * B * H * W * C3 * 400,
+          ms.data_ptr(), ld, wcomb.data_ptr(), B, H, W, C3, _stream())
+    return ms
+
+
+def litemla_attn(ms, heads2, eps=1e-15, tc=True):
     """ms: [B,H,W,48*heads2] bf16 -> att [B,H,W,16*heads2] bf16."""
     _chk(ms, torch.bfloat16, "ms")
     _ensure_init(ms)
@@ -237,7 +257,7 @@ def litemla_attn(ms, heads2, eps=1e-15):
     B, H, W, ld = ms.shape
     att = torch.empty((B, H, W, 16 * heads2), device=ms.device, dtype=torch.bfloat16)
     kv = torch.empty((B * heads2 * ((H * W + 511) // 512) * 17 * 16,), device=ms.device, dtype=torch.float32)
-    _call("es3_litemla_attn", "litemla_attn", _nb(ms) * 2 // 3 + _nb(ms) // 3 + _nb(att), 2 * B * H * W * heads2 * 17 * 16 * 2,
+    _call("es3_litemla_attn_tc" if tc else "es3_litemla_attn", "litemla_attn_tc" if tc else "litemla_attn", _nb(ms) * 2 // 3 + _nb(ms) // 3 + _nb(att), 2 * B * H * W * heads2 * 17 * 16 * 2,
           ms.data_ptr(), ld, kv.data_ptr(), att.data_ptr(), att.shape[3], B, H * W, heads2,
               float(eps), _stream())
     return att

@@ -102,6 +102,9 @@ int es3_litemla_aggreg(void* ms, long long ld, const float* wdw, const float* wp
 /* Same contract as es3_litemla_aggreg (C3 % 64 == 0): tiled dw5x5 with the grouped 1x1 fused in registers. */
 int es3_litemla_aggreg_tiled(void* ms, long long ld, const float* wdw, const float* wpw, int B, int H, int W, int C3,
                              void* stream);
+/* Tensor-core aggreg: the depthwise 5x5 and the grouped 1x1 are folded into one grouped 5x5 conv,
+ * wcomb [C3/16][25][16][16] bf16 with wcomb[g][tap][n][i] = wpw[g*16+n][i] * wdw[tap][g*16+i] (K = 400 per group). */
+int es3_litemla_aggreg_tc(void* ms, long long ld, const void* wcomb, int B, int H, int W, int C3, void* stream);
 /* ReLU linear attention over the multi-scale qkv buffer (head h = channels [48h,48h+48) = q|k|v, dim 16).
  * kv_ws: es3_litemla_ws_floats(B,HW,heads2) floats of scratch (two-stage deterministic reduction, no atomics).  att [B,HW,ldo] bf16.  Replaces relu_linear_att (ops.py:584-621). */
 long long es3_litemla_ws_floats(int B, int HW, int heads2);
@@ -124,6 +127,10 @@ int es3_attention_bf16(const void* qkv, void* out, int B, int H, int W, int C, i
                        void* stream);
 /* [B, HW, C] fp32 tokens -> [B, C, HW] fp32 (the NCHW map ViT.forward returns, vitdet.py:846-857). */
 int es3_tokens_f32_to_nchw(const float* in, float* out, int B, int HW, int C, void* stream);
+
+/* Same contract as es3_litemla_attn; KV state and the apply step run on mma.sync (KV split hi+lo bf16). */
+int es3_litemla_attn_tc(const void* ms, long long ld, float* kv_ws, void* att, long long ldo, int B, int HW, int heads2,
+                        float eps, void* stream);
 
 #ifdef __cplusplus
 }
