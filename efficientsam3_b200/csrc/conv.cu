@@ -182,44 +182,70 @@ __global__ void dsconv_res_kernel(const bf16* __restrict__ x, const float* __res
 // antialias=False (aten upsample_bilinear2d: src = (dst+0.5)*in/out - 0.5 clamped at 0).
 // grid (Ho, C/64, B), block 256: stage the two source rows of a 64-channel slab in smem, then write
 // rows of Wo contiguous floats.
-__global__ void bilinear_nhwc_to_nchw_kernel(const bf16* __restrict__ in, float* __restrict__ out, int Hi, int Wi, int C,
-                                             int Ho, int Wo, float sy, float sx) {
-  extern __shared__ float srow[];  // [2][Wi][65]
-  const int oy = blockIdx.x, c0 = blockIdx.y * 64, b = blockIdx.z;
-  float fy = (oy + 0.5f) * sy - 0.5f;
-  if (fy < 0.f) fy = 0.f;
-  const int y0 = min((int)fy, Hi - 1);
-  const int y1 = min(y0 + 1, Hi - 1);
-  const float ly = fy - (float)y0;
-  const int nvec = Wi * 8;  // 8 uint4 per pixel per 64 channels
-  for (int i = threadIdx.x; i < 2 * nvec; i += blockDim.x) {
-    const int r = i / nvec, j = i % nvec;
-    const int px = j >> 3, v = j & 7;
-    const int yy = r ? y1 : y0;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + (((long long)b * Hi + yy) * Wi + px) * C + c0 + v * 8));
+// One CTA = one image x 16 channels: the whole Hi x Wi x 16 source slab is staged in smem (fp32), then each
+// output plane [Ho][Wo] is written front to back -- 16 fully sequential Ho*Wo*4-byte streams per CTA (the first
+// version wrote one 256-byte row per plane per CTA and reached only 1.4-1.6 TB/s, profiles/r1_kernel_table_h.md).
+constexpr int BL_CB = 16;
+__global__ void __launch_bounds__(256) bilinear_nhwc_to_nchw_kernel(const bf16* __restrict__ in, float* __restrict__ out,
+                                                                    int Hi, int Wi, int C, int Ho, int Wo, float sy,
+                                                                    float sx) {
+  extern __shared__ float ssrc[];  // [Hi*Wi][17] then x tables [3][Wo], y tables [3][Ho]
+  const int npix = Hi * Wi;
+  int* s_x0 = reinterpret_cast<int*>(ssrc + (long long)npix * (BL_CB + 1));
+  int* s_x1 = s_x0 + Wo;
+  float* s_lx = reinterpret_cast<float*>(s_x1 + Wo);
+  int* s_y0 = reinterpret_cast<int*>(s_lx + Wo);
+  int* s_y1 = s_y0 + Ho;
+  float* s_ly = reinterpret_cast<float*>(s_y1 + Ho);
+  const int c0 = blockIdx.x * BL_CB, b = blockIdx.y;
+  for (int o = threadIdx.x; o < Wo; o += 256) {
+    float f = (o + 0.5f) * sx - 0.5f;
+    if (f < 0.f) f = 0.f;
+    const int i0 = min((int)f, Wi - 1);
+    s_x0[o] = i0; s_x1[o] = min(i0 + 1, Wi - 1); s_lx[o] = f - (float)i0;
+  }
+  for (int o = threadIdx.x; o < Ho; o += 256) {
+    float f = (o + 0.5f) * sy - 0.5f;
+    if (f < 0.f) f = 0.f;
+    const int i0 = min((int)f, Hi - 1);
+    s_y0[o] = i0; s_y1[o] = min(i0 + 1, Hi - 1); s_ly[o] = f - (float)i0;
+  }
+  for (int i = threadIdx.x; i < npix * 2; i += 256) {
+    const int px = i >> 1, v = i & 1;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((long long)b * npix + px) * C + c0 + v * 8));
     float f[8];
     unpack8(u, f);
-    float* d = srow + ((long long)r * Wi + px) * 65 + v * 8;
+    float* d = ssrc + (long long)px * (BL_CB + 1) + v * 8;
 #pragma unroll
     for (int e = 0; e < 8; ++e) d[e] = f[e];
   }
   __syncthreads();
-  const int nout = 64 * Wo;
-  for (int i = threadIdx.x; i < nout; i += blockDim.x) {
-    const int c = i / Wo, ox = i % Wo;
-    if (c0 + c >= C) continue;
-    float fx = (ox + 0.5f) * sx - 0.5f;
-    if (fx < 0.f) fx = 0.f;
-    const int x0 = min((int)fx, Wi - 1);
-    const int x1 = min(x0 + 1, Wi - 1);
-    const float lx = fx - (float)x0;
-    const float v00 = srow[(0 * Wi + x0) * 65 + c], v01 = srow[(0 * Wi + x1) * 65 + c];
-    const float v10 = srow[(1 * Wi + x0) * 65 + c], v11 = srow[(1 * Wi + x1) * 65 + c];
-    // same association order as aten's upsample_bilinear2d CPU kernel:
-    // w00*v00 + w01*v01 + w10*v10 + w11*v11 with w = (1-ly)(1-lx) etc.
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const float val = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
-    out[(((long long)b * C + c0 + c) * Ho + oy) * Wo + ox] = val;
+  const int nq = (Wo + 3) >> 2;
+  const int per_plane = Ho * nq;
+  for (int c = 0; c < BL_CB; ++c) {
+    float* plane = out + ((long long)b * C + c0 + c) * Ho * Wo;
+    const float* sc = ssrc + c;
+    for (int i = threadIdx.x; i < per_plane; i += 256) {
+      const int oy = i / nq, q = i - oy * nq;
+      const float* r0 = sc + (long long)s_y0[oy] * Wi * (BL_CB + 1);
+      const float* r1 = sc + (long long)s_y1[oy] * Wi * (BL_CB + 1);
+      const float ly = s_ly[oy], hy = 1.f - ly;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ox = min(q * 4 + e, Wo - 1);
+        const int x0 = s_x0[ox] * (BL_CB + 1), x1 = s_x1[ox] * (BL_CB + 1);
+        const float lx = s_lx[ox], hx = 1.f - lx;
+        v[e] = hy * (hx * r0[x0] + lx * r0[x1]) + ly * (hx * r1[x0] + lx * r1[x1]);
+      }
+      if ((Wo & 3) == 0) {
+        reinterpret_cast<float4*>(plane + (long long)oy * Wo)[q] = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (q * 4 + e < Wo) plane[(long long)oy * Wo + q * 4 + e] = v[e];
+      }
+    }
   }
 }
 
@@ -326,15 +352,15 @@ extern "C" int es3_dsconv_res_bf16(const void* x, const float* wdw, const float*
 
 extern "C" int es3_bilinear_nhwc_to_nchw(const void* in, float* out, int B, int Hi, int Wi, int C, int Ho, int Wo,
                                          void* stream) {
-  ES3_REQUIRE(C % 64 == 0, "es3_bilinear_nhwc_to_nchw: C=%d must be a multiple of 64", C);
-  const size_t smem = (size_t)2 * Wi * 65 * sizeof(float);
-  ES3_REQUIRE(smem <= 200 * 1024, "es3_bilinear_nhwc_to_nchw: Wi=%d too wide for the smem slab", Wi);
+  ES3_REQUIRE(C % BL_CB == 0, "es3_bilinear_nhwc_to_nchw: C=%d must be a multiple of %d", C, BL_CB);
+  const size_t smem = ((size_t)Hi * Wi * (BL_CB + 1) + 3 * (size_t)(Wo + Ho)) * sizeof(float);
+  ES3_REQUIRE(smem <= 200 * 1024, "es3_bilinear_nhwc_to_nchw: %dx%d source too large for the smem slab", Hi, Wi);
   static bool configured = false;
   if (!configured) {
     ES3_CHECK_CUDA(cudaFuncSetAttribute(bilinear_nhwc_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  dim3 grid(Ho, C / 64, B);
+  dim3 grid(C / BL_CB, B);
   bilinear_nhwc_to_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)in, out, Hi, Wi, C, Ho, Wo,
                                                                            (float)Hi / (float)Ho, (float)Wi / (float)Wo);
   ES3_LAUNCH_CHECK("bilinear_nhwc_to_nchw_kernel");

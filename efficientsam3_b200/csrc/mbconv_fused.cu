@@ -7,8 +7,8 @@
 // 512^2 / 256^2 / 128^2 that is ~85 % of the block's traffic (profiles/r1_kernel_table_c.md: the stage-1/2
 // pointwise GEMMs + depthwise kernels were 4.5 of 11.9 ms).  Here one CTA owns a TH x 16 tile of output
 // pixels: the haloed input tile is staged in shared memory once, and for each 64-channel chunk of the
-// expanded tensor the CTA runs  expand (mma.sync bf16, halo included) -> depthwise 3x3 (fp32 FMA from
-// smem) -> project (mma.sync, fp32 accumulators in registers).  The expanded tensor never leaves the SM;
+// expanded tensor the CTA runs  expand (mma.sync bf16, halo included) -> depthwise 3x3 (mma.sync with
+// diagonal B fragments, bf16 weights, fp32 accumulate) -> project (mma.sync, fp32 accumulators in registers).  The expanded tensor never leaves the SM;
 // HBM traffic is x (+halo) in, y out.
 //
 // These layers are HBM-bound with K = 16..64 contractions; warp-level mma.sync is used on purpose -- a
@@ -50,7 +50,8 @@ struct MBCfg {
   static constexpr int SZ_MID = cmax(P_IN_PAD * RS_MID, P_OUT * RS_OUT);
   static constexpr int SZ_DW = P_OUT * RS_MID;
   static constexpr int SZ_W1 = MC * RS_W1, SZ_W3 = COUT * RS_W3;
-  static constexpr int NF = 9 * MC + 3 * MC + 2 * COUT;  // wdw chunk | scale1 bias1 bias2 chunk | scale3 bias3
+  static constexpr int NBF = 9 * 4 * 2 * 32;             // depthwise B-fragment table (see kernel)
+  static constexpr int NF = NBF + 3 * MC + 2 * COUT;    // bfrag | scale1 bias1 bias2 chunk | scale3 bias3
   static constexpr int SMEM = SZ_IN + SZ_MID + SZ_DW + SZ_W1 + SZ_W3 + NF * 4;
 };
 
@@ -80,8 +81,11 @@ __global__ void __launch_bounds__(256) mbconv_fused_kernel(const MBArgs a) {
   uint8_t* s_w1 = s_dw + C::SZ_DW;
   uint8_t* s_w3 = s_w1 + C::SZ_W1;
   float* s_f = reinterpret_cast<float*>(s_w3 + C::SZ_W3);
-  float* s_wdw = s_f;                 // [9][64]
-  float* s_s1 = s_f + 9 * C::MC;      // [64]
+  // Depthwise on tensor cores: for a 16-channel group the 3x3 depthwise is 9 MMAs with DIAGONAL B
+  // matrices, D[px][c] += A[px+tap][c] * w[tap][c].  A diagonal 16x16 B fragment has at most one non-zero
+  // bf16 per lane, so the table stores the ready-made register: s_bfrag[tap][cg][nt][lane].
+  uint32_t* s_bfrag = reinterpret_cast<uint32_t*>(s_f);   // [9][4][2][32]
+  float* s_s1 = s_f + C::NBF;         // [64]
   float* s_b1 = s_s1 + C::MC;
   float* s_b2 = s_b1 + C::MC;
   float* s_s3 = s_b2 + C::MC;         // [COUT]
@@ -142,7 +146,17 @@ __global__ void __launch_bounds__(256) mbconv_fused_kernel(const MBArgs a) {
         const int r = i >> 3, v = i & 7;
         cp16(s_w3 + r * C::RS_W3 + v * 16, w3c + (long long)r * MID + v * 8, true);
       }
-      for (int i = tid; i < 9 * C::MC; i += 256) s_wdw[i] = a.wdw[(i / C::MC) * MID + ch * C::MC + (i % C::MC)];
+      for (int i = tid; i < C::NBF; i += 256) {
+        const int ln = i & 31, nt = (i >> 5) & 1, cg = (i >> 6) & 3, tap = i >> 8;
+        const int gg = ln >> 2, tt = ln & 3;
+        const float wv = a.wdw[tap * MID + ch * C::MC + cg * 16 + nt * 8 + gg];
+        uint32_t r = 0u;
+        if ((gg >> 1) == tt) {
+          const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(wv));
+          r = (gg & 1) ? (bits << 16) : bits;
+        }
+        s_bfrag[i] = r;
+      }
       for (int i = tid; i < C::MC; i += 256) {
         s_s1[i] = a.s1[ch * C::MC + i];
         s_b1[i] = a.b1[ch * C::MC + i];
@@ -188,48 +202,39 @@ __global__ void __launch_bounds__(256) mbconv_fused_kernel(const MBArgs a) {
     }
     __syncthreads();
 
-    // ---- depthwise 3x3 (stride STRIDE) on the chunk: strips of 4 outputs x 8 channels
+    // ---- depthwise 3x3 (stride STRIDE) on the chunk, on tensor cores (diagonal-B MMAs).
+    // warp -> channel group cg = warp % 4 (16 channels), output rows mt = warp / 4, +2, ... (one m-tile
+    // = the 16 output pixels of a tile row)
     {
-      constexpr int STRIPS = C::P_OUT / 4, ITEMS = STRIPS * 8, WIN = 3 * STRIDE + 3;
-      for (int it = tid; it < ITEMS; it += 256) {
-        const int v = it & 7, sidx = it >> 3;
-        const int sy = sidx / (C::TW / 4), sx = sidx % (C::TW / 4);
-        float o[4][8];
+      const int cg = warp & 3;
+      const uint32_t* bf = s_bfrag + cg * 64 + lane;
+#pragma unroll 1
+      for (int mt = warp >> 2; mt < C::TH; mt += 2) {
+        float d[2][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) o[j][q] = s_b2[v * 8 + q];
+        for (int i = 0; i < 2; ++i) { d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f; }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          float wk[3][8];
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const float4 w0 = *reinterpret_cast<const float4*>(s_wdw + (ky * 3 + kx) * C::MC + v * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(s_wdw + (ky * 3 + kx) * C::MC + v * 8 + 4);
-            wk[kx][0] = w0.x; wk[kx][1] = w0.y; wk[kx][2] = w0.z; wk[kx][3] = w0.w;
-            wk[kx][4] = w1.x; wk[kx][5] = w1.y; wk[kx][6] = w1.z; wk[kx][7] = w1.w;
-          }
-          const uint8_t* rowp = s_mid + ((sy * STRIDE + ky) * C::HWD + sx * 4 * STRIDE) * C::RS_MID + v * 16;
-#pragma unroll
-          for (int col = 0; col < WIN; ++col) {
-            float f[8];
-            unpack8(*reinterpret_cast<const uint4*>(rowp + col * C::RS_MID), f);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int kx = col - j * STRIDE;
-              if (kx >= 0 && kx < 3) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) o[j][q] = fmaf(f[q], wk[kx][q], o[j][q]);
-              }
-            }
+            const uint32_t b_lo = bf[(ky * 3 + kx) * 256], b_hi = bf[(ky * 3 + kx) * 256 + 32];
+            uint32_t af[4];
+            ldsm_x4(u_mid + ((mt * STRIDE + ky) * C::HWD + a_row * STRIDE + kx) * C::RS_MID + (cg * 16 + a_kh * 8) * 2,
+                    af[0], af[1], af[2], af[3]);
+            mma_bf16_16816(d[0], af, b_lo, 0u);
+            mma_bf16_16816(d[1], af, 0u, b_hi);
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int half = 0; half < 2; ++half) {
+          const int p = mt * C::TW + g + half * 8;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) o[j][q] = es3_act_t<ACT>(o[j][q]);
-          const int p = sy * C::TW + sx * 4 + j;
-          *reinterpret_cast<uint4*>(s_dw + p * C::RS_MID + v * 16) = pack8(o[j]);
+          for (int nt = 0; nt < 2; ++nt) {
+            const int c = cg * 16 + nt * 8 + t4 * 2;
+            const float v0 = es3_act_t<ACT>(d[nt][half * 2 + 0] + s_b2[c]);
+            const float v1 = es3_act_t<ACT>(d[nt][half * 2 + 1] + s_b2[c + 1]);
+            *reinterpret_cast<uint32_t*>(s_dw + p * C::RS_MID + c * 2) = pack_bf16x2(v0, v1);
+          }
         }
       }
     }
