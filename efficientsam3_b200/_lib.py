@@ -23,6 +23,16 @@ SIGNATURES: dict[str, list] = {
     "es3_im2col_patch": [_vp, _vp, _i, _i, _i, _i, _vp],
     "es3_attention_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
     "es3_tokens_f32_to_nchw": [_vp, _vp, _i, _i, _i, _vp],
+    "es3_convt2x2_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp],
+    "es3_dense_pe": [_vp, _i, _i, _i, _vp, _vp],
+    "es3_point_embed": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp],
+    "es3_add_rows": [_vp, _vp, _ll, _i, _i, _vp, _vp, _vp],
+    "es3_nchw_f32_to_tokens": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "es3_attn_few_queries": [_vp, _ll, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp],
+    "es3_attn_few_keys": [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp],
+    "es3_ln_rows_gelu": [_vp, _vp, _vp, _f, _vp, _ll, _i, _vp],
+    "es3_hyper_masks": [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "es3_bilinear_nchw_f32": [_vp, _vp, _vp, _f, _ll, _i, _i, _i, _i, _vp],
     "es3_conv3x3_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp],
     "es3_gemm_simt": [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _i, _vp],
     "es3_stem_conv3x3_s2": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],

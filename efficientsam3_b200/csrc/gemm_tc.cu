@@ -44,6 +44,10 @@ struct GemmArgs {
   // [0, rope_cols) are (q | k) heads of 64 dims = 32 complex pairs; rope: [positions][32] (cos, sin).
   const float2* rope;
   int rope_cols, rope_H, rope_W, rope_win;
+  // ConvTranspose2d(k=2, s=2) as a GEMM with N = 4*Cout (n = (dy*2+dx)*Cout + co): the epilogue scatters row
+  // (b,h,w) / column n to output pixel (b, 2h+dy, 2w+dx), channel co (depth-to-space).  0 = off.
+  int ct_cout, ct_H, ct_W;
+  int act_after_res;    // apply the activation after the residual add (MaskDecoder: gelu(dc2(x) + feat_s0))
 };
 
 constexpr int BM = 128;
@@ -226,8 +230,21 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
               f[4 * j + 0] += bi.x; f[4 * j + 1] += bi.y; f[4 * j + 2] += bi.z; f[4 * j + 3] += bi.w;
             }
           }
+          long long out_off = row_off * args.ldo + nb, res_off = row_off * args.ldr + nb;
+          if (args.ct_cout) {
+            const int pos = nb / args.ct_cout, co = nb - pos * args.ct_cout;
+            const long long hw = (long long)args.ct_H * args.ct_W;
+            const long long bi = row_off / hw;
+            const int rem = (int)(row_off - bi * hw);
+            const int hh = rem / args.ct_W, ww = rem - hh * args.ct_W;
+            const long long orow = (bi * 2 * args.ct_H + 2 * hh + (pos >> 1)) * (2LL * args.ct_W) + 2 * ww + (pos & 1);
+            out_off = orow * args.ldo + co;
+            res_off = orow * args.ldr + co;
+          }
+          if (!args.act_after_res) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = es3_act_t<ACT>(f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = es3_act_t<ACT>(f[j]);
+          }
           if (args.rope != nullptr && nb < args.rope_cols) {
             const int t = (int)(row_off % ((long long)args.rope_H * args.rope_W));
             const int h = t / args.rope_W, w = t - h * args.rope_W;
@@ -244,14 +261,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
             }
           }
           if (args.residual != nullptr && args.res_f32) {
-            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(args.residual) + row_off * args.ldr + nb);
+            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(args.residual) + res_off);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 r4 = __ldg(rp + j);
               f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
             }
           } else if (args.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(args.residual + row_off * args.ldr + nb);
+            const uint4* rp = reinterpret_cast<const uint4*>(args.residual + res_off);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float rf[8];
@@ -260,12 +277,16 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
               for (int e = 0; e < 8; ++e) f[j * 8 + e] += rf[e];
             }
           }
+          if (args.act_after_res) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = es3_act_t<ACT>(f[j]);
+          }
           if (args.out_f32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + row_off * args.ldo + nb);
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + out_off);
 #pragma unroll
             for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(args.out) + row_off * args.ldo + nb);
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(args.out) + out_off);
 #pragma unroll
             for (int j = 0; j < 4; ++j) op[j] = pack8(f + 8 * j);
           }
@@ -482,4 +503,41 @@ extern "C" int es3_conv3x3_bf16(const void* x, const void* W, void* out, int out
   // NOTE: when C is not a multiple of 64 the last K block of a tap would read the next tap's weights
   // from W; the A side is zero-filled by TMA (channel coordinate beyond C), so the product is still 0.
   return dispatch(bn, tmA, tmB, a, B * a.tiles_w * a.tiles_h, (cudaStream_t)stream);
+}
+
+// ConvTranspose2d(kernel 2, stride 2) on NHWC: x [B,H,W,Cin] bf16, Wt [4*Cout][Cin] bf16 with
+// Wt[(dy*2+dx)*Cout + co][ci] = w[ci][co][dy][dx]; bias4 [4*Cout] (the conv bias repeated per position) or NULL;
+// out [B,2H,2W,Cout] bf16|fp32; residual (same layout as out, bf16|fp32) optional; act applied before the
+// residual unless act_after_res.  Replaces nn.ConvTranspose2d in MaskDecoder.output_upscaling
+// (mask_decoder.py:59-70, 213-216) and the FPN neck (necks.py).  Cout % 32 == 0.
+extern "C" int es3_convt2x2_bf16(const void* x, const void* Wt, void* out, int out_f32, int B, int H, int Wd, int Cin,
+                                 int Cout, const float* bias4, int act, const void* residual, int res_f32,
+                                 int act_after_res, void* stream) {
+  ES3_REQUIRE(Cout % 32 == 0 && Cin % 8 == 0, "es3_convt2x2_bf16: need Cout %% 32 == 0 and Cin %% 8 == 0 (Cin=%d Cout=%d)", Cin, Cout);
+  const int M = B * H * Wd, N = 4 * Cout, K = Cin;
+  const int bn = pick_bn(N, 0);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+    if (encode_map(&tmA, x, 2, dims, str, box)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)bn};
+    if (encode_map(&tmB, Wt, 2, dims, str, box)) return 1;
+  }
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M; a.N = N;
+  a.num_kb = ceil_div(K, BK);
+  a.kb_per_tap = a.num_kb;
+  a.tiles_n = ceil_div(N, bn);
+  a.bias = bias4; a.act = act;
+  a.residual = (const bf16*)residual; a.ldr = Cout; a.res_f32 = res_f32;
+  a.out = out; a.ldo = Cout; a.out_f32 = out_f32;
+  a.ct_cout = Cout; a.ct_H = H; a.ct_W = Wd; a.act_after_res = act_after_res;
+  return dispatch(bn, tmA, tmB, a, ceil_div(M, BM), (cudaStream_t)stream);
 }

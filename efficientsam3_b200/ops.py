@@ -335,3 +335,140 @@ def tokens_f32_to_nchw(x, B, H, W):
     out = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
     _call("es3_tokens_f32_to_nchw", "tokens_to_nchw", _nb(x, out), 0, x.data_ptr(), out.data_ptr(), B, H * W, C, _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------ SAM heads
+def convt2x2(x, wt, bias4=None, act=None, residual=None, out_dtype=torch.bfloat16, act_after_res=False):
+    """ConvTranspose2d(k=2,s=2) on NHWC: x [B,H,W,Cin] bf16, wt [4*Cout, Cin] bf16 -> [B,2H,2W,Cout]."""
+    _chk(x, torch.bfloat16, "x"); _chk(wt, torch.bfloat16, "wt")
+    _ensure_init(x)
+    assert x.is_contiguous() and wt.is_contiguous()
+    B, H, W, Cin = x.shape
+    Cout = wt.shape[0] // 4
+    out = torch.empty((B, 2 * H, 2 * W, Cout), device=x.device, dtype=out_dtype)
+    res_f32 = int(residual is not None and residual.dtype == torch.float32)
+    if residual is not None:
+        assert residual.is_contiguous() and residual.shape == out.shape
+    _call("es3_convt2x2_bf16", f"convt2x2[{Cin}->{Cout}]", _nb(x, wt, out, residual), 2 * B * H * W * Cin * 4 * Cout,
+          x.data_ptr(), wt.data_ptr(), out.data_ptr(), int(out_dtype == torch.float32), B, H, W, Cin, Cout, _ptr(bias4),
+          ACT[act], _ptr(residual), res_f32, int(act_after_res), _stream())
+    return out
+
+
+def convt2x2_weight(w):
+    """nn.ConvTranspose2d weight [Cin,Cout,2,2] -> bf16 [4*Cout, Cin] with row (dy*2+dx)*Cout + co."""
+    cin, cout = w.shape[:2]
+    return w.detach().permute(2, 3, 1, 0).reshape(4 * cout, cin).to(torch.bfloat16).contiguous()
+
+
+def dense_pe(gauss, h, w):
+    _chk(gauss, torch.float32, "gauss")
+    _ensure_init(gauss)
+    F_ = gauss.shape[1]
+    out = torch.empty((h * w, 2 * F_), device=gauss.device, dtype=torch.float32)
+    _call("es3_dense_pe", "dense_pe", _nb(out), 0, gauss.contiguous().data_ptr(), F_, h, w, out.data_ptr(), _stream())
+    return out
+
+
+def point_embed(coords, labels, gauss, not_a_point, point_emb, img_w, img_h):
+    """coords [B,P,2] fp32, labels [B,P] int32 -> [B,P+1,C] fp32 (padding point appended)."""
+    _chk(coords, torch.float32, "coords")
+    _ensure_init(coords)
+    B, P, _ = coords.shape
+    F_ = gauss.shape[1]
+    out = torch.empty((B, P + 1, 2 * F_), device=coords.device, dtype=torch.float32)
+    _call("es3_point_embed", "point_embed", _nb(out), 0, coords.contiguous().data_ptr(),
+          labels.to(torch.int32).contiguous().data_ptr(), gauss.contiguous().data_ptr(), not_a_point.contiguous().data_ptr(),
+          point_emb.contiguous().data_ptr(), F_, B, P, float(img_w), float(img_h), out.data_ptr(), _stream())
+    return out
+
+
+def add_rows(x, add=None, out_bf16=False, out_f32=True):
+    """x [M,C] fp32 + add [R,C] fp32 (row m % R) -> (bf16|None, fp32|None)."""
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    assert x.dim() == 2 and x.is_contiguous()
+    M, C = x.shape
+    R = add.shape[0] if add is not None else 1
+    if add is not None:
+        assert add.is_contiguous() and add.shape[1] == C
+    yb = torch.empty((M, C), device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    yf = torch.empty((M, C), device=x.device, dtype=torch.float32) if out_f32 else None
+    _call("es3_add_rows", "add_rows", _nb(x, yb, yf), M * C, x.data_ptr(), _ptr(add), M, C, R, _ptr(yb), _ptr(yf), _stream())
+    return yb, yf
+
+
+def nchw_to_tokens(x, addc=None, out_bf16=True, out_f32=True):
+    """x [B,C,H,W] fp32 (+ per-channel addc) -> token-major ([B*HW,C] fp32 | None, bf16 | None)."""
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    yf = torch.empty((B * H * W, C), device=x.device, dtype=torch.float32) if out_f32 else None
+    yb = torch.empty((B * H * W, C), device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    _call("es3_nchw_f32_to_tokens", "nchw_to_tokens", _nb(x, yf, yb), 0, x.data_ptr(), _ptr(addc), _ptr(yf), _ptr(yb), B,
+          H * W, C, _stream())
+    return yf, yb
+
+
+def attn_few_queries(q, k, v, heads, scale):
+    """q [B,Tq,D] fp32; k,v [B,Tk,D] bf16 or fp32 -> [B,Tq,D] fp32."""
+    _chk(q, torch.float32, "q")
+    _ensure_init(q)
+    B, Tq, D = q.shape
+    Tk = k.shape[1]
+    assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous() and k.dtype == v.dtype
+    out = torch.empty_like(q)
+    _call("es3_attn_few_queries", f"attn_few_queries[Tk={Tk}]", _nb(q, k, v, out), 4 * B * Tq * Tk * D, q.data_ptr(), D,
+          k.data_ptr(), v.data_ptr(), D, int(k.dtype == torch.float32), out.data_ptr(), D, B, heads, D // heads, Tq, Tk,
+          float(scale), _stream())
+    return out
+
+
+def attn_few_keys(q, k, v, B, heads, scale):
+    """q [B*Nq, D] bf16; k,v [B,Tk,D] fp32 -> [B*Nq, D] bf16."""
+    _chk(q, torch.bfloat16, "q"); _chk(k, torch.float32, "k")
+    _ensure_init(q)
+    D = q.shape[1]
+    Nq, Tk = q.shape[0] // B, k.shape[1]
+    assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    out = torch.empty_like(q)
+    _call("es3_attn_few_keys", "attn_few_keys", _nb(q, k, v, out), 4 * B * Nq * Tk * D, q.data_ptr(), D, k.data_ptr(),
+          v.data_ptr(), D, out.data_ptr(), D, B, heads, D // heads, Nq, Tk, float(scale), _stream())
+    return out
+
+
+def ln_rows_gelu(x, w, b, eps):
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    assert x.dim() == 2 and x.is_contiguous()
+    M, C = x.shape
+    y = torch.empty((M, C), device=x.device, dtype=torch.bfloat16)
+    _call("es3_ln_rows_gelu", "ln_rows_gelu", _nb(x, y), 10 * M * C, x.data_ptr(), w.data_ptr(), b.data_ptr(), float(eps),
+          y.data_ptr(), M, C, _stream())
+    return y
+
+
+def hyper_masks(up, hyper, obj_logits, no_obj, K, k_off):
+    """up [B,HW,32] fp32, hyper [B,Ktot,32] fp32 -> masks [B,K,HW] fp32 (object-gated when obj_logits given)."""
+    _chk(up, torch.float32, "up"); _chk(hyper, torch.float32, "hyper")
+    _ensure_init(up)
+    assert up.is_contiguous() and hyper.is_contiguous()
+    B, HW, CU = up.shape
+    masks = torch.empty((B, K, HW), device=up.device, dtype=torch.float32)
+    _call("es3_hyper_masks", "hyper_masks", _nb(up, masks), 2 * B * HW * K * CU, up.data_ptr(), hyper.data_ptr(),
+          _ptr(obj_logits), float(no_obj), masks.data_ptr(), B, HW, CU, hyper.shape[1], K, k_off, _stream())
+    return masks
+
+
+def bilinear_nchw(x, Ho, Wo, binarize_thr=None, want_float=True):
+    """x [B,C,Hi,Wi] fp32 -> (fp32 [B,C,Ho,Wo] | None, uint8 mask | None)."""
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    x = x.contiguous()
+    B, C, Hi, Wi = x.shape
+    out = torch.empty((B, C, Ho, Wo), device=x.device, dtype=torch.float32) if want_float else None
+    binm = torch.empty((B, C, Ho, Wo), device=x.device, dtype=torch.uint8) if binarize_thr is not None else None
+    _call("es3_bilinear_nchw_f32", "bilinear_nchw", _nb(x, out, binm), 8 * B * C * Ho * Wo, x.data_ptr(), _ptr(out), _ptr(binm),
+          float(binarize_thr or 0.0), B * C, Hi, Wi, Ho, Wo, _stream())
+    return out, binm

@@ -45,6 +45,12 @@ int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, long long ldw,
                      long long ldr, int res_f32, const float* rope, int rope_cols, int rope_H, int rope_W, int rope_win,
                      int bn_hint, void* stream);
 
+/* ConvTranspose2d(k=2, s=2) on NHWC as a tcgen05 GEMM (N = 4*Cout) with a depth-to-space epilogue.
+ * Wt [4*Cout][Cin] bf16, Wt[(dy*2+dx)*Cout+co][ci] = w[ci][co][dy][dx]; bias4 [4*Cout]; out [B,2H,2W,Cout].
+ * Replaces MaskDecoder.output_upscaling ConvTranspose2d (mask_decoder.py:59-70) and the FPN upsamplers (necks.py). */
+int es3_convt2x2_bf16(const void* x, const void* Wt, void* out, int out_f32, int B, int H, int Wd, int Cin, int Cout,
+                      const float* bias4, int act, const void* residual, int res_f32, int act_after_res, void* stream);
+
 /* Dense 3x3 / stride 1 / pad 1 conv as an implicit tcgen05 GEMM (halo via TMA zero fill).
  * x [B,H,W,C] bf16 NHWC; W [N][9*C] with k = (ky*3+kx)*C + c; out [B,H,W,N].
  * Replaces head.3 = nn.Conv2d(1024,1024,3,padding=1) (stage1/model.py:198) and the FPN 3x3s (necks.py). */
@@ -131,6 +137,33 @@ int es3_tokens_f32_to_nchw(const float* in, float* out, int B, int HW, int C, vo
 /* Same contract as es3_litemla_attn; KV state and the apply step run on mma.sync (KV split hi+lo bf16). */
 int es3_litemla_attn_tc(const void* ms, long long ld, float* kv_ws, void* att, long long ldo, int B, int HW, int heads2,
                         float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------ SAM heads */
+/* PositionEmbeddingRandom over an h x w grid -> [h*w, 2F] fp32 (PromptEncoder.get_dense_pe, prompt_encoder.py:61-69). */
+int es3_dense_pe(const float* gauss, int F, int h, int w, float* out, void* stream);
+/* Point prompts (+ trailing padding point) -> sparse embeddings [B, P+1, 2F] fp32 (prompt_encoder.py:71-117). */
+int es3_point_embed(const float* coords, const int* labels, const float* gauss, const float* not_a_point,
+                    const float* point_emb, int F, int B, int P, float img_w, float img_h, float* out, void* stream);
+/* y[m] = x[m] + add[m % R] over C channels; bf16 and/or fp32 output (queries + pe, keys + key_pe). */
+int es3_add_rows(const float* x, const float* add, long long M, int C, int R, void* y_bf16, float* y_f32, void* stream);
+/* [B,C,HW] fp32 (+ per-channel vector, e.g. no_mask_embed) -> token-major [B,HW,C] fp32 and/or bf16. */
+int es3_nchw_f32_to_tokens(const float* in, const float* addc, float* out_f32, void* out_bf16, int B, int HW, int C,
+                           void* stream);
+/* Softmax attention, few queries (prompt tokens) x many keys; q fp32, k/v bf16 (kv_f32 = 0) or fp32; out fp32.
+ * Replaces Attention core for self_attn / cross_attn_token_to_image (transformer.py:185-264). head_dim 16|32. */
+int es3_attn_few_queries(const float* q, long long ldq, const void* k, const void* v, long long ldkv, int kv_f32, float* out,
+                         long long ldo, int B, int H, int head_dim, int Tq, int Tk, float scale, void* stream);
+/* Softmax attention, many queries (image tokens, bf16) x <= 16 keys (fp32); out bf16 (cross_attn_image_to_token). */
+int es3_attn_few_keys(const void* q, long long ldq, const float* k, const float* v, long long ldkv, void* out, long long ldo,
+                      int B, int H, int head_dim, int Nq, int Tk, float scale, void* stream);
+/* y = gelu(LayerNorm_C(x) * w + b) on rows of C <= 128 channels -> bf16 (LayerNorm2d + GELU, mask_decoder.py:59-70). */
+int es3_ln_rows_gelu(const float* x, const float* w, const float* bias, float eps, void* y, long long M, int C, void* stream);
+/* masks[b,k,p] = hyper[b,k_off+k,:] . up[b,p,:] (+ object gating) -> [B,K,HW] fp32 (mask_decoder.py:225-226). */
+int es3_hyper_masks(const float* up, const float* hyper, const float* obj_logits, float no_obj, float* masks, int B, int HW,
+                    int CU, int Ktot, int K, int k_off, void* stream);
+/* Bilinear (align_corners=False) on NCHW fp32 planes; optional uint8 (x > thr) output (tracker_base.py:355-360). */
+int es3_bilinear_nchw_f32(const float* in, float* out, void* bin, float thr, long long planes, int Hi, int Wi, int Ho,
+                          int Wo, void* stream);
 
 #ifdef __cplusplus
 }

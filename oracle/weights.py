@@ -31,6 +31,8 @@ def fill_state_dict(sd: dict, seed: int) -> dict:
             v = torch.rand(shape, generator=g) + 0.5
         elif t.dim() <= 1:                                # biases, LayerScale-like vectors
             v = torch.randn(shape, generator=g) * 0.1
+        elif "positional_encoding_gaussian_matrix" in key:   # PositionEmbeddingRandom buffer: unit normal
+            v = torch.randn(shape, generator=g)
         elif "pos_embed" in key or "attention_biases" in key or "embed" in leaf or "freqs" in key:
             v = torch.randn(shape, generator=g) * 0.5
         else:                                             # conv / linear weights

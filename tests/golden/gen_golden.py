@@ -80,7 +80,58 @@ def gen_vit(tag, cfg, seed_w, seed_x, batch):
           "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def build_ref_sam_heads(E, S):
+    """PromptEncoder + MaskDecoder exactly as Sam3TrackerBase._build_sam_heads builds them (:179-218)."""
+    from sam3.sam.mask_decoder import MaskDecoder
+    from sam3.sam.prompt_encoder import PromptEncoder
+    from sam3.sam.transformer import TwoWayTransformer
+
+    pe = PromptEncoder(embed_dim=256, image_embedding_size=(E, E), input_image_size=(S, S), mask_in_chans=16).eval()
+    md = MaskDecoder(num_multimask_outputs=3, transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
+                     transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256, use_high_res_features=True,
+                     iou_prediction_use_sigmoid=True, pred_obj_scores=True, pred_obj_scores_mlp=True,
+                     use_multimask_token_for_obj_ptr=True).eval()
+    return pe, md
+
+
+def sam_heads_inputs(B, E, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    feat = torch.randn(B, 256, E, E, generator=g)
+    f288 = torch.randn(B, 256, 4 * E, 4 * E, generator=g)
+    f144 = torch.randn(B, 256, 2 * E, 2 * E, generator=g)
+    coords = torch.rand(B, 1, 2, generator=g) * S
+    labels = torch.ones(B, 1, dtype=torch.int32)
+    return feat, f288, f144, coords, labels
+
+
+def gen_sam_heads(tag, E, S, B, seed_pe, seed_md, seed_x):
+    pe, md = build_ref_sam_heads(E, S)
+    sd_pe = fill_state_dict(pe.state_dict(), seed_pe)
+    sd_md = fill_state_dict(md.state_dict(), seed_md)
+    pe.load_state_dict(sd_pe)
+    md.load_state_dict(sd_md)
+    feat, f288, f144, coords, labels = sam_heads_inputs(B, E, S, seed_x)
+    hr = [md.conv_s0(f288), md.conv_s1(f144)]
+    sp, de = pe(points=(coords, labels), boxes=None, masks=None)
+    dpe = pe.get_dense_pe()
+    out = {}
+    for mm in (True, False):
+        m, iou, tok, obj = md(image_embeddings=feat, image_pe=dpe, sparse_prompt_embeddings=sp, dense_prompt_embeddings=de,
+                              multimask_output=mm, repeat_image=False, high_res_features=hr)
+        sfx = "mm" if mm else "single"
+        out.update({f"masks_{sfx}": m.numpy(), f"iou_{sfx}": iou.numpy(), f"tok_{sfx}": tok.numpy(), f"obj_{sfx}": obj.numpy()})
+    q, k = md.transformer(feat, dpe.expand(B, -1, -1, -1), torch.cat([sp, sp], dim=1))
+    path = os.path.join(HERE, f"{tag}.npz")
+    np.savez_compressed(path, sparse=sp.numpy(), dense_pe=dpe.numpy()[:, :, ::4, ::4], twoway_q=q.numpy(),
+                        twoway_k_stats=stats(k), keys_pe=keyshapes(pe.state_dict()), keys_md=keyshapes(md.state_dict()),
+                        E=E, S=S, B=B, seed_pe=seed_pe, seed_md=seed_md, seed_x=seed_x, **out)
+    print(tag, "masks", out["masks_mm"].shape, "absmean %.4f" % np.abs(out["masks_mm"]).mean(), "obj", out["obj_mm"].ravel(),
+          "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 def main(which):
+    if which in ("heads", "all"):
+        gen_sam_heads("sam_heads_16", E=16, S=224, B=2, seed_pe=5, seed_md=6, seed_x=1)
     if which in ("vit", "all"):
         gen_vit("vit_small_112", VIT_SMALL, seed_w=21, seed_x=3, batch=2)
     if which in ("evm", "all"):

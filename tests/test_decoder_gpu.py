@@ -1,0 +1,148 @@
+"""GPU parity of the SAM heads (PromptEncoder + TwoWayTransformer + MaskDecoder) through the reference-shaped
+module API (-> C ABI).
+
+Tolerances (stated; north-star: mask logits rtol 1e-3, argmax masks bit-exact): the image stream runs bf16 GEMM
+operands with fp32 accumulation/residuals, the token stream and the hypernetwork tail are fp32.  Asserted: mask
+logits rel-L2 <= 1e-2 and max|err| <= 2e-2 * max|logit|; IoU / object logits abs err <= 2e-2; the best-mask index
+equals the reference's; binary masks (logit > 0) agree on every pixel whose reference |logit| exceeds the measured
+max error (bit-exact outside the rounding band) and on >= 99.5 % of all pixels.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import cosine, load_golden, max_err_over_scale, rel_l2, sd_from_keys
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(E, S, sd_pe, sd_md, dev):
+    import torch.nn as nn
+    from efficientsam3_b200.sam import MaskDecoder, PromptEncoder, TwoWayTransformer
+    pe = PromptEncoder(embed_dim=256, image_embedding_size=(E, E), input_image_size=(S, S), mask_in_chans=16)
+    md = MaskDecoder(num_multimask_outputs=3, transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
+                     transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256, use_high_res_features=True,
+                     iou_prediction_use_sigmoid=True, pred_obj_scores=True, pred_obj_scores_mlp=True,
+                     use_multimask_token_for_obj_ptr=True)
+    pe.load_state_dict(sd_pe)
+    md.load_state_dict(sd_md)
+    return pe.to(dev).eval(), md.to(dev).eval()
+
+
+def _inputs(B, E, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    feat = torch.randn(B, 256, E, E, generator=g)
+    f288 = torch.randn(B, 256, 4 * E, 4 * E, generator=g)
+    f144 = torch.randn(B, 256, 2 * E, 2 * E, generator=g)
+    coords = torch.rand(B, 1, 2, generator=g) * S
+    labels = torch.ones(B, 1, dtype=torch.int32)
+    return feat, f288, f144, coords, labels
+
+
+def _mask_checks(got, ref, what):
+    l2, mx = rel_l2(got, ref), max_err_over_scale(got, ref)
+    err = (got.double() - ref.double()).abs().max().item()
+    agree = ((got > 0) == (ref > 0)).float().mean().item()
+    safe = ref.abs() > err
+    print(f"{what}: rel_l2={l2:.3e} max/scale={mx:.3e} abs_err={err:.3e} binary agreement={agree:.5f} "
+          f"({(~safe).float().mean().item():.4%} of pixels inside the rounding band)")
+    assert l2 <= 1e-2 and mx <= 2e-2, (what, l2, mx)
+    assert torch.equal((got > 0)[safe], (ref > 0)[safe])
+    assert agree >= 0.995
+
+
+def test_key_order_matches_reference_record():
+    g = load_golden("sam_heads_16")
+    from efficientsam3_b200.sam import MaskDecoder, PromptEncoder, TwoWayTransformer  # noqa: F401
+    pe, md = _build(16, 224, sd_from_keys(g["keys_pe"], 5), sd_from_keys(g["keys_md"], 6), "cpu")
+    sig = lambda sd: [f"{k}|{','.join(map(str, v.shape))}|{str(v.dtype).replace('torch.', '')}" for k, v in sd.items()]
+    assert sig(pe.state_dict()) == [str(k) for k in g["keys_pe"]]
+    assert sig(md.state_dict()) == [str(k) for k in g["keys_md"]]
+
+
+def test_heads_match_reference_fixture(cuda):
+    g = load_golden("sam_heads_16")
+    E, S, B = int(g["E"]), int(g["S"]), int(g["B"])
+    pe, md = _build(E, S, sd_from_keys(g["keys_pe"], int(g["seed_pe"])), sd_from_keys(g["keys_md"], int(g["seed_md"])), cuda)
+    feat, f288, f144, coords, labels = [t.to(cuda) for t in _inputs(B, E, S, int(g["seed_x"]))]
+    sp, de = pe(points=(coords, labels), boxes=None, masks=None)
+    assert max_err_over_scale(sp.cpu(), g["sparse"]) < 1e-5
+    dpe = pe.get_dense_pe()
+    assert max_err_over_scale(dpe.cpu()[:, :, ::4, ::4], g["dense_pe"]) < 1e-5
+    hr = [F.conv2d(f288, md.conv_s0.weight, md.conv_s0.bias), F.conv2d(f144, md.conv_s1.weight, md.conv_s1.bias)]  # test-side prep
+    for mm, sfx in ((True, "mm"), (False, "single")):
+        m, iou, tok, obj = md(image_embeddings=feat, image_pe=dpe, sparse_prompt_embeddings=sp, dense_prompt_embeddings=de,
+                              multimask_output=mm, repeat_image=False, high_res_features=hr)
+        _mask_checks(m.cpu(), torch.from_numpy(g[f"masks_{sfx}"]), f"fixture masks {sfx}")
+        assert (iou.cpu() - torch.from_numpy(g[f"iou_{sfx}"])).abs().max() <= 2e-2
+        assert (obj.cpu() - torch.from_numpy(g[f"obj_{sfx}"])).abs().max() <= 2e-2
+        assert rel_l2(tok.cpu(), g[f"tok_{sfx}"]) <= 1e-2
+        assert torch.equal(iou.cpu().argmax(-1), torch.from_numpy(g[f"iou_{sfx}"]).argmax(-1))
+    q, k = md.transformer(feat, dpe.expand(B, -1, -1, -1), torch.cat([sp, sp], dim=1))
+    assert rel_l2(q.cpu(), g["twoway_q"]) <= 1e-2
+
+
+def test_heads_full_size_vs_oracle(cuda):
+    """Config-3 geometry: 72x72 embeddings, 1008 px, 288x288 low-res masks, batch 4, against the CPU oracle,
+    plus the upsample + threshold tail (sam3_tracker_base.py:344-360)."""
+    from oracle import sam_heads as O
+    from efficientsam3_b200 import ops
+    g = load_golden("sam_heads_16")
+    E, S, B = 72, 1008, 4
+    sd_pe, sd_md = sd_from_keys(g["keys_pe"], 15), sd_from_keys(g["keys_md"], 16)
+    feat, f288, f144, coords, labels = _inputs(B, E, S, 3)
+    with torch.no_grad():
+        hr = O.high_res_from_fpn(sd_md, "", f288, f144)
+        ref = O.forward_sam_heads(sd_pe, sd_md, feat, hr, coords, labels, S, multimask_output=True)
+    pe, md = _build(E, S, sd_pe, sd_md, cuda)
+    sp, de = pe(points=(coords.to(cuda), labels.to(cuda)), boxes=None, masks=None)
+    m, iou, tok, obj = md(image_embeddings=feat.to(cuda), image_pe=pe.get_dense_pe(), sparse_prompt_embeddings=sp,
+                          dense_prompt_embeddings=de, multimask_output=True, repeat_image=False,
+                          high_res_features=[h.to(cuda) for h in hr])
+    gated = torch.where((obj > 0)[:, None, None], m, torch.full_like(m, -1024.0))
+    _mask_checks(gated.cpu(), ref["low_res_multimasks"], "full-size low-res masks")
+    assert torch.equal(iou.cpu().argmax(-1), ref["best"])
+    assert (iou.cpu() - ref["ious"]).abs().max() <= 2e-2
+    high, binm = ops.bilinear_nchw(gated, S, S, binarize_thr=0.0)
+    _mask_checks(high.cpu(), ref["high_res_multimasks"], "full-size high-res masks")
+    assert torch.equal(binm.bool().cpu(), high.cpu() > 0)
+
+
+@pytest.mark.parametrize("Tk,hd,kv32", [(8, 32, True), (5184, 16, False), (100, 16, False), (33, 32, True)])
+def test_attn_few_queries(cuda, Tk, hd, kv32):
+    from efficientsam3_b200 import ops
+    B, Tq, H = 2, 8, 8
+    g = torch.Generator().manual_seed(Tk)
+    q = torch.randn(B, Tq, H * hd, generator=g).to(cuda)
+    k = torch.randn(B, Tk, H * hd, generator=g).to(cuda)
+    v = torch.randn(B, Tk, H * hd, generator=g).to(cuda)
+    if not kv32:
+        k, v = k.bfloat16(), v.bfloat16()
+    out = ops.attn_few_queries(q, k, v, H, hd ** -0.5)
+    sep = lambda t: t.float().view(B, -1, H, hd).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sep(q), sep(k), sep(v)).transpose(1, 2).reshape(B, Tq, H * hd)
+    assert max_err_over_scale(out.cpu(), ref.cpu()) < 1e-4
+
+
+def test_attn_few_keys_and_convt(cuda):
+    from efficientsam3_b200 import ops
+    B, Nq, Tk, H, hd = 2, 777, 8, 8, 16
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(B * Nq, H * hd, generator=g).bfloat16().to(cuda)
+    k = torch.randn(B, Tk, H * hd, generator=g).to(cuda)
+    v = torch.randn(B, Tk, H * hd, generator=g).to(cuda)
+    out = ops.attn_few_keys(q, k, v, B, H, 0.25)
+    sep = lambda t, n: t.float().view(B, n, H, hd).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sep(q, Nq), sep(k, Tk), sep(v, Tk)).transpose(1, 2).reshape(B * Nq, H * hd)
+    assert max_err_over_scale(out.cpu(), ref.cpu()) < 1e-2
+    # ConvTranspose2d(k=2,s=2) + bias + fp32 residual, gelu after the residual
+    x = torch.randn(2, 9, 7, 64, generator=g).bfloat16().to(cuda)
+    w = (torch.randn(64, 32, 2, 2, generator=g) / 8).to(cuda)
+    b = torch.randn(32, generator=g).to(cuda)
+    r = torch.randn(2, 18, 14, 32, generator=g).to(cuda)
+    y = ops.convt2x2(x, ops.convt2x2_weight(w), bias4=b.repeat(4).contiguous(), act="gelu", residual=r,
+                     out_dtype=torch.float32, act_after_res=True)
+    ref = F.gelu(F.conv_transpose2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), b, stride=2) + r.permute(0, 3, 1, 2))
+    assert max_err_over_scale(y.cpu(), ref.permute(0, 2, 3, 1).cpu()) < 2e-3

@@ -52,3 +52,34 @@ def test_vit_oracle_matches_reference():
     with torch.no_grad():
         out = O.vit_trunk(sd, "", x, cfg)
     _assert_close(out.numpy(), g["out"], rtol=2e-5)
+
+
+def test_sam_heads_oracle_matches_reference():
+    """PromptEncoder + TwoWayTransformer + MaskDecoder oracle vs the reference classes' recorded outputs."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from oracle import sam_heads as O
+    g = _load("sam_heads_16")
+    E, S, B = int(g["E"]), int(g["S"]), int(g["B"])
+    sd_pe = _sd_from_keys(g["keys_pe"], int(g["seed_pe"]))
+    sd_md = _sd_from_keys(g["keys_md"], int(g["seed_md"]))
+    gen = torch.Generator().manual_seed(int(g["seed_x"]))
+    feat = torch.randn(B, 256, E, E, generator=gen)
+    f288 = torch.randn(B, 256, 4 * E, 4 * E, generator=gen)
+    f144 = torch.randn(B, 256, 2 * E, 2 * E, generator=gen)
+    coords = torch.rand(B, 1, 2, generator=gen) * S
+    labels = torch.ones(B, 1, dtype=torch.int32)
+    with torch.no_grad():
+        sp, de = O.prompt_encoder_points(sd_pe, "", coords, labels, (S, S), (E, E))
+        dpe = O.dense_pe(sd_pe, "", E, E)
+        hr = O.high_res_from_fpn(sd_md, "", f288, f144)
+        _assert_close(sp.numpy(), g["sparse"], rtol=1e-5)
+        _assert_close(dpe.numpy()[:, :, ::4, ::4], g["dense_pe"], rtol=1e-5)
+        for mm, sfx in ((True, "mm"), (False, "single")):
+            m, iou, tok, obj = O.mask_decoder(sd_md, "", feat, dpe, sp, de, mm, hr)
+            _assert_close(m.numpy(), g[f"masks_{sfx}"], rtol=5e-5)
+            _assert_close(iou.numpy(), g[f"iou_{sfx}"], rtol=5e-5)
+            _assert_close(tok.numpy(), g[f"tok_{sfx}"], rtol=5e-5)
+            _assert_close(obj.numpy(), g[f"obj_{sfx}"], rtol=5e-5)
+        q, k = O.two_way_transformer(sd_md, "transformer.", feat, dpe.expand(B, -1, -1, -1), torch.cat([sp, sp], dim=1))
+        _assert_close(q.numpy(), g["twoway_q"], rtol=5e-5)
