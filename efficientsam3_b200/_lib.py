@@ -42,6 +42,7 @@ SIGNATURES: dict[str, list] = {
     "es3_mbconv_fused_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "es3_dsconv_res_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "es3_bilinear_nhwc_to_nchw": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "es3_maxpool2x2_bf16": [_vp, _vp, _i, _i, _i, _i, _vp],
     "es3_nhwc_to_nchw_f32": [_vp, _vp, _i, _i, _i, _vp],
     "es3_nchw_f32_to_nhwc": [_vp, _vp, _i, _i, _i, _vp],
     "es3_litemla_aggreg": [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp],

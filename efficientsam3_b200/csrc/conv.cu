@@ -380,3 +380,38 @@ extern "C" int es3_nchw_f32_to_nhwc(const float* in, void* out, int B, int HW, i
   ES3_LAUNCH_CHECK("nchw_to_nhwc_kernel");
   return 0;
 }
+
+// MaxPool 2x2 stride 2 on NHWC bf16 (FPN 0.5x level, necks.py:64-69).  Thread = (output pixel, 8 channels).
+namespace es3 {
+__global__ void maxpool2x2_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, cg = C / 8;
+  const long long total = (long long)B * Ho * Wo * cg;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % cg);
+  const long long p = idx / cg;
+  const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho);
+  const int b = (int)(p / ((long long)Wo * Ho));
+  float m[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + oy * 2 + dy) * W + ox * 2 + dx) * C + g * 8)), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], f[e]);
+    }
+  *reinterpret_cast<uint4*>(out + p * C + g * 8) = pack8(m);
+}
+}  // namespace es3
+
+extern "C" int es3_maxpool2x2_bf16(const void* x, void* out, int B, int H, int W, int C, void* stream) {
+  ES3_REQUIRE(C % 8 == 0 && H >= 2 && W >= 2, "es3_maxpool2x2_bf16: bad shape");
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  es3::maxpool2x2_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, B, H, W, C);
+  ES3_LAUNCH_CHECK("maxpool2x2_kernel");
+  return 0;
+}

@@ -472,3 +472,13 @@ def bilinear_nchw(x, Ho, Wo, binarize_thr=None, want_float=True):
     _call("es3_bilinear_nchw_f32", "bilinear_nchw", _nb(x, out, binm), 8 * B * C * Ho * Wo, x.data_ptr(), _ptr(out), _ptr(binm),
           float(binarize_thr or 0.0), B * C, Hi, Wi, Ho, Wo, _stream())
     return out, binm
+
+
+def maxpool2x2(x):
+    _chk(x, torch.bfloat16, "x")
+    _ensure_init(x)
+    assert x.is_contiguous()
+    B, H, W, C = x.shape
+    out = torch.empty((B, H // 2, W // 2, C), device=x.device, dtype=torch.bfloat16)
+    _call("es3_maxpool2x2_bf16", "maxpool2x2", _nb(x, out), 0, x.data_ptr(), out.data_ptr(), B, H, W, C, _stream())
+    return out

@@ -96,6 +96,8 @@ int es3_mbconv_fused_bf16(const void* x, void* y, const void* w1, const float* s
 
 /* Bilinear (align_corners=False) NHWC bf16 -> NCHW fp32.  Replaces F.interpolate at stage1/model.py:204-210. */
 int es3_bilinear_nhwc_to_nchw(const void* in, float* out, int B, int Hi, int Wi, int C, int Ho, int Wo, void* stream);
+/* MaxPool2d(2,2) on NHWC bf16 (FPN 0.5x level, necks.py:64-69). */
+int es3_maxpool2x2_bf16(const void* x, void* out, int B, int H, int W, int C, void* stream);
 /* Layout conversions at the module boundary. */
 int es3_nhwc_to_nchw_f32(const void* in, float* out, int B, int HW, int C, void* stream);
 int es3_nchw_f32_to_nhwc(const float* in, void* out, int B, int HW, int C, void* stream);

@@ -145,9 +145,11 @@ def forward_sam_heads(sd_pe, sd_md, backbone_features, high_res_features, coords
     sparse, dense = prompt_encoder_points(sd_pe, "", coords, labels, (image_size, image_size), (h, w))
     pe = dense_pe(sd_pe, "", h, w)
     low, iou, toks, obj = mask_decoder(sd_md, "", backbone_features, pe, sparse, dense, multimask_output, high_res_features)
+    raw = low.float()
     low = torch.where((obj > 0)[:, None, None], low, torch.full_like(low, NO_OBJ_SCORE)).float()
     high = F.interpolate(low, size=(image_size, image_size), mode="bilinear", align_corners=False)
     best = torch.argmax(iou, dim=-1)
     idx = torch.arange(B)
     return dict(low_res_multimasks=low, high_res_multimasks=high, ious=iou, low_res_masks=low[idx, best].unsqueeze(1),
-                high_res_masks=high[idx, best].unsqueeze(1), object_score_logits=obj, best=best)
+                high_res_masks=high[idx, best].unsqueeze(1), object_score_logits=obj, best=best, low_res_ungated=raw,
+                high_res_ungated=F.interpolate(raw, size=(image_size, image_size), mode="bilinear", align_corners=False))

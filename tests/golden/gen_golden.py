@@ -129,7 +129,30 @@ def gen_sam_heads(tag, E, S, B, seed_pe, seed_md, seed_x):
           "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def gen_neck(tag, dim, d_model, hw, B, seed_w, seed_x):
+    from sam3.model.necks import Sam3DualViTDetNeck
+
+    class _Trunk(torch.nn.Module):          # test double: the neck only needs channel_list and a callable trunk
+        channel_list = [dim]
+
+        def forward(self, x):
+            return [x]
+
+    m = Sam3DualViTDetNeck(trunk=_Trunk(), position_encoding=lambda t: torch.zeros_like(t), d_model=d_model,
+                           scale_factors=[4.0, 2.0, 1.0, 0.5], add_sam2_neck=True).eval()
+    sd = fill_state_dict(m.state_dict(), seed_w)
+    m.load_state_dict(sd)
+    x = torch.randn(B, dim, hw, hw, generator=torch.Generator().manual_seed(seed_x))
+    s3, _, s2, _ = m(x)
+    path = os.path.join(HERE, f"{tag}.npz")
+    np.savez_compressed(path, keys=keyshapes(m.state_dict()), dim=dim, d_model=d_model, hw=hw, B=B, seed_w=seed_w, seed_x=seed_x,
+                        **{f"sam3_{i}": t.numpy() for i, t in enumerate(s3)}, **{f"sam2_{i}": t.numpy() for i, t in enumerate(s2)})
+    print(tag, [tuple(t.shape) for t in s3], "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 def main(which):
+    if which in ("neck", "all"):
+        gen_neck("neck_small", dim=128, d_model=64, hw=6, B=2, seed_w=31, seed_x=32)
     if which in ("heads", "all"):
         gen_sam_heads("sam_heads_16", E=16, S=224, B=2, seed_pe=5, seed_md=6, seed_x=1)
     if which in ("vit", "all"):

@@ -101,8 +101,13 @@ def test_heads_full_size_vs_oracle(cuda):
     m, iou, tok, obj = md(image_embeddings=feat.to(cuda), image_pe=pe.get_dense_pe(), sparse_prompt_embeddings=sp,
                           dense_prompt_embeddings=de, multimask_output=True, repeat_image=False,
                           high_res_features=[h.to(cuda) for h in hr])
+    _mask_checks(m.cpu(), ref["low_res_ungated"], "full-size low-res masks (ungated)")
+    assert (obj.cpu() - ref["object_score_logits"]).abs().max() <= 2e-2
+    assert torch.equal(obj.cpu() > 0, ref["object_score_logits"] > 0)
     gated = torch.where((obj > 0)[:, None, None], m, torch.full_like(m, -1024.0))
-    _mask_checks(gated.cpu(), ref["low_res_multimasks"], "full-size low-res masks")
+    _mask_checks(gated.cpu(), ref["low_res_multimasks"], "full-size low-res masks (object-gated)")
+    hi_u, _ = ops.bilinear_nchw(m, S, S)
+    _mask_checks(hi_u.cpu(), ref["high_res_ungated"], "full-size high-res masks (ungated)")
     assert torch.equal(iou.cpu().argmax(-1), ref["best"])
     assert (iou.cpu() - ref["ious"]).abs().max() <= 2e-2
     high, binm = ops.bilinear_nchw(gated, S, S, binarize_thr=0.0)

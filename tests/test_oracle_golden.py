@@ -83,3 +83,15 @@ def test_sam_heads_oracle_matches_reference():
             _assert_close(obj.numpy(), g[f"obj_{sfx}"], rtol=5e-5)
         q, k = O.two_way_transformer(sd_md, "transformer.", feat, dpe.expand(B, -1, -1, -1), torch.cat([sp, sp], dim=1))
         _assert_close(q.numpy(), g["twoway_q"], rtol=5e-5)
+
+
+def test_neck_oracle_matches_reference():
+    from oracle import necks as O
+    g = _load("neck_small")
+    sd = _sd_from_keys(g["keys"], int(g["seed_w"]))
+    x = torch.randn(int(g["B"]), int(g["dim"]), int(g["hw"]), int(g["hw"]), generator=torch.Generator().manual_seed(int(g["seed_x"])))
+    with torch.no_grad():
+        for pref, name in (("convs.", "sam3"), ("sam2_convs.", "sam2")):
+            outs = O.neck(sd, x, prefix=pref)
+            for i, t in enumerate(outs):
+                _assert_close(t.numpy(), g[f"{name}_{i}"], rtol=2e-5)
