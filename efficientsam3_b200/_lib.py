@@ -33,6 +33,10 @@ SIGNATURES: dict[str, list] = {
     "es3_ln_rows_gelu": [_vp, _vp, _vp, _f, _vp, _ll, _i, _vp],
     "es3_hyper_masks": [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_bilinear_nchw_f32": [_vp, _vp, _vp, _f, _ll, _i, _i, _i, _i, _vp],
+    "es3_kd_loss_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
+    "es3_conv3x3_s2_c32_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "es3_channel_mean": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "es3_scale_channels": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "es3_conv3x3_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp],
     "es3_gemm_simt": [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _i, _vp],
     "es3_stem_conv3x3_s2": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],

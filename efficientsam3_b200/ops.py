@@ -18,7 +18,7 @@ def _stream() -> int:
 
 # ------------------------------------------------------------------------------------ accounting
 # kernels launched per C-ABI call (memsets excluded) -- bench.py reports the sum as `gpu_launches`.
-KERNELS_PER_CALL = {"es3_litemla_attn": 2, "es3_litemla_attn_tc": 2}
+KERNELS_PER_CALL = {"es3_litemla_attn": 2, "es3_litemla_attn_tc": 2, "es3_kd_loss_fwd": 2, "es3_channel_mean": 2}
 launch_count = 0
 
 
@@ -482,3 +482,54 @@ def maxpool2x2(x):
     out = torch.empty((B, H // 2, W // 2, C), device=x.device, dtype=torch.bfloat16)
     _call("es3_maxpool2x2_bf16", "maxpool2x2", _nb(x, out), 0, x.data_ptr(), out.data_ptr(), B, H, W, C, _stream())
     return out
+
+
+def kd_loss_fwd(preds, teacher, sizes_hw, img_size, cosine_weight):
+    _chk(preds, torch.float32, "preds"); _chk(teacher, torch.float32, "teacher")
+    _ensure_init(preds)
+    preds, teacher = preds.contiguous(), teacher.contiguous()
+    assert preds.shape == teacher.shape and preds.shape[-1] == preds.shape[-2]
+    B, C, E, _ = preds.shape
+    ws = torch.empty((B * ((E * E + 255) // 256) * 3,), device=preds.device, dtype=torch.float32)
+    out = torch.empty((3,), device=preds.device, dtype=torch.float32)
+    per = torch.empty((B, 3), device=preds.device, dtype=torch.float32)
+    _call("es3_kd_loss_fwd", "kd_loss_fwd", _nb(preds, teacher), 8 * preds.numel(), preds.data_ptr(), teacher.data_ptr(),
+          sizes_hw.contiguous().data_ptr(), B, C, E, img_size, float(cosine_weight), ws.data_ptr(), out.data_ptr(), per.data_ptr(),
+          _stream())
+    return out, per
+
+
+def conv3x3_s2_c32(x, w9, scale, bias, act=None):
+    """x [B,H,W,32] bf16, w9 [9, Cout, 32] bf16 -> [B,Ho,Wo,Cout] bf16 (dense 3x3, stride 2, pad 1, folded BN)."""
+    _chk(x, torch.bfloat16, "x"); _chk(w9, torch.bfloat16, "w9")
+    _ensure_init(x)
+    assert x.is_contiguous() and w9.is_contiguous() and x.shape[3] == 32 and w9.shape[2] == 32
+    B, H, W, _ = x.shape
+    Cout = w9.shape[1]
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
+    _call("es3_conv3x3_s2_c32_bf16", "conv3x3_s2_c32", _nb(x, out), 2 * B * Ho * Wo * Cout * 9 * 32, x.data_ptr(), w9.data_ptr(),
+          scale.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, Cout, ACT[act], _stream())
+    return out
+
+
+def channel_mean(x):
+    """x [B,H,W,C] bf16 -> [B,C] fp32."""
+    _chk(x, torch.bfloat16, "x")
+    _ensure_init(x)
+    assert x.is_contiguous()
+    B, H, W, C = x.shape
+    ws = torch.empty((B * ((H * W + 127) // 128) * C,), device=x.device, dtype=torch.float32)
+    mean = torch.empty((B, C), device=x.device, dtype=torch.float32)
+    _call("es3_channel_mean", "channel_mean", _nb(x), B * H * W * C, x.data_ptr(), ws.data_ptr(), mean.data_ptr(), B, H * W, C, _stream())
+    return mean
+
+
+def scale_channels(x, gate):
+    _chk(x, torch.bfloat16, "x"); _chk(gate, torch.float32, "gate")
+    _ensure_init(x)
+    assert x.is_contiguous() and gate.is_contiguous()
+    B, H, W, C = x.shape
+    y = torch.empty_like(x)
+    _call("es3_scale_channels", "scale_channels", 2 * _nb(x), B * H * W * C, x.data_ptr(), gate.data_ptr(), y.data_ptr(), B, H * W, C, _stream())
+    return y

@@ -109,6 +109,21 @@ class SAM3ImageTeacherEncoder(nn.Module):
         return feats
 
 
+class RepViTAdapter(nn.Module):
+    """stage1/model.py:287-296."""
+
+    def __init__(self, model, out_channels):
+        super().__init__()
+        self.model = model
+        self.out_channels = out_channels
+
+    def forward(self, x):
+        return ops.nhwc_to_nchw_f32(self.model.forward_nhwc(x))
+
+    def forward_nhwc(self, x):
+        return self.model.forward_nhwc(x)
+
+
 class EfficientViTAdapter(nn.Module):
     def __init__(self, model):
         super().__init__()
@@ -128,6 +143,11 @@ def _build_backbone(name, img_size):
               "efficientvit_b2": efficientvit_backbone_b2}[name]
         adapter = EfficientViTAdapter(fn())
         return adapter, adapter.out_channels
+    if name == "repvit_m1_1":
+        from ..backbones.repvit import _make_divisible, repvit_m1_1
+        model = repvit_m1_1(pretrained=False, num_classes=0, distillation=False)
+        out_channels = _make_divisible(model.cfgs[-1][2], 8)
+        return RepViTAdapter(model, out_channels), out_channels
     if name.startswith("repvit") or name.startswith("tiny_vit"):
         raise NotImplementedError(f"{name}: native student backbone not built yet (see DESIGN.md scope table)")
     raise ValueError(f"Unsupported backbone {name}")

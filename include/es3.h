@@ -167,6 +167,23 @@ int es3_hyper_masks(const float* up, const float* hyper, const float* obj_logits
 int es3_bilinear_nchw_f32(const float* in, float* out, void* bin, float thr, long long planes, int Hi, int Wi, int Ho,
                           int Wo, void* stream);
 
+/* ------------------------------------------------------------------------------------------ RepViT / TinyViT */
+/* Dense 3x3, stride 2, pad 1, Cin = 32 (second patch-embed conv: repvit.py:222-223, tiny_vit.py:75-81) on mma.sync.
+ * x [B,H,W,32] bf16; w [9][Cout][32] bf16 (tap, out channel, in channel); folded-BN scale/bias; out [B,Ho,Wo,Cout]. */
+int es3_conv3x3_s2_c32_bf16(const void* x, const void* w, const float* scale, const float* bias, void* out, int B, int H,
+                            int W, int Cout, int act, void* stream);
+/* SqueezeExcite pieces (timm.layers.SqueezeExcite, repvit.py:136,150): per-image channel means of x [B,HW,C] bf16
+ * (ws: B*ceil(HW/128)*C floats; deterministic two-stage) and y = x * gate[b,c]. */
+int es3_channel_mean(const void* x, float* ws, float* mean, int B, int HW, int C, void* stream);
+int es3_scale_channels(const void* x, const float* gate, void* y, int B, int HW, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------ stage-1 loss */
+/* Masked MSE + masked cosine KD loss, forward (stage1/train_image_encoder_stage1.py:205-210, 271-307).
+ * preds / teacher [B,C,E,E] fp32 NCHW; sizes_hw int32 [B][2] (h, w before padding); ws: B*ceil(E*E/256)*3 floats;
+ * out3 = (loss, mse, cosine); per_sample [B][3] optional. */
+int es3_kd_loss_fwd(const float* preds, const float* teacher, const int* sizes_hw, int B, int C, int E, int img_size,
+                    float cosine_weight, float* ws, float* out3, float* per_sample, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,65 @@
+"""Oracle: RepViT backbone as used by the stage-1 student (TEST INFRASTRUCTURE ONLY).
+Restates sam3/sam3/backbones/repvit.py: Conv2d_BN :27-49, Residual :51-81, RepVGGDW :84-122, RepViTBlock :125-161,
+RepViT.features :219-246, configs :253-384; SqueezeExcite = timm.layers.SqueezeExcite(inp, 0.25) (un-vendored;
+mean_HW -> fc1 (1x1, bias) -> ReLU -> fc2 (1x1, bias) -> sigmoid gate); RepViTAdapter stage1/model.py:287-296.
+Eval mode, un-fused (exactly what the reference module executes)."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+CFGS = {
+    "repvit_m1_1": [[3, 2, 64, 1, 0, 1], [3, 2, 64, 0, 0, 1], [3, 2, 64, 0, 0, 1], [3, 2, 128, 0, 0, 2], [3, 2, 128, 1, 0, 1],
+                    [3, 2, 128, 0, 0, 1], [3, 2, 128, 0, 0, 1], [3, 2, 256, 0, 1, 2], [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1],
+                    [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1], [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1], [3, 2, 256, 1, 1, 1],
+                    [3, 2, 256, 0, 1, 1], [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1], [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1],
+                    [3, 2, 256, 0, 1, 1], [3, 2, 512, 0, 1, 2], [3, 2, 512, 1, 1, 1], [3, 2, 512, 0, 1, 1]],
+}
+
+
+def conv_bn(sd, p, x, stride=1, pad=0, groups=1):
+    x = F.conv2d(x, sd[p + ".c.weight"], None, stride=stride, padding=pad, groups=groups)
+    return F.batch_norm(x, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"], sd[p + ".bn.weight"], sd[p + ".bn.bias"],
+                        training=False, eps=1e-5)
+
+
+def squeeze_excite(sd, p, x):
+    s = x.mean((2, 3), keepdim=True)
+    s = F.relu(F.conv2d(s, sd[p + ".fc1.weight"], sd[p + ".fc1.bias"]))
+    s = F.conv2d(s, sd[p + ".fc2.weight"], sd[p + ".fc2.bias"])
+    return x * torch.sigmoid(s)
+
+
+def block(sd, p, x, stride, use_se):
+    c = x.shape[1]
+    if stride == 2:
+        x = conv_bn(sd, p + ".token_mixer.0", x, stride=2, pad=1, groups=c)
+        if use_se:
+            x = squeeze_excite(sd, p + ".token_mixer.1", x)
+        x = conv_bn(sd, p + ".token_mixer.2", x)
+    else:
+        q = p + ".token_mixer.0"
+        y = conv_bn(sd, q + ".conv", x, pad=1, groups=c) + F.conv2d(x, sd[q + ".conv1.weight"], sd[q + ".conv1.bias"], groups=c) + x
+        x = F.batch_norm(y, sd[q + ".bn.running_mean"], sd[q + ".bn.running_var"], sd[q + ".bn.weight"], sd[q + ".bn.bias"],
+                         training=False, eps=1e-5)
+        if use_se:
+            x = squeeze_excite(sd, p + ".token_mixer.1", x)
+    m = p + ".channel_mixer.m"
+    return x + conv_bn(sd, m + ".2", F.gelu(conv_bn(sd, m + ".0", x)))
+
+
+def backbone(sd, p, x, variant="repvit_m1_1", return_blocks=False):
+    """RepViTAdapter.forward: iterate model.features (stage1/model.py:293-296)."""
+    f = p + "features."
+    x = conv_bn(sd, f + "0.0", x, stride=2, pad=1)
+    x = conv_bn(sd, f + "0.2", F.gelu(x), stride=2, pad=1)
+    outs = []
+    for i, (k, t, c, se, hs, s) in enumerate(CFGS[variant], 1):
+        x = block(sd, f"{f}{i}", x, s, bool(se))
+        outs.append(x)
+    return (x, outs) if return_blocks else x
+
+
+def image_student_encoder(sd, x, embed_size, variant="repvit_m1_1"):
+    from .efficientvit import student_head
+    return student_head(sd, backbone(sd, "backbone.model.", x, variant), embed_size)

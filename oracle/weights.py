@@ -29,6 +29,10 @@ def fill_state_dict(sd: dict, seed: int) -> dict:
             v = torch.randn(shape, generator=g) * 0.1
         elif t.dim() <= 1 and leaf == "weight":          # norm scale (BN / LN / LayerNorm2d)
             v = torch.rand(shape, generator=g) + 0.5
+            if ".channel_mixer.m.2.bn." in key:          # RepViT residual tails (reference init: 0): keep the
+                v = v * 0.25                             # 24-block residual stream O(1) instead of O(2^24)
+            if ".token_mixer.0.bn." in key:              # RepVGGDW output BN sums three branches (3x the variance)
+                v = v * 0.55
         elif t.dim() <= 1:                                # biases, LayerScale-like vectors
             v = torch.randn(shape, generator=g) * 0.1
         elif "positional_encoding_gaussian_matrix" in key:   # PositionEmbeddingRandom buffer: unit normal

@@ -151,6 +151,8 @@ def gen_neck(tag, dim, d_model, hw, B, seed_w, seed_x):
 
 
 def main(which):
+    if which in ("rvm", "all"):
+        gen_student("repvit_m1_1", "rvm_160", img=160, embed=12, seed_w=51, seed_x=52, batch=1)
     if which in ("neck", "all"):
         gen_neck("neck_small", dim=128, d_model=64, hw=6, B=2, seed_w=31, seed_x=32)
     if which in ("heads", "all"):

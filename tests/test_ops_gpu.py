@@ -233,3 +233,25 @@ def test_mbconv_fused_uninstantiated_shape_returns_none(cuda):
     y = ops.mbconv_fused(x, z(192, 48).bfloat16(), z(192), z(192), z(9, 192), z(192), z(48, 192).bfloat16(), z(48), z(48),
                          1, True, "hswish")
     assert y is None
+
+
+@pytest.mark.parametrize("H,W,Cout", [(64, 64, 64), (63, 41, 64), (20, 36, 32)])
+def test_conv3x3_s2_c32(cuda, H, W, Cout):
+    from efficientsam3_b200 import ops
+    g = torch.Generator().manual_seed(H + Cout)
+    x = _bf(torch.randn(2, H, W, 32, generator=g)).to(cuda)
+    w = _bf(torch.randn(Cout, 32, 3, 3, generator=g) / 17).to(cuda)
+    sc = (torch.rand(Cout, generator=g) + 0.5).to(cuda); bi = torch.randn(Cout, generator=g).to(cuda)
+    out = ops.conv3x3_s2_c32(x, w.permute(2, 3, 0, 1).reshape(9, Cout, 32).contiguous(), sc, bi, None)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), stride=2, padding=1) * sc.view(1, -1, 1, 1) + bi.view(1, -1, 1, 1)
+    _close(out, ref.permute(0, 2, 3, 1), 1e-2, "conv3x3_s2_c32")
+
+
+def test_squeeze_excite_pieces(cuda):
+    from efficientsam3_b200 import ops
+    x = _bf(torch.randn(3, 17, 19, 128, generator=torch.Generator().manual_seed(2))).to(cuda)
+    m = ops.channel_mean(x)
+    _close(m, x.float().mean((1, 2)), 1e-5, "channel_mean")
+    gate = torch.rand(3, 128, device=cuda)
+    y = ops.scale_channels(x, gate)
+    _close(y, x.float() * gate.view(3, 1, 1, 128), 1e-2, "scale_channels")

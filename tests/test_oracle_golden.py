@@ -95,3 +95,13 @@ def test_neck_oracle_matches_reference():
             outs = O.neck(sd, x, prefix=pref)
             for i, t in enumerate(outs):
                 _assert_close(t.numpy(), g[f"{name}_{i}"], rtol=2e-5)
+
+
+def test_repvit_oracle_matches_reference():
+    from oracle import repvit as O
+    g = _load("rvm_160")
+    sd = _sd_from_keys(g["keys"], int(g["seed_w"]))
+    x = torch.randn(int(g["batch"]), 3, int(g["img"]), int(g["img"]), generator=torch.Generator().manual_seed(int(g["seed_x"])))
+    with torch.no_grad():
+        out = O.image_student_encoder(sd, x, int(g["embed"]))
+    _assert_close(out.numpy(), g["out"], rtol=2e-5)

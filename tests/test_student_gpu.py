@@ -78,3 +78,33 @@ def test_train_mode_is_refused(cuda):
     m = _build(160, 12, sd_from_keys(g["keys"], 1), cuda).train()
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 3, 160, 160, device=cuda))
+
+
+def _build_rv(img, embed, sd, dev):
+    from efficientsam3_b200.stage1.model import build_image_student_model
+    cfg = NS(MODEL=NS(BACKBONE="repvit_m1_1"), DATA=NS(IMG_SIZE=img), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=embed))
+    m = build_image_student_model(cfg)
+    m.load_state_dict(sd)
+    return m.to(dev).eval()
+
+
+def test_rvm_matches_reference_fixture(cuda):
+    g = load_golden("rvm_160")
+    sd = sd_from_keys(g["keys"], int(g["seed_w"]))
+    img, embed = int(g["img"]), int(g["embed"])
+    m = _build_rv(img, embed, sd, cuda)
+    x = torch.randn(int(g["batch"]), 3, img, img, generator=torch.Generator().manual_seed(int(g["seed_x"])))
+    out = m(x.to(cuda)).cpu()
+    _check(out, g["out"], "rvm_160 vs reference fixture")
+
+
+@pytest.mark.parametrize("img,embed,batch", [(256, 18, 2), (1024, 64, 1)])
+def test_rvm_matches_oracle(cuda, img, embed, batch):
+    from oracle import repvit as O
+    g = load_golden("rvm_160")
+    sd = sd_from_keys(g["keys"], 77)
+    x = torch.randn(batch, 3, img, img, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        ref = O.image_student_encoder(sd, x, embed)
+    out = _build_rv(img, embed, sd, cuda)(x.to(cuda)).cpu()
+    _check(out, ref, f"rvm {img} vs oracle")
