@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -81,9 +81,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def build_student(img, embed, device):
+def build_student(img, embed, device, backbone="efficientvit_b1"):
     from efficientsam3_b200.stage1.model import build_image_student_model
-    cfg = NS(MODEL=NS(BACKBONE="efficientvit_b1"), DATA=NS(IMG_SIZE=img), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=embed))
+    cfg = NS(MODEL=NS(BACKBONE=backbone), DATA=NS(IMG_SIZE=img), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=embed))
     torch.manual_seed(0)
     m = build_image_student_model(cfg)
     with torch.no_grad():  # random-init weights of the named architecture + non-trivial BN statistics
@@ -212,6 +212,11 @@ def run_native(args):
                             "alg_TFLOP_per_step": round(alg_flops / 1e12, 3),
                             "tensor_frac": round(alg_flops / 1e12 / (ms_step / 1e3) / pk["tf_sustained"], 4)}
 
+    # ---------------------------------------------------------------- the other encoders of the north-star (brief)
+    also = None
+    if rank == 0 and world == 1 and not args.no_also:
+        also = other_encoders(dev, S, E)
+
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -228,7 +233,7 @@ def run_native(args):
                        "l2_policy": f"inputs alternate between two {x_dev[0].numel()*4/1e6:.0f} MB buffers (> 126 MB L2)"},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": host[0].numel() * 4,
                     "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "also": also,
         }
         if kernel_table is not None and args.table:
             with open(args.table, "w") as f:
@@ -238,6 +243,48 @@ def run_native(args):
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _time_steps(fn, warm, steps):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def other_encoders(dev, S, E):
+    """Device-resident images/s of the other paths the north-star names, same run, short loops (reported beside the
+    headline; each has its own parity tests).  Teacher / config 3 run at their native 1008 px."""
+    from efficientsam3_b200.model.sam1_task import Sam3PointPromptSegmenter
+    from efficientsam3_b200.stage1.model import SAM3ImageTeacherEncoder
+    out = {}
+    torch.manual_seed(0)
+    rv = build_student(S, E, dev, "repvit_m1_1")
+    x = torch.randn(32, 3, S, S, device=dev)
+    ms = _time_steps(lambda: rv(x), 2, 5)
+    out["rvm_student_forward"] = {"images_per_s": round(32 / ms * 1e3, 1), "ms_per_step": round(ms, 3), "batch": 32, "img": S}
+    del rv, x
+    t = SAM3ImageTeacherEncoder(embed_size=72).to(dev)
+    x = torch.randn(8, 3, 1008, 1008, device=dev)
+    ms = _time_steps(lambda: t(x), 1, 3)
+    out["teacher_vit_forward"] = {"images_per_s": round(8 / ms * 1e3, 2), "ms_per_step": round(ms, 2), "batch": 8, "img": 1008,
+                                  "alg_TFLOP_per_s": round(5.4 * 8 / ms, 1)}
+    del t
+    seg = Sam3PointPromptSegmenter().to(dev)
+    coords = torch.rand(8, 1, 2, device=dev) * 1008
+    labels = torch.ones(8, 1, dtype=torch.int32, device=dev)
+    ms = _time_steps(lambda: seg.set_image_batch(x).predict_batch(coords, labels, multimask_output=True), 1, 3)
+    out["config3_vit_fpn_mask_decoder"] = {"images_per_s": round(8 / ms * 1e3, 2), "ms_per_step": round(ms, 2), "batch": 8,
+                                           "img": 1008, "prompt": "1 point / image, multimask"}
+    del seg, x
+    torch.cuda.empty_cache()
+    return out
 
 
 def cpu_oracle_throughput(S, E, batch, steps, warmup):
@@ -289,13 +336,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--img", type=int, default=1024)
     ap.add_argument("--embed", type=int, default=64, help="stage1/config.py:21,50 pair IMG_SIZE 1024 with EMBED_SIZE 64")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-also", action="store_true", help="skip the brief RV-M / teacher / config-3 measurements")
     ap.add_argument("--table", default=None, help="write the per-kernel-family table (markdown) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
