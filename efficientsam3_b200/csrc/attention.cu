@@ -44,7 +44,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 }  // namespace
 
-constexpr int AT_BM = 64, AT_BN = 64, AT_D = 64, AT_RS = AT_D * 2 + 16;  // smem row stride (bytes)
+constexpr int AT_BN = 64, AT_D = 64, AT_RS = AT_D * 2 + 16;  // smem row stride (bytes)
 
 struct AttnArgs {
   const bf16* qkv;  // [B*H*W, 3*C]
@@ -61,10 +61,16 @@ __device__ __forceinline__ long long token_row(const AttnArgs& a, int b, int wi,
   return (long long)b * a.H * a.W + (long long)(wy * a.win + i) * a.W + wx * a.win + j;
 }
 
+// MT = 16-row query tiles per warp.  K/V fragments loaded by ldmatrix are reused for all MT tiles: on this part
+// one m16n8k16 MMA (1 tensor-pipe cycle per SM at 2048 FMA/clk) consumes a 256-byte B fragment, i.e. 2 cycles of the
+// 128 B/clk shared-memory pipe -- with MT = 1 the kernel is smem-bandwidth-bound (profiles/r1_teacher.md).
+template <int MT>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
-  __shared__ __align__(16) uint8_t s_q[AT_BM * AT_RS];
-  __shared__ __align__(16) uint8_t s_k[2][AT_BN * AT_RS];
-  __shared__ __align__(16) uint8_t s_v[2][AT_BN * AT_RS];
+  constexpr int AT_BM = 64 * MT;
+  extern __shared__ __align__(16) uint8_t at_smem[];
+  uint8_t* s_q = at_smem;
+  uint8_t (*s_k)[AT_BN * AT_RS] = reinterpret_cast<uint8_t (*)[AT_BN * AT_RS]>(at_smem + AT_BM * AT_RS);
+  uint8_t (*s_v)[AT_BN * AT_RS] = reinterpret_cast<uint8_t (*)[AT_BN * AT_RS]>(at_smem + AT_BM * AT_RS + 2 * AT_BN * AT_RS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x, head = blockIdx.y;
@@ -74,8 +80,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
   const bf16* kbase = qbase + a.C;
   const bf16* vbase = qbase + 2 * a.C;
   const uint32_t u_q = static_cast<uint32_t>(__cvta_generic_to_shared(s_q));
-  const uint32_t u_k = static_cast<uint32_t>(__cvta_generic_to_shared(s_k));
-  const uint32_t u_v = static_cast<uint32_t>(__cvta_generic_to_shared(s_v));
+  const uint32_t u_k = static_cast<uint32_t>(__cvta_generic_to_shared(&s_k[0][0]));
+  const uint32_t u_v = static_cast<uint32_t>(__cvta_generic_to_shared(&s_v[0][0]));
 
   // ---- async loads: Q tile, then KV tile 0
   for (int i = tid; i < AT_BM * 8; i += 128) {
@@ -103,11 +109,16 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
   const int v_k = (lane & 7) + (((lane >> 3) & 1) << 3), v_n = (lane >> 4) << 3;  // B from [k][n] storage (.trans)
   const int g = lane >> 2, t4 = lane & 3;
 
-  float o[8][4];
+  float o[MT][8][4];
+  float m_run[MT][2], l_run[MT][2];
+  uint32_t qf[MT][4][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-  uint32_t qf[4][4];
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[mt][i][0] = o[mt][i][1] = o[mt][i][2] = o[mt][i][3] = 0.f; }
+    m_run[mt][0] = m_run[mt][1] = -INFINITY;
+    l_run[mt][0] = l_run[mt][1] = 0.f;
+  }
 
   const int ntiles = (a.L + AT_BN - 1) / AT_BN;
   for (int t = 0; t < ntiles; ++t) {
@@ -122,13 +133,18 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
     __syncthreads();
     if (t == 0) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        ldsm4(u_q + (warp * 16 + a_row) * AT_RS + (ks * 16 + a_kh * 8) * 2, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-    }
-    // ---- S = Q K^T
-    float s[8][4];
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+        for (int ks = 0; ks < 4; ++ks)
+          ldsm4(u_q + ((warp * MT + mt) * 16 + a_row) * AT_RS + (ks * 16 + a_kh * 8) * 2, qf[mt][ks][0], qf[mt][ks][1],
+                qf[mt][ks][2], qf[mt][ks][3]);
+    }
+    // ---- S = Q K^T (K fragments shared by the MT query tiles)
+    float s[MT][8][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[mt][i][0] = s[mt][i][1] = s[mt][i][2] = s[mt][i][3] = 0.f; }
     const uint32_t kb = u_k + buf * (AT_BN * AT_RS);
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -136,53 +152,59 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
       for (int np = 0; np < 4; ++np) {
         uint32_t b0, b1, b2, b3;
         ldsm4(kb + (np * 16 + b_n) * AT_RS + (ks * 16 + b_kh * 8) * 2, b0, b1, b2, b3);
-        mma16816(s[2 * np], qf[ks], b0, b1);
-        mma16816(s[2 * np + 1], qf[ks], b2, b3);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma16816(s[mt][2 * np], qf[mt][ks], b0, b1);
+          mma16816(s[mt][2 * np + 1], qf[mt][ks], b2, b3);
+        }
       }
     }
-    // ---- online softmax (rows g and g+8 of this warp's 16)
+    // ---- online softmax (rows g and g+8 of each 16-row tile)
     const int col0 = t * AT_BN;
-    float mx[2] = {-INFINITY, -INFINITY};
+    uint32_t pf[MT][4][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int mt = 0; mt < MT; ++mt) {
+      float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = col0 + nt * 8 + t4 * 2 + (e & 1);
-        float v = s[nt][e] * a.scale_log2;
-        if (col >= a.L) v = -INFINITY;
-        s[nt][e] = v;
-        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = col0 + nt * 8 + t4 * 2 + (e & 1);
+          float v = s[mt][nt][e] * a.scale_log2;
+          if (col >= a.L) v = -INFINITY;
+          s[mt][nt][e] = v;
+          mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        }
+      }
+      float corr[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float m_new = fmaxf(m_run[mt][r], mx[r]);
+        corr[r] = fast_exp2(m_run[mt][r] - m_new);   // first tile: exp2(-inf) = 0
+        m_run[mt][r] = m_new;
+        l_run[mt][r] *= corr[r];
+      }
+      float rs[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float p0 = fast_exp2(s[mt][nt][0] - m_run[mt][0]), p1 = fast_exp2(s[mt][nt][1] - m_run[mt][0]);
+        const float p2 = fast_exp2(s[mt][nt][2] - m_run[mt][1]), p3 = fast_exp2(s[mt][nt][3] - m_run[mt][1]);
+        rs[0] += p0 + p1;
+        rs[1] += p2 + p3;
+        pf[mt][nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+        pf[mt][nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      }
+      l_run[mt][0] += rs[0];
+      l_run[mt][1] += rs[1];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        o[mt][nt][0] *= corr[0]; o[mt][nt][1] *= corr[0];
+        o[mt][nt][2] *= corr[1]; o[mt][nt][3] *= corr[1];
       }
     }
-    float corr[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      const float m_new = fmaxf(m_run[r], mx[r]);
-      corr[r] = fast_exp2(m_run[r] - m_new);   // first tile: exp2(-inf) = 0
-      m_run[r] = m_new;
-      l_run[r] *= corr[r];
-    }
-    uint32_t pf[4][4];
-    float rs[2] = {0.f, 0.f};
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = fast_exp2(s[nt][0] - m_run[0]), p1 = fast_exp2(s[nt][1] - m_run[0]);
-      const float p2 = fast_exp2(s[nt][2] - m_run[1]), p3 = fast_exp2(s[nt][3] - m_run[1]);
-      rs[0] += p0 + p1;
-      rs[1] += p2 + p3;
-      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
-    }
-    l_run[0] += rs[0];
-    l_run[1] += rs[1];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      o[nt][0] *= corr[0]; o[nt][1] *= corr[0];
-      o[nt][2] *= corr[1]; o[nt][3] *= corr[1];
-    }
-    // ---- O += P V
+    // ---- O += P V (V fragments shared by the MT query tiles)
     const uint32_t vb = u_v + buf * (AT_BN * AT_RS);
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {      // 16 kv rows per step
@@ -190,8 +212,11 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
       for (int np = 0; np < 4; ++np) {    // two 8-wide d tiles per ldmatrix
         uint32_t b0, b1, b2, b3;
         ldsm4t(vb + (ks * 16 + v_k) * AT_RS + (np * 16 + v_n) * 2, b0, b1, b2, b3);
-        mma16816(o[2 * np], pf[ks], b0, b1);
-        mma16816(o[2 * np + 1], pf[ks], b2, b3);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma16816(o[mt][2 * np], pf[mt][ks], b0, b1);
+          mma16816(o[mt][2 * np + 1], pf[mt][ks], b2, b3);
+        }
       }
     }
     __syncthreads();  // all warps done with buf before the next iteration's prefetch overwrites it
@@ -199,15 +224,19 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
 
   // ---- normalise, stage through smem (Q tile is dead), 16-byte stores
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
-    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
-  }
-  const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+  for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    *reinterpret_cast<uint32_t*>(s_q + (warp * 16 + g) * AT_RS + (nt * 8 + t4 * 2) * 2) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
-    *reinterpret_cast<uint32_t*>(s_q + (warp * 16 + g + 8) * AT_RS + (nt * 8 + t4 * 2) * 2) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
+    for (int r = 0; r < 2; ++r) {
+      l_run[mt][r] += __shfl_xor_sync(0xffffffffu, l_run[mt][r], 1);
+      l_run[mt][r] += __shfl_xor_sync(0xffffffffu, l_run[mt][r], 2);
+    }
+    const float inv0 = 1.f / l_run[mt][0], inv1 = 1.f / l_run[mt][1];
+    const int r0 = (warp * MT + mt) * 16 + g;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      *reinterpret_cast<uint32_t*>(s_q + r0 * AT_RS + (nt * 8 + t4 * 2) * 2) = pack_bf16x2(o[mt][nt][0] * inv0, o[mt][nt][1] * inv0);
+      *reinterpret_cast<uint32_t*>(s_q + (r0 + 8) * AT_RS + (nt * 8 + t4 * 2) * 2) = pack_bf16x2(o[mt][nt][2] * inv1, o[mt][nt][3] * inv1);
+    }
   }
   __syncthreads();
   for (int i = tid; i < AT_BM * 8; i += 128) {
@@ -236,8 +265,19 @@ extern "C" int es3_attention_bf16(const void* qkv, void* out, int B, int H, int 
   a.nwin = win ? (H / win) * (W / win) : 1;
   a.L = win ? win * win : H * W;
   a.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid(ceil_div(a.L, AT_BM), num_heads, B * a.nwin);
-  attn_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  // two 16-row query tiles per warp (128-row CTA tile) whenever the sequence fills it; one otherwise
+  const bool mt2 = a.L >= 128;
+  const int bm = mt2 ? 128 : 64;
+  const size_t smem = (size_t)(bm + 4 * AT_BN) * AT_RS;
+  static bool configured = false;
+  if (!configured) {
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  dim3 grid(ceil_div(a.L, bm), num_heads, B * a.nwin);
+  if (mt2) attn_fwd_kernel<2><<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+  else attn_fwd_kernel<1><<<grid, 128, smem, (cudaStream_t)stream>>>(a);
   ES3_LAUNCH_CHECK("attn_fwd_kernel");
   return 0;
 }

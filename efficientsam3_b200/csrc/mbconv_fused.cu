@@ -70,7 +70,7 @@ struct MBArgs {
 };
 
 template <int CIN, int MID, int COUT, int STRIDE, bool RES, int ACT>
-__global__ void __launch_bounds__(256) mbconv_fused_kernel(const MBArgs a) {
+__global__ void __launch_bounds__(256, 2) mbconv_fused_kernel(const MBArgs a) {
   using C = MBCfg<CIN, MID, COUT, STRIDE>;
   static_assert(CIN % 16 == 0 && MID % 64 == 0 && COUT % 16 == 0, "channel multiples");
   static_assert(!RES || (CIN == COUT && STRIDE == 1), "residual needs matching shapes");
@@ -208,31 +208,41 @@ __global__ void __launch_bounds__(256) mbconv_fused_kernel(const MBArgs a) {
     {
       const int cg = warp & 3;
       const uint32_t* bf = s_bfrag + cg * 64 + lane;
-#pragma unroll 1
-      for (int mt = warp >> 2; mt < C::TH; mt += 2) {
-        float d[2][4];
+      constexpr int MT_PER_WARP = C::TH / 2;   // m-tiles (tile rows) per warp: rows warp/4, +2, +4, ...
+      // taps outer / m-tiles inner: MT_PER_WARP x 2 independent accumulator chains keep the tensor pipe busy
+      // (a single m-tile is a 9-deep dependent HMMA chain; profiles/r1_mbconv_ncu.md)
+      float d[MT_PER_WARP][2][4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) { d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f; }
+      for (int m = 0; m < MT_PER_WARP; ++m)
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+        for (int i = 0; i < 2; ++i) { d[m][i][0] = d[m][i][1] = d[m][i][2] = d[m][i][3] = 0.f; }
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const uint32_t b_lo = bf[(ky * 3 + kx) * 256], b_hi = bf[(ky * 3 + kx) * 256 + 32];
+      for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint32_t b_lo = bf[(ky * 3 + kx) * 256], b_hi = bf[(ky * 3 + kx) * 256 + 32];
+#pragma unroll
+          for (int m = 0; m < MT_PER_WARP; ++m) {
+            const int mt = (warp >> 2) + 2 * m;
             uint32_t af[4];
             ldsm_x4(u_mid + ((mt * STRIDE + ky) * C::HWD + a_row * STRIDE + kx) * C::RS_MID + (cg * 16 + a_kh * 8) * 2,
                     af[0], af[1], af[2], af[3]);
-            mma_bf16_16816(d[0], af, b_lo, 0u);
-            mma_bf16_16816(d[1], af, 0u, b_hi);
+            mma_bf16_16816(d[m][0], af, b_lo, 0u);
+            mma_bf16_16816(d[m][1], af, 0u, b_hi);
           }
         }
+      }
+#pragma unroll
+      for (int m = 0; m < MT_PER_WARP; ++m) {
+        const int mt = (warp >> 2) + 2 * m;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int p = mt * C::TW + g + half * 8;
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt) {
             const int c = cg * 16 + nt * 8 + t4 * 2;
-            const float v0 = es3_act_t<ACT>(d[nt][half * 2 + 0] + s_b2[c]);
-            const float v1 = es3_act_t<ACT>(d[nt][half * 2 + 1] + s_b2[c + 1]);
+            const float v0 = es3_act_t<ACT>(d[m][nt][half * 2 + 0] + s_b2[c]);
+            const float v1 = es3_act_t<ACT>(d[m][nt][half * 2 + 1] + s_b2[c + 1]);
             *reinterpret_cast<uint32_t*>(s_dw + p * C::RS_MID + c * 2) = pack_bf16x2(v0, v1);
           }
         }
