@@ -255,8 +255,22 @@ using namespace es3;
 
 // qkv [B*H*W, 3*C] bf16 (q|k|v, heads of 64 inside each) -> out [B*H*W, C] bf16.
 // win > 0: attention inside non-overlapping win x win windows (H, W multiples of win); win == 0: global.
+extern "C" int es3_attention_tc_bf16(const void* qkv, void* out, int B, int H, int W, int C, int num_heads, int win,
+                                     float scale, void* stream);
+
+// Dispatcher: sequences of >= 128 tokens run the tcgen05 / TMEM kernel (attention_tc.cu); shorter windows (only
+// reached by reduced-size test configurations) use the warp-level mma.sync kernel below.
+extern "C" int es3_attention_mma_bf16(const void* qkv, void* out, int B, int H, int W, int C, int num_heads, int win,
+                                      float scale, void* stream);
 extern "C" int es3_attention_bf16(const void* qkv, void* out, int B, int H, int W, int C, int num_heads, int win,
                                   float scale, void* stream) {
+  const int L = win ? win * win : H * W;
+  if (L >= 128) return es3_attention_tc_bf16(qkv, out, B, H, W, C, num_heads, win, scale, stream);
+  return es3_attention_mma_bf16(qkv, out, B, H, W, C, num_heads, win, scale, stream);
+}
+
+extern "C" int es3_attention_mma_bf16(const void* qkv, void* out, int B, int H, int W, int C, int num_heads, int win,
+                                      float scale, void* stream) {
   ES3_REQUIRE(C == num_heads * AT_D, "es3_attention_bf16: head_dim must be 64 (C=%d heads=%d)", C, num_heads);
   ES3_REQUIRE(win == 0 || (H % win == 0 && W % win == 0), "es3_attention_bf16: H,W must be multiples of the window (%d,%d,%d)", H, W, win);
   AttnArgs a;

@@ -315,14 +315,14 @@ def im2col_patch(x, P, Kp):
     return cols
 
 
-def attention(qkv, B, H, W, C, num_heads, win, scale):
-    """qkv: [B*H*W, 3C] bf16 -> [B*H*W, C] bf16."""
+def attention(qkv, B, H, W, C, num_heads, win, scale, impl=None):
+    """qkv: [B*H*W, 3C] bf16 -> [B*H*W, C] bf16.  impl: None (dispatch), "tc" (tcgen05), "mma" (mma.sync)."""
     _chk(qkv, torch.bfloat16, "qkv")
     _ensure_init(qkv)
     assert qkv.is_contiguous() and qkv.shape == (B * H * W, 3 * C)
     out = torch.empty((B * H * W, C), device=qkv.device, dtype=torch.bfloat16)
     L = win * win if win else H * W
-    _call("es3_attention_bf16", f"attention[L={L}]", _nb(qkv, out), 4 * B * H * W * L * C, qkv.data_ptr(), out.data_ptr(),
+    _call({None: "es3_attention_bf16", "tc": "es3_attention_tc_bf16", "mma": "es3_attention_mma_bf16"}[impl], f"attention[L={L}]", _nb(qkv, out), 4 * B * H * W * L * C, qkv.data_ptr(), out.data_ptr(),
           B, H, W, C, num_heads, win, float(scale), _stream())
     return out
 

@@ -133,6 +133,12 @@ int es3_im2col_patch(const float* x, void* cols, int B, int S, int P, int Kp, vo
  * Replaces window_partition + F.scaled_dot_product_attention + window_unpartition (vitdet.py:93-139, 502). */
 int es3_attention_bf16(const void* qkv, void* out, int B, int H, int W, int C, int num_heads, int win, float scale,
                        void* stream);
+/* The two implementations behind es3_attention_bf16: tcgen05 / TMEM flash attention (QK^T and PV as UMMAs, P kept in
+ * TMEM; used for L >= 128) and the warp-level mma.sync kernel (short windows; also the on-device cross-check). */
+int es3_attention_tc_bf16(const void* qkv, void* out, int B, int H, int W, int C, int num_heads, int win, float scale,
+                          void* stream);
+int es3_attention_mma_bf16(const void* qkv, void* out, int B, int H, int W, int C, int num_heads, int win, float scale,
+                           void* stream);
 /* [B, HW, C] fp32 tokens -> [B, C, HW] fp32 (the NCHW map ViT.forward returns, vitdet.py:846-857). */
 int es3_tokens_f32_to_nchw(const float* in, float* out, int B, int HW, int C, void* stream);
 

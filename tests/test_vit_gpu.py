@@ -59,14 +59,15 @@ def test_patch_embed(cuda):
     _close(out, ref, 2e-3, "patch embed")
 
 
+@pytest.mark.parametrize("impl", [None, "mma", "tc"])
 @pytest.mark.parametrize("B,H,W,heads,win", [(2, 8, 8, 4, 4), (1, 24, 24, 2, 8), (2, 24, 24, 2, 0), (1, 72, 72, 2, 24),
-                                             (1, 72, 72, 1, 0), (3, 6, 10, 2, 2)])
-def test_attention(cuda, B, H, W, heads, win):
+                                             (1, 72, 72, 1, 0), (3, 6, 10, 2, 2), (1, 36, 20, 2, 0), (2, 16, 16, 1, 0)])
+def test_attention(cuda, B, H, W, heads, win, impl):
     from efficientsam3_b200 import ops
     C = heads * 64
     g = torch.Generator().manual_seed(H * 7 + win)
     qkv = _bf(torch.randn(B * H * W, 3 * C, generator=g)).to(cuda)
-    out = ops.attention(qkv, B, H, W, C, heads, win, 0.125)
+    out = ops.attention(qkv, B, H, W, C, heads, win, 0.125, impl=impl)
     t = qkv.float().view(B, H, W, 3, heads, 64)
     if win:
         t = t.view(B, H // win, win, W // win, win, 3, heads, 64).permute(0, 1, 3, 2, 4, 5, 6, 7).reshape(-1, win * win, 3, heads, 64)
