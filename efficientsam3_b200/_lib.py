@@ -18,7 +18,9 @@ _vp, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 SIGNATURES: dict[str, list] = {
     "es3_init": [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
     "es3_gemm_bf16": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _i, _vp],
-    "es3_gemm_bf16_ex": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "es3_gemm_bf16_ex": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "es3_win_attn_bias_bf16": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "es3_layernorm_bf16": [_vp, _vp, _vp, _f, _vp, _ll, _i, _vp],
     "es3_layernorm_f32": [_vp, _vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _ll, _i, _vp],
     "es3_im2col_patch": [_vp, _vp, _i, _i, _i, _i, _vp],
     "es3_attention_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],

@@ -412,19 +412,19 @@ using namespace es3;
 extern "C" int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
                                 int out_f32, int M, int N, int K, const float* scale, const float* bias, int act,
                                 const void* residual, long long ldr, int res_f32, const float* rope, int rope_cols,
-                                int rope_H, int rope_W, int rope_win, int bn_hint, void* stream);
+                                int rope_H, int rope_W, int rope_win, int act_after_res, int bn_hint, void* stream);
 
 extern "C" int es3_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
                              int out_f32, int M, int N, int K, const float* scale, const float* bias, int act,
                              const void* residual, long long ldr, int bn_hint, void* stream) {
   return es3_gemm_bf16_ex(A, lda, W, ldw, out, ldo, out_f32, M, N, K, scale, bias, act, residual, ldr, 0, nullptr, 0, 0,
-                          0, 0, bn_hint, stream);
+                          0, 0, 0, bn_hint, stream);
 }
 
 extern "C" int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
                                 int out_f32, int M, int N, int K, const float* scale, const float* bias, int act,
                                 const void* residual, long long ldr, int res_f32, const float* rope, int rope_cols,
-                                int rope_H, int rope_W, int rope_win, int bn_hint, void* stream) {
+                                int rope_H, int rope_W, int rope_win, int act_after_res, int bn_hint, void* stream) {
   ES3_REQUIRE(M > 0 && N > 0 && K > 0, "es3_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
   ES3_REQUIRE(rope == nullptr || (rope_cols % 64 == 0 && rope_cols <= N && rope_H > 0 && rope_W > 0 &&
                                   M % (rope_H * rope_W) == 0 && ((uintptr_t)rope & 15) == 0),
@@ -459,6 +459,7 @@ extern "C" int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, lon
   a.scale = scale; a.bias = bias; a.act = act;
   a.residual = (const bf16*)residual; a.ldr = ldr; a.res_f32 = res_f32;
   a.rope = (const float2*)rope; a.rope_cols = rope_cols; a.rope_H = rope_H; a.rope_W = rope_W; a.rope_win = rope_win;
+  a.act_after_res = act_after_res;
   a.out = out; a.ldo = ldo; a.out_f32 = out_f32;
   return dispatch(bn, tmA, tmB, a, ceil_div(M, BM), (cudaStream_t)stream);
 }

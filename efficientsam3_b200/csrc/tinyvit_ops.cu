@@ -1,0 +1,235 @@
+// TinyViT-specific kernels (sam3/sam3/backbones/tiny_vit.py):
+//   * window attention with the learned relative-position bias (Attention :219-293) on window partitions with zero
+//     padding (TinyViTBlock.forward :344-375): windows are gathered in place from the raster token map; positions
+//     outside the map take the per-block constant qkv(LN(0)) vector, exactly like the reference's padded tokens.
+//     head_dim 32, N = ws*ws in {49, 196}.  One CTA per (window, head): S = QK^T on mma.sync with the whole
+//     score row block in registers, + bias, softmax, PV on mma.sync.
+//   * LayerNorm over bf16 rows with arbitrary C % 8 == 0 (C = 448 is not a multiple of 128).
+#include "common.cuh"
+
+namespace es3 {
+namespace {
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+}  // namespace
+
+constexpr int WA_HD = 32, WA_RS = WA_HD * 2 + 16;  // smem row: 32 bf16 = 64 B + 16 B pad
+
+struct WinAttnArgs {
+  const bf16* qkv;      // [B*H*W, 3*C], per head h: cols [h*96, +32) q | [+32, +64) k | [+64, +96) v
+  const bf16* qkv_pad;  // [3*C] value of a zero-padded token (qkv(LN(0)))
+  const float* bias;    // [heads][N][N]
+  bf16* out;            // [B*H*W, C]
+  int H, W, C, ws, nWx, nWin, N;
+  float scale;
+};
+
+// NT16 = ceil(N / 16): number of 16-row tiles (4 for N=49, 13 for N=196).  The query tiles of a window are split over
+// gridDim.z CTAs of blockDim/32 warps each (the 26x4 score registers per thread cap a CTA at ~7 warps); every CTA
+// stages the whole window's K / V.
+template <int NT16>
+__global__ void win_attn_bias_kernel(const WinAttnArgs a) {
+  constexpr int NP = NT16 * 16;
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* s_q = smem;
+  uint8_t* s_k = s_q + NP * WA_RS;
+  uint8_t* s_v = s_k + NP * WA_RS;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = blockIdx.z * (blockDim.x >> 5) + (tid >> 5);   // query tile handled by this warp
+  const int head = blockIdx.y;
+  const int b = blockIdx.x / a.nWin, wi = blockIdx.x % a.nWin;
+  const int wy = wi / a.nWx, wx = wi % a.nWx;
+  const int ld = 3 * a.C;
+  // ---- gather q, k, v rows of this window / head (4 x 16-byte chunks each); rows >= N are zero
+  for (int i = tid; i < NP * 12; i += blockDim.x) {
+    const int c = i % 12, r = i / 12;         // c: 0..3 q, 4..7 k, 8..11 v
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (r < a.N) {
+      const int h = wy * a.ws + r / a.ws, w = wx * a.ws + r % a.ws;
+      const bf16* src = (h < a.H && w < a.W) ? a.qkv + ((long long)b * a.H * a.W + (long long)h * a.W + w) * ld : a.qkv_pad;
+      val = *reinterpret_cast<const uint4*>(src + head * 96 + c * 8);
+    }
+    uint8_t* dst = (c < 4 ? s_q : (c < 8 ? s_k : s_v)) + r * WA_RS + (c & 3) * 16;
+    *reinterpret_cast<uint4*>(dst) = val;
+  }
+  __syncthreads();
+  if (warp >= NT16) return;
+  const uint32_t u_q = static_cast<uint32_t>(__cvta_generic_to_shared(s_q));
+  const uint32_t u_k = static_cast<uint32_t>(__cvta_generic_to_shared(s_k));
+  const uint32_t u_v = static_cast<uint32_t>(__cvta_generic_to_shared(s_v));
+  const int a_row = lane & 15, a_kh = lane >> 4;
+  const int b_n = (lane & 7) + ((lane >> 4) << 3), b_kh = (lane >> 3) & 1;
+  const int v_k = (lane & 7) + (((lane >> 3) & 1) << 3), v_n = (lane >> 4) << 3;
+  const int g = lane >> 2, t4 = lane & 3;
+
+  // ---- S = Q K^T for this warp's 16 query rows against all NP keys
+  uint32_t qf[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+    ldsm4(u_q + (warp * 16 + a_row) * WA_RS + (ks * 16 + a_kh * 8) * 2, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+  float s[2 * NT16][4];
+#pragma unroll
+  for (int i = 0; i < 2 * NT16; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+  for (int np = 0; np < NT16; ++np) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t b0, b1, b2, b3;
+      ldsm4(u_k + (np * 16 + b_n) * WA_RS + (ks * 16 + b_kh * 8) * 2, b0, b1, b2, b3);
+      mma16816(s[2 * np], qf[ks], b0, b1);
+      mma16816(s[2 * np + 1], qf[ks], b2, b3);
+    }
+  }
+  // ---- + bias, mask, softmax (rows g, g+8)
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+  const float* bias0 = a.bias + ((long long)head * a.N + min(r0, a.N - 1)) * a.N;
+  const float* bias1 = a.bias + ((long long)head * a.N + min(r1, a.N - 1)) * a.N;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 2 * NT16; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = nt * 8 + t4 * 2 + e;
+      const bool ok = col < a.N;
+      const float v0 = ok ? fmaf(s[nt][e], a.scale, __ldg(bias0 + col)) : -INFINITY;
+      const float v1 = ok ? fmaf(s[nt][2 + e], a.scale, __ldg(bias1 + col)) : -INFINITY;
+      s[nt][e] = v0; s[nt][2 + e] = v1;
+      mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t pf[NT16][4];
+#pragma unroll
+  for (int nt = 0; nt < 2 * NT16; ++nt) {
+    const float p0 = __expf(s[nt][0] - mx0), p1 = __expf(s[nt][1] - mx0);
+    const float p2 = __expf(s[nt][2] - mx1), p3 = __expf(s[nt][3] - mx1);
+    l0 += p0 + p1; l1 += p2 + p3;
+    pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+    pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // ---- O = P V   (V rows >= N are zero, P columns >= N are zero)
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+#pragma unroll
+  for (int ks = 0; ks < NT16; ++ks) {
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm4t(u_v + (ks * 16 + v_k) * WA_RS + (np * 16 + v_n) * 2, b0, b1, b2, b3);
+      mma16816(o[2 * np], pf[ks], b0, b1);
+      mma16816(o[2 * np + 1], pf[ks], b2, b3);
+    }
+  }
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int r = half ? r1 : r0;
+    if (r >= a.N) continue;
+    const int h = wy * a.ws + r / a.ws, w = wx * a.ws + r % a.ws;
+    if (h >= a.H || w >= a.W) continue;   // padded query: the reference crops it away (:373-374)
+    bf16* dst = a.out + ((long long)b * a.H * a.W + (long long)h * a.W + w) * a.C + head * WA_HD;
+    const float inv = half ? i1 : i0;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      *reinterpret_cast<uint32_t*>(dst + nt * 8 + t4 * 2) = pack_bf16x2(o[nt][half * 2] * inv, o[nt][half * 2 + 1] * inv);
+  }
+}
+
+// LayerNorm over rows of bf16, C % 8 == 0, C <= 1024.  One warp per row, values kept in registers.
+__global__ void layernorm_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      float eps, bf16* __restrict__ y, long long M, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nvec = C >> 3;
+  float v[4][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      unpack8(*reinterpret_cast<const uint4*>(x + row * C + vi * 8), v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[i][e];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * gamma[vi * 8 + e] + beta[vi * 8 + e];
+      *reinterpret_cast<uint4*>(y + row * C + vi * 8) = pack8(o);
+    }
+  }
+}
+
+}  // namespace es3
+
+using namespace es3;
+
+extern "C" int es3_win_attn_bias_bf16(const void* qkv, const void* qkv_pad, const float* bias, void* out, int B, int H, int W,
+                                      int C, int num_heads, int ws, float scale, void* stream) {
+  ES3_REQUIRE(C == num_heads * WA_HD, "es3_win_attn_bias_bf16: head_dim must be 32 (C=%d heads=%d)", C, num_heads);
+  const int N = ws * ws;
+  ES3_REQUIRE(N == 49 || N == 196, "es3_win_attn_bias_bf16: window %d not instantiated (7 or 14)", ws);
+  WinAttnArgs a;
+  a.qkv = (const bf16*)qkv; a.qkv_pad = (const bf16*)qkv_pad; a.bias = bias; a.out = (bf16*)out;
+  a.H = H; a.W = W; a.C = C; a.ws = ws; a.N = N; a.scale = scale;
+  const int nWy = ceil_div(H, ws);
+  a.nWx = ceil_div(W, ws);
+  a.nWin = nWy * a.nWx;
+  dim3 grid(B * a.nWin, num_heads);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 49) {
+    const size_t smem = (size_t)3 * 64 * WA_RS;
+    win_attn_bias_kernel<4><<<grid, 4 * 32, smem, st>>>(a);
+  } else {
+    const size_t smem = (size_t)3 * 208 * WA_RS;
+    static bool configured = false;
+    if (!configured) {
+      ES3_CHECK_CUDA(cudaFuncSetAttribute(win_attn_bias_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    grid.z = 2;
+    win_attn_bias_kernel<13><<<grid, 7 * 32, smem, st>>>(a);
+  }
+  ES3_LAUNCH_CHECK("win_attn_bias_kernel");
+  return 0;
+}
+
+extern "C" int es3_layernorm_bf16(const void* x, const float* gamma, const float* beta, float eps, void* y, long long M, int C,
+                                  void* stream) {
+  ES3_REQUIRE(C % 8 == 0 && C <= 1024, "es3_layernorm_bf16: C=%d must be a multiple of 8 and <= 1024", C);
+  layernorm_bf16_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, M, C);
+  ES3_LAUNCH_CHECK("layernorm_bf16_kernel");
+  return 0;
+}

@@ -84,7 +84,7 @@ def _ensure_init(t: torch.Tensor):
 
 
 def gemm(a, w, *, scale=None, bias=None, act=None, residual=None, out=None, out_dtype=torch.bfloat16, bn_hint=0,
-         rope=None):
+         rope=None, act_after_res=False):
     """out[m,n] = act(scale[n]*sum_k a[m,k] w[n,k] + bias[n]) (+residual).  a: [M,K] (row stride allowed),
     w: [N,K] bf16, scale/bias fp32 [N]; residual bf16 or fp32 [M,N].
     rope = (table[P,32,2] fp32, rope_cols, H, W, win): rotate columns [0, rope_cols) (see es3_gemm_bf16_ex)."""
@@ -112,7 +112,7 @@ def gemm(a, w, *, scale=None, bias=None, act=None, residual=None, out=None, out_
     _call("es3_gemm_bf16_ex", f"gemm_tc[K={K},N={N}]", M * K * 2 + M * N * out.element_size() + _nb(w, residual),
           2 * M * N * K, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
           int(out.dtype == torch.float32), M, N, K, _ptr(scale), _ptr(bias), ACT[act], _ptr(residual),
-          residual.stride(0) if residual is not None else 0, res_f32, *rargs, bn_hint, _stream())
+          residual.stride(0) if residual is not None else 0, res_f32, *rargs, int(act_after_res), bn_hint, _stream())
     return out
 
 
@@ -533,3 +533,26 @@ def scale_channels(x, gate):
     y = torch.empty_like(x)
     _call("es3_scale_channels", "scale_channels", 2 * _nb(x), B * H * W * C, x.data_ptr(), gate.data_ptr(), y.data_ptr(), B, H * W, C, _stream())
     return y
+
+
+def layernorm_bf16(x, gamma, beta, eps=1e-5):
+    """x [M,C] bf16 -> bf16 (C % 8 == 0)."""
+    _chk(x, torch.bfloat16, "x")
+    _ensure_init(x)
+    assert x.dim() == 2 and x.is_contiguous()
+    M, C = x.shape
+    y = torch.empty_like(x)
+    _call("es3_layernorm_bf16", "layernorm_bf16", 2 * _nb(x), 8 * M * C, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+          float(eps), y.data_ptr(), M, C, _stream())
+    return y
+
+
+def win_attn_bias(qkv, qkv_pad, bias, B, H, W, C, heads, ws, scale):
+    """qkv [B*H*W, 3C] bf16 (per-head q|k|v blocks of 32), qkv_pad [3C] bf16, bias [heads, ws^2, ws^2] fp32."""
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(qkv_pad, torch.bfloat16, "qkv_pad"); _chk(bias, torch.float32, "bias")
+    _ensure_init(qkv)
+    assert qkv.is_contiguous() and bias.is_contiguous() and qkv.shape == (B * H * W, 3 * C)
+    out = torch.empty((B * H * W, C), device=qkv.device, dtype=torch.bfloat16)
+    _call("es3_win_attn_bias_bf16", f"win_attn_bias[ws={ws}]", _nb(qkv, out), 4 * B * H * W * ws * ws * C, qkv.data_ptr(),
+          qkv_pad.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, C, heads, ws, float(scale), _stream())
+    return out

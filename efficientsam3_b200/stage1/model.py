@@ -124,6 +124,27 @@ class RepViTAdapter(nn.Module):
         return self.model.forward_nhwc(x)
 
 
+class TinyViTAdapter(nn.Module):
+    """stage1/model.py:299-324 (head / norm_head replaced by Identity)."""
+
+    def __init__(self, model, img_size):
+        super().__init__()
+        self.model = model
+        self.out_channels = self.model.norm_head.normalized_shape[0]
+        self.model.head = nn.Identity()
+        self.model.norm_head = nn.Identity()
+        H, W = self.model.patches_resolution
+        for _ in range(self.model.num_layers - 1):
+            H, W = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        self.final_hw = (H, W)
+
+    def forward(self, x):
+        return ops.nhwc_to_nchw_f32(self.model.forward_nhwc(x))
+
+    def forward_nhwc(self, x):
+        return self.model.forward_nhwc(x)
+
+
 class EfficientViTAdapter(nn.Module):
     def __init__(self, model):
         super().__init__()
@@ -148,6 +169,10 @@ def _build_backbone(name, img_size):
         model = repvit_m1_1(pretrained=False, num_classes=0, distillation=False)
         out_channels = _make_divisible(model.cfgs[-1][2], 8)
         return RepViTAdapter(model, out_channels), out_channels
+    if name == "tiny_vit_11m":
+        from ..backbones.tiny_vit import tiny_vit_11m_224
+        adapter = TinyViTAdapter(tiny_vit_11m_224(pretrained=False, img_size=img_size), img_size)
+        return adapter, adapter.out_channels
     if name.startswith("repvit") or name.startswith("tiny_vit"):
         raise NotImplementedError(f"{name}: native student backbone not built yet (see DESIGN.md scope table)")
     raise ValueError(f"Unsupported backbone {name}")

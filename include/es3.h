@@ -39,11 +39,12 @@ int es3_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, vo
  * columns [0, rope_cols) (the q|k part of a fused QKV projection, heads of 64) before rounding -- rope is a
  * [positions][32] table of (cos, sin) float pairs, position = raster index of the token inside its
  * rope_win x rope_win window (rope_win > 0) or inside the rope_H x rope_W map (rope_win = 0).
- * Replaces Attention.qkv + apply_rotary_enc (vitdet.py:68-90, 480-486). */
+ * act_after_res = 1 applies the activation after the residual add (TinyViT MBConv: act3(conv3(x) + shortcut),
+ * tiny_vit.py:112-125).  Replaces Attention.qkv + apply_rotary_enc (vitdet.py:68-90, 480-486). */
 int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int out_f32,
                      int M, int N, int K, const float* scale, const float* bias, int act, const void* residual,
                      long long ldr, int res_f32, const float* rope, int rope_cols, int rope_H, int rope_W, int rope_win,
-                     int bn_hint, void* stream);
+                     int act_after_res, int bn_hint, void* stream);
 
 /* ConvTranspose2d(k=2, s=2) on NHWC as a tcgen05 GEMM (N = 4*Cout) with a depth-to-space epilogue.
  * Wt [4*Cout][Cin] bf16, Wt[(dy*2+dx)*Cout+co][ci] = w[ci][co][dy][dx]; bias4 [4*Cout]; out [B,2H,2W,Cout].
@@ -182,6 +183,14 @@ int es3_conv3x3_s2_c32_bf16(const void* x, const void* w, const float* scale, co
  * (ws: B*ceil(HW/128)*C floats; deterministic two-stage) and y = x * gate[b,c]. */
 int es3_channel_mean(const void* x, float* ws, float* mean, int B, int HW, int C, void* stream);
 int es3_scale_channels(const void* x, const float* gate, void* y, int B, int HW, int C, void* stream);
+
+/* Window attention with the learned relative-position bias over zero-padded window partitions, head_dim 32, window 7 or 14
+ * (tiny_vit.py:219-293, 344-375).  qkv [B*H*W, 3C] with per-head [q|k|v] blocks of 32; qkv_pad [3C] = qkv(LN(0)), the value
+ * the reference's padded tokens take; bias [heads][ws^2][ws^2] fp32; out [B*H*W, C] bf16. */
+int es3_win_attn_bias_bf16(const void* qkv, const void* qkv_pad, const float* bias, void* out, int B, int H, int W, int C,
+                           int num_heads, int ws, float scale, void* stream);
+/* LayerNorm over bf16 rows, C % 8 == 0 (TinyViT token stream: Attention.norm / Mlp.norm, tiny_vit.py:206,240). */
+int es3_layernorm_bf16(const void* x, const float* gamma, const float* beta, float eps, void* y, long long M, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------ stage-1 loss */
 /* Masked MSE + masked cosine KD loss, forward (stage1/train_image_encoder_stage1.py:205-210, 271-307).

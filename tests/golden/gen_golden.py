@@ -43,6 +43,7 @@ def gen_student(backbone, tag, img, embed, seed_w, seed_x, batch=1):
     m = stage1_model.build_image_student_model(cfg).eval()
     sd = fill_state_dict(m.state_dict(), seed_w)
     m.load_state_dict(sd)
+    m.train(); m.eval()   # TinyViT's Attention caches `ab` (bias table) inside train(False): refresh after loading weights
     x = torch.randn(batch, 3, img, img, generator=torch.Generator().manual_seed(seed_x))
     out = m(x)
     extra = {}
@@ -151,6 +152,8 @@ def gen_neck(tag, dim, d_model, hw, B, seed_w, seed_x):
 
 
 def main(which):
+    if which in ("tvm", "all"):
+        gen_student("tiny_vit_11m", "tvm_160", img=160, embed=12, seed_w=61, seed_x=62, batch=1)
     if which in ("rvm", "all"):
         gen_student("repvit_m1_1", "rvm_160", img=160, embed=12, seed_w=51, seed_x=52, batch=1)
     if which in ("neck", "all"):

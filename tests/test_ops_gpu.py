@@ -255,3 +255,39 @@ def test_squeeze_excite_pieces(cuda):
     gate = torch.rand(3, 128, device=cuda)
     y = ops.scale_channels(x, gate)
     _close(y, x.float() * gate.view(3, 1, 1, 128), 1e-2, "scale_channels")
+
+
+@pytest.mark.parametrize("H,W,ws,heads", [(16, 16, 7, 4), (14, 14, 14, 2), (63, 63, 14, 8), (8, 10, 7, 14)])
+def test_win_attn_bias(cuda, H, W, ws, heads):
+    """Window attention with relative bias over zero-padded partitions vs the TinyViT formulation (tiny_vit.py:270-293,
+    352-375) on a given qkv tensor (padded tokens take the supplied constant row)."""
+    from efficientsam3_b200 import ops
+    B, kd = 2, 32
+    C, N = heads * kd, ws * ws
+    g = torch.Generator().manual_seed(H * 3 + ws)
+    qkv = _bf(torch.randn(B * H * W, 3 * C, generator=g)).to(cuda)
+    pad_row = _bf(torch.randn(3 * C, generator=g)).to(cuda)
+    bias = torch.randn(heads, N, N, generator=g).to(cuda)
+    out = ops.win_attn_bias(qkv, pad_row, bias, B, H, W, C, heads, ws, kd ** -0.5)
+    x = qkv.float().view(B, H, W, 3 * C)
+    pb, pr = (ws - H % ws) % ws, (ws - W % ws) % ws
+    xp = pad_row.float().view(1, 1, 1, -1).expand(B, H + pb, W + pr, -1).clone()
+    xp[:, :H, :W] = x
+    nH, nW = (H + pb) // ws, (W + pr) // ws
+    t = xp.view(B, nH, ws, nW, ws, 3 * C).transpose(2, 3).reshape(B * nH * nW, N, heads, 3 * kd)
+    q, k, v = t.split([kd, kd, kd], dim=3)
+    q, k, v = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3)
+    a = (q @ k.transpose(-2, -1)) * kd ** -0.5 + bias
+    o = (a.softmax(-1) @ v).transpose(1, 2).reshape(B * nH * nW, N, C)
+    ref = o.view(B, nH, nW, ws, ws, C).transpose(2, 3).reshape(B, H + pb, W + pr, C)[:, :H, :W].reshape(B * H * W, C)
+    _close(out, ref, 1e-2, "win_attn_bias")
+
+
+@pytest.mark.parametrize("M,C", [(300, 448), (1000, 128), (77, 256)])
+def test_layernorm_bf16(cuda, M, C):
+    from efficientsam3_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    x = _bf(torch.randn(M, C, generator=g) * 2 + 0.5).to(cuda)
+    gam, bet = (torch.rand(C, generator=g) + 0.5).to(cuda), torch.randn(C, generator=g).to(cuda)
+    y = ops.layernorm_bf16(x, gam, bet, 1e-5)
+    _close(y, F.layer_norm(x.float(), (C,), gam, bet, 1e-5), 1e-2, "layernorm_bf16")

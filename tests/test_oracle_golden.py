@@ -105,3 +105,13 @@ def test_repvit_oracle_matches_reference():
     with torch.no_grad():
         out = O.image_student_encoder(sd, x, int(g["embed"]))
     _assert_close(out.numpy(), g["out"], rtol=2e-5)
+
+
+def test_tinyvit_oracle_matches_reference():
+    from oracle import tinyvit as O
+    g = _load("tvm_160")
+    sd = _sd_from_keys(g["keys"], int(g["seed_w"]))
+    x = torch.randn(int(g["batch"]), 3, int(g["img"]), int(g["img"]), generator=torch.Generator().manual_seed(int(g["seed_x"])))
+    with torch.no_grad():
+        out = O.image_student_encoder(sd, x, int(g["embed"]))
+    _assert_close(out.numpy(), g["out"], rtol=2e-5)

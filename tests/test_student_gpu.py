@@ -108,3 +108,32 @@ def test_rvm_matches_oracle(cuda, img, embed, batch):
         ref = O.image_student_encoder(sd, x, embed)
     out = _build_rv(img, embed, sd, cuda)(x.to(cuda)).cpu()
     _check(out, ref, f"rvm {img} vs oracle")
+
+
+def _build_tv(img, embed, sd, dev):
+    from efficientsam3_b200.stage1.model import build_image_student_model
+    cfg = NS(MODEL=NS(BACKBONE="tiny_vit_11m"), DATA=NS(IMG_SIZE=img), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=embed))
+    m = build_image_student_model(cfg)
+    m.load_state_dict(sd)
+    return m.to(dev).eval()
+
+
+def test_tvm_matches_reference_fixture(cuda):
+    g = load_golden("tvm_160")
+    sd = sd_from_keys(g["keys"], int(g["seed_w"]))
+    img, embed = int(g["img"]), int(g["embed"])
+    x = torch.randn(int(g["batch"]), 3, img, img, generator=torch.Generator().manual_seed(int(g["seed_x"])))
+    out = _build_tv(img, embed, sd, cuda)(x.to(cuda)).cpu()
+    _check(out, g["out"], "tvm_160 vs reference fixture")
+
+
+@pytest.mark.parametrize("img,embed,batch", [(256, 18, 2), (1024, 64, 1), (1008, 72, 1)])
+def test_tvm_matches_oracle(cuda, img, embed, batch):
+    from oracle import tinyvit as O
+    g = load_golden("tvm_160")
+    sd = sd_from_keys(g["keys"], 88)
+    x = torch.randn(batch, 3, img, img, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        ref = O.image_student_encoder(sd, x, embed)
+    out = _build_tv(img, embed, sd, cuda)(x.to(cuda)).cpu()
+    _check(out, ref, f"tvm {img} vs oracle")
