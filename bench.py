@@ -269,7 +269,11 @@ def other_encoders(dev, S, E):
     x = torch.randn(32, 3, S, S, device=dev)
     ms = _time_steps(lambda: rv(x), 2, 5)
     out["rvm_student_forward"] = {"images_per_s": round(32 / ms * 1e3, 1), "ms_per_step": round(ms, 3), "batch": 32, "img": S}
-    del rv, x
+    del rv
+    tv = build_student(S, E, dev, "tiny_vit_11m")
+    ms = _time_steps(lambda: tv(x), 2, 5)
+    out["tvm_student_forward"] = {"images_per_s": round(32 / ms * 1e3, 1), "ms_per_step": round(ms, 3), "batch": 32, "img": S}
+    del tv, x
     t = SAM3ImageTeacherEncoder(embed_size=72).to(dev)
     x = torch.randn(8, 3, 1008, 1008, device=dev)
     ms = _time_steps(lambda: t(x), 1, 3)
