@@ -27,6 +27,7 @@ SIGNATURES: dict[str, list] = {
     "es3_attention_tc_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
     "es3_attention_mma_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
     "es3_tokens_f32_to_nchw": [_vp, _vp, _i, _i, _i, _vp],
+    "es3_cast_f32_to_f16": [_vp, _vp, _ll, _vp],
     "es3_convt2x2_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp],
     "es3_dense_pe": [_vp, _i, _i, _i, _vp, _vp],
     "es3_point_embed": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp],
@@ -38,7 +39,7 @@ SIGNATURES: dict[str, list] = {
     "es3_hyper_masks": [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_bilinear_nchw_f32": [_vp, _vp, _vp, _f, _ll, _i, _i, _i, _i, _vp],
     "es3_kd_loss_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
-    "es3_conv3x3_s2_c32_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "es3_conv3x3_s2_narrow_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_channel_mean": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "es3_scale_channels": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "es3_conv3x3_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp],
@@ -48,6 +49,7 @@ SIGNATURES: dict[str, list] = {
     "es3_dwconv_tiled_bf16": [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "es3_litemla_aggreg_tiled": [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp],
     "es3_mbconv_fused_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "es3_stem_fused_c16": [_vp] * 10 + [_i, _i, _i, _vp],
     "es3_dsconv_res_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "es3_bilinear_nhwc_to_nchw": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_maxpool2x2_bf16": [_vp, _vp, _i, _i, _i, _i, _vp],
@@ -57,6 +59,7 @@ SIGNATURES: dict[str, list] = {
     "es3_litemla_aggreg_tc": [_vp, _ll, _vp, _i, _i, _i, _i, _vp],
     "es3_litemla_attn_tc": [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _f, _vp],
     "es3_litemla_attn": [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _f, _vp],
+    "es3_litemla_attn_generic": [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _f, _vp],
 }
 
 _lib = None

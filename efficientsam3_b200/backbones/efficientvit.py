@@ -189,30 +189,43 @@ class _MBConvPlan:
 
 
 class _LiteMLAPlan:
+    """x + LiteMLA(x).  dim 16 (b0 / b1): the mma.sync kernels of litemla_tc.cu.  Other dims (b2: 32): depthwise 5x5 +
+    the grouped 1x1 as a block-diagonal tcgen05 GEMM + the generic CUDA-core attention kernels."""
+
     def __init__(self, m: LiteMLA, device):
-        if m.dim != 16:
-            raise NotImplementedError("native LiteMLA kernel is specialised for dim=16 (efficientvit b0/b1)")
         assert m.qkv.norm is None and m.qkv.conv.bias is None and m.aggreg[0][0].bias is None
+        self.dim = m.dim
         self.qkv_w = pw_weight(m.qkv.conv)
         self.c3 = self.qkv_w.shape[0]
         dw, pw = m.aggreg[0][0], m.aggreg[0][1]
         self.agg_dw = dw_weight(dw, None)                                         # [25, C3] fp32
-        self.agg_pw = pw.weight.detach().float().reshape(self.c3, 16).contiguous()  # [C3, 16] fp32
-        self.wcomb = ops.litemla_wcomb(self.agg_dw, self.agg_pw)                    # [C3/16, 25, 16, 16] bf16
+        if self.dim == 16:
+            self.agg_pw = pw.weight.detach().float().reshape(self.c3, 16).contiguous()  # [C3, 16] fp32
+            self.wcomb = ops.litemla_wcomb(self.agg_dw, self.agg_pw)                    # [C3/16, 25, 16, 16] bf16
+        else:
+            d = self.dim
+            wg = pw.weight.detach().float().reshape(self.c3 // d, d, d)               # [group][out][in]
+            self.agg_pw_bd = torch.block_diag(*wg).to(torch.bfloat16).contiguous()    # [C3, C3], zero off the groups
         self.proj = _PW(m.proj, device)
         self.heads2 = 2 * m.heads
         self.eps = m.eps
 
     def __call__(self, x):  # returns x + LiteMLA(x)
         B, H, W, C = x.shape
-        if H * W <= 16:
+        if H * W <= self.dim:
             raise NotImplementedError("LiteMLA quadratic branch (H*W <= dim, ops.py:623-654) is never reached at "
                                       "the hot path's resolutions and is not built natively")
-        ms = torch.empty((B, H, W, 2 * self.c3), device=x.device, dtype=torch.bfloat16)
-        ms2d = ms.view(-1, 2 * self.c3)
-        ops.gemm(x.view(-1, C), self.qkv_w, out=ms2d[:, : self.c3])
-        ops.litemla_aggreg_tc(ms, self.wcomb, self.c3)
-        att = ops.litemla_attn(ms, self.heads2, self.eps)
+        c3 = self.c3
+        ms = torch.empty((B, H, W, 2 * c3), device=x.device, dtype=torch.bfloat16)
+        ms2d = ms.view(-1, 2 * c3)
+        ops.gemm(x.view(-1, C), self.qkv_w, out=ms2d[:, :c3])
+        if self.dim == 16:
+            ops.litemla_aggreg_tc(ms, self.wcomb, c3)
+            att = ops.litemla_attn(ms, self.heads2, self.eps)
+        else:
+            t = ops.dwconv(ms[..., :c3], self.agg_dw, None, 5, 1, None)
+            ops.gemm(t.view(-1, c3), self.agg_pw_bd, out=ms2d[:, c3:])
+            att = ops.litemla_attn_generic(ms, self.heads2, self.dim, self.eps)
         out = self.proj(att.view(-1, att.shape[-1]), residual=x.view(-1, C))
         return out.view(B, H, W, C)
 
@@ -262,18 +275,49 @@ class EfficientViTBackbone(nn.Module, NativePlanMixin):
                       norm=(None, None, norm) if fewer_norm else norm, act_func=(act_func, act_func, None))
 
     # ---- plan -----------------------------------------------------------------------------------
+    @staticmethod
+    def _fused_stem_plan(stem_ops, dev):
+        """One-launch stem (es3_stem_fused_c16) when the stem is conv(3->16, hswish) + one residual DSConv(16, hswish)."""
+        if len(stem_ops) != 2:
+            return None
+        stem0, blk = stem_ops
+        ds = blk.main
+        if not (isinstance(ds, DSConv) and blk.shortcut is not None and stem0.conv.out_channels == 16
+                and stem0.conv.in_channels == 3 and stem0.act == "hswish" and ds.depth_conv.act == "hswish"
+                and ds.point_conv.act is None):
+            return None
+        ones = torch.ones(16, device=dev, dtype=torch.float32)
+        zeros = torch.zeros(16, device=dev, dtype=torch.float32)
+        s0, b0 = _fold(stem0, dev)
+        w0 = torch.zeros(16, 32, device=dev, dtype=torch.float32)
+        w0[:, :27] = stem0.conv.weight.detach().float().reshape(16, 27)
+        w0 = w0.to(torch.bfloat16).contiguous()
+        s1, b1 = _fold(ds.depth_conv, dev)
+        wdw = dw_weight(ds.depth_conv.conv, s1)
+        s2, b2 = _fold(ds.point_conv, dev)
+        wpw = ds.point_conv.conv.weight.detach().reshape(16, 16).to(torch.bfloat16).contiguous()
+        args = (w0, ones if s0 is None else s0, zeros if b0 is None else b0, wdw, zeros if b1 is None else b1, wpw,
+                ones if s2 is None else s2, zeros if b2 is None else b2)
+        return lambda x: ops.stem_fused_c16(x, *args)
+
     def _build_plan(self):
         dev = next(self.parameters()).device
         steps = []  # list of (stage_name_after | None, callable)
         stem0 = self.input_stem.op_list[0]
+        stem_ops = list(self.input_stem.op_list)
+        fused = self._fused_stem_plan(stem_ops, dev)
+        if fused is not None:
+            steps.append(fused)
+            stem_ops = []
         s, b = _fold(stem0, dev)
         w = stem0.conv.weight.detach().float()
         if s is not None:
             w = w * s.view(-1, 1, 1, 1)
         w27 = w.reshape(w.shape[0], 27).t().contiguous()
         act0 = stem0.act
-        steps.append(lambda x: ops.stem_conv3x3_s2(x, w27, b, act0))
-        for blk in list(self.input_stem.op_list)[1:]:
+        if stem_ops:
+            steps.append(lambda x: ops.stem_conv3x3_s2(x, w27, b, act0))
+        for blk in stem_ops[1:]:
             ds = blk.main
             assert isinstance(ds, DSConv) and blk.shortcut is not None
             s1, b1 = _fold(ds.depth_conv, dev)

@@ -2,7 +2,7 @@
 sam3/sam3/backbones/repvit.py (Conv2d_BN :27-49, Residual :51-81, RepVGGDW :84-122, RepViTBlock :125-161,
 RepViT :219-246, configs :253-472); SqueezeExcite parameters follow timm.layers.SqueezeExcite (fc1 / fc2 1x1 convs
 with bias).  Eval-mode execution:
-  patch embed   es3_stem_conv3x3_s2 (3->C/2, BN, GELU) + es3_conv3x3_s2_c32_bf16 (mma.sync implicit GEMM)
+  patch embed   es3_stem_conv3x3_s2 (3->C/2, BN, GELU) + es3_conv3x3_s2_narrow_bf16 (mma.sync implicit GEMM)
   RepVGGDW      re-parameterised on the host exactly as the reference's own fuse() (repvit.py:97-122) into one
                 depthwise 3x3 + bias -> es3_dwconv_tiled_bf16
   SqueezeExcite es3_channel_mean -> es3_gemm_simt x2 (ReLU, sigmoid) -> es3_scale_channels
@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..nn_utils import NativePlanMixin, bn_scale_bias, dw_weight, pw_weight
+from ..nn_utils import NativePlanMixin, bn_scale_bias, dw_weight, pack_patch_embed, pw_weight
 
 
 def _make_divisible(v, divisor, min_value=None):
@@ -175,13 +175,10 @@ class RepViT(nn.Module, NativePlanMixin):
         dev = next(self.parameters()).device
         pe = self.features[0]
         c0, c1 = pe[0], pe[2]
-        if c0.c.out_channels != 32:
-            raise NotImplementedError("native RepViT patch embed is built for a 32-channel first conv (m0_9 / m1_0 / m1_1)")
         s0, b0 = _fold_cb(c0, dev)
-        w0 = (c0.c.weight.detach().float() * s0.view(-1, 1, 1, 1)).reshape(32, 27).t().contiguous()
         s1, b1 = _fold_cb(c1, dev)
-        w1 = c1.c.weight.detach().permute(2, 3, 0, 1).reshape(9, c1.c.out_channels, 32).to(torch.bfloat16).contiguous()
-        steps = [lambda x: ops.conv3x3_s2_c32(ops.stem_conv3x3_s2(x, w0, b0, "gelu"), w1, s1, b1, None)]
+        w0, b0, w1 = pack_patch_embed(c0.c.weight, s0, b0, c1.c.weight)
+        steps = [lambda x: ops.conv3x3_s2_narrow(ops.stem_conv3x3_s2(x, w0, b0, "gelu"), w1, s1, b1, None)]
         steps += [_BlockPlan(b, dev) for b in list(self.features)[1:]]
         return steps
 
@@ -199,10 +196,27 @@ def _rv(cfgs, num_classes=1000, distillation=False):
     return RepViT(cfgs, num_classes=num_classes, distillation=distillation)
 
 
+def _stage_cfgs(widths, depths):
+    """RepViT block table rows [k, t, c, SE, HS, s] (repvit.py:280-520): four stages; a stage after the first opens with a
+    stride-2 block; SqueezeExcite alternates (first stage starts with SE, later ones with the plain downsample block) and
+    the last block of a stage never has it; hard-swish flag (unused by the blocks) is set in the last two stages."""
+    rows = []
+    for si, (c, n) in enumerate(zip(widths, depths)):
+        for i in range(n):
+            se = (i % 2 == 0) if si == 0 else (i % 2 == 1)
+            if i == n - 1:
+                se = False
+            rows.append([3, 2, c, int(se), int(si >= 2), 2 if (si > 0 and i == 0) else 1])
+    return rows
+
+
+def repvit_m0_9(pretrained=False, num_classes=1000, distillation=False):
+    return _rv(_stage_cfgs((48, 96, 192, 384), (3, 4, 16, 3)), num_classes, distillation)
+
+
 def repvit_m1_1(pretrained=False, num_classes=1000, distillation=False):
-    cfgs = [[3, 2, 64, 1, 0, 1], [3, 2, 64, 0, 0, 1], [3, 2, 64, 0, 0, 1], [3, 2, 128, 0, 0, 2], [3, 2, 128, 1, 0, 1],
-            [3, 2, 128, 0, 0, 1], [3, 2, 128, 0, 0, 1], [3, 2, 256, 0, 1, 2], [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1],
-            [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1], [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1], [3, 2, 256, 1, 1, 1],
-            [3, 2, 256, 0, 1, 1], [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1], [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1],
-            [3, 2, 256, 0, 1, 1], [3, 2, 512, 0, 1, 2], [3, 2, 512, 1, 1, 1], [3, 2, 512, 0, 1, 1]]
-    return _rv(cfgs, num_classes, distillation)
+    return _rv(_stage_cfgs((64, 128, 256, 512), (3, 4, 14, 3)), num_classes, distillation)
+
+
+def repvit_m2_3(pretrained=False, num_classes=1000, distillation=False):
+    return _rv(_stage_cfgs((80, 160, 320, 640), (7, 8, 36, 3)), num_classes, distillation)

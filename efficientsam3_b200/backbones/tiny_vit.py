@@ -3,7 +3,7 @@ sam3/sam3/backbones/tiny_vit.py (Conv2d_BN :29-53, PatchEmbed :67-84, MBConv :87
 ConvLayer :157-193, Mlp :196-216, Attention :219-293, TinyViTBlock :296-386, BasicLayer :393-454, TinyViT :460-607).
 
 Eval-mode execution (token stream NHWC bf16 = raster tokens x channels):
-  patch embed     es3_stem_conv3x3_s2 + es3_conv3x3_s2_c32_bf16
+  patch embed     es3_stem_conv3x3_s2 + es3_conv3x3_s2_narrow_bf16
   MBConv          es3_gemm_bf16_ex (conv1+BN+GELU) -> es3_dwconv_tiled_bf16 (+GELU) -> es3_gemm_bf16_ex (conv3+BN, +x, GELU
                   after the residual)
   PatchMerging    gemm+GELU -> depthwise s2 + GELU -> gemm
@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..nn_utils import NativePlanMixin, bn_scale_bias, dw_weight, pw_weight
+from ..nn_utils import NativePlanMixin, bn_scale_bias, dw_weight, pack_patch_embed, pw_weight
 
 
 class Conv2d_BN(nn.Sequential):
@@ -246,13 +246,10 @@ class TinyViT(nn.Module, NativePlanMixin):
     def _build_plan(self):
         dev = next(self.parameters()).device
         c0, c1 = self.patch_embed.seq[0], self.patch_embed.seq[2]
-        if c0.c.out_channels != 32:
-            raise NotImplementedError("native TinyViT patch embed is built for embed_dims[0] = 64 (tiny_vit_5m / 11m)")
         s0, b0 = _cb(c0, dev)
-        w0 = (c0.c.weight.detach().float() * s0.view(-1, 1, 1, 1)).reshape(32, 27).t().contiguous()
         s1, b1 = _cb(c1, dev)
-        w1 = c1.c.weight.detach().permute(2, 3, 0, 1).reshape(9, c1.c.out_channels, 32).to(torch.bfloat16).contiguous()
-        steps = [lambda x: ops.conv3x3_s2_c32(ops.stem_conv3x3_s2(x, w0, b0, "gelu"), w1, s1, b1, None)]
+        w0, b0, w1 = pack_patch_embed(c0.c.weight, s0, b0, c1.c.weight)
+        steps = [lambda x: ops.conv3x3_s2_narrow(ops.stem_conv3x3_s2(x, w0, b0, "gelu"), w1, s1, b1, None)]
         for li, layer in enumerate(self.layers):
             for blk in layer.blocks:
                 steps.append(_MBConvPlan(blk, dev) if li == 0 else _BlockPlan(blk, dev))
@@ -270,8 +267,19 @@ class TinyViT(nn.Module, NativePlanMixin):
         return x
 
 
-def tiny_vit_11m_224(pretrained=False, **kwargs):
-    kw = dict(embed_dims=[64, 128, 256, 448], depths=[2, 2, 6, 2], num_heads=[2, 4, 8, 14], window_sizes=[7, 7, 14, 7],
-              drop_path_rate=0.1)
+def _tiny_vit(defaults, kwargs):
+    kw = dict(depths=[2, 2, 6, 2], window_sizes=[7, 7, 14, 7], **defaults)
     kw.update(kwargs)
     return TinyViT(**kw)
+
+
+def tiny_vit_5m_224(pretrained=False, **kwargs):
+    return _tiny_vit(dict(embed_dims=[64, 128, 160, 320], num_heads=[2, 4, 5, 10], drop_path_rate=0.0), kwargs)
+
+
+def tiny_vit_11m_224(pretrained=False, **kwargs):
+    return _tiny_vit(dict(embed_dims=[64, 128, 256, 448], num_heads=[2, 4, 8, 14], drop_path_rate=0.1), kwargs)
+
+
+def tiny_vit_21m_224(pretrained=False, **kwargs):
+    return _tiny_vit(dict(embed_dims=[96, 192, 384, 576], num_heads=[3, 6, 12, 18], drop_path_rate=0.2), kwargs)

@@ -302,7 +302,8 @@ extern "C" int es3_stem_conv3x3_s2(const float* x, const float* w, const float* 
       case 16: stem_conv3x3_s2_kernel<16, A><<<blocks, threads, 0, st>>>(x, w, bias, (bf16*)out, B, H, W, Ho, Wo); break;
       case 24: stem_conv3x3_s2_kernel<24, A><<<blocks, threads, 0, st>>>(x, w, bias, (bf16*)out, B, H, W, Ho, Wo); break;
       case 32: stem_conv3x3_s2_kernel<32, A><<<blocks, threads, 0, st>>>(x, w, bias, (bf16*)out, B, H, W, Ho, Wo); break;
-      default: ES3_REQUIRE(false, "es3_stem_conv3x3_s2: unsupported Cout=%d (8/16/24/32)", Cout);
+      case 48: stem_conv3x3_s2_kernel<48, A><<<blocks, threads, 0, st>>>(x, w, bias, (bf16*)out, B, H, W, Ho, Wo); break;
+      default: ES3_REQUIRE(false, "es3_stem_conv3x3_s2: unsupported Cout=%d (8/16/24/32/48)", Cout);
     }
   })
   ES3_LAUNCH_CHECK("stem_conv3x3_s2_kernel");

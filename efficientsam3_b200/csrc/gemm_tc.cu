@@ -206,7 +206,26 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
         ptx::tmem_ld_wait();
         const int nb = n0 + c * 32;
-        if (valid && nb < args.N) {
+        if (valid && nb < args.N && nb + 32 > args.N) {
+          // ragged last chunk (N % 32 != 0, N % 8 == 0): per-column path, plain GEMM epilogue only
+          const int ncols = args.N - nb;
+          const long long out_off = row_off * args.ldo + nb, res_off = row_off * args.ldr + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < ncols) {
+              float x = __uint_as_float(v[j]);
+              if (args.scale != nullptr) x *= __ldg(args.scale + nb + j);
+              if (args.bias != nullptr) x += __ldg(args.bias + nb + j);
+              if (!args.act_after_res) x = es3_act_t<ACT>(x);
+              if (args.residual != nullptr)
+                x += args.res_f32 ? __ldg(reinterpret_cast<const float*>(args.residual) + res_off + j)
+                                  : __bfloat162float(args.residual[res_off + j]);
+              if (args.act_after_res) x = es3_act_t<ACT>(x);
+              if (args.out_f32) reinterpret_cast<float*>(args.out)[out_off + j] = x;
+              else reinterpret_cast<bf16*>(args.out)[out_off + j] = __float2bfloat16(x);
+            }
+          }
+        } else if (valid && nb < args.N) {
           float f[32];
           if (args.scale != nullptr) {
             const float4* sc4 = reinterpret_cast<const float4*>(args.scale + nb);
@@ -429,7 +448,8 @@ extern "C" int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, lon
   ES3_REQUIRE(rope == nullptr || (rope_cols % 64 == 0 && rope_cols <= N && rope_H > 0 && rope_W > 0 &&
                                   M % (rope_H * rope_W) == 0 && ((uintptr_t)rope & 15) == 0),
               "es3_gemm_bf16_ex: bad rope arguments");
-  ES3_REQUIRE(N % 32 == 0, "es3_gemm_bf16: N=%d must be a multiple of 32", N);
+  ES3_REQUIRE(N % 8 == 0, "es3_gemm_bf16: N=%d must be a multiple of 8", N);
+  ES3_REQUIRE(N % 32 == 0 || rope == nullptr, "es3_gemm_bf16_ex: the rope epilogue needs N %% 32 == 0 (N=%d)", N);
   ES3_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "es3_gemm_bf16: K/lda/ldw must be multiples of 8 (16-byte TMA strides)");
   ES3_REQUIRE(ldo % 8 == 0 && (residual == nullptr || ldr % 8 == 0), "es3_gemm_bf16: ldo/ldr must be multiples of 8");
   ES3_REQUIRE(rope == nullptr || act == ACT_NONE, "es3_gemm_bf16_ex: rope epilogue expects act = none");

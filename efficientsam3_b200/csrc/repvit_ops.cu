@@ -25,16 +25,17 @@ __device__ __forceinline__ void cpa16(uint32_t saddr, const void* g, bool valid)
 __device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 }  // namespace
 
-// ---------------------------------------------------------------------------------- conv3x3 s2, Cin = 32
-constexpr int S2_CIN = 32, S2_TH = 8, S2_TW = 16, S2_IH = 2 * S2_TH + 1, S2_IW = 2 * S2_TW + 1, S2_RS = S2_CIN * 2 + 16;
+// ---------------------------------------------------------------------------------- conv3x3 s2, Cin = 32 | 48
+constexpr int S2_TH = 8, S2_TW = 16, S2_IH = 2 * S2_TH + 1, S2_IW = 2 * S2_TW + 1;
 
-// x [B,H,W,32] bf16; w [9][COUT][32] bf16 (tap-major, then output channel, K = input channel);
+// x [B,H,W,CIN] bf16; w [9][COUT][CIN] bf16 (tap-major, then output channel, K = input channel);
 // scale/bias fp32 [COUT] (folded BN); out [B,Ho,Wo,COUT] bf16.  Block 256 = 8 warps, warp = one output row of 16 px.
-template <int COUT, int ACT>
+template <int CIN, int COUT, int ACT>
 __global__ void __launch_bounds__(256) conv3x3_s2_c32_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                              const float* __restrict__ scale, const float* __restrict__ bias,
                                                              bf16* __restrict__ out, int H, int W, int Ho, int Wo, int tiles_x) {
   extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int S2_CIN = CIN, S2_RS = CIN * 2 + 16, NV = CIN / 8;
   constexpr int TILE_BYTES = S2_IH * S2_IW * S2_RS;
   const uint32_t u_tile = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
   const uint32_t u_w = u_tile + TILE_BYTES;
@@ -43,14 +44,14 @@ __global__ void __launch_bounds__(256) conv3x3_s2_c32_kernel(const bf16* __restr
   const int oy0 = (tile / tiles_x) * S2_TH, ox0 = (tile % tiles_x) * S2_TW;
   const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
   const bf16* xb = x + (long long)b * H * W * S2_CIN;
-  for (int i = tid; i < S2_IH * S2_IW * 4; i += 256) {
-    const int v = i & 3, p = i >> 2;
+  for (int i = tid; i < S2_IH * S2_IW * NV; i += 256) {
+    const int v = i % NV, p = i / NV;
     const int iy = iy0 + p / S2_IW, ix = ix0 + p % S2_IW;
     const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
     cpa16(u_tile + p * S2_RS + v * 16, ok ? xb + ((long long)iy * W + ix) * S2_CIN + v * 8 : xb, ok);
   }
-  for (int i = tid; i < 9 * COUT * 4; i += 256) {
-    const int v = i & 3, r = i >> 2;  // r = tap*COUT + n
+  for (int i = tid; i < 9 * COUT * NV; i += 256) {
+    const int v = i % NV, r = i / NV;  // r = tap*COUT + n
     cpa16(u_w + r * S2_RS + v * 16, w + (long long)r * S2_CIN + v * 8, true);
   }
   cpa_wait_all();
@@ -140,26 +141,31 @@ __global__ void scale_channels_kernel(const bf16* __restrict__ x, const float* _
 
 using namespace es3;
 
-extern "C" int es3_conv3x3_s2_c32_bf16(const void* x, const void* w, const float* scale, const float* bias, void* out, int B,
-                                       int H, int W, int Cout, int act, void* stream) {
-  ES3_REQUIRE(Cout == 64 || Cout == 48 || Cout == 32 || Cout == 96, "es3_conv3x3_s2_c32_bf16: Cout=%d not instantiated (32/48/64/96)", Cout);
-  ES3_REQUIRE(act == ACT_NONE || act == ACT_GELU, "es3_conv3x3_s2_c32_bf16: act %d not instantiated", act);
+extern "C" int es3_conv3x3_s2_narrow_bf16(const void* x, const void* w, const float* scale, const float* bias, void* out,
+                                          int B, int H, int W, int Cin, int Cout, int act, void* stream) {
+  ES3_REQUIRE((Cin == 32 && (Cout == 32 || Cout == 48 || Cout == 64)) || (Cin == 48 && (Cout == 80 || Cout == 96)),
+              "es3_conv3x3_s2_narrow_bf16: Cin=%d Cout=%d not instantiated (32: 32/48/64, 48: 80/96)", Cin, Cout);
+  ES3_REQUIRE(act == ACT_NONE || act == ACT_GELU, "es3_conv3x3_s2_narrow_bf16: act %d not instantiated", act);
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int tiles_x = ceil_div(Wo, S2_TW), tiles_y = ceil_div(Ho, S2_TH);
-  const size_t smem = (size_t)S2_IH * S2_IW * S2_RS + (size_t)9 * Cout * S2_RS;
+  const size_t rs = (size_t)Cin * 2 + 16;
+  const size_t smem = (size_t)S2_IH * S2_IW * rs + (size_t)9 * Cout * rs;
   dim3 grid(tiles_x * tiles_y, B);
   cudaStream_t st = (cudaStream_t)stream;
-#define ES3_S2(CO, A)                                                                                                      \
+#define ES3_S2(CI, CO, A)                                                                                                  \
   {                                                                                                                        \
-    auto k = conv3x3_s2_c32_kernel<CO, A>;                                                                                 \
+    auto k = conv3x3_s2_c32_kernel<CI, CO, A>;                                                                             \
     ES3_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
     k<<<grid, 256, smem, st>>>((const bf16*)x, (const bf16*)w, scale, bias, (bf16*)out, H, W, Ho, Wo, tiles_x);           \
   }
-  if (act == ACT_NONE) {
-    if (Cout == 64) ES3_S2(64, ACT_NONE) else if (Cout == 48) ES3_S2(48, ACT_NONE) else if (Cout == 32) ES3_S2(32, ACT_NONE) else ES3_S2(96, ACT_NONE)
+#define ES3_S2_ACT(CI, CO)                                                                                                 \
+  if (act == ACT_NONE) ES3_S2(CI, CO, ACT_NONE) else ES3_S2(CI, CO, ACT_GELU)
+  if (Cin == 32) {
+    if (Cout == 64) { ES3_S2_ACT(32, 64) } else if (Cout == 48) { ES3_S2_ACT(32, 48) } else { ES3_S2_ACT(32, 32) }
   } else {
-    if (Cout == 64) ES3_S2(64, ACT_GELU) else if (Cout == 48) ES3_S2(48, ACT_GELU) else if (Cout == 32) ES3_S2(32, ACT_GELU) else ES3_S2(96, ACT_GELU)
+    if (Cout == 80) { ES3_S2_ACT(48, 80) } else { ES3_S2_ACT(48, 96) }
   }
+#undef ES3_S2_ACT
 #undef ES3_S2
   ES3_LAUNCH_CHECK("conv3x3_s2_c32_kernel");
   return 0;

@@ -4,6 +4,8 @@
 //     (get_abs_pos tiling branch, vitdet.py:205-214) for ln_pre
 //   * im2col for the 14x14/stride-14 patch embedding (PatchEmbed, vitdet.py:299-336) -> bf16 GEMM operand
 //   * [B, HW, C] fp32 tokens -> [B, C, HW] fp32 (the NCHW map ViT.forward returns, vitdet.py:846-857)
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace es3 {
@@ -133,5 +135,30 @@ extern "C" int es3_tokens_f32_to_nchw(const float* in, float* out, int B, int HW
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), B);
   tokens_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, HW, C);
   ES3_LAUNCH_CHECK("tokens_to_nchw_kernel");
+  return 0;
+}
+
+// fp32 -> fp16 (round to nearest even), 8 elements per thread: the teacher-embedding dump stores fp16
+// (save_embedding_image_stage1.py:92 `.to(dtype=torch.float16)`), so the cast runs before the D2H copy and halves it.
+namespace es3 {
+__global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(in + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(in + i + 4));
+    __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+    *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(h);
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = __float2half_rn(in[j]);
+  }
+}
+}  // namespace es3
+
+extern "C" int es3_cast_f32_to_f16(const float* in, void* out, long long n, void* stream) {
+  ES3_REQUIRE(n >= 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "es3_cast_f32_to_f16: pointers must be 16-byte aligned");
+  if (n == 0) return 0;
+  const int threads = 256;
+  cast_f32_f16_kernel<<<(unsigned)(((n + 7) / 8 + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(in, (__half*)out, n);
+  ES3_LAUNCH_CHECK("cast_f32_f16_kernel");
   return 0;
 }

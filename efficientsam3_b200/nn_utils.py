@@ -38,6 +38,28 @@ def dw_weight(conv: nn.Conv2d, scale: torch.Tensor | None) -> torch.Tensor:
     return w.reshape(c, k * k).t().contiguous()
 
 
+def pack_patch_embed(w0: torch.Tensor, s0, b0, w1: torch.Tensor):
+    """Two-conv patch embed (3 -> C/2 -> C, both 3x3 stride 2; repvit.py:219-223, tiny_vit.py:67-84) packed for
+    es3_stem_conv3x3_s2 + es3_conv3x3_s2_narrow_bf16.  The intermediate width C/2 (24/32/40/48) is zero-padded to the
+    kernel widths 32 / 48: padded channels carry weight 0 and bias 0, so they stay act(0) = 0 and meet zero weights again.
+    Returns (w27 fp32 [27, Cp] with BN scale folded, bias [Cp], w9 bf16 [9, Cout, Cp])."""
+    cmid, cout = w0.shape[0], w1.shape[0]
+    cp = 32 if cmid <= 32 else 48
+    if cmid > 48:
+        raise NotImplementedError(f"patch embed with a {cmid}-channel first conv is not instantiated (<= 48)")
+    w0 = w0.detach().float()
+    if s0 is not None:
+        w0 = w0 * s0.view(-1, 1, 1, 1)
+    w27 = torch.zeros(27, cp, device=w0.device, dtype=torch.float32)
+    w27[:, :cmid] = w0.reshape(cmid, 27).t()
+    bias = torch.zeros(cp, device=w0.device, dtype=torch.float32)
+    if b0 is not None:
+        bias[:cmid] = b0
+    w9 = torch.zeros(9, cout, cp, device=w0.device, dtype=torch.bfloat16)
+    w9[:, :, :cmid] = w1.detach().permute(2, 3, 0, 1).reshape(9, cout, cmid).to(torch.bfloat16)
+    return w27.contiguous(), bias, w9.contiguous()
+
+
 def conv3x3_weight(conv: nn.Conv2d) -> torch.Tensor:
     """dense 3x3 weight [N,C,3,3] -> bf16 [N, 9*C] with k = (ky*3+kx)*C + c."""
     w = conv.weight.detach()

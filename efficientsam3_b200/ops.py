@@ -18,7 +18,7 @@ def _stream() -> int:
 
 # ------------------------------------------------------------------------------------ accounting
 # kernels launched per C-ABI call (memsets excluded) -- bench.py reports the sum as `gpu_launches`.
-KERNELS_PER_CALL = {"es3_litemla_attn": 2, "es3_litemla_attn_tc": 2, "es3_kd_loss_fwd": 2, "es3_channel_mean": 2}
+KERNELS_PER_CALL = {"es3_litemla_attn": 2, "es3_litemla_attn_generic": 2, "es3_litemla_attn_tc": 2, "es3_kd_loss_fwd": 2, "es3_channel_mean": 2}
 launch_count = 0
 
 
@@ -188,6 +188,20 @@ def dsconv_res(x, wdw, bdw, wpw, bpw, act):
     return out
 
 
+def stem_fused_c16(x, w0, s0, b0, wdw, bdw, wpw, spw, bpw):
+    """EfficientViT-B1 stem conv + DSConv residual in one launch.  x: [B,3,H,W] fp32 -> [B,Ho,Wo,16] bf16."""
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    x = x.contiguous()
+    B, _, H, W = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty((B, Ho, Wo, 16), device=x.device, dtype=torch.bfloat16)
+    _call("es3_stem_fused_c16", "stem_fused_c16", _nb(x, out), 2 * B * Ho * Wo * 16 * (27 + 9 + 16),
+          x.data_ptr(), w0.data_ptr(), s0.data_ptr(), b0.data_ptr(), wdw.data_ptr(), bdw.data_ptr(), wpw.data_ptr(),
+          spw.data_ptr(), bpw.data_ptr(), out.data_ptr(), B, H, W, _stream())
+    return out
+
+
 def bilinear_nhwc_to_nchw(x, Ho, Wo):
     _chk(x, torch.bfloat16, "x")
     _ensure_init(x)
@@ -263,6 +277,19 @@ def litemla_attn(ms, heads2, eps=1e-15, tc=True):
     return att
 
 
+def litemla_attn_generic(ms, heads2, dim, eps=1e-15):
+    """ReLU linear attention for head dim 16 | 32 (CUDA-core kernels).  ms: [B,H,W,3*dim*heads2] bf16 -> [B,H,W,dim*heads2]."""
+    _chk(ms, torch.bfloat16, "ms")
+    _ensure_init(ms)
+    assert ms.is_contiguous() and ms.shape[3] == 3 * dim * heads2
+    B, H, W, ld = ms.shape
+    att = torch.empty((B, H, W, dim * heads2), device=ms.device, dtype=torch.bfloat16)
+    kv = torch.empty((B * heads2 * ((H * W + 127) // 128) * (dim + 1) * dim,), device=ms.device, dtype=torch.float32)
+    _call("es3_litemla_attn_generic", f"litemla_attn_generic[{dim}]", _nb(ms, att), 2 * B * H * W * heads2 * (dim + 1) * dim * 2,
+          ms.data_ptr(), ld, kv.data_ptr(), att.data_ptr(), att.shape[3], B, H * W, heads2, dim, float(eps), _stream())
+    return att
+
+
 def mbconv_fused(x, w1, s1, b1, wdw, b2, w3, s3, b3, stride, residual, act):
     """Fused MBConv (expand -> dw3x3 -> project [+x]); returns None when the shape is not instantiated."""
     global launch_count
@@ -334,6 +361,18 @@ def tokens_f32_to_nchw(x, B, H, W):
     C = x.shape[-1]
     out = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
     _call("es3_tokens_f32_to_nchw", "tokens_to_nchw", _nb(x, out), 0, x.data_ptr(), out.data_ptr(), B, H * W, C, _stream())
+    return out
+
+
+def cast_f32_to_f16(x, out=None):
+    """fp32 -> fp16 (RN) of a contiguous tensor; `out` may be a preallocated fp16 staging buffer of the same numel."""
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    assert out.is_cuda and out.dtype == torch.float16 and out.is_contiguous() and out.numel() == x.numel()
+    _call("es3_cast_f32_to_f16", "cast_f32_f16", x.numel() * 6, 0, x.data_ptr(), out.data_ptr(), x.numel(), _stream())
     return out
 
 
@@ -499,17 +538,17 @@ def kd_loss_fwd(preds, teacher, sizes_hw, img_size, cosine_weight):
     return out, per
 
 
-def conv3x3_s2_c32(x, w9, scale, bias, act=None):
-    """x [B,H,W,32] bf16, w9 [9, Cout, 32] bf16 -> [B,Ho,Wo,Cout] bf16 (dense 3x3, stride 2, pad 1, folded BN)."""
+def conv3x3_s2_narrow(x, w9, scale, bias, act=None):
+    """x [B,H,W,Cin] bf16, w9 [9, Cout, Cin] bf16 -> [B,Ho,Wo,Cout] bf16 (dense 3x3, stride 2, pad 1, folded BN)."""
     _chk(x, torch.bfloat16, "x"); _chk(w9, torch.bfloat16, "w9")
     _ensure_init(x)
-    assert x.is_contiguous() and w9.is_contiguous() and x.shape[3] == 32 and w9.shape[2] == 32
-    B, H, W, _ = x.shape
+    assert x.is_contiguous() and w9.is_contiguous() and x.shape[3] == w9.shape[2]
+    B, H, W, Cin = x.shape
     Cout = w9.shape[1]
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     out = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
-    _call("es3_conv3x3_s2_c32_bf16", "conv3x3_s2_c32", _nb(x, out), 2 * B * Ho * Wo * Cout * 9 * 32, x.data_ptr(), w9.data_ptr(),
-          scale.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, Cout, ACT[act], _stream())
+    _call("es3_conv3x3_s2_narrow_bf16", f"conv3x3_s2[{Cin}-{Cout}]", _nb(x, out), 2 * B * Ho * Wo * Cout * 9 * Cin, x.data_ptr(),
+          w9.data_ptr(), scale.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, Cin, Cout, ACT[act], _stream())
     return out
 
 

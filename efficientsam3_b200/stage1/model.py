@@ -104,8 +104,8 @@ class SAM3ImageTeacherEncoder(nn.Module):
     def forward(self, x):
         feats = self.sam3.backbone.vision_backbone.trunk(x)[-1]
         if feats.shape[-1] != self.embed_size or feats.shape[-2] != self.embed_size:
-            raise NotImplementedError("teacher output resize (stage1/model.py:241-248) is not built: the shipped "
-                                      "configs use EMBED_SIZE 72 with 1008px inputs, where it is a no-op")
+            # stage1/model.py:241-248 (bilinear, align_corners=False); a no-op in the shipped configs (EMBED_SIZE 72)
+            feats, _ = ops.bilinear_nchw(feats, self.embed_size, self.embed_size)
         return feats
 
 
@@ -164,15 +164,13 @@ def _build_backbone(name, img_size):
               "efficientvit_b2": efficientvit_backbone_b2}[name]
         adapter = EfficientViTAdapter(fn())
         return adapter, adapter.out_channels
-    if name == "repvit_m1_1":
-        from ..backbones.repvit import _make_divisible, repvit_m1_1
-        model = repvit_m1_1(pretrained=False, num_classes=0, distillation=False)
-        out_channels = _make_divisible(model.cfgs[-1][2], 8)
+    if name in ("repvit_m0_9", "repvit_m1_1", "repvit_m2_3"):
+        from ..backbones import repvit
+        model = getattr(repvit, name)(pretrained=False, num_classes=0, distillation=False)
+        out_channels = repvit._make_divisible(model.cfgs[-1][2], 8)
         return RepViTAdapter(model, out_channels), out_channels
-    if name == "tiny_vit_11m":
-        from ..backbones.tiny_vit import tiny_vit_11m_224
-        adapter = TinyViTAdapter(tiny_vit_11m_224(pretrained=False, img_size=img_size), img_size)
+    if name in ("tiny_vit_5m", "tiny_vit_11m", "tiny_vit_21m"):
+        from ..backbones import tiny_vit
+        adapter = TinyViTAdapter(getattr(tiny_vit, name + "_224")(pretrained=False, img_size=img_size), img_size)
         return adapter, adapter.out_channels
-    if name.startswith("repvit") or name.startswith("tiny_vit"):
-        raise NotImplementedError(f"{name}: native student backbone not built yet (see DESIGN.md scope table)")
     raise ValueError(f"Unsupported backbone {name}")

@@ -66,7 +66,7 @@ int es3_gemm_simt(const void* A, long long lda, int a_f32, const void* W, long l
 
 /* ------------------------------------------------------------------------------------------ convs */
 /* 3x3 stride-2 pad-1 conv from the NCHW fp32 image to NHWC bf16, folded BN + act.
- * w [27][Cout] fp32 tap-major ((ci*9+ky*3+kx)), Cout in {8,16,24,32}.
+ * w [27][Cout] fp32 tap-major ((ci*9+ky*3+kx)), Cout in {8,16,24,32,48}.
  * Replaces EfficientViT input_stem op 0 (efficientvit/backbone.py:49-57). */
 int es3_stem_conv3x3_s2(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int Cout,
                         int act, void* stream);
@@ -84,6 +84,14 @@ int es3_dwconv_tiled_bf16(const void* x, long long ldx, const float* w, const fl
  * Replaces the stem ResidualBlock(DSConv) (efficientvit/backbone.py:58-67). */
 int es3_dsconv_res_bf16(const void* x, const float* wdw, const float* bdw, const float* wpw, const float* bpw,
                         void* out, int B, int H, int W, int C, int act, void* stream);
+
+/* EfficientViT-B1 input stem in one kernel on mma.sync: x1 = hswish(BN(conv3x3_s2(img))), y = x1 + BN(pw(hswish(BN(dw3x3(x1))))).
+ * img [B,3,H,W] fp32 NCHW -> out [B,Ho,Wo,16] bf16 NHWC.  w0 [16][32] bf16 (k = ci*9+ky*3+kx, zero padded), s0/b0
+ * folded BN [16]; wdw [9][16] fp32 (BN scale folded), bdw [16]; wpw [16][16] bf16 [n][k], spw/bpw folded BN [16].
+ * Replaces input_stem op 0 + op 1 (efficientvit/backbone.py:49-67) for width_list[0] == 16, hswish. */
+int es3_stem_fused_c16(const float* img, const void* w0, const float* s0, const float* b0, const float* wdw,
+                       const float* bdw, const void* wpw, const float* spw, const float* bpw, void* out, int B, int H,
+                       int W, void* stream);
 
 /* Whole MBConv block in one kernel: y = [x +] BN3(pw2(act(BN2(dw3x3_s(act(BN1(pw1(x)))))))) with the 4x-expanded
  * tensor kept in shared memory (mma.sync expand/project around an fp32 depthwise).  w1 [Mid][Cin], w3 [Cout][Mid]
@@ -119,6 +127,11 @@ int es3_litemla_aggreg_tc(void* ms, long long ld, const void* wcomb, int B, int 
 long long es3_litemla_ws_floats(int B, int HW, int heads2);
 int es3_litemla_attn(const void* ms, long long ld, float* kv_ws, void* att, long long ldo, int B, int HW, int heads2,
                      float eps, void* stream);
+/* Same contract for any head dim in {16, 32} (efficientvit_b2 / b3: dim 32): head h occupies channels [h*3*dim, +3*dim)
+ * of ms as q|k|v and [h*dim, +dim) of att.  CUDA-core fp32 formulation; kv_ws = es3_litemla_generic_ws_floats floats. */
+long long es3_litemla_generic_ws_floats(int B, int HW, int heads2, int dim);
+int es3_litemla_attn_generic(const void* ms, long long ld, float* kv_ws, void* att, long long ldo, int B, int HW, int heads2,
+                             int dim, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------ ViT trunk */
 /* LayerNorm over C (C % 128 == 0) of fp32 rows, optional tiled abs-pos add first (pos [pos_size^2, C], token
@@ -142,6 +155,9 @@ int es3_attention_mma_bf16(const void* qkv, void* out, int B, int H, int W, int 
                            void* stream);
 /* [B, HW, C] fp32 tokens -> [B, C, HW] fp32 (the NCHW map ViT.forward returns, vitdet.py:846-857). */
 int es3_tokens_f32_to_nchw(const float* in, float* out, int B, int HW, int C, void* stream);
+/* fp32 -> fp16 (RN) over n contiguous elements: the stored format of the teacher-embedding dump
+ * (save_embedding_image_stage1.py:92); done on the device so the D2H copy moves 2 bytes per element. */
+int es3_cast_f32_to_f16(const float* in, void* out, long long n, void* stream);
 
 /* Same contract as es3_litemla_attn; KV state and the apply step run on mma.sync (KV split hi+lo bf16). */
 int es3_litemla_attn_tc(const void* ms, long long ld, float* kv_ws, void* att, long long ldo, int B, int HW, int heads2,
@@ -175,10 +191,11 @@ int es3_bilinear_nchw_f32(const float* in, float* out, void* bin, float thr, lon
                           int Wo, void* stream);
 
 /* ------------------------------------------------------------------------------------------ RepViT / TinyViT */
-/* Dense 3x3, stride 2, pad 1, Cin = 32 (second patch-embed conv: repvit.py:222-223, tiny_vit.py:75-81) on mma.sync.
- * x [B,H,W,32] bf16; w [9][Cout][32] bf16 (tap, out channel, in channel); folded-BN scale/bias; out [B,Ho,Wo,Cout]. */
-int es3_conv3x3_s2_c32_bf16(const void* x, const void* w, const float* scale, const float* bias, void* out, int B, int H,
-                            int W, int Cout, int act, void* stream);
+/* Dense 3x3, stride 2, pad 1 with a narrow input (second patch-embed conv: repvit.py:222-223, tiny_vit.py:75-81) on
+ * mma.sync.  x [B,H,W,Cin] bf16; w [9][Cout][Cin] bf16 (tap, out channel, in channel); folded-BN scale/bias;
+ * out [B,Ho,Wo,Cout].  Instantiated: Cin 32 -> Cout 32/48/64, Cin 48 -> Cout 80/96 (narrower first convs are zero padded). */
+int es3_conv3x3_s2_narrow_bf16(const void* x, const void* w, const float* scale, const float* bias, void* out, int B, int H,
+                               int W, int Cin, int Cout, int act, void* stream);
 /* SqueezeExcite pieces (timm.layers.SqueezeExcite, repvit.py:136,150): per-image channel means of x [B,HW,C] bf16
  * (ws: B*ceil(HW/128)*C floats; deterministic two-stage) and y = x * gate[b,c]. */
 int es3_channel_mean(const void* x, float* ws, float* mean, int B, int HW, int C, void* stream);

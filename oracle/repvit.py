@@ -8,12 +8,21 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
+def _stage_cfgs(widths, depths):
+    """[k, t, c, SE, HS, s] rows of repvit.py:280-520: SE alternates inside a stage (stage 1 starts with SE, later stages
+    with the stride-2 block that has none), never on a stage's last block; HS flag on the last two stages."""
+    rows = []
+    for si, (c, n) in enumerate(zip(widths, depths)):
+        for i in range(n):
+            se = ((i % 2 == 0) if si == 0 else (i % 2 == 1)) and i != n - 1
+            rows.append([3, 2, c, int(se), int(si >= 2), 2 if (si > 0 and i == 0) else 1])
+    return rows
+
+
 CFGS = {
-    "repvit_m1_1": [[3, 2, 64, 1, 0, 1], [3, 2, 64, 0, 0, 1], [3, 2, 64, 0, 0, 1], [3, 2, 128, 0, 0, 2], [3, 2, 128, 1, 0, 1],
-                    [3, 2, 128, 0, 0, 1], [3, 2, 128, 0, 0, 1], [3, 2, 256, 0, 1, 2], [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1],
-                    [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1], [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1], [3, 2, 256, 1, 1, 1],
-                    [3, 2, 256, 0, 1, 1], [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1], [3, 2, 256, 1, 1, 1], [3, 2, 256, 0, 1, 1],
-                    [3, 2, 256, 0, 1, 1], [3, 2, 512, 0, 1, 2], [3, 2, 512, 1, 1, 1], [3, 2, 512, 0, 1, 1]],
+    "repvit_m0_9": _stage_cfgs((48, 96, 192, 384), (3, 4, 16, 3)),      # repvit.py:280-313
+    "repvit_m1_1": _stage_cfgs((64, 128, 256, 512), (3, 4, 14, 3)),     # repvit.py:353-384
+    "repvit_m2_3": _stage_cfgs((80, 160, 320, 640), (7, 8, 36, 3)),     # repvit.py:442-505
 }
 
 

@@ -11,8 +11,12 @@ import itertools
 import torch
 import torch.nn.functional as F
 
-VARIANTS = {"tiny_vit_11m": dict(embed_dims=[64, 128, 256, 448], depths=[2, 2, 6, 2], num_heads=[2, 4, 8, 14],
-                                 window_sizes=[7, 7, 14, 7], mlp_ratio=4.0, mbconv_expand_ratio=4.0)}
+_COMMON = dict(depths=[2, 2, 6, 2], window_sizes=[7, 7, 14, 7], mlp_ratio=4.0, mbconv_expand_ratio=4.0)
+VARIANTS = {  # tiny_vit.py:656-692
+    "tiny_vit_5m": dict(embed_dims=[64, 128, 160, 320], num_heads=[2, 4, 5, 10], **_COMMON),
+    "tiny_vit_11m": dict(embed_dims=[64, 128, 256, 448], num_heads=[2, 4, 8, 14], **_COMMON),
+    "tiny_vit_21m": dict(embed_dims=[96, 192, 384, 576], num_heads=[3, 6, 12, 18], **_COMMON),
+}
 
 
 def conv_bn(sd, p, x, stride=1, pad=0, groups=1):

@@ -151,9 +151,47 @@ def gen_neck(tag, dim, d_model, hw, B, seed_w, seed_x):
     print(tag, [tuple(t.shape) for t in s3], "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def gen_store(tag, n_rank=2, embed_dim=8, num_embedding=6):
+    """A tiny teacher-embedding store written by the reference's TxtManager (stage1/data/augmentation/manager.py),
+    including a duplicate key (first occurrence wins).  Committed as a directory of keys.txt / values.bin files."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_manager", "/root/reference/stage1/data/augmentation/manager.py")
+    ref_manager = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_manager)   # the file on its own: the package __init__ pulls in mmengine
+    TxtManager = ref_manager.TxtManager
+
+    path = os.path.join(HERE, tag)
+    if os.path.isdir(path):
+        import shutil
+        shutil.rmtree(path)
+    isz = embed_dim * 2 * num_embedding + 4
+    rng = np.random.default_rng(99)
+    for r in range(n_rank):
+        m = TxtManager(path, isz, r)
+        for i in range(4):
+            key = f"sa_{r}_{i:03d}"
+            emb = rng.standard_normal(embed_dim * num_embedding).astype(np.float16)
+            m.write(key, np.int32(1000 * r + i).tobytes() + emb.tobytes())
+            if i == 1:   # duplicate: must be ignored
+                m.write(key, np.int32(-1).tobytes() + (emb * 0).tobytes())
+        m.writer.__del__()
+        m.writer.worker = None
+    print(tag, sorted(os.listdir(path)))
+
+
 def main(which):
     if which in ("tvm", "all"):
         gen_student("tiny_vit_11m", "tvm_160", img=160, embed=12, seed_w=61, seed_x=62, batch=1)
+    if which in ("store", "all"):
+        gen_store("store_small")
+    if which in ("variants", "all"):
+        # the other six names build_image_student_model accepts (stage1/model.py:386-417); small embeds keep the files small
+        gen_student("repvit_m0_9", "rv_m0_9_128", img=128, embed=6, seed_w=71, seed_x=72, batch=1)
+        gen_student("repvit_m2_3", "rv_m2_3_128", img=128, embed=6, seed_w=73, seed_x=74, batch=1)
+        gen_student("tiny_vit_5m", "tv_5m_160", img=160, embed=6, seed_w=75, seed_x=76, batch=1)
+        gen_student("tiny_vit_21m", "tv_21m_160", img=160, embed=6, seed_w=77, seed_x=78, batch=1)
+        gen_student("efficientvit_b0", "ev_b0_160", img=160, embed=6, seed_w=79, seed_x=80, batch=1)
+        gen_student("efficientvit_b2", "ev_b2_192", img=192, embed=6, seed_w=81, seed_x=82, batch=1)   # 6x6 = 36 > dim 32
     if which in ("rvm", "all"):
         gen_student("repvit_m1_1", "rvm_160", img=160, embed=12, seed_w=51, seed_x=52, batch=1)
     if which in ("neck", "all"):

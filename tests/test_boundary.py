@@ -55,6 +55,19 @@ def test_product_does_not_import_oracle():
                 assert "/root/reference" not in text, os.path.join(dp, f)
 
 
+STUDENT_FIXTURES = {"efficientvit_b0": "ev_b0_160", "efficientvit_b1": "evm_160", "efficientvit_b2": "ev_b2_192",
+                    "repvit_m0_9": "rv_m0_9_128", "repvit_m1_1": "rvm_160", "repvit_m2_3": "rv_m2_3_128",
+                    "tiny_vit_5m": "tv_5m_160", "tiny_vit_11m": "tvm_160", "tiny_vit_21m": "tv_21m_160"}
+
+
+def test_unknown_backbone_is_a_value_error():
+    from types import SimpleNamespace as NS
+    import pytest
+    from efficientsam3_b200.stage1.model import build_image_student_model
+    with pytest.raises(ValueError):
+        build_image_student_model(NS(MODEL=NS(BACKBONE="resnet50"), DATA=NS(IMG_SIZE=160), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=12)))
+
+
 def test_state_dict_keys_match_reference_record():
     """Key-for-key (name, shape, dtype, order) equality with the key list recorded from the reference modules."""
     from types import SimpleNamespace as NS
@@ -65,8 +78,12 @@ def test_state_dict_keys_match_reference_record():
     def sig(sd):
         return [f"{k}|{','.join(map(str, v.shape))}|{str(v.dtype).replace('torch.', '')}" for k, v in sd.items()]
 
-    g = load_golden("evm_160")
-    cfg = NS(MODEL=NS(BACKBONE="efficientvit_b1"), DATA=NS(IMG_SIZE=160), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=12))
-    assert sig(build_image_student_model(cfg).state_dict()) == [str(k) for k in g["keys"]]
+    # all nine names the reference builder accepts (stage1/model.py:386-417)
+    for name, fixture in STUDENT_FIXTURES.items():
+        g = load_golden(fixture)
+        cfg = NS(MODEL=NS(BACKBONE=name), DATA=NS(IMG_SIZE=int(g["img"])), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=int(g["embed"])))
+        m = build_image_student_model(cfg)
+        assert sig(m.state_dict()) == [str(k) for k in g["keys"]], name
+        assert sum(p.numel() for p in m.parameters()) == int(g["n_params"]), name
     g = load_golden("vit_small_112")
     assert sig(create_sam3_vit_backbone(**eval(str(g["cfg"]))).state_dict()) == [str(k) for k in g["keys"]]

@@ -46,6 +46,13 @@ GEMM_CASES = [
     (3969, 384, 128, None, False, False, 0),
     (2048, 512, 128, "hswish", False, False, 64),
     (2048, 128, 512, None, True, False, 32),
+    # N % 32 != 0 (ragged last 32-column chunk: channel widths 8/16/24/48/80 of efficientvit b0/b2, repvit m0_9/m2_3), small K
+    (1000, 48, 96, "hswish", True, False, 0),
+    (777, 80, 160, "gelu", True, False, 0),
+    (513, 16, 64, None, True, False, 0),
+    (300, 8, 32, "relu", False, True, 0),
+    (640, 24, 8, None, False, False, 0),
+    (2048, 160, 24, "hswish", True, True, 0),
 ]
 
 
@@ -138,6 +145,34 @@ def test_dsconv_res(cuda):
     mid = F.hardswish(F.conv2d(xn, wdw, bdw, padding=1, groups=C)).to(torch.bfloat16).float()
     ref = (F.conv2d(mid, wpw[:, :, None, None], bpw) + xn).permute(0, 2, 3, 1)
     _close(out, ref, 1e-2, "dsconv_res")
+
+
+@pytest.mark.parametrize("H,W", [(64, 64), (61, 75), (130, 34), (18, 7)])
+def test_stem_fused(cuda, H, W):
+    """One-launch stem (conv3x3 s2 + residual DSConv on mma.sync) vs the fp32 torch composition with the same bf16 roundings."""
+    from efficientsam3_b200 import ops
+    _r = lambda t: t.to(torch.bfloat16).float()
+    g = torch.Generator().manual_seed(H * 7 + W)
+    C = 16
+    x = torch.randn(2, 3, H, W, generator=g).to(cuda)
+    w0 = _r(torch.randn(C, 3, 3, 3, generator=g) / 5).to(cuda)
+    s0 = (torch.rand(C, generator=g) + 0.5).to(cuda)
+    b0 = torch.randn(C, generator=g).to(cuda)
+    wdw = _r(torch.randn(C, 1, 3, 3, generator=g) / 3).to(cuda)
+    bdw = torch.randn(C, generator=g).to(cuda)
+    wpw = _r(torch.randn(C, C, generator=g) / 4).to(cuda)
+    spw = (torch.rand(C, generator=g) + 0.5).to(cuda)
+    bpw = torch.randn(C, generator=g).to(cuda)
+    w0p = torch.zeros(C, 32, device=cuda)
+    w0p[:, :27] = w0.reshape(C, 27)
+    out = ops.stem_fused_c16(x, w0p.to(torch.bfloat16).contiguous(), s0, b0, wdw.reshape(C, 9).t().contiguous(), bdw,
+                             wpw.to(torch.bfloat16).contiguous(), spw, bpw)
+    x1 = F.hardswish(F.conv2d(_r(x), w0, None, stride=2, padding=1) * s0.view(1, -1, 1, 1) + b0.view(1, -1, 1, 1))
+    x1 = _r(x1)
+    mid = _r(F.hardswish(F.conv2d(x1, wdw, bdw, padding=1, groups=C)))
+    ref = (F.conv2d(mid, wpw[:, :, None, None]) * spw.view(1, -1, 1, 1) + bpw.view(1, -1, 1, 1) + x1).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    _close(out, ref, 1e-2, "stem_fused")
 
 
 @pytest.mark.parametrize("Hi,Wi,Ho,Wo", [(32, 32, 72, 72), (32, 32, 64, 64), (8, 8, 18, 18), (16, 16, 16, 16)])
@@ -235,16 +270,17 @@ def test_mbconv_fused_uninstantiated_shape_returns_none(cuda):
     assert y is None
 
 
-@pytest.mark.parametrize("H,W,Cout", [(64, 64, 64), (63, 41, 64), (20, 36, 32)])
-def test_conv3x3_s2_c32(cuda, H, W, Cout):
+@pytest.mark.parametrize("H,W,Cin,Cout", [(64, 64, 32, 64), (63, 41, 32, 64), (20, 36, 32, 32), (40, 40, 32, 48), (33, 50, 48, 80),
+                                          (64, 30, 48, 96)])
+def test_conv3x3_s2_narrow(cuda, H, W, Cin, Cout):
     from efficientsam3_b200 import ops
     g = torch.Generator().manual_seed(H + Cout)
-    x = _bf(torch.randn(2, H, W, 32, generator=g)).to(cuda)
-    w = _bf(torch.randn(Cout, 32, 3, 3, generator=g) / 17).to(cuda)
+    x = _bf(torch.randn(2, H, W, Cin, generator=g)).to(cuda)
+    w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g) / 17).to(cuda)
     sc = (torch.rand(Cout, generator=g) + 0.5).to(cuda); bi = torch.randn(Cout, generator=g).to(cuda)
-    out = ops.conv3x3_s2_c32(x, w.permute(2, 3, 0, 1).reshape(9, Cout, 32).contiguous(), sc, bi, None)
+    out = ops.conv3x3_s2_narrow(x, w.permute(2, 3, 0, 1).reshape(9, Cout, Cin).contiguous(), sc, bi, None)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), stride=2, padding=1) * sc.view(1, -1, 1, 1) + bi.view(1, -1, 1, 1)
-    _close(out, ref.permute(0, 2, 3, 1), 1e-2, "conv3x3_s2_c32")
+    _close(out, ref.permute(0, 2, 3, 1), 1e-2, "conv3x3_s2_narrow")
 
 
 def test_squeeze_excite_pieces(cuda):

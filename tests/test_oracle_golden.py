@@ -24,15 +24,15 @@ def _assert_close(got, ref, rtol=1e-5):
     assert err <= rtol * scale + 1e-7, f"max abs err {err:.3e} vs scale {scale:.3e}"
 
 
-@pytest.mark.parametrize("name", ["evm_160", "evm_64_quadratic"])
-def test_efficientvit_oracle_matches_reference(name):
+@pytest.mark.parametrize("name,variant", [("evm_160", "b1"), ("evm_64_quadratic", "b1"), ("ev_b0_160", "b0"), ("ev_b2_192", "b2")])
+def test_efficientvit_oracle_matches_reference(name, variant):
     from oracle import efficientvit as O
     g = _load(name)
     sd = _sd_from_keys(g["keys"], int(g["seed_w"]))
     img, embed, batch = int(g["img"]), int(g["embed"]), int(g["batch"])
     x = torch.randn(batch, 3, img, img, generator=torch.Generator().manual_seed(int(g["seed_x"])))
     with torch.no_grad():
-        out, stages = O.image_student_encoder(sd, x, embed, "b1", return_stages=True)
+        out, stages = O.image_student_encoder(sd, x, embed, variant, return_stages=True)
     _assert_close(out.numpy(), g["out"], rtol=2e-5)
     for k, t in stages.items():
         assert tuple(t.shape) == tuple(g[f"shape_{k}"])
@@ -97,21 +97,23 @@ def test_neck_oracle_matches_reference():
                 _assert_close(t.numpy(), g[f"{name}_{i}"], rtol=2e-5)
 
 
-def test_repvit_oracle_matches_reference():
+@pytest.mark.parametrize("name,variant", [("rvm_160", "repvit_m1_1"), ("rv_m0_9_128", "repvit_m0_9"), ("rv_m2_3_128", "repvit_m2_3")])
+def test_repvit_oracle_matches_reference(name, variant):
     from oracle import repvit as O
-    g = _load("rvm_160")
+    g = _load(name)
     sd = _sd_from_keys(g["keys"], int(g["seed_w"]))
     x = torch.randn(int(g["batch"]), 3, int(g["img"]), int(g["img"]), generator=torch.Generator().manual_seed(int(g["seed_x"])))
     with torch.no_grad():
-        out = O.image_student_encoder(sd, x, int(g["embed"]))
+        out = O.image_student_encoder(sd, x, int(g["embed"]), variant)
     _assert_close(out.numpy(), g["out"], rtol=2e-5)
 
 
-def test_tinyvit_oracle_matches_reference():
+@pytest.mark.parametrize("name,variant", [("tvm_160", "tiny_vit_11m"), ("tv_5m_160", "tiny_vit_5m"), ("tv_21m_160", "tiny_vit_21m")])
+def test_tinyvit_oracle_matches_reference(name, variant):
     from oracle import tinyvit as O
-    g = _load("tvm_160")
+    g = _load(name)
     sd = _sd_from_keys(g["keys"], int(g["seed_w"]))
     x = torch.randn(int(g["batch"]), 3, int(g["img"]), int(g["img"]), generator=torch.Generator().manual_seed(int(g["seed_x"])))
     with torch.no_grad():
-        out = O.image_student_encoder(sd, x, int(g["embed"]))
+        out = O.image_student_encoder(sd, x, int(g["embed"]), variant)
     _assert_close(out.numpy(), g["out"], rtol=2e-5)

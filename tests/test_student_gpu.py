@@ -137,3 +137,43 @@ def test_tvm_matches_oracle(cuda, img, embed, batch):
         ref = O.image_student_encoder(sd, x, embed)
     out = _build_tv(img, embed, sd, cuda)(x.to(cuda)).cpu()
     _check(out, ref, f"tvm {img} vs oracle")
+
+
+# ---- the other six backbones build_image_student_model accepts (stage1/model.py:386-417) -----------------------------
+VARIANTS = {"efficientvit_b0": ("ev_b0_160", "efficientvit", "b0"), "efficientvit_b2": ("ev_b2_192", "efficientvit", "b2"),
+            "repvit_m0_9": ("rv_m0_9_128", "repvit", "repvit_m0_9"), "repvit_m2_3": ("rv_m2_3_128", "repvit", "repvit_m2_3"),
+            "tiny_vit_5m": ("tv_5m_160", "tinyvit", "tiny_vit_5m"), "tiny_vit_21m": ("tv_21m_160", "tinyvit", "tiny_vit_21m")}
+
+
+def _build_any(name, img, embed, sd, dev):
+    from efficientsam3_b200.stage1.model import build_image_student_model
+    cfg = NS(MODEL=NS(BACKBONE=name), DATA=NS(IMG_SIZE=img), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=embed))
+    m = build_image_student_model(cfg)
+    m.load_state_dict(sd)
+    return m.to(dev).eval()
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_variant_matches_reference_fixture(cuda, name):
+    g = load_golden(VARIANTS[name][0])
+    sd = sd_from_keys(g["keys"], int(g["seed_w"]))
+    img, embed = int(g["img"]), int(g["embed"])
+    x = torch.randn(int(g["batch"]), 3, img, img, generator=torch.Generator().manual_seed(int(g["seed_x"])))
+    out = _build_any(name, img, embed, sd, cuda)(x.to(cuda)).cpu()
+    assert out.shape == tuple(g["out"].shape)
+    _check(out, g["out"], f"{name} vs reference fixture")
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_variant_matches_oracle_512(cuda, name):
+    """A second, larger shape (batch 2, 512^2 -> ragged tiles, more windows) against the CPU oracle."""
+    import importlib
+    fixture, mod, variant = VARIANTS[name]
+    O = importlib.import_module(f"oracle.{mod}")
+    g = load_golden(fixture)
+    sd = sd_from_keys(g["keys"], 303)
+    x = torch.randn(2, 3, 512, 512, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        ref = O.image_student_encoder(sd, x, 20, variant)
+    out = _build_any(name, 512, 20, sd, cuda)(x.to(cuda)).cpu()
+    _check(out, ref, f"{name} 512 vs oracle")

@@ -5,6 +5,7 @@ end-to-end trunk embedding (bf16 GEMM operands, fp32 residual stream, fp32 softm
 relative L2 <= 2e-2, cosine >= 0.9995 against the fp32 reference / oracle.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -172,3 +173,43 @@ def test_teacher_encoder_api(cuda):
     assert out.shape == (1, 1024, 72, 72) and out.dtype == torch.float32 and torch.isfinite(out).all()
     with pytest.raises(AssertionError):
         t(torch.randn(1, 3, 1022, 1022, device=cuda))   # the reference asserts on any size but 1008
+
+
+def test_teacher_resize_and_embedding_dump(cuda, tmp_path):
+    """A21: teacher forward -> device fp16 cast -> double-buffered D2H -> store records; read back through the store reader
+    and compare with `model(x).half()` record by record (bit-exact: same forward, same RN cast)."""
+    import numpy as np
+    import torch.nn.functional as F
+    from efficientsam3_b200.stage1 import embeddings as E
+    from efficientsam3_b200.stage1.model import SAM3ImageTeacherEncoder
+    torch.manual_seed(0)
+    t = SAM3ImageTeacherEncoder(embed_size=64, vit_overrides=dict(depth=1, global_att_blocks=())).to(cuda)
+    xs = [torch.randn(2, 3, 1008, 1008) for _ in range(3)]
+    # resize path == bilinear of the 72x72 map
+    t72 = SAM3ImageTeacherEncoder(embed_size=72, vit_overrides=dict(depth=1, global_att_blocks=())).to(cuda)
+    t72.load_state_dict(t.state_dict())
+    ref = F.interpolate(t72(xs[0].to(cuda)), size=(64, 64), mode="bilinear", align_corners=False)
+    got = t(xs[0].to(cuda))
+    assert got.shape == (2, 1024, 64, 64)
+    assert (got - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+    keys = [[f"img_{b}_{i}" for i in range(2)] for b in range(3)]
+    keys[2][1] = keys[0][0]                         # duplicate key: the first record must win
+    seeds = [[10 * b + i for i in range(2)] for b in range(3)]
+    loader = [((list(x), None), (keys[b], np.array(seeds[b], dtype=np.int32))) for b, x in enumerate(xs)]
+    path = str(tmp_path / "emb")
+    n = E.save_embeddings_one_epoch(t, loader, path, rank=0)
+    assert n == 6
+    rd = E.EmbeddingStoreReader(path, E.item_size(1024, 64 * 64), 0)
+    for b, x in enumerate(xs):
+        want = t(x.to(cuda)).half().cpu().numpy()
+        for i in range(2):
+            if b == 2 and i == 1:
+                continue
+            seed, emb = rd.read_embedding(keys[b][i], (1024, 64, 64))
+            assert seed == seeds[b][i]
+            assert np.array_equal(emb, want[i]), (b, i)
+    seed, emb = rd.read_embedding(keys[0][0], (1024, 64, 64))
+    assert seed == 0
+    with open(os.path.join(path, "rank0-keys.txt")) as f:
+        assert len(f.read().split()) == 5
