@@ -30,7 +30,9 @@ SIGNATURES: dict[str, list] = {
     "es3_cast_f32_to_f16": [_vp, _vp, _ll, _vp],
     "es3_convt2x2_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp],
     "es3_dense_pe": [_vp, _i, _i, _i, _vp, _vp],
-    "es3_point_embed": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp],
+    "es3_point_embed": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp],
+    "es3_mask_downscale_tokens": [_vp] * 12 + [_ll, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "es3_fill_small_components": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp],
     "es3_add_rows": [_vp, _vp, _ll, _i, _i, _vp, _vp, _vp],
     "es3_nchw_f32_to_tokens": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "es3_attn_few_queries": [_vp, _ll, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp],
@@ -39,6 +41,9 @@ SIGNATURES: dict[str, list] = {
     "es3_hyper_masks": [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_bilinear_nchw_f32": [_vp, _vp, _vp, _f, _ll, _i, _i, _i, _i, _vp],
     "es3_kd_loss_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
+    "es3_kd_loss_bwd": [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _f, _vp, _vp],
+    "es3_grad_norm": [_vp, _ll, _vp, _vp, _vp],
+    "es3_adamw_flat": [_vp, _vp, _vp, _vp, _ll, _ll, _f, _f, _f, _f, _f, _f, _f, _vp, _vp, _i, _f, _f, _i, _vp],
     "es3_conv3x3_s2_narrow_bf16": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_channel_mean": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "es3_scale_channels": [_vp, _vp, _vp, _i, _i, _i, _vp],

@@ -28,15 +28,15 @@ __global__ void dense_pe_kernel(const float* __restrict__ gauss, int F, int h, i
   out[(long long)p * 2 * F + F + f] = c;
 }
 
-// Sparse point embeddings with the trailing padding point (_embed_points with pad=True, :71-117).
-// coords [B,P,2] (x,y) pixels, labels [B,P] int32.  out [B,P+1,2F] fp32.
+// Sparse point embeddings, optionally with the trailing padding point (_embed_points, pad = boxes is None, :71-117).
+// coords [B,P,2] (x,y) pixels, labels [B,P] int32.  out [B,P+pad,2F] fp32.
 // tables: not_a_point [2F], point_emb [4][2F].
 __global__ void point_embed_kernel(const float* __restrict__ coords, const int* __restrict__ labels,
                                    const float* __restrict__ gauss, const float* __restrict__ not_a_point,
-                                   const float* __restrict__ point_emb, int F, int P, float img_w, float img_h,
+                                   const float* __restrict__ point_emb, int F, int P, int pad, float img_w, float img_h,
                                    float* __restrict__ out) {
-  const int bp = blockIdx.x;  // b*(P+1) + p
-  const int b = bp / (P + 1), p = bp % (P + 1);
+  const int bp = blockIdx.x;  // b*(P+pad) + p
+  const int b = bp / (P + pad), p = bp % (P + pad);
   float x = 0.f, y = 0.f;
   int lab = -1;
   if (p < P) {
@@ -280,6 +280,146 @@ __global__ void bilinear_nchw_kernel(const float* __restrict__ in, float* __rest
   if (bin) bin[idx] = v > thr ? 1 : 0;
 }
 
+
+// ------------------------------------------------------------------------------------ mask prompt
+// PromptEncoder.mask_downscaling (prompt_encoder.py:45-63): Conv2d(1,4,k2,s2) -> LayerNorm2d -> GELU -> Conv2d(4,16,k2,s2)
+// -> LayerNorm2d -> GELU -> Conv2d(16,C,1), fused with `src = image_embeddings + dense` (mask_decoder.py:189) and emitted
+// token-major: keys[row][c] = base[row % base_rows][c] + dense[row][c].  One block = 16 output pixels: 16 threads run the
+// two tiny convs for their pixel (a 4x4 input patch), then thread c owns output channel c for all 16 pixels.
+struct MaskDsW {
+  const float *w0, *b0, *g1, *be1;   // [4][2][2], [4], LN 4
+  const float *w1, *b1, *g2, *be2;   // [16][4][2][2], [16], LN 16
+  const float *w2, *b2;              // [C][16], [C]
+};
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+__global__ void __launch_bounds__(256) mask_downscale_kernel(const float* __restrict__ mask, MaskDsW wt, const float* __restrict__ base,
+                                                             long long base_rows, float* __restrict__ out_f32,
+                                                             bf16* __restrict__ out_bf16, int B, int h, int w, int C, float eps) {
+  __shared__ float s_v[16][17];
+  const long long row0 = (long long)blockIdx.x * 16;
+  const long long rows = (long long)B * h * w;
+  if (threadIdx.x < 16 && row0 + threadIdx.x < rows) {
+    const long long row = row0 + threadIdx.x;
+    const int b = (int)(row / (h * w)), p = (int)(row % (h * w));
+    const int y = p / w, x = p % w;
+    const float* mp = mask + ((long long)b * 4 * h + 4 * y) * (4 * w) + 4 * x;   // 4x4 input patch
+    float a[4][4];   // [position (py*2+px)][channel] after conv0 + LN + GELU
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        float t[4], mu = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float acc = wt.b0[c];
+#pragma unroll
+          for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 2; ++kx) acc = fmaf(wt.w0[c * 4 + ky * 2 + kx], mp[(2 * py + ky) * (4 * w) + 2 * px + kx], acc);
+          t[c] = acc; mu += acc;
+        }
+        mu *= 0.25f;
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) var += (t[c] - mu) * (t[c] - mu);
+        const float rs = rsqrtf(var * 0.25f + eps);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a[py * 2 + px][c] = gelu_erf(wt.g1[c] * ((t[c] - mu) * rs) + wt.be1[c]);
+      }
+    float u[16], mu = 0.f;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      float acc = wt.b1[n];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int pos = 0; pos < 4; ++pos) acc = fmaf(wt.w1[(n * 4 + c) * 4 + pos], a[pos][c], acc);
+      u[n] = acc; mu += acc;
+    }
+    mu *= (1.f / 16.f);
+    float var = 0.f;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) var += (u[n] - mu) * (u[n] - mu);
+    const float rs = rsqrtf(var * (1.f / 16.f) + eps);
+#pragma unroll
+    for (int n = 0; n < 16; ++n) s_v[threadIdx.x][n] = gelu_erf(wt.g2[n] * ((u[n] - mu) * rs) + wt.be2[n]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float wr[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) wr[k] = wt.w2[c * 16 + k];
+    const float bc = wt.b2[c];
+    for (int i = 0; i < 16 && row0 + i < rows; ++i) {
+      float acc = bc;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc = fmaf(wr[k], s_v[i][k], acc);
+      const long long row = row0 + i;
+      if (base != nullptr) acc += base[(row % base_rows) * C + c];
+      if (out_f32) out_f32[row * C + c] = acc;
+      if (out_bf16) out_bf16[row * C + c] = __float2bfloat16(acc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ small-component filling
+// SAM2Transforms.postprocess_masks before the resize (sam1_utils.py:77-105): connected components (8-connectivity, as
+// skimage.measure.label / cc_torch / the Triton kernel in perflib/) of the background (score <= thr) with area <= max_hole
+// become thr + 10; components of the foreground (score > thr, judged on the ORIGINAL scores) with area <= max_sprinkle
+// become thr - 10.  Labels: lock-free union-find on global memory (root = smallest pixel index of the component, so the
+// result is deterministic), areas by integer atomics on the roots.
+__device__ __forceinline__ int cc_find(const int* L, int i) {
+  int p = L[i];
+  while (p != i) { i = p; p = L[i]; }
+  return i;
+}
+__device__ __forceinline__ void cc_union(int* L, int a, int b) {
+  bool done;
+  do {
+    a = cc_find(L, a);
+    b = cc_find(L, b);
+    if (a < b) { const int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+    else if (b < a) { const int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+    else done = true;
+  } while (!done);
+}
+// sel > 0: component class = (score > thr); sel == 0: class = (score <= thr).
+__device__ __forceinline__ bool cc_in_class(float v, float thr, int fg) { return fg ? (v > thr) : (v <= thr); }
+
+__global__ void cc_init_kernel(const float* __restrict__ in, int* __restrict__ L, int* __restrict__ area, long long total, float thr, int fg) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  L[i] = cc_in_class(in[i], thr, fg) ? (int)i : -1;
+  area[i] = 0;
+}
+__global__ void cc_merge_kernel(const float* __restrict__ in, int* __restrict__ L, int N, int H, int W) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * H * W) return;
+  if (L[i] < 0) return;
+  const int x = (int)(i % W), y = (int)((i / W) % H);
+  // half of the 8-neighbourhood is enough: W, NW, N, NE
+  if (x > 0 && L[i - 1] >= 0) cc_union(L, (int)i, (int)i - 1);
+  if (y > 0) {
+    if (L[i - W] >= 0) cc_union(L, (int)i, (int)i - W);
+    if (x > 0 && L[i - W - 1] >= 0) cc_union(L, (int)i, (int)i - W - 1);
+    if (x + 1 < W && L[i - W + 1] >= 0) cc_union(L, (int)i, (int)i - W + 1);
+  }
+}
+__global__ void cc_count_kernel(int* __restrict__ L, int* __restrict__ area, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total || L[i] < 0) return;
+  const int r = cc_find(L, (int)i);
+  L[i] = r;                     // roots are fixed points, so compressing while others still read is safe
+  atomicAdd(&area[r], 1);
+}
+__global__ void cc_apply_kernel(const int* __restrict__ L, const int* __restrict__ area, float* __restrict__ out, long long total,
+                                float max_area, float value) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total || L[i] < 0) return;
+  if ((float)area[cc_find(L, (int)i)] <= max_area) out[i] = value;
+}
+
 }  // namespace es3
 
 using namespace es3;
@@ -292,10 +432,11 @@ extern "C" int es3_dense_pe(const float* gauss, int F, int h, int w, float* out,
 }
 
 extern "C" int es3_point_embed(const float* coords, const int* labels, const float* gauss, const float* not_a_point,
-                               const float* point_emb, int F, int B, int P, float img_w, float img_h, float* out,
+                               const float* point_emb, int F, int B, int P, int pad, float img_w, float img_h, float* out,
                                void* stream) {
-  point_embed_kernel<<<B * (P + 1), 128, 0, (cudaStream_t)stream>>>(coords, labels, gauss, not_a_point, point_emb, F, P, img_w,
-                                                                  img_h, out);
+  ES3_REQUIRE(B > 0 && P + (pad != 0) > 0, "es3_point_embed: empty prompt batch");
+  point_embed_kernel<<<B * (P + (pad != 0)), 128, 0, (cudaStream_t)stream>>>(coords, labels, gauss, not_a_point, point_emb, F, P,
+                                                                           pad != 0, img_w, img_h, out);
   ES3_LAUNCH_CHECK("point_embed_kernel");
   return 0;
 }
@@ -367,5 +508,39 @@ extern "C" int es3_bilinear_nchw_f32(const float* in, float* out, void* bin, flo
   bilinear_nchw_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
       in, out, (uint8_t*)bin, thr, Hi, Wi, Ho, Wo, (float)Hi / Ho, (float)Wi / Wo, planes);
   ES3_LAUNCH_CHECK("bilinear_nchw_kernel");
+  return 0;
+}
+
+extern "C" int es3_mask_downscale_tokens(const float* mask, const float* w0, const float* b0, const float* g1, const float* be1,
+                                         const float* w1, const float* b1, const float* g2, const float* be2, const float* w2,
+                                         const float* b2, const float* base, long long base_rows, float* out_f32, void* out_bf16,
+                                         int B, int h, int w, int C, float eps, void* stream) {
+  ES3_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && (base == nullptr || base_rows > 0), "es3_mask_downscale_tokens: bad shape");
+  MaskDsW wt{w0, b0, g1, be1, w1, b1, g2, be2, w2, b2};
+  const long long rows = (long long)B * h * w;
+  mask_downscale_kernel<<<(unsigned)ceil_div(rows, 16), 256, 0, (cudaStream_t)stream>>>(mask, wt, base, base_rows, out_f32,
+                                                                                       (bf16*)out_bf16, B, h, w, C, eps);
+  ES3_LAUNCH_CHECK("mask_downscale_kernel");
+  return 0;
+}
+
+// in/out [N,H,W] fp32 (out may not alias in); labels_ws / area_ws: N*H*W ints each.
+extern "C" int es3_fill_small_components(const float* in, float* out, int* labels_ws, int* area_ws, int N, int H, int W, float thr,
+                                         float max_hole_area, float max_sprinkle_area, void* stream) {
+  ES3_REQUIRE(N > 0 && H > 0 && W > 0 && (long long)N * H * W < 2147483647LL, "es3_fill_small_components: bad shape");
+  ES3_REQUIRE(in != out, "es3_fill_small_components: in-place operation is not supported");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)N * H * W;
+  const unsigned blocks = (unsigned)ceil_div(total, 256);
+  ES3_CHECK_CUDA(cudaMemcpyAsync(out, in, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  for (int fg = 0; fg < 2; ++fg) {
+    const float max_area = fg ? max_sprinkle_area : max_hole_area;
+    if (!(max_area > 0.f)) continue;
+    cc_init_kernel<<<blocks, 256, 0, st>>>(in, labels_ws, area_ws, total, thr, fg);
+    cc_merge_kernel<<<blocks, 256, 0, st>>>(in, labels_ws, N, H, W);
+    cc_count_kernel<<<blocks, 256, 0, st>>>(labels_ws, area_ws, total);
+    cc_apply_kernel<<<blocks, 256, 0, st>>>(labels_ws, area_ws, out, total, max_area, fg ? thr - 10.f : thr + 10.f);
+  }
+  ES3_LAUNCH_CHECK("cc kernels");
   return 0;
 }

@@ -18,7 +18,7 @@ def _stream() -> int:
 
 # ------------------------------------------------------------------------------------ accounting
 # kernels launched per C-ABI call (memsets excluded) -- bench.py reports the sum as `gpu_launches`.
-KERNELS_PER_CALL = {"es3_litemla_attn": 2, "es3_litemla_attn_generic": 2, "es3_litemla_attn_tc": 2, "es3_kd_loss_fwd": 2, "es3_channel_mean": 2}
+KERNELS_PER_CALL = {"es3_litemla_attn": 2, "es3_litemla_attn_generic": 2, "es3_fill_small_components": 4, "es3_grad_norm": 2, "es3_adamw_flat": 2, "es3_litemla_attn_tc": 2, "es3_kd_loss_fwd": 2, "es3_channel_mean": 2}
 launch_count = 0
 
 
@@ -409,16 +409,52 @@ def dense_pe(gauss, h, w):
     return out
 
 
-def point_embed(coords, labels, gauss, not_a_point, point_emb, img_w, img_h):
-    """coords [B,P,2] fp32, labels [B,P] int32 -> [B,P+1,C] fp32 (padding point appended)."""
+def point_embed(coords, labels, gauss, not_a_point, point_emb, img_w, img_h, pad=True):
+    """coords [B,P,2] fp32, labels [B,P] int32 -> [B,P+pad,C] fp32 (pad: the padding point appended when no box is given)."""
     _chk(coords, torch.float32, "coords")
     _ensure_init(coords)
     B, P, _ = coords.shape
     F_ = gauss.shape[1]
-    out = torch.empty((B, P + 1, 2 * F_), device=coords.device, dtype=torch.float32)
+    out = torch.empty((B, P + int(pad), 2 * F_), device=coords.device, dtype=torch.float32)
     _call("es3_point_embed", "point_embed", _nb(out), 0, coords.contiguous().data_ptr(),
           labels.to(torch.int32).contiguous().data_ptr(), gauss.contiguous().data_ptr(), not_a_point.contiguous().data_ptr(),
-          point_emb.contiguous().data_ptr(), F_, B, P, float(img_w), float(img_h), out.data_ptr(), _stream())
+          point_emb.contiguous().data_ptr(), F_, B, P, int(pad), float(img_w), float(img_h), out.data_ptr(), _stream())
+    return out
+
+
+def mask_downscale_tokens(mask, weights, base=None, eps=1e-6, out_bf16=True, out_f32=True):
+    """mask [B,1,4h,4w] fp32; weights = (w0,b0,g1,be1,w1,b1,g2,be2,w2,b2) fp32 contiguous -> token-major
+    (bf16|None, fp32|None) [B*h*w, C] = base[row % base_rows] + mask_downscaling(mask)."""
+    _chk(mask, torch.float32, "mask")
+    _ensure_init(mask)
+    mask = mask.contiguous()
+    B, one, H4, W4 = mask.shape
+    assert one == 1 and H4 % 4 == 0 and W4 % 4 == 0 and len(weights) == 10
+    h, w = H4 // 4, W4 // 4
+    C = weights[8].shape[0]
+    for t in weights:
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    if base is not None:
+        _chk(base, torch.float32, "base")
+        assert base.is_contiguous() and base.shape[1] == C
+    yb = torch.empty((B * h * w, C), device=mask.device, dtype=torch.bfloat16) if out_bf16 else None
+    yf = torch.empty((B * h * w, C), device=mask.device, dtype=torch.float32) if out_f32 else None
+    _call("es3_mask_downscale_tokens", "mask_downscale", _nb(mask, yb, yf, base), 0, mask.data_ptr(), *[t.data_ptr() for t in weights],
+          _ptr(base), base.shape[0] if base is not None else 0, _ptr(yf), _ptr(yb), B, h, w, C, float(eps), _stream())
+    return yb, yf
+
+
+def fill_small_components(masks, thr=0.0, max_hole_area=0.0, max_sprinkle_area=0.0):
+    """masks [..., H, W] fp32 logits -> copy with small background holes / foreground sprinkles filled (8-connectivity)."""
+    _chk(masks, torch.float32, "masks")
+    _ensure_init(masks)
+    x = masks.contiguous()
+    H, W = x.shape[-2:]
+    N = x.numel() // (H * W)
+    out = torch.empty_like(x)
+    ws = torch.empty((2, N * H * W), device=x.device, dtype=torch.int32)
+    _call("es3_fill_small_components", "fill_small_components", _nb(x, out), 0, x.data_ptr(), out.data_ptr(), ws[0].data_ptr(),
+          ws[1].data_ptr(), N, H, W, float(thr), float(max_hole_area), float(max_sprinkle_area), _stream())
     return out
 
 
@@ -536,6 +572,41 @@ def kd_loss_fwd(preds, teacher, sizes_hw, img_size, cosine_weight):
           sizes_hw.contiguous().data_ptr(), B, C, E, img_size, float(cosine_weight), ws.data_ptr(), out.data_ptr(), per.data_ptr(),
           _stream())
     return out, per
+
+
+def kd_loss_bwd(preds, teacher, sizes_hw, per_sample, img_size, cosine_weight, grad_scale=1.0, scale_dev=None):
+    """Gradient of the KD loss w.r.t. preds ([B,C,E,E] fp32), times grad_scale (and the device loss scale scale_dev[0])."""
+    _chk(preds, torch.float32, "preds"); _chk(teacher, torch.float32, "teacher")
+    _ensure_init(preds)
+    preds, teacher = preds.contiguous(), teacher.contiguous()
+    B, C, E, _ = preds.shape
+    out = torch.empty_like(preds)
+    _call("es3_kd_loss_bwd", "kd_loss_bwd", 3 * _nb(preds), 8 * preds.numel(), preds.data_ptr(), teacher.data_ptr(),
+          sizes_hw.contiguous().data_ptr(), per_sample.data_ptr(), _ptr(scale_dev), float(grad_scale), B, C, E, img_size,
+          float(cosine_weight), out.data_ptr(), _stream())
+    return out
+
+
+def grad_norm(flat_grad, part_ws, norm_ws):
+    """norm_ws[0] = sum g^2, norm_ws[1] = non-finite flag over the flat fp32 arena (no host sync)."""
+    _chk(flat_grad, torch.float32, "flat_grad")
+    _ensure_init(flat_grad)
+    assert flat_grad.is_contiguous() and part_ws.numel() >= 8192 and norm_ws.numel() >= 2
+    _call("es3_grad_norm", "grad_norm", _nb(flat_grad), 2 * flat_grad.numel(), flat_grad.data_ptr(), flat_grad.numel(),
+          part_ws.data_ptr(), norm_ws.data_ptr(), _stream())
+
+
+def adamw_flat(p, g, m, v, n_decay, lr, betas, eps, weight_decay, max_norm, inv_world, norm_ws, state, dynamic_scale=False,
+               growth=2.0, backoff=0.5, growth_interval=2000):
+    """Fused AdamW over flat arenas (see es3_adamw_flat in include/es3.h)."""
+    for t in (p, g, m, v):
+        _chk(t, torch.float32, "arena")
+        assert t.is_contiguous() and t.numel() == p.numel()
+    _ensure_init(p)
+    _call("es3_adamw_flat", "adamw_flat", 7 * _nb(p), 12 * p.numel(), p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
+          p.numel(), int(n_decay), float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), float(max_norm),
+          float(inv_world), norm_ws.data_ptr(), state.data_ptr(), int(dynamic_scale), float(growth), float(backoff),
+          int(growth_interval), _stream())
 
 
 def conv3x3_s2_narrow(x, w9, scale, bias, act=None):

@@ -130,15 +130,20 @@ class MaskDecoder(nn.Module, NativePlanMixin):
                 repeat_image, high_res_features: Optional[List[torch.Tensor]] = None):
         """Reference signature (mask_decoder.py:107-163); NCHW fp32 CUDA tensors in, NCHW fp32 out."""
         self._require_eval("MaskDecoder.forward")
-        if repeat_image:
-            raise NotImplementedError("repeat_image=True (several prompts per image) is not built")
         assert image_pe.size(0) == 1, "image_pe should have size 1 in batch dim (from `get_dense_pe()`)"
-        B, C, h, w = image_embeddings.shape
+        B = sparse_prompt_embeddings.shape[0]
+        _, C, h, w = image_embeddings.shape
+        if repeat_image:      # one image, B prompts (mask_decoder.py:185-188): the broadcast add below repeats the image
+            assert image_embeddings.shape[0] == 1, "repeat_image expects a single image embedding"
+        else:
+            assert image_embeddings.shape[0] == B
         src = image_embeddings.float() + dense_prompt_embeddings.float()   # torch broadcast add: plumbing at the API edge
-        keys_f32, keys_b16 = ops.nchw_to_tokens(src)
+        if src.shape[0] != B:
+            src = src.expand(B, -1, -1, -1)
+        keys_f32, keys_b16 = ops.nchw_to_tokens(src.contiguous())
         pe_tok, _ = ops.nchw_to_tokens(image_pe.float(), out_bf16=False)
         f0, f1 = high_res_features
-        feat_s0 = f0.float().permute(0, 2, 3, 1).contiguous()
-        feat_s1 = f1.float().permute(0, 2, 3, 1).contiguous()
+        feat_s0 = f0.float().expand(B, -1, -1, -1).permute(0, 2, 3, 1).contiguous()
+        feat_s1 = f1.float().expand(B, -1, -1, -1).permute(0, 2, 3, 1).contiguous()
         return self.predict_tokens(keys_f32, keys_b16, pe_tok, sparse_prompt_embeddings, B, h, w, feat_s0, feat_s1,
                                    obj_gate=False, multimask_output=multimask_output)

@@ -1,6 +1,6 @@
 """PromptEncoder, B200-native.  Module tree / keys of sam3/sam3/sam/prompt_encoder.py (PromptEncoder :12-197,
-PositionEmbeddingRandom :200-243).  Point prompts and the no-mask dense embedding run natively; box and mask
-prompts are not on the hot path (config 3 = one point per image) and raise."""
+PositionEmbeddingRandom :200-243).  Points, box corners (labels 2 / 3) and the padding point run on es3_point_embed; a mask prompt
+runs on the fused es3_mask_downscale_tokens kernel; without a mask the dense embedding is the broadcast no_mask_embed."""
 from __future__ import annotations
 
 import torch
@@ -48,18 +48,54 @@ class PromptEncoder(nn.Module):
     def get_dense_pe(self):
         return self.pe_layer(self.image_embedding_size).unsqueeze(0)
 
+    def _tables(self):
+        table = torch.cat([e.weight for e in self.point_embeddings], dim=0).detach().float().contiguous()
+        return (self.pe_layer.positional_encoding_gaussian_matrix.float(),
+                self.not_a_point_embed.weight.detach().float().reshape(-1), table)
+
+    def mask_weights(self):
+        """mask_downscaling parameters in the order es3_mask_downscale_tokens takes them."""
+        c0, n0, _, c1, n1, _, c2 = self.mask_downscaling
+        f = lambda t: t.detach().float().contiguous()
+        return (f(c0.weight), f(c0.bias), f(n0.weight), f(n0.bias), f(c1.weight), f(c1.bias), f(n1.weight), f(n1.bias),
+                f(c2.weight.reshape(c2.out_channels, -1)), f(c2.bias)), n0.eps
+
+    @torch.no_grad()
+    def embed_sparse(self, points, boxes):
+        """Sparse prompt tokens (prompt_encoder.py:71-131, 170-181): points (+ padding point when no box) then box corners."""
+        gauss, nap, table = self._tables()
+        W_, H_ = self.input_image_size[1], self.input_image_size[0]
+        parts = []
+        if points is not None:
+            coords, labels = points
+            parts.append(ops.point_embed(coords.float(), labels, gauss, nap, table, W_, H_, pad=(boxes is None)))
+        if boxes is not None:
+            corners = boxes.float().reshape(-1, 2, 2)
+            lab = torch.tensor([[2, 3]], dtype=torch.int32, device=corners.device).expand(corners.shape[0], 2)
+            parts.append(ops.point_embed(corners, lab, gauss, nap, table, W_, H_, pad=False))
+        if not parts:
+            return None
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+
     @torch.no_grad()
     def forward(self, points, boxes, masks):
-        if boxes is not None or masks is not None:
-            raise NotImplementedError("native PromptEncoder: box / mask prompts are not built (point prompts only)")
-        if points is None:
-            raise NotImplementedError("native PromptEncoder: a point prompt is required")
-        coords, labels = points
-        table = torch.cat([e.weight for e in self.point_embeddings], dim=0).detach().float().contiguous()
-        sparse = ops.point_embed(coords.float(), labels, self.pe_layer.positional_encoding_gaussian_matrix.float(),
-                                 self.not_a_point_embed.weight.detach().float().reshape(-1), table,
-                                 self.input_image_size[1], self.input_image_size[0])
-        bs = coords.shape[0]
-        dense = self.no_mask_embed.weight.detach().reshape(1, -1, 1, 1).expand(
-            bs, -1, self.image_embedding_size[0], self.image_embedding_size[1])
+        """Reference signature (prompt_encoder.py:152-197) -> (sparse [B,N,C] fp32, dense [B,C,h,w] fp32)."""
+        if points is not None:
+            bs = points[0].shape[0]
+        elif boxes is not None:
+            bs = boxes.shape[0]
+        elif masks is not None:
+            bs = masks.shape[0]
+        else:
+            bs = 1
+        sparse = self.embed_sparse(points, boxes)
+        if sparse is None:
+            sparse = torch.empty((bs, 0, self.embed_dim), device=self.no_mask_embed.weight.device, dtype=torch.float32)
+        h, w = self.image_embedding_size
+        if masks is not None:
+            wts, eps = self.mask_weights()
+            _, tok = ops.mask_downscale_tokens(masks.float(), wts, None, eps, out_bf16=False)
+            dense = tok.view(masks.shape[0], h, w, -1).permute(0, 3, 1, 2)
+        else:
+            dense = self.no_mask_embed.weight.detach().reshape(1, -1, 1, 1).expand(bs, -1, h, w)
         return sparse, dense

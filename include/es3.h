@@ -166,9 +166,22 @@ int es3_litemla_attn_tc(const void* ms, long long ld, float* kv_ws, void* att, l
 /* ------------------------------------------------------------------------------------------ SAM heads */
 /* PositionEmbeddingRandom over an h x w grid -> [h*w, 2F] fp32 (PromptEncoder.get_dense_pe, prompt_encoder.py:61-69). */
 int es3_dense_pe(const float* gauss, int F, int h, int w, float* out, void* stream);
-/* Point prompts (+ trailing padding point) -> sparse embeddings [B, P+1, 2F] fp32 (prompt_encoder.py:71-117). */
+/* Point prompts with labels -1 (not a point) / 0,1 (point) / 2,3 (box corners) -> sparse embeddings [B, P+pad, 2F] fp32;
+ * pad != 0 appends the padding point used when no box is given (prompt_encoder.py:71-131). */
 int es3_point_embed(const float* coords, const int* labels, const float* gauss, const float* not_a_point,
-                    const float* point_emb, int F, int B, int P, float img_w, float img_h, float* out, void* stream);
+                    const float* point_emb, int F, int B, int P, int pad, float img_w, float img_h, float* out, void* stream);
+/* Mask prompt: PromptEncoder.mask_downscaling (prompt_encoder.py:45-63) on mask [B,1,4h,4w] fp32, fused with the decoder's
+ * `image_embeddings + dense` (mask_decoder.py:189) and written token-major: keys[row] = base[row % base_rows] + dense[row],
+ * rows = B*h*w (base NULL -> the dense embedding alone).  Weights are the module's tensors in their native layouts. */
+int es3_mask_downscale_tokens(const float* mask, const float* w0, const float* b0, const float* g1, const float* be1,
+                              const float* w1, const float* b1, const float* g2, const float* be2, const float* w2,
+                              const float* b2, const float* base, long long base_rows, float* out_f32, void* out_bf16, int B,
+                              int h, int w, int C, float eps, void* stream);
+/* Hole / sprinkle filling of low-res mask logits (SAM2Transforms.postprocess_masks, sam1_utils.py:77-105): 8-connected
+ * components of (score <= thr) with area <= max_hole_area become thr + 10, components of (score > thr) of the input with
+ * area <= max_sprinkle_area become thr - 10.  in/out [N,H,W] fp32, not aliased; labels_ws, area_ws: N*H*W ints each. */
+int es3_fill_small_components(const float* in, float* out, int* labels_ws, int* area_ws, int N, int H, int W, float thr,
+                              float max_hole_area, float max_sprinkle_area, void* stream);
 /* y[m] = x[m] + add[m % R] over C channels; bf16 and/or fp32 output (queries + pe, keys + key_pe). */
 int es3_add_rows(const float* x, const float* add, long long M, int C, int R, void* y_bf16, float* y_f32, void* stream);
 /* [B,C,HW] fp32 (+ per-channel vector, e.g. no_mask_embed) -> token-major [B,HW,C] fp32 and/or bf16. */
@@ -215,6 +228,28 @@ int es3_layernorm_bf16(const void* x, const float* gamma, const float* beta, flo
  * out3 = (loss, mse, cosine); per_sample [B][3] optional. */
 int es3_kd_loss_fwd(const float* preds, const float* teacher, const int* sizes_hw, int B, int C, int E, int img_size,
                     float cosine_weight, float* ws, float* out3, float* per_sample, void* stream);
+/* d loss / d preds of es3_kd_loss_fwd (masked MSE + cosine_weight * masked cosine, batch mean), times grad_scale and --
+ * when scale_dev != NULL -- the device-resident loss scale scale_dev[0] (GradScaler.scale(loss).backward()).
+ * per_sample: the [B][3] array es3_kd_loss_fwd wrote (its mask counts are the denominators).  dpreds [B,C,E,E] fp32. */
+int es3_kd_loss_bwd(const float* preds, const float* teacher, const int* sizes_hw, const float* per_sample,
+                    const float* scale_dev, float grad_scale, int B, int C, int E, int img_size, float cosine_weight,
+                    float* dpreds, void* stream);
+
+/* ------------------------------------------------------------------------------------------ optimiser (A20) */
+/* Sum of squares + non-finite flag over a flat fp32 gradient arena (deterministic two-stage): norm_ws[0] = sum g^2 (raw,
+ * still loss-scaled), norm_ws[1] = 1 if any inf / nan.  part_ws: es3_grad_norm_ws_floats(n) floats.
+ * Replaces GradScaler.unscale_'s inf check + clip_grad_norm_'s norm (stage1/utils.py:341-368). */
+long long es3_grad_norm_ws_floats(long long n);
+int es3_grad_norm(const float* g, long long n, float* part_ws, float* norm_ws, void* stream);
+/* One fused AdamW step over flat arenas p/g/m/v of n floats (torch.optim.AdamW update rule; stage1/optimizer.py:6-30 puts
+ * 1-D params and biases in a no-decay group: here the first n_decay elements are the decay group).  The gradient is
+ * multiplied by inv_world / state[0] (allreduce-sum -> mean, loss-scale unscale) and by the clip_grad_norm_ coefficient
+ * min(1, max_norm / (norm + 1e-6)) computed from norm_ws on the device; when norm_ws[1] != 0 the update is skipped.
+ * state (device, 4 floats): [0] loss scale, [1] growth tracker, [2] step count, [3] last total norm; advanced after the
+ * update as GradScaler.update does (dynamic_scale: growth x after `growth_interval` clean steps, backoff x on inf). */
+int es3_adamw_flat(float* p, const float* g, float* m, float* v, long long n, long long n_decay, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float max_norm, float inv_world, const float* norm_ws,
+                   float* state, int dynamic_scale, float growth, float backoff, int growth_interval, void* stream);
 
 #ifdef __cplusplus
 }

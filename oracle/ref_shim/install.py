@@ -201,6 +201,17 @@ def install(reference_root: str = REFERENCE_ROOT):
         pc.mask = _mod("pycocotools.mask")
     if not _try("decord"):
         _mod("decord")
+    if not _try("skimage"):
+        # scikit-image is absent here; the reference's CPU connected-components backend (perflib/connected_components.py:
+        # 18-29) calls skimage.measure.label(values, return_num=True): default connectivity = input.ndim, i.e.
+        # 8-connected components of the non-zero pixels in 2-D, numbered from 1.  Restated with scipy.ndimage.label.
+        def _label(values, return_num=False, connectivity=None):
+            import numpy as np
+            from scipy import ndimage
+            lab, n = ndimage.label(np.asarray(values) != 0, structure=np.ones((3,) * np.ndim(values), dtype=np.int32))
+            return (lab.astype(np.int64), n) if return_num else lab.astype(np.int64)
+        sk = _mod("skimage")
+        sk.measure = _mod("skimage.measure", label=_label)
     if not _try("termcolor"):
         _mod("termcolor", colored=lambda s, *a, **k: s)
 

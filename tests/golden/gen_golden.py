@@ -130,6 +130,59 @@ def gen_sam_heads(tag, E, S, B, seed_pe, seed_md, seed_x):
           "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def gen_sam_prompts(tag, E, S, seed_pe, seed_md, seed_x):
+    """Box + point + mask prompts, several prompts on ONE image (repeat_image=True), and SAM2Transforms.postprocess_masks
+    (hole / sprinkle filling through the reference's CPU connected-components backend + resize) -- the pieces of
+    SAM3InteractiveImagePredictor._predict (sam1_task_predictor.py:329-430) beyond the single-point path."""
+    from sam3.model.utils.sam1_utils import SAM2Transforms
+
+    pe, md = build_ref_sam_heads(E, S)
+    pe.load_state_dict(fill_state_dict(pe.state_dict(), seed_pe))
+    md.load_state_dict(fill_state_dict(md.state_dict(), seed_md))
+    g = torch.Generator().manual_seed(seed_x)
+    P = 3
+    feat = torch.randn(1, 256, E, E, generator=g)
+    f288 = torch.randn(1, 256, 4 * E, 4 * E, generator=g)
+    f144 = torch.randn(1, 256, 2 * E, 2 * E, generator=g)
+    coords = torch.rand(P, 2, 2, generator=g) * S
+    labels = torch.tensor([[1, 0], [1, 1], [0, 1]], dtype=torch.int32)
+    xy0 = torch.rand(P, 2, generator=g) * S * 0.5
+    boxes = torch.cat([xy0, xy0 + 8 + torch.rand(P, 2, generator=g) * S * 0.4], dim=1)
+    mask_in = torch.randn(P, 1, 4 * E, 4 * E, generator=g) * 4
+    hr = [md.conv_s0(f288), md.conv_s1(f144)]
+    dpe = pe.get_dense_pe()
+    out = {}
+    # (a) PromptEncoder.forward with a direct `boxes` argument (no padding point) and a mask
+    sp_a, de_a = pe(points=(coords, labels), boxes=boxes, masks=mask_in)
+    out["sparse_pts_boxes"], out["dense_mask0"] = sp_a.numpy(), de_a.numpy()[:1]     # first prompt's map + stats of all
+    out["dense_mask_stats"] = np.stack([stats(de_a[i]) for i in range(P)])
+    # (b) the predictor's merge: boxes in front as label-2/3 points, boxes=None -> padding point appended
+    cc = torch.cat([boxes.reshape(-1, 2, 2), coords], dim=1)
+    cl = torch.cat([torch.tensor([[2, 3]], dtype=torch.int32).repeat(P, 1), labels], dim=1)
+    sp_b, de_b = pe(points=(cc, cl), boxes=None, masks=mask_in)
+    out["sparse_merged"] = sp_b.numpy()
+    for mm in (True, False):
+        m, iou, tok, obj = md(image_embeddings=feat, image_pe=dpe, sparse_prompt_embeddings=sp_b, dense_prompt_embeddings=de_b,
+                              multimask_output=mm, repeat_image=True, high_res_features=hr)
+        sfx = "mm" if mm else "single"
+        out.update({f"masks_{sfx}": m.numpy(), f"iou_{sfx}": iou.numpy(), f"obj_{sfx}": obj.numpy()})
+    # (c) postprocess_masks: holes <= 12 px filled (+10), sprinkles <= 5 px removed (-10), bilinear to a non-square size
+    tr = SAM2Transforms(resolution=S, mask_threshold=0.0, max_hole_area=12.0, max_sprinkle_area=5.0)
+    low = torch.from_numpy(out["masks_mm"]).clone()
+    gm = torch.Generator().manual_seed(seed_x + 1)
+    low = low + torch.randn(low.shape, generator=gm) * low.abs().mean() * 1.5       # speckle: many small components
+    post = tr.postprocess_masks(low, (50, 70))
+    tr0 = SAM2Transforms(resolution=S, mask_threshold=0.0, max_hole_area=0.0, max_sprinkle_area=0.0)
+    plain = tr0.postprocess_masks(low, (50, 70))
+    assert not torch.equal(post, plain), "hole filling did not change anything: fixture would not pin it"
+    out["post_in"], out["post_out"] = low.numpy(), post.numpy()
+    out["post_changed_px"] = int(((post > 0) != (plain > 0)).sum())
+    path = os.path.join(HERE, f"{tag}.npz")
+    np.savez_compressed(path, E=E, S=S, P=P, seed_pe=seed_pe, seed_md=seed_md, seed_x=seed_x, keys_pe=keyshapes(pe.state_dict()),
+                        keys_md=keyshapes(md.state_dict()), **out)
+    print(tag, "masks", out["masks_mm"].shape, "changed px", out["post_changed_px"], "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 def gen_neck(tag, dim, d_model, hw, B, seed_w, seed_x):
     from sam3.model.necks import Sam3DualViTDetNeck
 
@@ -196,6 +249,8 @@ def main(which):
         gen_student("repvit_m1_1", "rvm_160", img=160, embed=12, seed_w=51, seed_x=52, batch=1)
     if which in ("neck", "all"):
         gen_neck("neck_small", dim=128, d_model=64, hw=6, B=2, seed_w=31, seed_x=32)
+    if which in ("prompts", "all"):
+        gen_sam_prompts("sam_prompts_12", E=12, S=168, seed_pe=5, seed_md=6, seed_x=41)
     if which in ("heads", "all"):
         gen_sam_heads("sam_heads_16", E=16, S=224, B=2, seed_pe=5, seed_md=6, seed_x=1)
     if which in ("vit", "all"):

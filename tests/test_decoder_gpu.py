@@ -151,3 +151,83 @@ def test_attn_few_keys_and_convt(cuda):
                      out_dtype=torch.float32, act_after_res=True)
     ref = F.gelu(F.conv_transpose2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), b, stride=2) + r.permute(0, 3, 1, 2))
     assert max_err_over_scale(y.cpu(), ref.permute(0, 2, 3, 1).cpu()) < 2e-3
+
+
+# ---- box / mask prompts, several prompts per image, hole filling (sam1_task_predictor.py:329-430) --------------------
+def _prompt_inputs(g):
+    E, S, P = int(g["E"]), int(g["S"]), int(g["P"])
+    gen = torch.Generator().manual_seed(int(g["seed_x"]))
+    feat = torch.randn(1, 256, E, E, generator=gen)
+    f288 = torch.randn(1, 256, 4 * E, 4 * E, generator=gen)
+    f144 = torch.randn(1, 256, 2 * E, 2 * E, generator=gen)
+    coords = torch.rand(P, 2, 2, generator=gen) * S
+    labels = torch.tensor([[1, 0], [1, 1], [0, 1]], dtype=torch.int32)
+    xy0 = torch.rand(P, 2, generator=gen) * S * 0.5
+    boxes = torch.cat([xy0, xy0 + 8 + torch.rand(P, 2, generator=gen) * S * 0.4], dim=1)
+    mask_in = torch.randn(P, 1, 4 * E, 4 * E, generator=gen) * 4
+    return E, S, P, feat, f288, f144, coords, labels, boxes, mask_in
+
+
+def test_box_and_mask_prompts_match_reference_fixture(cuda):
+    g = load_golden("sam_prompts_12")
+    E, S, P, feat, f288, f144, coords, labels, boxes, mask_in = _prompt_inputs(g)
+    pe, md = _build(E, S, sd_from_keys(g["keys_pe"], int(g["seed_pe"])), sd_from_keys(g["keys_md"], int(g["seed_md"])), cuda)
+    c = lambda t: t.to(cuda)
+    sp, de = pe(points=(c(coords), c(labels)), boxes=c(boxes), masks=c(mask_in))
+    assert sp.shape == (P, 4, 256) and de.shape == (P, 256, E, E)
+    assert (sp.cpu() - torch.from_numpy(g["sparse_pts_boxes"])).abs().max().item() <= 2e-5
+    ref0 = torch.from_numpy(g["dense_mask0"])
+    assert (de[:1].cpu() - ref0).abs().max().item() <= 1e-4 * ref0.abs().max().item()
+    for i in range(P):
+        d = de[i].double()
+        got = torch.tensor([d.mean().item(), d.abs().mean().item(), d.std().item()], dtype=torch.float64)
+        assert torch.allclose(got, torch.from_numpy(g["dense_mask_stats"][i]).double(), rtol=1e-3, atol=1e-5)
+    # predictor-style merge (boxes in front as label-2/3 points, padding point appended) + repeat_image decoding
+    cc = torch.cat([boxes.reshape(-1, 2, 2), coords], dim=1)
+    cl = torch.cat([torch.tensor([[2, 3]], dtype=torch.int32).repeat(P, 1), labels], dim=1)
+    sp2, de2 = pe(points=(c(cc), c(cl)), boxes=None, masks=c(mask_in))
+    assert (sp2.cpu() - torch.from_numpy(g["sparse_merged"])).abs().max().item() <= 2e-5
+    hr = [F.conv2d(c(f288), md.conv_s0.weight, md.conv_s0.bias), F.conv2d(c(f144), md.conv_s1.weight, md.conv_s1.bias)]
+    for mm, sfx in ((True, "mm"), (False, "single")):
+        masks, iou, tok, obj = md(image_embeddings=c(feat), image_pe=pe.get_dense_pe(), sparse_prompt_embeddings=sp2,
+                                  dense_prompt_embeddings=de2, multimask_output=mm, repeat_image=True, high_res_features=hr)
+        _mask_checks(masks.cpu(), torch.from_numpy(g[f"masks_{sfx}"]), f"repeat_image masks ({sfx})")
+        assert (iou.cpu() - torch.from_numpy(g[f"iou_{sfx}"])).abs().max().item() <= 2e-2
+        assert (obj.cpu() - torch.from_numpy(g[f"obj_{sfx}"])).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("case", ["fixture", "speckle288", "empty", "full", "checker"])
+def test_fill_small_components_is_exact(cuda, case):
+    """Integer / index work: the filled masks must equal the oracle's bit for bit (same float inputs, same 8-connectivity)."""
+    from efficientsam3_b200 import ops
+    from oracle import sam_heads as O
+    if case == "fixture":
+        g = load_golden("sam_prompts_12")
+        x = torch.from_numpy(g["post_in"])
+        hole, spr = 12.0, 5.0
+        ref_resized = torch.from_numpy(g["post_out"])
+    else:
+        gen = torch.Generator().manual_seed(3)
+        if case == "speckle288":
+            x = F.avg_pool2d(torch.randn(2, 3, 288, 288, generator=gen), 5, 1, 2) * 3 + torch.randn(2, 3, 288, 288, generator=gen) * 0.3
+        elif case == "empty":
+            x = -torch.rand(1, 2, 40, 56, generator=gen) - 0.1
+        elif case == "full":
+            x = torch.rand(1, 2, 40, 56, generator=gen) + 0.1
+        else:  # diagonal-only connections: one component under 8-connectivity, singletons under 4-connectivity
+            yy, xx = torch.meshgrid(torch.arange(33), torch.arange(47), indexing="ij")
+            x = (((yy + xx) % 2).float() * 2 - 1)[None, None].repeat(1, 2, 1, 1)
+            x[0, 1] = -x[0, 1]
+        hole, spr = 256.0, 9.0
+        ref_resized = None
+    got = ops.fill_small_components(x.to(cuda), 0.0, hole, spr).cpu()
+    ref = O.fill_holes(x, 0.0, hole, spr)
+    assert torch.equal(got, ref), f"{case}: {(got != ref).sum().item()} pixels differ"
+    if case == "speckle288":
+        assert (got != x).sum().item() > 1000          # the case really exercises the filling
+    if ref_resized is not None:
+        up, _ = ops.bilinear_nchw(got.to(cuda), 50, 70)
+        assert (up.cpu() - ref_resized).abs().max().item() <= 1e-5 * ref_resized.abs().max().item()
+    # only holes / only sprinkles
+    assert torch.equal(ops.fill_small_components(x.to(cuda), 0.0, hole, 0.0).cpu(), O.fill_holes(x, 0.0, hole, 0.0))
+    assert torch.equal(ops.fill_small_components(x.to(cuda), 0.0, 0.0, spr).cpu(), O.fill_holes(x, 0.0, 0.0, spr))

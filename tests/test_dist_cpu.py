@@ -44,3 +44,36 @@ def test_two_rank_gloo_max_time_and_distinct_shards():
     B, steps = 32, 20
     value = world * B * steps / (res[0][1] * steps / 1e3)           # whole-job images/s as bench.py computes it
     assert abs(value - world * B / 15e-3) < 1e-6
+
+
+def _grad_worker(rank, world, port, q):
+    """Data-parallel gradient exchange of the KD step: ONE all-reduce over the flat grad arena."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from efficientsam3_b200.stage1.optim import FlatAdamW
+    torch.manual_seed(0)                                            # identical replicas
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 5, 3), torch.nn.BatchNorm2d(5), torch.nn.Flatten(), torch.nn.Linear(5 * 36, 7))
+    opt = FlatAdamW(model, lr=1e-3)
+    g = torch.Generator().manual_seed(100 + rank)                   # different local gradients
+    for p in model.parameters():
+        p.grad.copy_(torch.randn(p.shape, generator=g))
+    local = opt.flat_grad.clone()
+    n = opt.all_reduce_grads()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    ok = torch.equal(opt.flat_grad, sum(gathered)) and n == world
+    views_ok = all(torch.equal(p.grad.reshape(-1), opt.flat_grad[o:o + p.numel()]) for p, o in zip(opt.params, opt.offsets))
+    q.put((rank, bool(ok), bool(views_ok), opt.flat_grad.sum().item()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_flat_gradient_allreduce():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(timeout=60) for p in ps]
+    assert all(r[1] and r[2] for r in res)
+    assert res[0][3] == res[1][3]                                   # both ranks hold the same summed arena

@@ -117,3 +117,38 @@ def test_tinyvit_oracle_matches_reference(name, variant):
     with torch.no_grad():
         out = O.image_student_encoder(sd, x, int(g["embed"]), variant)
     _assert_close(out.numpy(), g["out"], rtol=2e-5)
+
+
+def test_prompt_and_postprocess_oracle_matches_reference():
+    """Box / mask prompts, repeat_image decoding and hole filling (+ resize) vs outputs of the reference classes."""
+    import torch.nn.functional as F
+    from oracle import sam_heads as O
+    g = _load("sam_prompts_12")
+    E, S, P = int(g["E"]), int(g["S"]), int(g["P"])
+    sd_pe = _sd_from_keys(g["keys_pe"], int(g["seed_pe"]))
+    sd_md = _sd_from_keys(g["keys_md"], int(g["seed_md"]))
+    gen = torch.Generator().manual_seed(int(g["seed_x"]))
+    feat = torch.randn(1, 256, E, E, generator=gen)
+    f288 = torch.randn(1, 256, 4 * E, 4 * E, generator=gen)
+    f144 = torch.randn(1, 256, 2 * E, 2 * E, generator=gen)
+    coords = torch.rand(P, 2, 2, generator=gen) * S
+    labels = torch.tensor([[1, 0], [1, 1], [0, 1]], dtype=torch.int32)
+    xy0 = torch.rand(P, 2, generator=gen) * S * 0.5
+    boxes = torch.cat([xy0, xy0 + 8 + torch.rand(P, 2, generator=gen) * S * 0.4], dim=1)
+    mask_in = torch.randn(P, 1, 4 * E, 4 * E, generator=gen) * 4
+    with torch.no_grad():
+        sp, de = O.prompt_encoder(sd_pe, "", (coords, labels), boxes, mask_in, (S, S), (E, E))
+        _assert_close(sp.numpy(), g["sparse_pts_boxes"], rtol=2e-5)
+        _assert_close(de[:1].numpy(), g["dense_mask0"], rtol=2e-5)
+        for i in range(P):
+            got = np.array([de[i].double().mean().item(), de[i].double().abs().mean().item(), de[i].double().std().item()])
+            np.testing.assert_allclose(got, g["dense_mask_stats"][i], rtol=1e-4, atol=1e-6)
+        hr = O.high_res_from_fpn(sd_md, "", f288, f144)
+        for mm, sfx in ((True, "mm"), (False, "single")):
+            masks, iou, low = O.predict(sd_pe, sd_md, feat, hr, coords, labels, boxes, mask_in, S, (4 * E, 4 * E), multimask_output=mm,
+                                        return_logits=True, max_hole_area=0.0)
+            _assert_close(low.numpy(), np.clip(g[f"masks_{sfx}"], -32, 32), rtol=5e-5)
+            _assert_close(iou.numpy(), g[f"iou_{sfx}"], rtol=5e-5)
+        post = F.interpolate(O.fill_holes(torch.from_numpy(g["post_in"]), 0.0, 12.0, 5.0), (50, 70), mode="bilinear", align_corners=False)
+    assert int(g["post_changed_px"]) > 100
+    assert np.array_equal(post.numpy(), g["post_out"])       # same fp32 ops on the same labels: exact

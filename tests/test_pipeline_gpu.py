@@ -80,3 +80,80 @@ def test_point_prompt_pipeline_vs_oracles(cuda):
     assert agree >= 0.99
     bm = seg.predict_batch(coords.to(cuda), labels.to(cuda), multimask_output=True)["high_res"]
     assert bm.dtype == torch.bool and torch.equal(bm.cpu(), high > 0)
+
+
+def test_interactive_predictor_api_vs_oracle(cuda):
+    """SAM3InteractiveImagePredictor drop-in (set_image / set_image_batch / predict / predict_batch): uint8 HWC images of
+    arbitrary size, point / box / mask prompts, several prompts on one image, hole filling, resize to the original size.
+    The decoder path is checked against oracle.sam_heads.predict fed with the NATIVE image features, so this test isolates
+    prompt encoding + decoding + post-processing (the encoder has its own parity tests)."""
+    import numpy as np
+    from efficientsam3_b200.model.sam1_task import SAM3InteractiveImagePredictor, Sam3PointPromptSegmenter
+    from oracle import sam_heads as OH
+    from oracle.weights import fill_state_dict
+    seg = Sam3PointPromptSegmenter(vit_overrides=dict(depth=1, global_att_blocks=()))
+    sd = {k: v for k, v in fill_state_dict(seg.state_dict(), 43).items() if not v.is_complex()}
+    seg.load_state_dict(sd, strict=False)
+    seg = seg.to(cuda)
+    pred = SAM3InteractiveImagePredictor(seg, mask_threshold=0.0, max_hole_area=64.0, max_sprinkle_area=16.0)
+    with pytest.raises(RuntimeError):
+        pred.predict(point_coords=np.array([[5.0, 5.0]]), point_labels=np.array([1]))
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, size=(300, 420, 3), dtype=np.uint8), rng.integers(0, 256, size=(512, 384, 3), dtype=np.uint8)]
+    sd_md = {k[len("sam_mask_decoder."):]: v for k, v in sd.items() if k.startswith("sam_mask_decoder.")}
+    sd_pe = {k[len("sam_prompt_encoder."):]: v for k, v in sd.items() if k.startswith("sam_prompt_encoder.")}
+    S = 1008
+
+    def oracle_for(idx, coords, labels, box, mask_in, mm, hw):
+        f = seg._features
+        emb = pred.get_image_embedding()[idx:idx + 1].float().cpu()
+        hr = (f["feat_s0"][idx:idx + 1].permute(0, 3, 1, 2).float().cpu(), f["feat_s1"][idx:idx + 1].permute(0, 3, 1, 2).float().cpu())
+        sc = torch.tensor([S / hw[1], S / hw[0]])
+        pc = torch.as_tensor(coords, dtype=torch.float32) * sc if coords is not None else None
+        pl = torch.as_tensor(labels, dtype=torch.int32) if labels is not None else None
+        if pc is not None and pc.dim() == 2:
+            pc, pl = pc[None], pl[None]
+        bx = (torch.as_tensor(box, dtype=torch.float32).reshape(-1, 2, 2) * sc).reshape(-1, 4) if box is not None else None
+        mi = torch.as_tensor(mask_in, dtype=torch.float32) if mask_in is not None else None
+        if mi is not None and mi.dim() == 3:
+            mi = mi[None]
+        with torch.no_grad():
+            return OH.predict(sd_pe, sd_md, emb, hr, pc, pl, bx, mi, S, hw, multimask_output=mm, return_logits=True,
+                              mask_threshold=0.0, max_hole_area=64.0, max_sprinkle_area=16.0)
+
+    def compare(got, ref, what):
+        masks, iou, low = (torch.from_numpy(np.asarray(t)) for t in got)
+        rm, ri, rl = ref
+        rm, ri, rl = rm[0], ri[0], rl[0]
+        assert masks.shape == rm.shape and low.shape == rl.shape, (masks.shape, rm.shape)
+        e = rel_l2(low, rl)
+        print(f"{what}: low-res rel_l2={e:.3e} iou err={(iou - ri).abs().max().item():.3e}")
+        assert e <= 2e-2 and (iou - ri).abs().max().item() <= 3e-2
+        agree = ((masks > 0) == (rm > 0)).float().mean().item()
+        assert agree >= 0.99, (what, agree)
+
+    # --- single image: point, box + point, then the returned low-res logits fed back as a mask prompt
+    pred.set_image(imgs[0])
+    hw = (300, 420)
+    pc, pl = np.array([[210.0, 150.0], [30.0, 40.0]]), np.array([1, 0])
+    out = pred.predict(point_coords=pc, point_labels=pl, multimask_output=True, return_logits=True)
+    assert out[0].shape == (3, 300, 420) and out[1].shape == (3,) and out[2].shape == (3, 288, 288)
+    compare(out, oracle_for(0, pc, pl, None, None, True, hw), "points")
+    box = np.array([60.0, 50.0, 300.0, 220.0])
+    out_b = pred.predict(point_coords=pc[:1], point_labels=pl[:1], box=box, multimask_output=False, return_logits=True)
+    assert out_b[0].shape == (1, 300, 420)
+    compare(out_b, oracle_for(0, pc[:1], pl[:1], box, None, False, hw), "box + point")
+    out_m = pred.predict(point_coords=pc[:1], point_labels=pl[:1], mask_input=out_b[2], multimask_output=True, return_logits=True)
+    compare(out_m, oracle_for(0, pc[:1], pl[:1], None, out_b[2], True, hw), "point + mask")
+    bm = pred.predict(point_coords=pc, point_labels=pl, multimask_output=True)[0]
+    assert bm.dtype == np.bool_ and np.array_equal(bm, out[0] > 0)
+    assert np.abs(out[2]).max() <= 32.0
+    # --- batch of two images with per-image prompt lists; the second image gets two prompts (repeat_image path)
+    pred.set_image_batch(imgs)
+    pcs = [np.array([[100.0, 100.0]]), np.array([[[100.0, 200.0]], [[300.0, 50.0]]])]
+    pls = [np.array([1]), np.array([[1], [1]])]
+    masks, ious, lows = pred.predict_batch(pcs, pls, multimask_output=True, return_logits=True)
+    assert masks[0].shape == (3, 300, 420) and masks[1].shape == (2, 3, 512, 384) and ious[1].shape == (2, 3)
+    ref1 = oracle_for(1, pcs[1], pls[1], None, None, True, (512, 384))
+    for j in range(2):
+        compare((masks[1][j], ious[1][j], lows[1][j]), tuple(t[j:j + 1] for t in ref1), f"batch image 1 prompt {j}")
