@@ -287,6 +287,18 @@ def other_encoders(dev, S, E):
     out["config3_vit_fpn_mask_decoder"] = {"images_per_s": round(8 / ms * 1e3, 2), "ms_per_step": round(ms, 2), "batch": 8,
                                            "img": 1008, "prompt": "1 point / image, multimask"}
     del seg, x
+    # optimiser side of the KD step (A20): grad norm + fused AdamW over an EV-M-sized flat arena; HBM streams
+    from efficientsam3_b200.stage1.optim import FlatAdamW
+    ev = build_student(S, E, dev, "efficientvit_b1")
+    for p in ev.parameters():
+        p.requires_grad_(True)
+    opt = FlatAdamW(ev, lr=1e-3, weight_decay=0.01)
+    opt.flat_grad.normal_(0, 1e-3)
+    ms = _time_steps(lambda: opt.step(max_norm=5.0), 3, 20)
+    gbs = opt.numel * 32 / ms / 1e6     # 4 B (norm) + 28 B (AdamW: read p,g,m,v, write p,m,v) per parameter
+    out["kd_optimizer_step_evm"] = {"ms_per_step": round(ms, 4), "params": int(opt.numel), "alg_GB_per_s": round(gbs, 1),
+                                    "frac_of_hbm_peak": round(gbs / _peaks()["hbm"], 3)}
+    del ev, opt
     torch.cuda.empty_cache()
     return out
 

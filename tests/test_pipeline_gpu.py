@@ -146,7 +146,8 @@ def test_interactive_predictor_api_vs_oracle(cuda):
     out_m = pred.predict(point_coords=pc[:1], point_labels=pl[:1], mask_input=out_b[2], multimask_output=True, return_logits=True)
     compare(out_m, oracle_for(0, pc[:1], pl[:1], None, out_b[2], True, hw), "point + mask")
     bm = pred.predict(point_coords=pc, point_labels=pl, multimask_output=True)[0]
-    assert bm.dtype == np.bool_ and np.array_equal(bm, out[0] > 0)
+    # like the reference (`masks.squeeze(0).float()...numpy()`, :290) the thresholded masks come back as float32 0/1
+    assert bm.dtype == np.float32 and set(np.unique(bm)) <= {0.0, 1.0} and np.array_equal(bm > 0.5, out[0] > 0)
     assert np.abs(out[2]).max() <= 32.0
     # --- batch of two images with per-image prompt lists; the second image gets two prompts (repeat_image path)
     pred.set_image_batch(imgs)
