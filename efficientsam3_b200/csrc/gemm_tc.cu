@@ -348,7 +348,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // rank-N bf16 tensor map, 128B swizzle, zero OOB fill. dims/strides innermost first; strides in BYTES for dims 1..
-static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
                       const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return 1;

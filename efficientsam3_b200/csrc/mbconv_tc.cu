@@ -12,11 +12,12 @@
 //     dw3x3    9 diagonal-B mma.sync per (16 px, 16 ch) from s_mid -> +bias, act -> bf16 s_dw, written in the
 //              128B-swizzled K-major layout a UMMA A operand needs (fence.proxy.async before handing it over)
 //     project  D_proj[128 x COUT] (TMEM) += s_dw x W3c^T                           tcgen05.mma, SS, accumulating over chunks
-//   final     tcgen05.ld D_proj -> BN3 + residual (x re-read from the swizzled s_in) -> global
+//   final     tcgen05.ld D_proj -> BN3 + residual (x re-read from global / L2) -> global
 //
 // Warps 0-7 do the elementwise / depthwise work, warp 8 lane 0 issues TMA and UMMAs; chunk weights sit in a 2-stage ring so
 // expand(c+1) and the weight loads overlap the depthwise of chunk c.  TMEM: 128 (D_exp) + COUT (D_proj) <= 256 columns, so
-// two CTAs share an SM.
+// two CTAs share an SM.  CTAs are persistent: parameters, TMEM and barriers are set up once, the weight ring runs across
+// tiles and the next tile's input TMA is issued as soon as the current tile's last expand retires.
 #include <cuda.h>
 
 #include "ptx.cuh"
@@ -57,11 +58,12 @@ struct MTSmem {
   static constexpr int OFF_WDW = OFF_MID + (MIDB + 15) / 16 * 16;   // bf16 [MID/64][9][64]
   static constexpr int OFF_PAR = OFF_WDW + 9 * MID * 2;              // fp32 s1[MID] b1[MID] b2[MID] s3[COUT] b3[COUT]
   static constexpr int OFF_BAR = OFF_PAR + (3 * MID + 2 * COUT) * 4;
-  static constexpr int TOTAL = OFF_BAR + 128 + 1024;                 // + slack for the manual 1024-byte alignment
+  static constexpr int TOTAL = OFF_BAR + 128;   // 10 mbarriers
   static_assert(OFF_W1 + 76 * 128 <= OFF_MID, "the aliased tail of the A operand must stay inside the operand buffers");
 };
 
 struct MTArgs {
+  const bf16* x;       // [B,H,W,CIN] (the TMA map reads it; the final epilogue re-reads the residual)
   bf16* y;             // [B,H,W,COUT]
   const float* s1;     // [MID]
   const float* b1;
@@ -69,7 +71,7 @@ struct MTArgs {
   const float* b2;     // [MID]
   const float* s3;     // [COUT]
   const float* b3;
-  int H, W, tiles_x;
+  int H, W, tiles_x, tiles_y, total_tiles;
 };
 
 template <int CIN, int MID, int COUT, int ACT>
@@ -78,9 +80,10 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
                  const __grid_constant__ CUtensorMap tm_w3, const MTArgs a) {
   using L = MTSmem<MID, COUT>;
   constexpr int NC = MID / MT_MC;
-  static_assert(CIN == COUT && CIN % 16 == 0 && CIN <= 64 && MID % 64 == 0 && (COUT == 32 || COUT == 64), "shape");
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  static_assert(CIN == COUT && CIN % 16 == 0 && CIN <= 64 && MID % 64 == 0 && NC >= 2 && (COUT == 32 || COUT == 64), "shape");
+  // (no integer round trip on the pointer: the compiler must keep seeing shared-space addresses, or every access below
+  //  turns into a generic LD/ST -- the first version of this kernel spent its time in long-scoreboard stalls on those)
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_in = smem;
   uint8_t* s_w1 = smem + L::OFF_W1;
   uint8_t* s_w3 = smem + L::OFF_W3;
@@ -91,15 +94,16 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   float *s_s1 = s_par, *s_b1 = s_par + MID, *s_b2 = s_par + 2 * MID, *s_s3 = s_par + 3 * MID, *s_b3 = s_s3 + COUT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t *bar_in = bars, *bar_w1 = bars + 1, *bar_w3 = bars + 3, *bar_exp = bars + 5, *bar_expfree = bars + 6,
-           *bar_dw = bars + 7, *bar_proj = bars + 8;
+           *bar_dw = bars + 7, *bar_proj = bars + 8, *bar_projfree = bars + 9;
   __shared__ uint32_t tmem_holder;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x, b = blockIdx.y;
-  const int oy0 = (tile / a.tiles_x) * MT_TH, ox0 = (tile % a.tiles_x) * MT_TW;
-  const int iy0 = oy0 - 1, ix0 = ox0 - 1;
+  // persistent: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the B * tiles_y * tiles_x tiles
+  const int my_tiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_total = my_tiles * NC;                      // chunks this CTA will run (the weight ring spans tiles)
 
   if (tid == 0) {
+    if (ptx::smem_u32(smem) & 1023u) { printf("es3: mbconv_tc dynamic smem base not 1024-byte aligned\n"); __trap(); }
     ptx::prefetch_tmap(&tm_in); ptx::prefetch_tmap(&tm_w1); ptx::prefetch_tmap(&tm_w3);
     ptx::mbar_init(bar_in, 1);
     ptx::mbar_init(bar_w1, 1); ptx::mbar_init(bar_w1 + 1, 1);
@@ -108,10 +112,11 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     ptx::mbar_init(bar_expfree, 8);
     ptx::mbar_init(bar_dw, 8);
     ptx::mbar_init(bar_proj, 1);
+    ptx::mbar_init(bar_projfree, 8);
     ptx::fence_mbar_init();
   }
   if (warp == 8) ptx::tmem_alloc(&tmem_holder, 256);
-  // per-channel parameters and the depthwise weights (bf16, [chunk][tap][64]) -- plain loads, shared by all warps
+  // per-channel parameters and the depthwise weights (bf16, [chunk][tap][64]) -- once per CTA
   for (int i = tid; i < MID; i += MT_THREADS) { s_s1[i] = a.s1[i]; s_b1[i] = a.b1[i]; s_b2[i] = a.b2[i]; }
   for (int i = tid; i < COUT; i += MT_THREADS) { s_s3[i] = a.s3[i]; s_b3[i] = a.b3[i]; }
   for (int i = tid; i < 9 * MID; i += MT_THREADS) {
@@ -123,59 +128,72 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_holder;
   const uint32_t t_exp = tmem, t_proj = tmem + 128;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
 
   if (warp == 8) {
     // ------------------------------------------------------------------------------------ control: TMA + UMMA issue
-    if (lane == 0) {
+    if (lane == 0 && my_tiles > 0) {
       constexpr uint32_t W1_BYTES = MT_MC * 128, W3_BYTES = COUT * 128;
-      ptx::mbar_arrive_expect_tx(bar_in, MT_PIN * 128);
-      ptx::tma_load_4d(&tm_in, bar_in, s_in, 0, ix0, iy0, b);
-      for (int s = 0; s < (NC < 2 ? NC : 2); ++s) {
-        ptx::mbar_arrive_expect_tx(bar_w1 + s, W1_BYTES);
-        ptx::tma_load_2d(&tm_w1, bar_w1 + s, s_w1 + s * W1_BYTES, 0, s * MT_MC);
-        ptx::mbar_arrive_expect_tx(bar_w3 + s, W3_BYTES);
-        ptx::tma_load_2d(&tm_w3, bar_w3 + s, s_w3 + s * W3_BYTES, s * MT_MC, 0);
-      }
       constexpr uint32_t idesc_exp = ptx::make_idesc_bf16_f32(128, MT_MC);
       constexpr uint32_t idesc_proj = ptx::make_idesc_bf16_f32(128, COUT);
       const uint32_t u_in = ptx::smem_u32(s_in), u_dw = ptx::smem_u32(s_dw);
-      ptx::mbar_wait(bar_in, 0);
+      auto load_in = [&](int t) {
+        const int bb = t / tiles_per_img, r = t % tiles_per_img;
+        ptx::mbar_arrive_expect_tx(bar_in, MT_PIN * 128);
+        ptx::tma_load_4d(&tm_in, bar_in, s_in, 0, (r % a.tiles_x) * MT_TW - 1, (r / a.tiles_x) * MT_TH - 1, bb);
+      };
+      auto load_w1 = [&](int gc) {
+        const int s = gc & 1;
+        ptx::mbar_arrive_expect_tx(bar_w1 + s, W1_BYTES);
+        ptx::tma_load_2d(&tm_w1, bar_w1 + s, s_w1 + s * W1_BYTES, 0, (gc % NC) * MT_MC);
+      };
+      auto load_w3 = [&](int gc) {
+        const int s = gc & 1;
+        ptx::mbar_arrive_expect_tx(bar_w3 + s, W3_BYTES);
+        ptx::tma_load_2d(&tm_w3, bar_w3 + s, s_w3 + s * W3_BYTES, (gc % NC) * MT_MC, 0);
+      };
+      load_in((int)blockIdx.x);
+      load_w1(0); load_w3(0); load_w1(1); load_w3(1);
+      int gc = 0;
 #pragma unroll 1
-      for (int c = 0; c < NC; ++c) {
-        const int st = c & 1;
-        const uint32_t par = (uint32_t)((c >> 1) & 1);
-        ptx::mbar_wait(bar_w1 + st, par);
-        if (c > 0) ptx::mbar_wait(bar_expfree, (uint32_t)((c - 1) & 1));   // epilogue(c-1) has drained D_exp
-        ptx::tc_fence_after();
-        const uint64_t db1 = ptx::make_desc_sw128(ptx::smem_u32(s_w1 + st * W1_BYTES));
+      for (int it = 0; it < my_tiles; ++it) {
+        ptx::mbar_wait(bar_in, (uint32_t)(it & 1));
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c, ++gc) {
+          const int st = gc & 1;
+          const uint32_t par = (uint32_t)((gc >> 1) & 1);
+          ptx::mbar_wait(bar_w1 + st, par);
+          if (gc > 0) ptx::mbar_wait(bar_expfree, (uint32_t)((gc - 1) & 1));   // the previous epilogue has drained D_exp
+          ptx::tc_fence_after();
+          const uint64_t db1 = ptx::make_desc_sw128(ptx::smem_u32(s_w1 + st * W1_BYTES));
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint64_t da = ptx::make_desc_sw128(u_in + half * 128 * 128);
+          for (int half = 0; half < 2; ++half) {
+            const uint64_t da = ptx::make_desc_sw128(u_in + half * 128 * 128);
 #pragma unroll
-          for (int k = 0; k < CIN / 16; ++k)
-            ptx::umma_f16(t_exp + half * MT_MC, da + (uint64_t)(k * 2), db1 + (uint64_t)(k * 2), idesc_exp, k != 0);
-        }
-        ptx::umma_commit(bar_exp);
-        // the W1 stage of chunk c+1 was last read by expand(c-1), which completed before bar_expfree(c-1): refill it now
-        if (c >= 1 && c + 1 < NC) {
-          const int s2 = (c + 1) & 1;
-          ptx::mbar_arrive_expect_tx(bar_w1 + s2, W1_BYTES);
-          ptx::tma_load_2d(&tm_w1, bar_w1 + s2, s_w1 + s2 * W1_BYTES, 0, (c + 1) * MT_MC);
-        }
-        ptx::mbar_wait(bar_w3 + st, par);
-        ptx::mbar_wait(bar_dw, (uint32_t)(c & 1));       // s_dw(c) written (and, transitively, project(c-1) retired)
-        ptx::tc_fence_after();
-        if (c >= 1 && c + 1 < NC) {                      // ... so the W3 stage of chunk c+1 is free as well
-          const int s2 = (c + 1) & 1;
-          ptx::mbar_arrive_expect_tx(bar_w3 + s2, W3_BYTES);
-          ptx::tma_load_2d(&tm_w3, bar_w3 + s2, s_w3 + s2 * W3_BYTES, (c + 1) * MT_MC, 0);
-        }
-        const uint64_t da = ptx::make_desc_sw128(u_dw);
-        const uint64_t db3 = ptx::make_desc_sw128(ptx::smem_u32(s_w3 + st * W3_BYTES));
+            for (int k = 0; k < CIN / 16; ++k)
+              ptx::umma_f16(t_exp + half * MT_MC, da + (uint64_t)(k * 2), db1 + (uint64_t)(k * 2), idesc_exp, k != 0);
+          }
+          ptx::umma_commit(bar_exp);
+          // the W1 stage of chunk gc+1 was last read by expand(gc-1), complete since bar_expfree(gc-1): refill it now
+          if (gc >= 1 && gc + 1 < n_total) load_w1(gc + 1);
+          if (c == NC - 1 && it + 1 < my_tiles) {
+            // last expand of this tile: once it retires s_in is free -> prefetch the next tile's input under the
+            // remaining depthwise / project / final epilogue (the residual is re-read from global, not from s_in)
+            ptx::mbar_wait(bar_exp, (uint32_t)(gc & 1));
+            load_in((int)blockIdx.x + (it + 1) * (int)gridDim.x);
+          }
+          ptx::mbar_wait(bar_w3 + st, par);
+          ptx::mbar_wait(bar_dw, (uint32_t)(gc & 1));     // s_dw(gc) written (and, transitively, project(gc-1) retired)
+          if (gc >= 1 && gc + 1 < n_total) load_w3(gc + 1);   // ... so the W3 stage of chunk gc+1 is free as well
+          if (c == 0 && it > 0) ptx::mbar_wait(bar_projfree, (uint32_t)((it - 1) & 1));   // D_proj drained by the last epilogue
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::make_desc_sw128(u_dw);
+          const uint64_t db3 = ptx::make_desc_sw128(ptx::smem_u32(s_w3 + st * W3_BYTES));
 #pragma unroll
-        for (int k = 0; k < MT_MC / 16; ++k)
-          ptx::umma_f16(t_proj, da + (uint64_t)(k * 2), db3 + (uint64_t)(k * 2), idesc_proj, (c | k) != 0);
-        ptx::umma_commit(bar_proj);
+          for (int k = 0; k < MT_MC / 16; ++k)
+            ptx::umma_f16(t_proj, da + (uint64_t)(k * 2), db3 + (uint64_t)(k * 2), idesc_proj, (c | k) != 0);
+          ptx::umma_commit(bar_proj);
+        }
       }
     }
   } else {
@@ -186,116 +204,129 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
     const uint32_t u_mid = ptx::smem_u32(s_mid);
     const uint32_t dshift = (g & 1) ? 16u : 0u;
     const bool dvalid = (g >> 1) == t4;
+    int gc = 0;
 
 #pragma unroll 1
-    for (int c = 0; c < NC; ++c) {
-      ptx::mbar_wait(bar_exp, (uint32_t)(c & 1));
-      ptx::tc_fence_after();
-      compute_bar_sync();                                // every warp is done reading s_mid for chunk c-1
-      // ---- expand epilogue: BN1 + act, zero outside the image, bf16 -> s_mid[row][hsel*32 .. +32)
+    for (int it = 0; it < my_tiles; ++it) {
+      const int t = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = t / tiles_per_img, tr = t % tiles_per_img;
+      const int oy0 = (tr / a.tiles_x) * MT_TH, ox0 = (tr % a.tiles_x) * MT_TW;
+      const int iy0 = oy0 - 1, ix0 = ox0 - 1;
+#pragma unroll 1
+      for (int c = 0; c < NC; ++c, ++gc) {
+        ptx::mbar_wait(bar_exp, (uint32_t)(gc & 1));
+        ptx::tc_fence_after();
+        compute_bar_sync();                              // every warp is done reading s_mid for the previous chunk
+        // ---- expand epilogue: BN1 + act, zero outside the image, bf16 -> s_mid[row][hsel*32 .. +32)
 #pragma unroll
-      for (int d = 0; d < 2; ++d) {
-        if (d == 1 && q >= 2) break;                     // rows 192..255 of the second M=128 block are padding (warp-uniform)
-        const int row = d * 128 + q * 32 + lane;
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_exp + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * MT_MC + hsel * 32), v);
-        ptx::tmem_ld_wait();
-        if (row < MT_PIN) {
-          const int iy = iy0 + row / MT_HW, ix = ix0 + row % MT_HW;
-          const bool in = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
-          const float* sc = s_s1 + c * MT_MC + hsel * 32;
-          const float* bi = s_b1 + c * MT_MC + hsel * 32;
-          uint4* dst = reinterpret_cast<uint4*>(s_mid + row * MT_RS_MID + hsel * 64);
+        for (int d = 0; d < 2; ++d) {
+          if (d == 1 && q >= 2) break;                   // rows 192..255 of the second M=128 block are padding (warp-uniform)
+          const int row = d * 128 + q * 32 + lane;
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_exp + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * MT_MC + hsel * 32), v);
+          ptx::tmem_ld_wait();
+          if (row < MT_PIN) {
+            const int iy = iy0 + row / MT_HW, ix = ix0 + row % MT_HW;
+            const bool in = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+            const float4* sc = reinterpret_cast<const float4*>(s_s1 + c * MT_MC + hsel * 32);   // warp-uniform: LDS.128 broadcasts
+            const float4* bi = reinterpret_cast<const float4*>(s_b1 + c * MT_MC + hsel * 32);
+            uint4* dst = reinterpret_cast<uint4*>(s_mid + row * MT_RS_MID + hsel * 64);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float f[8];
+            for (int j = 0; j < 4; ++j) {
+              const float4 s0 = sc[2 * j], s1v = sc[2 * j + 1], b0 = bi[2 * j], b1v = bi[2 * j + 1];
+              const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1v.x, s1v.y, s1v.z, s1v.w};
+              const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
+              float f[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float x = es3_act_t<ACT>(fmaf(__uint_as_float(v[j * 8 + e]), sc[j * 8 + e], bi[j * 8 + e]));
-              f[e] = in ? x : 0.f;
+              for (int e = 0; e < 8; ++e) {
+                const float x = es3_act_t<ACT>(fmaf(__uint_as_float(v[j * 8 + e]), sv[e], bv[e]));
+                f[e] = in ? x : 0.f;
+              }
+              dst[j] = pack8(f);
             }
-            dst[j] = pack8(f);
           }
         }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_expfree);
-      compute_bar_sync();                                // s_mid(c) complete
-      if (c > 0) ptx::mbar_wait(bar_proj, (uint32_t)((c - 1) & 1));   // project(c-1) has finished reading s_dw
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_expfree);
+        compute_bar_sync();                              // s_mid complete
+        if (c > 0) ptx::mbar_wait(bar_proj, (uint32_t)((gc - 1) & 1));   // project(gc-1) has finished reading s_dw
 
-      // ---- depthwise 3x3 on tensor cores (diagonal-B MMAs): warp -> channel group cg (16 ch), m-tiles hsel, hsel+2, ...
-      {
-        const int cg = q;
-        const bf16* wd = s_wdw + c * 9 * 64 + cg * 16 + g;
-        float dacc[4][2][4];
+        // ---- depthwise 3x3 on tensor cores (diagonal-B MMAs): warp -> channel group cg (16 ch), m-tiles hsel, hsel+2, ...
+        {
+          const int cg = q;
+          const bf16* wd = s_wdw + c * 9 * 64 + cg * 16 + g;
+          float dacc[4][2][4];
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+          for (int m = 0; m < 4; ++m)
 #pragma unroll
-          for (int i = 0; i < 2; ++i) { dacc[m][i][0] = dacc[m][i][1] = dacc[m][i][2] = dacc[m][i][3] = 0.f; }
+            for (int i = 0; i < 2; ++i) { dacc[m][i][0] = dacc[m][i][1] = dacc[m][i][2] = dacc[m][i][3] = 0.f; }
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+          for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const uint32_t w_lo = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * 64]);
-            const uint32_t w_hi = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * 64 + 8]);
-            const uint32_t b_lo = dvalid ? (w_lo << dshift) : 0u, b_hi = dvalid ? (w_hi << dshift) : 0u;
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint32_t w_lo = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * 64]);
+              const uint32_t w_hi = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * 64 + 8]);
+              const uint32_t b_lo = dvalid ? (w_lo << dshift) : 0u, b_hi = dvalid ? (w_hi << dshift) : 0u;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int mt = hsel + 2 * m;
-              uint32_t af[4];
-              ldsm_x4(u_mid + ((mt + ky) * MT_HW + a_row + kx) * MT_RS_MID + (cg * 16 + a_kh * 8) * 2, af[0], af[1], af[2], af[3]);
-              mma_16816(dacc[m][0], af, b_lo, 0u);
-              mma_16816(dacc[m][1], af, 0u, b_hi);
+              for (int m = 0; m < 4; ++m) {
+                const int mt = hsel + 2 * m;
+                uint32_t af[4];
+                ldsm_x4(u_mid + ((mt + ky) * MT_HW + a_row + kx) * MT_RS_MID + (cg * 16 + a_kh * 8) * 2, af[0], af[1], af[2], af[3]);
+                mma_16816(dacc[m][0], af, b_lo, 0u);
+                mma_16816(dacc[m][1], af, 0u, b_hi);
+              }
+            }
+          }
+          const float* b2 = s_b2 + c * MT_MC;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int mt = hsel + 2 * m;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int p = mt * MT_TW + g + half * 8;     // output pixel = A-operand row of the project UMMA
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) {
+                const int ch = cg * 16 + nt * 8 + t4 * 2;
+                const float2 bb = *reinterpret_cast<const float2*>(b2 + ch);
+                const float v0 = es3_act_t<ACT>(dacc[m][nt][half * 2 + 0] + bb.x);
+                const float v1 = es3_act_t<ACT>(dacc[m][nt][half * 2 + 1] + bb.y);
+                const int j = cg * 2 + nt;                  // 16-byte chunk inside the 128-byte row; XOR-swizzled by row % 8
+                *reinterpret_cast<uint32_t*>(s_dw + p * 128 + ((j ^ (p & 7)) << 4) + t4 * 4) = pack_bf16x2(v0, v1);
+              }
             }
           }
         }
-        const float* b2 = s_b2 + c * MT_MC;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int mt = hsel + 2 * m;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int p = mt * MT_TW + g + half * 8;       // output pixel = A-operand row of the project UMMA
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              const int ch = cg * 16 + nt * 8 + t4 * 2;
-              const float v0 = es3_act_t<ACT>(dacc[m][nt][half * 2 + 0] + b2[ch]);
-              const float v1 = es3_act_t<ACT>(dacc[m][nt][half * 2 + 1] + b2[ch + 1]);
-              const int j = cg * 2 + nt;                    // 16-byte chunk inside the 128-byte row; XOR-swizzled by row % 8
-              *reinterpret_cast<uint32_t*>(s_dw + p * 128 + ((j ^ (p & 7)) << 4) + t4 * 4) = pack_bf16x2(v0, v1);
-            }
-          }
-        }
+        ptx::fence_proxy_async();                         // generic-proxy writes -> visible to the UMMA (async proxy)
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_dw);
       }
-      ptx::fence_proxy_async();                           // generic-proxy writes -> visible to the UMMA (async proxy)
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_dw);
-    }
 
-    // ---- final epilogue: BN3 + residual -> global.  Thread = output pixel q*32+lane, channel half hsel (COUT 64) or all (COUT 32).
-    ptx::mbar_wait(bar_proj, (uint32_t)((NC - 1) & 1));
-    ptx::mbar_wait(bar_in, 0);                            // TMA-written s_in is read through the generic proxy below
-    ptx::tc_fence_after();
-    constexpr int CW = 32;                                 // columns per warp
-    const bool active = (COUT == 64) || (hsel == 0);
-    if (active) {
+      // ---- final epilogue: BN3 + residual -> global.  Thread = output pixel q*32+lane, channel half hsel (COUT 64) or all (COUT 32).
+      const bool active = (COUT == 64) || (hsel == 0);
       const int col0 = (COUT == 64) ? hsel * 32 : 0;
+      const int r = q * 32 + lane;
+      const int oy = oy0 + r / MT_TW, ox = ox0 + r % MT_TW;
+      const bool inb = active && oy < a.H && ox < a.W;
+      const long long pix = (((long long)b * a.H + oy) * a.W + ox) * COUT + col0;
+      uint4 xres[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)                         // residual x (L2-resident: TMA just read it), issued before the wait
+        xres[j] = inb ? __ldg(reinterpret_cast<const uint4*>(a.x + pix) + j) : make_uint4(0u, 0u, 0u, 0u);
+      ptx::mbar_wait(bar_proj, (uint32_t)((gc - 1) & 1));
+      ptx::tc_fence_after();
       uint32_t v[32];
       ptx::tmem_ld_32x32(t_proj + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
       ptx::tmem_ld_wait();
-      const int r = q * 32 + lane;
-      const int sy = r / MT_TW, sx = r % MT_TW;
-      const int oy = oy0 + sy, ox = ox0 + sx;
-      if (oy < a.H && ox < a.W) {
-        const int rr = (sy + 1) * MT_HW + sx + 1;          // the pixel's row in the swizzled input tile
-        bf16* dst = a.y + (((long long)b * a.H + oy) * a.W + ox) * COUT + col0;
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_projfree);
+      if (inb) {
+        bf16* dst = a.y + pix;
 #pragma unroll
-        for (int j = 0; j < CW / 8; ++j) {
-          float xr[8];
-          const int jj = col0 / 8 + j;
-          unpack8(*reinterpret_cast<const uint4*>(s_in + rr * 128 + ((jj ^ (rr & 7)) << 4)), xr);
-          float f[8];
+        for (int j = 0; j < 4; ++j) {
+          float xr[8], f[8];
+          unpack8(xres[j], xr);
 #pragma unroll
           for (int e = 0; e < 8; ++e)
             f[e] = fmaf(__uint_as_float(v[j * 8 + e]), s_s3[col0 + j * 8 + e], s_b3[col0 + j * 8 + e]) + xr[e];
@@ -341,8 +372,14 @@ static int launch_mbconv_tc(const void* x, void* y, const void* w1, const void* 
     ES3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  dim3 grid((unsigned)(a.tiles_x * ceil_div(a.H, MT_TH)), (unsigned)B);
-  kern<<<grid, MT_THREADS, L::TOTAL, st>>>(tm_in, tm_w1, tm_w3, a);
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    ES3_CHECK_CUDA(cudaGetDevice(&dev));
+    ES3_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int ctas = a.total_tiles < 2 * sm_count ? a.total_tiles : 2 * sm_count;   // persistent, two CTAs per SM
+  kern<<<ctas, MT_THREADS, L::TOTAL, st>>>(tm_in, tm_w1, tm_w3, a);
   ES3_LAUNCH_CHECK("mbconv_tc_kernel");
   return 0;
 }
@@ -360,8 +397,9 @@ extern "C" int es3_mbconv_tc_bf16(const void* x, void* y, const void* w1, const 
   ES3_REQUIRE(B > 0 && H > 0 && W > 0, "es3_mbconv_tc_bf16: bad shape");
   ES3_REQUIRE((((uintptr_t)x | (uintptr_t)w1 | (uintptr_t)w3 | (uintptr_t)y) & 15) == 0, "es3_mbconv_tc_bf16: 16-byte alignment");
   MTArgs a;
-  a.y = (bf16*)y; a.s1 = s1; a.b1 = b1; a.wdw = wdw; a.b2 = b2; a.s3 = s3; a.b3 = b3;
-  a.H = H; a.W = W; a.tiles_x = ceil_div(W, MT_TW);
+  a.x = (const bf16*)x; a.y = (bf16*)y; a.s1 = s1; a.b1 = b1; a.wdw = wdw; a.b2 = b2; a.s3 = s3; a.b3 = b3;
+  a.H = H; a.W = W; a.tiles_x = ceil_div(W, MT_TW); a.tiles_y = ceil_div(H, MT_TH);
+  a.total_tiles = B * a.tiles_x * a.tiles_y;
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 32) return launch_mbconv_tc<32, 128, 32>(x, y, w1, w3, a, B, st);
   return launch_mbconv_tc<64, 256, 64>(x, y, w1, w3, a, B, st);

@@ -290,8 +290,12 @@ def litemla_attn_generic(ms, heads2, dim, eps=1e-15):
     return att
 
 
-def mbconv_fused(x, w1, s1, b1, wdw, b2, w3, s3, b3, stride, residual, act):
-    """Fused MBConv (expand -> dw3x3 -> project [+x]); returns None when the shape is not instantiated."""
+MBCONV_TC = True   # stride-1 residual blocks on the tcgen05 kernel (es3_mbconv_tc_bf16); False -> mma.sync kernel only
+
+
+def mbconv_fused(x, w1, s1, b1, wdw, b2, w3, s3, b3, stride, residual, act, impl=None):
+    """Fused MBConv (expand -> dw3x3 -> project [+x]); returns None when the shape is not instantiated.
+    impl: None = tcgen05 kernel where it applies, else the mma.sync kernel; "tc" / "mma" force one (None if not instantiated)."""
     global launch_count
     _chk(x, torch.bfloat16, "x")
     _ensure_init(x)
@@ -307,14 +311,18 @@ def mbconv_fused(x, w1, s1, b1, wdw, b2, w3, s3, b3, stride, residual, act):
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = _lib.call_rc("es3_mbconv_fused_bf16", *args)
+    rc, tag = -1, "mbconv_tc"
+    if impl == "tc" or (impl is None and MBCONV_TC):
+        rc = _lib.call_rc("es3_mbconv_tc_bf16", *args)
+    if rc < 0 and impl != "tc":
+        rc, tag = _lib.call_rc("es3_mbconv_fused_bf16", *args), "mbconv_fused"
     if rc < 0:
         return None
     launch_count += 1
     if prof is not None:
         e1.record()
         flops = 2 * B * (H * W * Cin * Mid + Ho * Wo * Mid * (9 + Cout))
-        prof.records.append((f"mbconv_fused[{Cin}-{Mid}-{Cout},s{stride}]", e0, e1, _nb(x, y), flops))
+        prof.records.append((f"{tag}[{Cin}-{Mid}-{Cout},s{stride}]", e0, e1, _nb(x, y), flops))
     return y
 
 

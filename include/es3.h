@@ -102,6 +102,12 @@ int es3_stem_fused_c16(const float* img, const void* w0, const float* s0, const 
 int es3_mbconv_fused_bf16(const void* x, void* y, const void* w1, const float* s1, const float* b1, const float* wdw,
                           const float* b2, const void* w3, const float* s3, const float* b3, int B, int H, int W,
                           int Cin, int Mid, int Cout, int stride, int residual, int act, void* stream);
+/* Same contract on tcgen05 for the stride-1 residual blocks (Cin == Cout in {32, 64}, Mid = 4 Cin, hardswish): the two
+ * pointwise GEMMs are UMMAs (TMA-staged 128B-swizzled operands, TMEM accumulators, project accumulating over 64-channel
+ * chunks), the depthwise stays on mma.sync with diagonal B fragments.  Returns -1 for any other shape. */
+int es3_mbconv_tc_bf16(const void* x, void* y, const void* w1, const float* s1, const float* b1, const float* wdw,
+                       const float* b2, const void* w3, const float* s3, const float* b3, int B, int H, int W, int Cin, int Mid,
+                       int Cout, int stride, int residual, int act, void* stream);
 
 /* Bilinear (align_corners=False) NHWC bf16 -> NCHW fp32.  Replaces F.interpolate at stage1/model.py:204-210. */
 int es3_bilinear_nhwc_to_nchw(const void* in, float* out, int B, int Hi, int Wi, int C, int Ho, int Wo, void* stream);
