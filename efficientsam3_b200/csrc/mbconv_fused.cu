@@ -28,6 +28,13 @@ __device__ __forceinline__ void mma_bf16_16816(float* d, const uint32_t* a, uint
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// m16n8k8: with a diagonal 8x8 B fragment no structural zeros are multiplied (the k16 form wasted half of every MMA)
+__device__ __forceinline__ void mma_bf16_1688(float* d, uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
 __device__ __forceinline__ void cp16(void* smem, const void* gmem, bool valid) {
   const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
   const int sz = valid ? 16 : 0;
@@ -227,8 +234,8 @@ __global__ void __launch_bounds__(256, 2) mbconv_fused_kernel(const MBArgs a) {
             uint32_t af[4];
             ldsm_x4(u_mid + ((mt * STRIDE + ky) * C::HWD + a_row * STRIDE + kx) * C::RS_MID + (cg * 16 + a_kh * 8) * 2,
                     af[0], af[1], af[2], af[3]);
-            mma_bf16_16816(d[m][0], af, b_lo, 0u);
-            mma_bf16_16816(d[m][1], af, 0u, b_hi);
+            mma_bf16_1688(d[m][0], af[0], af[1], b_lo);
+            mma_bf16_1688(d[m][1], af[2], af[3], b_hi);
           }
         }
       }

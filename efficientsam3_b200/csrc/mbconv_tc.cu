@@ -37,6 +37,13 @@ __device__ __forceinline__ void mma_16816(float* d, const uint32_t* a, uint32_t 
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// m16n8k8: a diagonal 8x8 B has no structural zeros to multiply (the k16 form wasted half of every MMA)
+__device__ __forceinline__ void mma_1688(float* d, uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
 __device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 }  // namespace
 
@@ -154,46 +161,51 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
       };
       load_in((int)blockIdx.x);
       load_w1(0); load_w3(0); load_w1(1); load_w3(1);
-      int gc = 0;
-#pragma unroll 1
-      for (int it = 0; it < my_tiles; ++it) {
-        ptx::mbar_wait(bar_in, (uint32_t)(it & 1));
-#pragma unroll 1
-        for (int c = 0; c < NC; ++c, ++gc) {
-          const int st = gc & 1;
-          const uint32_t par = (uint32_t)((gc >> 1) & 1);
-          ptx::mbar_wait(bar_w1 + st, par);
-          if (gc > 0) ptx::mbar_wait(bar_expfree, (uint32_t)((gc - 1) & 1));   // the previous epilogue has drained D_exp
-          ptx::tc_fence_after();
-          const uint64_t db1 = ptx::make_desc_sw128(ptx::smem_u32(s_w1 + st * W1_BYTES));
+      // expand(g): needs the tile's input (first chunk), the W1 stage and a drained D_exp (the caller has waited for that)
+      auto issue_expand = [&](int g) {
+        const int it = g / NC, c = g % NC, st = g & 1;
+        if (c == 0) ptx::mbar_wait(bar_in, (uint32_t)(it & 1));
+        ptx::mbar_wait(bar_w1 + st, (uint32_t)((g >> 1) & 1));
+        ptx::tc_fence_after();
+        const uint64_t db1 = ptx::make_desc_sw128(ptx::smem_u32(s_w1 + st * W1_BYTES));
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint64_t da = ptx::make_desc_sw128(u_in + half * 128 * 128);
+        for (int half = 0; half < 2; ++half) {
+          const uint64_t da = ptx::make_desc_sw128(u_in + half * 128 * 128);
 #pragma unroll
-            for (int k = 0; k < CIN / 16; ++k)
-              ptx::umma_f16(t_exp + half * MT_MC, da + (uint64_t)(k * 2), db1 + (uint64_t)(k * 2), idesc_exp, k != 0);
-          }
-          ptx::umma_commit(bar_exp);
-          // the W1 stage of chunk gc+1 was last read by expand(gc-1), complete since bar_expfree(gc-1): refill it now
-          if (gc >= 1 && gc + 1 < n_total) load_w1(gc + 1);
-          if (c == NC - 1 && it + 1 < my_tiles) {
-            // last expand of this tile: once it retires s_in is free -> prefetch the next tile's input under the
-            // remaining depthwise / project / final epilogue (the residual is re-read from global, not from s_in)
-            ptx::mbar_wait(bar_exp, (uint32_t)(gc & 1));
-            load_in((int)blockIdx.x + (it + 1) * (int)gridDim.x);
-          }
-          ptx::mbar_wait(bar_w3 + st, par);
-          ptx::mbar_wait(bar_dw, (uint32_t)(gc & 1));     // s_dw(gc) written (and, transitively, project(gc-1) retired)
-          if (gc >= 1 && gc + 1 < n_total) load_w3(gc + 1);   // ... so the W3 stage of chunk gc+1 is free as well
-          if (c == 0 && it > 0) ptx::mbar_wait(bar_projfree, (uint32_t)((it - 1) & 1));   // D_proj drained by the last epilogue
-          ptx::tc_fence_after();
-          const uint64_t da = ptx::make_desc_sw128(u_dw);
-          const uint64_t db3 = ptx::make_desc_sw128(ptx::smem_u32(s_w3 + st * W3_BYTES));
-#pragma unroll
-          for (int k = 0; k < MT_MC / 16; ++k)
-            ptx::umma_f16(t_proj, da + (uint64_t)(k * 2), db3 + (uint64_t)(k * 2), idesc_proj, (c | k) != 0);
-          ptx::umma_commit(bar_proj);
+          for (int k = 0; k < CIN / 16; ++k)
+            ptx::umma_f16(t_exp + half * MT_MC, da + (uint64_t)(k * 2), db1 + (uint64_t)(k * 2), idesc_exp, k != 0);
         }
+        ptx::umma_commit(bar_exp);
+        // the W1 stage of chunk g+1 was last read by expand(g-1), which retired before epilogue(g-1) ran: refill it now
+        if (g >= 1 && g + 1 < n_total) load_w1(g + 1);
+        if (c == NC - 1 && it + 1 < my_tiles) {
+          // last expand of this tile: once it retires s_in is free -> prefetch the next tile's input under the remaining
+          // depthwise / project / final epilogue (the residual is re-read from global, not from s_in)
+          ptx::mbar_wait(bar_exp, (uint32_t)(g & 1));
+          load_in((int)blockIdx.x + (it + 1) * (int)gridDim.x);
+        }
+      };
+      issue_expand(0);
+#pragma unroll 1
+      for (int g = 0; g < n_total; ++g) {
+        const int it = g / NC, c = g % NC, st = g & 1;
+        if (g + 1 < n_total) {
+          // expand runs ONE chunk ahead: as soon as epilogue(g) has drained D_exp, expand(g+1) is issued, so it overlaps the
+          // depthwise of chunk g instead of sitting behind project(g) (first version: 15 % of samples waiting on bar_exp)
+          ptx::mbar_wait(bar_expfree, (uint32_t)(g & 1));
+          issue_expand(g + 1);
+        }
+        ptx::mbar_wait(bar_w3 + st, (uint32_t)((g >> 1) & 1));
+        ptx::mbar_wait(bar_dw, (uint32_t)(g & 1));        // s_dw(g) written (and, transitively, project(g-1) retired)
+        if (g >= 1 && g + 1 < n_total) load_w3(g + 1);    // ... so the W3 stage of chunk g+1 is free as well
+        if (c == 0 && it > 0) ptx::mbar_wait(bar_projfree, (uint32_t)((it - 1) & 1));   // D_proj drained by the last epilogue
+        ptx::tc_fence_after();
+        const uint64_t da = ptx::make_desc_sw128(u_dw);
+        const uint64_t db3 = ptx::make_desc_sw128(ptx::smem_u32(s_w3 + st * W3_BYTES));
+#pragma unroll
+        for (int k = 0; k < MT_MC / 16; ++k)
+          ptx::umma_f16(t_proj, da + (uint64_t)(k * 2), db3 + (uint64_t)(k * 2), idesc_proj, (c | k) != 0);
+        ptx::umma_commit(bar_proj);
       }
     }
   } else {
@@ -273,8 +285,8 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
                 const int mt = hsel + 2 * m;
                 uint32_t af[4];
                 ldsm_x4(u_mid + ((mt + ky) * MT_HW + a_row + kx) * MT_RS_MID + (cg * 16 + a_kh * 8) * 2, af[0], af[1], af[2], af[3]);
-                mma_16816(dacc[m][0], af, b_lo, 0u);
-                mma_16816(dacc[m][1], af, 0u, b_hi);
+                mma_1688(dacc[m][0], af[0], af[1], b_lo);   // channels cg*16 + 0..7
+                mma_1688(dacc[m][1], af[2], af[3], b_hi);   // channels cg*16 + 8..15
               }
             }
           }

@@ -26,6 +26,12 @@ __device__ __forceinline__ void mma16816(float* d, const uint32_t* a, uint32_t b
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma1688(float* d, uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
 }  // namespace
 
 constexpr int SF_TH = 8, SF_TW = 32, SF_C = 16;
@@ -175,8 +181,8 @@ __global__ void __launch_bounds__(256) stem_fused_kernel(const StemArgs a) {
         for (int kx = 0; kx < 3; ++kx) {
           uint32_t af[4];
           ldsm4(u_x + ((ry + ky) * SF_XW + rx0 + a_row + kx) * SF_XRS + a_kh * 16, af[0], af[1], af[2], af[3]);
-          mma16816(d[0], af, dlo[ky * 3 + kx], 0u);
-          mma16816(d[1], af, 0u, dhi[ky * 3 + kx]);
+          mma1688(d[0], af[0], af[1], dlo[ky * 3 + kx]);   // diagonal 8x8 B: no structural zeros multiplied
+          mma1688(d[1], af[2], af[3], dhi[ky * 3 + kx]);
         }
       // hswish(dw + bias) -> A fragment of the pointwise MMA (C-fragment layout == A-fragment layout)
       uint32_t pa[4];
