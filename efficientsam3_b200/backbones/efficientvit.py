@@ -201,7 +201,7 @@ class _LiteMLAPlan:
         self.agg_dw = dw_weight(dw, None)                                         # [25, C3] fp32
         if self.dim == 16:
             self.agg_pw = pw.weight.detach().float().reshape(self.c3, 16).contiguous()  # [C3, 16] fp32
-            self.wcomb = ops.litemla_wcomb(self.agg_dw, self.agg_pw)                    # [C3/16, 25, 16, 16] bf16
+            self.agg_wd, self.agg_wp = ops.litemla_dwpw_weights(self.agg_dw, self.agg_pw)  # [C3/16, 25, 16], [C3, 16] bf16
         else:
             d = self.dim
             wg = pw.weight.detach().float().reshape(self.c3 // d, d, d)               # [group][out][in]
@@ -220,7 +220,7 @@ class _LiteMLAPlan:
         ms2d = ms.view(-1, 2 * c3)
         ops.gemm(x.view(-1, C), self.qkv_w, out=ms2d[:, :c3])
         if self.dim == 16:
-            ops.litemla_aggreg_tc(ms, self.wcomb, c3)
+            ops.litemla_aggreg_dwpw(ms, self.agg_wd, self.agg_wp, c3)
             att = ops.litemla_attn(ms, self.heads2, self.eps)
         else:
             t = ops.dwconv(ms[..., :c3], self.agg_dw, None, 5, 1, None)

@@ -185,65 +185,84 @@ __global__ void dsconv_res_kernel(const bf16* __restrict__ x, const float* __res
 // One CTA = one image x 16 channels: the whole Hi x Wi x 16 source slab is staged in smem (fp32), then each
 // output plane [Ho][Wo] is written front to back -- 16 fully sequential Ho*Wo*4-byte streams per CTA (the first
 // version wrote one 256-byte row per plane per CTA and reached only 1.4-1.6 TB/s, profiles/r1_kernel_table_h.md).
-constexpr int BL_CB = 16;
-__global__ void __launch_bounds__(256) bilinear_nhwc_to_nchw_kernel(const bf16* __restrict__ in, float* __restrict__ out,
+constexpr int BL_CB = 16, BL_PS = 20;   // pixel stride in floats: 16 channels + 4 pad -> 16-byte aligned, conflict-free LDS.128
+__global__ void __launch_bounds__(256, 2) bilinear_nhwc_to_nchw_kernel(const bf16* __restrict__ in, float* __restrict__ out,
                                                                     int Hi, int Wi, int C, int Ho, int Wo, float sy,
                                                                     float sx) {
-  extern __shared__ float ssrc[];  // [Hi*Wi][17] then x tables [3][Wo], y tables [3][Ho]
+  extern __shared__ __align__(16) float ssrc[];  // [Hi*Wi][BL_PS]
   const int npix = Hi * Wi;
-  int* s_x0 = reinterpret_cast<int*>(ssrc + (long long)npix * (BL_CB + 1));
-  int* s_x1 = s_x0 + Wo;
-  float* s_lx = reinterpret_cast<float*>(s_x1 + Wo);
-  int* s_y0 = reinterpret_cast<int*>(s_lx + Wo);
-  int* s_y1 = s_y0 + Ho;
-  float* s_ly = reinterpret_cast<float*>(s_y1 + Ho);
   const int c0 = blockIdx.x * BL_CB, b = blockIdx.y;
-  for (int o = threadIdx.x; o < Wo; o += 256) {
-    float f = (o + 0.5f) * sx - 0.5f;
-    if (f < 0.f) f = 0.f;
-    const int i0 = min((int)f, Wi - 1);
-    s_x0[o] = i0; s_x1[o] = min(i0 + 1, Wi - 1); s_lx[o] = f - (float)i0;
-  }
-  for (int o = threadIdx.x; o < Ho; o += 256) {
-    float f = (o + 0.5f) * sy - 0.5f;
-    if (f < 0.f) f = 0.f;
-    const int i0 = min((int)f, Hi - 1);
-    s_y0[o] = i0; s_y1[o] = min(i0 + 1, Hi - 1); s_ly[o] = f - (float)i0;
-  }
   for (int i = threadIdx.x; i < npix * 2; i += 256) {
     const int px = i >> 1, v = i & 1;
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((long long)b * npix + px) * C + c0 + v * 8));
     float f[8];
     unpack8(u, f);
-    float* d = ssrc + (long long)px * (BL_CB + 1) + v * 8;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) d[e] = f[e];
+    float4* d = reinterpret_cast<float4*>(ssrc + (long long)px * BL_PS + v * 8);
+    d[0] = make_float4(f[0], f[1], f[2], f[3]);
+    d[1] = make_float4(f[4], f[5], f[6], f[7]);
   }
   __syncthreads();
+  // thread -> one output pixel column-quad q (fixed: its x taps / weights live in registers) and rows oy = r, r + RS, ...;
+  // every tap is read once as 4 x LDS.128 (16 channels) and feeds 16 planes: ~1 shared load and 4 FMAs per output value
+  // (the per-plane loop this replaces spent ~7 LDS per output; profiles/r1_kernel_table_i.md: 2.1 TB/s).
   const int nq = (Wo + 3) >> 2;
-  const int per_plane = Ho * nq;
-  for (int c = 0; c < BL_CB; ++c) {
-    float* plane = out + ((long long)b * C + c0 + c) * Ho * Wo;
-    const float* sc = ssrc + c;
-    for (int i = threadIdx.x; i < per_plane; i += 256) {
-      const int oy = i / nq, q = i - oy * nq;
-      const float* r0 = sc + (long long)s_y0[oy] * Wi * (BL_CB + 1);
-      const float* r1 = sc + (long long)s_y1[oy] * Wi * (BL_CB + 1);
-      const float ly = s_ly[oy], hy = 1.f - ly;
-      float v[4];
+  int QT = 1;
+  while (QT < nq && QT < 256) QT <<= 1;
+  const int RS = 256 / QT;
+  const int r = threadIdx.x / QT;
+  float* obase = out + ((long long)b * C + c0) * Ho * Wo;
+  const long long plane = (long long)Ho * Wo;
+  for (int q = threadIdx.x % QT; q < nq; q += QT) {
+    int x0[4], x1[4];
+    float lx[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int ox = min(q * 4 + e, Wo - 1);
-        const int x0 = s_x0[ox] * (BL_CB + 1), x1 = s_x1[ox] * (BL_CB + 1);
-        const float lx = s_lx[ox], hx = 1.f - lx;
-        v[e] = hy * (hx * r0[x0] + lx * r0[x1]) + ly * (hx * r1[x0] + lx * r1[x1]);
-      }
-      if ((Wo & 3) == 0) {
-        reinterpret_cast<float4*>(plane + (long long)oy * Wo)[q] = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
+    for (int e = 0; e < 4; ++e) {
+      const int ox = min(q * 4 + e, Wo - 1);
+      float f = (ox + 0.5f) * sx - 0.5f;
+      if (f < 0.f) f = 0.f;
+      const int i0 = min((int)f, Wi - 1);
+      x0[e] = i0 * BL_PS; x1[e] = min(i0 + 1, Wi - 1) * BL_PS; lx[e] = f - (float)i0;
+    }
+    for (int oy = r; oy < Ho; oy += RS) {
+      float fy = (oy + 0.5f) * sy - 0.5f;
+      if (fy < 0.f) fy = 0.f;
+      const int y0 = min((int)fy, Hi - 1), y1 = min(y0 + 1, Hi - 1);
+      const float ly = fy - (float)y0, hy = 1.f - ly;
+      const float* r0 = ssrc + (long long)y0 * Wi * BL_PS;
+      const float* r1 = ssrc + (long long)y1 * Wi * BL_PS;
+      float* orow = obase + (long long)oy * Wo + q * 4;
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (q * 4 + e < Wo) plane[(long long)oy * Wo + q * 4 + e] = v[e];
+      for (int jh = 0; jh < 2; ++jh) {             // two passes of 8 channels keep the accumulators at 32 registers
+        float v[8][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float hx = 1.f - lx[e];
+#pragma unroll
+          for (int j2 = 0; j2 < 2; ++j2) {
+            const int j = jh * 2 + j2;
+            const float4 a = *reinterpret_cast<const float4*>(r0 + x0[e] + 4 * j);
+            const float4 bb = *reinterpret_cast<const float4*>(r0 + x1[e] + 4 * j);
+            const float4 c = *reinterpret_cast<const float4*>(r1 + x0[e] + 4 * j);
+            const float4 d = *reinterpret_cast<const float4*>(r1 + x1[e] + 4 * j);
+            // same association as aten's upsample_bilinear2d: hy * (hx a + lx b) + ly * (hx c + lx d)
+            v[4 * j2 + 0][e] = hy * (hx * a.x + lx[e] * bb.x) + ly * (hx * c.x + lx[e] * d.x);
+            v[4 * j2 + 1][e] = hy * (hx * a.y + lx[e] * bb.y) + ly * (hx * c.y + lx[e] * d.y);
+            v[4 * j2 + 2][e] = hy * (hx * a.z + lx[e] * bb.z) + ly * (hx * c.z + lx[e] * d.z);
+            v[4 * j2 + 3][e] = hy * (hx * a.w + lx[e] * bb.w) + ly * (hx * c.w + lx[e] * d.w);
+          }
+        }
+        float* o8 = orow + (long long)(jh * 8) * plane;
+        if ((Wo & 3) == 0) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(o8 + c * plane) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (q * 4 + e < Wo) o8[c * plane + e] = v[c][e];
+        }
       }
     }
   }
@@ -354,7 +373,7 @@ extern "C" int es3_dsconv_res_bf16(const void* x, const float* wdw, const float*
 extern "C" int es3_bilinear_nhwc_to_nchw(const void* in, float* out, int B, int Hi, int Wi, int C, int Ho, int Wo,
                                          void* stream) {
   ES3_REQUIRE(C % BL_CB == 0, "es3_bilinear_nhwc_to_nchw: C=%d must be a multiple of %d", C, BL_CB);
-  const size_t smem = ((size_t)Hi * Wi * (BL_CB + 1) + 3 * (size_t)(Wo + Ho)) * sizeof(float);
+  const size_t smem = (size_t)Hi * Wi * BL_PS * sizeof(float);
   ES3_REQUIRE(smem <= 200 * 1024, "es3_bilinear_nhwc_to_nchw: %dx%d source too large for the smem slab", Hi, Wi);
   static bool configured = false;
   if (!configured) {

@@ -117,6 +117,96 @@ __global__ void __launch_bounds__(256) litemla_aggreg_tc_kernel(const bf16* ms_i
   }
 }
 
+// Second formulation of the aggregation: depthwise 5x5 as 25 x 2 DIAGONAL m16n8k8 MMAs (no structural zeros), its fp32 result
+// rounded to bf16 and re-used in registers as the A fragment of ONE 16x16x16 grouped-pointwise MMA pair.  27 half-cost MMAs
+// per 16 pixels instead of 50 full ones for the combined K = 400 contraction above; the depthwise output is rounded to bf16
+// exactly where the unfused reference path materialises it.
+// wdw: [C3/16][25][16] bf16 (group, tap, channel);  wpw: [C3][16] bf16 (output channel, input channel within its group).
+constexpr int AG2_SMEM = AG_TILE_BYTES + 25 * 16 * 2 + 16 * AG_PS;
+__device__ __forceinline__ void mma1688(float* d, uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
+__global__ void __launch_bounds__(256) litemla_aggreg_dwpw_kernel(const bf16* ms_in, bf16* ms_out, long long ld,
+                                                                  const bf16* __restrict__ wdw, const bf16* __restrict__ wpw,
+                                                                  int H, int W, int tiles_x) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t u_tile = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  const bf16* s_wd = reinterpret_cast<const bf16*>(smem + AG_TILE_BYTES);   // [25][16]
+  const uint32_t u_wp = u_tile + AG_TILE_BYTES + 25 * 16 * 2;               // [16 n][16 k], row stride AG_PS
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, grp = blockIdx.y, b = blockIdx.z;
+  const int oy0 = (tile / tiles_x) * AG_TH, ox0 = (tile % tiles_x) * AG_TW;
+
+  const bf16* xb = ms_in + (long long)b * H * W * ld + grp * 16;
+  for (int i = tid; i < AG_IH * AG_IW * 2; i += 256) {
+    const int v = i & 1, p = i >> 1;
+    const int iy = oy0 - 2 + p / AG_IW, ix = ox0 - 2 + p % AG_IW;
+    const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+    cpa16(u_tile + p * AG_PS + v * 16, ok ? xb + ((long long)iy * W + ix) * ld + v * 8 : xb, ok);
+  }
+  if (tid < 50) cpa16(u_tile + AG_TILE_BYTES + tid * 16, wdw + (long long)grp * 400 + tid * 8, true);
+  if (tid >= 64 && tid < 96) {
+    const int i = tid - 64, n = i >> 1, v = i & 1;
+    cpa16(u_wp + n * AG_PS + v * 16, wpw + ((long long)grp * 16 + n) * 16 + v * 8, true);
+  }
+  cpa_wait_all();
+  __syncthreads();
+
+  const int a_row = lane & 15, a_kh = lane >> 4;
+  const int b_n = (lane & 7) + ((lane >> 4) << 3), b_kh = (lane >> 3) & 1;
+  const int g = lane >> 2, t4 = lane & 3;
+  const uint32_t dshift = (g & 1) ? 16u : 0u;
+  const bool dvalid = (g >> 1) == t4;
+  float acc[4][2][4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < 2; ++n) { acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f; }
+
+#pragma unroll 1
+  for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 5; ++kx) {
+      const uint32_t w_lo = (uint32_t)__bfloat16_as_ushort(s_wd[(ky * 5 + kx) * 16 + g]);
+      const uint32_t w_hi = (uint32_t)__bfloat16_as_ushort(s_wd[(ky * 5 + kx) * 16 + 8 + g]);
+      const uint32_t b_lo = dvalid ? (w_lo << dshift) : 0u, b_hi = dvalid ? (w_hi << dshift) : 0u;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int y = warp * 2 + (m >> 1), x0 = (m & 1) * 16;
+        uint32_t af[4];
+        ldsm4(u_tile + ((y + ky) * AG_IW + x0 + a_row + kx) * AG_PS + a_kh * 16, af[0], af[1], af[2], af[3]);
+        mma1688(acc[m][0], af[0], af[1], b_lo);
+        mma1688(acc[m][1], af[2], af[3], b_hi);
+      }
+    }
+  }
+  uint32_t p0, p1, p2, p3;
+  ldsm4(u_wp + b_n * AG_PS + b_kh * 16, p0, p1, p2, p3);
+  bf16* ob = ms_out + (long long)b * H * W * ld + grp * 16;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    // depthwise result (C fragment of two n-tiles) -> bf16 A fragment of the 16x16x16 grouped pointwise product
+    const uint32_t pa[4] = {pack_bf16x2(acc[m][0][0], acc[m][0][1]), pack_bf16x2(acc[m][0][2], acc[m][0][3]),
+                            pack_bf16x2(acc[m][1][0], acc[m][1][1]), pack_bf16x2(acc[m][1][2], acc[m][1][3])};
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    mma16816(o[0], pa, p0, p1);
+    mma16816(o[1], pa, p2, p3);
+    const int oy = oy0 + warp * 2 + (m >> 1);
+    if (oy >= H) continue;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int ox = ox0 + (m & 1) * 16 + g + half * 8;
+      if (ox >= W) continue;
+      bf16* dst = ob + ((long long)oy * W + ox) * ld + t4 * 2;
+      *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(o[0][half * 2], o[0][half * 2 + 1]);
+      *reinterpret_cast<uint32_t*>(dst + 8) = pack_bf16x2(o[1][half * 2], o[1][half * 2 + 1]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ kv
 constexpr int KV_PX = 512, KV_RS = 80;  // 32 ch (k|v) = 64 B + 16 B pad
 
@@ -279,6 +369,23 @@ extern "C" int es3_litemla_aggreg_tc(void* ms, long long ld, const void* wcomb, 
   litemla_aggreg_tc_kernel<<<grid, 256, AG_SMEM, (cudaStream_t)stream>>>((const bf16*)ms, (bf16*)ms + C3, ld,
                                                                           (const bf16*)wcomb, H, W, tiles_x);
   ES3_LAUNCH_CHECK("litemla_aggreg_tc_kernel");
+  return 0;
+}
+
+// Same data contract; depthwise and grouped-pointwise weights separately: wdw [C3/16][25][16] bf16, wpw [C3][16] bf16.
+extern "C" int es3_litemla_aggreg_dwpw(void* ms, long long ld, const void* wdw, const void* wpw, int B, int H, int W, int C3,
+                                       void* stream) {
+  ES3_REQUIRE(C3 % 16 == 0 && ld % 8 == 0 && ld >= 2 * C3, "es3_litemla_aggreg_dwpw: bad C3=%d ld=%lld", C3, ld);
+  static bool configured = false;
+  if (!configured) {
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(litemla_aggreg_dwpw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AG2_SMEM));
+    configured = true;
+  }
+  const int tiles_x = ceil_div(W, AG_TW), tiles_y = ceil_div(H, AG_TH);
+  dim3 grid(tiles_x * tiles_y, C3 / 16, B);
+  litemla_aggreg_dwpw_kernel<<<grid, 256, AG2_SMEM, (cudaStream_t)stream>>>((const bf16*)ms, (bf16*)ms + C3, ld, (const bf16*)wdw,
+                                                                            (const bf16*)wpw, H, W, tiles_x);
+  ES3_LAUNCH_CHECK("litemla_aggreg_dwpw_kernel");
   return 0;
 }
 

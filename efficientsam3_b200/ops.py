@@ -263,6 +263,24 @@ def litemla_aggreg_tc(ms, wcomb, C3):
     return ms
 
 
+def litemla_dwpw_weights(wdw, wpw):
+    """wdw [25, C3] fp32 (tap-major), wpw [C3, 16] fp32 -> ([C3/16, 25, 16] bf16, [C3, 16] bf16) for es3_litemla_aggreg_dwpw."""
+    C3 = wpw.shape[0]
+    d = wdw.reshape(25, C3 // 16, 16).permute(1, 0, 2)
+    return d.to(torch.bfloat16).contiguous(), wpw.to(torch.bfloat16).contiguous()
+
+
+def litemla_aggreg_dwpw(ms, wd, wp, C3):
+    _chk(ms, torch.bfloat16, "ms"); _chk(wd, torch.bfloat16, "wd"); _chk(wp, torch.bfloat16, "wp")
+    _ensure_init(ms)
+    assert ms.is_contiguous() and wd.is_contiguous() and wp.is_contiguous()
+    assert wd.shape == (C3 // 16, 25, 16) and wp.shape == (C3, 16)
+    B, H, W, ld = ms.shape
+    _call("es3_litemla_aggreg_dwpw", "litemla_aggreg_dwpw", 2 * B * H * W * C3 * 2, 2 * B * H * W * C3 * (25 + 16),
+          ms.data_ptr(), ld, wd.data_ptr(), wp.data_ptr(), B, H, W, C3, _stream())
+    return ms
+
+
 def litemla_attn(ms, heads2, eps=1e-15, tc=True):
     """ms: [B,H,W,48*heads2] bf16 -> att [B,H,W,16*heads2] bf16."""
     _chk(ms, torch.bfloat16, "ms")

@@ -193,7 +193,7 @@ def test_layout_roundtrip(cuda):
     assert torch.equal(z, x.to(torch.bfloat16).float())
 
 
-@pytest.mark.parametrize("simple", [False, True, "tc"])
+@pytest.mark.parametrize("simple", [False, True, "tc", "dwpw"])
 @pytest.mark.parametrize("H,W,heads,B", [(32, 32, 16, 2), (63, 63, 8, 1), (64, 64, 8, 2), (5, 7, 2, 3)])
 def test_litemla(cuda, H, W, heads, B, simple):
     """aggreg + ReLU linear attention vs the textbook formulation (efficientvit/nn/ops.py:584-621)."""
@@ -210,15 +210,17 @@ def test_litemla(cuda, H, W, heads, B, simple):
     wdw_t, wpw_t = wdw.reshape(C3, 25).t().contiguous(), wpw.reshape(C3, 16).contiguous()
     if simple == "tc":
         ops.litemla_aggreg_tc(ms, ops.litemla_wcomb(wdw_t, wpw_t), C3)
+    elif simple == "dwpw":
+        ops.litemla_aggreg_dwpw(ms, *ops.litemla_dwpw_weights(wdw_t, wpw_t), C3)
     else:
         ops.litemla_aggreg(ms, wdw_t, wpw_t, C3, force_simple=simple)
     x = qkv.float().permute(0, 3, 1, 2)
     dw = F.conv2d(x, wdw, padding=2, groups=C3)
-    if simple != "tc":      # the FMA kernels materialise the depthwise output in bf16; the tc kernel folds the weights
+    if simple != "tc":      # the FMA / dwpw kernels round the depthwise output to bf16; the tc kernel folds the weights
         dw = dw.to(torch.bfloat16).float()
     agg = F.conv2d(dw, wpw, groups=3 * heads)
     _close(ms[..., C3:], agg.permute(0, 2, 3, 1), 1e-2, "aggreg")
-    att = ops.litemla_attn(ms, 2 * heads, tc=(simple == "tc"))
+    att = ops.litemla_attn(ms, 2 * heads, tc=(simple in ("tc", "dwpw")))
     full = ms.float().permute(0, 3, 1, 2).reshape(B, -1, 3 * dim, H * W)
     q, k, v = F.relu(full[:, :, :dim]), F.relu(full[:, :, dim:2 * dim]), full[:, :, 2 * dim:]
     v = F.pad(v, (0, 0, 0, 1), value=1.0)
