@@ -173,6 +173,7 @@ class _MBConvPlan:
             w3=self.pt.w, s3=self.pt.scale if self.pt.scale is not None else _ones(cout, device),
             b3=self.pt.bias if self.pt.bias is not None else _zeros(cout, device))
         self.fusable = (self.dw.ks == 3 and self.inv.act == self.dw.act == "hswish" and self.pt.act is None)
+        self.dwproj = self.dw.ks == 3 and self.dw.stride == 1 and self.dw.act == "hswish" and self.pt.act is None
 
     def __call__(self, x):  # x: [B,H,W,C] bf16
         if self.fusable:
@@ -182,6 +183,12 @@ class _MBConvPlan:
             self.fusable = False  # shape not instantiated: remember and use the unfused native path
         B, H, W, C = x.shape
         mid = self.inv(x.view(-1, C)).view(B, H, W, -1)
+        if self.dwproj:      # depthwise + projection in one tcgen05 kernel (stage 3/4 blocks)
+            y = ops.dwproj(mid, self.f["wdw"], self.f["b2"], self.f["w3"], self.f["s3"], self.f["b3"],
+                           residual=x if self.residual else None)
+            if y is not None:
+                return y
+            self.dwproj = False
         mid = self.dw(mid)
         B2, H2, W2, Cm = mid.shape
         out = self.pt(mid.view(-1, Cm), residual=x.view(-1, C) if self.residual else None)

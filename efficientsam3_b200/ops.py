@@ -344,6 +344,34 @@ def mbconv_fused(x, w1, s1, b1, wdw, b2, w3, s3, b3, stride, residual, act, impl
     return y
 
 
+def dwproj(mid, wdw, b2, w3, s3, b3, residual=None, act="hswish"):
+    """act(dw3x3(mid) + b2) -> 1x1 projection -> s3 * . + b3 (+ residual) in one tcgen05 kernel; None if the shape is not
+    instantiated (the caller then runs dwconv + gemm).  mid [B,H,W,Mid] bf16, w3 [Cout, Mid] bf16, residual [B,H,W,Cout]."""
+    global launch_count
+    _chk(mid, torch.bfloat16, "mid"); _chk(w3, torch.bfloat16, "w3")
+    _ensure_init(mid)
+    assert mid.is_contiguous() and w3.is_contiguous()
+    B, H, W, Mid = mid.shape
+    Cout = w3.shape[0]
+    if residual is not None:
+        _chk(residual, torch.bfloat16, "residual")
+        assert residual.is_contiguous() and residual.shape == (B, H, W, Cout)
+    y = torch.empty((B, H, W, Cout), device=mid.device, dtype=torch.bfloat16)
+    prof = _profiler
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = _lib.call_rc("es3_dwproj_tc_bf16", mid.data_ptr(), wdw.data_ptr(), b2.data_ptr(), w3.data_ptr(), s3.data_ptr(),
+                      b3.data_ptr(), _ptr(residual), y.data_ptr(), B, H, W, Mid, Cout, ACT[act], _stream())
+    if rc < 0:
+        return None
+    launch_count += 1
+    if prof is not None:
+        e1.record()
+        prof.records.append((f"dwproj_tc[{Mid}-{Cout}]", e0, e1, _nb(mid, y, residual), 2 * B * H * W * Mid * (9 + Cout)))
+    return y
+
+
 def layernorm(x, gamma, beta, eps=1e-5, *, pos=None, pos_size=0, H=0, W=0, out_bf16=True, out_f32=False):
     """x: [M, C] fp32 -> (bf16 [M,C] | None, fp32 [M,C] | None); optional tiled abs-pos add before the norm."""
     _chk(x, torch.float32, "x")

@@ -108,6 +108,14 @@ int es3_mbconv_fused_bf16(const void* x, void* y, const void* w1, const float* s
 int es3_mbconv_tc_bf16(const void* x, void* y, const void* w1, const float* s1, const float* b1, const float* wdw,
                        const float* b2, const void* w3, const float* s3, const float* b3, int B, int H, int W, int Cin, int Mid,
                        int Cout, int stride, int residual, int act, void* stream);
+/* Depthwise 3x3 (stride 1) + bias + hardswish + pointwise projection + BN (+ residual) in one tcgen05 kernel, for MBConv blocks
+ * whose expanded tensor is too wide for the fully fused kernels (EfficientViT stages 3/4): mid [B,H,W,Mid] bf16 is TMA-staged in
+ * 64-channel chunks with its halo, the depthwise runs as diagonal m16n8k8 MMAs, its output goes straight into the swizzled A
+ * operand of UMMAs accumulating [128 px x Cout] in TMEM.  wdw [9][Mid] fp32 (BN scale folded), b2 [Mid], w3 [Cout][Mid] bf16,
+ * s3/b3 [Cout]; residual [B,H,W,Cout] bf16 or NULL.  Instantiated (Mid, Cout) = (512,128), (1024,256); -1 otherwise.
+ * Replaces es3_dwconv_tiled_bf16 + es3_gemm_bf16 for ops.py:315-367 (depth_conv + point_conv). */
+int es3_dwproj_tc_bf16(const void* mid, const float* wdw, const float* b2, const void* w3, const float* s3, const float* b3,
+                       const void* residual, void* y, int B, int H, int W, int Mid, int Cout, int act, void* stream);
 
 /* Bilinear (align_corners=False) NHWC bf16 -> NCHW fp32.  Replaces F.interpolate at stage1/model.py:204-210. */
 int es3_bilinear_nhwc_to_nchw(const void* in, float* out, int B, int Hi, int Wi, int C, int Ho, int Wo, void* stream);

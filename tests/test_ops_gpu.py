@@ -267,6 +267,30 @@ def test_mbconv_fused(cuda, cin, mid, cout, stride, res, H, W, impl):
     _close(y, ref.permute(0, 2, 3, 1), 1e-2, "mbconv_fused")
 
 
+@pytest.mark.parametrize("mid,cout,H,W,res", [(512, 128, 64, 64, True), (512, 128, 19, 37, True), (512, 128, 8, 16, False),
+                                              (1024, 256, 32, 32, True), (1024, 256, 9, 21, False)])
+def test_dwproj_tc(cuda, mid, cout, H, W, res):
+    """depthwise 3x3 + bias + hswish + projection + BN (+ residual) in one tcgen05 kernel vs the op-by-op statement."""
+    from efficientsam3_b200 import ops
+    g = torch.Generator().manual_seed(mid + H)
+    B = 2
+    m = _bf(torch.randn(B, H, W, mid, generator=g)).to(cuda)
+    wdw = (torch.randn(mid, 1, 3, 3, generator=g) / 3).to(cuda); b2 = (torch.randn(mid, generator=g) * 0.2).to(cuda)
+    w3 = _bf(torch.randn(cout, mid, generator=g) / math.sqrt(mid)).to(cuda)
+    s3 = (torch.rand(cout, generator=g) + 0.5).to(cuda); b3 = (torch.randn(cout, generator=g) * 0.2).to(cuda)
+    x = _bf(torch.randn(B, H, W, cout, generator=g)).to(cuda) if res else None
+    y = ops.dwproj(m, wdw.reshape(mid, 9).t().contiguous(), b2, w3, s3, b3, residual=x)
+    assert y is not None
+    wq = wdw.to(torch.bfloat16).float()      # the kernel multiplies bf16 depthwise weights
+    d = F.hardswish(F.conv2d(m.float().permute(0, 3, 1, 2), wq, b2, padding=1, groups=mid)).to(torch.bfloat16).float()
+    ref = F.conv2d(d, w3.float()[:, :, None, None]) * s3.view(1, -1, 1, 1) + b3.view(1, -1, 1, 1)
+    if res:
+        ref = ref + x.float().permute(0, 3, 1, 2)
+    _close(y, ref.permute(0, 2, 3, 1), 1e-2, "dwproj_tc")
+    assert ops.dwproj(m[..., :256].contiguous(), wdw.reshape(mid, 9).t()[:, :256].contiguous(), b2[:256], w3[:, :256].contiguous(),
+                      s3, b3) is None      # shape not instantiated -> None, the caller falls back to dwconv + gemm
+
+
 def test_mbconv_fused_uninstantiated_shape_returns_none(cuda):
     from efficientsam3_b200 import ops
     x = torch.zeros(1, 8, 8, 48, device=cuda, dtype=torch.bfloat16)
