@@ -332,6 +332,8 @@ def mbconv_fused(x, w1, s1, b1, wdw, b2, w3, s3, b3, stride, residual, act, impl
     rc, tag = -1, "mbconv_tc"
     if impl == "tc" or (impl is None and MBCONV_TC):
         rc = _lib.call_rc("es3_mbconv_tc_bf16", *args)
+        if rc < 0:
+            rc = _lib.call_rc("es3_mbconv_tc_s2_bf16", *args)
     if rc < 0 and impl != "tc":
         rc, tag = _lib.call_rc("es3_mbconv_fused_bf16", *args), "mbconv_fused"
     if rc < 0:

@@ -108,6 +108,11 @@ int es3_mbconv_fused_bf16(const void* x, void* y, const void* w1, const float* s
 int es3_mbconv_tc_bf16(const void* x, void* y, const void* w1, const float* s1, const float* b1, const float* wdw,
                        const float* b2, const void* w3, const float* s3, const float* b3, int B, int H, int W, int Cin, int Mid,
                        int Cout, int stride, int residual, int act, void* stream);
+/* Same contract on tcgen05 for the stride-2, no-residual blocks (Cin, Mid, Cout) in {(16,64,32), (32,128,64), (64,256,128)}:
+ * 4 x 16 output tiles, 9 x 33 input tiles = three M=128 UMMA row blocks, 32-channel chunks.  Returns -1 for any other shape. */
+int es3_mbconv_tc_s2_bf16(const void* x, void* y, const void* w1, const float* s1, const float* b1, const float* wdw,
+                          const float* b2, const void* w3, const float* s3, const float* b3, int B, int H, int W, int Cin,
+                          int Mid, int Cout, int stride, int residual, int act, void* stream);
 /* Depthwise 3x3 (stride 1) + bias + hardswish + pointwise projection + BN (+ residual) in one tcgen05 kernel, for MBConv blocks
  * whose expanded tensor is too wide for the fully fused kernels (EfficientViT stages 3/4): mid [B,H,W,Mid] bf16 is TMA-staged in
  * 64-channel chunks with its halo, the depthwise runs as diagonal m16n8k8 MMAs, its output goes straight into the swizzled A

@@ -2,7 +2,8 @@
 import sys, math, torch
 sys.path.insert(0, "/root/repo")
 from efficientsam3_b200 import ops
-cfgs = {"a": (32, 128, 32, 1, True, 256), "b": (64, 256, 64, 1, True, 128), "c": (16, 64, 32, 2, False, 512)}
+cfgs = {"a": (32, 128, 32, 1, True, 256), "b": (64, 256, 64, 1, True, 128), "c": (16, 64, 32, 2, False, 512),
+        "d": (32, 128, 64, 2, False, 256), "e": (64, 256, 128, 2, False, 128)}
 cin, mid, cout, stride, res, S = cfgs[sys.argv[1] if len(sys.argv) > 1 else "a"]
 impls = sys.argv[2:] or ["mma", "tc"]
 B = 32
