@@ -203,6 +203,13 @@ def run_native(args):
         else:
             roofline = {"bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s",
                         "frac": round(frac_hbm, 4), "traffic": None}
+        # DRAM bytes per launch of that kernel from an `ncu --set full` capture (profiles/r1_traffic.json; null if not captured)
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            tr = json.load(open(tpath)).get(name)
+            if tr:
+                roofline["traffic"] = tr["dram_bytes_per_launch"]
+                roofline["algorithmic_bytes_per_launch"] = round(kbytes / max(calls, 1))
         roofline.update(kernel=name, launches_per_step=calls, ms_per_step=round(kms, 4),
                         share_of_step=round(kms / sum(r[1] for r in kernel_table), 4), peak_source=pk["src"])
         # whole-step figures against SURVEY section 8d's per-image algorithmic bytes / flops
