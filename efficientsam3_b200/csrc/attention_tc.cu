@@ -16,10 +16,8 @@
 
 namespace es3 {
 
-constexpr int FA_BM = 128, FA_D = 64, FA_STAGES = 3;   // KV tile rows BN is a template parameter (128 or 96)
+constexpr int FA_BM = 128, FA_D = 64, FA_STAGES = 3;   // (max) KV ring depth   // KV tile rows BN is a template parameter (128 or 96)
 constexpr int FA_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
-constexpr int FA_THREADS = 352;           // 11 warps
-constexpr int FA_SMEM = 1024 + 2 * FA_TILE_BYTES + FA_STAGES * 2 * FA_TILE_BYTES;
 
 struct FaArgs {
   const bf16* qkv;
@@ -80,8 +78,12 @@ __device__ __forceinline__ uint64_t fa_desc_mn(uint32_t smem_addr) {
 }
 
 // BN = keys per tile: 128 in general; 96 for 24x24 windows (576 = 6 x 96: no padded columns).
-template <int FA_BN>
-__global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const FaArgs a) {
+template <int FA_BN, int NS>
+__global__ void __launch_bounds__((3 + 4 * NS) * 32, NS == 1 ? 2 : 1) attn_tc_kernel(const FaArgs a) {
+  // NS query slots per CTA: 2 (one CTA per SM, the slots ping-pong) for long sequences; 1 (two CTAs per SM, 256 TMEM columns
+  // each, 2-stage KV ring) for the 24x24 windows, where a CTA lives for only 6 key tiles and the start-up / drain of
+  // a single resident CTA was not hidden (ncu: 31 K cycles per CTA, 21 % of samples waiting on MMA results)
+  constexpr int STG = NS == 2 ? 3 : 2, THR = (3 + 4 * NS) * 32, VWARP = 2 + 4 * NS;
   extern __shared__ uint8_t fa_raw[];
   __shared__ __align__(8) uint64_t kv_full[FA_STAGES], kv_empty[FA_STAGES];
   __shared__ __align__(8) uint64_t s_full[2], p_full[2], ot_full[2], ot_free[2];
@@ -89,13 +91,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const FaArgs a) 
 
   const uint32_t smem0 = (ptx::smem_u32(fa_raw) + 1023u) & ~1023u;
   const uint32_t u_q = smem0;                          // [2][128 x 128 B]
-  const uint32_t u_kv = smem0 + 2 * FA_TILE_BYTES;     // [stage][K | V]
+  const uint32_t u_kv = smem0 + NS * FA_TILE_BYTES;    // [stage][K | V]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = blockIdx.y;
   const int b = blockIdx.z / a.nwin, wi = blockIdx.z % a.nwin;
-  const int q0 = blockIdx.x * 2 * FA_BM;               // first query row of slot 0
-  const int nslots = (q0 + FA_BM < a.L) ? 2 : 1;
+  const int q0 = blockIdx.x * NS * FA_BM;              // first query row of slot 0
+  const int nslots = (NS == 2 && q0 + FA_BM < a.L) ? 2 : 1;
   const int ld = 3 * a.C;
   const bf16* qbase = a.qkv + head * FA_D;
   const bf16* kbase = qbase + a.C;
@@ -103,16 +105,16 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const FaArgs a) 
   const int ntiles = (a.L + FA_BN - 1) / FA_BN;
 
   if (tid == 0) {
-    for (int s = 0; s < FA_STAGES; ++s) { ptx::mbar_init(&kv_full[s], 2); ptx::mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < STG; ++s) { ptx::mbar_init(&kv_full[s], 2); ptx::mbar_init(&kv_empty[s], 1); }
     for (int q = 0; q < 2; ++q) {
       ptx::mbar_init(&s_full[q], 1); ptx::mbar_init(&p_full[q], 4);
       ptx::mbar_init(&ot_full[q], 1); ptx::mbar_init(&ot_free[q], 4);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(&tmem_holder, 512);
+  if (warp == 1) ptx::tmem_alloc(&tmem_holder, 256 * NS);
   // Q tiles (both slots), gathered by everyone
-  for (int i = tid; i < 2 * FA_BM * 8; i += FA_THREADS) {
+  for (int i = tid; i < NS * FA_BM * 8; i += THR) {
     const int c = i & 7, r = (i >> 3) & 127, q = i >> 10;
     const int l = q0 + q * FA_BM + r;
     const bool ok = l < a.L;
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const FaArgs a) 
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_holder;
 
-  if (warp == 0 || warp == 10) {
+  if (warp == 0 || warp == VWARP) {
     // ------------------------------------------------------------------ K (warp 0) / V (warp 10) producers
     const bf16* base = (warp == 0) ? kbase : vbase;
     const uint32_t off = (warp == 0) ? 0 : FA_TILE_BYTES;
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const FaArgs a) 
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&kv_full[stage]);
-      if (++stage == FA_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == STG) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const FaArgs a) 
         const uint32_t jp = (uint32_t)(j & 1);
         int nstage = stage + 1;
         uint32_t nphase = phase;
-        if (nstage == FA_STAGES) { nstage = 0; nphase ^= 1; }
+        if (nstage == STG) { nstage = 0; nphase ^= 1; }
         for (int q = 0; q < nslots; ++q) {
           ptx::mbar_wait(&p_full[q], jp);          // P_q(j) written, S_q(j) fully consumed
           ptx::mbar_wait(&ot_free[q], jp ^ 1);      // Ot_q(j-1) folded into registers
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_tc_kernel(const FaArgs a) 
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem, 512);
+    ptx::tmem_dealloc(tmem, 256 * NS);
   }
 }
 
@@ -307,16 +309,29 @@ extern "C" int es3_attention_tc_bf16(const void* qkv, void* out, int B, int H, i
   a.nwin = win ? (H / win) * (W / win) : 1;
   a.L = win ? win * win : H * W;
   a.scale_log2 = scale * 1.4426950408889634f;
+  const int ns = a.L <= 1024 ? 1 : 2;       // windows: one slot per CTA, two CTAs per SM; global attention: two slots
+  const int smem = 1024 + ns * FA_TILE_BYTES + (ns == 2 ? 3 : 2) * 2 * FA_TILE_BYTES;
+  const int threads = (3 + 4 * ns) * 32;
   static bool configured = false;
   if (!configured) {
-    ES3_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    ES3_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    const int s2 = 1024 + 2 * FA_TILE_BYTES + 3 * 2 * FA_TILE_BYTES, s1 = 1024 + FA_TILE_BYTES + 2 * 2 * FA_TILE_BYTES;
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<96, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<96, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
     configured = true;
   }
-  dim3 grid(ceil_div(a.L, 2 * FA_BM), num_heads, B * a.nwin);
+  dim3 grid(ceil_div(a.L, ns * FA_BM), num_heads, B * a.nwin);
+  cudaStream_t st = (cudaStream_t)stream;
   // 24x24 windows (L = 576 = 6 x 96) and other multiples of 96 that are not multiples of 128: 96-key tiles, no padding
-  if (a.L % 96 == 0 && a.L % 128 != 0) attn_tc_kernel<96><<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(a);
-  else attn_tc_kernel<128><<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(a);
+  const bool bn96 = a.L % 96 == 0 && a.L % 128 != 0;
+  if (ns == 1) {
+    if (bn96) attn_tc_kernel<96, 1><<<grid, threads, smem, st>>>(a);
+    else attn_tc_kernel<128, 1><<<grid, threads, smem, st>>>(a);
+  } else {
+    if (bn96) attn_tc_kernel<96, 2><<<grid, threads, smem, st>>>(a);
+    else attn_tc_kernel<128, 2><<<grid, threads, smem, st>>>(a);
+  }
   ES3_LAUNCH_CHECK("attn_tc_kernel");
   return 0;
 }
