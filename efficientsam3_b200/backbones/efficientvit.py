@@ -2,10 +2,11 @@
 state_dict keys) of the reference `sam3/sam3/backbones/efficientvit/{backbone.py, nn/ops.py}` so that
 reference checkpoints load unchanged, but every forward runs on the hand-written kernels of libes3.so:
 
-  ConvLayer(k=1)+BN+act, nn.Linear-like contractions -> es3_gemm_bf16 (tcgen05 / TMEM / TMA)
-  depthwise convs                                    -> es3_dwconv_bf16
-  stem conv / stem DSConv residual                   -> es3_stem_conv3x3_s2 / es3_dsconv_res_bf16
-  LiteMLA (ops.py:521-671)                           -> es3_gemm_bf16 + es3_litemla_aggreg + es3_litemla_attn
+  input stem (conv 3x3 s2 + residual DSConv)         -> es3_stem_fused_c16 (b1; other widths: es3_stem_conv3x3_s2 + es3_dsconv_res_bf16)
+  MBConv blocks, stages 1-2 and the stage openers    -> es3_mbconv_tc_bf16 / es3_mbconv_tc_s2_bf16 (tcgen05, whole block on the SM)
+  MBConv blocks, stages 3-4                          -> es3_gemm_bf16 (expand) + es3_dwproj_tc_bf16 (depthwise + project + residual)
+  LiteMLA (ops.py:521-671)                           -> es3_gemm_bf16 (qkv, proj) + es3_litemla_aggreg_dwpw + es3_litemla_attn_tc
+  anything not instantiated                          -> es3_gemm_bf16 / es3_dwconv_tiled_bf16 / es3_mbconv_fused_bf16 (all native)
 
 Activations live in HBM as NHWC bf16; accumulation is fp32.  Eval-mode only (see NativePlanMixin).
 """
