@@ -208,8 +208,8 @@ def run_native(args):
         if os.path.exists(tpath):
             tr = json.load(open(tpath)).get(name)
             if tr:
-                roofline["traffic"] = tr["dram_bytes_per_launch"]
-                roofline["algorithmic_bytes_per_launch"] = round(kbytes / max(calls, 1))
+                roofline["traffic"] = tr["dram_bytes_per_launch"]     # of the captured launch below, not the family average
+                roofline["traffic_launch"] = tr.get("captured_launch")
         roofline.update(kernel=name, launches_per_step=calls, ms_per_step=round(kms, 4),
                         share_of_step=round(kms / sum(r[1] for r in kernel_table), 4), peak_source=pk["src"])
         # whole-step figures against SURVEY section 8d's per-image algorithmic bytes / flops

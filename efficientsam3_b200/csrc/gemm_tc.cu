@@ -406,8 +406,15 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs
 
 // Tile width: N need not be a multiple of BN (TMA zero-fills weight rows >= N, the epilogue masks 32-column
 // chunks), so take 256 whenever the padding waste is small -- it halves the smem operand traffic per MMA.
-static int pick_bn(int N, int bn_hint) {
+static int pick_bn(int N, int bn_hint, int K = 1 << 30, int act = ACT_NONE) {
   if (bn_hint == 32 || bn_hint == 64 || bn_hint == 128 || bn_hint == 256) return bn_hint;
+  // short-K GEMMs (the pointwise convs of the students: K = 128 / 256) are epilogue- and store-bound, and narrower tiles
+  // (two CTAs per SM, more tiles in flight) win there: measured with scripts/gemm_bn_sweep.py on B200, e.g. K=128 N=512
+  // 104 -> 85 us, K=256 N=1024 56 -> 49 us, K=256 N=128 (+residual) 48 -> 43 us, K=256 N=1024 + GELU 68 -> 61 us
+  if (K < 512 && N >= 64) {
+    if (act == ACT_GELU) return 64;
+    return N >= 384 ? 128 : 64;
+  }
   if (N >= 512 && (ceil_div(N, 256) * 256 - N) * 16 <= N) return 256;   // <= 6.25 % padded columns
   if (N % 128 == 0 || N > 1024) return 128;
   if (N % 64 == 0) return 64;
@@ -455,7 +462,7 @@ extern "C" int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, lon
   ES3_REQUIRE(rope == nullptr || act == ACT_NONE, "es3_gemm_bf16_ex: rope epilogue expects act = none");
   ES3_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
               "es3_gemm_bf16: pointers must be 16-byte aligned");
-  const int bn = pick_bn(N, bn_hint);
+  const int bn = pick_bn(N, bn_hint, K, act);
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};

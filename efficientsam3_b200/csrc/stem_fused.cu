@@ -20,6 +20,9 @@ __device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1,
 __device__ __forceinline__ void cpa4(uint32_t saddr, const void* g, uint32_t sz) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cpa16(uint32_t saddr, const void* g, uint32_t sz) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
+}
 __device__ __forceinline__ void mma16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -37,7 +40,8 @@ __device__ __forceinline__ void mma1688(float* d, uint32_t a0, uint32_t a1, uint
 constexpr int SF_TH = 8, SF_TW = 32, SF_C = 16;
 constexpr int SF_XH = SF_TH + 2, SF_XW = SF_TW + 2;            // x1 tile with halo: 10 x 34
 constexpr int SF_NPX = SF_XH * SF_XW, SF_NPX_PAD = (SF_NPX + 15) / 16 * 16;   // 340 -> 352
-constexpr int SF_IH = 2 * (SF_XH - 1) + 3, SF_IW = 2 * (SF_XW - 1) + 3;       // 21 x 69 input pixels
+constexpr int SF_IH = 2 * (SF_XH - 1) + 3;                                    // 21 input rows
+constexpr int SF_IW = 72;   // 69 input columns (2*33 + 3), widened to 72 with the origin moved one pixel left: 16-byte aligned rows
 constexpr int SF_ARS = 32 * 2 + 16;   // im2col row: 32 bf16 + pad
 constexpr int SF_XRS = SF_C * 2 + 16; // x1 row: 16 bf16 + pad
 constexpr int SF_IN_BYTES = (3 * SF_IH * SF_IW * 4 + 15) / 16 * 16;
@@ -54,6 +58,7 @@ struct StemArgs {
   const bf16* wpw;    // [16][16] pointwise weights [n][k]
   const float* spw; const float* bpw;  // folded BN after the pointwise conv
   int H, W, Ho, Wo, tiles_x;
+  int vec16;          // image rows are 16-byte aligned (W % 4 == 0, aligned base): 16-byte cp.async
 };
 
 __global__ void __launch_bounds__(256) stem_fused_kernel(const StemArgs a) {
@@ -69,22 +74,33 @@ __global__ void __launch_bounds__(256) stem_fused_kernel(const StemArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
   const int oy0 = (blockIdx.x / a.tiles_x) * SF_TH, ox0 = (blockIdx.x % a.tiles_x) * SF_TW;
-  const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;   // input coords of the patch origin
+  const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 4;   // input coords of the patch origin (x: one extra pixel on the left, see SF_IW)
 
   // ---- phase 0: input patch (4-byte cp.async with zero fill outside the image: every copy of the CTA is in flight
   // before anything waits) + weights
   const float* ib = a.img + (long long)b * 3 * a.H * a.W;
   const uint32_t u_in = static_cast<uint32_t>(__cvta_generic_to_shared(s_in));
-  for (int r = warp; r < 3 * SF_IH; r += 8) {
-    const int c = r / SF_IH, y = r - c * SF_IH;
-    const int iy = iy0 + y;
-    const bool rowin = iy >= 0 && iy < a.H;
-    const float* src = ib + ((long long)c * a.H + (rowin ? iy : 0)) * a.W;
+  if (a.vec16) {
+    // rows are 16-byte aligned and no 4-pixel group straddles the image border: 18 cp.async.16 per row instead of 69 x 4 bytes
+    for (int i = tid; i < 3 * SF_IH * (SF_IW / 4); i += 256) {
+      const int r = i / (SF_IW / 4), k = i - r * (SF_IW / 4);
+      const int c = r / SF_IH, y = r - c * SF_IH;
+      const int iy = iy0 + y, ix = ix0 + 4 * k;
+      const bool in = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+      cpa16(u_in + (r * SF_IW + 4 * k) * 4, ib + ((long long)c * a.H + (in ? iy : 0)) * a.W + (in ? ix : 0), in ? 16u : 0u);
+    }
+  } else {
+    for (int r = warp; r < 3 * SF_IH; r += 8) {
+      const int c = r / SF_IH, y = r - c * SF_IH;
+      const int iy = iy0 + y;
+      const bool rowin = iy >= 0 && iy < a.H;
+      const float* src = ib + ((long long)c * a.H + (rowin ? iy : 0)) * a.W;
 #pragma unroll
-    for (int x = lane; x < SF_IW; x += 32) {
-      const int ix = ix0 + x;
-      const bool in = rowin && ix >= 0 && ix < a.W;
-      cpa4(u_in + (r * SF_IW + x) * 4, src + (in ? ix : 0), in ? 4u : 0u);
+      for (int x = lane; x < SF_IW; x += 32) {
+        const int ix = ix0 + x;
+        const bool in = rowin && ix >= 0 && ix < a.W;
+        cpa4(u_in + (r * SF_IW + x) * 4, src + (in ? ix : 0), in ? 4u : 0u);
+      }
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -116,7 +132,7 @@ __global__ void __launch_bounds__(256) stem_fused_kernel(const StemArgs a) {
       kval[j] = k < 27;
       const int kk = kval[j] ? k : 0;
       const int ci = kk / 9, r = kk - ci * 9, ky = r / 3, kx = r - ky * 3;
-      koff[j] = (ci * SF_IH + ky) * SF_IW + kx;
+      koff[j] = (ci * SF_IH + ky) * SF_IW + kx + 1;   // +1: the patch origin sits one pixel left of the first tap
     }
     for (int mt = warp; mt < SF_NPX_PAD / 16; mt += 8) {
       float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -230,6 +246,7 @@ extern "C" int es3_stem_fused_c16(const float* img, const void* w0, const float*
   a.wpw = (const bf16*)wpw; a.spw = spw; a.bpw = bpw;
   a.H = H; a.W = W; a.Ho = (H - 1) / 2 + 1; a.Wo = (W - 1) / 2 + 1;
   a.tiles_x = ceil_div(a.Wo, SF_TW);
+  a.vec16 = ((W & 3) == 0 && ((uintptr_t)img & 15) == 0) ? 1 : 0;
   static bool configured = false;
   if (!configured) {
     ES3_CHECK_CUDA(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
