@@ -69,6 +69,27 @@ SIGNATURES: dict[str, list] = {
     "es3_litemla_attn_tc": [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _f, _vp],
     "es3_litemla_attn": [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _f, _vp],
     "es3_litemla_attn_generic": [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _f, _vp],
+    # student backward (train_bwd.cu)
+    "es3_bn_stats": [_vp, _ll, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "es3_affine_act": [_vp, _vp, _vp, _i, _vp, _vp, _ll, _i, _vp],
+    "es3_bn_act_bwd_reduce": [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp],
+    "es3_bn_act_bwd_apply": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _ll, _i, _vp],
+    "es3_add_bf16": [_vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _vp],
+    "es3_wgrad_pw": [_vp, _ll, _vp, _ll, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _ll, _ll, _vp],
+    "es3_dwconv_bwd_data": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "es3_dwconv_wgrad": [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "es3_stem_wgrad": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
+    "es3_bilinear_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "es3_litemla_attn_bwd": [_vp, _ll, _vp, _ll, _vp, _i, _vp, _vp, _ll, _i, _i, _i, _f, _vp],
+}
+
+# workspace-size helpers: name -> argtypes, restype long long
+SIZE_HELPERS: dict[str, list] = {
+    "es3_col_reduce_ws_floats": [_ll, _i],
+    "es3_wgrad_pw_ws_floats": [_ll, _i, _i],
+    "es3_dwconv_wgrad_ws_floats": [_i, _i, _i, _i, _i, _i],
+    "es3_stem_wgrad_ws_floats": [_i, _i, _i, _i],
+    "es3_litemla_bwd_ws_floats": [_i, _i, _i],
 }
 
 _lib = None
@@ -97,6 +118,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
         fn.restype = _i
         fn.argtypes = argtypes
+    for name, argtypes in SIZE_HELPERS.items():
+        fn = getattr(lib, name)
+        fn.restype = _ll
+        fn.argtypes = argtypes
     _lib = lib
     return lib
 
@@ -110,6 +135,11 @@ def call(name: str, *args) -> None:
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise Es3Error(f"{name} failed ({rc}): {last_error()}")
+
+
+def size(name: str, *args) -> int:
+    """Workspace size (in floats) from one of the *_ws_floats helpers; pure host arithmetic, no GPU needed."""
+    return int(getattr(load(), name)(*args))
 
 
 def call_rc(name: str, *args) -> int:

@@ -1,0 +1,939 @@
+// Student backward (the `loss.backward()` half of train_one_epoch,
+// stage1/train_image_encoder_stage1.py:154-268) -- the kernels the train-mode forward and the backward of the
+// EfficientViT student need beyond the inference kernels:
+//
+//   train-mode BatchNorm2d (efficientvit/nn/ops.py:39-80 ConvLayer.norm in .train(): batch statistics + running-stat update)
+//     es3_bn_stats            per-channel mean / invstd over the rows of a raw conv output  (two-stage, deterministic)
+//     es3_affine_act          a = act(scale[c] * z + shift[c]) (+ residual)                (the normalise + activation pass)
+//     es3_bn_act_bwd_reduce   g = da * act'(u); per-channel sum g, sum g z -> dgamma, dbeta and the dz coefficients
+//     es3_bn_act_bwd_apply    dz = A[c] g + B[c] z + C[c]   (batch BN, eval BN and bias-only layers share it)
+//   convolution gradients
+//     es3_wgrad_pw            dW[n][k] = sum_m dz[m][n] x[m][k]: 1x1 convs, and one tap of a dense 3x3 (spatially shifted x)
+//                             -- mma.sync m16n8k16 with both operands through ldmatrix.trans (contraction over pixels)
+//     es3_dwconv_bwd_data     depthwise conv input gradient for any stride (stride 1 can also use es3_dwconv with flipped taps)
+//     es3_dwconv_wgrad        depthwise conv weight gradient
+//     es3_stem_wgrad          weight gradient of the 3 -> C stride-2 stem conv on the fp32 NCHW image
+//     (input gradients of 1x1 / dense 3x3 convs are es3_gemm_bf16 / es3_conv3x3_bf16 calls on transposed / flipped weights)
+//   es3_bilinear_bwd          adjoint of es3_bilinear_nhwc_to_nchw (F.interpolate backward, stage1/model.py:204-210)
+//   es3_litemla_attn_bwd      backward of the ReLU linear attention (ops.py:592-621), head dim 16
+//   es3_add_bf16              out = a + b on (row-strided) bf16 matrices: gradient fan-in at residual joins
+//
+// Gradients of activations are bf16 (the reference's AMP path keeps them fp16), parameter gradients fp32 and ACCUMULATED
+// (+=) into their destination, all reductions are two-stage with a fixed order: no atomics, bit-reproducible.
+#include "common.cuh"
+
+namespace es3 {
+namespace {
+
+// ------------------------------------------------------------------------------------------ activation derivative
+template <int ACT>
+__device__ __forceinline__ float act_grad_t(float u) {
+  if constexpr (ACT == ACT_RELU) return u > 0.f ? 1.f : 0.f;
+  // aten hardswish_backward: 0 below -3, x/3 + 0.5 on [-3, 3], 1 above
+  else if constexpr (ACT == ACT_HSWISH) return u < -3.f ? 0.f : (u <= 3.f ? fmaf(u, 1.f / 3.f, 0.5f) : 1.f);
+  else if constexpr (ACT == ACT_GELU)
+    return 0.5f * (1.f + erff(u * 0.70710678118654752440f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+  else if constexpr (ACT == ACT_RELU6) return (u > 0.f && u < 6.f) ? 1.f : 0.f;
+  else return 1.f;
+}
+
+#define ES3_DISPATCH_ACT_BWD(act, ACT_CONST, ...)                                                       \
+  switch (act) {                                                                                        \
+    case ACT_NONE: { constexpr int ACT_CONST = ACT_NONE; __VA_ARGS__; } break;                          \
+    case ACT_RELU: { constexpr int ACT_CONST = ACT_RELU; __VA_ARGS__; } break;                          \
+    case ACT_HSWISH: { constexpr int ACT_CONST = ACT_HSWISH; __VA_ARGS__; } break;                      \
+    case ACT_GELU: { constexpr int ACT_CONST = ACT_GELU; __VA_ARGS__; } break;                          \
+    case ACT_RELU6: { constexpr int ACT_CONST = ACT_RELU6; __VA_ARGS__; } break;                        \
+    default: es3::set_error("activation code %d has no backward instantiated", act); return 1;          \
+  }
+
+__device__ __forceinline__ void cpa16(uint32_t saddr, const void* g, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// ------------------------------------------------------------------------------------------ per-channel column reductions
+// z (and da) are [M][C] bf16, contiguous.  grid (nblk, ceil(CV / CVB)), block 256.  A thread owns one 8-channel vector
+// (cv) and every `lanes`-th row of the block's row range; the lanes are then tree-reduced through shared memory.
+// STATS: s0 = sum z, s1 = sum z^2.   else: g = da * act'(scale z + shift), s0 = sum g, s1 = sum g z.
+// part: [nblk][2][C] fp32.
+constexpr int CR_THREADS = 256;
+
+template <int ACT, bool STATS>
+__global__ void __launch_bounds__(CR_THREADS) col_reduce_kernel(const bf16* __restrict__ z, const bf16* __restrict__ da,
+                                                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                long long M, int C, int CVB, long long rows_per_block,
+                                                                float* __restrict__ part) {
+  __shared__ float red[CR_THREADS][17];
+  const int tid = threadIdx.x;
+  const int lanes = CR_THREADS / CVB;
+  const int cvl = tid % CVB, pl = tid / CVB;
+  const int cv = blockIdx.y * CVB + cvl;
+  const bool active = pl < lanes && cv * 8 < C;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
+  if (active) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = (!STATS && scale) ? scale[cv * 8 + i] : 1.f;
+      sh[i] = (!STATS && shift) ? shift[cv * 8 + i] : 0.f;
+    }
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(M, r0 + rows_per_block);
+    for (long long r = r0 + pl; r < r1; r += lanes) {
+      float fz[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * C + cv * 8)), fz);
+      if constexpr (STATS) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s0[i] += fz[i]; s1[i] = fmaf(fz[i], fz[i], s1[i]); }
+      } else {
+        float fd[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(da + r * C + cv * 8)), fd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float g = fd[i] * act_grad_t<ACT>(fmaf(sc[i], fz[i], sh[i]));
+          s0[i] += g;
+          s1[i] = fmaf(g, fz[i], s1[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[tid][i] = s0[i]; red[tid][8 + i] = s1[i]; }
+  __syncthreads();
+  int top = 1;
+  while (top < lanes) top <<= 1;
+  for (int stride = top >> 1; stride > 0; stride >>= 1) {
+    if (pl < stride && pl + stride < lanes) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) red[tid][i] += red[tid + stride * CVB][i];
+    }
+    __syncthreads();
+  }
+  if (pl == 0 && cv * 8 < C) {
+    float* p0 = part + ((long long)blockIdx.x * 2) * C + cv * 8;
+    float* p1 = p0 + C;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { p0[i] = red[tid][i]; p1[i] = red[tid][8 + i]; }
+  }
+}
+
+// one thread per channel: batch statistics, folded (scale, shift) for the normalise pass, running-stat update
+// (nn.BatchNorm2d: momentum 0.1 on the UNBIASED variance).
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ part, int nblk, int C, long long M, float eps, float momentum,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean,
+                                         float* __restrict__ invstd, float* __restrict__ scale, float* __restrict__ shift,
+                                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                                         long long* __restrict__ num_batches_tracked) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) num_batches_tracked[0] += 1;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += (double)part[((long long)b * 2) * C + c];
+    q += (double)part[((long long)b * 2 + 1) * C + c];
+  }
+  const double mu = s / (double)M;
+  double var = q / (double)M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)mu;
+  invstd[c] = is;
+  const float sc = (gamma ? gamma[c] : 1.f) * is;
+  scale[c] = sc;
+  shift[c] = (beta ? beta[c] : 0.f) - (float)mu * sc;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+  if (running_var) {
+    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// mode 0: no norm (scale = 1 or given, shift = conv bias): A = scale, dbeta (= d bias) += sum g
+// mode 1: eval-mode BN (running stats): A = scale; dbeta += sum g; dgamma += invstd (sum g z - mean sum g)
+// mode 2: batch-stat BN: additionally B, C carry the mean / variance terms of the BN backward.
+// coef: [3][C] = A | B | C with dz = A g + B z + C.
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, long long M, int mode,
+                                       const float* __restrict__ scale, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sg = 0.0, sgz = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    sg += (double)part[((long long)b * 2) * C + c];
+    sgz += (double)part[((long long)b * 2 + 1) * C + c];
+  }
+  const float sc = scale ? scale[c] : 1.f;
+  float A = sc, Bc = 0.f, Cc = 0.f;
+  if (mode != 0) {
+    const double mu = (double)mean[c], is = (double)invstd[c];
+    const double dgam = is * (sgz - mu * sg);
+    if (dgamma) dgamma[c] += (float)dgam;
+    if (mode == 2) {
+      const double mg = sg / (double)M, mgx = dgam / (double)M;
+      Bc = (float)(-(double)sc * is * mgx);
+      Cc = (float)(-(double)sc * mg + (double)sc * is * mu * mgx);
+    }
+  }
+  if (dbeta) dbeta[c] += (float)sg;
+  coef[c] = A;
+  coef[C + c] = Bc;
+  coef[2 * C + c] = Cc;
+}
+
+// ------------------------------------------------------------------------------------------ elementwise passes
+// a[m][c] = act(scale[c] z[m][c] + shift[c]) (+ residual[m][c]); one thread per 8-channel vector.
+template <int ACT>
+__global__ void affine_act_kernel(const bf16* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                                  const bf16* __restrict__ residual, bf16* __restrict__ out, long long total_vec, int CV) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int cv = (int)(i % CV);
+  float f[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float sc = scale ? __ldg(scale + cv * 8 + k) : 1.f, sh = shift ? __ldg(shift + cv * 8 + k) : 0.f;
+    f[k] = es3_act_t<ACT>(fmaf(sc, f[k], sh));
+  }
+  if (residual) {
+    float r[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(residual) + i), r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] += r[k];
+  }
+  reinterpret_cast<uint4*>(out)[i] = pack8(f);
+}
+
+// dz = A[c] * (da * act'(scale z + shift)) + B[c] * z + C[c]
+template <int ACT>
+__global__ void bn_act_bwd_apply_kernel(const bf16* __restrict__ da, const bf16* __restrict__ z, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, const float* __restrict__ coef, bf16* __restrict__ dz,
+                                        long long total_vec, int CV) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int cv = (int)(i % CV), C = CV * 8;
+  float fz[8], fd[8], o[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), fz);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(da) + i), fd);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = cv * 8 + k;
+    const float sc = scale ? __ldg(scale + c) : 1.f, sh = shift ? __ldg(shift + c) : 0.f;
+    const float g = fd[k] * act_grad_t<ACT>(fmaf(sc, fz[k], sh));
+    o[k] = fmaf(__ldg(coef + c), g, fmaf(__ldg(coef + C + c), fz[k], __ldg(coef + 2 * C + c)));
+  }
+  reinterpret_cast<uint4*>(dz)[i] = pack8(o);
+}
+
+// out[m][c] = a[m][c] + b[m][c]; row strides in elements (channel-sliced views), C % 8 == 0.
+__global__ void add_bf16_kernel(const bf16* __restrict__ a, long long lda, const bf16* __restrict__ b, long long ldb,
+                                bf16* __restrict__ out, long long ldo, long long M, int CV) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * CV) return;
+  const long long m = i / CV;
+  const int cv = (int)(i % CV);
+  float fa[8], fb[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a + m * lda + cv * 8)), fa);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(b + m * ldb + cv * 8)), fb);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+  *reinterpret_cast<uint4*>(out + m * ldo + cv * 8) = pack8(fa);
+}
+
+// out[(i / inner) * ld_outer + (i % inner) * ld_inner] += sum_b part[b * n + i]   (fixed order over b)
+__global__ void sum_partials_kernel(const float* __restrict__ part, int nblk, long long n, int inner, long long ld_outer,
+                                    long long ld_inner, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += part[(long long)b * n + i];
+  out[(i / inner) * ld_outer + (i % inner) * ld_inner] += s;
+}
+
+// ------------------------------------------------------------------------------------------ pointwise weight gradient
+// part[split][n][k] = sum over the split's row chunks of dz[m][n] * x[shift(m)][k].
+// CTA tile: 64 (n) x 64 (k) outputs, 256-row chunks staged with cp.async; warp w contracts rows [32 w, 32 w + 32) of the
+// chunk for the whole tile (4 x 8 m16n8 accumulator tiles), the 8 warps are summed through shared memory at the end.
+// Both operands are [row = pixel][channel] in shared memory and go through ldmatrix.trans (the contraction index is the
+// row), exactly the v^T k pattern of litemla_kv_tc_kernel.  shift: x row of output pixel (b, y, x) is (b, y+dy, x+dx),
+// zero outside the H x W map (one tap of a 3x3 conv); dy = dx = 0 and H = 0 for plain 1x1 convs.
+constexpr int WG_TN = 64, WG_TK = 64, WG_ROWS = 256;
+constexpr int WG_RS = (WG_TN + WG_TK) * 2 + 16;      // 272-byte rows: ldmatrix conflict-free
+constexpr int WG_SMEM = WG_ROWS * WG_RS;             // 69632 B
+
+__global__ void __launch_bounds__(256) wgrad_pw_kernel(const bf16* __restrict__ dz, long long lddz, const bf16* __restrict__ x,
+                                                       long long ldx, long long M, int N, int K, int H, int W, int dy, int dx,
+                                                       float* __restrict__ part) {
+  extern __shared__ __align__(16) uint8_t wg_smem[];
+  const uint32_t u = static_cast<uint32_t>(__cvta_generic_to_shared(wg_smem));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * WG_TN, k0 = blockIdx.z * WG_TK;
+  const long long nchunks = (M + WG_ROWS - 1) / WG_ROWS;
+  float acc[4][8][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
+  const int av_p = (lane & 7) + ((lane >> 4) << 3), av_cb = ((lane >> 3) & 1) * 16;
+  const int bk_p = (lane & 7) + (((lane >> 3) & 1) << 3), bk_cb = (lane >> 4) * 16;
+  const bool shifted = H > 0;
+
+  for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const long long row0 = chunk * WG_ROWS;
+    __syncthreads();   // every warp is done with the previous chunk
+    for (int i = tid; i < WG_ROWS * 16; i += 256) {
+      const int rl = i >> 4, v = i & 15;
+      const long long r = row0 + rl;
+      const bf16* src = dz;
+      bool ok = r < M;
+      if (v < 8) {
+        const int c = n0 + v * 8;
+        ok = ok && c < N;
+        if (ok) src = dz + r * lddz + c;
+      } else {
+        const int c = k0 + (v - 8) * 8;
+        ok = ok && c < K;
+        long long rs = r;
+        if (ok && shifted) {
+          const int px = (int)(r % W), py = (int)((r / W) % H);
+          const int yy = py + dy, xx = px + dx;
+          ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+          rs = r + (long long)dy * W + dx;
+        }
+        if (ok) src = x + rs * ldx + c;
+      }
+      cpa16(u + rl * WG_RS + v * 16, src, ok);
+    }
+    cpa_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int p0 = warp * 32 + ks * 16;
+      uint32_t af[4][4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+        ldsm4t(u + (p0 + av_p) * WG_RS + mt * 32 + av_cb, af[mt][0], af[mt][1], af[mt][2], af[mt][3]);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm4t(u + (p0 + bk_p) * WG_RS + WG_TN * 2 + np * 32 + bk_cb, b0, b1, b2, b3);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          mma16816(acc[mt][2 * np], af[mt], b0, b1);
+          mma16816(acc[mt][2 * np + 1], af[mt], b2, b3);
+        }
+      }
+    }
+  }
+  // cross-warp sum, one 16-row slab (mt) at a time: red[8 warps][16][64] fp32 = 32 KB of the staging buffer
+  float* red = reinterpret_cast<float*>(wg_smem);
+  const int g = lane >> 2, t4 = lane & 3;
+  float* dst = part + (long long)blockIdx.x * N * K;
+#pragma unroll   // static indices: acc stays in registers
+  for (int mt = 0; mt < 4; ++mt) {
+    __syncthreads();
+    float* mine = red + warp * 16 * 64;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int col = nt * 8 + t4 * 2;
+      mine[g * 64 + col] = acc[mt][nt][0];
+      mine[g * 64 + col + 1] = acc[mt][nt][1];
+      mine[(g + 8) * 64 + col] = acc[mt][nt][2];
+      mine[(g + 8) * 64 + col + 1] = acc[mt][nt][3];
+    }
+    __syncthreads();
+    for (int i = tid; i < 16 * 64; i += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w * 16 * 64 + i];
+      const int n = n0 + mt * 16 + (i >> 6), k = k0 + (i & 63);
+      if (n < N && k < K) dst[(long long)n * K + k] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ depthwise conv gradients
+// dx[b,iy,ix,c] = sum_{ky,kx} dz[b,oy,ox,c] w[ky*KS+kx][c] over the (oy, ox) with oy*stride + ky - pad == iy (same for x).
+__global__ void dw_bwd_data_kernel(const bf16* __restrict__ dz, const float* __restrict__ w, bf16* __restrict__ dxo, int B, int H,
+                                   int W, int C, int Ho, int Wo, int ks, int stride) {
+  const int CV = C >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * H * W * CV) return;
+  const int cv = (int)(i % CV);
+  const long long p = i / CV;
+  const int ix = (int)(p % W), iy = (int)((p / W) % H), b = (int)(p / ((long long)W * H));
+  const int pad = ks >> 1;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int ky = 0; ky < ks; ++ky) {
+    const int ty = iy + pad - ky;
+    if (ty < 0 || ty % stride) continue;
+    const int oy = ty / stride;
+    if (oy >= Ho) continue;
+    for (int kx = 0; kx < ks; ++kx) {
+      const int tx = ix + pad - kx;
+      if (tx < 0 || tx % stride) continue;
+      const int ox = tx / stride;
+      if (ox >= Wo) continue;
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dz + (((long long)b * Ho + oy) * Wo + ox) * C + cv * 8)), f);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (long long)(ky * ks + kx) * C + cv * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (long long)(ky * ks + kx) * C + cv * 8 + 4));
+      acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
+      acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+      acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
+      acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+    }
+  }
+  *reinterpret_cast<uint4*>(dxo + p * C + cv * 8) = pack8(acc);
+}
+
+// part[blk][tap][c] = sum over the block's output pixels of dz[p][c] * x[src(p, tap)][c].
+// grid (nblk, ceil(CP / CPB)), block 256: thread = (channel pair, pixel lane).  x may be a channel slice (pixel stride ldx).
+template <int KS>
+__global__ void __launch_bounds__(256) dw_wgrad_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ x, long long ldx, int B,
+                                                       int H, int W, int C, int Ho, int Wo, int stride, int CPB,
+                                                       long long pix_per_block, float* __restrict__ part) {
+  __shared__ float red[256][2];
+  constexpr int KK = KS * KS, PAD = KS / 2;
+  const int tid = threadIdx.x;
+  const int lanes = 256 / CPB;
+  const int cpl = tid % CPB, pl = tid / CPB;
+  const int cp = blockIdx.y * CPB + cpl;
+  const bool active = pl < lanes && cp * 2 < C;
+  float acc[KK][2];
+#pragma unroll
+  for (int t = 0; t < KK; ++t) acc[t][0] = acc[t][1] = 0.f;
+  const long long total = (long long)B * Ho * Wo;
+  const long long p0 = (long long)blockIdx.x * pix_per_block, p1 = min(total, p0 + pix_per_block);
+  if (active) {
+    for (long long p = p0 + pl; p < p1; p += lanes) {
+      const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
+      const float2 g = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(dz + p * C + cp * 2)));
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky) {
+        const int iy = oy * stride + ky - PAD;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          const int ix = ox * stride + kx - PAD;
+          if (ix < 0 || ix >= W) continue;
+          const float2 xv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(x + (((long long)b * H + iy) * W + ix) * ldx + cp * 2)));
+          acc[ky * KS + kx][0] = fmaf(g.x, xv.x, acc[ky * KS + kx][0]);
+          acc[ky * KS + kx][1] = fmaf(g.y, xv.y, acc[ky * KS + kx][1]);
+        }
+      }
+    }
+  }
+  int top = 1;
+  while (top < lanes) top <<= 1;
+#pragma unroll   // static indices keep acc[][] in registers
+  for (int t = 0; t < KK; ++t) {
+    red[tid][0] = acc[t][0];
+    red[tid][1] = acc[t][1];
+    __syncthreads();
+    for (int s = top >> 1; s > 0; s >>= 1) {
+      if (pl < s && pl + s < lanes) {
+        red[tid][0] += red[tid + s * CPB][0];
+        red[tid][1] += red[tid + s * CPB][1];
+      }
+      __syncthreads();
+    }
+    if (pl == 0 && cp * 2 < C) {
+      float* d = part + ((long long)blockIdx.x * KK + t) * C + cp * 2;
+      d[0] = red[tid][0];
+      d[1] = red[tid][1];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ stem conv weight gradient
+// img [B,3,H,W] fp32 NCHW; dz [B,Ho,Wo,COUT] bf16 (3x3, stride 2, pad 1).  part[blk][n][27] with 27 = ci*9 + ky*3 + kx.
+// block = ceil32(COUT * 27) threads: thread = one (n, tap) weight; 64-pixel chunks staged in shared memory.
+constexpr int SW_PX = 64, SW_MAXC = 32;
+__global__ void stem_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ dz, int B, int H, int W, int Ho, int Wo,
+                                  int COUT, int chunks_per_block, float* __restrict__ part) {
+  __shared__ float s_dz[SW_PX][SW_MAXC + 1];
+  __shared__ float s_patch[SW_PX][28];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int n = tid / 27, tap = tid % 27;
+  const bool owner = tid < COUT * 27;
+  const long long total = (long long)B * Ho * Wo;
+  float acc = 0.f;
+  for (int ch = 0; ch < chunks_per_block; ++ch) {
+    const long long p0 = ((long long)blockIdx.x * chunks_per_block + ch) * SW_PX;
+    if (p0 >= total) break;
+    __syncthreads();
+    for (int i = tid; i < SW_PX * COUT; i += nthr) {
+      const int pp = i / COUT, c = i % COUT;
+      const long long p = p0 + pp;
+      s_dz[pp][c] = p < total ? __bfloat162float(dz[p * COUT + c]) : 0.f;
+    }
+    for (int i = tid; i < SW_PX * 27; i += nthr) {
+      const int pp = i / 27, t = i % 27;
+      const long long p = p0 + pp;
+      float v = 0.f;
+      if (p < total) {
+        const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
+        const int ci = t / 9, ky = (t % 9) / 3, kx = t % 3;
+        const int iy = oy * 2 - 1 + ky, ix = ox * 2 - 1 + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((long long)b * 3 + ci) * H + iy) * W + ix);
+      }
+      s_patch[pp][t] = v;
+    }
+    __syncthreads();
+    if (owner) {
+#pragma unroll 8
+      for (int pp = 0; pp < SW_PX; ++pp) acc = fmaf(s_dz[pp][n], s_patch[pp][tap], acc);
+    }
+  }
+  if (owner) part[(long long)blockIdx.x * COUT * 27 + tid] = acc;
+}
+
+// ------------------------------------------------------------------------------------------ bilinear adjoint
+// dout [B,C,Ho,Wo] fp32 NCHW -> din [B,Hi,Wi,C] bf16 NHWC, adjoint of bilinear_nhwc_to_nchw_kernel (same source-index
+// arithmetic).  grid (C/32, Hi, B), block 256: 32 channels x one input row; the result goes through shared memory so
+// the NHWC store is 64-byte contiguous per pixel.
+constexpr int BB_CB = 32;
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ din, int Hi, int Wi, int C,
+                                                           int Ho, int Wo, float sy, float sx) {
+  extern __shared__ float bb_tile[];   // [Wi][BB_CB + 1]
+  const int c0 = blockIdx.x * BB_CB, iy = blockIdx.y, b = blockIdx.z;
+  // candidate output rows: every oy whose source interval [y0, y1] can contain iy
+  int oy_lo = (int)floorf(((float)iy - 1.f + 0.5f) / sy - 0.5f) - 1;
+  int oy_hi = (int)ceilf(((float)iy + 1.f + 0.5f) / sy - 0.5f) + 1;
+  oy_lo = max(oy_lo, 0);
+  oy_hi = min(oy_hi, Ho - 1);
+  for (int idx = threadIdx.x; idx < BB_CB * Wi; idx += 256) {
+    const int ix = idx % Wi, cl = idx / Wi;
+    const int c = c0 + cl;
+    float acc = 0.f;
+    if (c < C) {
+      int ox_lo = (int)floorf(((float)ix - 1.f + 0.5f) / sx - 0.5f) - 1;
+      int ox_hi = (int)ceilf(((float)ix + 1.f + 0.5f) / sx - 0.5f) + 1;
+      ox_lo = max(ox_lo, 0);
+      ox_hi = min(ox_hi, Wo - 1);
+      const float* plane = dout + ((long long)b * C + c) * Ho * Wo;
+      for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        float fy = (oy + 0.5f) * sy - 0.5f;
+        if (fy < 0.f) fy = 0.f;
+        const int y0 = min((int)fy, Hi - 1), y1 = min(y0 + 1, Hi - 1);
+        const float ly = fy - (float)y0, hy = 1.f - ly;
+        const float wy = (y0 == iy ? hy : 0.f) + (y1 == iy ? ly : 0.f);
+        if (wy == 0.f) continue;
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+          float fx = (ox + 0.5f) * sx - 0.5f;
+          if (fx < 0.f) fx = 0.f;
+          const int x0 = min((int)fx, Wi - 1), x1 = min(x0 + 1, Wi - 1);
+          const float lx = fx - (float)x0, hx = 1.f - lx;
+          const float wx = (x0 == ix ? hx : 0.f) + (x1 == ix ? lx : 0.f);
+          if (wx != 0.f) acc = fmaf(wy * wx, __ldg(plane + (long long)oy * Wo + ox), acc);
+        }
+      }
+    }
+    bb_tile[ix * (BB_CB + 1) + cl] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < BB_CB * Wi; idx += 256) {
+    const int cl = idx % BB_CB, ix = idx / BB_CB;
+    if (c0 + cl < C) din[(((long long)b * Hi + iy) * Wi + ix) * C + c0 + cl] = __float2bfloat16(bb_tile[ix * (BB_CB + 1) + cl]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ LiteMLA attention backward
+// Forward (ops.py:592-621, head dim 16): q' = relu(q), k' = relu(k), vpad = [v, 1]; KV[j][i] = sum_n vpad[n][j] k'[n][i]
+// (17 x 16); o[n][j] = sum_i KV[j][i] q'[n][i]; y[n][j] = o[n][j] / (o[n][16] + eps), j < 16.
+// Backward, with r = 1 / (o16 + eps):   do[j] = dy[j] r (j < 16),  do[16] = -r sum_j dy[j] y[j]
+//   dKV[j][i] = sum_n do[n][j] q'[n][i];  dq'[i] = sum_j KV[j][i] do[j];  dv[j] = sum_i dKV[j][i] k'[i];
+//   dk'[i] = sum_j vpad[j] dKV[j][i];  dq = dq' [q > 0], dk = dk' [k > 0].
+// ms [B][HW][ld] bf16 with head h at channels [48 h, 48 h + 48) = q | k | v; dy [B][HW][lddy] bf16, head h at [16 h, +16).
+constexpr int LB_PX = 128;
+
+__device__ __forceinline__ void load16(const bf16* p, float* f) {
+  unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(p) + 1), f + 8);
+}
+
+__device__ __forceinline__ void sum_kv_partials(const float* __restrict__ src, int nchunk, float* s_dst, int tid, int nthr) {
+  for (int i = tid; i < 17 * 16; i += nthr) {
+    float a = 0.f;
+    for (int c = 0; c < nchunk; ++c) a += src[(long long)c * 17 * 16 + i];
+    s_dst[i] = a;
+  }
+}
+
+// do[0..16] for one token from q' (fp32, already relu'd), dy and KV
+__device__ __forceinline__ void token_do(const float* skv, const float* q, const float* dy, float eps, float* dof) {
+  float o[17];
+#pragma unroll
+  for (int j = 0; j < 17; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a = fmaf(skv[j * 16 + i], q[i], a);
+    o[j] = a;
+  }
+  const float r = 1.f / (o[16] + eps);
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    dof[j] = dy[j] * r;
+    dot = fmaf(dy[j], o[j] * r, dot);
+  }
+  dof[16] = -r * dot;
+}
+
+// grid (ceil(HW / 128), heads2, B), block 288.  dkv_part [B][heads2][nchunk_b][17][16].
+__global__ void __launch_bounds__(288) litemla_dkv_kernel(const bf16* __restrict__ ms, long long ld, const bf16* __restrict__ dy,
+                                                          long long lddy, const float* __restrict__ kv_part, int nchunk_f,
+                                                          float* __restrict__ dkv_part, int HW, float eps) {
+  __shared__ float skv[17 * 16];
+  __shared__ float s_q[LB_PX][17];
+  __shared__ float s_do[LB_PX][17];
+  const int tid = threadIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z, heads2 = gridDim.y;
+  sum_kv_partials(kv_part + ((long long)b * heads2 + h) * nchunk_f * 17 * 16, nchunk_f, skv, tid, 288);
+  __syncthreads();
+  if (tid < LB_PX) {
+    const int n = blockIdx.x * LB_PX + tid;
+    float q[16], dyv[16], dof[17];
+    if (n < HW) {
+      load16(ms + ((long long)b * HW + n) * ld + h * 48, q);
+      load16(dy + ((long long)b * HW + n) * lddy + h * 16, dyv);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) q[i] = fmaxf(q[i], 0.f);
+      token_do(skv, q, dyv, eps, dof);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) q[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 17; ++j) dof[j] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s_q[tid][i] = q[i];
+#pragma unroll
+    for (int j = 0; j < 17; ++j) s_do[tid][j] = dof[j];
+  }
+  __syncthreads();
+  if (tid < 17 * 16) {
+    const int j = tid >> 4, i = tid & 15;
+    float a = 0.f;
+#pragma unroll 8
+    for (int n = 0; n < LB_PX; ++n) a = fmaf(s_do[n][j], s_q[n][i], a);
+    dkv_part[(((long long)b * heads2 + h) * gridDim.x + blockIdx.x) * 17 * 16 + tid] = a;
+  }
+}
+
+// grid (ceil(HW / 128), heads2, B), block 128: thread = token.  dms [B][HW][ld] bf16 (same layout as ms).
+__global__ void __launch_bounds__(128) litemla_dqkv_kernel(const bf16* __restrict__ ms, long long ld, const bf16* __restrict__ dy,
+                                                           long long lddy, const float* __restrict__ kv_part, int nchunk_f,
+                                                           const float* __restrict__ dkv_part, int nchunk_b, bf16* __restrict__ dms,
+                                                           long long lddms, int HW, float eps) {
+  __shared__ float skv[17 * 16];
+  __shared__ float sdkv[17 * 16];
+  const int tid = threadIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z, heads2 = gridDim.y;
+  sum_kv_partials(kv_part + ((long long)b * heads2 + h) * nchunk_f * 17 * 16, nchunk_f, skv, tid, 128);
+  sum_kv_partials(dkv_part + ((long long)b * heads2 + h) * nchunk_b * 17 * 16, nchunk_b, sdkv, tid, 128);
+  __syncthreads();
+  const int n = blockIdx.x * LB_PX + tid;
+  if (n >= HW) return;
+  const bf16* row = ms + ((long long)b * HW + n) * ld + h * 48;
+  float q[16], k[16], v[16], dyv[16], dof[17], qr[16];
+  load16(row, q);
+  load16(row + 16, k);
+  load16(row + 32, v);
+  load16(dy + ((long long)b * HW + n) * lddy + h * 16, dyv);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) qr[i] = fmaxf(q[i], 0.f);
+  token_do(skv, qr, dyv, eps, dof);
+  float dq[16], dk[16], dv[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 17; ++j) a = fmaf(skv[j * 16 + i], dof[j], a);
+    dq[i] = q[i] > 0.f ? a : 0.f;
+    float c = sdkv[16 * 16 + i];               // vpad[16] = 1
+#pragma unroll
+    for (int j = 0; j < 16; ++j) c = fmaf(v[j], sdkv[j * 16 + i], c);
+    dk[i] = k[i] > 0.f ? c : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a = fmaf(sdkv[j * 16 + i], fmaxf(k[i], 0.f), a);
+    dv[j] = a;
+  }
+  uint4* o = reinterpret_cast<uint4*>(dms + ((long long)b * HW + n) * lddms + h * 48);
+  o[0] = pack8(dq); o[1] = pack8(dq + 8);
+  o[2] = pack8(dk); o[3] = pack8(dk + 8);
+  o[4] = pack8(dv); o[5] = pack8(dv + 8);
+}
+
+static int pick_blocks(long long rows, int lanes, int max_blocks) {
+  // enough blocks to fill the GPU, but at least ~64 rows per lane and block so the per-block tail stays small
+  long long want = (rows + (long long)lanes * 64 - 1) / ((long long)lanes * 64);
+  if (want < 1) want = 1;
+  if (want > max_blocks) want = max_blocks;
+  return (int)want;
+}
+
+}  // namespace
+}  // namespace es3
+
+using namespace es3;
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" long long es3_col_reduce_ws_floats(long long M, int C) {
+  const int CV = C / 8, CVB = CV < CR_THREADS ? CV : CR_THREADS;
+  const int nblk = pick_blocks(M, CR_THREADS / (CVB > 0 ? CVB : 1), 1184);
+  return (long long)nblk * 2 * C;
+}
+
+static int col_reduce_geometry(long long M, int C, int* CVB, int* nblk, long long* rpb, int* gy) {
+  const int CV = C / 8;
+  *CVB = CV < CR_THREADS ? CV : CR_THREADS;
+  *nblk = pick_blocks(M, CR_THREADS / *CVB, 1184);
+  *rpb = (M + *nblk - 1) / *nblk;
+  *gy = (CV + *CVB - 1) / *CVB;
+  return 0;
+}
+
+extern "C" int es3_bn_stats(const void* z, long long M, int C, float eps, float momentum, const float* gamma, const float* beta,
+                            float* ws, float* mean, float* invstd, float* scale, float* shift, float* running_mean,
+                            float* running_var, long long* num_batches_tracked, void* stream) {
+  ES3_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "es3_bn_stats: need M > 0 and C %% 8 == 0 (M=%lld C=%d)", M, C);
+  ES3_REQUIRE(((uintptr_t)z & 15) == 0, "es3_bn_stats: z must be 16-byte aligned");
+  int CVB, nblk, gy;
+  long long rpb;
+  col_reduce_geometry(M, C, &CVB, &nblk, &rpb, &gy);
+  cudaStream_t st = (cudaStream_t)stream;
+  col_reduce_kernel<ACT_NONE, true><<<dim3(nblk, gy), CR_THREADS, 0, st>>>((const bf16*)z, nullptr, nullptr, nullptr, M, C, CVB, rpb, ws);
+  ES3_LAUNCH_CHECK("col_reduce_kernel<stats>");
+  bn_stats_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, nblk, C, M, eps, momentum, gamma, beta, mean, invstd, scale, shift,
+                                                            running_mean, running_var, num_batches_tracked);
+  ES3_LAUNCH_CHECK("bn_stats_finalize_kernel");
+  return 0;
+}
+
+extern "C" int es3_affine_act(const void* z, const float* scale, const float* shift, int act, const void* residual, void* out,
+                              long long M, int C, void* stream) {
+  ES3_REQUIRE(M > 0 && C % 8 == 0, "es3_affine_act: need C %% 8 == 0 (C=%d)", C);
+  const long long total = M * (C / 8);
+  const unsigned blocks = (unsigned)ceil_div(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  ES3_DISPATCH_ACT(act, A, {
+    affine_act_kernel<A><<<blocks, 256, 0, st>>>((const bf16*)z, scale, shift, (const bf16*)residual, (bf16*)out, total, C / 8);
+  })
+  ES3_LAUNCH_CHECK("affine_act_kernel");
+  return 0;
+}
+
+extern "C" int es3_bn_act_bwd_reduce(const void* da, const void* z, const float* scale, const float* shift, int act, int mode,
+                                     const float* mean, const float* invstd, long long M, int C, float* ws, float* coef,
+                                     float* dgamma, float* dbeta, void* stream) {
+  ES3_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "es3_bn_act_bwd_reduce: need C %% 8 == 0 (C=%d)", C);
+  ES3_REQUIRE(mode >= 0 && mode <= 2, "es3_bn_act_bwd_reduce: mode %d", mode);
+  ES3_REQUIRE(mode == 0 || (mean && invstd), "es3_bn_act_bwd_reduce: BN modes need mean / invstd");
+  int CVB, nblk, gy;
+  long long rpb;
+  col_reduce_geometry(M, C, &CVB, &nblk, &rpb, &gy);
+  cudaStream_t st = (cudaStream_t)stream;
+  ES3_DISPATCH_ACT_BWD(act, A, {
+    col_reduce_kernel<A, false><<<dim3(nblk, gy), CR_THREADS, 0, st>>>((const bf16*)z, (const bf16*)da, scale, shift, M, C, CVB, rpb, ws);
+  })
+  ES3_LAUNCH_CHECK("col_reduce_kernel<bwd>");
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, nblk, C, M, mode, scale, mean, invstd, coef, dgamma, dbeta);
+  ES3_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+  return 0;
+}
+
+extern "C" int es3_bn_act_bwd_apply(const void* da, const void* z, const float* scale, const float* shift, int act,
+                                    const float* coef, void* dz, long long M, int C, void* stream) {
+  ES3_REQUIRE(M > 0 && C % 8 == 0, "es3_bn_act_bwd_apply: need C %% 8 == 0 (C=%d)", C);
+  const long long total = M * (C / 8);
+  const unsigned blocks = (unsigned)ceil_div(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  ES3_DISPATCH_ACT_BWD(act, A, {
+    bn_act_bwd_apply_kernel<A><<<blocks, 256, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, coef, (bf16*)dz, total, C / 8);
+  })
+  ES3_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
+  return 0;
+}
+
+extern "C" int es3_add_bf16(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, long long M, int C,
+                            void* stream) {
+  ES3_REQUIRE(M > 0 && C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0, "es3_add_bf16: C / strides must be multiples of 8");
+  const long long total = M * (C / 8);
+  add_bf16_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)out,
+                                                                                    ldo, M, C / 8);
+  ES3_LAUNCH_CHECK("add_bf16_kernel");
+  return 0;
+}
+
+static int wgrad_splits(long long M, int N, int K) {
+  const long long nchunks = (M + WG_ROWS - 1) / WG_ROWS;
+  const long long tiles = (long long)ceil_div(N, WG_TN) * ceil_div(K, WG_TK);
+  long long s = (2 * 148 + tiles - 1) / tiles;
+  if (s > nchunks) s = nchunks;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+extern "C" long long es3_wgrad_pw_ws_floats(long long M, int N, int K) { return (long long)wgrad_splits(M, N, K) * N * K; }
+
+/* dW[n * ldn + k * ldk] += sum_m dz[m][n] * x[shift(m)][k] */
+extern "C" int es3_wgrad_pw(const void* dz, long long lddz, const void* x, long long ldx, long long M, int N, int K, int H, int W,
+                            int dy, int dx, float* ws, float* dW, long long ldn, long long ldk, void* stream) {
+  ES3_REQUIRE(M > 0 && N % 8 == 0 && K % 8 == 0 && lddz % 8 == 0 && ldx % 8 == 0, "es3_wgrad_pw: N/K/strides must be multiples of 8 (N=%d K=%d)", N, K);
+  ES3_REQUIRE(((uintptr_t)dz & 15) == 0 && ((uintptr_t)x & 15) == 0, "es3_wgrad_pw: operands must be 16-byte aligned");
+  ES3_REQUIRE((H == 0 && dy == 0 && dx == 0) || (H > 0 && W > 0 && M % ((long long)H * W) == 0), "es3_wgrad_pw: bad shift geometry");
+  static bool configured = false;
+  if (!configured) {
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(wgrad_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+    configured = true;
+  }
+  const int splits = wgrad_splits(M, N, K);
+  cudaStream_t st = (cudaStream_t)stream;
+  wgrad_pw_kernel<<<dim3(splits, ceil_div(N, WG_TN), ceil_div(K, WG_TK)), 256, WG_SMEM, st>>>((const bf16*)dz, lddz, (const bf16*)x, ldx, M,
+                                                                                             N, K, H, W, dy, dx, ws);
+  ES3_LAUNCH_CHECK("wgrad_pw_kernel");
+  const long long n = (long long)N * K;
+  sum_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ws, splits, n, K, ldn, ldk, dW);
+  ES3_LAUNCH_CHECK("sum_partials_kernel");
+  return 0;
+}
+
+extern "C" int es3_dwconv_bwd_data(const void* dz, const float* w, void* dx, int B, int H, int W, int C, int ks, int stride,
+                                   void* stream) {
+  ES3_REQUIRE(C % 8 == 0 && (ks == 3 || ks == 5) && (stride == 1 || stride == 2), "es3_dwconv_bwd_data: unsupported C=%d ks=%d stride=%d", C, ks, stride);
+  const int pad = ks / 2;
+  const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
+  const long long total = (long long)B * H * W * (C / 8);
+  dw_bwd_data_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dz, w, (bf16*)dx, B, H, W, C, Ho, Wo,
+                                                                                       ks, stride);
+  ES3_LAUNCH_CHECK("dw_bwd_data_kernel");
+  return 0;
+}
+
+static int dw_wgrad_geometry(int B, int Ho, int Wo, int C, int* CPB, int* nblk, long long* ppb, int* gy) {
+  const int CP = C / 2;
+  *CPB = CP < 256 ? CP : 256;
+  const long long total = (long long)B * Ho * Wo;
+  *nblk = pick_blocks(total, 256 / *CPB, 1184);
+  *ppb = (total + *nblk - 1) / *nblk;
+  *gy = (CP + *CPB - 1) / *CPB;
+  return 0;
+}
+
+extern "C" long long es3_dwconv_wgrad_ws_floats(int B, int H, int W, int C, int ks, int stride) {
+  const int pad = ks / 2;
+  const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
+  int CPB, nblk, gy;
+  long long ppb;
+  dw_wgrad_geometry(B, Ho, Wo, C, &CPB, &nblk, &ppb, &gy);
+  return (long long)nblk * ks * ks * C;
+}
+
+/* dW[c * ks*ks + tap] += sum_p dz[p][c] x[src(p, tap)][c]   (torch layout [C,1,ks,ks]) */
+extern "C" int es3_dwconv_wgrad(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, int stride, float* ws,
+                                float* dW, void* stream) {
+  ES3_REQUIRE(C % 2 == 0 && ldx % 2 == 0 && (ks == 3 || ks == 5) && (stride == 1 || stride == 2),
+              "es3_dwconv_wgrad: unsupported C=%d ks=%d stride=%d", C, ks, stride);
+  const int pad = ks / 2;
+  const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
+  int CPB, nblk, gy;
+  long long ppb;
+  dw_wgrad_geometry(B, Ho, Wo, C, &CPB, &nblk, &ppb, &gy);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ks == 3)
+    dw_wgrad_kernel<3><<<dim3(nblk, gy), 256, 0, st>>>((const bf16*)dz, (const bf16*)x, ldx, B, H, W, C, Ho, Wo, stride, CPB, ppb, ws);
+  else
+    dw_wgrad_kernel<5><<<dim3(nblk, gy), 256, 0, st>>>((const bf16*)dz, (const bf16*)x, ldx, B, H, W, C, Ho, Wo, stride, CPB, ppb, ws);
+  ES3_LAUNCH_CHECK("dw_wgrad_kernel");
+  const long long n = (long long)ks * ks * C;
+  // part index i = tap * C + c  ->  dW[c * ks*ks + tap]
+  sum_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ws, nblk, n, C, 1, (long long)ks * ks, dW);
+  ES3_LAUNCH_CHECK("sum_partials_kernel");
+  return 0;
+}
+
+static int stem_wgrad_blocks(int B, int Ho, int Wo, int* chunks_per_block) {
+  const long long total = (long long)B * Ho * Wo;
+  const long long chunks = (total + SW_PX - 1) / SW_PX;
+  long long nblk = chunks < 592 ? chunks : 592;
+  *chunks_per_block = (int)((chunks + nblk - 1) / nblk);
+  return (int)((chunks + *chunks_per_block - 1) / *chunks_per_block);
+}
+
+extern "C" long long es3_stem_wgrad_ws_floats(int B, int H, int W, int Cout) {
+  int cpb;
+  const int nblk = stem_wgrad_blocks(B, (H - 1) / 2 + 1, (W - 1) / 2 + 1, &cpb);
+  return (long long)nblk * Cout * 27;
+}
+
+/* dW[n][ci][ky][kx] += sum_p dz[p][n] img[b][ci][2 oy - 1 + ky][2 ox - 1 + kx] */
+extern "C" int es3_stem_wgrad(const float* img, const void* dz, int B, int H, int W, int Cout, float* ws, float* dW, void* stream) {
+  ES3_REQUIRE(Cout > 0 && Cout <= SW_MAXC, "es3_stem_wgrad: Cout=%d not supported (<= %d)", Cout, SW_MAXC);
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  int cpb;
+  const int nblk = stem_wgrad_blocks(B, Ho, Wo, &cpb);
+  const int threads = ((Cout * 27 + 31) / 32) * 32;
+  cudaStream_t st = (cudaStream_t)stream;
+  stem_wgrad_kernel<<<nblk, threads, 0, st>>>(img, (const bf16*)dz, B, H, W, Ho, Wo, Cout, cpb, ws);
+  ES3_LAUNCH_CHECK("stem_wgrad_kernel");
+  const long long n = (long long)Cout * 27;
+  sum_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ws, nblk, n, 27, 27, 1, dW);
+  ES3_LAUNCH_CHECK("sum_partials_kernel");
+  return 0;
+}
+
+extern "C" int es3_bilinear_bwd(const float* dout, void* din, int B, int Hi, int Wi, int C, int Ho, int Wo, void* stream) {
+  ES3_REQUIRE(B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0, "es3_bilinear_bwd: bad shape");
+  const int smem = Wi * (BB_CB + 1) * (int)sizeof(float);
+  ES3_REQUIRE(smem <= 48 * 1024, "es3_bilinear_bwd: Wi=%d too wide for the row tile", Wi);
+  bilinear_bwd_kernel<<<dim3(ceil_div(C, BB_CB), Hi, B), 256, smem, (cudaStream_t)stream>>>(dout, (bf16*)din, Hi, Wi, C, Ho, Wo,
+                                                                                          (float)Hi / (float)Ho, (float)Wi / (float)Wo);
+  ES3_LAUNCH_CHECK("bilinear_bwd_kernel");
+  return 0;
+}
+
+extern "C" long long es3_litemla_bwd_ws_floats(int B, int HW, int heads2) {
+  return (long long)B * heads2 * ceil_div(HW, LB_PX) * 17 * 16;
+}
+
+/* kv_part: the [B][heads2][nchunk_f][17][16] partial KV sums es3_litemla_attn[_tc] left in its workspace
+ * (nchunk_f = ceil(HW / 512)). */
+extern "C" int es3_litemla_attn_bwd(const void* ms, long long ld, const void* dy, long long lddy, const float* kv_part, int nchunk_f,
+                                    float* dkv_ws, void* dms, long long lddms, int B, int HW, int heads2, float eps, void* stream) {
+  ES3_REQUIRE(ld >= 48 * heads2 && ld % 8 == 0 && lddy % 8 == 0 && lddms % 8 == 0 && lddy >= 16 * heads2 && lddms >= 48 * heads2,
+              "es3_litemla_attn_bwd: bad strides ld=%lld lddy=%lld lddms=%lld heads2=%d", ld, lddy, lddms, heads2);
+  ES3_REQUIRE(nchunk_f == ceil_div(HW, 512), "es3_litemla_attn_bwd: kv_part must come from es3_litemla_attn (nchunk %d != %d)", nchunk_f,
+              ceil_div(HW, 512));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunk_b = ceil_div(HW, LB_PX);
+  dim3 grid(nchunk_b, heads2, B);
+  litemla_dkv_kernel<<<grid, 288, 0, st>>>((const bf16*)ms, ld, (const bf16*)dy, lddy, kv_part, nchunk_f, dkv_ws, HW, eps);
+  ES3_LAUNCH_CHECK("litemla_dkv_kernel");
+  litemla_dqkv_kernel<<<grid, 128, 0, st>>>((const bf16*)ms, ld, (const bf16*)dy, lddy, kv_part, nchunk_f, dkv_ws, nchunk_b, (bf16*)dms,
+                                            lddms, HW, eps);
+  ES3_LAUNCH_CHECK("litemla_dqkv_kernel");
+  return 0;
+}

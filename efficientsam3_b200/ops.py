@@ -281,8 +281,9 @@ def litemla_aggreg_dwpw(ms, wd, wp, C3):
     return ms
 
 
-def litemla_attn(ms, heads2, eps=1e-15, tc=True):
-    """ms: [B,H,W,48*heads2] bf16 -> att [B,H,W,16*heads2] bf16."""
+def litemla_attn(ms, heads2, eps=1e-15, tc=True, return_kv=False):
+    """ms: [B,H,W,48*heads2] bf16 -> att [B,H,W,16*heads2] bf16.  return_kv: also return the workspace holding the
+    [B][heads2][ceil(HW/512)][17][16] partial KV sums (es3_litemla_attn_bwd consumes it)."""
     _chk(ms, torch.bfloat16, "ms")
     _ensure_init(ms)
     assert ms.is_contiguous()
@@ -292,7 +293,7 @@ def litemla_attn(ms, heads2, eps=1e-15, tc=True):
     _call("es3_litemla_attn_tc" if tc else "es3_litemla_attn", "litemla_attn_tc" if tc else "litemla_attn", _nb(ms) * 2 // 3 + _nb(ms) // 3 + _nb(att), 2 * B * H * W * heads2 * 17 * 16 * 2,
           ms.data_ptr(), ld, kv.data_ptr(), att.data_ptr(), att.shape[3], B, H * W, heads2,
               float(eps), _stream())
-    return att
+    return (att, kv) if return_kv else att
 
 
 def litemla_attn_generic(ms, heads2, dim, eps=1e-15):
@@ -722,3 +723,161 @@ def win_attn_bias(qkv, qkv_pad, bias, B, H, W, C, heads, ws, scale):
     _call("es3_win_attn_bias_bf16", f"win_attn_bias[ws={ws}]", _nb(qkv, out), 4 * B * H * W * ws * ws * C, qkv.data_ptr(),
           qkv_pad.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, C, heads, ws, float(scale), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------ student backward (train_bwd.cu)
+BN_MODE = {"none": 0, "eval": 1, "batch": 2}
+KERNELS_PER_CALL.update({"es3_bn_stats": 2, "es3_bn_act_bwd_reduce": 2, "es3_wgrad_pw": 2, "es3_dwconv_wgrad": 2,
+                         "es3_stem_wgrad": 2, "es3_litemla_attn_bwd": 2})
+
+
+def _f32ws(n, dev):
+    return torch.empty((max(int(n), 1),), device=dev, dtype=torch.float32)
+
+
+def bn_stats(z, gamma, beta, eps, momentum, running_mean=None, running_var=None, num_batches_tracked=None):
+    """Train-mode BatchNorm statistics of z [M,C] bf16 (any leading dims, C last, contiguous).
+    Returns (mean, invstd, scale, shift) fp32 [C]; updates the running buffers in place (nn.BatchNorm2d semantics)."""
+    _chk(z, torch.bfloat16, "z")
+    _ensure_init(z)
+    assert z.is_contiguous()
+    C = z.shape[-1]
+    M = z.numel() // C
+    dev = z.device
+    mean, invstd, scale, shift = (torch.empty(C, device=dev, dtype=torch.float32) for _ in range(4))
+    ws = _f32ws(_lib.size("es3_col_reduce_ws_floats", M, C), dev)
+    for t in (running_mean, running_var):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    assert num_batches_tracked is None or num_batches_tracked.dtype == torch.int64
+    _call("es3_bn_stats", "bn_stats", _nb(z), 3 * z.numel(), z.data_ptr(), M, C, float(eps), float(momentum), _ptr(gamma),
+          _ptr(beta), ws.data_ptr(), mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+          _ptr(running_mean), _ptr(running_var), _ptr(num_batches_tracked), _stream())
+    return mean, invstd, scale, shift
+
+
+def affine_act(z, scale, shift, act, residual=None):
+    """act(scale[c] z + shift[c]) (+ residual) on [..., C] bf16 contiguous."""
+    _chk(z, torch.bfloat16, "z")
+    _ensure_init(z)
+    assert z.is_contiguous() and (residual is None or (residual.is_contiguous() and residual.shape == z.shape))
+    C = z.shape[-1]
+    out = torch.empty_like(z)
+    _call("es3_affine_act", "affine_act", _nb(z, out, residual), 4 * z.numel(), z.data_ptr(), _ptr(scale), _ptr(shift), ACT[act],
+          _ptr(residual), out.data_ptr(), z.numel() // C, C, _stream())
+    return out
+
+
+def bn_act_bwd(da, z, scale, shift, act, mode, mean=None, invstd=None, dgamma=None, dbeta=None):
+    """Backward through act(scale z + shift) and the norm that produced (scale, shift); see es3_bn_act_bwd_reduce.
+    da, z: [..., C] bf16 contiguous.  dgamma / dbeta: fp32 [C] accumulated in place (None: not needed).  Returns dz bf16."""
+    _chk(da, torch.bfloat16, "da"); _chk(z, torch.bfloat16, "z")
+    _ensure_init(z)
+    assert da.is_contiguous() and z.is_contiguous() and da.shape == z.shape
+    C = z.shape[-1]
+    M = z.numel() // C
+    dev = z.device
+    ws = _f32ws(_lib.size("es3_col_reduce_ws_floats", M, C), dev)
+    coef = torch.empty((3, C), device=dev, dtype=torch.float32)
+    _call("es3_bn_act_bwd_reduce", "bn_act_bwd_reduce", _nb(da, z), 6 * z.numel(), da.data_ptr(), z.data_ptr(), _ptr(scale),
+          _ptr(shift), ACT[act], BN_MODE[mode], _ptr(mean), _ptr(invstd), M, C, ws.data_ptr(), coef.data_ptr(), _ptr(dgamma),
+          _ptr(dbeta), _stream())
+    dz = torch.empty_like(z)
+    _call("es3_bn_act_bwd_apply", "bn_act_bwd_apply", _nb(da, z, dz), 8 * z.numel(), da.data_ptr(), z.data_ptr(), _ptr(scale),
+          _ptr(shift), ACT[act], coef.data_ptr(), dz.data_ptr(), M, C, _stream())
+    return dz
+
+
+def add_bf16(a, b):
+    """a + b for 2-D bf16 matrices with unit column stride (row-strided views allowed) -> contiguous bf16."""
+    _chk(a, torch.bfloat16, "a"); _chk(b, torch.bfloat16, "b")
+    _ensure_init(a)
+    assert a.dim() == 2 and a.shape == b.shape and a.stride(1) == 1 and b.stride(1) == 1
+    M, C = a.shape
+    out = torch.empty((M, C), device=a.device, dtype=torch.bfloat16)
+    _call("es3_add_bf16", "add_bf16", 3 * M * C * 2, M * C, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
+          out.stride(0), M, C, _stream())
+    return out
+
+
+def wgrad_pw(dz, x, dW, ldn=None, ldk=1, shift=None):
+    """dW[n*ldn + k*ldk] += sum_m dz[m,n] x[m,k].  dz [M,N], x [M,K] bf16 (row strides allowed); dW fp32 (flat indexing
+    from its data pointer).  shift = (H, W, dy, dx): x row of pixel (b,y,x) is (b,y+dy,x+dx), zero outside the map."""
+    _chk(dz, torch.bfloat16, "dz"); _chk(x, torch.bfloat16, "x"); _chk(dW, torch.float32, "dW")
+    _ensure_init(dz)
+    assert dz.dim() == 2 and x.dim() == 2 and dz.stride(1) == 1 and x.stride(1) == 1 and dz.shape[0] == x.shape[0]
+    M, N = dz.shape
+    K = x.shape[1]
+    H, W, dy, dx = shift if shift is not None else (0, 0, 0, 0)
+    ws = _f32ws(_lib.size("es3_wgrad_pw_ws_floats", M, N, K), dz.device)
+    _call("es3_wgrad_pw", f"wgrad_pw[N={N},K={K}]", M * (N + K) * 2, 2 * M * N * K, dz.data_ptr(), dz.stride(0), x.data_ptr(),
+          x.stride(0), M, N, K, H, W, dy, dx, ws.data_ptr(), dW.data_ptr(), K if ldn is None else ldn, ldk, _stream())
+    return dW
+
+
+def dwconv_bwd_data(dz, w, H, W, ks, stride):
+    """Input gradient of a depthwise conv (pad ks//2): dz [B,Ho,Wo,C] bf16, w [ks*ks, C] fp32 -> dx [B,H,W,C] bf16."""
+    _chk(dz, torch.bfloat16, "dz"); _chk(w, torch.float32, "w")
+    _ensure_init(dz)
+    assert dz.is_contiguous() and w.is_contiguous()
+    B, Ho, Wo, C = dz.shape
+    pad = ks // 2
+    assert Ho == (H + 2 * pad - ks) // stride + 1 and Wo == (W + 2 * pad - ks) // stride + 1
+    dx = torch.empty((B, H, W, C), device=dz.device, dtype=torch.bfloat16)
+    _call("es3_dwconv_bwd_data", f"dwconv_bwd_data{ks}x{ks}s{stride}", _nb(dz, dx), 2 * dz.numel() * ks * ks, dz.data_ptr(),
+          w.data_ptr(), dx.data_ptr(), B, H, W, C, ks, stride, _stream())
+    return dx
+
+
+def dwconv_wgrad(dz, x, dW, ks, stride):
+    """dW [C,1,ks,ks] fp32 += depthwise weight gradient; dz [B,Ho,Wo,C] bf16 contiguous, x [B,H,W,C] bf16 (channel slice ok)."""
+    _chk(dz, torch.bfloat16, "dz"); _chk(x, torch.bfloat16, "x"); _chk(dW, torch.float32, "dW")
+    _ensure_init(dz)
+    B, H, W, C = x.shape
+    assert dz.is_contiguous() and dW.is_contiguous() and dW.numel() == C * ks * ks and dz.shape[3] == C
+    assert x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1)
+    ws = _f32ws(_lib.size("es3_dwconv_wgrad_ws_floats", B, H, W, C, ks, stride), dz.device)
+    _call("es3_dwconv_wgrad", f"dwconv_wgrad{ks}x{ks}s{stride}", _nb(dz) + B * H * W * C * 2, 2 * dz.numel() * ks * ks,
+          dz.data_ptr(), x.data_ptr(), x.stride(2), B, H, W, C, ks, stride, ws.data_ptr(), dW.data_ptr(), _stream())
+    return dW
+
+
+def stem_wgrad(img, dz, dW):
+    """dW [Cout,3,3,3] fp32 += weight gradient of the 3x3 stride-2 stem conv; img [B,3,H,W] fp32, dz [B,Ho,Wo,Cout] bf16."""
+    _chk(img, torch.float32, "img"); _chk(dz, torch.bfloat16, "dz"); _chk(dW, torch.float32, "dW")
+    _ensure_init(dz)
+    img = img.contiguous()
+    B, _, H, W = img.shape
+    Cout = dz.shape[3]
+    assert dz.is_contiguous() and dW.is_contiguous() and dW.numel() == Cout * 27
+    ws = _f32ws(_lib.size("es3_stem_wgrad_ws_floats", B, H, W, Cout), dz.device)
+    _call("es3_stem_wgrad", "stem_wgrad", _nb(img, dz), 2 * dz.numel() * 27, img.data_ptr(), dz.data_ptr(), B, H, W, Cout,
+          ws.data_ptr(), dW.data_ptr(), _stream())
+    return dW
+
+
+def bilinear_bwd(dout, Hi, Wi):
+    """Adjoint of bilinear_nhwc_to_nchw: dout [B,C,Ho,Wo] fp32 -> [B,Hi,Wi,C] bf16."""
+    _chk(dout, torch.float32, "dout")
+    _ensure_init(dout)
+    dout = dout.contiguous()
+    B, C, Ho, Wo = dout.shape
+    din = torch.empty((B, Hi, Wi, C), device=dout.device, dtype=torch.bfloat16)
+    _call("es3_bilinear_bwd", "bilinear_bwd", _nb(dout, din), 8 * dout.numel(), dout.data_ptr(), din.data_ptr(), B, Hi, Wi, C, Ho, Wo,
+          _stream())
+    return din
+
+
+def litemla_attn_bwd(ms, datt, kv, heads2, eps=1e-15):
+    """Backward of litemla_attn (head dim 16).  ms [B,H,W,48*heads2] bf16, datt [B,H,W,16*heads2] bf16, kv: the workspace
+    litemla_attn(..., return_kv=True) returned.  Returns dms [B,H,W,48*heads2] bf16."""
+    _chk(ms, torch.bfloat16, "ms"); _chk(datt, torch.bfloat16, "datt"); _chk(kv, torch.float32, "kv")
+    _ensure_init(ms)
+    assert ms.is_contiguous() and datt.is_contiguous()
+    B, H, W, ld = ms.shape
+    HW = H * W
+    dms = torch.empty_like(ms)
+    ws = _f32ws(_lib.size("es3_litemla_bwd_ws_floats", B, HW, heads2), ms.device)
+    _call("es3_litemla_attn_bwd", "litemla_attn_bwd", 2 * _nb(ms, datt) + _nb(dms), 2 * B * HW * heads2 * 17 * 16 * 5,
+          ms.data_ptr(), ld, datt.data_ptr(), datt.shape[3], kv.data_ptr(), (HW + 511) // 512, ws.data_ptr(), dms.data_ptr(), ld,
+          B, HW, heads2, float(eps), _stream())
+    return dms

@@ -274,6 +274,59 @@ int es3_adamw_flat(float* p, const float* g, float* m, float* v, long long n, lo
                    float beta2, float eps, float weight_decay, float max_norm, float inv_world, const float* norm_ws,
                    float* state, int dynamic_scale, float growth, float backoff, int growth_interval, void* stream);
 
+/* ------------------------------------------------------------------------------------------ student backward (A20) */
+/* The `loss.backward()` half of train_one_epoch (stage1/train_image_encoder_stage1.py:154-268) for the EfficientViT
+ * student.  Activation gradients are bf16 [M][C] row-major (NHWC), parameter gradients fp32 and ACCUMULATED (+=) into the
+ * destination; every reduction is two-stage in a fixed order (bit-reproducible).  Workspaces: the *_ws_floats helpers.
+ *
+ * Train-mode nn.BatchNorm2d of ConvLayer (efficientvit/nn/ops.py:39-80) over the raw conv output z [M][C] bf16:
+ * mean / invstd (biased variance, eps) per channel, the folded scale = gamma invstd, shift = beta - mean scale, and the
+ * running-stat update (momentum on the unbiased variance; running_* / num_batches_tracked may be NULL). */
+long long es3_col_reduce_ws_floats(long long M, int C);
+int es3_bn_stats(const void* z, long long M, int C, float eps, float momentum, const float* gamma, const float* beta, float* ws,
+                 float* mean, float* invstd, float* scale, float* shift, float* running_mean, float* running_var,
+                 long long* num_batches_tracked, void* stream);
+/* out = act(scale[c] z + shift[c]) (+ residual): the normalise + activation pass (scale / shift / residual may be NULL). */
+int es3_affine_act(const void* z, const float* scale, const float* shift, int act, const void* residual, void* out, long long M,
+                   int C, void* stream);
+/* Backward of act(scale z + shift) and of the BatchNorm producing (scale, shift).  g = da act'(scale z + shift);
+ * mode 0: no norm (shift = conv bias): dbeta += sum g.  mode 1: eval-mode BN (mean / invstd = running stats;
+ * set_bn_state with TRAIN.EVAL_BN_WHEN_TRAINING, train_image_encoder_stage1.py:310-314): dgamma, dbeta.  mode 2: batch
+ * statistics (full BN backward).  Writes coef [3][C] so that dz = coef0 g + coef1 z + coef2 (es3_bn_act_bwd_apply).
+ * act in {none, relu, hswish, gelu, relu6}.  dgamma / dbeta may be NULL. */
+int es3_bn_act_bwd_reduce(const void* da, const void* z, const float* scale, const float* shift, int act, int mode,
+                          const float* mean, const float* invstd, long long M, int C, float* ws, float* coef, float* dgamma,
+                          float* dbeta, void* stream);
+int es3_bn_act_bwd_apply(const void* da, const void* z, const float* scale, const float* shift, int act, const float* coef,
+                         void* dz, long long M, int C, void* stream);
+/* out = a + b, bf16 [M][C] with row strides in elements (gradient fan-in at residual joins / LiteMLA multi-scale). */
+int es3_add_bf16(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, long long M, int C,
+                 void* stream);
+/* Weight gradient of a 1x1 conv / nn.Linear: dW[n ldn + k ldk] += sum_m dz[m][n] x[m][k]  (mma.sync, contraction over
+ * pixels).  With H > 0 the x row of pixel (b, y, x) is (b, y + dy, x + dx), zero outside the H x W map: one tap of a dense
+ * 3x3 conv (head.3, stage1/model.py:198).  ws: es3_wgrad_pw_ws_floats(M, N, K) floats. */
+long long es3_wgrad_pw_ws_floats(long long M, int N, int K);
+int es3_wgrad_pw(const void* dz, long long lddz, const void* x, long long ldx, long long M, int N, int K, int H, int W, int dy,
+                 int dx, float* ws, float* dW, long long ldn, long long ldk, void* stream);
+/* Depthwise k x k conv (pad k/2): input gradient dx [B,H,W,C] from dz [B,Ho,Wo,C] and w [k*k][C] fp32 (any stride), and
+ * weight gradient dW [C][k*k] (torch layout) += from dz and the layer input x (pixel stride ldx: channel slices allowed). */
+int es3_dwconv_bwd_data(const void* dz, const float* w, void* dx, int B, int H, int W, int C, int ks, int stride, void* stream);
+long long es3_dwconv_wgrad_ws_floats(int B, int H, int W, int C, int ks, int stride);
+int es3_dwconv_wgrad(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, int stride, float* ws,
+                     float* dW, void* stream);
+/* Weight gradient of the 3 -> Cout stride-2 stem conv on the fp32 NCHW image (efficientvit/backbone.py:47-56):
+ * dW [Cout][3][3][3] += . */
+long long es3_stem_wgrad_ws_floats(int B, int H, int W, int Cout);
+int es3_stem_wgrad(const float* img, const void* dz, int B, int H, int W, int Cout, float* ws, float* dW, void* stream);
+/* Adjoint of es3_bilinear_nhwc_to_nchw: dout [B,C,Ho,Wo] fp32 NCHW -> din [B,Hi,Wi,C] bf16 NHWC. */
+int es3_bilinear_bwd(const float* dout, void* din, int B, int Hi, int Wi, int C, int Ho, int Wo, void* stream);
+/* Backward of es3_litemla_attn[_tc] (ReLU linear attention, head dim 16, ops.py:592-621): dy [B,HW,lddy] (head h at
+ * [16h, 16h+16)) -> dms [B,HW,lddms] in the q|k|v layout of ms.  kv_part: the partial KV sums the forward call left in its
+ * workspace (nchunk_f = ceil(HW / 512)); dkv_ws: es3_litemla_bwd_ws_floats floats. */
+long long es3_litemla_bwd_ws_floats(int B, int HW, int heads2);
+int es3_litemla_attn_bwd(const void* ms, long long ld, const void* dy, long long lddy, const float* kv_part, int nchunk_f,
+                         float* dkv_ws, void* dms, long long lddms, int B, int HW, int heads2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
