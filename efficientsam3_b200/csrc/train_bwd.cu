@@ -66,7 +66,8 @@ __device__ __forceinline__ void mma16816(float* d, const uint32_t* a, uint32_t b
 // ------------------------------------------------------------------------------------------ per-channel column reductions
 // z (and da) are [M][C] bf16, contiguous.  grid (nblk, ceil(CV / CVB)), block 256.  A thread owns one 8-channel vector
 // (cv) and every `lanes`-th row of the block's row range; the lanes are then tree-reduced through shared memory.
-// STATS: s0 = sum z, s1 = sum z^2.   else: g = da * act'(scale z + shift), s0 = sum g, s1 = sum g z.
+// STATS: s0 = sum (z - k), s1 = sum (z - k)^2 with the per-channel pivot k = z[row 0] (shifted sums: no cancellation in
+// E[z^2] - E[z]^2 when |mean| >> std).   else: g = da * act'(scale z + shift), s0 = sum g, s1 = sum g z.
 // part: [nblk][2][C] fp32.
 constexpr int CR_THREADS = 256;
 
@@ -91,6 +92,8 @@ __global__ void __launch_bounds__(CR_THREADS) col_reduce_kernel(const bf16* __re
       sc[i] = (!STATS && scale) ? scale[cv * 8 + i] : 1.f;
       sh[i] = (!STATS && shift) ? shift[cv * 8 + i] : 0.f;
     }
+    float piv[8];
+    if constexpr (STATS) unpack8(__ldg(reinterpret_cast<const uint4*>(z + cv * 8)), piv);
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = min(M, r0 + rows_per_block);
     for (long long r = r0 + pl; r < r1; r += lanes) {
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(CR_THREADS) col_reduce_kernel(const bf16* __re
       unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * C + cv * 8)), fz);
       if constexpr (STATS) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s0[i] += fz[i]; s1[i] = fmaf(fz[i], fz[i], s1[i]); }
+        for (int i = 0; i < 8; ++i) { const float d = fz[i] - piv[i]; s0[i] += d; s1[i] = fmaf(d, d, s1[i]); }
       } else {
         float fd[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(da + r * C + cv * 8)), fd);
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(CR_THREADS) col_reduce_kernel(const bf16* __re
 
 // one thread per channel: batch statistics, folded (scale, shift) for the normalise pass, running-stat update
 // (nn.BatchNorm2d: momentum 0.1 on the UNBIASED variance).
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ part, int nblk, int C, long long M, float eps, float momentum,
+__global__ void bn_stats_finalize_kernel(const bf16* __restrict__ z, const float* __restrict__ part, int nblk, int C, long long M, float eps, float momentum,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean,
                                          float* __restrict__ invstd, float* __restrict__ scale, float* __restrict__ shift,
                                          float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -146,8 +149,9 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ part, int nbl
     s += (double)part[((long long)b * 2) * C + c];
     q += (double)part[((long long)b * 2 + 1) * C + c];
   }
-  const double mu = s / (double)M;
-  double var = q / (double)M - mu * mu;
+  const double dm = s / (double)M;                       // mean of (z - pivot)
+  const double mu = (double)__bfloat162float(z[c]) + dm;
+  double var = q / (double)M - dm * dm;
   if (var < 0.0) var = 0.0;
   const float is = (float)(1.0 / sqrt(var + (double)eps));
   mean[c] = (float)mu;
@@ -727,7 +731,7 @@ extern "C" int es3_bn_stats(const void* z, long long M, int C, float eps, float 
   cudaStream_t st = (cudaStream_t)stream;
   col_reduce_kernel<ACT_NONE, true><<<dim3(nblk, gy), CR_THREADS, 0, st>>>((const bf16*)z, nullptr, nullptr, nullptr, M, C, CVB, rpb, ws);
   ES3_LAUNCH_CHECK("col_reduce_kernel<stats>");
-  bn_stats_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, nblk, C, M, eps, momentum, gamma, beta, mean, invstd, scale, shift,
+  bn_stats_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const bf16*)z, ws, nblk, C, M, eps, momentum, gamma, beta, mean, invstd, scale, shift,
                                                             running_mean, running_var, num_batches_tracked);
   ES3_LAUNCH_CHECK("bn_stats_finalize_kernel");
   return 0;

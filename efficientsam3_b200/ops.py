@@ -9,6 +9,7 @@ import torch
 
 from . import _lib
 
+ACT_DTYPE = torch.bfloat16   # storage dtype of activations / activation gradients in HBM
 ACT = {None: 0, "none": 0, "relu": 1, "hswish": 2, "gelu": 3, "gelu_tanh": 4, "relu6": 5, "sigmoid": 6}
 
 
@@ -767,9 +768,10 @@ def affine_act(z, scale, shift, act, residual=None):
     return out
 
 
-def bn_act_bwd(da, z, scale, shift, act, mode, mean=None, invstd=None, dgamma=None, dbeta=None):
+def bn_act_bwd(da, z, scale, shift, act, mode, mean=None, invstd=None, dgamma=None, dbeta=None, apply=True):
     """Backward through act(scale z + shift) and the norm that produced (scale, shift); see es3_bn_act_bwd_reduce.
-    da, z: [..., C] bf16 contiguous.  dgamma / dbeta: fp32 [C] accumulated in place (None: not needed).  Returns dz bf16."""
+    da, z: [..., C] bf16 contiguous.  dgamma / dbeta: fp32 [C] accumulated in place (None: not needed).  Returns dz bf16
+    (apply=False: only the per-channel reductions, returns None)."""
     _chk(da, torch.bfloat16, "da"); _chk(z, torch.bfloat16, "z")
     _ensure_init(z)
     assert da.is_contiguous() and z.is_contiguous() and da.shape == z.shape
@@ -781,6 +783,8 @@ def bn_act_bwd(da, z, scale, shift, act, mode, mean=None, invstd=None, dgamma=No
     _call("es3_bn_act_bwd_reduce", "bn_act_bwd_reduce", _nb(da, z), 6 * z.numel(), da.data_ptr(), z.data_ptr(), _ptr(scale),
           _ptr(shift), ACT[act], BN_MODE[mode], _ptr(mean), _ptr(invstd), M, C, ws.data_ptr(), coef.data_ptr(), _ptr(dgamma),
           _ptr(dbeta), _stream())
+    if not apply:
+        return None
     dz = torch.empty_like(z)
     _call("es3_bn_act_bwd_apply", "bn_act_bwd_apply", _nb(da, z, dz), 8 * z.numel(), da.data_ptr(), z.data_ptr(), _ptr(scale),
           _ptr(shift), ACT[act], coef.data_ptr(), dz.data_ptr(), M, C, _stream())

@@ -47,9 +47,23 @@ class ImageStudentEncoder(nn.Module, NativePlanMixin):
         return dict(w0=pw_weight(self.head[0]), s0=s, b0=b, w3=conv3x3_weight(self.head[3]),
                     b3=self.head[3].bias.detach().float().contiguous())
 
-    @torch.no_grad()
     def forward(self, x):
-        self._require_eval("ImageStudentEncoder.forward")
+        if self.training:
+            return self._forward_train(x)
+        with torch.no_grad():
+            return self._forward_eval(x)
+
+    def _forward_train(self, x):
+        """Train-mode forward recorded as ONE autograd node (StudentTrainFunction): batch-statistics BatchNorm (or frozen
+        BN modules, set_bn_state), backward on the kernels of train_bwd.cu.  Built for the EfficientViT b0 / b1 students."""
+        if not isinstance(self.backbone, EfficientViTAdapter):
+            raise NotImplementedError(
+                "train-mode forward/backward is built for the EfficientViT students (efficientvit_b0 / b1) in this round; "
+                f"{type(self.backbone).__name__} is eval-only (see DESIGN.md).  Call .eval() first.")
+        params = [p for p in self.parameters()]
+        return StudentTrainFunction.apply(self, x, *params)
+
+    def _forward_eval(self, x):
         feats = self.backbone.forward_nhwc(x)          # [B,h,w,Cin] bf16
         p = self._plan()
         B, h, w, cin = feats.shape
@@ -58,6 +72,35 @@ class ImageStudentEncoder(nn.Module, NativePlanMixin):
         if h != self.embed_size or w != self.embed_size:
             return ops.bilinear_nhwc_to_nchw(y, self.embed_size, self.embed_size)
         return ops.nhwc_to_nchw_f32(y)
+
+
+class StudentTrainFunction(torch.autograd.Function):
+    """preds = model(samples) with a native backward: forward runs the training graph (backbones/efficientvit_train.py) and
+    keeps it; backward(d preds) walks it in reverse and returns one fp32 gradient per parameter, so `loss.backward()`,
+    `p.grad`, DDP's gradient hooks and GradScaler work exactly as with the reference nn.Module."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        from ..backbones.efficientvit_train import EfficientViTTrainGraph, HeadTrainUnit
+        if not (x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3):
+            raise ValueError("expected an fp32 NCHW image batch [B,3,H,W]")
+        for m in module.modules():          # packed eval-mode weights go stale once parameters / running stats move
+            if isinstance(m, NativePlanMixin):
+                m._plan_key = None
+        body = EfficientViTTrainGraph(module.backbone.model)
+        head = HeadTrainUnit(module.head, module.embed_size)
+        out = head.forward(body.forward(x))
+        ctx.graph = (body, head)
+        ctx.params = params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        body, head = ctx.graph
+        ctx.graph = None
+        grads = {}
+        body.backward(head.backward(dout, grads), grads)
+        return (None, None) + tuple(grads.get(p) for p in ctx.params)
 
 
 def build_image_teacher_model(config):

@@ -7,7 +7,9 @@ Functional fp32 restatement, driven by a reference-keyed state_dict `sd`:
   EfficientViTBlock / ResidualBlock   ops.py:674-732 / 740-770
   EfficientViTBackbone                efficientvit/backbone.py:32-156, variants :158-196
   ImageStudentEncoder (head + resize) stage1/model.py:188-211
-Eval-mode semantics (BatchNorm uses running statistics).
+Eval-mode semantics (BatchNorm uses running statistics) by default; inside `with bn_batch_stats():` every BatchNorm2d
+behaves as in module.train() (batch statistics, running buffers of `sd` updated in place with momentum 0.1) -- the
+train-mode forward whose autograd is the oracle for the student backward (stage1/train_image_encoder_stage1.py:154-268).
 """
 from __future__ import annotations
 
@@ -21,6 +23,24 @@ VARIANTS = {  # backbone.py:158-196
     "b3": dict(width_list=[32, 64, 128, 256, 512], depth_list=[1, 4, 6, 6, 9], dim=32),
 }
 BN_EPS = 1e-5
+_BN_TRAIN = False
+
+
+class bn_batch_stats:
+    """Context manager: nn.BatchNorm2d train-mode semantics for every norm in this file."""
+
+    def __enter__(self):
+        global _BN_TRAIN
+        self.prev, _BN_TRAIN = _BN_TRAIN, True
+
+    def __exit__(self, *exc):
+        global _BN_TRAIN
+        _BN_TRAIN = self.prev
+
+
+def _bn(x, sd, p):
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        training=_BN_TRAIN, momentum=0.1, eps=BN_EPS)
 
 
 def conv_layer(sd, p, x, *, stride=1, groups=1, act=None):
@@ -30,8 +50,7 @@ def conv_layer(sd, p, x, *, stride=1, groups=1, act=None):
     k = w.shape[-1]
     x = F.conv2d(x, w, b, stride=stride, padding=k // 2, groups=groups)
     if (p + ".norm.weight") in sd:
-        x = F.batch_norm(x, sd[p + ".norm.running_mean"], sd[p + ".norm.running_var"], sd[p + ".norm.weight"],
-                         sd[p + ".norm.bias"], training=False, eps=BN_EPS)
+        x = _bn(x, sd, p + ".norm")
     if act == "hswish":
         x = F.hardswish(x)
     elif act is not None:
@@ -104,8 +123,7 @@ def backbone(sd, p, x, variant="b1", return_stages=False):
 def student_head(sd, feats, embed_size):
     """stage1/model.py:194-211: Conv1x1(no bias) -> BN -> GELU(erf) -> Conv3x3(pad 1, bias) -> bilinear."""
     x = F.conv2d(feats, sd["head.0.weight"])
-    x = F.batch_norm(x, sd["head.1.running_mean"], sd["head.1.running_var"], sd["head.1.weight"], sd["head.1.bias"],
-                     training=False, eps=BN_EPS)
+    x = _bn(x, sd, "head.1")
     x = F.gelu(x)
     x = F.conv2d(x, sd["head.3.weight"], sd["head.3.bias"], padding=1)
     if x.shape[-1] != embed_size or x.shape[-2] != embed_size:

@@ -1,0 +1,332 @@
+"""GPU: the student-backward kernels (efficientsam3_b200/csrc/train_bwd.cu) against their torch statements in
+tests/emu_ops.py (which the CPU suite ties to autograd of the train-mode oracle), then whole training steps.
+
+Tolerances: bf16 outputs 1e-2 of the tensor's scale (bf16 step 2^-8); fp32 reductions (statistics, parameter
+gradients) 2e-3 of the tensor's scale (bf16 products, fp32 accumulation in a different order).  Whole-step parity of
+parameter gradients: frozen-BN mode (well conditioned) rel-L2 <= 5e-2 over all gradients; batch-statistics mode on the
+random-weight fixture is ill-conditioned (the fp32 oracle itself is 2.5e-3 from the fp64 one, bf16 storage of the
+activations alone moves the gradients by ~12 %; tests/test_train_cpu.py) and is held to a loose bound, next to a
+functional check: a few optimiser steps reduce the loss.
+
+(The file name sorts last on purpose: it is the newest code of the round.)"""
+import math
+from types import SimpleNamespace as NS
+
+import pytest
+import torch
+
+import emu_ops as E
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def _close(got, ref, tol, what=""):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    scale = ref.abs().max().item() + 1e-20
+    err = (got - ref).abs().max().item() / scale
+    assert math.isfinite(err) and err <= tol, f"{what}: max err / scale = {err:.3e} > {tol}"
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# --------------------------------------------------------------------------------------------- BatchNorm pieces
+@pytest.mark.parametrize("M,C", [(1000, 16), (4099, 24), (777, 64), (20000, 128), (3000, 1024), (131, 2560)])
+def test_bn_stats(cuda, M, C):
+    from efficientsam3_b200 import ops
+    g = _g(M + C)
+    z = _bf(torch.randn(M, C, generator=g) * (torch.rand(C, generator=g) + 0.2) + torch.randn(C, generator=g) * 2)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    rm, rv, nbt = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5, torch.tensor(7)
+    rm_d, rv_d, nbt_d = rm.clone().to(cuda), rv.clone().to(cuda), nbt.clone().to(cuda)
+    got = ops.bn_stats(z.to(cuda), gamma.to(cuda), beta.to(cuda), 1e-5, 0.1, rm_d, rv_d, nbt_d)
+    ref = E.bn_stats(z, gamma, beta, 1e-5, 0.1, rm, rv, nbt)
+    for a, b, name in zip(got, ref, ("mean", "invstd", "scale", "shift")):
+        _close(a, b, 1e-4, f"bn_stats {name}")
+    _close(rm_d, rm, 1e-5, "running_mean")
+    _close(rv_d, rv, 1e-4, "running_var")
+    assert int(nbt_d) == 8
+
+
+@pytest.mark.parametrize("act", [None, "hswish", "gelu", "relu"])
+@pytest.mark.parametrize("M,C,res", [(513, 16, True), (1000, 256, False), (77, 1024, True)])
+def test_affine_act(cuda, M, C, res, act):
+    from efficientsam3_b200 import ops
+    g = _g(M * 3 + C)
+    z = _bf(torch.randn(M, C, generator=g) * 2)
+    scale, shift = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    r = _bf(torch.randn(M, C, generator=g)) if res else None
+    got = ops.affine_act(z.to(cuda), scale.to(cuda), shift.to(cuda), act, r.to(cuda) if res else None)
+    _close(got, E.affine_act(z, scale, shift, act, r), 1e-2, f"affine_act {act}")
+    got = ops.affine_act(z.to(cuda), None, shift.to(cuda), act)        # bias-only layers (fewer_norm MBConv)
+    _close(got, E.affine_act(z, None, shift, act), 1e-2, "affine_act bias-only")
+
+
+@pytest.mark.parametrize("mode", ["none", "eval", "batch"])
+@pytest.mark.parametrize("act", [None, "hswish", "gelu"])
+@pytest.mark.parametrize("M,C", [(2000, 16), (1111, 64), (300, 512)])
+def test_bn_act_bwd(cuda, M, C, act, mode):
+    from efficientsam3_b200 import ops
+    g = _g(M + 7 * C)
+    z = _bf(torch.randn(M, C, generator=g) * (torch.rand(C, generator=g) + 0.3) + torch.randn(C, generator=g))
+    da = _bf(torch.randn(M, C, generator=g))
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.5
+    if mode == "none":
+        scale, shift, mean, invstd = None, beta, None, None
+    elif mode == "eval":
+        mean, invstd = torch.randn(C, generator=g) * 0.5, torch.rsqrt(torch.rand(C, generator=g) + 0.5)
+        scale = gamma * invstd
+        shift = beta - mean * scale
+    else:
+        mean, invstd, scale, shift = E.bn_stats(z, gamma, beta, 1e-5, 0.1)
+    dg_ref, db_ref = torch.full((C,), 0.25), torch.full((C,), -0.5)     # the kernels accumulate (+=)
+    dz_ref = E.bn_act_bwd(da, z, scale, shift, act, mode, mean, invstd, dg_ref if mode != "none" else None, db_ref)
+    dev = lambda t: None if t is None else t.to(cuda)
+    dg, db = torch.full((C,), 0.25, device=cuda), torch.full((C,), -0.5, device=cuda)
+    dz = ops.bn_act_bwd(dev(da), dev(z), dev(scale), dev(shift), act, mode, dev(mean), dev(invstd), dg if mode != "none" else None, db)
+    _close(dz, dz_ref, 1e-2, f"dz {mode} {act}")
+    _close(db, db_ref, 2e-3, f"dbeta {mode} {act}")
+    if mode != "none":
+        _close(dg, dg_ref, 2e-3, f"dgamma {mode} {act}")
+    # reductions only (bias gradient of the head's 3x3 conv)
+    db2 = torch.zeros(C, device=cuda)
+    assert ops.bn_act_bwd(dev(da), dev(da), None, None, None, "none", dbeta=db2, apply=False) is None
+    _close(db2, da.float().sum(0), 2e-3, "column sums")
+
+
+def test_add_bf16_strided(cuda):
+    from efficientsam3_b200 import ops
+    g = _g(4)
+    big = _bf(torch.randn(999, 768, generator=g))
+    b = _bf(torch.randn(999, 384, generator=g))
+    got = ops.add_bf16(big.to(cuda)[:, :384], b.to(cuda))
+    _close(got, E.add_bf16(big[:, :384], b), 1e-2, "add strided")
+    got = ops.add_bf16(big.to(cuda)[:, 384:], b.to(cuda))
+    _close(got, E.add_bf16(big[:, 384:], b), 1e-2, "add strided 2")
+
+
+# --------------------------------------------------------------------------------------------- weight gradients
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 16), (4103, 16, 16), (2560, 32, 128), (777, 128, 512), (5000, 384, 384),
+                                   (300, 1024, 256), (256, 24, 96), (20000, 16, 64)])
+def test_wgrad_pw(cuda, M, N, K):
+    from efficientsam3_b200 import ops
+    g = _g(M + N + K)
+    dz, x = _bf(torch.randn(M, N, generator=g)), _bf(torch.randn(M, K, generator=g))
+    dW_ref = torch.full((N, K), 0.5)
+    E.wgrad_pw(dz, x, dW_ref)
+    dW = torch.full((N, K), 0.5, device=cuda)
+    ops.wgrad_pw(dz.to(cuda), x.to(cuda), dW)
+    _close(dW, dW_ref, 2e-3, f"wgrad_pw {M}x{N}x{K}")
+
+
+def test_wgrad_pw_strided_operands(cuda):
+    """dz is a channel slice of the LiteMLA gradient buffer (row stride 2*c3)."""
+    from efficientsam3_b200 import ops
+    g = _g(11)
+    M, c3 = 1500, 96
+    big, x = _bf(torch.randn(M, 2 * c3, generator=g)), _bf(torch.randn(M, c3, generator=g))
+    ref = torch.zeros(c3, c3)
+    E.wgrad_pw(big[:, c3:], x, ref)
+    got = torch.zeros(c3, c3, device=cuda)
+    ops.wgrad_pw(big.to(cuda)[:, c3:], x.to(cuda), got)
+    _close(got, ref, 2e-3, "wgrad_pw strided")
+
+
+@pytest.mark.parametrize("B,H,W,N,C", [(2, 9, 7, 32, 16), (1, 12, 12, 64, 128), (3, 5, 32, 1024, 64)])
+def test_wgrad_pw_conv3x3_taps(cuda, B, H, W, N, C):
+    """Nine shifted launches = the weight gradient of a dense 3x3 conv, written with the [N][C][3][3] strides."""
+    import torch.nn.functional as F
+    from efficientsam3_b200 import ops
+    g = _g(B + H + N)
+    dy, a = _bf(torch.randn(B, H, W, N, generator=g)), _bf(torch.randn(B, H, W, C, generator=g))
+    w = torch.zeros(N, C, 3, 3, requires_grad=True)
+    y = F.conv2d(a.float().permute(0, 3, 1, 2), w, padding=1)
+    (ref,) = torch.autograd.grad(y, w, dy.float().permute(0, 3, 1, 2))
+    got = torch.zeros(N, C, 3, 3, device=cuda)
+    flat = got.view(-1)
+    dy2, a2 = dy.to(cuda).view(-1, N), a.to(cuda).view(-1, C)
+    for ky in range(3):
+        for kx in range(3):
+            ops.wgrad_pw(dy2, a2, flat[ky * 3 + kx:], ldn=9 * C, ldk=9, shift=(H, W, ky - 1, kx - 1))
+    _close(got, ref, 2e-3, "conv3x3 wgrad")
+
+
+@pytest.mark.parametrize("B,H,W,C,ks,stride", [(2, 17, 23, 64, 3, 2), (1, 32, 32, 256, 3, 2), (2, 16, 16, 16, 3, 1), (1, 9, 11, 96, 5, 1),
+                                               (2, 8, 8, 1024, 3, 2), (1, 21, 20, 128, 5, 2)])
+def test_dwconv_gradients(cuda, B, H, W, C, ks, stride):
+    from efficientsam3_b200 import ops
+    g = _g(B * H + C + ks)
+    pad = ks // 2
+    Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+    x = _bf(torch.randn(B, H, W, C, generator=g))
+    dz = _bf(torch.randn(B, Ho, Wo, C, generator=g))
+    w = torch.randn(ks * ks, C, generator=g) / ks
+    _close(ops.dwconv_bwd_data(dz.to(cuda), w.to(cuda), H, W, ks, stride), E.dwconv_bwd_data(dz, w, H, W, ks, stride), 1e-2,
+           "dwconv_bwd_data")
+    if stride == 1:   # the route the training graph takes for stride 1: the forward kernel on the rotated taps
+        _close(ops.dwconv(dz.to(cuda), w.flip(0).contiguous().to(cuda), None, ks, 1, None), E.dwconv_bwd_data(dz, w, H, W, ks, 1), 1e-2,
+               "dwconv on flipped taps")
+    ref = torch.full((C, 1, ks, ks), 0.125)
+    E.dwconv_wgrad(dz, x, ref, ks, stride)
+    got = torch.full((C, 1, ks, ks), 0.125, device=cuda)
+    ops.dwconv_wgrad(dz.to(cuda), x.to(cuda), got, ks, stride)
+    _close(got, ref, 2e-3, "dwconv_wgrad")
+
+
+def test_dwconv_wgrad_channel_slice(cuda):
+    """x is the qkv half of the LiteMLA multi-scale buffer (pixel stride 2*c3)."""
+    from efficientsam3_b200 import ops
+    g = _g(21)
+    B, H, W, c3 = 2, 10, 10, 96
+    ms = _bf(torch.randn(B, H, W, 2 * c3, generator=g))
+    dz = _bf(torch.randn(B, H, W, c3, generator=g))
+    ref = torch.zeros(c3, 1, 5, 5)
+    E.dwconv_wgrad(dz, ms[..., :c3], ref, 5, 1)
+    got = torch.zeros(c3, 1, 5, 5, device=cuda)
+    ops.dwconv_wgrad(dz.to(cuda), ms.to(cuda)[..., :c3], got, 5, 1)
+    _close(got, ref, 2e-3, "dwconv_wgrad slice")
+
+
+@pytest.mark.parametrize("B,H,W,Cout", [(2, 64, 64, 16), (1, 37, 51, 8), (3, 32, 48, 24)])
+def test_stem_wgrad(cuda, B, H, W, Cout):
+    from efficientsam3_b200 import ops
+    g = _g(B + H + Cout)
+    img = torch.randn(B, 3, H, W, generator=g)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dz = _bf(torch.randn(B, Ho, Wo, Cout, generator=g))
+    ref = torch.full((Cout, 3, 3, 3), 1.0)
+    E.stem_wgrad(img, dz, ref)
+    got = torch.full((Cout, 3, 3, 3), 1.0, device=cuda)
+    ops.stem_wgrad(img.to(cuda), dz.to(cuda), got)
+    _close(got, ref, 2e-3, "stem_wgrad")
+
+
+@pytest.mark.parametrize("B,C,Hi,Wi,Ho,Wo", [(2, 64, 5, 5, 12, 12), (1, 1024, 32, 32, 64, 64), (2, 96, 10, 7, 9, 20), (1, 32, 16, 16, 6, 6)])
+def test_bilinear_bwd(cuda, B, C, Hi, Wi, Ho, Wo):
+    from efficientsam3_b200 import ops
+    dout = torch.randn(B, C, Ho, Wo, generator=_g(B + C + Ho))
+    _close(ops.bilinear_bwd(dout.to(cuda), Hi, Wi), E.bilinear_bwd(dout, Hi, Wi), 1e-2, "bilinear_bwd")
+
+
+@pytest.mark.parametrize("B,H,W,heads2", [(2, 10, 10, 16), (1, 32, 32, 32), (2, 23, 29, 4)])
+def test_litemla_attn_bwd(cuda, B, H, W, heads2):
+    from efficientsam3_b200 import ops
+    g = _g(B + H + heads2)
+    ms = _bf(torch.randn(B, H, W, 48 * heads2, generator=g))
+    datt = _bf(torch.randn(B, H, W, 16 * heads2, generator=g))
+    att, kv = ops.litemla_attn(ms.to(cuda), heads2, 1e-15, return_kv=True)
+    _close(att, E.litemla_attn(ms, heads2, 1e-15), 1e-2, "litemla_attn fwd")
+    got = ops.litemla_attn_bwd(ms.to(cuda), datt.to(cuda), kv, heads2, 1e-15)
+    _close(got, E.litemla_attn_bwd(ms, datt, None, heads2, 1e-15), 1.5e-2, "litemla_attn_bwd")
+
+
+# --------------------------------------------------------------------------------------------- whole steps
+def _student(name, img, embed, seed=3):
+    from efficientsam3_b200.stage1.model import build_image_student_model
+    from oracle.weights import fill_state_dict
+    cfg = NS(MODEL=NS(BACKBONE=name), DATA=NS(IMG_SIZE=img), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=embed))
+    m = build_image_student_model(cfg)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed))
+    return m
+
+
+def _oracle_grads(sd0, x, teacher, img, sizes, variant, embed, bn_train):
+    from oracle import efficientvit as O
+    from oracle.kd_loss import kd_loss
+    sd = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v.clone()) for k, v in sd0.items()}
+    if bn_train:
+        with O.bn_batch_stats():
+            out = O.image_student_encoder(sd, x, embed, variant)
+    else:
+        out = O.image_student_encoder(sd, x, embed, variant)
+    loss, _, _ = kd_loss(out, teacher, img, sizes, 1.0)
+    loss.backward()
+    return out.detach(), loss.item(), sd
+
+
+@pytest.mark.parametrize("name,variant,bn_train", [("efficientvit_b1", "b1", False), ("efficientvit_b1", "b1", True),
+                                                   ("efficientvit_b0", "b0", False)])
+def test_student_training_step_matches_oracle_autograd(cuda, name, variant, bn_train):
+    """preds = model(x); loss = KD(preds, teacher); loss.backward() on the native path vs autograd of the CPU oracle."""
+    from efficientsam3_b200.stage1.optim import KDLossFunction
+    img, embed, B = 320, 20, 4
+    m = _student(name, img, embed)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(B, 3, img, img, generator=_g(1))
+    teacher = torch.randn(B, 1024, embed, embed, generator=_g(2))
+    sizes = [(3, img, img * 3 // 4) if i % 2 == 0 else (3, img * 2 // 3, img) for i in range(B)]
+    m = m.to(cuda).train()
+    if not bn_train:
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                mod.eval()
+    out = m(x.to(cuda))
+    assert out.requires_grad and out.dtype == torch.float32 and out.shape == (B, 1024, embed, embed)
+    sz = torch.tensor([[s[1], s[2]] for s in sizes], dtype=torch.int32, device=cuda)
+    loss = KDLossFunction.apply(out, teacher.to(cuda), sz, img, 1.0)
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_out, ref_loss, sd = _oracle_grads(sd0, x, teacher, img, sizes, variant, embed, bn_train)
+    tol_out, tol_all = (0.15, 0.6) if bn_train else (2e-2, 5e-2)
+    rel_out = ((out.detach().cpu().double() - ref_out.double()).norm() / ref_out.double().norm()).item()
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        g = sd[k].grad.double()
+        num += (p.grad.cpu().double() - g).pow(2).sum().item()
+        den += g.pow(2).sum().item()
+    rel_all = (num / den) ** 0.5
+    print(f"{name} bn_train={bn_train}: out rel-L2 {rel_out:.3e}, loss {loss.item():.5f} vs {ref_loss:.5f}, all-gradient rel-L2 {rel_all:.3e}")
+    assert rel_out < tol_out, rel_out
+    assert rel_all < tol_all, rel_all
+    if bn_train:
+        for k, v in m.state_dict().items():
+            if k.endswith("num_batches_tracked"):
+                assert int(v) == int(sd0[k]) + 1, k
+
+
+def test_training_steps_reduce_the_loss_and_are_deterministic(cuda):
+    """A few full KD steps (train-mode student -> KD loss -> backward -> FlatAdamW) on one fixed batch: the loss goes down,
+    and two identical runs produce bit-identical parameters (fixed-order reductions, no atomics)."""
+    from efficientsam3_b200.stage1.optim import FlatAdamW, KDLossFunction
+    img, embed, B = 256, 16, 4
+    x = torch.randn(B, 3, img, img, generator=_g(5)).to(cuda)
+    teacher = (torch.randn(B, 1024, embed, embed, generator=_g(6)) * 0.5).to(cuda)
+    sz = torch.tensor([[img, img]] * B, dtype=torch.int32, device=cuda)
+
+    def run():
+        m = _student("efficientvit_b1", img, embed).to(cuda).train()
+        opt = FlatAdamW(m, lr=2e-3, weight_decay=0.01)
+        losses = []
+        for _ in range(6):
+            opt.zero_grad()
+            loss = KDLossFunction.apply(m(x), teacher, sz, img, 1.0)
+            loss.backward()
+            opt.step(max_norm=5.0)
+            losses.append(loss.item())
+        return losses, opt.flat_param.clone()
+
+    l1, p1 = run()
+    l2, p2 = run()
+    print("losses", [round(v, 4) for v in l1])
+    assert all(math.isfinite(v) for v in l1)
+    assert l1[-1] < 0.9 * l1[0], l1
+    assert l1 == l2 and torch.equal(p1, p2)
+    # and the eval-mode forward after training uses the updated weights (stale packed plans are dropped)
+    m = _student("efficientvit_b1", img, embed).to(cuda)
+    m.eval()
+    e0 = m(x)
+    m.train()
+    opt = FlatAdamW(m, lr=1e-2, weight_decay=0.0)
+    loss = KDLossFunction.apply(m(x), teacher, sz, img, 1.0)
+    loss.backward()
+    opt.step()
+    m.eval()
+    e1 = m(x)
+    assert (e1 - e0).abs().max().item() > 1e-3
