@@ -302,7 +302,7 @@ def test_training_steps_reduce_the_loss_and_are_deterministic(cuda):
 
     def run():
         m = _student("efficientvit_b1", img, embed).to(cuda).train()
-        opt = FlatAdamW(m, lr=2e-3, weight_decay=0.01)
+        opt = FlatAdamW(m, lr=1e-4, weight_decay=0.01)   # 2e-3 diverges on this random-weight fixture (CPU emulation agrees)
         losses = []
         for _ in range(6):
             opt.zero_grad()
@@ -316,7 +316,7 @@ def test_training_steps_reduce_the_loss_and_are_deterministic(cuda):
     l2, p2 = run()
     print("losses", [round(v, 4) for v in l1])
     assert all(math.isfinite(v) for v in l1)
-    assert l1[-1] < 0.9 * l1[0], l1
+    assert l1[-1] < 0.8 * l1[0] and all(b < a for a, b in zip(l1, l1[1:])), l1
     assert l1 == l2 and torch.equal(p1, p2)
     # and the eval-mode forward after training uses the updated weights (stale packed plans are dropped)
     m = _student("efficientvit_b1", img, embed).to(cuda)
