@@ -277,6 +277,8 @@ class HeadTrainUnit:
     """ImageStudentEncoder.head + resize (stage1/model.py:194-211): Conv1x1(no bias) -> BN -> GELU -> Conv3x3(bias) ->
     bilinear to embed_size -> NCHW fp32."""
 
+    WGRAD_TC = True   # head.3 weight gradient on tcgen05 (False: nine es3_wgrad_pw launches; 19.3 -> see profiles/r1_train_step_*.md)
+
     def __init__(self, head: nn.Sequential, embed_size: int):
         self.c0 = ConvUnit(head[0], head[1], "gelu", "pw")
         self.conv3 = head[3]
@@ -306,7 +308,9 @@ class HeadTrainUnit:
         if gb is not None:      # d bias = column sums of dy: the reduce half of the BN/act backward with act = none
             ops.bn_act_bwd(dy, dy, None, None, None, "none", dbeta=gb, apply=False)
         gw = _grad_of(grads, conv3.weight)
-        if gw is not None:      # one shifted pointwise weight gradient per tap, written with the [N][C][3][3] strides
+        if gw is not None and self.WGRAD_TC:      # nine tcgen05 GEMMs over the zero-framed, transposed pixel index
+            ops.conv3x3_wgrad(dy, a1, gw)
+        elif gw is not None:    # one shifted mma.sync weight gradient per tap, written with the [N][C][3][3] strides
             flat = gw.view(-1)
             dy2, a2 = dy.view(-1, n), a1.view(-1, c)
             for ky in range(3):

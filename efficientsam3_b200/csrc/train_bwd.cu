@@ -96,20 +96,34 @@ __global__ void __launch_bounds__(CR_THREADS) col_reduce_kernel(const bf16* __re
     if constexpr (STATS) unpack8(__ldg(reinterpret_cast<const uint4*>(z + cv * 8)), piv);
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = min(M, r0 + rows_per_block);
-    for (long long r = r0 + pl; r < r1; r += lanes) {
-      float fz[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * C + cv * 8)), fz);
-      if constexpr (STATS) {
+    // two rows per iteration: both loads (four in the backward form) are issued before any arithmetic
+    for (long long r = r0 + pl; r < r1; r += 2 * lanes) {
+      const long long rb = r + lanes;
+      const bool two = rb < r1;
+      const uint4 uza = __ldg(reinterpret_cast<const uint4*>(z + r * C + cv * 8));
+      const uint4 uzb = two ? __ldg(reinterpret_cast<const uint4*>(z + rb * C + cv * 8)) : make_uint4(0, 0, 0, 0);
+      uint4 uda = make_uint4(0, 0, 0, 0), udb = make_uint4(0, 0, 0, 0);
+      if constexpr (!STATS) {
+        uda = __ldg(reinterpret_cast<const uint4*>(da + r * C + cv * 8));
+        if (two) udb = __ldg(reinterpret_cast<const uint4*>(da + rb * C + cv * 8));
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float d = fz[i] - piv[i]; s0[i] += d; s1[i] = fmaf(d, d, s1[i]); }
-      } else {
-        float fd[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(da + r * C + cv * 8)), fd);
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        float fz[8];
+        unpack8(h ? uzb : uza, fz);
+        if constexpr (STATS) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float g = fd[i] * act_grad_t<ACT>(fmaf(sc[i], fz[i], sh[i]));
-          s0[i] += g;
-          s1[i] = fmaf(g, fz[i], s1[i]);
+          for (int i = 0; i < 8; ++i) { const float d = fz[i] - piv[i]; s0[i] += d; s1[i] = fmaf(d, d, s1[i]); }
+        } else {
+          float fd[8];
+          unpack8(h ? udb : uda, fd);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float g = fd[i] * act_grad_t<ACT>(fmaf(sc[i], fz[i], sh[i]));
+            s0[i] += g;
+            s1[i] = fmaf(g, fz[i], s1[i]);
+          }
         }
       }
     }
@@ -199,48 +213,76 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk,
 }
 
 // ------------------------------------------------------------------------------------------ elementwise passes
-// a[m][c] = act(scale[c] z[m][c] + shift[c]) (+ residual[m][c]); one thread per 8-channel vector.
+// Elementwise passes over [M][C] bf16.  Same thread map as the reductions: grid (nblk, ceil(CV / CVB)), a thread owns one
+// 8-channel vector (its per-channel coefficients are loaded ONCE into registers) and every `lanes`-th row of the block's
+// row range.  (The first version recomputed cv per element and re-read 3-5 coefficient scalars per value through
+// LDG.32: 2.1 TB/s, profiles/r1_train_step_a.md.)
+__device__ __forceinline__ void load8f(const float* p, float* f, float fill) {
+  if (p) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fill;
+  }
+}
+
+// a[m][c] = act(scale[c] z[m][c] + shift[c]) (+ residual[m][c])
 template <int ACT>
-__global__ void affine_act_kernel(const bf16* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
-                                  const bf16* __restrict__ residual, bf16* __restrict__ out, long long total_vec, int CV) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total_vec) return;
-  const int cv = (int)(i % CV);
-  float f[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), f);
+__global__ void __launch_bounds__(256) affine_act_kernel(const bf16* __restrict__ z, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, const bf16* __restrict__ residual,
+                                                         bf16* __restrict__ out, long long M, int C, int CVB, long long rows_per_block) {
+  const int tid = threadIdx.x, lanes = 256 / CVB;
+  const int cv = blockIdx.y * CVB + tid % CVB, pl = tid / CVB;
+  if (pl >= lanes || cv * 8 >= C) return;
+  float sc[8], sh[8];
+  load8f(scale ? scale + cv * 8 : nullptr, sc, 1.f);
+  load8f(shift ? shift + cv * 8 : nullptr, sh, 0.f);
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (long long r = r0 + pl; r < r1; r += lanes) {
+    const long long off = r * C + cv * 8;
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(z + off)), f);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float sc = scale ? __ldg(scale + cv * 8 + k) : 1.f, sh = shift ? __ldg(shift + cv * 8 + k) : 0.f;
-    f[k] = es3_act_t<ACT>(fmaf(sc, f[k], sh));
-  }
-  if (residual) {
-    float r[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(residual) + i), r);
+    for (int k = 0; k < 8; ++k) f[k] = es3_act_t<ACT>(fmaf(sc[k], f[k], sh[k]));
+    if (residual) {
+      float rr[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(residual + off)), rr);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] += r[k];
+      for (int k = 0; k < 8; ++k) f[k] += rr[k];
+    }
+    *reinterpret_cast<uint4*>(out + off) = pack8(f);
   }
-  reinterpret_cast<uint4*>(out)[i] = pack8(f);
 }
 
 // dz = A[c] * (da * act'(scale z + shift)) + B[c] * z + C[c]
 template <int ACT>
-__global__ void bn_act_bwd_apply_kernel(const bf16* __restrict__ da, const bf16* __restrict__ z, const float* __restrict__ scale,
-                                        const float* __restrict__ shift, const float* __restrict__ coef, bf16* __restrict__ dz,
-                                        long long total_vec, int CV) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total_vec) return;
-  const int cv = (int)(i % CV), C = CV * 8;
-  float fz[8], fd[8], o[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), fz);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(da) + i), fd);
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const bf16* __restrict__ da, const bf16* __restrict__ z,
+                                                               const float* __restrict__ scale, const float* __restrict__ shift,
+                                                               const float* __restrict__ coef, bf16* __restrict__ dz, long long M, int C,
+                                                               int CVB, long long rows_per_block) {
+  const int tid = threadIdx.x, lanes = 256 / CVB;
+  const int cv = blockIdx.y * CVB + tid % CVB, pl = tid / CVB;
+  if (pl >= lanes || cv * 8 >= C) return;
+  float sc[8], sh[8], cA[8], cB[8], cC[8];
+  load8f(scale ? scale + cv * 8 : nullptr, sc, 1.f);
+  load8f(shift ? shift + cv * 8 : nullptr, sh, 0.f);
+  load8f(coef + cv * 8, cA, 0.f);
+  load8f(coef + C + cv * 8, cB, 0.f);
+  load8f(coef + 2 * C + cv * 8, cC, 0.f);
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (long long r = r0 + pl; r < r1; r += lanes) {
+    const long long off = r * C + cv * 8;
+    float fz[8], fd[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(z + off)), fz);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(da + off)), fd);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = cv * 8 + k;
-    const float sc = scale ? __ldg(scale + c) : 1.f, sh = shift ? __ldg(shift + c) : 0.f;
-    const float g = fd[k] * act_grad_t<ACT>(fmaf(sc, fz[k], sh));
-    o[k] = fmaf(__ldg(coef + c), g, fmaf(__ldg(coef + C + c), fz[k], __ldg(coef + 2 * C + c)));
+    for (int k = 0; k < 8; ++k) {
+      const float g = fd[k] * act_grad_t<ACT>(fmaf(sc[k], fz[k], sh[k]));
+      o[k] = fmaf(cA[k], g, fmaf(cB[k], fz[k], cC[k]));
+    }
+    *reinterpret_cast<uint4*>(dz + off) = pack8(o);
   }
-  reinterpret_cast<uint4*>(dz)[i] = pack8(o);
 }
 
 // out[m][c] = a[m][c] + b[m][c]; row strides in elements (channel-sliced views), C % 8 == 0.
@@ -275,23 +317,33 @@ __global__ void sum_partials_kernel(const float* __restrict__ part, int nblk, lo
 // Both operands are [row = pixel][channel] in shared memory and go through ldmatrix.trans (the contraction index is the
 // row), exactly the v^T k pattern of litemla_kv_tc_kernel.  shift: x row of output pixel (b, y, x) is (b, y+dy, x+dx),
 // zero outside the H x W map (one tap of a 3x3 conv); dy = dx = 0 and H = 0 for plain 1x1 convs.
-constexpr int WG_TN = 64, WG_TK = 64, WG_ROWS = 256;
-constexpr int WG_RS = (WG_TN + WG_TK) * 2 + 16;      // 272-byte rows: ldmatrix conflict-free
-constexpr int WG_SMEM = WG_ROWS * WG_RS;             // 69632 B
+// MT / NP: the CTA tile is (16 MT) n x (16 NP) k outputs, MT, NP in {1, 2, 4} (narrow layers do not pay for a 64 x 64 tile:
+// wgrad_pw[N=16,K=16] ran at 0.4 TB/s with the fixed tile, profiles/r1_train_step_a.md).
+constexpr int WG_ROWS = 256;
+template <int MT, int NP>
+struct WgCfg {
+  static constexpr int TN = MT * 16, TK = NP * 16;
+  static constexpr int VPR = (MT + NP) * 2;                 // 16-byte vectors per staged row
+  static constexpr int RS = (MT + NP) * 32 + 16;            // row stride in bytes: odd multiple of 16 -> ldmatrix conflict-free
+  static constexpr int RED = 8 * 16 * TK * 4;               // cross-warp reduction buffer (one 16-row slab)
+  static constexpr int SMEM = (WG_ROWS * RS > RED) ? WG_ROWS * RS : RED;
+};
 
+template <int MT, int NP>
 __global__ void __launch_bounds__(256) wgrad_pw_kernel(const bf16* __restrict__ dz, long long lddz, const bf16* __restrict__ x,
                                                        long long ldx, long long M, int N, int K, int H, int W, int dy, int dx,
                                                        float* __restrict__ part) {
+  using Cfg = WgCfg<MT, NP>;
   extern __shared__ __align__(16) uint8_t wg_smem[];
   const uint32_t u = static_cast<uint32_t>(__cvta_generic_to_shared(wg_smem));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.y * WG_TN, k0 = blockIdx.z * WG_TK;
+  const int n0 = blockIdx.y * Cfg::TN, k0 = blockIdx.z * Cfg::TK;
   const long long nchunks = (M + WG_ROWS - 1) / WG_ROWS;
-  float acc[4][8][4];
+  float acc[MT][2 * NP][4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < MT; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
+    for (int b = 0; b < 2 * NP; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
   const int av_p = (lane & 7) + ((lane >> 4) << 3), av_cb = ((lane >> 3) & 1) * 16;
   const int bk_p = (lane & 7) + (((lane >> 3) & 1) << 3), bk_cb = (lane >> 4) * 16;
   const bool shifted = H > 0;
@@ -299,17 +351,17 @@ __global__ void __launch_bounds__(256) wgrad_pw_kernel(const bf16* __restrict__ 
   for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const long long row0 = chunk * WG_ROWS;
     __syncthreads();   // every warp is done with the previous chunk
-    for (int i = tid; i < WG_ROWS * 16; i += 256) {
-      const int rl = i >> 4, v = i & 15;
+    for (int i = tid; i < WG_ROWS * Cfg::VPR; i += 256) {
+      const int rl = i / Cfg::VPR, v = i % Cfg::VPR;
       const long long r = row0 + rl;
       const bf16* src = dz;
       bool ok = r < M;
-      if (v < 8) {
+      if (v < MT * 2) {
         const int c = n0 + v * 8;
         ok = ok && c < N;
         if (ok) src = dz + r * lddz + c;
       } else {
-        const int c = k0 + (v - 8) * 8;
+        const int c = k0 + (v - MT * 2) * 8;
         ok = ok && c < K;
         long long rs = r;
         if (ok && shifted) {
@@ -320,51 +372,51 @@ __global__ void __launch_bounds__(256) wgrad_pw_kernel(const bf16* __restrict__ 
         }
         if (ok) src = x + rs * ldx + c;
       }
-      cpa16(u + rl * WG_RS + v * 16, src, ok);
+      cpa16(u + rl * Cfg::RS + v * 16, src, ok);
     }
     cpa_wait_all();
     __syncthreads();
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       const int p0 = warp * 32 + ks * 16;
-      uint32_t af[4][4];
+      uint32_t af[MT][4];
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-        ldsm4t(u + (p0 + av_p) * WG_RS + mt * 32 + av_cb, af[mt][0], af[mt][1], af[mt][2], af[mt][3]);
+      for (int mt = 0; mt < MT; ++mt)
+        ldsm4t(u + (p0 + av_p) * Cfg::RS + mt * 32 + av_cb, af[mt][0], af[mt][1], af[mt][2], af[mt][3]);
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {
+      for (int np = 0; np < NP; ++np) {
         uint32_t b0, b1, b2, b3;
-        ldsm4t(u + (p0 + bk_p) * WG_RS + WG_TN * 2 + np * 32 + bk_cb, b0, b1, b2, b3);
+        ldsm4t(u + (p0 + bk_p) * Cfg::RS + Cfg::TN * 2 + np * 32 + bk_cb, b0, b1, b2, b3);
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
           mma16816(acc[mt][2 * np], af[mt], b0, b1);
           mma16816(acc[mt][2 * np + 1], af[mt], b2, b3);
         }
       }
     }
   }
-  // cross-warp sum, one 16-row slab (mt) at a time: red[8 warps][16][64] fp32 = 32 KB of the staging buffer
+  // cross-warp sum, one 16-row slab (mt) at a time: red[8 warps][16][TK] fp32 inside the staging buffer
   float* red = reinterpret_cast<float*>(wg_smem);
   const int g = lane >> 2, t4 = lane & 3;
   float* dst = part + (long long)blockIdx.x * N * K;
 #pragma unroll   // static indices: acc stays in registers
-  for (int mt = 0; mt < 4; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     __syncthreads();
-    float* mine = red + warp * 16 * 64;
+    float* mine = red + warp * 16 * Cfg::TK;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < 2 * NP; ++nt) {
       const int col = nt * 8 + t4 * 2;
-      mine[g * 64 + col] = acc[mt][nt][0];
-      mine[g * 64 + col + 1] = acc[mt][nt][1];
-      mine[(g + 8) * 64 + col] = acc[mt][nt][2];
-      mine[(g + 8) * 64 + col + 1] = acc[mt][nt][3];
+      mine[g * Cfg::TK + col] = acc[mt][nt][0];
+      mine[g * Cfg::TK + col + 1] = acc[mt][nt][1];
+      mine[(g + 8) * Cfg::TK + col] = acc[mt][nt][2];
+      mine[(g + 8) * Cfg::TK + col + 1] = acc[mt][nt][3];
     }
     __syncthreads();
-    for (int i = tid; i < 16 * 64; i += 256) {
+    for (int i = tid; i < 16 * Cfg::TK; i += 256) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w * 16 * 64 + i];
-      const int n = n0 + mt * 16 + (i >> 6), k = k0 + (i & 63);
+      for (int w = 0; w < 8; ++w) s += red[w * 16 * Cfg::TK + i];
+      const int n = n0 + mt * 16 + i / Cfg::TK, k = k0 + i % Cfg::TK;
       if (n < N && k < K) dst[(long long)n * K + k] = s;
     }
   }
@@ -408,27 +460,43 @@ __global__ void dw_bwd_data_kernel(const bf16* __restrict__ dz, const float* __r
 }
 
 // part[blk][tap][c] = sum over the block's output pixels of dz[p][c] * x[src(p, tap)][c].
-// grid (nblk, ceil(CP / CPB)), block 256: thread = (channel pair, pixel lane).  x may be a channel slice (pixel stride ldx).
-template <int KS>
+// grid (nblk, ceil(CG / CGB)), block 256: thread = (VEC-channel group, pixel lane); VEC = 8 (one 16-byte load per operand,
+// 3x3: 72 accumulators) or 4 (5x5: 100 accumulators).  x may be a channel slice (pixel stride ldx).
+// (First version: 2 channels per thread, LDG.32 per tap -> 0.14-0.45 TB/s, profiles/r1_train_step_a.md.)
+template <int VEC>
+__device__ __forceinline__ void ldvec(const bf16* p, float* f) {
+  if constexpr (VEC == 8) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
+  } else {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
+}
+
+template <int KS, int VEC>
 __global__ void __launch_bounds__(256) dw_wgrad_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ x, long long ldx, int B,
-                                                       int H, int W, int C, int Ho, int Wo, int stride, int CPB,
+                                                       int H, int W, int C, int Ho, int Wo, int stride, int CGB,
                                                        long long pix_per_block, float* __restrict__ part) {
-  __shared__ float red[256][2];
+  __shared__ float red[256][VEC + 1];
   constexpr int KK = KS * KS, PAD = KS / 2;
   const int tid = threadIdx.x;
-  const int lanes = 256 / CPB;
-  const int cpl = tid % CPB, pl = tid / CPB;
-  const int cp = blockIdx.y * CPB + cpl;
-  const bool active = pl < lanes && cp * 2 < C;
-  float acc[KK][2];
+  const int lanes = 256 / CGB;
+  const int cgl = tid % CGB, pl = tid / CGB;
+  const int cg = blockIdx.y * CGB + cgl;
+  const bool active = pl < lanes && cg * VEC < C;
+  float acc[KK][VEC];
 #pragma unroll
-  for (int t = 0; t < KK; ++t) acc[t][0] = acc[t][1] = 0.f;
+  for (int t = 0; t < KK; ++t)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[t][v] = 0.f;
   const long long total = (long long)B * Ho * Wo;
   const long long p0 = (long long)blockIdx.x * pix_per_block, p1 = min(total, p0 + pix_per_block);
   if (active) {
     for (long long p = p0 + pl; p < p1; p += lanes) {
       const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
-      const float2 g = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(dz + p * C + cp * 2)));
+      float g[VEC];
+      ldvec<VEC>(dz + p * C + cg * VEC, g);
 #pragma unroll
       for (int ky = 0; ky < KS; ++ky) {
         const int iy = oy * stride + ky - PAD;
@@ -437,9 +505,10 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const bf16* __restrict__ 
         for (int kx = 0; kx < KS; ++kx) {
           const int ix = ox * stride + kx - PAD;
           if (ix < 0 || ix >= W) continue;
-          const float2 xv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(x + (((long long)b * H + iy) * W + ix) * ldx + cp * 2)));
-          acc[ky * KS + kx][0] = fmaf(g.x, xv.x, acc[ky * KS + kx][0]);
-          acc[ky * KS + kx][1] = fmaf(g.y, xv.y, acc[ky * KS + kx][1]);
+          float xv[VEC];
+          ldvec<VEC>(x + (((long long)b * H + iy) * W + ix) * ldx + cg * VEC, xv);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[ky * KS + kx][v] = fmaf(g[v], xv[v], acc[ky * KS + kx][v]);
         }
       }
     }
@@ -448,20 +517,20 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const bf16* __restrict__ 
   while (top < lanes) top <<= 1;
 #pragma unroll   // static indices keep acc[][] in registers
   for (int t = 0; t < KK; ++t) {
-    red[tid][0] = acc[t][0];
-    red[tid][1] = acc[t][1];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) red[tid][v] = acc[t][v];
     __syncthreads();
     for (int s = top >> 1; s > 0; s >>= 1) {
       if (pl < s && pl + s < lanes) {
-        red[tid][0] += red[tid + s * CPB][0];
-        red[tid][1] += red[tid + s * CPB][1];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) red[tid][v] += red[tid + s * CGB][v];
       }
       __syncthreads();
     }
-    if (pl == 0 && cp * 2 < C) {
-      float* d = part + ((long long)blockIdx.x * KK + t) * C + cp * 2;
-      d[0] = red[tid][0];
-      d[1] = red[tid][1];
+    if (pl == 0 && cg * VEC < C) {
+      float* d = part + ((long long)blockIdx.x * KK + t) * C + cg * VEC;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) d[v] = red[tid][v];
     }
     __syncthreads();
   }
@@ -508,6 +577,39 @@ __global__ void stem_wgrad_kernel(const float* __restrict__ img, const bf16* __r
     }
   }
   if (owner) part[(long long)blockIdx.x * COUT * 27 + tid] = acc;
+}
+
+// ------------------------------------------------------------------------------------------ padded transpose
+// in [B,H,W,C] bf16 NHWC -> out [C][Mp] bf16, Mp = B * (H+2) * Wp (Wp >= W + 2, multiple of 8):
+//   out[c][(b (H+2) + y + 1) Wp + x + 1 - dx] = in[b,y,x,c], zero everywhere else (the caller clears `out`).
+// With the zero frame around every image a 3x3 tap becomes a pure column offset of the transposed operand, so the
+// weight gradient of a dense 3x3 conv is nine tcgen05 GEMMs over the pixel index: dW[ky][kx] = dYp^T[:, P] . Ap_dx^T[:, P + (ky-1) Wp]
+// (dx = kx - 1 is baked into the copy so that every TMA base address stays 16-byte aligned).
+// grid (ceil(C / 64), H, B), block 256: 32-pixel x 64-channel tiles through shared memory.
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int H, int W, int C,
+                                                            int Wp, int dx, long long Mp) {
+  __shared__ __align__(16) bf16 tile[32][72];
+  const int c0 = blockIdx.x * 64, y = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x;
+  const long long prow = ((long long)b * (H + 2) + y + 1) * Wp + 1 - dx;   // column of pixel x = 0
+  for (int x0 = 0; x0 < W; x0 += 32) {
+    __syncthreads();
+    {
+      const int xl = tid >> 3, v = tid & 7;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (x0 + xl < W && c0 + v * 8 < C)
+        u = __ldg(reinterpret_cast<const uint4*>(in + (((long long)b * H + y) * W + x0 + xl) * C + c0 + v * 8));
+      *reinterpret_cast<uint4*>(&tile[xl][v * 8]) = u;
+    }
+    __syncthreads();
+    const int c = tid >> 2, part = tid & 3;
+    if (c0 + c < C) {
+      bf16* dst = out + (long long)(c0 + c) * Mp + prow + x0 + part * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (x0 + part * 8 + i < W) dst[i] = tile[part * 8 + i][c];
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ bilinear adjoint
@@ -720,6 +822,20 @@ static int col_reduce_geometry(long long M, int C, int* CVB, int* nblk, long lon
   return 0;
 }
 
+// elementwise passes: up to 16 CTAs per SM worth of blocks, at least 8 rows per lane
+static int elementwise_geometry(long long M, int C, int* CVB, int* nblk, long long* rpb, int* gy) {
+  const int CV = C / 8;
+  *CVB = CV < 256 ? CV : 256;
+  const int lanes = 256 / *CVB;
+  long long want = (M + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
+  if (want < 1) want = 1;
+  if (want > 148 * 16) want = 148 * 16;
+  *nblk = (int)want;
+  *rpb = (M + *nblk - 1) / *nblk;
+  *gy = (CV + *CVB - 1) / *CVB;
+  return 0;
+}
+
 extern "C" int es3_bn_stats(const void* z, long long M, int C, float eps, float momentum, const float* gamma, const float* beta,
                             float* ws, float* mean, float* invstd, float* scale, float* shift, float* running_mean,
                             float* running_var, long long* num_batches_tracked, void* stream) {
@@ -740,11 +856,12 @@ extern "C" int es3_bn_stats(const void* z, long long M, int C, float eps, float 
 extern "C" int es3_affine_act(const void* z, const float* scale, const float* shift, int act, const void* residual, void* out,
                               long long M, int C, void* stream) {
   ES3_REQUIRE(M > 0 && C % 8 == 0, "es3_affine_act: need C %% 8 == 0 (C=%d)", C);
-  const long long total = M * (C / 8);
-  const unsigned blocks = (unsigned)ceil_div(total, 256);
+  int CVB, nblk, gy;
+  long long rpb;
+  elementwise_geometry(M, C, &CVB, &nblk, &rpb, &gy);
   cudaStream_t st = (cudaStream_t)stream;
   ES3_DISPATCH_ACT(act, A, {
-    affine_act_kernel<A><<<blocks, 256, 0, st>>>((const bf16*)z, scale, shift, (const bf16*)residual, (bf16*)out, total, C / 8);
+    affine_act_kernel<A><<<dim3(nblk, gy), 256, 0, st>>>((const bf16*)z, scale, shift, (const bf16*)residual, (bf16*)out, M, C, CVB, rpb);
   })
   ES3_LAUNCH_CHECK("affine_act_kernel");
   return 0;
@@ -772,11 +889,12 @@ extern "C" int es3_bn_act_bwd_reduce(const void* da, const void* z, const float*
 extern "C" int es3_bn_act_bwd_apply(const void* da, const void* z, const float* scale, const float* shift, int act,
                                     const float* coef, void* dz, long long M, int C, void* stream) {
   ES3_REQUIRE(M > 0 && C % 8 == 0, "es3_bn_act_bwd_apply: need C %% 8 == 0 (C=%d)", C);
-  const long long total = M * (C / 8);
-  const unsigned blocks = (unsigned)ceil_div(total, 256);
+  int CVB, nblk, gy;
+  long long rpb;
+  elementwise_geometry(M, C, &CVB, &nblk, &rpb, &gy);
   cudaStream_t st = (cudaStream_t)stream;
   ES3_DISPATCH_ACT_BWD(act, A, {
-    bn_act_bwd_apply_kernel<A><<<blocks, 256, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, coef, (bf16*)dz, total, C / 8);
+    bn_act_bwd_apply_kernel<A><<<dim3(nblk, gy), 256, 0, st>>>((const bf16*)da, (const bf16*)z, scale, shift, coef, (bf16*)dz, M, C, CVB, rpb);
   })
   ES3_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
   return 0;
@@ -792,10 +910,14 @@ extern "C" int es3_add_bf16(const void* a, long long lda, const void* b, long lo
   return 0;
 }
 
+static int wg_pick(int c) { return c <= 16 ? 1 : (c <= 32 ? 2 : 4); }
+
 static int wgrad_splits(long long M, int N, int K) {
+  const int mt = wg_pick(N), np = wg_pick(K);
   const long long nchunks = (M + WG_ROWS - 1) / WG_ROWS;
-  const long long tiles = (long long)ceil_div(N, WG_TN) * ceil_div(K, WG_TK);
-  long long s = (2 * 148 + tiles - 1) / tiles;
+  const long long tiles = (long long)ceil_div(N, mt * 16) * ceil_div(K, np * 16);
+  const long long target = (mt + np <= 3) ? 4 * 148 : 2 * 148;      // light CTAs: several per SM
+  long long s = (target + tiles - 1) / tiles;
   if (s > nchunks) s = nchunks;
   if (s < 1) s = 1;
   return (int)s;
@@ -803,22 +925,37 @@ static int wgrad_splits(long long M, int N, int K) {
 
 extern "C" long long es3_wgrad_pw_ws_floats(long long M, int N, int K) { return (long long)wgrad_splits(M, N, K) * N * K; }
 
+template <int MT, int NP>
+static int wgrad_launch(const bf16* dz, long long lddz, const bf16* x, long long ldx, long long M, int N, int K, int H, int W, int dy,
+                        int dx, float* ws, int splits, cudaStream_t st) {
+  using Cfg = WgCfg<MT, NP>;
+  static bool configured = false;
+  if (!configured) {
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(wgrad_pw_kernel<MT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    configured = true;
+  }
+  wgrad_pw_kernel<MT, NP><<<dim3(splits, ceil_div(N, Cfg::TN), ceil_div(K, Cfg::TK)), 256, Cfg::SMEM, st>>>(dz, lddz, x, ldx, M, N, K, H, W,
+                                                                                                          dy, dx, ws);
+  ES3_LAUNCH_CHECK("wgrad_pw_kernel");
+  return 0;
+}
+
 /* dW[n * ldn + k * ldk] += sum_m dz[m][n] * x[shift(m)][k] */
 extern "C" int es3_wgrad_pw(const void* dz, long long lddz, const void* x, long long ldx, long long M, int N, int K, int H, int W,
                             int dy, int dx, float* ws, float* dW, long long ldn, long long ldk, void* stream) {
   ES3_REQUIRE(M > 0 && N % 8 == 0 && K % 8 == 0 && lddz % 8 == 0 && ldx % 8 == 0, "es3_wgrad_pw: N/K/strides must be multiples of 8 (N=%d K=%d)", N, K);
   ES3_REQUIRE(((uintptr_t)dz & 15) == 0 && ((uintptr_t)x & 15) == 0, "es3_wgrad_pw: operands must be 16-byte aligned");
   ES3_REQUIRE((H == 0 && dy == 0 && dx == 0) || (H > 0 && W > 0 && M % ((long long)H * W) == 0), "es3_wgrad_pw: bad shift geometry");
-  static bool configured = false;
-  if (!configured) {
-    ES3_CHECK_CUDA(cudaFuncSetAttribute(wgrad_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
-    configured = true;
-  }
   const int splits = wgrad_splits(M, N, K);
   cudaStream_t st = (cudaStream_t)stream;
-  wgrad_pw_kernel<<<dim3(splits, ceil_div(N, WG_TN), ceil_div(K, WG_TK)), 256, WG_SMEM, st>>>((const bf16*)dz, lddz, (const bf16*)x, ldx, M,
-                                                                                             N, K, H, W, dy, dx, ws);
-  ES3_LAUNCH_CHECK("wgrad_pw_kernel");
+  const bf16* a = (const bf16*)dz;
+  const bf16* b = (const bf16*)x;
+  const int mt = wg_pick(N), np = wg_pick(K);
+  int rc = 1;
+#define ES3_WG(MT_, NP_) if (mt == MT_ && np == NP_) rc = wgrad_launch<MT_, NP_>(a, lddz, b, ldx, M, N, K, H, W, dy, dx, ws, splits, st)
+  ES3_WG(1, 1); ES3_WG(1, 2); ES3_WG(1, 4); ES3_WG(2, 1); ES3_WG(2, 2); ES3_WG(2, 4); ES3_WG(4, 1); ES3_WG(4, 2); ES3_WG(4, 4);
+#undef ES3_WG
+  if (rc != 0) return rc;
   const long long n = (long long)N * K;
   sum_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ws, splits, n, K, ldn, ldk, dW);
   ES3_LAUNCH_CHECK("sum_partials_kernel");
@@ -837,13 +974,14 @@ extern "C" int es3_dwconv_bwd_data(const void* dz, const float* w, void* dx, int
   return 0;
 }
 
-static int dw_wgrad_geometry(int B, int Ho, int Wo, int C, int* CPB, int* nblk, long long* ppb, int* gy) {
-  const int CP = C / 2;
-  *CPB = CP < 256 ? CP : 256;
+static int dw_wgrad_geometry(int B, int Ho, int Wo, int C, int ks, int* CGB, int* nblk, long long* ppb, int* gy) {
+  const int vec = ks == 3 ? 8 : 4;
+  const int CG = C / vec;
+  *CGB = CG < 256 ? CG : 256;
   const long long total = (long long)B * Ho * Wo;
-  *nblk = pick_blocks(total, 256 / *CPB, 1184);
+  *nblk = pick_blocks(total, 256 / *CGB, 1184);
   *ppb = (total + *nblk - 1) / *nblk;
-  *gy = (CP + *CPB - 1) / *CPB;
+  *gy = (CG + *CGB - 1) / *CGB;
   return 0;
 }
 
@@ -852,25 +990,25 @@ extern "C" long long es3_dwconv_wgrad_ws_floats(int B, int H, int W, int C, int 
   const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
   int CPB, nblk, gy;
   long long ppb;
-  dw_wgrad_geometry(B, Ho, Wo, C, &CPB, &nblk, &ppb, &gy);
+  dw_wgrad_geometry(B, Ho, Wo, C, ks, &CPB, &nblk, &ppb, &gy);
   return (long long)nblk * ks * ks * C;
 }
 
 /* dW[c * ks*ks + tap] += sum_p dz[p][c] x[src(p, tap)][c]   (torch layout [C,1,ks,ks]) */
 extern "C" int es3_dwconv_wgrad(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, int stride, float* ws,
                                 float* dW, void* stream) {
-  ES3_REQUIRE(C % 2 == 0 && ldx % 2 == 0 && (ks == 3 || ks == 5) && (stride == 1 || stride == 2),
+  ES3_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && (ks == 3 || ks == 5) && (stride == 1 || stride == 2),
               "es3_dwconv_wgrad: unsupported C=%d ks=%d stride=%d", C, ks, stride);
   const int pad = ks / 2;
   const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
   int CPB, nblk, gy;
   long long ppb;
-  dw_wgrad_geometry(B, Ho, Wo, C, &CPB, &nblk, &ppb, &gy);
+  dw_wgrad_geometry(B, Ho, Wo, C, ks, &CPB, &nblk, &ppb, &gy);
   cudaStream_t st = (cudaStream_t)stream;
   if (ks == 3)
-    dw_wgrad_kernel<3><<<dim3(nblk, gy), 256, 0, st>>>((const bf16*)dz, (const bf16*)x, ldx, B, H, W, C, Ho, Wo, stride, CPB, ppb, ws);
+    dw_wgrad_kernel<3, 8><<<dim3(nblk, gy), 256, 0, st>>>((const bf16*)dz, (const bf16*)x, ldx, B, H, W, C, Ho, Wo, stride, CPB, ppb, ws);
   else
-    dw_wgrad_kernel<5><<<dim3(nblk, gy), 256, 0, st>>>((const bf16*)dz, (const bf16*)x, ldx, B, H, W, C, Ho, Wo, stride, CPB, ppb, ws);
+    dw_wgrad_kernel<5, 4><<<dim3(nblk, gy), 256, 0, st>>>((const bf16*)dz, (const bf16*)x, ldx, B, H, W, C, Ho, Wo, stride, CPB, ppb, ws);
   ES3_LAUNCH_CHECK("dw_wgrad_kernel");
   const long long n = (long long)ks * ks * C;
   // part index i = tap * C + c  ->  dW[c * ks*ks + tap]
@@ -905,6 +1043,28 @@ extern "C" int es3_stem_wgrad(const float* img, const void* dz, int B, int H, in
   ES3_LAUNCH_CHECK("stem_wgrad_kernel");
   const long long n = (long long)Cout * 27;
   sum_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ws, nblk, n, 27, 27, 1, dW);
+  ES3_LAUNCH_CHECK("sum_partials_kernel");
+  return 0;
+}
+
+/* out [C][Mp] = zero-framed, x-shifted transpose of in [B,H,W,C] (see transpose_pad_kernel); Mp = B (H+2) Wp. */
+extern "C" int es3_transpose_pad_bf16(const void* in, void* out, int B, int H, int W, int C, int Wp, int dx, void* stream) {
+  ES3_REQUIRE(B > 0 && H > 0 && W > 0 && C % 8 == 0, "es3_transpose_pad_bf16: bad shape (C=%d)", C);
+  ES3_REQUIRE(Wp % 8 == 0 && Wp >= W + 2 && dx >= -1 && dx <= 1, "es3_transpose_pad_bf16: need Wp %% 8 == 0, Wp >= W + 2, |dx| <= 1");
+  const long long Mp = (long long)B * (H + 2) * Wp;
+  cudaStream_t st = (cudaStream_t)stream;
+  ES3_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)C * Mp * sizeof(bf16), st));
+  transpose_pad_kernel<<<dim3(ceil_div(C, 64), H, B), 256, 0, st>>>((const bf16*)in, (bf16*)out, H, W, C, Wp, dx, Mp);
+  ES3_LAUNCH_CHECK("transpose_pad_kernel");
+  return 0;
+}
+
+/* dst[(i / inner) ld_outer + (i % inner) ld_inner] += src[i], i < n  (fp32): adds a dense [n / inner][inner] block into a
+ * strided parameter-gradient tensor (one tap of a [N][C][3][3] weight). */
+extern "C" int es3_accumulate_strided(const float* src, long long n, int inner, long long ld_outer, long long ld_inner, float* dst,
+                                      void* stream) {
+  ES3_REQUIRE(n > 0 && inner > 0, "es3_accumulate_strided: bad shape");
+  sum_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, 1, n, inner, ld_outer, ld_inner, dst);
   ES3_LAUNCH_CHECK("sum_partials_kernel");
   return 0;
 }

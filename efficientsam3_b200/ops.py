@@ -818,6 +818,46 @@ def wgrad_pw(dz, x, dW, ldn=None, ldk=1, shift=None):
     return dW
 
 
+def transpose_pad(x, Wp, dx):
+    """x [B,H,W,C] bf16 -> [C, B*(H+2)*Wp] bf16: zero-framed, x-shifted transpose (es3_transpose_pad_bf16)."""
+    _chk(x, torch.bfloat16, "x")
+    _ensure_init(x)
+    assert x.is_contiguous()
+    B, H, W, C = x.shape
+    out = torch.empty((C, B * (H + 2) * Wp), device=x.device, dtype=torch.bfloat16)
+    _call("es3_transpose_pad_bf16", "transpose_pad", _nb(x) + 2 * _nb(out), 0, x.data_ptr(), out.data_ptr(), B, H, W, C, Wp, dx, _stream())
+    return out
+
+
+def accumulate_strided(src, dst, inner, ld_outer, ld_inner):
+    """dst.flat[(i // inner) * ld_outer + (i % inner) * ld_inner] += src.flat[i]  (fp32)."""
+    _chk(src, torch.float32, "src"); _chk(dst, torch.float32, "dst")
+    _ensure_init(src)
+    assert src.is_contiguous()
+    _call("es3_accumulate_strided", "accumulate_strided", 3 * _nb(src), src.numel(), src.data_ptr(), src.numel(), inner, ld_outer,
+          ld_inner, dst.data_ptr(), _stream())
+    return dst
+
+
+def conv3x3_wgrad(dy, a, gw):
+    """gw [N,C,3,3] fp32 += weight gradient of a dense 3x3 / pad 1 conv; dy [B,H,W,N], a [B,H,W,C] bf16 NHWC.
+    Nine tcgen05 GEMMs over the zero-framed pixel index (see es3_transpose_pad_bf16 in include/es3.h)."""
+    B, H, W, N = dy.shape
+    C = a.shape[3]
+    Wp = (W + 2 + 7) // 8 * 8
+    Mp = B * (H + 2) * Wp
+    dyT = transpose_pad(dy, Wp, 0)
+    full = torch.empty((N, C), device=dy.device, dtype=torch.float32)
+    flat = gw.view(-1)
+    for kx in range(3):
+        aT = transpose_pad(a, Wp, kx - 1)
+        for ky in range(3):
+            lo = Wp + (ky - 1) * Wp
+            gemm(dyT[:, Wp:Mp - Wp], aT[:, lo:lo + Mp - 2 * Wp], out=full)
+            accumulate_strided(full, flat[ky * 3 + kx:], C, 9 * C, 9)
+    return gw
+
+
 def dwconv_bwd_data(dz, w, H, W, ks, stride):
     """Input gradient of a depthwise conv (pad ks//2): dz [B,Ho,Wo,C] bf16, w [ks*ks, C] fp32 -> dx [B,H,W,C] bf16."""
     _chk(dz, torch.bfloat16, "dz"); _chk(w, torch.float32, "w")

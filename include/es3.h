@@ -308,6 +308,13 @@ int es3_add_bf16(const void* a, long long lda, const void* b, long long ldb, voi
 long long es3_wgrad_pw_ws_floats(long long M, int N, int K);
 int es3_wgrad_pw(const void* dz, long long lddz, const void* x, long long ldx, long long M, int N, int K, int H, int W, int dy,
                  int dx, float* ws, float* dW, long long ldn, long long ldk, void* stream);
+/* Dense 3x3 weight gradient on tcgen05: es3_transpose_pad_bf16 lays in [B,H,W,C] out as out [C][Mp], Mp = B (H+2) Wp (Wp >= W+2,
+ * multiple of 8), every image inside a zero frame and shifted by dx in x; a tap (ky, kx) is then the plain GEMM
+ * dW[ky][kx] = dYp^T[:, Wp : Mp-Wp] . Ap_{kx-1}^T[:, Wp + (ky-1) Wp : ...]^T (es3_gemm_bf16, fp32 out), added into the
+ * [N][C][3][3] gradient by es3_accumulate_strided (dst[(i / inner) ld_outer + (i % inner) ld_inner] += src[i]). */
+int es3_transpose_pad_bf16(const void* in, void* out, int B, int H, int W, int C, int Wp, int dx, void* stream);
+int es3_accumulate_strided(const float* src, long long n, int inner, long long ld_outer, long long ld_inner, float* dst,
+                           void* stream);
 /* Depthwise k x k conv (pad k/2): input gradient dx [B,H,W,C] from dz [B,Ho,Wo,C] and w [k*k][C] fp32 (any stride), and
  * weight gradient dW [C][k*k] (torch layout) += from dz and the layer input x (pixel stride ldx: channel slices allowed). */
 int es3_dwconv_bwd_data(const void* dz, const float* w, void* dx, int B, int H, int W, int C, int ks, int stride, void* stream);

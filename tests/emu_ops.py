@@ -227,6 +227,29 @@ def wgrad_pw(dz, x, dW, ldn=None, ldk=1, shift=None):
     return dW
 
 
+def conv3x3_wgrad(dy, a, gw):
+    N, C = dy.shape[3], a.shape[3]
+    w = torch.zeros(N, C, 3, 3, dtype=CD, requires_grad=True)
+    with torch.enable_grad():
+        y = F.conv2d(_nchw(a), w, padding=1)
+        (g,) = torch.autograd.grad(y, w, _nchw(dy))
+    gw += g
+    return gw
+
+
+def transpose_pad(x, Wp, dx):
+    B, H, W, C = x.shape
+    out = torch.zeros(C, B, H + 2, Wp, dtype=x.dtype)
+    out[:, :, 1:H + 1, 1 - dx:1 - dx + W] = x.permute(3, 0, 1, 2)
+    return out.reshape(C, -1)
+
+
+def accumulate_strided(src, dst, inner, ld_outer, ld_inner):
+    i = torch.arange(src.numel())
+    dst.view(-1)[(i // inner) * ld_outer + (i % inner) * ld_inner] += src.reshape(-1)
+    return dst
+
+
 def dwconv_bwd_data(dz, w, H, W, ks, stride):
     B, Ho, Wo, C = dz.shape
     x = torch.zeros(B, C, H, W, dtype=CD, requires_grad=True)
@@ -276,7 +299,7 @@ def litemla_attn_bwd(ms, datt, kv, heads2, eps=1e-15):
 
 PATCHED = ["gemm", "conv3x3", "stem_conv3x3_s2", "dwconv", "litemla_dwpw_weights", "litemla_aggreg_dwpw", "litemla_attn",
            "bilinear_nhwc_to_nchw", "nhwc_to_nchw_f32", "nchw_f32_to_nhwc", "bn_stats", "affine_act", "bn_act_bwd", "add_bf16",
-           "wgrad_pw", "dwconv_bwd_data", "dwconv_wgrad", "stem_wgrad", "bilinear_bwd", "litemla_attn_bwd"]
+           "wgrad_pw", "transpose_pad", "accumulate_strided", "dwconv_bwd_data", "dwconv_wgrad", "stem_wgrad", "bilinear_bwd", "litemla_attn_bwd"]
 
 
 def install(monkeypatch):

@@ -138,3 +138,19 @@ def test_train_mode_is_refused_where_it_is_not_built():
     m = build_image_student_model(cfg).train()
     with pytest.raises(NotImplementedError):
         m(torch.randn(1, 3, 160, 160))
+
+
+@pytest.mark.parametrize("B,H,W,N,C", [(2, 5, 7, 32, 16), (1, 8, 8, 64, 24), (3, 4, 14, 16, 8)])
+def test_conv3x3_wgrad_composition(monkeypatch, B, H, W, N, C):
+    """ops.conv3x3_wgrad = zero-framed transposes + nine GEMMs over the pixel index + strided accumulation: the composition
+    (frame geometry, tap offsets, strides) against autograd, with the three primitives emulated."""
+    from efficientsam3_b200 import ops
+    emu_ops.install(monkeypatch)
+    g = torch.Generator().manual_seed(B + H + N)
+    dy = torch.randn(B, H, W, N, generator=g).to(torch.bfloat16)
+    a = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
+    ref = torch.full((N, C, 3, 3), 0.5)
+    emu_ops.conv3x3_wgrad(dy, a, ref)
+    got = torch.full((N, C, 3, 3), 0.5)
+    ops.conv3x3_wgrad(dy, a, got)
+    assert (got - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()

@@ -113,7 +113,7 @@ def test_add_bf16_strided(cuda):
 
 # --------------------------------------------------------------------------------------------- weight gradients
 @pytest.mark.parametrize("M,N,K", [(1000, 64, 16), (4103, 16, 16), (2560, 32, 128), (777, 128, 512), (5000, 384, 384),
-                                   (300, 1024, 256), (256, 24, 96), (20000, 16, 64)])
+                                   (300, 1024, 256), (256, 24, 96), (20000, 16, 64), (3000, 16, 32), (3001, 32, 16), (999, 32, 32), (5555, 64, 32)])
 def test_wgrad_pw(cuda, M, N, K):
     from efficientsam3_b200 import ops
     g = _g(M + N + K)
@@ -155,6 +155,23 @@ def test_wgrad_pw_conv3x3_taps(cuda, B, H, W, N, C):
         for kx in range(3):
             ops.wgrad_pw(dy2, a2, flat[ky * 3 + kx:], ldn=9 * C, ldk=9, shift=(H, W, ky - 1, kx - 1))
     _close(got, ref, 2e-3, "conv3x3 wgrad")
+
+
+@pytest.mark.parametrize("B,H,W,N,C", [(2, 9, 7, 32, 16), (1, 12, 12, 64, 128), (2, 32, 32, 1024, 256), (3, 5, 33, 128, 64)])
+def test_conv3x3_wgrad_tc(cuda, B, H, W, N, C):
+    """The tcgen05 route of the head.3 weight gradient: zero-framed transposes + nine GEMMs over the pixel index."""
+    from efficientsam3_b200 import ops
+    g = _g(B + H + N + 1)
+    dy, a = _bf(torch.randn(B, H, W, N, generator=g)), _bf(torch.randn(B, H, W, C, generator=g))
+    # the primitive first
+    for dx in (-1, 0, 1):
+        Wp = (W + 2 + 7) // 8 * 8
+        assert torch.equal(ops.transpose_pad(a.to(cuda), Wp, dx).cpu(), E.transpose_pad(a, Wp, dx)), dx
+    ref = torch.full((N, C, 3, 3), 0.5)
+    E.conv3x3_wgrad(dy, a, ref)
+    got = torch.full((N, C, 3, 3), 0.5, device=cuda)
+    ops.conv3x3_wgrad(dy.to(cuda), a.to(cuda), got)
+    _close(got, ref, 2e-3, "conv3x3_wgrad (tcgen05)")
 
 
 @pytest.mark.parametrize("B,H,W,C,ks,stride", [(2, 17, 23, 64, 3, 2), (1, 32, 32, 256, 3, 2), (2, 16, 16, 16, 3, 1), (1, 9, 11, 96, 5, 1),
