@@ -148,21 +148,42 @@ __global__ void __launch_bounds__(CR_THREADS) col_reduce_kernel(const bf16* __re
   }
 }
 
-// one thread per channel: batch statistics, folded (scale, shift) for the normalise pass, running-stat update
-// (nn.BatchNorm2d: momentum 0.1 on the UNBIASED variance).
-__global__ void bn_stats_finalize_kernel(const bf16* __restrict__ z, const float* __restrict__ part, int nblk, int C, long long M, float eps, float momentum,
-                                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean,
-                                         float* __restrict__ invstd, float* __restrict__ scale, float* __restrict__ shift,
-                                         float* __restrict__ running_mean, float* __restrict__ running_var,
-                                         long long* __restrict__ num_batches_tracked) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && num_batches_tracked) num_batches_tracked[0] += 1;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s += (double)part[((long long)b * 2) * C + c];
-    q += (double)part[((long long)b * 2 + 1) * C + c];
+// Second stage of the column reductions.  block 256 = 8 channels x 32 lanes: lane l adds partials l, l + 32, ... (double),
+// the 32 lanes are then summed in a fixed order.  (One thread per channel walking all <= 1184 partials serially cost
+// ~0.1 ms per BatchNorm layer -- 35 + 54 launches per step, profiles/r1_train_step_b.md.)
+__device__ __forceinline__ bool sum_block_partials(const float* __restrict__ part, int nblk, int C, double& s, double& q, int& c_out) {
+  __shared__ double r0[32][9], r1[32][9];
+  const int cl = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int blk = lane; blk < nblk; blk += 32) {
+      a += (double)part[((long long)blk * 2) * C + c];
+      b += (double)part[((long long)blk * 2 + 1) * C + c];
+    }
   }
+  r0[lane][cl] = a;
+  r1[lane][cl] = b;
+  __syncthreads();
+  c_out = c;
+  if (lane != 0 || c >= C) return false;
+  s = 0.0; q = 0.0;
+  for (int l = 0; l < 32; ++l) { s += r0[l][cl]; q += r1[l][cl]; }
+  return true;
+}
+
+// batch statistics, folded (scale, shift) for the normalise pass, running-stat update (nn.BatchNorm2d: momentum on the
+// UNBIASED variance).  grid ceil(C / 8), block 256.
+__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const bf16* __restrict__ z, const float* __restrict__ part, int nblk, int C,
+                                                                long long M, float eps, float momentum, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float* __restrict__ mean,
+                                                                float* __restrict__ invstd, float* __restrict__ scale, float* __restrict__ shift,
+                                                                float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                long long* __restrict__ num_batches_tracked) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) num_batches_tracked[0] += 1;
+  double s, q;
+  int c;
+  if (!sum_block_partials(part, nblk, C, s, q, c)) return;
   const double dm = s / (double)M;                       // mean of (z - pivot)
   const double mu = (double)__bfloat162float(z[c]) + dm;
   double var = q / (double)M - dm * dm;
@@ -183,17 +204,14 @@ __global__ void bn_stats_finalize_kernel(const bf16* __restrict__ z, const float
 // mode 0: no norm (scale = 1 or given, shift = conv bias): A = scale, dbeta (= d bias) += sum g
 // mode 1: eval-mode BN (running stats): A = scale; dbeta += sum g; dgamma += invstd (sum g z - mean sum g)
 // mode 2: batch-stat BN: additionally B, C carry the mean / variance terms of the BN backward.
-// coef: [3][C] = A | B | C with dz = A g + B z + C.
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, long long M, int mode,
-                                       const float* __restrict__ scale, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                       float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double sg = 0.0, sgz = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    sg += (double)part[((long long)b * 2) * C + c];
-    sgz += (double)part[((long long)b * 2 + 1) * C + c];
-  }
+// coef: [3][C] = A | B | C with dz = A g + B z + C.   grid ceil(C / 8), block 256.
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, long long M, int mode,
+                                                              const float* __restrict__ scale, const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd, float* __restrict__ coef,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  double sg, sgz;
+  int c;
+  if (!sum_block_partials(part, nblk, C, sg, sgz, c)) return;
   const float sc = scale ? scale[c] : 1.f;
   float A = sc, Bc = 0.f, Cc = 0.f;
   if (mode != 0) {
@@ -300,14 +318,24 @@ __global__ void add_bf16_kernel(const bf16* __restrict__ a, long long lda, const
   *reinterpret_cast<uint4*>(out + m * ldo + cv * 8) = pack8(fa);
 }
 
-// out[(i / inner) * ld_outer + (i % inner) * ld_inner] += sum_b part[b * n + i]   (fixed order over b)
-__global__ void sum_partials_kernel(const float* __restrict__ part, int nblk, long long n, int inner, long long ld_outer,
-                                    long long ld_inner, float* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// out[(i / inner) * ld_outer + (i % inner) * ld_inner] += sum_b part[b * n + i]   (fixed order over b).
+// block 256 = 32 outputs x 8 lanes (lane l adds partials l, l + 8, ...), grid ceil(n / 32).
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int nblk, long long n, int inner,
+                                                           long long ld_outer, long long ld_inner, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int il = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + il;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += part[(long long)b * n + i];
-  out[(i / inner) * ld_outer + (i % inner) * ld_inner] += s;
+  if (i < n)
+    for (int b = lane; b < nblk; b += 8) s += part[(long long)b * n + i];
+  red[lane][il] = s;
+  __syncthreads();
+  if (lane == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += red[l][il];
+    out[(i / inner) * ld_outer + (i % inner) * ld_inner] += t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ pointwise weight gradient
@@ -510,6 +538,91 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const bf16* __restrict__ 
 #pragma unroll
           for (int v = 0; v < VEC; ++v) acc[ky * KS + kx][v] = fmaf(g[v], xv[v], acc[ky * KS + kx][v]);
         }
+      }
+    }
+  }
+  int top = 1;
+  while (top < lanes) top <<= 1;
+#pragma unroll   // static indices keep acc[][] in registers
+  for (int t = 0; t < KK; ++t) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) red[tid][v] = acc[t][v];
+    __syncthreads();
+    for (int s = top >> 1; s > 0; s >>= 1) {
+      if (pl < s && pl + s < lanes) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) red[tid][v] += red[tid + s * CGB][v];
+      }
+      __syncthreads();
+    }
+    if (pl == 0 && cg * VEC < C) {
+      float* d = part + ((long long)blockIdx.x * KK + t) * C + cg * VEC;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) d[v] = red[tid][v];
+    }
+    __syncthreads();
+  }
+}
+
+// Stride-1 version with register reuse along x: a thread owns a strip of P consecutive output pixels of one row; per kernel
+// row it loads the P + KS - 1 input vectors of the strip once and every one of them feeds up to KS taps
+// (loads per pixel and kernel row: (P + KS - 1) / P instead of KS -- the per-pixel kernel above is LSU-bound at
+// 0.1-0.7 TB/s, profiles/r1_train_step_b.md).  Work unit = (image, output row, strip); same partial-sum layout.
+template <int KS, int VEC, int P>
+__global__ void __launch_bounds__(256) dw_wgrad_strip_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ x, long long ldx, int B,
+                                                             int H, int W, int C, int CGB, long long strips_per_block,
+                                                             float* __restrict__ part) {
+  __shared__ float red[256][VEC + 1];
+  constexpr int KK = KS * KS, PAD = KS / 2, XW = P + KS - 1;
+  const int tid = threadIdx.x;
+  const int lanes = 256 / CGB;
+  const int cgl = tid % CGB, pl = tid / CGB;
+  const int cg = blockIdx.y * CGB + cgl;
+  const bool active = pl < lanes && cg * VEC < C;
+  float acc[KK][VEC];
+#pragma unroll
+  for (int t = 0; t < KK; ++t)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[t][v] = 0.f;
+  const int spr = (W + P - 1) / P;                           // strips per row (stride 1: Ho = H, Wo = W)
+  const long long total = (long long)B * H * spr;
+  const long long s0 = (long long)blockIdx.x * strips_per_block, s1 = min(total, s0 + strips_per_block);
+  if (active) {
+    for (long long sidx = s0 + pl; sidx < s1; sidx += lanes) {
+      const int xs = (int)(sidx % spr), oy = (int)((sidx / spr) % H), b = (int)(sidx / ((long long)spr * H));
+      const int ox0 = xs * P;
+      float g[P][VEC];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        if (ox0 + j < W) {
+          ldvec<VEC>(dz + (((long long)b * H + oy) * W + ox0 + j) * C + cg * VEC, g[j]);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) g[j][v] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky) {
+        const int iy = oy + ky - PAD;
+        if (iy < 0 || iy >= H) continue;
+        const bf16* xrow = x + ((long long)b * H + iy) * W * ldx + cg * VEC;
+        float xr[XW][VEC];
+#pragma unroll
+        for (int j = 0; j < XW; ++j) {
+          const int ix = ox0 - PAD + j;
+          if (ix >= 0 && ix < W) {
+            ldvec<VEC>(xrow + (long long)ix * ldx, xr[j]);
+          } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) xr[j][v] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+          for (int j = 0; j < P; ++j)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[ky * KS + kx][v] = fmaf(g[j][v], xr[j + kx][v], acc[ky * KS + kx][v]);
       }
     }
   }
@@ -847,7 +960,7 @@ extern "C" int es3_bn_stats(const void* z, long long M, int C, float eps, float 
   cudaStream_t st = (cudaStream_t)stream;
   col_reduce_kernel<ACT_NONE, true><<<dim3(nblk, gy), CR_THREADS, 0, st>>>((const bf16*)z, nullptr, nullptr, nullptr, M, C, CVB, rpb, ws);
   ES3_LAUNCH_CHECK("col_reduce_kernel<stats>");
-  bn_stats_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const bf16*)z, ws, nblk, C, M, eps, momentum, gamma, beta, mean, invstd, scale, shift,
+  bn_stats_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>((const bf16*)z, ws, nblk, C, M, eps, momentum, gamma, beta, mean, invstd, scale, shift,
                                                             running_mean, running_var, num_batches_tracked);
   ES3_LAUNCH_CHECK("bn_stats_finalize_kernel");
   return 0;
@@ -881,7 +994,7 @@ extern "C" int es3_bn_act_bwd_reduce(const void* da, const void* z, const float*
     col_reduce_kernel<A, false><<<dim3(nblk, gy), CR_THREADS, 0, st>>>((const bf16*)z, (const bf16*)da, scale, shift, M, C, CVB, rpb, ws);
   })
   ES3_LAUNCH_CHECK("col_reduce_kernel<bwd>");
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, nblk, C, M, mode, scale, mean, invstd, coef, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(ws, nblk, C, M, mode, scale, mean, invstd, coef, dgamma, dbeta);
   ES3_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   return 0;
 }
@@ -957,7 +1070,7 @@ extern "C" int es3_wgrad_pw(const void* dz, long long lddz, const void* x, long 
 #undef ES3_WG
   if (rc != 0) return rc;
   const long long n = (long long)N * K;
-  sum_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ws, splits, n, K, ldn, ldk, dW);
+  sum_partials_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, st>>>(ws, splits, n, K, ldn, ldk, dW);
   ES3_LAUNCH_CHECK("sum_partials_kernel");
   return 0;
 }
@@ -974,13 +1087,26 @@ extern "C" int es3_dwconv_bwd_data(const void* dz, const float* w, void* dx, int
   return 0;
 }
 
-static int dw_wgrad_geometry(int B, int Ho, int Wo, int C, int ks, int* CGB, int* nblk, long long* ppb, int* gy) {
+constexpr int DWS_P3 = 4, DWS_P5 = 8;   // strip lengths of the stride-1 kernels (3x3: 8 channels / thread, 5x5: 4 channels / thread)
+
+// units = output pixels (stride 2, per-pixel kernel) or strips (stride 1, strip kernel)
+static int dw_wgrad_geometry(int B, int Ho, int Wo, int C, int ks, int stride, int* CGB, int* nblk, long long* upb, int* gy) {
   const int vec = ks == 3 ? 8 : 4;
   const int CG = C / vec;
   *CGB = CG < 256 ? CG : 256;
-  const long long total = (long long)B * Ho * Wo;
-  *nblk = pick_blocks(total, 256 / *CGB, 1184);
-  *ppb = (total + *nblk - 1) / *nblk;
+  const int lanes = 256 / *CGB;
+  long long total = (long long)B * Ho * Wo;
+  if (stride == 1) {
+    const int P = ks == 3 ? DWS_P3 : DWS_P5;
+    total = (long long)B * Ho * ((Wo + P - 1) / P);
+    long long want = (total + (long long)lanes * 8 - 1) / ((long long)lanes * 8);     // >= 8 strips per lane and block
+    if (want < 1) want = 1;
+    if (want > 1184) want = 1184;
+    *nblk = (int)want;
+  } else {
+    *nblk = pick_blocks(total, lanes, 1184);
+  }
+  *upb = (total + *nblk - 1) / *nblk;
   *gy = (CG + *CGB - 1) / *CGB;
   return 0;
 }
@@ -990,7 +1116,7 @@ extern "C" long long es3_dwconv_wgrad_ws_floats(int B, int H, int W, int C, int 
   const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
   int CPB, nblk, gy;
   long long ppb;
-  dw_wgrad_geometry(B, Ho, Wo, C, ks, &CPB, &nblk, &ppb, &gy);
+  dw_wgrad_geometry(B, Ho, Wo, C, ks, stride, &CPB, &nblk, &ppb, &gy);
   return (long long)nblk * ks * ks * C;
 }
 
@@ -1003,16 +1129,20 @@ extern "C" int es3_dwconv_wgrad(const void* dz, const void* x, long long ldx, in
   const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
   int CPB, nblk, gy;
   long long ppb;
-  dw_wgrad_geometry(B, Ho, Wo, C, ks, &CPB, &nblk, &ppb, &gy);
+  dw_wgrad_geometry(B, Ho, Wo, C, ks, stride, &CPB, &nblk, &ppb, &gy);
   cudaStream_t st = (cudaStream_t)stream;
-  if (ks == 3)
+  if (stride == 1 && ks == 3)
+    dw_wgrad_strip_kernel<3, 8, DWS_P3><<<dim3(nblk, gy), 256, 0, st>>>((const bf16*)dz, (const bf16*)x, ldx, B, H, W, C, CPB, ppb, ws);
+  else if (stride == 1)
+    dw_wgrad_strip_kernel<5, 4, DWS_P5><<<dim3(nblk, gy), 256, 0, st>>>((const bf16*)dz, (const bf16*)x, ldx, B, H, W, C, CPB, ppb, ws);
+  else if (ks == 3)
     dw_wgrad_kernel<3, 8><<<dim3(nblk, gy), 256, 0, st>>>((const bf16*)dz, (const bf16*)x, ldx, B, H, W, C, Ho, Wo, stride, CPB, ppb, ws);
   else
     dw_wgrad_kernel<5, 4><<<dim3(nblk, gy), 256, 0, st>>>((const bf16*)dz, (const bf16*)x, ldx, B, H, W, C, Ho, Wo, stride, CPB, ppb, ws);
   ES3_LAUNCH_CHECK("dw_wgrad_kernel");
   const long long n = (long long)ks * ks * C;
   // part index i = tap * C + c  ->  dW[c * ks*ks + tap]
-  sum_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ws, nblk, n, C, 1, (long long)ks * ks, dW);
+  sum_partials_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, st>>>(ws, nblk, n, C, 1, (long long)ks * ks, dW);
   ES3_LAUNCH_CHECK("sum_partials_kernel");
   return 0;
 }
@@ -1042,7 +1172,7 @@ extern "C" int es3_stem_wgrad(const float* img, const void* dz, int B, int H, in
   stem_wgrad_kernel<<<nblk, threads, 0, st>>>(img, (const bf16*)dz, B, H, W, Ho, Wo, Cout, cpb, ws);
   ES3_LAUNCH_CHECK("stem_wgrad_kernel");
   const long long n = (long long)Cout * 27;
-  sum_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ws, nblk, n, 27, 27, 1, dW);
+  sum_partials_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, st>>>(ws, nblk, n, 27, 27, 1, dW);
   ES3_LAUNCH_CHECK("sum_partials_kernel");
   return 0;
 }
@@ -1064,7 +1194,7 @@ extern "C" int es3_transpose_pad_bf16(const void* in, void* out, int B, int H, i
 extern "C" int es3_accumulate_strided(const float* src, long long n, int inner, long long ld_outer, long long ld_inner, float* dst,
                                       void* stream) {
   ES3_REQUIRE(n > 0 && inner > 0, "es3_accumulate_strided: bad shape");
-  sum_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, 1, n, inner, ld_outer, ld_inner, dst);
+  sum_partials_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, (cudaStream_t)stream>>>(src, 1, n, inner, ld_outer, ld_inner, dst);
   ES3_LAUNCH_CHECK("sum_partials_kernel");
   return 0;
 }

@@ -1,4 +1,4 @@
-"""Stage-1 KD loss (forward) on the native path: masked MSE + masked cosine between student and teacher embeddings,
+"""Stage-1 KD loss and KD steps on the native path: masked MSE + masked cosine between student and teacher embeddings,
 stage1/train_image_encoder_stage1.py:205-210, 271-307.  One streaming kernel + a fixed-order final reduction."""
 from __future__ import annotations
 
@@ -24,3 +24,29 @@ def kd_eval_step(student, teacher_model, images, img_size_before_pad, cosine_wei
     t = teacher_model(images).half().float()
     s = student(images)
     return kd_loss(s, t, images.shape[-1], img_size_before_pad, cosine_weight)
+
+
+def kd_train_step(student, optimizer, images, teacher_embeddings, img_size_before_pad, cosine_weight: float = 1.0,
+                  clip_grad: float = 5.0, lr: float | None = None, group=None):
+    """One iteration of the reference's train_one_epoch (stage1/train_image_encoder_stage1.py:185-230), everything on the
+    device and on libes3 kernels:
+
+        preds = model(samples)                 train-mode student forward (one autograd node, batch-statistics or frozen BN)
+        loss  = masked_mse + COSINE * cosine   es3_kd_loss_fwd            (targets: stored / online teacher embeddings, fp32)
+        loss_scaler(loss, optimizer, ...)      es3_kd_loss_bwd -> native student backward -> ONE all-reduce of the flat gradient
+                                               arena (data parallel) -> global-norm clip + fused AdamW
+
+    `optimizer` is a stage1.optim.FlatAdamW built on `student` (parameters and gradients live in its flat arenas, so the
+    backward accumulates straight into the buffer that is all-reduced).  Returns the detached loss (device scalar; no host sync).
+    """
+    from .optim import KDLossFunction
+    if not student.training:
+        raise RuntimeError("kd_train_step expects student.train() (freeze BN with set_bn_state-style .eval() on the BN modules)")
+    sizes = torch.tensor([[int(s[1]), int(s[2])] for s in img_size_before_pad], dtype=torch.int32, device=images.device)
+    optimizer.zero_grad()
+    preds = student(images)
+    loss = KDLossFunction.apply(preds, teacher_embeddings, sizes, images.shape[-1], cosine_weight)
+    (loss * optimizer.loss_scale_tensor[0]).backward()       # GradScaler.scale(loss).backward(): the scale stays on the device
+    world = optimizer.all_reduce_grads(group)
+    optimizer.step(lr=lr, max_norm=clip_grad, world_size=world)
+    return loss.detach()

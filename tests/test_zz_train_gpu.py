@@ -175,7 +175,8 @@ def test_conv3x3_wgrad_tc(cuda, B, H, W, N, C):
 
 
 @pytest.mark.parametrize("B,H,W,C,ks,stride", [(2, 17, 23, 64, 3, 2), (1, 32, 32, 256, 3, 2), (2, 16, 16, 16, 3, 1), (1, 9, 11, 96, 5, 1),
-                                               (2, 8, 8, 1024, 3, 2), (1, 21, 20, 128, 5, 2)])
+                                               (2, 8, 8, 1024, 3, 2), (1, 21, 20, 128, 5, 2), (2, 13, 19, 64, 3, 1), (1, 7, 5, 32, 5, 1), (2, 64, 64, 384, 5, 1),
+                                               (2, 40, 40, 512, 3, 1)])
 def test_dwconv_gradients(cuda, B, H, W, C, ks, stride):
     from efficientsam3_b200 import ops
     g = _g(B * H + C + ks)
