@@ -307,7 +307,38 @@ def other_encoders(dev, S, E):
                                     "frac_of_hbm_peak": round(gbs / _peaks()["hbm"], 3)}
     del ev, opt
     torch.cuda.empty_cache()
+    # the whole stage-1 KD training iteration (config 2 minus the frozen teacher, whose embeddings the reference loop reads
+    # from the store): train-mode student forward (batch-statistics BN) -> KD loss -> native backward -> fused AdamW
+    try:
+        out["kd_train_step_evm"] = kd_train_step_leg(dev, S, E, batch=32, steps=3, warm=2)
+    except Exception as e:  # never let a side measurement take the headline line down
+        out["kd_train_step_evm"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    torch.cuda.empty_cache()
     return out
+
+
+def kd_train_step_leg(dev, S, E, batch, steps, warm, dist=None):
+    """ms per stage-1 KD training iteration on this rank's GPU (data parallel when `dist` is given: one all-reduce of the flat
+    gradient arena per step, stage1/optim.FlatAdamW.all_reduce_grads); max over ranks is taken by the caller."""
+    from efficientsam3_b200.stage1.losses import kd_train_step
+    from efficientsam3_b200.stage1.optim import FlatAdamW
+    m = build_student(S, E, dev).train()
+    opt = FlatAdamW(m, lr=1e-4, weight_decay=0.01)
+    xs = [torch.randn(batch, 3, S, S, device=dev) for _ in range(2)]
+    teacher = torch.randn(batch, 1024, E, E, device=dev).half().float()
+    sizes = [(3, S, S * 3 // 4) if i % 2 == 0 else (3, S * 2 // 3, S) for i in range(batch)]
+    state = {"i": 0}
+
+    def step():
+        state["loss"] = kd_train_step(m, opt, xs[state["i"] % 2], teacher, sizes, 1.0, 5.0)
+        state["i"] += 1
+
+    n0 = ops.launch_count
+    ms = _time_steps(step, warm, steps)
+    world = dist.get_world_size() if dist is not None else 1
+    return {"ms_per_step": round(ms, 2), "images_per_s_per_gpu": round(batch / ms * 1e3, 1), "batch_per_gpu": batch, "img": S,
+            "bn": "batch statistics", "loss": round(float(state["loss"].item()), 3), "world": world,
+            "es3_launches_per_step": (ops.launch_count - n0) // (warm + steps), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1)}
 
 
 def cpu_oracle_throughput(S, E, batch, steps, warmup):

@@ -59,6 +59,60 @@ def gen_student(backbone, tag, img, embed, seed_w, seed_x, batch=1):
           "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def _ref_loss_functions():
+    """build_valid_mask / masked_mse / masked_cosine_loss, executed from the reference's own source
+    (stage1/train_image_encoder_stage1.py:271-307).  The script itself is not importable here (yacs, timm.scheduler, ...),
+    so only these three function definitions are compiled from its AST -- nothing is copied into the repo."""
+    import ast
+    import torch.nn.functional as F
+    path = "/root/reference/stage1/train_image_encoder_stage1.py"
+    tree = ast.parse(open(path).read())
+    ns = {"torch": torch, "F": F}
+    want = ("build_valid_mask", "masked_mse", "masked_cosine_loss")
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in want:
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return tuple(ns[k] for k in want)
+
+
+def gen_student_train(backbone, tag, img, embed, seed_w, seed_x, batch=2, cosine=1.0):
+    """One stage-1 training iteration of the UNMODIFIED reference student in .train() (batch-statistics BatchNorm), fp64:
+    preds = model(x); loss = masked_mse + COSINE * masked_cosine (the reference's own functions); loss.backward().
+    Records the output, the losses, every parameter gradient (norm, sum, first 4 entries) and the updated BN buffers.
+    fp64 because the random-weight batch-BN network is ill-conditioned in fp32 (2.5e-3 between fp32 and fp64 gradients)."""
+    import model as stage1_model
+    build_valid_mask, masked_mse, masked_cosine_loss = _ref_loss_functions()
+    cfg = NS(MODEL=NS(BACKBONE=backbone), DATA=NS(IMG_SIZE=img), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=embed))
+    m = stage1_model.build_image_student_model(cfg)
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed_w))
+    m = m.double().train()
+    g = torch.Generator().manual_seed(seed_x)
+    x = torch.randn(batch, 3, img, img, generator=g).double()
+    teacher = torch.randn(batch, 1024, embed, embed, generator=g).double()
+    sizes = [(3, img, img * 3 // 4) if i % 2 == 0 else (3, img * 2 // 3, img) for i in range(batch)]
+    with torch.enable_grad():
+        out = m(x)
+        mask = build_valid_mask(cfg, sizes, out.shape, out.device).double()
+        mse = masked_mse(out, teacher, mask)
+        cos = masked_cosine_loss(out, teacher, mask)
+        loss = mse + cosine * cos
+        loss.backward()
+    names, gstat = [], []
+    for k, p in m.named_parameters():
+        gr = p.grad.reshape(-1)
+        first = torch.zeros(4, dtype=torch.float64)
+        first[:min(4, gr.numel())] = gr[:4]
+        names.append(k)
+        gstat.append(torch.cat([gr.norm().reshape(1), gr.sum().reshape(1), first]).numpy())
+    bufs = {k: v.detach().numpy() for k, v in m.state_dict().items() if "running_" in k and ("input_stem" in k or "head." in k or "stages.3.op_list.4" in k)}
+    path = os.path.join(HERE, f"{tag}.npz")
+    np.savez_compressed(path, out=out.detach()[:, ::8].numpy(), loss=np.array([loss.item(), mse.item(), cos.item()]), grad_names=np.array(names),
+                        grad_stats=np.stack(gstat), buf_names=np.array(list(bufs.keys())), **{f"buf{i}": v for i, v in enumerate(bufs.values())},
+                        keys=keyshapes(m.float().state_dict()), img=img, embed=embed, seed_w=seed_w, seed_x=seed_x, batch=batch, cosine=cosine,
+                        sizes=np.array(sizes))
+    print(tag, "loss %.6f" % loss.item(), "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 VIT_SMALL = dict(img_size=112, pretrain_img_size=56, patch_size=14, embed_dim=256, depth=4, num_heads=4, mlp_ratio=4.625,
                  window_size=4, global_att_blocks=(1, 3))
 
@@ -233,6 +287,8 @@ def gen_store(tag, n_rank=2, embed_dim=8, num_embedding=6):
 
 
 def main(which):
+    if which in ("train", "all"):
+        gen_student_train("efficientvit_b1", "evm_train_160", img=160, embed=12, seed_w=71, seed_x=72)
     if which in ("tvm", "all"):
         gen_student("tiny_vit_11m", "tvm_160", img=160, embed=12, seed_w=61, seed_x=62, batch=1)
     if which in ("store", "all"):

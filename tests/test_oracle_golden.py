@@ -152,3 +152,33 @@ def test_prompt_and_postprocess_oracle_matches_reference():
         post = F.interpolate(O.fill_holes(torch.from_numpy(g["post_in"]), 0.0, 12.0, 5.0), (50, 70), mode="bilinear", align_corners=False)
     assert int(g["post_changed_px"]) > 100
     assert np.array_equal(post.numpy(), g["post_out"])       # same fp32 ops on the same labels: exact
+
+
+def test_efficientvit_train_mode_oracle_matches_reference_training_step():
+    """The oracle under bn_batch_stats() + oracle.kd_loss + autograd vs one training iteration of the unmodified reference
+    student in .train() with the reference's own masked_mse / masked_cosine_loss / build_valid_mask (fixture in fp64:
+    output, losses, every parameter gradient's norm / sum / leading entries, updated BN running statistics)."""
+    from oracle import efficientvit as O
+    from oracle.kd_loss import kd_loss
+    g = _load("evm_train_160")
+    img, embed, batch = int(g["img"]), int(g["embed"]), int(g["batch"])
+    sd32 = _sd_from_keys(g["keys"], int(g["seed_w"]))
+    sd = {k: ((v.double().requires_grad_(True) if "running" not in k else v.double()) if v.is_floating_point() else v.clone())
+          for k, v in sd32.items()}
+    gen = torch.Generator().manual_seed(int(g["seed_x"]))
+    x = torch.randn(batch, 3, img, img, generator=gen).double()
+    teacher = torch.randn(batch, 1024, embed, embed, generator=gen).double()
+    sizes = [tuple(int(v) for v in r) for r in g["sizes"]]
+    with O.bn_batch_stats():
+        out = O.image_student_encoder(sd, x, embed, "b1")
+    loss, mse, cos = kd_loss(out, teacher, img, sizes, float(g["cosine"]))
+    loss.backward()
+    np.testing.assert_allclose(out.detach()[:, ::8].numpy(), g["out"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose([loss.item(), mse.item(), cos.item()], g["loss"], rtol=1e-10)
+    scale = float(g["grad_stats"][:, 0].max())
+    for name, ref in zip(g["grad_names"], g["grad_stats"]):
+        gr = sd[str(name)].grad.reshape(-1)
+        got = np.concatenate([[gr.norm().item(), gr.sum().item()], np.pad(gr[:4].numpy(), (0, max(0, 4 - gr.numel())))])
+        np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-9 * scale, err_msg=str(name))
+    for i, name in enumerate(g["buf_names"]):
+        np.testing.assert_allclose(sd[str(name)].numpy(), g[f"buf{i}"], rtol=1e-10, atol=1e-12, err_msg=str(name))
