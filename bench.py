@@ -320,6 +320,7 @@ def other_encoders(dev, S, E):
 def kd_train_step_leg(dev, S, E, batch, steps, warm, dist=None):
     """ms per stage-1 KD training iteration on this rank's GPU (data parallel when `dist` is given: one all-reduce of the flat
     gradient arena per step, stage1/optim.FlatAdamW.all_reduce_grads); max over ranks is taken by the caller."""
+    from efficientsam3_b200 import ops
     from efficientsam3_b200.stage1.losses import kd_train_step
     from efficientsam3_b200.stage1.optim import FlatAdamW
     m = build_student(S, E, dev).train()
