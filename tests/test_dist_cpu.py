@@ -77,3 +77,77 @@ def test_two_rank_flat_gradient_allreduce():
     [p.join(timeout=60) for p in ps]
     assert all(r[1] and r[2] for r in res)
     assert res[0][3] == res[1][3]                                   # both ranks hold the same summed arena
+
+
+def _student_dp_worker(rank, world, port, q):
+    """Data-parallel KD iteration of the native student (ops emulated in fp64, frozen BN so that ranks are exchangeable):
+    train-mode forward -> KD loss -> native backward INTO the flat arena -> one all-reduce.  The averaged arena must equal
+    the gradient of the same model on the concatenated batch."""
+    import sys
+    from types import SimpleNamespace as NS
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(4)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emu_ops
+    from efficientsam3_b200 import ops
+    from efficientsam3_b200.stage1.model import build_image_student_model
+    from efficientsam3_b200.stage1.optim import FlatAdamW
+    from oracle.kd_loss import kd_loss
+    from oracle.weights import fill_state_dict
+
+    class _Patch:
+        def setattr(self, obj, name, value):
+            setattr(obj, name, value)
+
+    emu_ops.install(_Patch())
+    emu_ops.BF = emu_ops.CD = torch.float64
+    ops.ACT_DTYPE = torch.float64
+    img, embed, b = 160, 12, 1
+    cfg = NS(MODEL=NS(BACKBONE="efficientvit_b0"), DATA=NS(IMG_SIZE=img), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=embed))
+
+    def make():
+        m = build_image_student_model(cfg)
+        m.load_state_dict(fill_state_dict(m.state_dict(), 5))
+        m.train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                mod.eval()
+        return m
+
+    g = torch.Generator().manual_seed(7)
+    x_all = torch.randn(world * b, 3, img, img, generator=g)
+    t_all = torch.randn(world * b, 1024, embed, embed, generator=g).double()
+    sizes = [(3, img, img)] * (world * b)
+
+    # the global-batch reference first (before this rank takes part in any collective)
+    ref = make()
+    ropt = FlatAdamW(ref, lr=1e-3)
+    ropt.zero_grad()
+    rl, _, _ = kd_loss(ref(x_all), t_all, img, sizes, 1.0)
+    rl.backward()
+
+    m = make()
+    opt = FlatAdamW(m, lr=1e-3)
+    opt.zero_grad()
+    sl = slice(rank * b, (rank + 1) * b)
+    loss, _, _ = kd_loss(m(x_all[sl]), t_all[sl], img, sizes[sl], 1.0)
+    loss.backward()                                    # accumulates into opt.flat_grad through the p.grad views
+    n = opt.all_reduce_grads()
+    mean_grad = opt.flat_grad / n
+    err = ((mean_grad - ropt.flat_grad).norm() / ropt.flat_grad.norm()).item()
+    q.put((rank, n, err, float(mean_grad.abs().sum())))
+    dist.destroy_process_group()
+
+
+def test_two_rank_student_kd_iteration_matches_the_global_batch():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_student_dp_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    [p.join(timeout=60) for p in ps]
+    assert all(r[1] == world for r in res)
+    assert all(r[2] < 1e-5 for r in res), res             # fp32 accumulators in the arena are the only rounding left
+    assert res[0][3] == res[1][3] and res[0][3] > 0         # both ranks hold the same averaged arena
