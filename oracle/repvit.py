@@ -2,7 +2,8 @@
 Restates sam3/sam3/backbones/repvit.py: Conv2d_BN :27-49, Residual :51-81, RepVGGDW :84-122, RepViTBlock :125-161,
 RepViT.features :219-246, configs :253-384; SqueezeExcite = timm.layers.SqueezeExcite(inp, 0.25) (un-vendored;
 mean_HW -> fc1 (1x1, bias) -> ReLU -> fc2 (1x1, bias) -> sigmoid gate); RepViTAdapter stage1/model.py:287-296.
-Eval mode, un-fused (exactly what the reference module executes)."""
+Un-fused (exactly what the reference module executes); eval-mode BatchNorm by default, batch statistics inside
+`oracle.efficientvit.bn_batch_stats()` (the train-mode forward whose autograd is the oracle of the RepViT backward)."""
 from __future__ import annotations
 
 import torch
@@ -27,9 +28,9 @@ CFGS = {
 
 
 def conv_bn(sd, p, x, stride=1, pad=0, groups=1):
+    from .efficientvit import _bn
     x = F.conv2d(x, sd[p + ".c.weight"], None, stride=stride, padding=pad, groups=groups)
-    return F.batch_norm(x, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"], sd[p + ".bn.weight"], sd[p + ".bn.bias"],
-                        training=False, eps=1e-5)
+    return _bn(x, sd, p + ".bn")
 
 
 def squeeze_excite(sd, p, x):
@@ -49,8 +50,8 @@ def block(sd, p, x, stride, use_se):
     else:
         q = p + ".token_mixer.0"
         y = conv_bn(sd, q + ".conv", x, pad=1, groups=c) + F.conv2d(x, sd[q + ".conv1.weight"], sd[q + ".conv1.bias"], groups=c) + x
-        x = F.batch_norm(y, sd[q + ".bn.running_mean"], sd[q + ".bn.running_var"], sd[q + ".bn.weight"], sd[q + ".bn.bias"],
-                         training=False, eps=1e-5)
+        from .efficientvit import _bn
+        x = _bn(y, sd, q + ".bn")
         if use_se:
             x = squeeze_excite(sd, p + ".token_mixer.1", x)
     m = p + ".channel_mixer.m"

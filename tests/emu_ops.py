@@ -140,6 +140,25 @@ def nchw_f32_to_nhwc(x):
     return _nhwc(x).to(BF)
 
 
+def gemm_simt(a, w, *, scale=None, bias=None, act=None, residual=None, out=None, out_dtype=None):
+    return gemm(a, w, scale=scale, bias=bias, act=act, residual=residual, out=out, out_dtype=out_dtype)
+
+
+def channel_mean(x):
+    return x.to(CD).mean((1, 2))
+
+
+def scale_channels(x, gate):
+    return (x.to(CD) * gate.to(CD)[:, None, None, :]).to(BF)
+
+
+def conv3x3_s2_narrow(x, w9, scale, bias, act=None):
+    cout, cin = w9.shape[1], w9.shape[2]
+    w = w9.to(CD).reshape(3, 3, cout, cin).permute(2, 3, 0, 1)
+    v = F.conv2d(_nchw(x), w, None, stride=2, padding=1) * scale.to(CD).view(1, -1, 1, 1) + bias.to(CD).view(1, -1, 1, 1)
+    return _nhwc(_act(v, act)).to(BF)
+
+
 # ------------------------------------------------------------------------------------------ train_bwd.cu ops
 def bn_stats(z, gamma, beta, eps, momentum, running_mean=None, running_var=None, num_batches_tracked=None):
     C = z.shape[-1]
@@ -176,6 +195,9 @@ def bn_act_bwd(da, z, scale, shift, act, mode, mean=None, invstd=None, dgamma=No
     gamma / beta are recovered from (scale, shift, mean, invstd)."""
     C = z.shape[-1]
     zf = z.to(CD).reshape(-1, C).requires_grad_(True)
+    if mode != "none":      # the kernels read a NULL scale / shift as 1 / 0
+        scale = torch.ones(C, dtype=CD) if scale is None else scale
+        shift = torch.zeros(C, dtype=CD) if shift is None else shift
     with torch.enable_grad():
         if mode == "none":
             s = (scale if scale is not None else torch.ones(C, dtype=CD)).clone().requires_grad_(True)
@@ -297,7 +319,7 @@ def litemla_attn_bwd(ms, datt, kv, heads2, eps=1e-15):
     return g.reshape(ms.shape).to(BF)
 
 
-PATCHED = ["gemm", "conv3x3", "stem_conv3x3_s2", "dwconv", "litemla_dwpw_weights", "litemla_aggreg_dwpw", "litemla_attn",
+PATCHED = ["gemm", "gemm_simt", "channel_mean", "scale_channels", "conv3x3_s2_narrow", "conv3x3", "stem_conv3x3_s2", "dwconv", "litemla_dwpw_weights", "litemla_aggreg_dwpw", "litemla_attn",
            "bilinear_nhwc_to_nchw", "nhwc_to_nchw_f32", "nchw_f32_to_nhwc", "bn_stats", "affine_act", "bn_act_bwd", "add_bf16",
            "wgrad_pw", "transpose_pad", "accumulate_strided", "dwconv_bwd_data", "dwconv_wgrad", "stem_wgrad", "bilinear_bwd", "litemla_attn_bwd"]
 

@@ -134,10 +134,11 @@ def test_eval_plan_is_rebuilt_after_a_train_forward(monkeypatch):
 
 def test_train_mode_is_refused_where_it_is_not_built():
     from efficientsam3_b200.stage1.model import build_image_student_model
-    cfg = NS(MODEL=NS(BACKBONE="repvit_m1_1"), DATA=NS(IMG_SIZE=160), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=12))
-    m = build_image_student_model(cfg).train()
-    with pytest.raises(NotImplementedError):
-        m(torch.randn(1, 3, 160, 160))
+    for name in ("tiny_vit_11m", "repvit_m0_9"):      # TinyViT: no train path; RepViT other than m1_1: patch-embed width
+        cfg = NS(MODEL=NS(BACKBONE=name), DATA=NS(IMG_SIZE=160), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=12))
+        m = build_image_student_model(cfg).train()
+        with pytest.raises(NotImplementedError):
+            m(torch.randn(1, 3, 160, 160))
 
 
 @pytest.mark.parametrize("B,H,W,N,C", [(2, 5, 7, 32, 16), (1, 8, 8, 64, 24), (3, 4, 14, 16, 8)])
@@ -154,3 +155,78 @@ def test_conv3x3_wgrad_composition(monkeypatch, B, H, W, N, C):
     got = torch.full((N, C, 3, 3), 0.5)
     ops.conv3x3_wgrad(dy, a, got)
     assert (got - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------- RepViT (config 4)
+def _round_like_product_repvit(sd):
+    """bf16 in the product: every 1x1 Conv2d_BN weight, the second patch-embed conv, the head convs.  fp32: the stem conv,
+    depthwise taps (3x3 and the RepVGGDW 1x1), SqueezeExcite (es3_gemm_simt on fp32), BN vectors."""
+    out = {}
+    for k, v in sd.items():
+        dense = (v.dim() == 4 and v.shape[1] > 1 and (k.endswith(".c.weight") or k in ("head.0.weight", "head.3.weight"))
+                 and not k.endswith("features.0.0.c.weight"))
+        out[k] = v.to(torch.bfloat16).float() if dense else v.clone()
+    return out
+
+
+def _oracle_step_repvit(sd0, x, teacher, img, sizes, embed, bn_train):
+    from oracle import repvit as R
+    sd = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v.clone()) for k, v in sd0.items()}
+    if bn_train:
+        with O.bn_batch_stats():
+            out = R.image_student_encoder(sd, x, embed, "repvit_m1_1")
+    else:
+        out = R.image_student_encoder(sd, x, embed, "repvit_m1_1")
+    loss, _, _ = oracle_kd_loss(out, teacher, img, sizes, 1.0)
+    loss.backward()
+    return out.detach(), loss.detach(), sd
+
+
+@pytest.mark.parametrize("bn_train,exact", [(True, True), (False, True), (False, False)])
+def test_repvit_train_graph_matches_oracle_autograd(monkeypatch, bn_train, exact):
+    """RepViT-M1.1 training graph (un-fused RepVGGDW with batch-statistics BN, SqueezeExcite, stride-2 patch-embed conv through
+    the 2x2 phase decomposition) vs autograd of the oracle; exact = fp64 emulation (logic check), else bf16 storage (frozen BN)."""
+    from efficientsam3_b200 import ops
+    emu_ops.install(monkeypatch)
+    if exact:
+        monkeypatch.setattr(emu_ops, "BF", torch.float64)
+        monkeypatch.setattr(emu_ops, "CD", torch.float64)
+        monkeypatch.setattr(ops, "ACT_DTYPE", torch.float64)
+    img, embed, B = 128, 8, 2
+    m = _student("repvit_m1_1", img=img, embed=embed, seed=11)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(B, 3, img, img, generator=torch.Generator().manual_seed(1))
+    teacher = torch.randn(B, 1024, embed, embed, generator=torch.Generator().manual_seed(2))
+    sizes = [(3, img, img * 3 // 4), (3, img * 2 // 3, img)]
+    m.train()
+    if not bn_train:
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                mod.eval()
+    out = m(x)
+    loss, _, _ = oracle_kd_loss(out, teacher.to(out.dtype), img, sizes, 1.0)
+    loss.backward()
+    if exact:
+        sd_ref = {k: (v.double() if v.is_floating_point() else v) for k, v in _round_like_product_repvit(sd0).items()}
+        ref_out, ref_loss, sd = _oracle_step_repvit(sd_ref, x.double(), teacher.double(), img, sizes, embed, bn_train)
+        tol_out, tol_each, tol_all = 1e-5, 2e-4, 2e-5
+    else:
+        ref_out, ref_loss, sd = _oracle_step_repvit(sd0, x, teacher, img, sizes, embed, bn_train)
+        tol_out, tol_each, tol_all = 3e-2, 0.3, 6e-2
+    assert _rel(out.detach(), ref_out) < tol_out, _rel(out.detach(), ref_out)
+    gscale = max(v.grad.norm().item() for v in sd.values() if v.is_floating_point() and v.grad is not None)
+    num = den = worst = 0.0
+    for name, p in m.named_parameters():
+        assert p.grad is not None, name
+        g_ref = sd[name].grad.double()
+        err = (p.grad.double() - g_ref).norm().item()
+        num += err ** 2
+        den += g_ref.pow(2).sum().item()
+        r = err / max(g_ref.norm().item(), 1e-3 * gscale)
+        assert r < tol_each, (name, r)
+        worst = max(worst, r)
+    print(f"repvit bn_train={bn_train} exact={exact}: out {_rel(out.detach(), ref_out):.2e}, worst grad {worst:.2e}, all grads {(num / den) ** 0.5:.2e}")
+    assert (num / den) ** 0.5 < tol_all
+    for k, v in m.state_dict().items():
+        if "num_batches_tracked" in k:
+            assert int(v) == int(sd0[k]) + (1 if bn_train else 0), k

@@ -309,6 +309,52 @@ def test_student_training_step_matches_oracle_autograd(cuda, name, variant, bn_t
                 assert int(v) == int(sd0[k]) + 1, k
 
 
+@pytest.mark.xfail(strict=False, reason="RepViT training graph = host composition of kernels that each have a GPU parity test, validated on "
+                                        "CPU in fp64 (tests/test_train_cpu.py); the whole step has not run on a GPU yet (round-1 GPU budget "
+                                        "was exhausted before it was written)")
+@pytest.mark.parametrize("bn_train", [False, True])
+def test_repvit_training_step_matches_oracle_autograd(cuda, bn_train):
+    from efficientsam3_b200.stage1.optim import KDLossFunction
+    from oracle import efficientvit as O
+    from oracle import repvit as R
+    from oracle.kd_loss import kd_loss
+    img, embed, B = 256, 16, 4
+    m = _student("repvit_m1_1", img, embed, seed=11)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(B, 3, img, img, generator=_g(1))
+    teacher = torch.randn(B, 1024, embed, embed, generator=_g(2))
+    sizes = [(3, img, img * 3 // 4) if i % 2 == 0 else (3, img * 2 // 3, img) for i in range(B)]
+    m = m.to(cuda).train()
+    if not bn_train:
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                mod.eval()
+    out = m(x.to(cuda))
+    sz = torch.tensor([[s[1], s[2]] for s in sizes], dtype=torch.int32, device=cuda)
+    loss = KDLossFunction.apply(out, teacher.to(cuda), sz, img, 1.0)
+    loss.backward()
+    torch.cuda.synchronize()
+    sd = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v.clone()) for k, v in sd0.items()}
+    if bn_train:
+        with O.bn_batch_stats():
+            ref_out = R.image_student_encoder(sd, x, embed, "repvit_m1_1")
+    else:
+        ref_out = R.image_student_encoder(sd, x, embed, "repvit_m1_1")
+    ref_loss, _, _ = kd_loss(ref_out, teacher, img, sizes, 1.0)
+    ref_loss.backward()
+    rel_out = ((out.detach().cpu().double() - ref_out.detach().double()).norm() / ref_out.detach().double().norm()).item()
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        g = sd[k].grad.double()
+        num += (p.grad.cpu().double() - g).pow(2).sum().item()
+        den += g.pow(2).sum().item()
+    rel_all = (num / den) ** 0.5
+    print(f"repvit_m1_1 bn_train={bn_train}: out rel-L2 {rel_out:.3e}, all-gradient rel-L2 {rel_all:.3e}")
+    tol_out, tol_all = (0.15, 0.6) if bn_train else (2e-2, 5e-2)
+    assert rel_out < tol_out and rel_all < tol_all, (rel_out, rel_all)
+
+
 def test_training_steps_reduce_the_loss_and_are_deterministic(cuda):
     """A few full KD steps (train-mode student -> KD loss -> backward -> FlatAdamW) on one fixed batch: the loss goes down,
     and two identical runs produce bit-identical parameters (fixed-order reductions, no atomics)."""
