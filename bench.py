@@ -313,17 +313,54 @@ def other_encoders(dev, S, E):
         out["kd_train_step_evm"] = kd_train_step_leg(dev, S, E, batch=32, steps=3, warm=2)
     except Exception as e:  # never let a side measurement take the headline line down
         out["kd_train_step_evm"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-    torch.cuda.empty_cache()
+    # the same iteration for the RepViT-M1.1 student (config 4, per-GPU share: 32 of the global 256).  Its training graph is a host
+    # composition of kernels that each have GPU parity tests; the whole step was first run on a GPU by this measurement.
+    try:
+        torch.cuda.empty_cache()
+        out["kd_train_step_rvm"] = kd_train_step_leg(dev, S, E, batch=32, steps=3, warm=2, backbone="repvit_m1_1")
+    except Exception as e:
+        out["kd_train_step_rvm"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    # config 2 as BASELINE.json words it: EV-M student + frozen ViT teacher in the loop, batch 32, at the teacher's native 1008 px
+    try:
+        torch.cuda.empty_cache()
+        out["config2_online_kd_step"] = online_kd_step_leg(dev, batch=32, steps=2, warm=1)
+    except Exception as e:
+        out["config2_online_kd_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    try:
+        torch.cuda.empty_cache()
+    except Exception:
+        pass
     return out
 
 
-def kd_train_step_leg(dev, S, E, batch, steps, warm, dist=None):
+def online_kd_step_leg(dev, batch, steps, warm):
+    from efficientsam3_b200.stage1.losses import kd_train_step_online
+    from efficientsam3_b200.stage1.model import SAM3ImageTeacherEncoder
+    from efficientsam3_b200.stage1.optim import FlatAdamW
+    S, E = 1008, 72
+    teacher = SAM3ImageTeacherEncoder(embed_size=E).to(dev)
+    m = build_student(S, E, dev).train()
+    opt = FlatAdamW(m, lr=1e-4, weight_decay=0.01)
+    x = torch.randn(batch, 3, S, S, device=dev)
+    sizes = [(3, S, S * 3 // 4) if i % 2 == 0 else (3, S * 2 // 3, S) for i in range(batch)]
+    state = {}
+
+    def step():
+        state["loss"] = kd_train_step_online(m, teacher, opt, x, sizes, 1.0, 5.0)
+
+    ms = _time_steps(step, warm, steps)
+    return {"ms_per_step": round(ms, 1), "images_per_s": round(batch / ms * 1e3, 1), "batch": batch, "img": S, "embed": E,
+            "what": "frozen ViT teacher forward (chunks of 8) -> fp16-rounded targets -> EV-M train-mode forward -> KD loss -> backward -> AdamW",
+            "loss": round(float(state["loss"].item()), 3), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1)}
+
+
+def kd_train_step_leg(dev, S, E, batch, steps, warm, dist=None, backbone="efficientvit_b1"):
     """ms per stage-1 KD training iteration on this rank's GPU (data parallel when `dist` is given: one all-reduce of the flat
     gradient arena per step, stage1/optim.FlatAdamW.all_reduce_grads); max over ranks is taken by the caller."""
     from efficientsam3_b200 import ops
     from efficientsam3_b200.stage1.losses import kd_train_step
     from efficientsam3_b200.stage1.optim import FlatAdamW
-    m = build_student(S, E, dev).train()
+    m = build_student(S, E, dev, backbone).train()
     opt = FlatAdamW(m, lr=1e-4, weight_decay=0.01)
     xs = [torch.randn(batch, 3, S, S, device=dev) for _ in range(2)]
     teacher = torch.randn(batch, 1024, E, E, device=dev).half().float()
@@ -337,7 +374,7 @@ def kd_train_step_leg(dev, S, E, batch, steps, warm, dist=None):
     n0 = ops.launch_count
     ms = _time_steps(step, warm, steps)
     world = dist.get_world_size() if dist is not None else 1
-    return {"ms_per_step": round(ms, 2), "images_per_s_per_gpu": round(batch / ms * 1e3, 1), "batch_per_gpu": batch, "img": S,
+    return {"student": backbone, "ms_per_step": round(ms, 2), "images_per_s_per_gpu": round(batch / ms * 1e3, 1), "batch_per_gpu": batch, "img": S,
             "bn": "batch statistics", "loss": round(float(state["loss"].item()), 3), "world": world,
             "es3_launches_per_step": (ops.launch_count - n0) // (warm + steps), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1)}
 

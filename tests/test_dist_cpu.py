@@ -151,3 +151,69 @@ def test_two_rank_student_kd_iteration_matches_the_global_batch():
     assert all(r[1] == world for r in res)
     assert all(r[2] < 1e-5 for r in res), res             # fp32 accumulators in the arena are the only rounding left
     assert res[0][3] == res[1][3] and res[0][3] > 0         # both ranks hold the same averaged arena
+
+
+def _student_ddp_worker(rank, world, port, q):
+    """The reference's own arrangement: torch DistributedDataParallel around the (native) student, loss.backward(), gradients
+    averaged by DDP's bucketed all-reduce (train_image_encoder_stage1.py:96-101).  The native forward is ONE autograd node fed
+    by the parameters, so DDP's per-parameter hooks fire as for any module."""
+    import sys
+    from types import SimpleNamespace as NS
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(4)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emu_ops
+    from efficientsam3_b200 import ops
+    from efficientsam3_b200.stage1.model import build_image_student_model
+    from oracle.kd_loss import kd_loss
+    from oracle.weights import fill_state_dict
+
+    class _Patch:
+        def setattr(self, obj, name, value):
+            setattr(obj, name, value)
+
+    emu_ops.install(_Patch())
+    emu_ops.BF = emu_ops.CD = torch.float64
+    ops.ACT_DTYPE = torch.float64
+    img, embed, b = 160, 12, 1
+    cfg = NS(MODEL=NS(BACKBONE="efficientvit_b0"), DATA=NS(IMG_SIZE=img), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=embed))
+
+    def make():
+        m = build_image_student_model(cfg)
+        m.load_state_dict(fill_state_dict(m.state_dict(), 5))
+        m.train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                mod.eval()
+        return m
+
+    g = torch.Generator().manual_seed(7)
+    x_all = torch.randn(world * b, 3, img, img, generator=g)
+    t_all = torch.randn(world * b, 1024, embed, embed, generator=g).double()
+    sizes = [(3, img, img)] * (world * b)
+    ref = make()
+    rl, _, _ = kd_loss(ref(x_all), t_all, img, sizes, 1.0)
+    rl.backward()
+
+    ddp = torch.nn.parallel.DistributedDataParallel(make(), broadcast_buffers=False)
+    sl = slice(rank * b, (rank + 1) * b)
+    loss, _, _ = kd_loss(ddp(x_all[sl]), t_all[sl], img, sizes[sl], 1.0)
+    loss.backward()
+    num = den = 0.0
+    for (k, p), (_, r) in zip(ddp.module.named_parameters(), ref.named_parameters()):
+        num += (p.grad.double() - r.grad.double()).pow(2).sum().item()
+        den += r.grad.double().pow(2).sum().item()
+    q.put((rank, (num / den) ** 0.5))
+    dist.destroy_process_group()
+
+
+def test_two_rank_torch_ddp_around_the_native_student():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_student_ddp_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    [p.join(timeout=60) for p in ps]
+    assert all(r[1] < 1e-5 for r in res), res
