@@ -27,7 +27,8 @@ def kd_eval_step(student, teacher_model, images, img_size_before_pad, cosine_wei
 
 
 def kd_train_step(student, optimizer, images, teacher_embeddings, img_size_before_pad, cosine_weight: float = 1.0,
-                  clip_grad: float = 5.0, lr: float | None = None, group=None):
+                  clip_grad: float = 5.0, lr: float | None = None, group=None, accumulation_steps: int = 1,
+                  update: bool = True):
     """One iteration of the reference's train_one_epoch (stage1/train_image_encoder_stage1.py:185-230), everything on the
     device and on libes3 kernels:
 
@@ -37,18 +38,23 @@ def kd_train_step(student, optimizer, images, teacher_embeddings, img_size_befor
                                                arena (data parallel) -> global-norm clip + fused AdamW
 
     `optimizer` is a stage1.optim.FlatAdamW built on `student` (parameters and gradients live in its flat arenas, so the
-    backward accumulates straight into the buffer that is all-reduced).  Returns the detached loss (device scalar; no host sync).
+    backward accumulates straight into the buffer that is all-reduced).  Gradient accumulation as in the reference
+    (TRAIN.ACCUMULATION_STEPS, :212-226): the loss is divided by `accumulation_steps`, gradients add up in the arena, and only
+    calls with `update=True` exchange, step and clear it.  Returns the detached (divided) loss, a device scalar -- no host sync.
     """
     from .optim import KDLossFunction
     if not student.training:
         raise RuntimeError("kd_train_step expects student.train() (freeze BN with set_bn_state-style .eval() on the BN modules)")
     sizes = torch.tensor([[int(s[1]), int(s[2])] for s in img_size_before_pad], dtype=torch.int32, device=images.device)
-    optimizer.zero_grad()
     preds = student(images)
     loss = KDLossFunction.apply(preds, teacher_embeddings, sizes, images.shape[-1], cosine_weight)
+    if accumulation_steps != 1:
+        loss = loss / accumulation_steps
     (loss * optimizer.loss_scale_tensor[0]).backward()       # GradScaler.scale(loss).backward(): the scale stays on the device
-    world = optimizer.all_reduce_grads(group)
-    optimizer.step(lr=lr, max_norm=clip_grad, world_size=world)
+    if update:
+        world = optimizer.all_reduce_grads(group)
+        optimizer.step(lr=lr, max_norm=clip_grad, world_size=world)
+        optimizer.zero_grad()                                # as the reference: clear right after the update (:224-225)
     return loss.detach()
 
 

@@ -60,6 +60,7 @@ class FlatAdamW:
         skip = model.no_weight_decay() if hasattr(model, "no_weight_decay") else ()
         skip_kw = model.no_weight_decay_keywords() if hasattr(model, "no_weight_decay_keywords") else ()
         decay, no_decay = split_decay(model.named_parameters(), skip, skip_kw)
+        self._model = model
         self.lr, self.betas, self.eps, self.weight_decay = lr, tuple(betas), eps, weight_decay
         self.dynamic, self.growth_interval = dynamic_loss_scale, growth_interval
         self.names, self.params, self.offsets = [], [], []
@@ -111,6 +112,9 @@ class FlatAdamW:
             raise RuntimeError("FlatAdamW.step runs es3_adamw_flat on the GPU; there is no CPU fallback")
         if lr is not None:
             self.lr = lr
+        for mod in self._model.modules():      # the kernel moves the parameters through raw pointers: cached eval-mode packings are stale
+            if hasattr(mod, "_plan_key"):
+                mod._plan_key = None
         ops.grad_norm(self.flat_grad, self._part_ws, self._norm_ws)
         ops.adamw_flat(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.n_decay, self.lr, self.betas,
                        self.eps, self.weight_decay, max_norm, 1.0 / world_size, self._norm_ws, self.state,

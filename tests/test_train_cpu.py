@@ -230,3 +230,57 @@ def test_repvit_train_graph_matches_oracle_autograd(monkeypatch, bn_train, exact
     for k, v in m.state_dict().items():
         if "num_batches_tracked" in k:
             assert int(v) == int(sd0[k]) + (1 if bn_train else 0), k
+
+
+def test_train_one_epoch_follows_the_reference_loop(monkeypatch):
+    """stage1.train.train_one_epoch with the reference's loader contract: gradient accumulation (loss / ACCUMULATION_STEPS, update
+    and zero_grad every ACCUMULATION_STEPS iterations), per-update LR from the cosine schedule, frozen BN through set_bn_state.
+    The device ops are emulated; the optimiser update (a CUDA kernel) is replaced by a recorder that applies plain SGD."""
+    import numpy as np
+    from efficientsam3_b200.stage1 import optim as OPT
+    from efficientsam3_b200.stage1.train import train_one_epoch
+    emu_ops.install(monkeypatch)
+    img, embed, B, iters, accum = 160, 12, 1, 4, 2
+
+    # KD loss ops on CPU: the oracle's loss through autograd stands in for es3_kd_loss_fwd / _bwd
+    from efficientsam3_b200 import ops
+
+    def kd_fwd(preds, teacher, sizes, img_size, w):
+        szl = [(3, int(a), int(b)) for a, b in sizes.tolist()]
+        loss, mse, cos = oracle_kd_loss(preds.float(), teacher, img_size, szl, w)
+        return torch.stack([loss, mse, cos]).detach(), None
+
+    def kd_bwd(preds, teacher, sizes, per, img_size, w, grad_scale=1.0, scale_dev=None):
+        szl = [(3, int(a), int(b)) for a, b in sizes.tolist()]
+        p = preds.detach().float().requires_grad_(True)
+        with torch.enable_grad():
+            loss, _, _ = oracle_kd_loss(p, teacher, img_size, szl, w)
+            (g,) = torch.autograd.grad(loss, p)
+        return g * grad_scale * (scale_dev[0] if scale_dev is not None else 1.0)
+
+    monkeypatch.setattr(ops, "kd_loss_fwd", kd_fwd)
+    monkeypatch.setattr(ops, "kd_loss_bwd", kd_bwd)
+    calls = []
+
+    def fake_step(self, lr=None, max_norm=5.0, world_size=1):
+        calls.append((lr, max_norm, world_size, float(self.flat_grad.norm())))
+        self.flat_param -= 1e-6 * self.flat_grad
+
+    monkeypatch.setattr(OPT.FlatAdamW, "step", fake_step)
+    cfg = NS(TRAIN=NS(EVAL_BN_WHEN_TRAINING=True, ACCUMULATION_STEPS=accum, EPOCHS=3, WARMUP_EPOCHS=1, MIN_LR=1e-6, WARMUP_LR=1e-7,
+                      CLIP_GRAD=5.0),
+             DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=embed, COSINE=1.0), DATA=NS(IMG_SIZE=img))
+    m = _student("efficientvit_b0", img=img, embed=embed)
+    opt = OPT.FlatAdamW(m, lr=1e-3, weight_decay=0.01)
+    g = torch.Generator().manual_seed(3)
+    loader = [(([torch.randn(3, img, img, generator=g) for _ in range(B)], {"img_size_before_pad": [(3, img, img)] * B}),
+               ([np.random.RandomState(i).randn(1024 * embed * embed).astype(np.float16) for _ in range(B)], [i] * B)) for i in range(iters)]
+    losses = train_one_epoch(cfg, m, loader, opt, epoch=1)
+    assert len(losses) == iters and all(torch.isfinite(v) for v in losses)
+    assert len(calls) == iters // accum                                  # one update per ACCUMULATION_STEPS iterations
+    n_iter = iters // accum
+    expect = [OPT.cosine_lr((1 * iters + idx) // accum, 1e-3, 3 * n_iter, 1e-6, 1 * n_iter, 1e-7) for idx in (1, 3)]
+    assert [c[0] for c in calls] == expect and all(c[1] == 5.0 and c[2] == 1 for c in calls)
+    assert opt.flat_grad.abs().sum().item() == 0                         # cleared right after the last update
+    assert all(not mod.training for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d)) and m.training
+    assert all(c[3] > 0 for c in calls)
