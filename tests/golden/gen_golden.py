@@ -286,7 +286,28 @@ def gen_store(tag, n_rank=2, embed_dim=8, num_embedding=6):
     print(tag, sorted(os.listdir(path)))
 
 
+def gen_sampler_cases():
+    """Index plans of the reference's MyDistributedSampler (stage1/data/sampler.py) -> sampler_cases.json."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("ref_sampler", "/root/reference/stage1/data/sampler.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cases = []
+    for n, world, kw in [(10, 4, {}), (256, 8, {}), (7, 2, dict(drop_last=True)), (13, 4, dict(shuffle=False)), (5, 8, {}), (3, 8, {}),
+                         (12, 3, dict(pair=True)), (11, 2, dict(pair=True)), (9, 4, dict(padding=False)), (100, 8, dict(seed=5))]:
+        for epoch in (0, 3):
+            for rank in range(world):
+                s = mod.MyDistributedSampler(list(range(n)), num_replicas=world, rank=rank, **kw)
+                s.set_epoch(epoch)
+                cases.append(dict(n=n, world=world, rank=rank, epoch=epoch, kw=kw, indices=list(iter(s)), length=len(s)))
+    json.dump(cases, open(os.path.join(HERE, "sampler_cases.json"), "w"))
+    print("sampler_cases.json", len(cases), "cases")
+
+
 def main(which):
+    if which in ("sampler", "all"):
+        gen_sampler_cases()
     if which in ("train", "all"):
         gen_student_train("efficientvit_b1", "evm_train_160", img=160, embed=12, seed_w=71, seed_x=72)
     if which in ("tvm", "all"):

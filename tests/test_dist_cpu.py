@@ -217,3 +217,21 @@ def test_two_rank_torch_ddp_around_the_native_student():
     res = sorted(q.get(timeout=300) for _ in range(world))
     [p.join(timeout=60) for p in ps]
     assert all(r[1] < 1e-5 for r in res), res
+
+
+def test_rank_partition_matches_the_reference_sampler():
+    """stage1.sharding.shard_indices vs indices recorded from the unmodified MyDistributedSampler (stage1/data/sampler.py)
+    for 102 (dataset size, world, rank, epoch, option) combinations incl. padding, drop_last, pair and world > dataset."""
+    import json
+    from efficientsam3_b200.stage1.sharding import ShardedSampler, shard_indices
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sampler_cases.json")))
+    assert len(cases) >= 100
+    for c in cases:
+        got = shard_indices(c["n"], c["world"], c["rank"], c["epoch"], **c["kw"])
+        assert got == c["indices"], c
+        s = ShardedSampler(list(range(c["n"])), num_replicas=c["world"], rank=c["rank"], **c["kw"])
+        s.set_epoch(c["epoch"])
+        assert list(s) == c["indices"] and len(s) == len(c["indices"])
+    # every epoch all ranks together cover the dataset, and config 4's shape: 256 images -> 8 ranks x 32
+    parts = [shard_indices(256, 8, r, epoch=2, seed=1) for r in range(8)]
+    assert all(len(p) == 32 for p in parts) and sorted(sum(parts, [])) == list(range(256))
