@@ -116,7 +116,7 @@ class SEUnit:
         dm = (ops.gemm_simt(dpre1, w1.t().contiguous(), **f32) / HW).contiguous()                # [B, C]: d mean / HW
         dx = torch.empty_like(x)
         for b in range(B):                                   # dx = dy * gate + d mean / HW
-            dx[b] = ops.affine_act(dy[b], g[b], dm[b], None)
+            ops.affine_act(dy[b], g[b], dm[b], None, out=dx[b])
         return dx
 
 

@@ -756,13 +756,15 @@ def bn_stats(z, gamma, beta, eps, momentum, running_mean=None, running_var=None,
     return mean, invstd, scale, shift
 
 
-def affine_act(z, scale, shift, act, residual=None):
-    """act(scale[c] z + shift[c]) (+ residual) on [..., C] bf16 contiguous."""
+def affine_act(z, scale, shift, act, residual=None, out=None):
+    """act(scale[c] z + shift[c]) (+ residual) on [..., C] bf16 contiguous (out: optional contiguous destination of z's shape)."""
     _chk(z, torch.bfloat16, "z")
     _ensure_init(z)
     assert z.is_contiguous() and (residual is None or (residual.is_contiguous() and residual.shape == z.shape))
     C = z.shape[-1]
-    out = torch.empty_like(z)
+    if out is None:
+        out = torch.empty_like(z)
+    assert out.is_contiguous() and out.shape == z.shape and out.dtype == z.dtype
     _call("es3_affine_act", "affine_act", _nb(z, out, residual), 4 * z.numel(), z.data_ptr(), _ptr(scale), _ptr(shift), ACT[act],
           _ptr(residual), out.data_ptr(), z.numel() // C, C, _stream())
     return out

@@ -178,7 +178,7 @@ def bn_stats(z, gamma, beta, eps, momentum, running_mean=None, running_var=None,
     return mean, invstd, scale, shift
 
 
-def affine_act(z, scale, shift, act, residual=None):
+def affine_act(z, scale, shift, act, residual=None, out=None):
     u = z.to(CD)
     if scale is not None:
         u = u * scale
@@ -187,6 +187,9 @@ def affine_act(z, scale, shift, act, residual=None):
     v = _act(u, act)
     if residual is not None:
         v = v + residual.to(CD)
+    if out is not None:
+        out.copy_(v.to(out.dtype))
+        return out
     return v.to(BF)
 
 

@@ -284,3 +284,35 @@ def test_train_one_epoch_follows_the_reference_loop(monkeypatch):
     assert opt.flat_grad.abs().sum().item() == 0                         # cleared right after the last update
     assert all(not mod.training for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d)) and m.training
     assert all(c[3] > 0 for c in calls)
+
+
+def test_smoke_training_half_runs_under_emulation(monkeypatch, capsys):
+    """__graft_entry__.smoke()'s training half (wiring, thresholds) with the device ops emulated on CPU."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import __graft_entry__ as G
+    from efficientsam3_b200 import ops
+    emu_ops.install(monkeypatch)
+
+    def kd_fwd(preds, teacher, sizes, img_size, w):
+        szl = [(3, int(a), int(b)) for a, b in sizes.tolist()]
+        loss, mse, cos = oracle_kd_loss(preds.float(), teacher, img_size, szl, w)
+        return torch.stack([loss, mse, cos]).detach(), None
+
+    def kd_bwd(preds, teacher, sizes, per, img_size, w, grad_scale=1.0, scale_dev=None):
+        szl = [(3, int(a), int(b)) for a, b in sizes.tolist()]
+        p = preds.detach().float().requires_grad_(True)
+        with torch.enable_grad():
+            loss, _, _ = oracle_kd_loss(p, teacher, img_size, szl, w)
+            (g,) = torch.autograd.grad(loss, p)
+        return g * grad_scale * (scale_dev[0] if scale_dev is not None else 1.0)
+
+    monkeypatch.setattr(ops, "kd_loss_fwd", kd_fwd)
+    monkeypatch.setattr(ops, "kd_loss_bwd", kd_bwd)
+    img, embed = 192, 9
+    m = _student("efficientvit_b1", img=img, embed=embed, seed=3)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(2, 3, img, img, generator=torch.Generator().manual_seed(0))
+    G._smoke_train_step(torch.device("cpu"), m, sd, x, img, embed)
+    assert "training step" in capsys.readouterr().out and not m.training
