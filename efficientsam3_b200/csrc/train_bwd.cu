@@ -649,6 +649,95 @@ __global__ void __launch_bounds__(256) dw_wgrad_strip_kernel(const bf16* __restr
   }
 }
 
+// Shared-memory tiled version for stride 1, C % 32 == 0 (NOT the default path yet: written after the round's GPU budget was
+// spent, selected only through es3_dwconv_wgrad_tiled; see profiles/r1_next_steps.md).  A CTA owns a 32-channel slab and walks
+// 8 x 32 output-pixel tiles: the dz tile and the haloed x tile are staged once with cp.async (zero fill outside the map), a
+// half-warp = the 16 channel pairs of one pixel, so every shared-memory read is 64 contiguous bytes and the KS*KS taps of a pixel
+// re-use the staged tile instead of L1.  acc[KS*KS][2] per thread (<= 50 registers) -> full occupancy.
+constexpr int DWT_TH = 8, DWT_TW = 32, DWT_CS = 32;          // tile height / width (output pixels), channel slab
+template <int KS>
+struct DwtCfg {
+  static constexpr int IH = DWT_TH + KS - 1, IW = DWT_TW + KS - 1;
+  static constexpr int X_BYTES = IH * IW * DWT_CS * 2;      // haloed input tile, 64 B per pixel
+  static constexpr int DZ_BYTES = DWT_TH * DWT_TW * DWT_CS * 2;
+  static constexpr int RED_BYTES = 8 * KS * KS * DWT_CS * 4;
+  static constexpr int SMEM = (X_BYTES + DZ_BYTES > RED_BYTES) ? X_BYTES + DZ_BYTES : RED_BYTES;
+};
+
+template <int KS>
+__global__ void __launch_bounds__(256) dw_wgrad_tiled_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ x, long long ldx, int B,
+                                                             int H, int W, int C, int tiles_x, int tiles_y, float* __restrict__ part) {
+  using Cfg = DwtCfg<KS>;
+  constexpr int KK = KS * KS, PAD = KS / 2;
+  extern __shared__ __align__(16) uint8_t dwt_smem[];
+  const uint32_t u_x = static_cast<uint32_t>(__cvta_generic_to_shared(dwt_smem));
+  const uint32_t u_dz = u_x + Cfg::X_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cp = lane & 15, half = lane >> 4;               // channel pair inside the slab, which of the warp's two pixels
+  const int c0 = blockIdx.y * DWT_CS;
+  float acc[KK][2];
+#pragma unroll
+  for (int t = 0; t < KK; ++t) acc[t][0] = acc[t][1] = 0.f;
+  const long long ntiles = (long long)B * tiles_y * tiles_x;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y), b = (int)(tile / ((long long)tiles_x * tiles_y));
+    const int oy0 = ty * DWT_TH, ox0 = tx * DWT_TW;
+    __syncthreads();                                         // previous tile fully consumed
+    for (int i = tid; i < Cfg::IH * Cfg::IW * 4; i += 256) {
+      const int v = i & 3, pix = i >> 2;
+      const int iy = oy0 - PAD + pix / Cfg::IW, ix = ox0 - PAD + pix % Cfg::IW;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      cpa16(u_x + pix * 64 + v * 16, ok ? x + (((long long)b * H + iy) * W + ix) * ldx + c0 + v * 8 : x, ok);
+    }
+    for (int i = tid; i < DWT_TH * DWT_TW * 4; i += 256) {
+      const int v = i & 3, pix = i >> 2;
+      const int oy = oy0 + pix / DWT_TW, ox = ox0 + pix % DWT_TW;
+      const bool ok = oy < H && ox < W;
+      cpa16(u_dz + pix * 64 + v * 16, ok ? dz + (((long long)b * H + oy) * W + ox) * C + c0 + v * 8 : dz, ok);
+    }
+    cpa_wait_all();
+    __syncthreads();
+    // warp w, half h: pixels 16 w + 2 j + h of each 128-pixel half of the tile (adjacent pixels in the two half-warps)
+#pragma unroll 2
+    for (int j = 0; j < (DWT_TH * DWT_TW) / 16; ++j) {
+      const int pix = j * 16 + warp * 2 + half;
+      const int py = pix / DWT_TW, px = pix % DWT_TW;
+      const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dwt_smem + Cfg::X_BYTES + pix * 64 + cp * 4));
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          const float2 xv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dwt_smem + ((py + ky) * Cfg::IW + px + kx) * 64 + cp * 4));
+          acc[ky * KS + kx][0] = fmaf(g.x, xv.x, acc[ky * KS + kx][0]);
+          acc[ky * KS + kx][1] = fmaf(g.y, xv.y, acc[ky * KS + kx][1]);
+        }
+    }
+  }
+  // the two half-warps, then the 8 warps through shared memory: red[warp][tap][32 channels]
+#pragma unroll
+  for (int t = 0; t < KK; ++t) {
+    acc[t][0] += __shfl_xor_sync(0xffffffffu, acc[t][0], 16);
+    acc[t][1] += __shfl_xor_sync(0xffffffffu, acc[t][1], 16);
+  }
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(dwt_smem);
+  if (half == 0) {
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+      red[(warp * KK + t) * DWT_CS + cp * 2] = acc[t][0];
+      red[(warp * KK + t) * DWT_CS + cp * 2 + 1] = acc[t][1];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < KK * DWT_CS; i += 256) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w * KK * DWT_CS + i];
+    const int t = i / DWT_CS, c = i % DWT_CS;
+    part[((long long)blockIdx.x * KK + t) * C + c0 + c] = sum;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ stem conv weight gradient
 // img [B,3,H,W] fp32 NCHW; dz [B,Ho,Wo,COUT] bf16 (3x3, stride 2, pad 1).  part[blk][n][27] with 27 = ci*9 + ky*3 + kx.
 // block = ceil32(COUT * 27) threads: thread = one (n, tap) weight; 64-pixel chunks staged in shared memory.
@@ -1142,6 +1231,45 @@ extern "C" int es3_dwconv_wgrad(const void* dz, const void* x, long long ldx, in
   ES3_LAUNCH_CHECK("dw_wgrad_kernel");
   const long long n = (long long)ks * ks * C;
   // part index i = tap * C + c  ->  dW[c * ks*ks + tap]
+  sum_partials_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, st>>>(ws, nblk, n, C, 1, (long long)ks * ks, dW);
+  ES3_LAUNCH_CHECK("sum_partials_kernel");
+  return 0;
+}
+
+static int dwt_blocks(int B, int H, int W, int C) {
+  const long long ntiles = (long long)B * ceil_div(H, DWT_TH) * ceil_div(W, DWT_TW);
+  long long want = (4LL * 148 + C / DWT_CS - 1) / (C / DWT_CS);      // ~4 CTAs per SM over all channel slabs
+  if (want > ntiles) want = ntiles;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+extern "C" long long es3_dwconv_wgrad_tiled_ws_floats(int B, int H, int W, int C, int ks) {
+  return (long long)dwt_blocks(B, H, W, C) * ks * ks * C;
+}
+
+/* Same contract as es3_dwconv_wgrad for stride 1 and C % 32 == 0, shared-memory tiled (not yet the default: unmeasured). */
+extern "C" int es3_dwconv_wgrad_tiled(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, float* ws,
+                                      float* dW, void* stream) {
+  ES3_REQUIRE(C % DWT_CS == 0 && ldx % 8 == 0 && (ks == 3 || ks == 5), "es3_dwconv_wgrad_tiled: need C %% 32 == 0, ks 3|5 (C=%d ks=%d)", C, ks);
+  ES3_REQUIRE(((uintptr_t)dz & 15) == 0 && ((uintptr_t)x & 15) == 0, "es3_dwconv_wgrad_tiled: operands must be 16-byte aligned");
+  const int nblk = dwt_blocks(B, H, W, C);
+  const int tiles_x = ceil_div(W, DWT_TW), tiles_y = ceil_div(H, DWT_TH);
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) {
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(dw_wgrad_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwtCfg<3>::SMEM));
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(dw_wgrad_tiled_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwtCfg<5>::SMEM));
+    configured = true;
+  }
+  if (ks == 3)
+    dw_wgrad_tiled_kernel<3><<<dim3(nblk, C / DWT_CS), 256, DwtCfg<3>::SMEM, st>>>((const bf16*)dz, (const bf16*)x, ldx, B, H, W, C, tiles_x,
+                                                                                    tiles_y, ws);
+  else
+    dw_wgrad_tiled_kernel<5><<<dim3(nblk, C / DWT_CS), 256, DwtCfg<5>::SMEM, st>>>((const bf16*)dz, (const bf16*)x, ldx, B, H, W, C, tiles_x,
+                                                                                    tiles_y, ws);
+  ES3_LAUNCH_CHECK("dw_wgrad_tiled_kernel");
+  const long long n = (long long)ks * ks * C;
   sum_partials_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, st>>>(ws, nblk, n, C, 1, (long long)ks * ks, dW);
   ES3_LAUNCH_CHECK("sum_partials_kernel");
   return 0;

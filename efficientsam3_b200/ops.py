@@ -729,7 +729,7 @@ def win_attn_bias(qkv, qkv_pad, bias, B, H, W, C, heads, ws, scale):
 # ------------------------------------------------------------------------------------ student backward (train_bwd.cu)
 BN_MODE = {"none": 0, "eval": 1, "batch": 2}
 KERNELS_PER_CALL.update({"es3_bn_stats": 2, "es3_bn_act_bwd_reduce": 2, "es3_wgrad_pw": 2, "es3_dwconv_wgrad": 2,
-                         "es3_stem_wgrad": 2, "es3_litemla_attn_bwd": 2})
+                         "es3_stem_wgrad": 2, "es3_litemla_attn_bwd": 2, "es3_dwconv_wgrad_tiled": 2})
 
 
 def _f32ws(n, dev):
@@ -874,13 +874,23 @@ def dwconv_bwd_data(dz, w, H, W, ks, stride):
     return dx
 
 
-def dwconv_wgrad(dz, x, dW, ks, stride):
-    """dW [C,1,ks,ks] fp32 += depthwise weight gradient; dz [B,Ho,Wo,C] bf16 contiguous, x [B,H,W,C] bf16 (channel slice ok)."""
+DW_WGRAD_TILED = False   # route stride-1, C % 32 == 0 weight gradients to es3_dwconv_wgrad_tiled (no GPU parity run yet: off)
+
+
+def dwconv_wgrad(dz, x, dW, ks, stride, impl=None):
+    """dW [C,1,ks,ks] fp32 += depthwise weight gradient; dz [B,Ho,Wo,C] bf16 contiguous, x [B,H,W,C] bf16 (channel slice ok).
+    impl="tiled" forces the shared-memory tiled kernel (stride 1, C % 32 == 0)."""
     _chk(dz, torch.bfloat16, "dz"); _chk(x, torch.bfloat16, "x"); _chk(dW, torch.float32, "dW")
     _ensure_init(dz)
     B, H, W, C = x.shape
     assert dz.is_contiguous() and dW.is_contiguous() and dW.numel() == C * ks * ks and dz.shape[3] == C
     assert x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1)
+    if impl == "tiled" or (impl is None and DW_WGRAD_TILED and stride == 1 and C % 32 == 0):
+        assert stride == 1 and C % 32 == 0
+        ws = _f32ws(_lib.size("es3_dwconv_wgrad_tiled_ws_floats", B, H, W, C, ks), dz.device)
+        _call("es3_dwconv_wgrad_tiled", f"dwconv_wgrad_tiled{ks}x{ks}", _nb(dz) + B * H * W * C * 2, 2 * dz.numel() * ks * ks,
+              dz.data_ptr(), x.data_ptr(), x.stride(2), B, H, W, C, ks, ws.data_ptr(), dW.data_ptr(), _stream())
+        return dW
     ws = _f32ws(_lib.size("es3_dwconv_wgrad_ws_floats", B, H, W, C, ks, stride), dz.device)
     _call("es3_dwconv_wgrad", f"dwconv_wgrad{ks}x{ks}s{stride}", _nb(dz) + B * H * W * C * 2, 2 * dz.numel() * ks * ks,
           dz.data_ptr(), x.data_ptr(), x.stride(2), B, H, W, C, ks, stride, ws.data_ptr(), dW.data_ptr(), _stream())

@@ -321,6 +321,11 @@ int es3_dwconv_bwd_data(const void* dz, const float* w, void* dx, int B, int H, 
 long long es3_dwconv_wgrad_ws_floats(int B, int H, int W, int C, int ks, int stride);
 int es3_dwconv_wgrad(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, int stride, float* ws,
                      float* dW, void* stream);
+/* Shared-memory tiled variant of es3_dwconv_wgrad for stride 1 and C % 32 == 0 (same result contract).  Written after the round-1
+ * GPU budget was spent: NOT on the default path until it has a GPU parity run (profiles/r1_next_steps.md). */
+long long es3_dwconv_wgrad_tiled_ws_floats(int B, int H, int W, int C, int ks);
+int es3_dwconv_wgrad_tiled(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, float* ws, float* dW,
+                           void* stream);
 /* Weight gradient of the 3 -> Cout stride-2 stem conv on the fp32 NCHW image (efficientvit/backbone.py:47-56):
  * dW [Cout][3][3][3] += . */
 long long es3_stem_wgrad_ws_floats(int B, int H, int W, int Cout);

@@ -284,7 +284,7 @@ def dwconv_bwd_data(dz, w, H, W, ks, stride):
     return _nhwc(gx).to(BF)
 
 
-def dwconv_wgrad(dz, x, dW, ks, stride):
+def dwconv_wgrad(dz, x, dW, ks, stride, impl=None):
     C = x.shape[3]
     w = torch.zeros(ks * ks, C, dtype=CD, requires_grad=True)
     with torch.enable_grad():

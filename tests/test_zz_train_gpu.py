@@ -197,6 +197,21 @@ def test_dwconv_gradients(cuda, B, H, W, C, ks, stride):
     _close(got, ref, 2e-3, "dwconv_wgrad")
 
 
+@pytest.mark.xfail(strict=False, reason="es3_dwconv_wgrad_tiled was written after the round-1 GPU budget was spent: not on the default path, "
+                                        "first GPU run pending")
+@pytest.mark.parametrize("B,H,W,C,ks", [(2, 16, 16, 32, 3), (1, 9, 11, 96, 5), (2, 64, 64, 384, 5), (2, 40, 37, 512, 3), (1, 7, 5, 64, 5)])
+def test_dwconv_wgrad_tiled(cuda, B, H, W, C, ks):
+    from efficientsam3_b200 import ops
+    g = _g(B * H + C + ks + 1)
+    ms = _bf(torch.randn(B, H, W, 2 * C, generator=g))
+    dz = _bf(torch.randn(B, H, W, C, generator=g))
+    ref = torch.full((C, 1, ks, ks), 0.125)
+    E.dwconv_wgrad(dz, ms[..., :C], ref, ks, 1)
+    got = torch.full((C, 1, ks, ks), 0.125, device=cuda)
+    ops.dwconv_wgrad(dz.to(cuda), ms.to(cuda)[..., :C], got, ks, 1, impl="tiled")
+    _close(got, ref, 2e-3, "dwconv_wgrad tiled")
+
+
 def test_dwconv_wgrad_channel_slice(cuda):
     """x is the qkv half of the LiteMLA multi-scale buffer (pixel stride 2*c3)."""
     from efficientsam3_b200 import ops
