@@ -81,6 +81,8 @@ SIGNATURES: dict[str, list] = {
     "es3_dwconv_bwd_data": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_dwconv_wgrad": [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "es3_dwconv_wgrad_tiled": [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "es3_se_bwd_dgate": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "es3_se_bwd_apply": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "es3_stem_wgrad": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "es3_bilinear_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_litemla_attn_bwd": [_vp, _ll, _vp, _ll, _vp, _i, _vp, _vp, _ll, _i, _i, _i, _f, _vp],
@@ -92,6 +94,7 @@ SIZE_HELPERS: dict[str, list] = {
     "es3_wgrad_pw_ws_floats": [_ll, _i, _i],
     "es3_dwconv_wgrad_ws_floats": [_i, _i, _i, _i, _i, _i],
     "es3_dwconv_wgrad_tiled_ws_floats": [_i, _i, _i, _i, _i],
+    "es3_se_bwd_ws_floats": [_i, _i, _i],
     "es3_stem_wgrad_ws_floats": [_i, _i, _i, _i],
     "es3_litemla_bwd_ws_floats": [_i, _i, _i],
 }

@@ -738,6 +738,71 @@ __global__ void __launch_bounds__(256) dw_wgrad_tiled_kernel(const bf16* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------ SqueezeExcite backward (batched)
+// Per-image column reductions / per-image affine of the SqueezeExcite backward in ONE launch each (the training graph's first
+// version loops over the batch with es3_bn_act_bwd_reduce / es3_affine_act: ~100 launches per SE block at batch 32).
+// NOT on the default path yet (no GPU parity run; ops.SE_BWD_BATCHED).
+//   se_dgate:  part[chunk][b][c] = sum over the chunk's pixels of dy[b][p][c] * x[b][p][c]          grid (nchunk, B), block 256
+//   se_apply:  dx[b][p][c] = dy[b][p][c] * gate[b][c] + add[b][c]                                    one thread per 8-channel vector
+__global__ void __launch_bounds__(256) se_dgate_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, int HW, int C, int CVB,
+                                                       int px_per_chunk, float* __restrict__ part) {
+  __shared__ float red[256][9];
+  const int tid = threadIdx.x, lanes = 256 / CVB;
+  const int cvl = tid % CVB, pl = tid / CVB;
+  const int b = blockIdx.y, B = gridDim.y;
+  const int p0 = blockIdx.x * px_per_chunk, p1 = min(HW, p0 + px_per_chunk);
+  for (int cv0 = 0; cv0 * 8 < C; cv0 += CVB) {              // C > 2048: several passes over the chunk
+    const int cv = cv0 + cvl;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    if (pl < lanes && cv * 8 < C) {
+      for (int p = p0 + pl; p < p1; p += lanes) {
+        const long long off = ((long long)b * HW + p) * C + cv * 8;
+        float a[8], v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + off)), a);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + off)), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = fmaf(a[i], v[i], s[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[tid][i] = s[i];
+    __syncthreads();
+    int top = 1;
+    while (top < lanes) top <<= 1;
+    for (int st = top >> 1; st > 0; st >>= 1) {
+      if (pl < st && pl + st < lanes) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[tid][i] += red[tid + st * CVB][i];
+      }
+      __syncthreads();
+    }
+    if (pl == 0 && cv * 8 < C) {
+      float* d = part + ((long long)blockIdx.x * B + b) * C + cv * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = red[tid][i];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void se_apply_kernel(const bf16* __restrict__ dy, const float* __restrict__ gate, const float* __restrict__ add,
+                                bf16* __restrict__ dx, int HW, int CV, long long total_vec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int cv = (int)(i % CV);
+  const int b = (int)(i / ((long long)CV * HW));
+  const int C = CV * 8;
+  float f[8], g[8], a[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), f);
+  load8f(gate + (long long)b * C + cv * 8, g, 1.f);
+  load8f(add + (long long)b * C + cv * 8, a, 0.f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], g[k], a[k]);
+  reinterpret_cast<uint4*>(dx)[i] = pack8(f);
+}
+
 // ------------------------------------------------------------------------------------------ stem conv weight gradient
 // img [B,3,H,W] fp32 NCHW; dz [B,Ho,Wo,COUT] bf16 (3x3, stride 2, pad 1).  part[blk][n][27] with 27 = ci*9 + ky*3 + kx.
 // block = ceil32(COUT * 27) threads: thread = one (n, tap) weight; 64-pixel chunks staged in shared memory.
@@ -1272,6 +1337,45 @@ extern "C" int es3_dwconv_wgrad_tiled(const void* dz, const void* x, long long l
   const long long n = (long long)ks * ks * C;
   sum_partials_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, st>>>(ws, nblk, n, C, 1, (long long)ks * ks, dW);
   ES3_LAUNCH_CHECK("sum_partials_kernel");
+  return 0;
+}
+
+static int se_chunks(int HW, int C, int* CVB, int* ppc) {
+  const int CV = C / 8;
+  *CVB = CV < 256 ? CV : 256;
+  const int lanes = 256 / *CVB;
+  int nchunk = ceil_div(HW, lanes * 32);                     // >= 32 pixels per lane and chunk
+  if (nchunk > 64) nchunk = 64;
+  if (nchunk < 1) nchunk = 1;
+  *ppc = ceil_div(HW, nchunk);
+  return ceil_div(HW, *ppc);
+}
+
+extern "C" long long es3_se_bwd_ws_floats(int B, int HW, int C) {
+  int CVB, ppc;
+  return (long long)se_chunks(HW, C, &CVB, &ppc) * B * C;
+}
+
+/* dgate[b][c] += sum_p dy[b][p][c] x[b][p][c]  (dy, x: [B][HW][C] bf16 contiguous) */
+extern "C" int es3_se_bwd_dgate(const void* dy, const void* x, int B, int HW, int C, float* ws, float* dgate, void* stream) {
+  ES3_REQUIRE(B > 0 && HW > 0 && C % 8 == 0, "es3_se_bwd_dgate: bad shape (C=%d)", C);
+  int CVB, ppc;
+  const int nchunk = se_chunks(HW, C, &CVB, &ppc);
+  cudaStream_t st = (cudaStream_t)stream;
+  se_dgate_kernel<<<dim3(nchunk, B), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, HW, C, CVB, ppc, ws);
+  ES3_LAUNCH_CHECK("se_dgate_kernel");
+  const long long n = (long long)B * C;
+  sum_partials_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, st>>>(ws, nchunk, n, (int)n, 0, 1, dgate);
+  ES3_LAUNCH_CHECK("sum_partials_kernel");
+  return 0;
+}
+
+/* dx[b][p][c] = dy[b][p][c] * gate[b][c] + add[b][c] */
+extern "C" int es3_se_bwd_apply(const void* dy, const float* gate, const float* add, void* dx, int B, int HW, int C, void* stream) {
+  ES3_REQUIRE(B > 0 && HW > 0 && C % 8 == 0, "es3_se_bwd_apply: bad shape (C=%d)", C);
+  const long long total = (long long)B * HW * (C / 8);
+  se_apply_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, gate, add, (bf16*)dx, HW, C / 8, total);
+  ES3_LAUNCH_CHECK("se_apply_kernel");
   return 0;
 }
 

@@ -729,7 +729,7 @@ def win_attn_bias(qkv, qkv_pad, bias, B, H, W, C, heads, ws, scale):
 # ------------------------------------------------------------------------------------ student backward (train_bwd.cu)
 BN_MODE = {"none": 0, "eval": 1, "batch": 2}
 KERNELS_PER_CALL.update({"es3_bn_stats": 2, "es3_bn_act_bwd_reduce": 2, "es3_wgrad_pw": 2, "es3_dwconv_wgrad": 2,
-                         "es3_stem_wgrad": 2, "es3_litemla_attn_bwd": 2, "es3_dwconv_wgrad_tiled": 2})
+                         "es3_stem_wgrad": 2, "es3_litemla_attn_bwd": 2, "es3_dwconv_wgrad_tiled": 2, "es3_se_bwd_dgate": 2})
 
 
 def _f32ws(n, dev):
@@ -895,6 +895,34 @@ def dwconv_wgrad(dz, x, dW, ks, stride, impl=None):
     _call("es3_dwconv_wgrad", f"dwconv_wgrad{ks}x{ks}s{stride}", _nb(dz) + B * H * W * C * 2, 2 * dz.numel() * ks * ks,
           dz.data_ptr(), x.data_ptr(), x.stride(2), B, H, W, C, ks, stride, ws.data_ptr(), dW.data_ptr(), _stream())
     return dW
+
+
+SE_BWD_BATCHED = False   # SqueezeExcite backward through es3_se_bwd_* instead of per-image loops (no GPU parity run yet: off)
+
+
+def se_bwd_dgate(dy, x):
+    """dgate [B,C] fp32 = sum over pixels of dy * x; dy, x [B,H,W,C] bf16 contiguous."""
+    _chk(dy, torch.bfloat16, "dy"); _chk(x, torch.bfloat16, "x")
+    _ensure_init(x)
+    assert dy.is_contiguous() and x.is_contiguous() and dy.shape == x.shape
+    B, H, W, C = x.shape
+    dgate = torch.zeros((B, C), device=x.device, dtype=torch.float32)
+    ws = _f32ws(_lib.size("es3_se_bwd_ws_floats", B, H * W, C), x.device)
+    _call("es3_se_bwd_dgate", "se_bwd_dgate", _nb(dy, x), 2 * x.numel(), dy.data_ptr(), x.data_ptr(), B, H * W, C, ws.data_ptr(),
+          dgate.data_ptr(), _stream())
+    return dgate
+
+
+def se_bwd_apply(dy, gate, add):
+    """dy * gate[b,c] + add[b,c]; dy [B,H,W,C] bf16, gate / add [B,C] fp32 -> bf16."""
+    _chk(dy, torch.bfloat16, "dy"); _chk(gate, torch.float32, "gate"); _chk(add, torch.float32, "add")
+    _ensure_init(dy)
+    assert dy.is_contiguous() and gate.is_contiguous() and add.is_contiguous()
+    B, H, W, C = dy.shape
+    dx = torch.empty_like(dy)
+    _call("es3_se_bwd_apply", "se_bwd_apply", 2 * _nb(dy), 2 * dy.numel(), dy.data_ptr(), gate.data_ptr(), add.data_ptr(), dx.data_ptr(),
+          B, H * W, C, _stream())
+    return dx
 
 
 def stem_wgrad(img, dz, dW):

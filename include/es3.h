@@ -326,6 +326,12 @@ int es3_dwconv_wgrad(const void* dz, const void* x, long long ldx, int B, int H,
 long long es3_dwconv_wgrad_tiled_ws_floats(int B, int H, int W, int C, int ks);
 int es3_dwconv_wgrad_tiled(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, float* ws, float* dW,
                            void* stream);
+/* SqueezeExcite backward (timm SqueezeExcite, repvit.py:23,136) in one launch each instead of per-image loops:
+ * dgate[b][c] += sum_p dy x; dx = dy * gate[b][c] + add[b][c].  dy, x, dx: [B][HW][C] bf16.  Not on the default path yet
+ * (no GPU parity run; ops.SE_BWD_BATCHED). */
+long long es3_se_bwd_ws_floats(int B, int HW, int C);
+int es3_se_bwd_dgate(const void* dy, const void* x, int B, int HW, int C, float* ws, float* dgate, void* stream);
+int es3_se_bwd_apply(const void* dy, const float* gate, const float* add, void* dx, int B, int HW, int C, void* stream);
 /* Weight gradient of the 3 -> Cout stride-2 stem conv on the fp32 NCHW image (efficientvit/backbone.py:47-56):
  * dW [Cout][3][3][3] += . */
 long long es3_stem_wgrad_ws_floats(int B, int H, int W, int Cout);

@@ -275,6 +275,14 @@ def accumulate_strided(src, dst, inner, ld_outer, ld_inner):
     return dst
 
 
+def se_bwd_dgate(dy, x):
+    return (dy.to(CD) * x.to(CD)).sum((1, 2)).float()
+
+
+def se_bwd_apply(dy, gate, add):
+    return (dy.to(CD) * gate.to(CD)[:, None, None, :] + add.to(CD)[:, None, None, :]).to(BF)
+
+
 def dwconv_bwd_data(dz, w, H, W, ks, stride):
     B, Ho, Wo, C = dz.shape
     x = torch.zeros(B, C, H, W, dtype=CD, requires_grad=True)
@@ -324,7 +332,7 @@ def litemla_attn_bwd(ms, datt, kv, heads2, eps=1e-15):
 
 PATCHED = ["gemm", "gemm_simt", "channel_mean", "scale_channels", "conv3x3_s2_narrow", "conv3x3", "stem_conv3x3_s2", "dwconv", "litemla_dwpw_weights", "litemla_aggreg_dwpw", "litemla_attn",
            "bilinear_nhwc_to_nchw", "nhwc_to_nchw_f32", "nchw_f32_to_nhwc", "bn_stats", "affine_act", "bn_act_bwd", "add_bf16",
-           "wgrad_pw", "transpose_pad", "accumulate_strided", "dwconv_bwd_data", "dwconv_wgrad", "stem_wgrad", "bilinear_bwd", "litemla_attn_bwd"]
+           "wgrad_pw", "se_bwd_dgate", "se_bwd_apply", "transpose_pad", "accumulate_strided", "dwconv_bwd_data", "dwconv_wgrad", "stem_wgrad", "bilinear_bwd", "litemla_attn_bwd"]
 
 
 def install(monkeypatch):

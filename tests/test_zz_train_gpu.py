@@ -212,6 +212,17 @@ def test_dwconv_wgrad_tiled(cuda, B, H, W, C, ks):
     _close(got, ref, 2e-3, "dwconv_wgrad tiled")
 
 
+@pytest.mark.xfail(strict=False, reason="es3_se_bwd_* were written after the round-1 GPU budget was spent: not on the default path, first GPU run pending")
+@pytest.mark.parametrize("B,H,W,C", [(3, 16, 16, 64), (2, 9, 7, 128), (4, 32, 32, 256), (2, 5, 5, 2560)])
+def test_se_bwd_batched(cuda, B, H, W, C):
+    from efficientsam3_b200 import ops
+    g = _g(B + H + C)
+    dy, x = _bf(torch.randn(B, H, W, C, generator=g)), _bf(torch.randn(B, H, W, C, generator=g))
+    gate, add = torch.rand(B, C, generator=g), torch.randn(B, C, generator=g) * 0.1
+    _close(ops.se_bwd_dgate(dy.to(cuda), x.to(cuda)), E.se_bwd_dgate(dy, x), 2e-3, "se_bwd_dgate")
+    _close(ops.se_bwd_apply(dy.to(cuda), gate.to(cuda), add.to(cuda)), E.se_bwd_apply(dy, gate, add), 1e-2, "se_bwd_apply")
+
+
 def test_dwconv_wgrad_channel_slice(cuda):
     """x is the qkv half of the LiteMLA multi-scale buffer (pixel stride 2*c3)."""
     from efficientsam3_b200 import ops
