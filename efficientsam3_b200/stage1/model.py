@@ -98,6 +98,9 @@ class StudentTrainFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        if ctx.graph is None:
+            raise RuntimeError("the native student keeps its saved activations for ONE backward pass (retain_graph / double backward "
+                               "are not supported): run the forward again")
         body, head = ctx.graph
         ctx.graph = None
         grads = {}
