@@ -317,3 +317,33 @@ def test_smoke_training_half_runs_under_emulation(monkeypatch, capsys):
     x = torch.randn(2, 3, img, img, generator=torch.Generator().manual_seed(0))
     G._smoke_train_step(torch.device("cpu"), m, sd, x, img, embed)
     assert "training step" in capsys.readouterr().out and not m.training
+
+
+@pytest.mark.parametrize("name,variant,img,embed", [("efficientvit_b0", "b0", 160, 12), ("efficientvit_b1", "b1", 224, 9)])
+def test_other_sizes_exact(monkeypatch, name, variant, img, embed):
+    """The fp64 logic check on the second EfficientViT name with a training graph (b0: 8-channel stem, 2-block stages) and on an
+    odd-sized map chain (224 -> 112 / 56 / 28 / 14 / 7: stride-2 layers over odd extents, head resize 7 -> 9)."""
+    from efficientsam3_b200 import ops
+    emu_ops.install(monkeypatch)
+    monkeypatch.setattr(emu_ops, "BF", torch.float64)
+    monkeypatch.setattr(emu_ops, "CD", torch.float64)
+    monkeypatch.setattr(ops, "ACT_DTYPE", torch.float64)
+    B = 2
+    m = _student(name, img=img, embed=embed, seed=9)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(B, 3, img, img, generator=torch.Generator().manual_seed(4))
+    teacher = torch.randn(B, 1024, embed, embed, generator=torch.Generator().manual_seed(5)).double()
+    sizes = [(3, img, img * 3 // 4), (3, img * 2 // 3, img)]
+    m.train()
+    out = m(x)
+    loss, _, _ = oracle_kd_loss(out, teacher, img, sizes, 1.0)
+    loss.backward()
+    sd_ref = {k: (v.double() if v.is_floating_point() else v) for k, v in _round_like_product(sd0).items()}
+    ref_out, _, sd = _oracle_step(sd_ref, x.double(), teacher, img, sizes, variant, embed, True)
+    assert _rel(out.detach(), ref_out) < 1e-5
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        g = sd[k].grad.double()
+        num += (p.grad.double() - g).pow(2).sum().item()
+        den += g.pow(2).sum().item()
+    assert (num / den) ** 0.5 < 1e-5, (num / den) ** 0.5
