@@ -326,11 +326,28 @@ def other_encoders(dev, S, E):
         out["config2_online_kd_step"] = online_kd_step_leg(dev, batch=32, steps=2, warm=1)
     except Exception as e:
         out["config2_online_kd_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    # EfficientSAM3 as deployed for the SAM-1 task: EV-M student encoder + SAM2-branch FPN + mask decoder, 1 point / image
+    try:
+        torch.cuda.empty_cache()
+        out["efficientsam3_evm_point_prompt"] = efficientsam3_point_leg(dev, batch=8)
+    except Exception as e:
+        out["efficientsam3_evm_point_prompt"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     try:
         torch.cuda.empty_cache()
     except Exception:
         pass
     return out
+
+
+def efficientsam3_point_leg(dev, batch):
+    from efficientsam3_b200.model_builder import build_efficientsam3_point_segmenter
+    seg = build_efficientsam3_point_segmenter("efficientvit", "b1").to(dev)
+    x = torch.randn(batch, 3, 1008, 1008, device=dev)
+    coords = torch.rand(batch, 1, 2, device=dev) * 1008
+    labels = torch.ones(batch, 1, dtype=torch.int32, device=dev)
+    ms = _time_steps(lambda: seg.set_image_batch(x).predict_batch(coords, labels, multimask_output=True), 2, 5)
+    return {"images_per_s": round(batch / ms * 1e3, 1), "ms_per_step": round(ms, 2), "batch": batch, "img": 1008,
+            "what": "EV-M student encoder -> 1024x72x72 -> SAM2-branch FPN -> prompt encoder + TwoWay mask decoder -> 1008^2 masks"}
 
 
 def online_kd_step_leg(dev, batch, steps, warm):

@@ -30,14 +30,19 @@ class _Holder(nn.Module):
 
 
 class Sam3PointPromptSegmenter(nn.Module):
-    def __init__(self, image_size=1008, backbone_stride=14, hidden_dim=256, vit_overrides=None):
+    def __init__(self, image_size=1008, backbone_stride=14, hidden_dim=256, vit_overrides=None, vision_backbone=None):
+        """vision_backbone: an already built Sam3DualViTDetNeck (with the SAM2 branch), e.g. the EfficientSAM3 student encoder of
+        efficientsam3_b200.model_builder.create_student_vision_backbone; default: the SAM3 ViT trunk + neck."""
         super().__init__()
         self.image_size, self.hidden_dim = image_size, hidden_dim
         e = image_size // backbone_stride
-        trunk = create_sam3_vit_backbone(**(vit_overrides or {}))
         self.backbone = _Holder()
-        self.backbone.vision_backbone = Sam3DualViTDetNeck(trunk=trunk, position_encoding=None, d_model=hidden_dim,
-                                                           scale_factors=[4.0, 2.0, 1.0, 0.5], add_sam2_neck=True)
+        if vision_backbone is None:
+            trunk = create_sam3_vit_backbone(**(vit_overrides or {}))
+            vision_backbone = Sam3DualViTDetNeck(trunk=trunk, position_encoding=None, d_model=hidden_dim,
+                                                 scale_factors=[4.0, 2.0, 1.0, 0.5], add_sam2_neck=True)
+        assert vision_backbone.sam2_convs is not None, "the SAM heads read the SAM2 branch of the neck (enable_inst_interactivity)"
+        self.backbone.vision_backbone = vision_backbone
         self.no_mem_embed = nn.Parameter(torch.zeros(1, 1, hidden_dim))
         nn.init.trunc_normal_(self.no_mem_embed, std=0.02)
         self.sam_prompt_encoder = PromptEncoder(embed_dim=hidden_dim, image_embedding_size=(e, e),
@@ -54,8 +59,12 @@ class Sam3PointPromptSegmenter(nn.Module):
     def set_image_batch(self, images: torch.Tensor):
         """images [B,3,S,S] fp32 CUDA, already resized / normalised (mean 0.5, std 0.5 as Sam3Processor does)."""
         neck = self.backbone.vision_backbone
-        tok, (B, h, w) = neck.trunk.forward_tokens(images)
-        feats = ops.add_rows(tok, None, out_bf16=True, out_f32=False)[0].view(B, h, w, -1)
+        if hasattr(neck.trunk, "forward_tokens"):       # SAM3 ViT trunk: fp32 token stream -> bf16 NHWC
+            tok, (B, h, w) = neck.trunk.forward_tokens(images)
+            feats = ops.add_rows(tok, None, out_bf16=True, out_f32=False)[0].view(B, h, w, -1)
+        else:                                           # EfficientSAM3 student encoder (model_builder.ListWrapper)
+            feats = neck.trunk.forward_nhwc(images)
+            B, h, w, _ = feats.shape
         l288, l144, l72 = neck.forward_nhwc(feats, "sam2", (0, 1, 2), f32_levels=(2,))
         md = self.sam_mask_decoder
         feat_s0, feat_s1 = md.project_high_res(l288, l144)

@@ -286,6 +286,34 @@ def gen_store(tag, n_rank=2, embed_dim=8, num_embedding=6):
     print(tag, sorted(os.listdir(path)))
 
 
+def gen_student_neck(tag="student_neck_evm_160", img=160, seed_w=81, seed_x=82):
+    """EfficientSAM3 image encoder as the reference builds it (`_create_student_vision_backbone`, model_builder.py:789-941):
+    state_dict signatures of all nine student variants (sha256 of the key|shape|dtype list) and, for efficientvit b1 with
+    re-randomised weights, the FPN outputs of both branches on one small image (strided sub-samples + statistics)."""
+    import hashlib
+    from sam3 import model_builder as MB
+    sigs = {}
+    for bt, names in [("efficientvit", ["b0", "b1", "b2"]), ("repvit", ["m0.9", "m1.1", "m2.3"]), ("tinyvit", ["5m", "11m", "21m"])]:
+        for mn in names:
+            m = MB._create_student_vision_backbone(bt, mn, enable_inst_interactivity=True)
+            ks = keyshapes(m.state_dict())
+            sigs[f"{bt}:{mn}"] = f"{len(ks)}:{hashlib.sha256(chr(10).join(ks).encode()).hexdigest()}"
+    m = MB._create_student_vision_backbone("efficientvit", "b1", enable_inst_interactivity=True).eval()
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed_w))
+    x = torch.randn(1, 3, img, img, generator=torch.Generator().manual_seed(seed_x))
+    s3, _, s2, _ = m(x)
+    rec = {}
+    for name, outs in (("sam3", s3), ("sam2", s2)):
+        for i, t in enumerate(outs):
+            rec[f"{name}_{i}_shape"] = np.array(t.shape)
+            rec[f"{name}_{i}_stats"] = stats(t)
+            rec[f"{name}_{i}_sub"] = t[:, ::16, ::(6 if t.shape[-1] > 36 else 3), ::(6 if t.shape[-1] > 36 else 3)].numpy()
+    path = os.path.join(HERE, f"{tag}.npz")
+    np.savez_compressed(path, keys=keyshapes(m.state_dict()), sig_names=np.array(list(sigs.keys())), sig_values=np.array(list(sigs.values())),
+                        img=img, seed_w=seed_w, seed_x=seed_x, **rec)
+    print(tag, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 def gen_sampler_cases():
     """Index plans of the reference's MyDistributedSampler (stage1/data/sampler.py) -> sampler_cases.json."""
     import importlib.util
@@ -308,6 +336,8 @@ def gen_sampler_cases():
 def main(which):
     if which in ("sampler", "all"):
         gen_sampler_cases()
+    if which in ("student_neck", "all"):
+        gen_student_neck()
     if which in ("train", "all"):
         gen_student_train("efficientvit_b1", "evm_train_160", img=160, embed=12, seed_w=71, seed_x=72)
     if which in ("tvm", "all"):

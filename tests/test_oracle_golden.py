@@ -182,3 +182,40 @@ def test_efficientvit_train_mode_oracle_matches_reference_training_step():
         np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-9 * scale, err_msg=str(name))
     for i, name in enumerate(g["buf_names"]):
         np.testing.assert_allclose(sd[str(name)].numpy(), g[f"buf{i}"], rtol=1e-10, atol=1e-12, err_msg=str(name))
+
+
+def test_student_vision_backbone_oracle_matches_reference():
+    """EfficientSAM3 image encoder (student trunk + 1024-channel head + dual FPN) as `_create_student_vision_backbone` builds it:
+    oracle composition (efficientvit + student head + neck) vs the reference's outputs on both FPN branches."""
+    from oracle import efficientvit as EV
+    from oracle import necks as NK
+    g = _load("student_neck_evm_160")
+    sd = _sd_from_keys(g["keys"], int(g["seed_w"]))
+    img = int(g["img"])
+    x = torch.randn(1, 3, img, img, generator=torch.Generator().manual_seed(int(g["seed_x"])))
+    student = {k[len("trunk.model."):]: v for k, v in sd.items() if k.startswith("trunk.model.")}
+    with torch.no_grad():
+        feats = EV.image_student_encoder(student, x, 72, "b1")
+        assert tuple(feats.shape) == (1, 1024, 72, 72)
+        for name, prefix in (("sam3", "convs."), ("sam2", "sam2_convs.")):
+            for i, t in enumerate(NK.neck(sd, feats, prefix=prefix)):
+                assert tuple(t.shape) == tuple(g[f"{name}_{i}_shape"])
+                st = 6 if t.shape[-1] > 36 else 3
+                _assert_close(t[:, ::16, ::st, ::st].numpy(), g[f"{name}_{i}_sub"], rtol=5e-5)
+
+
+def test_student_vision_backbone_keys_match_reference_for_all_nine_students():
+    """Key-for-key (name, shape, dtype, order) equality of efficientsam3_b200.model_builder.create_student_vision_backbone with the
+    reference builder, through the sha256 of the signature list recorded from the reference."""
+    import hashlib
+    from efficientsam3_b200.model_builder import create_student_vision_backbone
+    g = _load("student_neck_evm_160")
+    want = dict(zip([str(k) for k in g["sig_names"]], [str(v) for v in g["sig_values"]]))
+    assert len(want) == 9
+    for key, ref in want.items():
+        bt, mn = key.split(":")
+        sd = create_student_vision_backbone(bt, mn, enable_inst_interactivity=True).state_dict()
+        ks = [f"{k}|{','.join(map(str, v.shape))}|{str(v.dtype).replace('torch.', '')}" for k, v in sd.items()]
+        assert f"{len(ks)}:{hashlib.sha256(chr(10).join(ks).encode()).hexdigest()}" == ref, key
+    with pytest.raises(ValueError):
+        create_student_vision_backbone("resnet", "50")

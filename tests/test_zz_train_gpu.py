@@ -423,3 +423,38 @@ def test_se_bwd_batched(cuda, B, H, W, C):
     gate, add = torch.rand(B, C, generator=g), torch.randn(B, C, generator=g) * 0.1
     _close(ops.se_bwd_dgate(dy.to(cuda), x.to(cuda)), E.se_bwd_dgate(dy, x), 2e-3, "se_bwd_dgate")
     _close(ops.se_bwd_apply(dy.to(cuda), gate.to(cuda), add.to(cuda)), E.se_bwd_apply(dy, gate, add), 1e-2, "se_bwd_apply")
+
+
+@pytest.mark.xfail(strict=False, reason="EfficientSAM3 student encoder + FPN + SAM heads: Python composition of modules that each have a GPU "
+                                        "parity test (student forward, FPN, heads); key-for-key equal to the reference builder and oracle-"
+                                        "checked on CPU; written after the round-1 GPU budget was spent, first GPU run pending")
+def test_efficientsam3_student_segmenter_vs_oracles(cuda):
+    """build_efficientsam3_point_segmenter("efficientvit", "b1"): image -> EV-M student -> 1024 x 72 x 72 -> SAM2-branch FPN -> point-prompt
+    mask decoding, against the oracle composition (efficientvit + student head + neck + SAM heads)."""
+    from efficientsam3_b200.model_builder import build_efficientsam3_point_segmenter
+    from oracle import efficientvit as EV, necks as ON, sam_heads as OH
+    from oracle.weights import fill_state_dict
+    seg = build_efficientsam3_point_segmenter("efficientvit", "b1")
+    sd = {k: v for k, v in fill_state_dict(seg.state_dict(), 47).items() if not v.is_complex()}
+    seg.load_state_dict(sd, strict=False)
+    B, S = 2, 1008
+    g = torch.Generator().manual_seed(6)
+    img = torch.randn(B, 3, S, S, generator=g)
+    coords = torch.rand(B, 1, 2, generator=g) * S
+    labels = torch.ones(B, 1, dtype=torch.int32)
+    with torch.no_grad():
+        vb = {k[len("backbone.vision_backbone."):]: v for k, v in sd.items() if k.startswith("backbone.vision_backbone.")}
+        feats = EV.image_student_encoder({k[len("trunk.model."):]: v for k, v in vb.items() if k.startswith("trunk.model.")}, img, 72, "b1")
+        l288, l144, l72 = ON.neck(vb, feats, prefix="sam2_convs.")[:3]
+        sd_md = {k[len("sam_mask_decoder."):]: v for k, v in sd.items() if k.startswith("sam_mask_decoder.")}
+        sd_pe = {k[len("sam_prompt_encoder."):]: v for k, v in sd.items() if k.startswith("sam_prompt_encoder.")}
+        hr = OH.high_res_from_fpn(sd_md, "", l288, l144)
+        ref = OH.forward_sam_heads(sd_pe, sd_md, l72 + sd["no_mem_embed"].reshape(1, -1, 1, 1), hr, coords, labels, S, multimask_output=True)
+    seg = seg.to(cuda)
+    out = seg.set_image_batch(img.to(cuda)).predict_batch(coords.to(cuda), labels.to(cuda), multimask_output=True, return_logits=True)
+    low = out["low_res_multimasks"].cpu()
+    e_low = ((low.double() - ref["low_res_multimasks"].double()).norm() / ref["low_res_multimasks"].double().norm()).item()
+    agree = ((out["high_res"].cpu() > 0) == (ref["high_res_multimasks"] > 0)).float().mean().item()
+    print(f"EfficientSAM3 (EV-M) point-prompt pipeline: low-res logits rel_l2={e_low:.3e}, binary mask agreement {agree:.5f}")
+    assert e_low <= 3e-2 and agree >= 0.99
+    assert torch.equal(out["best"].cpu(), ref["best"])
