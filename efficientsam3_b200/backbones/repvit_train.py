@@ -16,7 +16,7 @@ composition only:
                                            9 es3_gemm_bf16 calls on shifted dz, accumulated per phase through the residual operand
 
 The phase split / interleave and the shifted copies are torch strided copies (re-layouts, as the weight packing is).
-Built for repvit_m1_1 (patch-embed mid width 32); the other widths raise.
+Built for repvit_m1_1 and repvit_m0_9 (patch-embed mid widths 32 and 24 -> zero-padded to 32); repvit_m2_3 (40) raises.
 """
 from __future__ import annotations
 
@@ -213,8 +213,12 @@ class PatchEmbedUnit:
         self.c0 = _cu(pe[0], "gelu", "stem")
         self.cb1 = pe[2]
         cmid = pe[2].c.in_channels
-        if cmid not in (32, 48):
-            raise NotImplementedError(f"train-mode RepViT patch embed is built for a 32 / 48-channel first conv (repvit_m1_1); got {cmid}")
+        # es3_conv3x3_s2_narrow_bf16 is instantiated for 32 / 48 input channels: narrower first convs (repvit_m0_9: 24) are
+        # zero-padded, exactly as the eval path's pack_patch_embed does; 40 (repvit_m2_3) would also need a 40-wide stem kernel
+        if cmid not in (24, 32, 48):
+            raise NotImplementedError(f"train-mode RepViT patch embed is built for a 24 / 32 / 48-channel first conv "
+                                      f"(repvit_m0_9, repvit_m1_1); got {cmid}")
+        self.cp = 32 if cmid <= 32 else 48
         self.saved = None
 
     def forward(self, x):
@@ -224,7 +228,13 @@ class PatchEmbedUnit:
         B, H, W, _ = a0.shape
         if H % 2 or W % 2:
             raise NotImplementedError("train-mode RepViT patch embed needs an even feature map after the first conv")
-        w9 = conv.weight.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).to(torch.bfloat16).contiguous()
+        cp = self.cp
+        if cp != cin:                                                            # zero-padded channels meet zero weights
+            a0p = torch.zeros((B, H, W, cp), device=a0.device, dtype=a0.dtype)
+            a0p[..., :cin] = a0
+            a0 = a0p
+        w9 = torch.zeros((9, cout, cp), device=a0.device, dtype=torch.bfloat16)
+        w9[:, :, :cin] = conv.weight.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).to(torch.bfloat16)
         ones = torch.ones(cout, device=a0.device, dtype=torch.float32)
         z = ops.conv3x3_s2_narrow(a0, w9, ones, torch.zeros_like(ones), None)    # raw conv
         mean, invstd, scale, shift, mode = _norm_params(bn, z)
@@ -235,13 +245,15 @@ class PatchEmbedUnit:
         a0, z, w9, (mean, invstd, scale, shift, mode) = self.saved
         self.saved = None
         conv, bn = self.cb1.c, self.cb1.bn
-        cout, cin = conv.out_channels, conv.in_channels
-        B, H, W, _ = a0.shape
+        cout, cin_true = conv.out_channels, conv.in_channels
+        B, H, W, cin = a0.shape                                                  # cin = padded width of the staged input
         Ho, Wo = H // 2, W // 2
         dz = ops.bn_act_bwd(dy.contiguous(), z, scale, shift, None, mode, mean, invstd, _grad_of(grads, bn.weight), _grad_of(grads, bn.bias))
         dz2 = dz.view(-1, cout)
         # weight gradient: tap (ky, kx) reads phase (py, px) of a0 at a stride-1 shift
-        gw = _grad_of(grads, conv.weight)
+        gw_true = _grad_of(grads, conv.weight)
+        gw = gw_true if cin == cin_true else (torch.zeros((cout, cin, 3, 3), device=a0.device, dtype=torch.float32)
+                                             if gw_true is not None else None)
         if gw is not None:
             flat = gw.view(-1)
             phase = {(py, px): a0[:, py::2, px::2, :].contiguous().view(-1, cin) for py in (0, 1) for px in (0, 1)}
@@ -250,6 +262,8 @@ class PatchEmbedUnit:
                 for kx in range(3):
                     px, sx = _TAP[kx]
                     ops.wgrad_pw(dz2, phase[(py, px)], flat[ky * 3 + kx:], ldn=9 * cin, ldk=9, shift=(Ho, Wo, sy, sx))
+            if gw is not gw_true:
+                gw_true += gw[:, :cin_true]
         # input gradient, phase by phase: d a0[2y'+py, 2x'+px] = sum over the taps landing on that phase of dz[y'-sy, x'-sx] W_tap
         shifted = {}
 
@@ -277,6 +291,8 @@ class PatchEmbedUnit:
                         wt = w9[ky * 3 + kx].t().contiguous()                    # [cin, cout]: d a0 = dz . W_tap
                         acc = ops.gemm(dz_at(-_TAP[ky][1], -_TAP[kx][1]), wt, residual=acc)
                 da0[:, py::2, px::2, :] = acc.view(B, Ho, Wo, cin)
+        if cin != cin_true:
+            da0 = da0[..., :cin_true].contiguous()
         self.c0.backward(da0, grads, need_dx=False)
         return None
 

@@ -134,7 +134,7 @@ def test_eval_plan_is_rebuilt_after_a_train_forward(monkeypatch):
 
 def test_train_mode_is_refused_where_it_is_not_built():
     from efficientsam3_b200.stage1.model import build_image_student_model
-    for name in ("tiny_vit_11m", "repvit_m0_9"):      # TinyViT: no train path; RepViT other than m1_1: patch-embed width
+    for name in ("tiny_vit_11m", "repvit_m2_3"):      # TinyViT: no train path; repvit_m2_3: 40-channel patch-embed stem
         cfg = NS(MODEL=NS(BACKBONE=name), DATA=NS(IMG_SIZE=160), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=12))
         m = build_image_student_model(cfg).train()
         with pytest.raises(NotImplementedError):
@@ -169,17 +169,47 @@ def _round_like_product_repvit(sd):
     return out
 
 
-def _oracle_step_repvit(sd0, x, teacher, img, sizes, embed, bn_train):
+def _oracle_step_repvit(sd0, x, teacher, img, sizes, embed, bn_train, variant="repvit_m1_1"):
     from oracle import repvit as R
     sd = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v.clone()) for k, v in sd0.items()}
     if bn_train:
         with O.bn_batch_stats():
-            out = R.image_student_encoder(sd, x, embed, "repvit_m1_1")
+            out = R.image_student_encoder(sd, x, embed, variant)
     else:
-        out = R.image_student_encoder(sd, x, embed, "repvit_m1_1")
+        out = R.image_student_encoder(sd, x, embed, variant)
     loss, _, _ = oracle_kd_loss(out, teacher, img, sizes, 1.0)
     loss.backward()
     return out.detach(), loss.detach(), sd
+
+
+def test_repvit_m0_9_patch_embed_padding_exact(monkeypatch):
+    """repvit_m0_9: the 24-channel first conv is zero-padded to the 32 channels the stride-2 kernel is instantiated for; the padding
+    must not leak into any gradient (fp64 emulation vs oracle autograd)."""
+    from efficientsam3_b200 import ops
+    emu_ops.install(monkeypatch)
+    monkeypatch.setattr(emu_ops, "BF", torch.float64)
+    monkeypatch.setattr(emu_ops, "CD", torch.float64)
+    monkeypatch.setattr(ops, "ACT_DTYPE", torch.float64)
+    img, embed, B = 128, 8, 2
+    m = _student("repvit_m0_9", img=img, embed=embed, seed=13)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(B, 3, img, img, generator=torch.Generator().manual_seed(1))
+    teacher = torch.randn(B, 1024, embed, embed, generator=torch.Generator().manual_seed(2)).double()
+    sizes = [(3, img, img)] * B
+    m.train()
+    out = m(x)
+    loss, _, _ = oracle_kd_loss(out, teacher, img, sizes, 1.0)
+    loss.backward()
+    sd_ref = {k: (v.double() if v.is_floating_point() else v) for k, v in _round_like_product_repvit(sd0).items()}
+    ref_out, _, sd = _oracle_step_repvit(sd_ref, x.double(), teacher, img, sizes, embed, True, "repvit_m0_9")
+    assert _rel(out.detach(), ref_out) < 1e-5
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        g = sd[k].grad.double()
+        assert p.grad.shape == p.shape
+        num += (p.grad.double() - g).pow(2).sum().item()
+        den += g.pow(2).sum().item()
+    assert (num / den) ** 0.5 < 2e-5, (num / den) ** 0.5
 
 
 @pytest.mark.parametrize("bn_train,exact,batched_se", [(True, True, False), (False, True, False), (False, False, False), (True, True, True)])
