@@ -239,6 +239,74 @@ class LiteMLAUnit:
         return ops.gemm(d_qkv, qkv_w.t().contiguous(), residual=dy.reshape(-1, C)).view(B, H, W, C)
 
 
+class LiteMLAGenericUnit:
+    """x + LiteMLA(x) for head dims other than 16 (efficientvit_b2: 32), on the route the inference plan takes for them:
+    depthwise 5x5 (es3_dwconv) + the grouped 1x1 as a block-diagonal tcgen05 GEMM + es3_litemla_attn_generic; backward through
+    es3_litemla_attn_bwd_generic.  (That backward kernel has had no GPU run yet -- litemla_bwd_generic.cu.)"""
+
+    def __init__(self, m: LiteMLA):
+        if m.dim not in (16, 32):
+            raise NotImplementedError(f"LiteMLA head dim {m.dim} is not instantiated (16, 32)")
+        assert m.qkv.norm is None and m.qkv.conv.bias is None and m.qkv.act is None and m.aggreg[0][0].bias is None
+        self.m = m
+        self.proj = _unit(m.proj, "pw")
+        self.saved = None
+
+    def forward(self, x):
+        m = self.m
+        d = m.dim
+        B, H, W, C = x.shape
+        if H * W <= d:
+            raise NotImplementedError("LiteMLA quadratic branch (H*W <= dim, ops.py:623-654) is not built natively")
+        qkv_w = pw_weight(m.qkv.conv)
+        c3 = qkv_w.shape[0]
+        G = c3 // d
+        dwc, pwc = m.aggreg[0][0], m.aggreg[0][1]
+        agg_dw = dw_weight(dwc, None)                                            # [25, c3] fp32
+        wg = pwc.weight.detach().reshape(G, d, d).to(torch.bfloat16)             # [group][out n][in i]
+        w_bd = torch.block_diag(*wg).contiguous()                                # y2 = t . w_bd^T
+        ms = torch.empty((B, H, W, 2 * c3), device=x.device, dtype=ops.ACT_DTYPE)
+        ms2 = ms.view(-1, 2 * c3)
+        ops.gemm(x.view(-1, C), qkv_w, out=ms2[:, :c3])
+        t = ops.dwconv(ms[..., :c3], agg_dw, None, 5, 1, None)
+        ops.gemm(t.view(-1, c3), w_bd, out=ms2[:, c3:])
+        att, kv = ops.litemla_attn_generic(ms, 2 * m.heads, d, m.eps, return_kv=True)
+        y = self.proj.forward(att, residual=x)
+        self.saved = (x, ms, t, kv, qkv_w, agg_dw, wg)
+        return y
+
+    def backward(self, dy, grads):
+        m = self.m
+        d = m.dim
+        x, ms, t, kv, qkv_w, agg_dw, wg = self.saved
+        self.saved = None
+        B, H, W, C = x.shape
+        c3 = qkv_w.shape[0]
+        G = c3 // d
+        dwc, pwc = m.aggreg[0][0], m.aggreg[0][1]
+        datt = self.proj.backward(dy, grads)
+        dms = ops.litemla_attn_bwd_generic(ms, datt.contiguous(), kv, 2 * m.heads, d, m.eps)
+        dms2 = dms.view(-1, 2 * c3)
+        d_y2 = dms2[:, c3:]
+        g_pw = _grad_of(grads, pwc.weight)
+        if g_pw is not None:
+            full = torch.zeros((c3, c3), device=x.device, dtype=torch.float32)
+            ops.wgrad_pw(d_y2, t.view(-1, c3), full)
+            idx = torch.arange(G, device=x.device)
+            g_pw += full.view(G, d, G, d)[idx, :, idx, :].reshape(pwc.weight.shape)
+        w_bd_t = torch.block_diag(*wg.transpose(1, 2)).contiguous()              # [d g + i][d g + n]
+        d_t = ops.gemm(d_y2, w_bd_t).view(B, H, W, c3)
+        g_dw = _grad_of(grads, dwc.weight)
+        if g_dw is not None:
+            ops.dwconv_wgrad(d_t, ms[..., :c3], g_dw, 5, 1)
+        d_q1 = ops.dwconv(d_t, agg_dw.flip(0).contiguous(), None, 5, 1, None)
+        d_qkv = ops.add_bf16(dms2[:, :c3], d_q1.view(-1, c3))
+        g_qkv = _grad_of(grads, m.qkv.conv.weight)
+        if g_qkv is not None:
+            ops.wgrad_pw(d_qkv, x.view(-1, C), g_qkv)
+        return ops.gemm(d_qkv, qkv_w.t().contiguous(), residual=dy.reshape(-1, C)).view(B, H, W, C)
+
+
 class EfficientViTTrainGraph:
     """Units of EfficientViTBackbone in execution order (backbone.py:32-156)."""
 
@@ -256,7 +324,8 @@ class EfficientViTTrainGraph:
                     self.units.append(MBConvUnit(main, op.shortcut is not None) if isinstance(main, MBConv)
                                       else DSConvUnit(main, op.shortcut is not None))
                 elif isinstance(op, EfficientViTBlock):
-                    self.units.append(LiteMLAUnit(op.context_module.main))
+                    mla = op.context_module.main
+                    self.units.append(LiteMLAUnit(mla) if mla.dim == 16 else LiteMLAGenericUnit(mla))
                     self.units.append(MBConvUnit(op.local_module.main, True))
                 else:
                     raise TypeError(type(op))

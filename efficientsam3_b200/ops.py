@@ -297,8 +297,9 @@ def litemla_attn(ms, heads2, eps=1e-15, tc=True, return_kv=False):
     return (att, kv) if return_kv else att
 
 
-def litemla_attn_generic(ms, heads2, dim, eps=1e-15):
-    """ReLU linear attention for head dim 16 | 32 (CUDA-core kernels).  ms: [B,H,W,3*dim*heads2] bf16 -> [B,H,W,dim*heads2]."""
+def litemla_attn_generic(ms, heads2, dim, eps=1e-15, return_kv=False):
+    """ReLU linear attention for head dim 16 | 32 (CUDA-core kernels).  ms: [B,H,W,3*dim*heads2] bf16 -> [B,H,W,dim*heads2].
+    return_kv: also return the partial-KV workspace (es3_litemla_attn_bwd_generic consumes it)."""
     _chk(ms, torch.bfloat16, "ms")
     _ensure_init(ms)
     assert ms.is_contiguous() and ms.shape[3] == 3 * dim * heads2
@@ -307,7 +308,7 @@ def litemla_attn_generic(ms, heads2, dim, eps=1e-15):
     kv = torch.empty((B * heads2 * ((H * W + 127) // 128) * (dim + 1) * dim,), device=ms.device, dtype=torch.float32)
     _call("es3_litemla_attn_generic", f"litemla_attn_generic[{dim}]", _nb(ms, att), 2 * B * H * W * heads2 * (dim + 1) * dim * 2,
           ms.data_ptr(), ld, kv.data_ptr(), att.data_ptr(), att.shape[3], B, H * W, heads2, dim, float(eps), _stream())
-    return att
+    return (att, kv) if return_kv else att
 
 
 MBCONV_TC = True   # stride-1 residual blocks on the tcgen05 kernel (es3_mbconv_tc_bf16); False -> mma.sync kernel only
@@ -729,7 +730,8 @@ def win_attn_bias(qkv, qkv_pad, bias, B, H, W, C, heads, ws, scale):
 # ------------------------------------------------------------------------------------ student backward (train_bwd.cu)
 BN_MODE = {"none": 0, "eval": 1, "batch": 2}
 KERNELS_PER_CALL.update({"es3_bn_stats": 2, "es3_bn_act_bwd_reduce": 2, "es3_wgrad_pw": 2, "es3_dwconv_wgrad": 2,
-                         "es3_stem_wgrad": 2, "es3_litemla_attn_bwd": 2, "es3_dwconv_wgrad_tiled": 2, "es3_se_bwd_dgate": 2})
+                         "es3_stem_wgrad": 2, "es3_litemla_attn_bwd": 2, "es3_dwconv_wgrad_tiled": 2, "es3_se_bwd_dgate": 2,
+                         "es3_litemla_attn_bwd_generic": 2})
 
 
 def _f32ws(n, dev):
@@ -895,6 +897,21 @@ def dwconv_wgrad(dz, x, dW, ks, stride, impl=None):
     _call("es3_dwconv_wgrad", f"dwconv_wgrad{ks}x{ks}s{stride}", _nb(dz) + B * H * W * C * 2, 2 * dz.numel() * ks * ks,
           dz.data_ptr(), x.data_ptr(), x.stride(2), B, H, W, C, ks, stride, ws.data_ptr(), dW.data_ptr(), _stream())
     return dW
+
+
+def litemla_attn_bwd_generic(ms, datt, kv, heads2, dim, eps=1e-15):
+    """Backward of litemla_attn_generic (head dim 16 | 32): ms [B,H,W,3*dim*heads2], datt [B,H,W,dim*heads2] bf16 -> dms like ms."""
+    _chk(ms, torch.bfloat16, "ms"); _chk(datt, torch.bfloat16, "datt"); _chk(kv, torch.float32, "kv")
+    _ensure_init(ms)
+    assert ms.is_contiguous() and datt.is_contiguous() and ms.shape[3] == 3 * dim * heads2 and datt.shape[3] == dim * heads2
+    B, H, W, ld = ms.shape
+    HW = H * W
+    dms = torch.empty_like(ms)
+    ws = _f32ws(_lib.size("es3_litemla_bwd_generic_ws_floats", B, HW, heads2, dim), ms.device)
+    _call("es3_litemla_attn_bwd_generic", f"litemla_attn_bwd_generic[{dim}]", 2 * _nb(ms, datt) + _nb(dms),
+          2 * B * HW * heads2 * (dim + 1) * dim * 5, ms.data_ptr(), ld, datt.data_ptr(), datt.shape[3], kv.data_ptr(), (HW + 127) // 128,
+          ws.data_ptr(), dms.data_ptr(), ld, B, HW, heads2, dim, float(eps), _stream())
+    return dms
 
 
 SE_BWD_BATCHED = False   # SqueezeExcite backward through es3_se_bwd_* instead of per-image loops (no GPU parity run yet: off)

@@ -58,7 +58,7 @@ class ImageStudentEncoder(nn.Module, NativePlanMixin):
         BN modules, set_bn_state), backward on the kernels of train_bwd.cu.  Built for the EfficientViT b0 / b1 and RepViT m1_1 / m0_9 students."""
         if not isinstance(self.backbone, (EfficientViTAdapter, RepViTAdapter)):
             raise NotImplementedError(
-                "train-mode forward/backward is built for the EfficientViT (efficientvit_b0 / b1) and RepViT (repvit_m1_1 / m0_9) "
+                "train-mode forward/backward is built for the EfficientViT (efficientvit_b0 / b1 / b2) and RepViT (repvit_m1_1 / m0_9) "
                 f"students; {type(self.backbone).__name__} is eval-only (see DESIGN.md).  Call .eval() first.")
         params = [p for p in self.parameters()]
         return StudentTrainFunction.apply(self, x, *params)

@@ -321,6 +321,12 @@ int es3_dwconv_bwd_data(const void* dz, const float* w, void* dx, int B, int H, 
 long long es3_dwconv_wgrad_ws_floats(int B, int H, int W, int C, int ks, int stride);
 int es3_dwconv_wgrad(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, int stride, float* ws,
                      float* dW, void* stream);
+/* Backward of es3_litemla_attn_generic (head dim 16 | 32; efficientvit_b2 uses 32): same contract as es3_litemla_attn_bwd with
+ * kv_part = the workspace es3_litemla_attn_generic filled (nchunk_f = ceil(HW / 128)).  No GPU run yet (written after the
+ * round-1 GPU budget was spent). */
+long long es3_litemla_bwd_generic_ws_floats(int B, int HW, int heads2, int dim);
+int es3_litemla_attn_bwd_generic(const void* ms, long long ld, const void* dy, long long lddy, const float* kv_part, int nchunk_f,
+                                 float* dkv_ws, void* dms, long long lddms, int B, int HW, int heads2, int dim, float eps, void* stream);
 /* Shared-memory tiled variant of es3_dwconv_wgrad for stride 1 and C % 32 == 0 (same result contract).  Written after the round-1
  * GPU budget was spent: NOT on the default path until it has a GPU parity run (profiles/r1_next_steps.md). */
 long long es3_dwconv_wgrad_tiled_ws_floats(int B, int H, int W, int C, int ks);

@@ -104,16 +104,16 @@ def litemla_aggreg_dwpw(ms, wd, wp, C3):
     return ms
 
 
-def _lite_attn(ms, heads2, eps):
-    """ms [B,HW,heads2*48] float -> (att [B,HW,heads2*16], KV [B,heads2,17,16])."""
+def _lite_attn(ms, heads2, eps, dim=16):
+    """ms [B,HW,heads2*3*dim] float -> (att [B,HW,heads2*dim], KV [B,heads2,dim+1,dim])."""
     B, HW, _ = ms.shape
-    t = ms.reshape(B, HW, heads2, 48)
-    q, k, v = F.relu(t[..., :16]), F.relu(t[..., 16:32]), t[..., 32:]
+    t = ms.reshape(B, HW, heads2, 3 * dim)
+    q, k, v = F.relu(t[..., :dim]), F.relu(t[..., dim:2 * dim]), t[..., 2 * dim:]
     vpad = torch.cat([v, torch.ones_like(v[..., :1])], dim=-1)        # [B,HW,h,17]
     kv = torch.einsum("bnhj,bnhi->bhji", vpad, k)                     # [B,h,17,16]
     o = torch.einsum("bhji,bnhi->bnhj", kv, q)                        # [B,HW,h,17]
-    y = o[..., :16] / (o[..., 16:] + eps)
-    return y.reshape(B, HW, heads2 * 16), kv
+    y = o[..., :dim] / (o[..., dim:] + eps)
+    return y.reshape(B, HW, heads2 * dim), kv
 
 
 def litemla_attn(ms, heads2, eps=1e-15, tc=True, return_kv=False):
@@ -126,6 +126,26 @@ def litemla_attn(ms, heads2, eps=1e-15, tc=True, return_kv=False):
     ws = torch.zeros(B, heads2, nchunk, 17, 16, dtype=CD)
     ws[:, :, 0] = kv                                                  # same layout as the kernel's partial sums
     return att, ws.reshape(-1)
+
+
+def litemla_attn_generic(ms, heads2, dim, eps=1e-15, return_kv=False):
+    B, H, W, ld = ms.shape
+    y, kv = _lite_attn(ms.to(CD).reshape(B, H * W, ld), heads2, eps, dim)
+    att = y.reshape(B, H, W, heads2 * dim).to(BF)
+    if not return_kv:
+        return att
+    ws = torch.zeros(B, heads2, (H * W + 127) // 128, dim + 1, dim, dtype=CD)
+    ws[:, :, 0] = kv
+    return att, ws.reshape(-1)
+
+
+def litemla_attn_bwd_generic(ms, datt, kv, heads2, dim, eps=1e-15):
+    B, H, W, ld = ms.shape
+    msf = ms.to(CD).reshape(B, H * W, ld).requires_grad_(True)
+    with torch.enable_grad():
+        y, _ = _lite_attn(msf, heads2, eps, dim)
+        (g,) = torch.autograd.grad(y, msf, datt.to(CD).reshape(B, H * W, heads2 * dim))
+    return g.reshape(ms.shape).to(BF)
 
 
 def bilinear_nhwc_to_nchw(x, Ho, Wo):
@@ -330,7 +350,7 @@ def litemla_attn_bwd(ms, datt, kv, heads2, eps=1e-15):
     return g.reshape(ms.shape).to(BF)
 
 
-PATCHED = ["gemm", "gemm_simt", "channel_mean", "scale_channels", "conv3x3_s2_narrow", "conv3x3", "stem_conv3x3_s2", "dwconv", "litemla_dwpw_weights", "litemla_aggreg_dwpw", "litemla_attn",
+PATCHED = ["gemm", "gemm_simt", "channel_mean", "scale_channels", "conv3x3_s2_narrow", "conv3x3", "stem_conv3x3_s2", "dwconv", "litemla_dwpw_weights", "litemla_aggreg_dwpw", "litemla_attn", "litemla_attn_generic", "litemla_attn_bwd_generic",
            "bilinear_nhwc_to_nchw", "nhwc_to_nchw_f32", "nchw_f32_to_nhwc", "bn_stats", "affine_act", "bn_act_bwd", "add_bf16",
            "wgrad_pw", "se_bwd_dgate", "se_bwd_apply", "transpose_pad", "accumulate_strided", "dwconv_bwd_data", "dwconv_wgrad", "stem_wgrad", "bilinear_bwd", "litemla_attn_bwd"]
 

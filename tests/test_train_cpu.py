@@ -37,12 +37,15 @@ def _rel(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
 
 
-def _round_like_product(sd):
+def _round_like_product(sd, dw5_fp32=False):
     """The weights the product packs to bf16 (every dense contraction operand: 1x1 / dense 3x3 convs and the LiteMLA
-    aggregation taps); depthwise 3x3 taps, the stem conv, biases and BN vectors stay fp32."""
+    aggregation taps); depthwise 3x3 taps, the stem conv, biases and BN vectors stay fp32.  dw5_fp32: the dim-32 LiteMLA route
+    (efficientvit_b2) keeps the 5x5 aggregation taps in fp32 (es3_dwconv), only the grouped 1x1 is a bf16 GEMM operand."""
     out = {}
     for k, v in sd.items():
         dense = v.dim() == 4 and k.endswith(".weight") and (v.shape[1] > 1 or ".aggreg." in k) and "input_stem.op_list.0." not in k
+        if dw5_fp32 and ".aggreg.0.0." in k:
+            dense = False
         out[k] = v.to(torch.bfloat16).float() if dense else v.clone()
     return out
 
@@ -349,7 +352,8 @@ def test_smoke_training_half_runs_under_emulation(monkeypatch, capsys):
     assert "training step" in capsys.readouterr().out and not m.training
 
 
-@pytest.mark.parametrize("name,variant,img,embed", [("efficientvit_b0", "b0", 160, 12), ("efficientvit_b1", "b1", 224, 9)])
+@pytest.mark.parametrize("name,variant,img,embed", [("efficientvit_b0", "b0", 160, 12), ("efficientvit_b1", "b1", 224, 9),
+                                                    ("efficientvit_b2", "b2", 192, 9)])
 def test_other_sizes_exact(monkeypatch, name, variant, img, embed):
     """The fp64 logic check on the second EfficientViT name with a training graph (b0: 8-channel stem, 2-block stages) and on an
     odd-sized map chain (224 -> 112 / 56 / 28 / 14 / 7: stride-2 layers over odd extents, head resize 7 -> 9)."""
@@ -368,7 +372,7 @@ def test_other_sizes_exact(monkeypatch, name, variant, img, embed):
     out = m(x)
     loss, _, _ = oracle_kd_loss(out, teacher, img, sizes, 1.0)
     loss.backward()
-    sd_ref = {k: (v.double() if v.is_floating_point() else v) for k, v in _round_like_product(sd0).items()}
+    sd_ref = {k: (v.double() if v.is_floating_point() else v) for k, v in _round_like_product(sd0, dw5_fp32=(variant == "b2")).items()}
     ref_out, _, sd = _oracle_step(sd_ref, x.double(), teacher, img, sizes, variant, embed, True)
     assert _rel(out.detach(), ref_out) < 1e-5
     num = den = 0.0

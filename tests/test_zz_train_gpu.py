@@ -458,3 +458,45 @@ def test_efficientsam3_student_segmenter_vs_oracles(cuda):
     print(f"EfficientSAM3 (EV-M) point-prompt pipeline: low-res logits rel_l2={e_low:.3e}, binary mask agreement {agree:.5f}")
     assert e_low <= 3e-2 and agree >= 0.99
     assert torch.equal(out["best"].cpu(), ref["best"])
+
+
+@pytest.mark.xfail(strict=False, reason="es3_litemla_attn_bwd_generic (head dim 16 | 32, efficientvit_b2) was written after the round-1 GPU budget was "
+                                        "spent: the b2 training graph is exact on CPU, first GPU run pending")
+@pytest.mark.parametrize("B,H,W,heads2,dim", [(2, 10, 10, 8, 32), (1, 23, 29, 4, 32), (2, 12, 12, 6, 16)])
+def test_litemla_attn_bwd_generic(cuda, B, H, W, heads2, dim):
+    from efficientsam3_b200 import ops
+    g = _g(B + H + heads2 + dim)
+    ms = _bf(torch.randn(B, H, W, 3 * dim * heads2, generator=g))
+    datt = _bf(torch.randn(B, H, W, dim * heads2, generator=g))
+    att, kv = ops.litemla_attn_generic(ms.to(cuda), heads2, dim, 1e-15, return_kv=True)
+    _close(att, E.litemla_attn_generic(ms, heads2, dim, 1e-15), 1e-2, "litemla_attn_generic fwd")
+    got = ops.litemla_attn_bwd_generic(ms.to(cuda), datt.to(cuda), kv, heads2, dim, 1e-15)
+    _close(got, E.litemla_attn_bwd_generic(ms, datt, None, heads2, dim, 1e-15), 1.5e-2, "litemla_attn_bwd_generic")
+
+
+@pytest.mark.xfail(strict=False, reason="efficientvit_b2 training graph: exact on CPU, first GPU run pending (its attention backward kernel is new)")
+def test_efficientvit_b2_training_step_matches_oracle_autograd(cuda):
+    from efficientsam3_b200.stage1.optim import KDLossFunction
+    img, embed, B = 320, 20, 2
+    m = _student("efficientvit_b2", img, embed)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(B, 3, img, img, generator=_g(1))
+    teacher = torch.randn(B, 1024, embed, embed, generator=_g(2))
+    sizes = [(3, img, img)] * B
+    m = m.to(cuda).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+            mod.eval()
+    out = m(x.to(cuda))
+    sz = torch.tensor([[img, img]] * B, dtype=torch.int32, device=cuda)
+    loss = KDLossFunction.apply(out, teacher.to(cuda), sz, img, 1.0)
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_out, _, sd = _oracle_grads(sd0, x, teacher, img, sizes, "b2", embed, False)
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        g = sd[k].grad.double()
+        num += (p.grad.cpu().double() - g).pow(2).sum().item()
+        den += g.pow(2).sum().item()
+    print(f"efficientvit_b2 (frozen BN): all-gradient rel-L2 {(num / den) ** 0.5:.3e}")
+    assert (num / den) ** 0.5 < 5e-2
