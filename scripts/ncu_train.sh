@@ -7,6 +7,7 @@
 set -x
 mkdir -p gpurun_out
 ARGS="scripts/train_step_bench.py --batch 8 --img 512 --embed 32 --steps 1 --warmup 1"
+# (a normal, un-profiled run with the CPU baseline beside it:  python scripts/train_step_bench.py --cpu-baseline --table gpurun_out/train_step.md)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2200 --csv --log-file gpurun_out/train_launches.csv python $ARGS > gpurun_out/train_ncu.log 2>&1
 for k in wgrad_pw_kernel dw_wgrad_strip_kernel col_reduce_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 40 -c 2 -o gpurun_out/train_$k -f python $ARGS >> gpurun_out/train_ncu.log 2>&1

@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--backbone", default="efficientvit_b1")
     ap.add_argument("--frozen-bn", action="store_true")
     ap.add_argument("--table", default=None)
+    ap.add_argument("--cpu-baseline", action="store_true", help="also time the same iteration of the CPU oracle (PyTorch fp32 eager autograd, "
+                                                                "all host threads) on a bounded sample: batch 2")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     B, S, E = a.batch, a.img, a.embed
@@ -89,6 +91,8 @@ def main():
             "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 2),
             "profiled_kernel_ms": round(sum(r[1] for r in rows), 3),
             "top": [{"kernel": k, "ms": round(t, 3), "calls": c} for k, t, c, _, _ in rows[:8]]}
+    if a.cpu_baseline:
+        line["cpu_baseline"] = cpu_oracle_train_step(S, E, a.backbone)
     print(json.dumps(line), flush=True)
     if a.table:
         with open(a.table, "w") as f:
@@ -97,6 +101,32 @@ def main():
             f.write("| kernel family | launches/step | ms/step | alg GB/s | alg TFLOP/s |\n|---|---|---|---|---|\n")
             for k, t, c, kb, kf in rows:
                 f.write(f"| `{k}` | {c} | {t:.4f} | {kb/1e9/(t/1e3):.0f} | {kf/1e12/(t/1e3):.1f} |\n")
+
+
+def cpu_oracle_train_step(S, E, backbone, batch=2):
+    """The same KD iteration (train-mode forward, KD loss, backward; no optimiser) on the CPU oracle -- a reported baseline only."""
+    import time
+    from oracle import efficientvit as O
+    from oracle.kd_loss import kd_loss
+    from oracle.weights import fill_state_dict
+    assert backbone.startswith("efficientvit_"), "the CPU baseline leg is wired for the EfficientViT oracle"
+    variant = backbone.split("_")[-1]
+    cfg = NS(MODEL=NS(BACKBONE=backbone), DATA=NS(IMG_SIZE=S), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=E))
+    sd0 = fill_state_dict(build_image_student_model(cfg).state_dict(), 7)
+    x = torch.randn(batch, 3, S, S, generator=torch.Generator().manual_seed(1))
+    teacher = torch.randn(batch, 1024, E, E, generator=torch.Generator().manual_seed(2))
+    sizes = [(3, S, S)] * batch
+    ts = []
+    for _ in range(2):
+        sd = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v.clone()) for k, v in sd0.items()}
+        t0 = time.perf_counter()
+        with O.bn_batch_stats():
+            out = O.image_student_encoder(sd, x, E, variant)
+        loss, _, _ = kd_loss(out, teacher, S, sizes, 1.0)
+        loss.backward()
+        ts.append(time.perf_counter() - t0)
+    return {"images_per_s": round(batch / min(ts), 3), "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"best of 2 iterations of batch {batch} x 3x{S}x{S}, PyTorch-CPU fp32 eager autograd of the oracle port"}
 
 
 if __name__ == "__main__":
