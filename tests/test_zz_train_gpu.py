@@ -10,6 +10,9 @@ functional check: a few optimiser steps reduce the loss.
 
 (The file name sorts last on purpose: it is the newest code of the round.)"""
 import math
+import os
+import subprocess
+import sys
 from types import SimpleNamespace as NS
 
 import pytest
@@ -18,6 +21,11 @@ import torch
 import emu_ops as E
 
 pytestmark = pytest.mark.gpu
+
+
+# Kernels that have never run on a GPU execute in their OWN process (test_never_run_kernels_isolated below): a fault in one of
+# them cannot poison the CUDA context the verified tests share.
+_isolated = pytest.mark.skipif(os.environ.get("ES3_ISOLATED") != "1", reason="runs inside test_never_run_kernels_isolated's subprocess")
 
 
 def _bf(t):
@@ -399,6 +407,7 @@ def test_repvit_training_step_matches_oracle_autograd(cuda, bn_train):
     assert rel_out < tol_out and rel_all < tol_all, (rel_out, rel_all)
 
 
+@_isolated
 @pytest.mark.xfail(strict=False, reason="es3_dwconv_wgrad_tiled was written after the round-1 GPU budget was spent: not on the default path, "
                                         "first GPU run pending")
 @pytest.mark.parametrize("B,H,W,C,ks", [(2, 16, 16, 32, 3), (1, 9, 11, 96, 5), (2, 64, 64, 384, 5), (2, 40, 37, 512, 3), (1, 7, 5, 64, 5)])
@@ -414,6 +423,7 @@ def test_dwconv_wgrad_tiled(cuda, B, H, W, C, ks):
     _close(got, ref, 2e-3, "dwconv_wgrad tiled")
 
 
+@_isolated
 @pytest.mark.xfail(strict=False, reason="es3_se_bwd_* were written after the round-1 GPU budget was spent: not on the default path, first GPU run pending")
 @pytest.mark.parametrize("B,H,W,C", [(3, 16, 16, 64), (2, 9, 7, 128), (4, 32, 32, 256), (2, 5, 5, 2560)])
 def test_se_bwd_batched(cuda, B, H, W, C):
@@ -460,6 +470,7 @@ def test_efficientsam3_student_segmenter_vs_oracles(cuda):
     assert torch.equal(out["best"].cpu(), ref["best"])
 
 
+@_isolated
 @pytest.mark.xfail(strict=False, reason="es3_litemla_attn_bwd_generic (head dim 16 | 32, efficientvit_b2) was written after the round-1 GPU budget was "
                                         "spent: the b2 training graph is exact on CPU, first GPU run pending")
 @pytest.mark.parametrize("B,H,W,heads2,dim", [(2, 10, 10, 8, 32), (1, 23, 29, 4, 32), (2, 12, 12, 6, 16)])
@@ -474,6 +485,7 @@ def test_litemla_attn_bwd_generic(cuda, B, H, W, heads2, dim):
     _close(got, E.litemla_attn_bwd_generic(ms, datt, None, heads2, dim, 1e-15), 1.5e-2, "litemla_attn_bwd_generic")
 
 
+@_isolated
 @pytest.mark.xfail(strict=False, reason="efficientvit_b2 training graph: exact on CPU, first GPU run pending (its attention backward kernel is new)")
 def test_efficientvit_b2_training_step_matches_oracle_autograd(cuda):
     from efficientsam3_b200.stage1.optim import KDLossFunction
@@ -500,3 +512,13 @@ def test_efficientvit_b2_training_step_matches_oracle_autograd(cuda):
         den += g.pow(2).sum().item()
     print(f"efficientvit_b2 (frozen BN): all-gradient rel-L2 {(num / den) ** 0.5:.3e}")
     assert (num / den) ** 0.5 < 5e-2
+
+
+@pytest.mark.xfail(strict=False, reason="never-run kernels (es3_dwconv_wgrad_tiled, es3_se_bwd_*, es3_litemla_attn_bwd_generic) and the efficientvit_b2 "
+                                        "training step, executed in a separate process; first GPU run pending")
+def test_never_run_kernels_isolated(cuda):
+    env = dict(os.environ, ES3_ISOLATED="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-p", "no:cacheprovider", "-s", "-k",
+                        "tiled or batched or generic or b2"], env=env, capture_output=True, text=True, timeout=900)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "xfailed" not in r.stdout.splitlines()[-1], r.stdout[-500:] + r.stderr[-500:]
