@@ -358,6 +358,20 @@ def test_training_steps_reduce_the_loss_and_are_deterministic(cuda):
     assert (e1 - e0).abs().max().item() > 1e-3
 
 
+def test_half_width_image_batches(cuda):
+    """bf16 image batches (half the host->device bytes) go through a device cast and then the same kernels: the result equals the forward
+    of the rounded batch exactly, and is within the bf16 tolerance of the fp32 batch (the stem rounds its operands to bf16 itself)."""
+    img, embed = 192, 9
+    m = _student("efficientvit_b1", img, embed).to(cuda).eval()
+    x = torch.randn(2, 3, img, img, generator=_g(3)).to(cuda)
+    xb = x.to(torch.bfloat16)
+    a, b, c = m(x), m(xb), m(xb.float())
+    assert torch.equal(b, c)
+    rel = ((a - b).double().norm() / a.double().norm()).item()
+    print(f"bf16 image batch vs fp32 batch: rel-L2 {rel:.3e}, bit-identical: {torch.equal(a, b)}")
+    assert rel < 1e-2
+
+
 # ---------------------------------------------------------------------------------------------
 # Code that has not run on a GPU yet (written after the round-1 GPU budget was spent).  These stay the LAST tests of the last
 # file on purpose: a fault in a never-run kernel must not be able to disturb a verified test.
