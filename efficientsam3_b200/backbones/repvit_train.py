@@ -16,7 +16,8 @@ composition only:
                                            9 es3_gemm_bf16 calls on shifted dz, accumulated per phase through the residual operand
 
 The phase split / interleave and the shifted copies are torch strided copies (re-layouts, as the weight packing is).
-Built for repvit_m1_1 and repvit_m0_9 (patch-embed mid widths 32 and 24 -> zero-padded to 32); repvit_m2_3 (40) raises.
+Built for all three RepViT widths: patch-embed mid widths 32 (m1_1), 24 (m0_9: zero-padded to 32 in front of the second conv) and
+40 (m2_3: the whole first conv + BN runs zero-padded to 48, PaddedStemUnit).
 """
 from __future__ import annotations
 
@@ -202,6 +203,74 @@ class TokenMixerUnit:
         return self.rv.backward(dy, grads)
 
 
+_STEM_WIDTHS = (8, 16, 24, 32, 48)      # es3_stem_conv3x3_s2 instantiations
+_STEM_WGRAD_MAX = 32                    # es3_stem_wgrad: one (output channel, tap) weight per thread, <= 32 channels per launch
+
+
+class PaddedStemUnit:
+    """First patch-embed conv (3 -> C, 3x3, stride 2) + BN + GELU when C is not a width the stem kernels are instantiated for
+    (repvit_m2_3: 40): the conv, its BatchNorm vectors and the running statistics are zero-/one-padded to the next instantiated
+    width P, so the extra channels are exactly zero after the GELU; the weight gradient runs in chunks of <= 32 output channels.
+    Returns / consumes [B,H,W,P] activations (the following conv is padded to P input channels as well)."""
+
+    def __init__(self, cb: Conv2d_BN):
+        self.conv, self.bn = cb.c, cb.bn
+        c = cb.c.out_channels
+        wider = [w for w in _STEM_WIDTHS if w >= c]
+        if not wider:
+            raise NotImplementedError(f"stem conv with {c} output channels exceeds the instantiated widths {_STEM_WIDTHS}")
+        self.c, self.p = c, wider[0]
+        self.saved = None
+
+    def _pad(self, v, fill):
+        out = torch.full((self.p,), fill, device=v.device, dtype=torch.float32)
+        out[:self.c] = v.detach().float()
+        return out
+
+    def forward(self, x):
+        conv, bn, c, p = self.conv, self.bn, self.c, self.p
+        w27 = torch.zeros((27, p), device=x.device, dtype=torch.float32)
+        w27[:, :c] = conv.weight.detach().float().reshape(c, 27).t()
+        z = ops.stem_conv3x3_s2(x, w27, None, None)                              # [B,Ho,Wo,P], extra channels = 0
+        gamma, beta = self._pad(bn.weight, 1.0), self._pad(bn.bias, 0.0)
+        if bn.training:
+            rm, rv = self._pad(bn.running_mean, 0.0), self._pad(bn.running_var, 1.0)
+            mean, invstd, scale, shift = ops.bn_stats(z, gamma, beta, bn.eps, bn.momentum, rm, rv, bn.num_batches_tracked)
+            bn.running_mean.copy_(rm[:c])
+            bn.running_var.copy_(rv[:c])
+            mode = "batch"
+        else:
+            mean = self._pad(bn.running_mean, 0.0)
+            invstd = torch.rsqrt(self._pad(bn.running_var, 1.0) + bn.eps).contiguous()
+            scale = (gamma * invstd).contiguous()
+            shift = (beta - mean * scale).contiguous()
+            mode = "eval"
+        self.saved = (x, z, scale, shift, mean, invstd, mode)
+        return ops.affine_act(z, scale, shift, "gelu")
+
+    def backward(self, da, grads):
+        x, z, scale, shift, mean, invstd, mode = self.saved
+        self.saved = None
+        conv, bn, c, p = self.conv, self.bn, self.c, self.p
+        dev = z.device
+        dg, db = torch.zeros(p, device=dev, dtype=torch.float32), torch.zeros(p, device=dev, dtype=torch.float32)
+        dz = ops.bn_act_bwd(da.contiguous(), z, scale, shift, "gelu", mode, mean, invstd, dg, db)
+        g_w, g_b = _grad_of(grads, bn.weight), _grad_of(grads, bn.bias)
+        if g_w is not None:
+            g_w += dg[:c]
+        if g_b is not None:
+            g_b += db[:c]
+        gw = _grad_of(grads, conv.weight)
+        if gw is not None:      # chunks of output channels in widths the weight-gradient kernel is instantiated for (40 = 32 + 8)
+            c0 = 0
+            while c0 < c:
+                n = max(w for w in _STEM_WIDTHS if w <= min(_STEM_WGRAD_MAX, c - c0))
+                tmp = torch.zeros((n, 3, 3, 3), device=dev, dtype=torch.float32)
+                ops.stem_wgrad(x, dz[..., c0:c0 + n].contiguous(), tmp)
+                gw[c0:c0 + n] += tmp
+                c0 += n
+
+
 # stride-2 3x3 taps on the 2x2 phase decomposition of the input: input row 2 oy + k - 1 = 2 (oy + shift) + phase
 _TAP = {0: (1, -1), 1: (0, 0), 2: (1, 0)}          # k -> (phase, shift of the OUTPUT index inside that phase image)
 
@@ -210,15 +279,16 @@ class PatchEmbedUnit:
     """Conv2d_BN(3, C/2, 3, 2, 1) -> GELU -> Conv2d_BN(C/2, C, 3, 2, 1)  (repvit.py:219-223)."""
 
     def __init__(self, pe: nn.Sequential):
-        self.c0 = _cu(pe[0], "gelu", "stem")
         self.cb1 = pe[2]
         cmid = pe[2].c.in_channels
-        # es3_conv3x3_s2_narrow_bf16 is instantiated for 32 / 48 input channels: narrower first convs (repvit_m0_9: 24) are
-        # zero-padded, exactly as the eval path's pack_patch_embed does; 40 (repvit_m2_3) would also need a 40-wide stem kernel
-        if cmid not in (24, 32, 48):
-            raise NotImplementedError(f"train-mode RepViT patch embed is built for a 24 / 32 / 48-channel first conv "
-                                      f"(repvit_m0_9, repvit_m1_1); got {cmid}")
+        # es3_conv3x3_s2_narrow_bf16 is instantiated for 32 / 48 input channels: narrower first convs (repvit_m0_9: 24,
+        # repvit_m2_3: 40) are zero-padded, exactly as the eval path's pack_patch_embed does
+        if cmid > 48:
+            raise NotImplementedError(f"train-mode patch embed is built for a first conv of <= 48 channels; got {cmid}")
         self.cp = 32 if cmid <= 32 else 48
+        # a first conv whose width the stem kernels are not instantiated for (40) runs zero-padded end to end
+        self.padded_stem = cmid not in _STEM_WIDTHS or cmid > _STEM_WGRAD_MAX
+        self.c0 = PaddedStemUnit(pe[0]) if self.padded_stem else _cu(pe[0], "gelu", "stem")
         self.saved = None
 
     def forward(self, x):
@@ -229,9 +299,9 @@ class PatchEmbedUnit:
         if H % 2 or W % 2:
             raise NotImplementedError("train-mode RepViT patch embed needs an even feature map after the first conv")
         cp = self.cp
-        if cp != cin:                                                            # zero-padded channels meet zero weights
+        if a0.shape[-1] != cp:                                                   # zero-padded channels meet zero weights
             a0p = torch.zeros((B, H, W, cp), device=a0.device, dtype=a0.dtype)
-            a0p[..., :cin] = a0
+            a0p[..., :a0.shape[-1]] = a0
             a0 = a0p
         w9 = torch.zeros((9, cout, cp), device=a0.device, dtype=torch.bfloat16)
         w9[:, :, :cin] = conv.weight.detach().permute(2, 3, 0, 1).reshape(9, cout, cin).to(torch.bfloat16)
@@ -291,6 +361,9 @@ class PatchEmbedUnit:
                         wt = w9[ky * 3 + kx].t().contiguous()                    # [cin, cout]: d a0 = dz . W_tap
                         acc = ops.gemm(dz_at(-_TAP[ky][1], -_TAP[kx][1]), wt, residual=acc)
                 da0[:, py::2, px::2, :] = acc.view(B, Ho, Wo, cin)
+        if self.padded_stem:
+            self.c0.backward(da0[..., :self.c0.p].contiguous(), grads)
+            return None
         if cin != cin_true:
             da0 = da0[..., :cin_true].contiguous()
         self.c0.backward(da0, grads, need_dx=False)

@@ -55,10 +55,10 @@ class ImageStudentEncoder(nn.Module, NativePlanMixin):
 
     def _forward_train(self, x):
         """Train-mode forward recorded as ONE autograd node (StudentTrainFunction): batch-statistics BatchNorm (or frozen
-        BN modules, set_bn_state), backward on the kernels of train_bwd.cu.  Built for the EfficientViT b0 / b1 and RepViT m1_1 / m0_9 students."""
+        BN modules, set_bn_state), backward on the kernels of train_bwd.cu.  Built for the EfficientViT b0 / b1 / b2 and RepViT m0_9 / m1_1 / m2_3 students."""
         if not isinstance(self.backbone, (EfficientViTAdapter, RepViTAdapter)):
             raise NotImplementedError(
-                "train-mode forward/backward is built for the EfficientViT (efficientvit_b0 / b1 / b2) and RepViT (repvit_m1_1 / m0_9) "
+                "train-mode forward/backward is built for the EfficientViT (efficientvit_b0 / b1 / b2) and RepViT (repvit_m0_9 / m1_1 / m2_3) "
                 f"students; {type(self.backbone).__name__} is eval-only (see DESIGN.md).  Call .eval() first.")
         params = [p for p in self.parameters()]
         return StudentTrainFunction.apply(self, x, *params)

@@ -137,7 +137,7 @@ def test_eval_plan_is_rebuilt_after_a_train_forward(monkeypatch):
 
 def test_train_mode_is_refused_where_it_is_not_built():
     from efficientsam3_b200.stage1.model import build_image_student_model
-    for name in ("tiny_vit_11m", "repvit_m2_3"):      # TinyViT: no train path; repvit_m2_3: 40-channel patch-embed stem
+    for name in ("tiny_vit_11m",):      # TinyViT: no training graph yet
         cfg = NS(MODEL=NS(BACKBONE=name), DATA=NS(IMG_SIZE=160), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=12))
         m = build_image_student_model(cfg).train()
         with pytest.raises(NotImplementedError):
@@ -185,16 +185,18 @@ def _oracle_step_repvit(sd0, x, teacher, img, sizes, embed, bn_train, variant="r
     return out.detach(), loss.detach(), sd
 
 
-def test_repvit_m0_9_patch_embed_padding_exact(monkeypatch):
-    """repvit_m0_9: the 24-channel first conv is zero-padded to the 32 channels the stride-2 kernel is instantiated for; the padding
-    must not leak into any gradient (fp64 emulation vs oracle autograd)."""
+@pytest.mark.parametrize("name", ["repvit_m0_9", "repvit_m2_3"])
+def test_repvit_padded_patch_embed_exact(monkeypatch, name):
+    """repvit_m0_9: the 24-channel first conv is zero-padded to the 32 channels the stride-2 kernel is instantiated for; repvit_m2_3: the
+    40-channel first conv + BN run zero-padded to 48 end to end (PaddedStemUnit).  The padding must not leak into any gradient or
+    running statistic (fp64 emulation vs oracle autograd)."""
     from efficientsam3_b200 import ops
     emu_ops.install(monkeypatch)
     monkeypatch.setattr(emu_ops, "BF", torch.float64)
     monkeypatch.setattr(emu_ops, "CD", torch.float64)
     monkeypatch.setattr(ops, "ACT_DTYPE", torch.float64)
     img, embed, B = 128, 8, 2
-    m = _student("repvit_m0_9", img=img, embed=embed, seed=13)
+    m = _student(name, img=img, embed=embed, seed=13)
     sd0 = {k: v.clone() for k, v in m.state_dict().items()}
     x = torch.randn(B, 3, img, img, generator=torch.Generator().manual_seed(1))
     teacher = torch.randn(B, 1024, embed, embed, generator=torch.Generator().manual_seed(2)).double()
@@ -204,8 +206,11 @@ def test_repvit_m0_9_patch_embed_padding_exact(monkeypatch):
     loss, _, _ = oracle_kd_loss(out, teacher, img, sizes, 1.0)
     loss.backward()
     sd_ref = {k: (v.double() if v.is_floating_point() else v) for k, v in _round_like_product_repvit(sd0).items()}
-    ref_out, _, sd = _oracle_step_repvit(sd_ref, x.double(), teacher, img, sizes, embed, True, "repvit_m0_9")
+    ref_out, _, sd = _oracle_step_repvit(sd_ref, x.double(), teacher, img, sizes, embed, True, name)
     assert _rel(out.detach(), ref_out) < 1e-5
+    for k, v in m.state_dict().items():
+        if "running_" in k:
+            assert v.shape == sd[k].shape and _rel(v, sd[k]) < 1e-5, k
     num = den = 0.0
     for k, p in m.named_parameters():
         g = sd[k].grad.double()
