@@ -237,6 +237,14 @@ class TinyViT(nn.Module, NativePlanMixin):
                 cur = ((cur[0] - 1) // 2 + 1, (cur[1] - 1) // 2 + 1)
         self.norm_head = nn.LayerNorm(embed_dims[-1]) if num_classes > 0 else nn.Identity()
         self.head = nn.Linear(embed_dims[-1], num_classes) if num_classes > 0 else nn.Identity()
+        # stochastic-depth rates (tiny_vit.py:491-503: linspace over all blocks); the eval plan ignores them, the training graph
+        # (backbones/tinyvit_train.py) applies timm's DropPath with them
+        dpr = [float(v) for v in torch.linspace(0, drop_path_rate, sum(depths))]
+        k = 0
+        for layer in self.layers:
+            for blk in layer.blocks:
+                blk.drop_path_rate = dpr[k]
+                k += 1
         for m in self.modules():
             if isinstance(m, nn.Linear):
                 nn.init.trunc_normal_(m.weight, std=0.02)

@@ -914,6 +914,44 @@ def litemla_attn_bwd_generic(ms, datt, kv, heads2, dim, eps=1e-15):
     return dms
 
 
+def layernorm_bwd(x, dy, gamma, eps, dgamma=None, dbeta=None, dres=None):
+    """nn.LayerNorm backward over rows: x, dy [M,C] bf16 (the LN input and the gradient of its output) -> dx bf16 (+ dres);
+    dgamma / dbeta fp32 [C] accumulated in place."""
+    _chk(x, torch.bfloat16, "x"); _chk(dy, torch.bfloat16, "dy")
+    _ensure_init(x)
+    assert x.dim() == 2 and x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape
+    assert dres is None or (dres.is_contiguous() and dres.shape == x.shape and dres.dtype == x.dtype)
+    M, C = x.shape
+    dx = torch.empty_like(x)
+    ws = _f32ws(_lib.size("es3_layernorm_bwd_ws_floats", M, C), x.device)
+    _call("es3_layernorm_bwd", "layernorm_bwd", _nb(x, dy, dx, dres), 12 * x.numel(), x.data_ptr(), dy.data_ptr(), gamma.data_ptr(),
+          _ptr(dres), float(eps), dx.data_ptr(), M, C, ws.data_ptr(), _ptr(dgamma), _ptr(dbeta), _stream())
+    return dx
+
+
+def win_attn_bias_bwd(qkv, dout, bias, B, H, W, C, heads, ws, scale):
+    """Backward of win_attn_bias on a map with H, W multiples of ws: qkv [B*H*W, 3C], dout [B*H*W, C] bf16, bias [heads,N,N] fp32
+    -> (dqkv [B*H*W, 3C] bf16, dbias [heads,N,N] fp32).  The kernel writes the per-window score gradients; their sum over the windows
+    (the bias gradient) is a column reduction on the verified es3_bn_act_bwd_reduce kernel."""
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(dout, torch.bfloat16, "dout"); _chk(bias, torch.float32, "bias")
+    _ensure_init(qkv)
+    assert qkv.is_contiguous() and dout.is_contiguous() and bias.is_contiguous()
+    assert qkv.shape == (B * H * W, 3 * C) and dout.shape == (B * H * W, C) and H % ws == 0 and W % ws == 0
+    N = ws * ws
+    nwin = B * (H // ws) * (W // ws)
+    row = heads * N * N
+    ld = (row + 7) // 8 * 8
+    dS = torch.empty((nwin, ld), device=qkv.device, dtype=torch.bfloat16)
+    if ld != row:
+        dS[:, row:].zero_()
+    dqkv = torch.empty_like(qkv)
+    _call("es3_win_attn_bias_bwd", f"win_attn_bias_bwd[ws={ws}]", 2 * _nb(qkv) + _nb(dout, dS), 16 * B * H * W * N * C, qkv.data_ptr(),
+          dout.data_ptr(), bias.data_ptr(), dqkv.data_ptr(), dS.data_ptr(), ld, B, H, W, C, heads, ws, float(scale), _stream())
+    dbias = torch.zeros(ld, device=qkv.device, dtype=torch.float32)
+    bn_act_bwd(dS, dS, None, None, None, "none", dbeta=dbias, apply=False)        # column sums over the windows
+    return dqkv, dbias[:row].view(heads, N, N)
+
+
 SE_BWD_BATCHED = False   # SqueezeExcite backward through es3_se_bwd_* instead of per-image loops (no GPU parity run yet: off)
 
 

@@ -55,10 +55,10 @@ class ImageStudentEncoder(nn.Module, NativePlanMixin):
 
     def _forward_train(self, x):
         """Train-mode forward recorded as ONE autograd node (StudentTrainFunction): batch-statistics BatchNorm (or frozen
-        BN modules, set_bn_state), backward on the kernels of train_bwd.cu.  Built for the EfficientViT b0 / b1 / b2 and RepViT m0_9 / m1_1 / m2_3 students."""
-        if not isinstance(self.backbone, (EfficientViTAdapter, RepViTAdapter)):
+        BN modules, set_bn_state), backward on the kernels of train_bwd.cu.  Built for all nine students (EfficientViT b0 / b1 / b2, RepViT m0_9 / m1_1 / m2_3, TinyViT 5m / 11m / 21m)."""
+        if not isinstance(self.backbone, (EfficientViTAdapter, RepViTAdapter, TinyViTAdapter)):
             raise NotImplementedError(
-                "train-mode forward/backward is built for the EfficientViT (efficientvit_b0 / b1 / b2) and RepViT (repvit_m0_9 / m1_1 / m2_3) "
+                "train-mode forward/backward is built for the EfficientViT, RepViT and TinyViT "
                 f"students; {type(self.backbone).__name__} is eval-only (see DESIGN.md).  Call .eval() first.")
         params = [p for p in self.parameters()]
         return StudentTrainFunction.apply(self, x, *params)
@@ -87,13 +87,18 @@ class StudentTrainFunction(torch.autograd.Function):
     def forward(ctx, module, x, *params):
         from ..backbones.efficientvit_train import EfficientViTTrainGraph, HeadTrainUnit
         from ..backbones.repvit_train import RepViTTrainGraph
+        from ..backbones.tinyvit_train import TinyViTTrainGraph
         if not (x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3):
             raise ValueError("expected an fp32 NCHW image batch [B,3,H,W]")
         for m in module.modules():          # packed eval-mode weights go stale once parameters / running stats move
             if isinstance(m, NativePlanMixin):
                 m._plan_key = None
-        body = (RepViTTrainGraph(module.backbone.model) if isinstance(module.backbone, RepViTAdapter)
-                else EfficientViTTrainGraph(module.backbone.model))
+        if isinstance(module.backbone, RepViTAdapter):
+            body = RepViTTrainGraph(module.backbone.model)
+        elif isinstance(module.backbone, TinyViTAdapter):
+            body = TinyViTTrainGraph(module.backbone.model)
+        else:
+            body = EfficientViTTrainGraph(module.backbone.model)
         head = HeadTrainUnit(module.head, module.embed_size)
         out = head.forward(body.forward(x))
         ctx.graph = (body, head)

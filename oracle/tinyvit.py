@@ -3,7 +3,8 @@ Restates sam3/sam3/backbones/tiny_vit.py: Conv2d_BN :29-53, PatchEmbed :67-84, M
 ConvLayer :157-193, Mlp :196-216, Attention :219-293 (learned relative bias table indexed by |dy|,|dx|),
 TinyViTBlock :296-386 (zero padding to a window multiple BEFORE the attention LayerNorm, so padded tokens enter the
 softmax as LN(0) = beta), BasicLayer :393-454, TinyViT :460-607, tiny_vit_11m_224 :669-679;
-TinyViTAdapter stage1/model.py:299-324.  Eval mode (DropPath = identity)."""
+TinyViTAdapter stage1/model.py:299-324.  DropPath = identity (eval mode, or training with drop_path_rate 0: the
+stochastic-depth draws are not part of the oracle)."""
 from __future__ import annotations
 
 import itertools
@@ -20,9 +21,9 @@ VARIANTS = {  # tiny_vit.py:656-692
 
 
 def conv_bn(sd, p, x, stride=1, pad=0, groups=1):
+    from .efficientvit import _bn      # eval-mode BN by default, batch statistics inside efficientvit.bn_batch_stats()
     x = F.conv2d(x, sd[p + ".c.weight"], None, stride=stride, padding=pad, groups=groups)
-    return F.batch_norm(x, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"], sd[p + ".bn.weight"], sd[p + ".bn.bias"],
-                        training=False, eps=1e-5)
+    return _bn(x, sd, p + ".bn")
 
 
 def mbconv(sd, p, x):

@@ -179,6 +179,52 @@ def conv3x3_s2_narrow(x, w9, scale, bias, act=None):
     return _nhwc(_act(v, act)).to(BF)
 
 
+def layernorm_bf16(x, gamma, beta, eps=1e-5):
+    return F.layer_norm(x.to(CD), (x.shape[-1],), gamma.to(CD), beta.to(CD), eps).to(BF)
+
+
+def layernorm_bwd(x, dy, gamma, eps, dgamma=None, dbeta=None, dres=None):
+    C = x.shape[-1]
+    xf = x.to(CD).requires_grad_(True)
+    g = gamma.to(CD).clone().requires_grad_(True)
+    b = torch.zeros(C, dtype=CD, requires_grad=True)
+    with torch.enable_grad():
+        y = F.layer_norm(xf, (C,), g, b, eps)
+        gx, gg, gb = torch.autograd.grad(y, (xf, g, b), dy.to(CD))
+    if dgamma is not None:
+        dgamma += gg
+    if dbeta is not None:
+        dbeta += gb
+    if dres is not None:
+        gx = gx + dres.to(CD)
+    return gx.to(BF)
+
+
+def _win_attn(qkv, bias, B, H, W, C, heads, ws, scale):
+    """qkv [B*H*W, 3C] (head h at columns [96h, 96h+96) = q|k|v), H, W multiples of ws -> out [B*H*W, C]."""
+    nH, nW, N = H // ws, W // ws, ws * ws
+    t = qkv.reshape(B, nH, ws, nW, ws, heads, 3, 32).permute(0, 1, 3, 5, 6, 2, 4, 7).reshape(B, nH, nW, heads, 3, N, 32)
+    q, k, v = t[:, :, :, :, 0], t[:, :, :, :, 1], t[:, :, :, :, 2]
+    a = (q @ k.transpose(-1, -2)) * scale + bias
+    o = a.softmax(-1) @ v                                                   # [B,nH,nW,heads,N,32]
+    o = o.reshape(B, nH, nW, heads, ws, ws, 32).permute(0, 1, 4, 2, 5, 3, 6)   # B,nH,ws,nW,ws,heads,32
+    return o.reshape(B * H * W, C)
+
+
+def win_attn_bias(qkv, qkv_pad, bias, B, H, W, C, heads, ws, scale):
+    assert H % ws == 0 and W % ws == 0, "the emulation covers window-multiple maps (the training graph pads the map itself)"
+    return _win_attn(qkv.to(CD), bias.to(CD), B, H, W, C, heads, ws, scale).to(BF)
+
+
+def win_attn_bias_bwd(qkv, dout, bias, B, H, W, C, heads, ws, scale):
+    q = qkv.to(CD).requires_grad_(True)
+    b = bias.to(CD).clone().requires_grad_(True)
+    with torch.enable_grad():
+        o = _win_attn(q, b, B, H, W, C, heads, ws, scale)
+        gq, gb = torch.autograd.grad(o, (q, b), dout.to(CD))
+    return gq.to(BF), gb.float()
+
+
 # ------------------------------------------------------------------------------------------ train_bwd.cu ops
 def bn_stats(z, gamma, beta, eps, momentum, running_mean=None, running_var=None, num_batches_tracked=None):
     C = z.shape[-1]
@@ -350,7 +396,7 @@ def litemla_attn_bwd(ms, datt, kv, heads2, eps=1e-15):
     return g.reshape(ms.shape).to(BF)
 
 
-PATCHED = ["gemm", "gemm_simt", "channel_mean", "scale_channels", "conv3x3_s2_narrow", "conv3x3", "stem_conv3x3_s2", "dwconv", "litemla_dwpw_weights", "litemla_aggreg_dwpw", "litemla_attn", "litemla_attn_generic", "litemla_attn_bwd_generic",
+PATCHED = ["layernorm_bf16", "layernorm_bwd", "win_attn_bias", "win_attn_bias_bwd", "gemm", "gemm_simt", "channel_mean", "scale_channels", "conv3x3_s2_narrow", "conv3x3", "stem_conv3x3_s2", "dwconv", "litemla_dwpw_weights", "litemla_aggreg_dwpw", "litemla_attn", "litemla_attn_generic", "litemla_attn_bwd_generic",
            "bilinear_nhwc_to_nchw", "nhwc_to_nchw_f32", "nchw_f32_to_nhwc", "bn_stats", "affine_act", "bn_act_bwd", "add_bf16",
            "wgrad_pw", "se_bwd_dgate", "se_bwd_apply", "transpose_pad", "accumulate_strided", "dwconv_bwd_data", "dwconv_wgrad", "stem_wgrad", "bilinear_bwd", "litemla_attn_bwd"]
 

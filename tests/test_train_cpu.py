@@ -135,12 +135,14 @@ def test_eval_plan_is_rebuilt_after_a_train_forward(monkeypatch):
     assert m._plan_key is None and m.backbone.model._plan_key is None
 
 
-def test_train_mode_is_refused_where_it_is_not_built():
+def test_train_mode_has_no_cpu_fallback():
+    """All nine students have a training graph now; without the device ops (CPU tensors) train mode raises like eval mode does."""
+    from efficientsam3_b200 import _lib
     from efficientsam3_b200.stage1.model import build_image_student_model
-    for name in ("tiny_vit_11m",):      # TinyViT: no training graph yet
+    for name in ("efficientvit_b1", "repvit_m1_1", "tiny_vit_11m"):
         cfg = NS(MODEL=NS(BACKBONE=name), DATA=NS(IMG_SIZE=160), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=12))
         m = build_image_student_model(cfg).train()
-        with pytest.raises(NotImplementedError):
+        with pytest.raises(_lib.Es3Error):
             m(torch.randn(1, 3, 160, 160))
 
 
@@ -386,3 +388,87 @@ def test_other_sizes_exact(monkeypatch, name, variant, img, embed):
         num += (p.grad.double() - g).pow(2).sum().item()
         den += g.pow(2).sum().item()
     assert (num / den) ** 0.5 < 1e-5, (num / den) ** 0.5
+
+
+# ------------------------------------------------------------------------------------------------- TinyViT
+def _round_like_product_tinyvit(sd):
+    """bf16 in the product: every 1x1 Conv2d_BN weight, the second patch-embed conv, every nn.Linear weight, the head convs."""
+    out = {}
+    for k, v in sd.items():
+        conv = (v.dim() == 4 and v.shape[1] > 1 and (k.endswith(".c.weight") or k in ("head.0.weight", "head.3.weight"))
+                and not k.endswith("patch_embed.seq.0.c.weight"))
+        lin = v.dim() == 2 and k.endswith(".weight") and (".qkv." in k or ".proj." in k or ".fc1." in k or ".fc2." in k)
+        out[k] = v.to(torch.bfloat16).float() if (conv or lin) else v.clone()
+    return out
+
+
+@pytest.mark.parametrize("name,bn_train", [("tiny_vit_5m", True), ("tiny_vit_11m", False), ("tiny_vit_21m", True)])
+def test_tinyvit_train_graph_exact(monkeypatch, name, bn_train):
+    """TinyViT training graph (MBConv with the post-add GELU, PatchMerging, window attention with relative bias on maps padded to a
+    window multiple -- 20 -> 21, 10 -> 14, 5 -> 7 at 160 px --, LayerNorm, GELU MLPs; DropPath rates set to 0) in fp64 emulation
+    vs autograd of the oracle."""
+    from efficientsam3_b200 import ops
+    from oracle import tinyvit as TV
+    emu_ops.install(monkeypatch)
+    monkeypatch.setattr(emu_ops, "BF", torch.float64)
+    monkeypatch.setattr(emu_ops, "CD", torch.float64)
+    monkeypatch.setattr(ops, "ACT_DTYPE", torch.float64)
+    img, embed, B = 160, 12, 2
+    m = _student(name, img=img, embed=embed, seed=17)
+    for mod in m.modules():
+        if hasattr(mod, "drop_path_rate"):
+            mod.drop_path_rate = 0.0
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(B, 3, img, img, generator=torch.Generator().manual_seed(1))
+    teacher = torch.randn(B, 1024, embed, embed, generator=torch.Generator().manual_seed(2)).double()
+    sizes = [(3, img, img)] * B
+    m.train()
+    if not bn_train:
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                mod.eval()
+    out = m(x)
+    loss, _, _ = oracle_kd_loss(out, teacher, img, sizes, 1.0)
+    loss.backward()
+    sd = {k: ((v.double().requires_grad_(True) if "running" not in k else v.double()) if v.is_floating_point() else v.clone())
+          for k, v in _round_like_product_tinyvit(sd0).items()}
+    if bn_train:
+        with O.bn_batch_stats():
+            ref_out = TV.image_student_encoder(sd, x.double(), embed, name)
+    else:
+        ref_out = TV.image_student_encoder(sd, x.double(), embed, name)
+    rl, _, _ = oracle_kd_loss(ref_out, teacher, img, sizes, 1.0)
+    rl.backward()
+    assert _rel(out.detach(), ref_out.detach()) < 1e-5, _rel(out.detach(), ref_out.detach())
+    gscale = max(v.grad.norm().item() for v in sd.values() if v.is_floating_point() and v.grad is not None)
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape, k
+        g = sd[k].grad.double()
+        err = (p.grad.double() - g).norm().item()
+        assert err / max(g.norm().item(), 1e-3 * gscale) < 2e-4, (k, err / max(g.norm().item(), 1e-3 * gscale))
+        num += err ** 2
+        den += g.pow(2).sum().item()
+    print(f"{name} bn_train={bn_train}: out {_rel(out.detach(), ref_out.detach()):.2e}, all grads {(num / den) ** 0.5:.2e}")
+    assert (num / den) ** 0.5 < 2e-5
+
+
+def test_drop_path_gate(monkeypatch):
+    """timm DropPath in the TinyViT training graph: one Bernoulli(keep) draw per sample scaled by 1 / keep, the same gate in the backward,
+    identity for rate 0 -- and the 11m builder keeps the reference's per-block rates (linspace(0, 0.1, 12))."""
+    from efficientsam3_b200.backbones.tinyvit_train import DropPath
+    from efficientsam3_b200.backbones.tiny_vit import tiny_vit_11m_224
+    emu_ops.install(monkeypatch)
+    torch.manual_seed(0)
+    x = torch.randn(64, 3, 5, 16).to(torch.bfloat16)
+    dp = DropPath(0.25)
+    y = dp.forward(x)
+    g = dp.gate[:, 0]
+    assert all(v == 0.0 or abs(v - 1.0 / 0.75) < 1e-6 for v in g.tolist()) and 0 < (g == 0).sum().item() < 64
+    assert torch.equal(y, (x.float() * g.view(-1, 1, 1, 1)).to(torch.bfloat16))
+    d = torch.randn_like(x)
+    assert torch.equal(dp.backward(d), (d.float() * g.view(-1, 1, 1, 1)).to(torch.bfloat16))
+    assert DropPath(0.0).forward(x) is x
+    m = tiny_vit_11m_224(img_size=224, num_classes=0)
+    rates = [blk.drop_path_rate for layer in m.layers for blk in layer.blocks]
+    assert len(rates) == 12 and rates[0] == 0.0 and abs(rates[-1] - 0.1) < 1e-7 and all(a <= b for a, b in zip(rates, rates[1:]))

@@ -530,11 +530,85 @@ def test_efficientvit_b2_training_step_matches_oracle_autograd(cuda):
     assert (num / den) ** 0.5 < 5e-2
 
 
+@_isolated
+@pytest.mark.xfail(strict=False, reason="es3_layernorm_bwd / es3_win_attn_bias_bwd (tinyvit_bwd.cu) were written after the round-1 GPU budget was spent: "
+                                        "first GPU run pending")
+@pytest.mark.parametrize("M,C", [(1000, 64), (777, 448), (4100, 160), (300, 576)])
+def test_layernorm_bwd(cuda, M, C):
+    from efficientsam3_b200 import ops
+    g = _g(M + C)
+    x, dy = _bf(torch.randn(M, C, generator=g) * 2 + 0.5), _bf(torch.randn(M, C, generator=g))
+    dres = _bf(torch.randn(M, C, generator=g))
+    gamma = torch.rand(C, generator=g) + 0.5
+    dg_ref, db_ref = torch.full((C,), 0.5), torch.full((C,), -1.0)
+    ref = E.layernorm_bwd(x, dy, gamma, 1e-5, dg_ref, db_ref, dres)
+    dg, db = torch.full((C,), 0.5, device=cuda), torch.full((C,), -1.0, device=cuda)
+    got = ops.layernorm_bwd(x.to(cuda), dy.to(cuda), gamma.to(cuda), 1e-5, dg, db, dres.to(cuda))
+    _close(got, ref, 1e-2, "layernorm_bwd dx")
+    _close(dg, dg_ref, 2e-3, "layernorm_bwd dgamma")
+    _close(db, db_ref, 2e-3, "layernorm_bwd dbeta")
+
+
+@_isolated
+@pytest.mark.xfail(strict=False, reason="es3_win_attn_bias_bwd: first GPU run pending")
+@pytest.mark.parametrize("B,H,W,heads,ws", [(2, 14, 21, 4, 7), (1, 14, 28, 8, 14), (2, 7, 7, 5, 7)])
+def test_win_attn_bias_bwd(cuda, B, H, W, heads, ws):
+    from efficientsam3_b200 import ops
+    g = _g(B + H + heads + ws)
+    C, N = 32 * heads, ws * ws
+    qkv = _bf(torch.randn(B * H * W, 3 * C, generator=g))
+    dout = _bf(torch.randn(B * H * W, C, generator=g))
+    bias = torch.randn(heads, N, N, generator=g) * 0.5
+    scale = 32 ** -0.5
+    fwd = ops.win_attn_bias(qkv.to(cuda), torch.zeros(3 * C, dtype=torch.bfloat16, device=cuda), bias.to(cuda), B, H, W, C, heads, ws, scale)
+    _close(fwd, E.win_attn_bias(qkv, None, bias, B, H, W, C, heads, ws, scale), 1e-2, "win_attn_bias fwd")
+    dq, db = ops.win_attn_bias_bwd(qkv.to(cuda), dout.to(cuda), bias.to(cuda), B, H, W, C, heads, ws, scale)
+    rq, rb = E.win_attn_bias_bwd(qkv, dout, bias, B, H, W, C, heads, ws, scale)
+    _close(dq, rq, 1.5e-2, "win_attn_bias_bwd dqkv")
+    _close(db, rb, 1e-2, "win_attn_bias_bwd dbias")      # per-window dS is stored in bf16 before the sum over windows
+
+
+@_isolated
+@pytest.mark.xfail(strict=False, reason="TinyViT training graph: exact on CPU, first GPU run pending (two new kernels)")
+def test_tinyvit_training_step_matches_oracle_autograd(cuda):
+    from efficientsam3_b200.stage1.optim import KDLossFunction
+    from oracle import tinyvit as TV
+    from oracle.kd_loss import kd_loss
+    img, embed, B = 224, 14, 2
+    m = _student("tiny_vit_11m", img, embed, seed=17)
+    for mod in m.modules():
+        if hasattr(mod, "drop_path_rate"):
+            mod.drop_path_rate = 0.0
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(B, 3, img, img, generator=_g(1))
+    teacher = torch.randn(B, 1024, embed, embed, generator=_g(2))
+    sizes = [(3, img, img)] * B
+    m = m.to(cuda).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+            mod.eval()
+    out = m(x.to(cuda))
+    sz = torch.tensor([[img, img]] * B, dtype=torch.int32, device=cuda)
+    loss = KDLossFunction.apply(out, teacher.to(cuda), sz, img, 1.0)
+    loss.backward()
+    torch.cuda.synchronize()
+    sd = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v.clone()) for k, v in sd0.items()}
+    ref_loss, _, _ = kd_loss(TV.image_student_encoder(sd, x, embed, "tiny_vit_11m"), teacher, img, sizes, 1.0)
+    ref_loss.backward()
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        gq = sd[k].grad.double()
+        num += (p.grad.cpu().double() - gq).pow(2).sum().item()
+        den += gq.pow(2).sum().item()
+    print(f"tiny_vit_11m (frozen BN, no DropPath): all-gradient rel-L2 {(num / den) ** 0.5:.3e}")
+    assert (num / den) ** 0.5 < 8e-2
+
+
 @pytest.mark.xfail(strict=False, reason="never-run code: kernels es3_dwconv_wgrad_tiled / es3_se_bwd_* / es3_litemla_attn_bwd_generic, the efficientvit_b2 and "
                                         "RepViT training steps, the EfficientSAM3 student segmenter -- executed in a separate process; first GPU run pending")
 def test_never_run_kernels_isolated(cuda):
     env = dict(os.environ, ES3_ISOLATED="1")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-p", "no:cacheprovider", "-s", "-k",
-                        "tiled or batched or generic or b2 or repvit or segmenter"], env=env, capture_output=True, text=True, timeout=900)
+                        "tiled or batched or generic or b2 or repvit or segmenter or layernorm_bwd or win_attn_bias_bwd or tinyvit"], env=env, capture_output=True, text=True, timeout=900)
     print(r.stdout[-3000:])
     assert r.returncode == 0 and "xfailed" not in r.stdout.splitlines()[-1], r.stdout[-500:] + r.stderr[-500:]
