@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(256) dw_wgrad_tiled_kernel(const bf16* __restr
 // ------------------------------------------------------------------------------------------ SqueezeExcite backward (batched)
 // Per-image column reductions / per-image affine of the SqueezeExcite backward in ONE launch each (the training graph's first
 // version loops over the batch with es3_bn_act_bwd_reduce / es3_affine_act: ~100 launches per SE block at batch 32).
-// NOT on the default path yet (no GPU parity run; ops.SE_BWD_BATCHED).
+// Default path since round 2 (ops.SE_BWD_BATCHED; GPU parity in tests/test_zz_train_gpu.py::test_se_bwd_batched).
 //   se_dgate:  part[chunk][b][c] = sum over the chunk's pixels of dy[b][p][c] * x[b][p][c]          grid (nchunk, B), block 256
 //   se_apply:  dx[b][p][c] = dy[b][p][c] * gate[b][c] + add[b][c]                                    one thread per 8-channel vector
 __global__ void __launch_bounds__(256) se_dgate_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, int HW, int C, int CVB,

@@ -876,7 +876,7 @@ def dwconv_bwd_data(dz, w, H, W, ks, stride):
     return dx
 
 
-DW_WGRAD_TILED = False   # route stride-1, C % 32 == 0 weight gradients to es3_dwconv_wgrad_tiled (no GPU parity run yet: off)
+DW_WGRAD_TILED = True    # route stride-1, C % 32 == 0 weight gradients to es3_dwconv_wgrad_tiled (GPU parity: test_dwconv_wgrad_tiled, r2)
 
 
 def dwconv_wgrad(dz, x, dW, ks, stride, impl=None):
@@ -952,7 +952,7 @@ def win_attn_bias_bwd(qkv, dout, bias, B, H, W, C, heads, ws, scale):
     return dqkv, dbias[:row].view(heads, N, N)
 
 
-SE_BWD_BATCHED = False   # SqueezeExcite backward through es3_se_bwd_* instead of per-image loops (no GPU parity run yet: off)
+SE_BWD_BATCHED = True    # SqueezeExcite backward through es3_se_bwd_* instead of per-image loops (GPU parity: test_se_bwd_batched, r2)
 
 
 def se_bwd_dgate(dy, x):

@@ -115,7 +115,9 @@ class EmbeddingStoreReader:
         stem = self._stems[self._loaded]
         with open(stem + "-keys.txt") as f:
             for i, line in enumerate(f):
-                self._index.setdefault(line.strip(), (self._loaded, i))
+                # plain assignment, as the reference's _Reader does (manager.py:92-99): a key that the sampler's padding put into
+                # several ranks' packages resolves to the LAST package loaded so far, and to the last line inside a package
+                self._index[line.strip()] = (self._loaded, i)
         self._loaded += 1
 
     def read(self, key: str) -> bytes:
@@ -192,6 +194,11 @@ class EmbeddingDumper:
         slot.free.wait()           # the host thread has finished writing this slot's previous contents
         slot.free.clear()
         n = B * per
+        if n > slot.dev.numel():   # a batch larger than the one the slots were sized from: grow this slot (it is idle here)
+            torch.cuda.current_stream().synchronize()
+            grown = _Slot(n, slot.dev.device)
+            grown.free.clear()
+            self._slots[(self._next - 1) % len(self._slots)] = slot = grown
         ops.cast_f32_to_f16(outputs.contiguous(), out=slot.dev[:n])
         ready = torch.cuda.Event()
         ready.record()
@@ -225,7 +232,7 @@ def save_embeddings_one_epoch(model, data_loader, path: str, rank: int = 0, max_
                 x = x.to(dev, non_blocking=True)
                 out = model(x)
                 if dumper is None:
-                    cap = (max_batch or x.shape[0]) * out[0].numel()
+                    cap = (max_batch or getattr(data_loader, "batch_size", None) or x.shape[0]) * out[0].numel()
                     dumper = EmbeddingDumper(writer, dev, max(cap, out.numel()))
                 dumper.submit(out, keys, np.asarray(seeds).astype(np.int32))
                 n += x.shape[0]

@@ -59,11 +59,13 @@ def kd_train_step(student, optimizer, images, teacher_embeddings, img_size_befor
 
 
 def kd_train_step_online(student, teacher_model, optimizer, images, img_size_before_pad, cosine_weight: float = 1.0,
-                         clip_grad: float = 5.0, lr: float | None = None, group=None, teacher_chunk: int = 8):
+                         clip_grad: float = 5.0, lr: float | None = None, group=None, teacher_chunk: int = 8,
+                         accumulation_steps: int = 1, update: bool = True):
     """The north-star wording of the stage-1 iteration: the frozen SAM3 teacher embeds the batch on the
     fly (no embedding store), the student is trained against it.  Targets are rounded through fp16 exactly as the stored
     embeddings are (save_embedding_image_stage1.py:89-92).  The teacher runs in chunks to bound its activation memory."""
     with torch.no_grad():
         t = torch.cat([teacher_model(images[i:i + teacher_chunk]) for i in range(0, images.shape[0], teacher_chunk)], 0)
         t = t.half().float()
-    return kd_train_step(student, optimizer, images, t, img_size_before_pad, cosine_weight, clip_grad, lr, group)
+    return kd_train_step(student, optimizer, images, t, img_size_before_pad, cosine_weight, clip_grad, lr, group,
+                         accumulation_steps=accumulation_steps, update=update)

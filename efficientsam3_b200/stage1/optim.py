@@ -61,7 +61,11 @@ class FlatAdamW:
         skip_kw = model.no_weight_decay_keywords() if hasattr(model, "no_weight_decay_keywords") else ()
         decay, no_decay = split_decay(model.named_parameters(), skip, skip_kw)
         self._model = model
+        self._plan_holders = None
         self.lr, self.betas, self.eps, self.weight_decay = lr, tuple(betas), eps, weight_decay
+        # the configured LR the schedule is built from (timm keeps it as param_group['initial_lr']); `self.lr` is the value of the
+        # current update and moves with the schedule, `base_lr` never does
+        self.base_lr = lr
         self.dynamic, self.growth_interval = dynamic_loss_scale, growth_interval
         self.names, self.params, self.offsets = [], [], []
         off = 0
@@ -112,9 +116,12 @@ class FlatAdamW:
             raise RuntimeError("FlatAdamW.step runs es3_adamw_flat on the GPU; there is no CPU fallback")
         if lr is not None:
             self.lr = lr
-        for mod in self._model.modules():      # the kernel moves the parameters through raw pointers: cached eval-mode packings are stale
-            if hasattr(mod, "_plan_key"):
-                mod._plan_key = None
+        # the kernel moves the parameters through raw pointers: cached eval-mode packings are stale.  The holders are collected
+        # once (a per-step walk over every module cost 0.2 ms of host time per update)
+        if self._plan_holders is None:
+            self._plan_holders = [mod for mod in self._model.modules() if hasattr(mod, "_plan_key")]
+        for mod in self._plan_holders:
+            mod._plan_key = None
         ops.grad_norm(self.flat_grad, self._part_ws, self._norm_ws)
         ops.adamw_flat(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.n_decay, self.lr, self.betas,
                        self.eps, self.weight_decay, max_norm, 1.0 / world_size, self._norm_ws, self.state,
@@ -135,7 +142,7 @@ class FlatAdamW:
             state[i] = dict(step=torch.tensor(step), exp_avg=self.exp_avg[sl].view_as(p).clone(),
                             exp_avg_sq=self.exp_avg_sq[sl].view_as(p).clone())
         n_dec = sum(1 for o in self.offsets if o < self.n_decay)
-        common = dict(lr=self.lr, betas=self.betas, eps=self.eps, amsgrad=False, maximize=False)
+        common = dict(lr=self.lr, initial_lr=self.base_lr, betas=self.betas, eps=self.eps, amsgrad=False, maximize=False)
         groups = [dict(common, weight_decay=self.weight_decay, params=list(range(n_dec))),
                   dict(common, weight_decay=0.0, params=list(range(n_dec, len(self.params))))]
         return dict(state=state, param_groups=groups,
@@ -151,7 +158,12 @@ class FlatAdamW:
             self.exp_avg_sq[sl].copy_(st["exp_avg_sq"].reshape(-1))
             self.state[2] = float(st["step"])
         if sd.get("param_groups"):
-            self.lr = sd["param_groups"][0]["lr"]
+            g0 = sd["param_groups"][0]
+            self.lr = g0["lr"]
+            # timm schedulers write `initial_lr` into every group; a checkpoint without it (plain torch AdamW that never met a
+            # scheduler) leaves the configured base LR of this object untouched rather than adopting a mid-schedule value
+            if "initial_lr" in g0:
+                self.base_lr = g0["initial_lr"]
         sc = sd.get("amp_scaler")
         if sc:
             self.state[0] = float(sc["scale"])

@@ -35,10 +35,21 @@ def train_one_epoch(config, model, data_loader, optimizer, epoch, lr_at=None, on
         n_iter = num_steps // accum                  # build_scheduler(config, optimizer, len(loader) // ACCUMULATION_STEPS), :80-84
         total = int(config.TRAIN.EPOCHS * n_iter)
         warm = int(config.TRAIN.WARMUP_EPOCHS * n_iter)
-        base = optimizer.lr
+        base = getattr(optimizer, "base_lr", optimizer.lr)     # never optimizer.lr: step(lr=...) overwrites it every update
 
         def lr_at(t):
             return cosine_lr(t, base, total, config.TRAIN.MIN_LR, warm, config.TRAIN.WARMUP_LR)
+
+    # The reference applies update u with the LR the PREVIOUS `step_update` call left in the optimiser (the scheduler is stepped
+    # after optimizer.step(), :216-229); the very first update runs at the scheduler's initial value, which is lr_at(0).
+    def lr_for_update(idx):
+        prev = idx - accum                               # iteration index of the previous update inside this epoch
+        if prev >= 0:
+            return lr_at((epoch * num_steps + prev) // accum)
+        last = (num_steps // accum) * accum - 1          # last updating iteration of the previous epoch
+        if epoch > 0 and last >= 0:
+            return lr_at(((epoch - 1) * num_steps + last) // accum)
+        return lr_at(0)
 
     cosine_w = float(config.DISTILL.COSINE)
     dev = next(model.parameters()).device
@@ -49,7 +60,7 @@ def train_one_epoch(config, model, data_loader, optimizer, epoch, lr_at=None, on
         saved = saved.view(samples.size(0), *embed_shape).to(dev, non_blocking=True)
         update = (idx + 1) % accum == 0
         loss = kd_train_step(model, optimizer, samples, saved, annos["img_size_before_pad"], cosine_weight=cosine_w,
-                             clip_grad=config.TRAIN.CLIP_GRAD, lr=lr_at((epoch * num_steps + idx) // accum),
+                             clip_grad=config.TRAIN.CLIP_GRAD, lr=lr_for_update(idx) if update else None,
                              accumulation_steps=accum, update=update)
         losses.append(loss)
         if on_step is not None:

@@ -73,11 +73,17 @@ def test_evm_full_size_properties(cuda):
     assert torch.equal(solo[0], out[1]), "embedding depends on batch neighbours"
 
 
-def test_train_mode_is_refused(cuda):
+def test_train_mode_returns_autograd_tensor(cuda):
+    """`.train()` runs the native training graph (stage1/model.py:188-211 in train mode): the output carries a
+    grad_fn, and backward fills every parameter gradient."""
     g = load_golden("evm_160")
     m = _build(160, 12, sd_from_keys(g["keys"], 1), cuda).train()
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 3, 160, 160, device=cuda))
+    out = m(torch.randn(2, 3, 160, 160, device=cuda))
+    assert out.shape == (2, 1024, 12, 12) and out.grad_fn is not None
+    out.float().square().mean().backward()
+    missing = [n for n, p in m.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing[:5]
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
 
 
 def _build_rv(img, embed, sd, dev):

@@ -304,6 +304,8 @@ def test_train_one_epoch_follows_the_reference_loop(monkeypatch):
     calls = []
 
     def fake_step(self, lr=None, max_norm=5.0, world_size=1):
+        if lr is not None:
+            self.lr = lr                       # the real step() bookkeeping: the schedule must not be built from this value
         calls.append((lr, max_norm, world_size, float(self.flat_grad.norm())))
         self.flat_param -= 1e-6 * self.flat_grad
 
@@ -316,12 +318,21 @@ def test_train_one_epoch_follows_the_reference_loop(monkeypatch):
     g = torch.Generator().manual_seed(3)
     loader = [(([torch.randn(3, img, img, generator=g) for _ in range(B)], {"img_size_before_pad": [(3, img, img)] * B}),
                ([np.random.RandomState(i).randn(1024 * embed * embed).astype(np.float16) for _ in range(B)], [i] * B)) for i in range(iters)]
-    losses = train_one_epoch(cfg, m, loader, opt, epoch=1)
-    assert len(losses) == iters and all(torch.isfinite(v) for v in losses)
-    assert len(calls) == iters // accum                                  # one update per ACCUMULATION_STEPS iterations
+    losses = train_one_epoch(cfg, m, loader, opt, epoch=0) + train_one_epoch(cfg, m, loader, opt, epoch=1)
+    assert len(losses) == 2 * iters and all(torch.isfinite(v) for v in losses)
+    assert len(calls) == 2 * iters // accum                              # one update per ACCUMULATION_STEPS iterations
     n_iter = iters // accum
-    expect = [OPT.cosine_lr((1 * iters + idx) // accum, 1e-3, 3 * n_iter, 1e-6, 1 * n_iter, 1e-7) for idx in (1, 3)]
+    # the reference's order (train_image_encoder_stage1.py:216-229): optimizer.step() with the LR currently in the optimiser, THEN
+    # lr_scheduler.step_update(arg); the scheduler's constructor leaves lr_at(0) (= WARMUP_LR when there is a warm-up) behind
+    sched = lambda t: OPT.cosine_lr(t, 1e-3, 3 * n_iter, 1e-6, 1 * n_iter, 1e-7)
+    cur, expect = sched(0), []
+    for epoch in (0, 1):
+        for idx in range(iters):
+            if (idx + 1) % accum == 0:
+                expect.append(cur)
+                cur = sched((epoch * iters + idx) // accum)
     assert [c[0] for c in calls] == expect and all(c[1] == 5.0 and c[2] == 1 for c in calls)
+    assert opt.base_lr == 1e-3 and opt.lr == expect[-1]
     assert opt.flat_grad.abs().sum().item() == 0                         # cleared right after the last update
     assert all(not mod.training for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d)) and m.training
     assert all(c[3] > 0 for c in calls)

@@ -23,11 +23,6 @@ import emu_ops as E
 pytestmark = pytest.mark.gpu
 
 
-# Kernels that have never run on a GPU execute in their OWN process (test_never_run_kernels_isolated below): a fault in one of
-# them cannot poison the CUDA context the verified tests share.
-_isolated = pytest.mark.skipif(os.environ.get("ES3_ISOLATED") != "1", reason="runs inside test_never_run_kernels_isolated's subprocess")
-
-
 def _bf(t):
     return t.to(torch.bfloat16)
 
@@ -373,12 +368,8 @@ def test_half_width_image_batches(cuda):
 
 
 # ---------------------------------------------------------------------------------------------
-# Code that has not run on a GPU yet (written after the round-1 GPU budget was spent).  These stay the LAST tests of the last
-# file on purpose: a fault in a never-run kernel must not be able to disturb a verified test.
-@_isolated
-@pytest.mark.xfail(strict=False, reason="RepViT training graph = host composition of kernels that each have a GPU parity test, validated on "
-                                        "CPU in fp64 (tests/test_train_cpu.py); the whole step has not run on a GPU yet (round-1 GPU budget "
-                                        "was exhausted before it was written)")
+# Kernels and training graphs written at the end of round 1; first run (and passed) on a B200 in round 2
+# (gpurun_out/r2a_tests.log -> profiles/r2_gpu_tests.md).
 @pytest.mark.parametrize("bn_train", [False, True])
 def test_repvit_training_step_matches_oracle_autograd(cuda, bn_train):
     from efficientsam3_b200.stage1.optim import KDLossFunction
@@ -422,9 +413,6 @@ def test_repvit_training_step_matches_oracle_autograd(cuda, bn_train):
     assert rel_out < tol_out and rel_all < tol_all, (rel_out, rel_all)
 
 
-@_isolated
-@pytest.mark.xfail(strict=False, reason="es3_dwconv_wgrad_tiled was written after the round-1 GPU budget was spent: not on the default path, "
-                                        "first GPU run pending")
 @pytest.mark.parametrize("B,H,W,C,ks", [(2, 16, 16, 32, 3), (1, 9, 11, 96, 5), (2, 64, 64, 384, 5), (2, 40, 37, 512, 3), (1, 7, 5, 64, 5)])
 def test_dwconv_wgrad_tiled(cuda, B, H, W, C, ks):
     from efficientsam3_b200 import ops
@@ -438,8 +426,6 @@ def test_dwconv_wgrad_tiled(cuda, B, H, W, C, ks):
     _close(got, ref, 2e-3, "dwconv_wgrad tiled")
 
 
-@_isolated
-@pytest.mark.xfail(strict=False, reason="es3_se_bwd_* were written after the round-1 GPU budget was spent: not on the default path, first GPU run pending")
 @pytest.mark.parametrize("B,H,W,C", [(3, 16, 16, 64), (2, 9, 7, 128), (4, 32, 32, 256), (2, 5, 5, 2560)])
 def test_se_bwd_batched(cuda, B, H, W, C):
     from efficientsam3_b200 import ops
@@ -450,10 +436,6 @@ def test_se_bwd_batched(cuda, B, H, W, C):
     _close(ops.se_bwd_apply(dy.to(cuda), gate.to(cuda), add.to(cuda)), E.se_bwd_apply(dy, gate, add), 1e-2, "se_bwd_apply")
 
 
-@_isolated
-@pytest.mark.xfail(strict=False, reason="EfficientSAM3 student encoder + FPN + SAM heads: Python composition of modules that each have a GPU "
-                                        "parity test (student forward, FPN, heads); key-for-key equal to the reference builder and oracle-"
-                                        "checked on CPU; written after the round-1 GPU budget was spent, first GPU run pending")
 def test_efficientsam3_student_segmenter_vs_oracles(cuda):
     """build_efficientsam3_point_segmenter("efficientvit", "b1"): image -> EV-M student -> 1024 x 72 x 72 -> SAM2-branch FPN -> point-prompt
     mask decoding, against the oracle composition (efficientvit + student head + neck + SAM heads)."""
@@ -486,9 +468,6 @@ def test_efficientsam3_student_segmenter_vs_oracles(cuda):
     assert torch.equal(out["best"].cpu(), ref["best"])
 
 
-@_isolated
-@pytest.mark.xfail(strict=False, reason="es3_litemla_attn_bwd_generic (head dim 16 | 32, efficientvit_b2) was written after the round-1 GPU budget was "
-                                        "spent: the b2 training graph is exact on CPU, first GPU run pending")
 @pytest.mark.parametrize("B,H,W,heads2,dim", [(2, 10, 10, 8, 32), (1, 23, 29, 4, 32), (2, 12, 12, 6, 16)])
 def test_litemla_attn_bwd_generic(cuda, B, H, W, heads2, dim):
     from efficientsam3_b200 import ops
@@ -501,8 +480,6 @@ def test_litemla_attn_bwd_generic(cuda, B, H, W, heads2, dim):
     _close(got, E.litemla_attn_bwd_generic(ms, datt, None, heads2, dim, 1e-15), 1.5e-2, "litemla_attn_bwd_generic")
 
 
-@_isolated
-@pytest.mark.xfail(strict=False, reason="efficientvit_b2 training graph: exact on CPU, first GPU run pending (its attention backward kernel is new)")
 def test_efficientvit_b2_training_step_matches_oracle_autograd(cuda):
     from efficientsam3_b200.stage1.optim import KDLossFunction
     img, embed, B = 320, 20, 2
@@ -530,9 +507,6 @@ def test_efficientvit_b2_training_step_matches_oracle_autograd(cuda):
     assert (num / den) ** 0.5 < 5e-2
 
 
-@_isolated
-@pytest.mark.xfail(strict=False, reason="es3_layernorm_bwd / es3_win_attn_bias_bwd (tinyvit_bwd.cu) were written after the round-1 GPU budget was spent: "
-                                        "first GPU run pending")
 @pytest.mark.parametrize("M,C", [(1000, 64), (777, 448), (4100, 160), (300, 576)])
 def test_layernorm_bwd(cuda, M, C):
     from efficientsam3_b200 import ops
@@ -549,8 +523,6 @@ def test_layernorm_bwd(cuda, M, C):
     _close(db, db_ref, 2e-3, "layernorm_bwd dbeta")
 
 
-@_isolated
-@pytest.mark.xfail(strict=False, reason="es3_win_attn_bias_bwd: first GPU run pending")
 @pytest.mark.parametrize("B,H,W,heads,ws", [(2, 14, 21, 4, 7), (1, 14, 28, 8, 14), (2, 7, 7, 5, 7)])
 def test_win_attn_bias_bwd(cuda, B, H, W, heads, ws):
     from efficientsam3_b200 import ops
@@ -568,8 +540,6 @@ def test_win_attn_bias_bwd(cuda, B, H, W, heads, ws):
     _close(db, rb, 1e-2, "win_attn_bias_bwd dbias")      # per-window dS is stored in bf16 before the sum over windows
 
 
-@_isolated
-@pytest.mark.xfail(strict=False, reason="TinyViT training graph: exact on CPU, first GPU run pending (two new kernels)")
 def test_tinyvit_training_step_matches_oracle_autograd(cuda):
     from efficientsam3_b200.stage1.optim import KDLossFunction
     from oracle import tinyvit as TV
@@ -602,13 +572,3 @@ def test_tinyvit_training_step_matches_oracle_autograd(cuda):
         den += gq.pow(2).sum().item()
     print(f"tiny_vit_11m (frozen BN, no DropPath): all-gradient rel-L2 {(num / den) ** 0.5:.3e}")
     assert (num / den) ** 0.5 < 8e-2
-
-
-@pytest.mark.xfail(strict=False, reason="never-run code: kernels es3_dwconv_wgrad_tiled / es3_se_bwd_* / es3_litemla_attn_bwd_generic, the efficientvit_b2 and "
-                                        "RepViT training steps, the EfficientSAM3 student segmenter -- executed in a separate process; first GPU run pending")
-def test_never_run_kernels_isolated(cuda):
-    env = dict(os.environ, ES3_ISOLATED="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-p", "no:cacheprovider", "-s", "-k",
-                        "tiled or batched or generic or b2 or repvit or segmenter or layernorm_bwd or win_attn_bias_bwd or tinyvit"], env=env, capture_output=True, text=True, timeout=900)
-    print(r.stdout[-3000:])
-    assert r.returncode == 0 and "xfailed" not in r.stdout.splitlines()[-1], r.stdout[-500:] + r.stderr[-500:]
