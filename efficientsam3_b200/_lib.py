@@ -85,6 +85,7 @@ SIGNATURES: dict[str, list] = {
     "es3_se_bwd_apply": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "es3_layernorm_bwd": [_vp, _vp, _vp, _vp, _f, _vp, _ll, _i, _vp, _vp, _vp, _vp],
     "es3_win_attn_bias_bwd": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "es3_colsum_f32": [_vp, _ll, _ll, _i, _vp, _vp, _vp],
     "es3_stem_wgrad": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "es3_bilinear_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_litemla_attn_bwd_generic": [_vp, _ll, _vp, _ll, _vp, _i, _vp, _vp, _ll, _i, _i, _i, _i, _f, _vp],
@@ -99,6 +100,7 @@ SIZE_HELPERS: dict[str, list] = {
     "es3_dwconv_wgrad_tiled_ws_floats": [_i, _i, _i, _i, _i],
     "es3_se_bwd_ws_floats": [_i, _i, _i],
     "es3_layernorm_bwd_ws_floats": [_ll, _i],
+    "es3_colsum_f32_ws_floats": [_ll, _i],
     "es3_stem_wgrad_ws_floats": [_i, _i, _i, _i],
     "es3_litemla_bwd_ws_floats": [_i, _i, _i],
     "es3_litemla_bwd_generic_ws_floats": [_i, _i, _i, _i],

@@ -27,13 +27,25 @@ from .. import ops
 from ..nn_utils import dw_weight, pw_weight
 from .efficientvit import (ConvLayer, DSConv, EfficientViTBlock, LiteMLA, MBConv, ResidualBlock)
 
-__all__ = ["EfficientViTTrainGraph", "HeadTrainUnit"]
+__all__ = ["EfficientViTTrainGraph", "HeadTrainUnit", "GradSink"]
+
+
+class GradSink(dict):
+    """parameter -> fp32 gradient accumulator of one backward pass.  `direct`: accumulate straight into `p.grad` when that is an fp32
+    contiguous tensor -- with stage1.optim.FlatAdamW every `p.grad` is a view into the ONE flat gradient arena that is all-reduced, so
+    the backward kernels write the communication buffer itself (no per-parameter temporaries, no autograd accumulate pass, and a
+    finished range of the arena can be handed to NCCL while the rest of the backward is still running)."""
+    direct = False
 
 
 def _grad_of(grads: dict, p: torch.Tensor):
     """fp32 accumulator for parameter `p` (None when it does not require grad)."""
     if p is None or not p.requires_grad:
         return None
+    if getattr(grads, "direct", False):
+        g = p.grad
+        if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape:
+            return g
     g = grads.get(p)
     if g is None:
         g = torch.zeros(p.shape, device=p.device, dtype=torch.float32)

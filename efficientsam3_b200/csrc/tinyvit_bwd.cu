@@ -133,7 +133,8 @@ __global__ void layernorm_bwd_finalize_kernel(const float* __restrict__ part, in
 // One CTA per (window, head), 256 threads, N = ws^2 <= 196 tokens of head dim 32.  Forward: s_ij = scale q_i.k_j + bias[h][i][j],
 // P = softmax_j(s), o_i = sum_j P_ij v_j.  Backward with do_i: dP_ij = do_i.v_j, D_i = sum_j P_ij dP_ij, dS_ij = P_ij (dP_ij - D_i),
 // dq_i = scale sum_j dS_ij k_j, dk_j = scale sum_i dS_ij q_i, dv_j = sum_i P_ij do_i, dbias = sum over windows of dS.
-// Phase 1: thread i (row): row max, row sum, D_i, then dq_i and the dS row (written to global, bf16).  Phase 2: thread j (key):
+// Phase 1: thread i (row): row max, row sum, D_i, then dq_i and the dS row (written to global in fp32: the bias gradient is its
+// sum over thousands of windows, and rounding every term to bf16 first cost three digits of it).  Phase 2: thread j (key):
 // dk_j, dv_j with P_ij recomputed from the saved row statistics.  Tiles live in shared memory as fp32 [N][33].
 constexpr int WB_HD = 32, WB_LD = WB_HD + 1;
 
@@ -142,7 +143,7 @@ struct WinBwdArgs {
   const bf16* dout;   // [B*H*W, C]: head h at columns [32 h, +32)
   const float* bias;  // [heads][N][N]
   bf16* dqkv;         // like qkv
-  bf16* dS;           // [B * nWin][ldS], row = [heads][N][N] (ldS >= heads N N: the caller pads it to a multiple of 8)
+  float* dS;          // [B * nWin][ldS] fp32, row = [heads][N][N] (ldS >= heads N N); summed over the windows by es3_colsum_f32
   long long ldS;
   int H, W, C, ws, nWx, nWin, N;
   float scale;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(256) win_attn_bias_bwd_kernel(const WinBwdArgs
     float dq[WB_HD];
 #pragma unroll
     for (int c = 0; c < WB_HD; ++c) dq[c] = 0.f;
-    bf16* dS_row = a.dS + (long long)blockIdx.x * a.ldS + ((long long)head * N + i) * N;
+    float* dS_row = a.dS + (long long)blockIdx.x * a.ldS + ((long long)head * N + i) * N;
     for (int j = 0; j < N; ++j) {
       float s = 0.f, dp = 0.f;
 #pragma unroll
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(256) win_attn_bias_bwd_kernel(const WinBwdArgs
       }
       const float p = __expf(fmaf(s, a.scale, bi[j]) - mx) * inv_l;
       const float ds = p * (dp - D);
-      dS_row[j] = __float2bfloat16(ds);
+      dS_row[j] = ds;
 #pragma unroll
       for (int c = 0; c < WB_HD; ++c) dq[c] = fmaf(ds, s_k[j * WB_LD + c], dq[c]);
     }
@@ -256,6 +257,30 @@ __global__ void __launch_bounds__(256) win_attn_bias_bwd_kernel(const WinBwdArgs
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ fp32 column sums
+// out[c] += sum_r src[r][c], two stages in a fixed order (no atomics): block (x = 128-column slab, y = row split) sums rows
+// y, y + nsplit, ... with coalesced 512-byte row reads, then one thread per column adds the nsplit partials.
+__global__ void __launch_bounds__(128) colsum_f32_kernel(const float* __restrict__ src, long long ld, long long M, int L, int nsplit,
+                                                         float* __restrict__ part) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= L) return;
+  float a0 = 0.f, a1 = 0.f;
+  long long r = blockIdx.y;
+  for (; r + nsplit < M; r += 2 * (long long)nsplit) {
+    a0 += src[r * ld + c];
+    a1 += src[(r + nsplit) * ld + c];
+  }
+  if (r < M) a0 += src[r * ld + c];
+  part[(long long)blockIdx.y * L + c] = a0 + a1;
+}
+__global__ void __launch_bounds__(128) colsum_f32_finalize_kernel(const float* __restrict__ part, int nsplit, int L, float* __restrict__ out) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= L) return;
+  float a = 0.f;
+  for (int k = 0; k < nsplit; ++k) a += part[(long long)k * L + c];
+  out[c] += a;
+}
 }  // namespace
 }  // namespace es3
 
@@ -289,7 +314,8 @@ extern "C" int es3_layernorm_bwd(const void* x, const void* dy, const float* gam
 }
 
 /* Backward of es3_win_attn_bias_bf16 on a map whose H and W are multiples of ws (the training graph pads the token map itself).
- * dS: [B * (H/ws) * (W/ws)][ldS] bf16, a row holding [heads][ws^2][ws^2] (ldS >= heads ws^4); the bias gradient is the column sum. */
+ * dS: [B * (H/ws) * (W/ws)][ldS] fp32, a row holding [heads][ws^2][ws^2] (ldS >= heads ws^4); the bias gradient is its column sum
+ * (es3_colsum_f32). */
 extern "C" int es3_win_attn_bias_bwd(const void* qkv, const void* dout, const float* bias, void* dqkv, void* dS, long long ldS, int B, int H,
                                      int W, int C, int num_heads, int ws, float scale, void* stream) {
   ES3_REQUIRE(C == num_heads * WB_HD, "es3_win_attn_bias_bwd: head_dim must be 32 (C=%d heads=%d)", C, num_heads);
@@ -298,15 +324,35 @@ extern "C" int es3_win_attn_bias_bwd(const void* qkv, const void* dout, const fl
   ES3_REQUIRE(N <= 256, "es3_win_attn_bias_bwd: window %d too large (N <= 256)", ws);
   ES3_REQUIRE(ldS >= (long long)num_heads * N * N, "es3_win_attn_bias_bwd: ldS=%lld too small", ldS);
   WinBwdArgs a;
-  a.qkv = (const bf16*)qkv; a.dout = (const bf16*)dout; a.bias = bias; a.dqkv = (bf16*)dqkv; a.dS = (bf16*)dS; a.ldS = ldS;
+  a.qkv = (const bf16*)qkv; a.dout = (const bf16*)dout; a.bias = bias; a.dqkv = (bf16*)dqkv; a.dS = (float*)dS; a.ldS = ldS;
   a.H = H; a.W = W; a.C = C; a.ws = ws; a.nWx = W / ws; a.nWin = (H / ws) * (W / ws); a.N = N; a.scale = scale;
   const int smem = (4 * N * WB_LD + 3 * N) * (int)sizeof(float);
-  static int configured = 0;
-  if (smem > configured) {
-    ES3_CHECK_CUDA(cudaFuncSetAttribute(win_attn_bias_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  // function attributes are per device: set unconditionally (a per-process cache would leave a second device at the 48 KB default)
+  ES3_CHECK_CUDA(cudaFuncSetAttribute(win_attn_bias_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   win_attn_bias_bwd_kernel<<<dim3(B * a.nWin, num_heads), 256, smem, (cudaStream_t)stream>>>(a);
   ES3_LAUNCH_CHECK("win_attn_bias_bwd_kernel");
+  return 0;
+}
+
+static int colsum_split(long long M, int L) {
+  const long long slabs = (L + 127) / 128;
+  long long ns = (148LL * 8 + slabs - 1) / slabs;     // ~8 CTAs per SM in flight
+  if (ns > M) ns = M;
+  if (ns > 1024) ns = 1024;
+  if (ns < 1) ns = 1;
+  return (int)ns;
+}
+
+extern "C" long long es3_colsum_f32_ws_floats(long long M, int L) { return (long long)colsum_split(M, L) * L; }
+
+/* out[c] += sum over the M rows of src[r * ld + c], c < L (fp32, deterministic order). */
+extern "C" int es3_colsum_f32(const float* src, long long ld, long long M, int L, float* ws, float* out, void* stream) {
+  ES3_REQUIRE(M > 0 && L > 0 && ld >= L, "es3_colsum_f32: bad shape M=%lld L=%d ld=%lld", M, L, ld);
+  const int ns = colsum_split(M, L);
+  cudaStream_t st = (cudaStream_t)stream;
+  colsum_f32_kernel<<<dim3(ceil_div(L, 128), ns), 128, 0, st>>>(src, ld, M, L, ns, ws);
+  ES3_LAUNCH_CHECK("colsum_f32_kernel");
+  colsum_f32_finalize_kernel<<<ceil_div(L, 128), 128, 0, st>>>(ws, ns, L, out);
+  ES3_LAUNCH_CHECK("colsum_f32_finalize_kernel");
   return 0;
 }

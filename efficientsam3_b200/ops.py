@@ -19,7 +19,7 @@ def _stream() -> int:
 
 # ------------------------------------------------------------------------------------ accounting
 # kernels launched per C-ABI call (memsets excluded) -- bench.py reports the sum as `gpu_launches`.
-KERNELS_PER_CALL = {"es3_litemla_attn": 2, "es3_litemla_attn_generic": 2, "es3_fill_small_components": 4, "es3_grad_norm": 2, "es3_adamw_flat": 2, "es3_litemla_attn_tc": 2, "es3_kd_loss_fwd": 2, "es3_channel_mean": 2}
+KERNELS_PER_CALL = {"es3_colsum_f32": 2, "es3_layernorm_bwd": 2, "es3_litemla_attn": 2, "es3_litemla_attn_generic": 2, "es3_fill_small_components": 4, "es3_grad_norm": 2, "es3_adamw_flat": 2, "es3_litemla_attn_tc": 2, "es3_kd_loss_fwd": 2, "es3_channel_mean": 2}
 launch_count = 0
 
 
@@ -931,8 +931,8 @@ def layernorm_bwd(x, dy, gamma, eps, dgamma=None, dbeta=None, dres=None):
 
 def win_attn_bias_bwd(qkv, dout, bias, B, H, W, C, heads, ws, scale):
     """Backward of win_attn_bias on a map with H, W multiples of ws: qkv [B*H*W, 3C], dout [B*H*W, C] bf16, bias [heads,N,N] fp32
-    -> (dqkv [B*H*W, 3C] bf16, dbias [heads,N,N] fp32).  The kernel writes the per-window score gradients; their sum over the windows
-    (the bias gradient) is a column reduction on the verified es3_bn_act_bwd_reduce kernel."""
+    -> (dqkv [B*H*W, 3C] bf16, dbias [heads,N,N] fp32).  The kernel writes the per-window score gradients in fp32; their sum over the
+    windows (the bias gradient) is es3_colsum_f32."""
     _chk(qkv, torch.bfloat16, "qkv"); _chk(dout, torch.bfloat16, "dout"); _chk(bias, torch.float32, "bias")
     _ensure_init(qkv)
     assert qkv.is_contiguous() and dout.is_contiguous() and bias.is_contiguous()
@@ -940,16 +940,24 @@ def win_attn_bias_bwd(qkv, dout, bias, B, H, W, C, heads, ws, scale):
     N = ws * ws
     nwin = B * (H // ws) * (W // ws)
     row = heads * N * N
-    ld = (row + 7) // 8 * 8
-    dS = torch.empty((nwin, ld), device=qkv.device, dtype=torch.bfloat16)
-    if ld != row:
-        dS[:, row:].zero_()
+    dS = torch.empty((nwin, row), device=qkv.device, dtype=torch.float32)
     dqkv = torch.empty_like(qkv)
     _call("es3_win_attn_bias_bwd", f"win_attn_bias_bwd[ws={ws}]", 2 * _nb(qkv) + _nb(dout, dS), 16 * B * H * W * N * C, qkv.data_ptr(),
-          dout.data_ptr(), bias.data_ptr(), dqkv.data_ptr(), dS.data_ptr(), ld, B, H, W, C, heads, ws, float(scale), _stream())
-    dbias = torch.zeros(ld, device=qkv.device, dtype=torch.float32)
-    bn_act_bwd(dS, dS, None, None, None, "none", dbeta=dbias, apply=False)        # column sums over the windows
-    return dqkv, dbias[:row].view(heads, N, N)
+          dout.data_ptr(), bias.data_ptr(), dqkv.data_ptr(), dS.data_ptr(), row, B, H, W, C, heads, ws, float(scale), _stream())
+    dbias = torch.zeros(row, device=qkv.device, dtype=torch.float32)
+    colsum_f32(dS, dbias)                                                        # fp32 sum over the windows, fixed order
+    return dqkv, dbias.view(heads, N, N)
+
+
+def colsum_f32(src, out):
+    """out[c] += sum_r src[r, c] for an fp32 matrix (unit column stride), deterministic two-stage reduction."""
+    _chk(src, torch.float32, "src"); _chk(out, torch.float32, "out")
+    _ensure_init(src)
+    assert src.dim() == 2 and src.stride(1) == 1 and out.is_contiguous() and out.numel() == src.shape[1]
+    M, L = src.shape
+    ws = _f32ws(_lib.size("es3_colsum_f32_ws_floats", M, L), src.device)
+    _call("es3_colsum_f32", "colsum_f32", _nb(src), M * L, src.data_ptr(), src.stride(0), M, L, ws.data_ptr(), out.data_ptr(), _stream())
+    return out
 
 
 SE_BWD_BATCHED = True    # SqueezeExcite backward through es3_se_bwd_* instead of per-image loops (GPU parity: test_se_bwd_batched, r2)

@@ -50,6 +50,8 @@ def kd_train_step(student, optimizer, images, teacher_embeddings, img_size_befor
     loss = KDLossFunction.apply(preds, teacher_embeddings, sizes, images.shape[-1], cosine_weight)
     if accumulation_steps != 1:
         loss = loss / accumulation_steps
+    if hasattr(optimizer, "begin_backward"):
+        optimizer.begin_backward(update, group)              # finished arena ranges may go to NCCL from inside the backward
     (loss * optimizer.loss_scale_tensor[0]).backward()       # GradScaler.scale(loss).backward(): the scale stays on the device
     if update:
         world = optimizer.all_reduce_grads(group)

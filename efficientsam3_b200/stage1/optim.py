@@ -56,7 +56,8 @@ class FlatAdamW:
     ALIGN = 4   # floats: every parameter starts 16-byte aligned inside the arena
 
     def __init__(self, model: torch.nn.Module, lr: float, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                 loss_scale: float = 1.0, dynamic_loss_scale: bool = False, growth_interval: int = 2000):
+                 loss_scale: float = 1.0, dynamic_loss_scale: bool = False, growth_interval: int = 2000,
+                 direct_grads: bool = True, overlap_allreduce: bool = True):
         skip = model.no_weight_decay() if hasattr(model, "no_weight_decay") else ()
         skip_kw = model.no_weight_decay_keywords() if hasattr(model, "no_weight_decay_keywords") else ()
         decay, no_decay = split_decay(model.named_parameters(), skip, skip_kw)
@@ -90,6 +91,18 @@ class FlatAdamW:
         self.state = torch.tensor([loss_scale, 0.0, 0.0, 0.0], device=dev, dtype=torch.float32)
         self._norm_ws = torch.zeros(2, device=dev, dtype=torch.float32)
         self._part_ws = torch.zeros(8192, device=dev, dtype=torch.float32)
+        # The native student's backward accumulates straight into the arena views (`p.grad`) instead of returning per-parameter
+        # gradients to autograd.  Do NOT combine with torch DDP (its hooks would never see a gradient): this class owns the exchange.
+        self._pending, self._exchange_on, self._group = [], False, None
+        self.early_exchanges = 0
+        self.overlap = bool(overlap_allreduce)
+        head = [o for n, o in zip(self.names, self.offsets) if n.startswith("head.") and o < self.n_decay]
+        self._head_lo = min(head) if head else self.n_decay        # [head_lo, n_decay): head.0.weight, head.3.weight (decay group tail)
+        if direct_grads and hasattr(model, "head"):
+            model._es3_grad_arena = self
+        self.overlap_note = ("two buckets: the head's weight gradients [%d, %d) are all-reduced asynchronously as soon as the head's backward "
+                             "has been enqueued (they overlap the backbone's backward), the rest after the backward returns"
+                             % (self._head_lo, self.n_decay)) if self.overlap else "blocking, after the backward returns"
 
     # ---- step pieces ---------------------------------------------------------------------------------------------------
     def zero_grad(self):
@@ -100,12 +113,39 @@ class FlatAdamW:
         """Device float the backward kernels multiply by (es3_kd_loss_bwd scale_dev)."""
         return self.state[0:1]
 
-    def all_reduce_grads(self, group=None):
-        """The ONE collective of the data-parallel step: sum over ranks of the whole grad arena; the mean
-        (1 / world) is folded into the AdamW kernel's gradient multiplier."""
+    def begin_backward(self, exchange: bool, group=None):
+        """Called by kd_train_step before `loss.backward()`: `exchange` = this backward ends an accumulation window, so finished
+        ranges of the arena may be handed to NCCL from inside the backward (head_grads_ready)."""
+        self._exchange_on, self._group = bool(exchange), group
+
+    def head_grads_ready(self):
+        """Hook of the native student's backward (stage1/model.StudentTrainFunction): every gradient in [head_lo, n_decay) is final.
+        Launch their all-reduce now; it runs on NCCL's stream behind the kernels enqueued so far and overlaps the backbone backward."""
         import torch.distributed as dist
+        if not (self.overlap and self._exchange_on and self._head_lo < self.n_decay):
+            return
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self._group) > 1:
+            w = dist.all_reduce(self.flat_grad[self._head_lo:self.n_decay], op=dist.ReduceOp.SUM, group=self._group, async_op=True)
+            self._pending.append(w)
+            self.early_exchanges += 1
+
+    def all_reduce_grads(self, group=None):
+        """The collective of the data-parallel step: sum over ranks of the whole grad arena; the mean (1 / world) is
+        folded into the AdamW kernel's gradient multiplier.  One all-reduce of the arena, or -- when the backward already handed
+        the head range to NCCL (head_grads_ready) -- the remaining two ranges, after which the early one is waited for."""
+        import torch.distributed as dist
+        self._exchange_on = False
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
+            if self._pending:
+                if self._head_lo > 0:
+                    dist.all_reduce(self.flat_grad[:self._head_lo], op=dist.ReduceOp.SUM, group=group)
+                if self.n_decay < self.numel:
+                    dist.all_reduce(self.flat_grad[self.n_decay:], op=dist.ReduceOp.SUM, group=group)
+                for w in self._pending:
+                    w.wait()
+                self._pending = []
+            else:
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
             return dist.get_world_size(group)
         return 1
 

@@ -327,15 +327,18 @@ int es3_dwconv_wgrad(const void* dz, const void* x, long long ldx, int B, int H,
 long long es3_litemla_bwd_generic_ws_floats(int B, int HW, int heads2, int dim);
 int es3_litemla_attn_bwd_generic(const void* ms, long long ld, const void* dy, long long lddy, const float* kv_part, int nchunk_f,
                                  float* dkv_ws, void* dms, long long lddms, int B, int HW, int heads2, int dim, float eps, void* stream);
-/* TinyViT backward pieces (tinyvit_bwd.cu; no GPU run yet).  es3_layernorm_bwd: nn.LayerNorm backward over bf16 rows [M][C]
+/* TinyViT backward pieces (tinyvit_bwd.cu).  es3_layernorm_bwd: nn.LayerNorm backward over bf16 rows [M][C]
  * (tiny_vit.py:205,262): dx = dLN(x) (+ dres), dgamma += sum dy xhat, dbeta += sum dy.  es3_win_attn_bias_bwd: backward of
  * es3_win_attn_bias_bf16 (tiny_vit.py:264-293) on a token map whose H, W are multiples of ws: dqkv in the forward's layout and the
- * per-window score gradients dS [B nWin][ldS] bf16 (row = [heads][ws^2][ws^2]); the bias gradient is the column sum of dS. */
+ * per-window score gradients dS [B nWin][ldS] fp32 (row = [heads][ws^2][ws^2]); the bias gradient is the column sum of dS,
+ * es3_colsum_f32: out[c] += sum_r src[r * ld + c] in a fixed order (ws: es3_colsum_f32_ws_floats(M, L) floats). */
 long long es3_layernorm_bwd_ws_floats(long long M, int C);
 int es3_layernorm_bwd(const void* x, const void* dy, const float* gamma, const void* dres, float eps, void* dx, long long M, int C,
                       float* ws, float* dgamma, float* dbeta, void* stream);
 int es3_win_attn_bias_bwd(const void* qkv, const void* dout, const float* bias, void* dqkv, void* dS, long long ldS, int B, int H, int W,
                           int C, int num_heads, int ws, float scale, void* stream);
+long long es3_colsum_f32_ws_floats(long long M, int L);
+int es3_colsum_f32(const float* src, long long ld, long long M, int L, float* ws, float* out, void* stream);
 /* Shared-memory tiled variant of es3_dwconv_wgrad for stride 1 and C % 32 == 0 (same result contract).  Written after the round-1
  * GPU budget was spent: NOT on the default path until it has a GPU parity run (profiles/r1_next_steps.md). */
 long long es3_dwconv_wgrad_tiled_ws_floats(int B, int H, int W, int C, int ks);

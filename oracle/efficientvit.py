@@ -79,17 +79,21 @@ def lite_mla(sd, p, x, dim, eps=1.0e-15):
     agg = F.conv2d(agg, sd[p + ".aggreg.0.1.weight"], sd.get(p + ".aggreg.0.1.bias"), groups=3 * heads)
     ms = torch.cat([qkv, agg], dim=1)
     B, _, H, W = ms.shape
-    t = ms.reshape(B, -1, 3 * dim, H * W)
-    q, k, v = t[:, :, :dim], t[:, :, dim:2 * dim], t[:, :, 2 * dim:]
-    q, k = F.relu(q), F.relu(k)
-    if H * W > dim:
-        v1 = F.pad(v, (0, 0, 0, 1), mode="constant", value=1.0)
-        out = torch.matmul(torch.matmul(v1, k.transpose(-1, -2)), q)
-        out = out[:, :, :-1] / (out[:, :, -1:] + eps)
-    else:
-        att = torch.matmul(k.transpose(-1, -2), q)
-        att = att / (att.sum(dim=2, keepdim=True) + eps)
-        out = torch.matmul(v, att)
+    # ops.py:586-589 / 627-628: the attention runs with autocast disabled, fp16 inputs promoted to fp32 (a no-op on the fp32 CPU path)
+    with torch.autocast(device_type=ms.device.type, enabled=False):
+        t = ms.float() if ms.dtype == torch.float16 else ms
+        t = t.reshape(B, -1, 3 * dim, H * W)
+        q, k, v = t[:, :, :dim], t[:, :, dim:2 * dim], t[:, :, 2 * dim:]
+        q, k = F.relu(q), F.relu(k)
+        if H * W > dim:
+            v1 = F.pad(v, (0, 0, 0, 1), mode="constant", value=1.0)
+            out = torch.matmul(torch.matmul(v1, k.transpose(-1, -2)), q)
+            out = out[:, :, :-1] / (out[:, :, -1:] + eps)
+        else:
+            att = torch.matmul(k.transpose(-1, -2), q)
+            att = att / (att.sum(dim=2, keepdim=True) + eps)
+            out = torch.matmul(v, att)
+    out = out.to(ms.dtype)
     out = out.reshape(B, -1, H, W)
     return conv_layer(sd, p + ".proj", out)
 

@@ -5,9 +5,9 @@ import torch
 import torch.nn.functional as F
 
 
-def build_valid_mask(img_size, img_size_before_pad, target_hw):
+def build_valid_mask(img_size, img_size_before_pad, target_hw, device=None):
     B = len(img_size_before_pad)
-    valid = torch.zeros(B, 1, img_size, img_size)
+    valid = torch.zeros(B, 1, img_size, img_size, device=device)
     for i in range(B):
         h, w = img_size_before_pad[i][1:]
         valid[i, :, :h, :w] = 1
@@ -28,6 +28,6 @@ def masked_cosine_loss(preds, teacher, mask):
 
 
 def kd_loss(preds, teacher, img_size, img_size_before_pad, cosine_weight=1.0):
-    mask = build_valid_mask(img_size, img_size_before_pad, preds.shape[-2:])
+    mask = build_valid_mask(img_size, img_size_before_pad, preds.shape[-2:], device=preds.device)
     mse, cos = masked_mse(preds, teacher, mask), masked_cosine_loss(preds, teacher, mask)
     return mse + cosine_weight * cos, mse, cos

@@ -36,7 +36,7 @@ def axial_cis(head_dim, end_x, end_y, theta=10000.0, scale_pos=1.0):
 def rope(x, cis):
     """x: [B, heads, L, D] real -> rotated, pairs (2i, 2i+1) form complex numbers."""
     xc = torch.view_as_complex(x.float().reshape(*x.shape[:-1], -1, 2))
-    return torch.view_as_real(xc * cis.view(1, 1, *cis.shape)).flatten(3)
+    return torch.view_as_real(xc * cis.view(1, 1, *cis.shape)).flatten(3).type_as(x)     # vitdet.py:86-89: .type_as(xq)
 
 
 def attention(sd, p, x, num_heads, cis):
@@ -87,8 +87,8 @@ def vit_trunk(sd, p, x, cfg=SAM3_VIT, return_blocks=False):
     x = x + abs_pos_tiled(sd[p + "pos_embed"], h, w)
     x = F.layer_norm(x, (C,), sd[p + "ln_pre.weight"], sd[p + "ln_pre.bias"], eps=1e-5)
     hd = C // heads
-    cis_win = axial_cis(hd, win, win, scale_pos=1.0)                 # rope_pt_size == window -> scale 1
-    cis_glob = axial_cis(hd, h, w, scale_pos=win / h)                # interpolated: scale = rope_pt / input
+    cis_win = axial_cis(hd, win, win, scale_pos=1.0).to(x.device)    # rope_pt_size == window -> scale 1
+    cis_glob = axial_cis(hd, h, w, scale_pos=win / h).to(x.device)   # interpolated: scale = rope_pt / input
     outs = []
     for i in range(cfg["depth"]):
         g = i in glob

@@ -132,8 +132,11 @@ def _student_dp_worker(rank, world, port, q):
     opt.zero_grad()
     sl = slice(rank * b, (rank + 1) * b)
     loss, _, _ = kd_loss(m(x_all[sl]), t_all[sl], img, sizes[sl], 1.0)
+    opt.begin_backward(True)                           # as kd_train_step does: the head range is exchanged from inside the backward
     loss.backward()                                    # accumulates into opt.flat_grad through the p.grad views
-    n = opt.all_reduce_grads()
+    assert opt.early_exchanges == 1 and len(opt._pending) == 1, (opt.early_exchanges, opt._pending)
+    n = opt.all_reduce_grads()                         # the two remaining ranges + wait for the early one
+    assert not opt._pending
     mean_grad = opt.flat_grad / n
     err = ((mean_grad - ropt.flat_grad).norm() / ropt.flat_grad.norm()).item()
     q.put((rank, n, err, float(mean_grad.abs().sum())))

@@ -353,6 +353,63 @@ def test_training_steps_reduce_the_loss_and_are_deterministic(cuda):
     assert (e1 - e0).abs().max().item() > 1e-3
 
 
+def test_direct_arena_gradients_equal_autograd_gradients(cuda):
+    """FlatAdamW(direct_grads=True): the backward kernels accumulate straight into the flat gradient arena (the all-reduce buffer);
+    direct_grads=False: per-parameter temporaries returned to autograd, which adds them into the same views.  Bit-identical."""
+    from efficientsam3_b200.stage1.optim import FlatAdamW, KDLossFunction
+    img, embed, B = 192, 12, 2
+    x = torch.randn(B, 3, img, img, generator=_g(8)).to(cuda)
+    teacher = torch.randn(B, 1024, embed, embed, generator=_g(9)).to(cuda)
+    sz = torch.tensor([[img, img * 3 // 4]] * B, dtype=torch.int32, device=cuda)
+    arenas = []
+    for direct in (True, False):
+        m = _student("efficientvit_b1", img, embed).to(cuda).train()
+        opt = FlatAdamW(m, lr=1e-4, direct_grads=direct)
+        assert (getattr(m, "_es3_grad_arena", None) is opt) == direct
+        for _ in range(2):                                   # two backward passes: accumulation into the arena
+            KDLossFunction.apply(m(x), teacher, sz, img, 1.0).backward()
+        arenas.append(opt.flat_grad.clone())
+    assert arenas[0].abs().sum().item() > 0 and torch.equal(arenas[0], arenas[1])
+
+
+def test_cuda_graph_replay_equals_the_kernel_sequence(cuda):
+    """enable_cuda_graphs(): the eval forward replayed from a CUDA graph is bit-identical to the host-launched kernel sequence, per
+    input buffer; a parameter update invalidates the captured graph."""
+    img, embed = 192, 12
+    m = _student("efficientvit_b1", img, embed).to(cuda).eval()
+    xs = [torch.randn(2, 3, img, img, generator=_g(20 + i)).to(cuda) for i in range(2)]
+    ref = [m(x).clone() for x in xs]
+    m.enable_cuda_graphs()
+    for rep in range(3):
+        for x, r in zip(xs, ref):
+            assert torch.equal(m(x), r)
+    assert len(m._graphs) == 2 and m.graph_launches_per_step > 0
+    xs[0].mul_(0.5)                                          # same buffer, new contents: replay must read the new pixels
+    assert torch.equal(m(xs[0]), m.forward_uncaptured(xs[0]))
+    with torch.no_grad():
+        m.head[3].bias.add_(1.0)                             # bumps the parameter version: the graph is captured again
+    out = m(xs[1])
+    assert torch.equal(out, m.forward_uncaptured(xs[1])) and not torch.equal(out, ref[1])
+    m.enable_cuda_graphs(False)
+    assert torch.equal(m(xs[1]), out)
+
+
+@pytest.mark.parametrize("M,L,ld", [(1, 5, 5), (37, 130, 136), (4000, 784, 784), (11552, 9604, 9604), (3, 38416, 38416)])
+def test_colsum_f32(cuda, M, L, ld):
+    from efficientsam3_b200 import ops
+    g = _g(M + L)
+    src = torch.randn(M, ld, generator=g)
+    out0 = torch.randn(L, generator=g)
+    got = out0.clone().to(cuda)
+    ops.colsum_f32(src.to(cuda)[:, :L], got)
+    ref = out0.double() + src[:, :L].double().sum(0)
+    err = (got.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err
+    again = out0.clone().to(cuda)
+    ops.colsum_f32(src.to(cuda)[:, :L], again)
+    assert torch.equal(got, again)                          # fixed reduction order
+
+
 def test_half_width_image_batches(cuda):
     """bf16 image batches (half the host->device bytes) go through a device cast and then the same kernels: the result equals the forward
     of the rounded batch exactly, and is within the bf16 tolerance of the fp32 batch (the stem rounds its operands to bf16 itself)."""
@@ -537,7 +594,7 @@ def test_win_attn_bias_bwd(cuda, B, H, W, heads, ws):
     dq, db = ops.win_attn_bias_bwd(qkv.to(cuda), dout.to(cuda), bias.to(cuda), B, H, W, C, heads, ws, scale)
     rq, rb = E.win_attn_bias_bwd(qkv, dout, bias, B, H, W, C, heads, ws, scale)
     _close(dq, rq, 1.5e-2, "win_attn_bias_bwd dqkv")
-    _close(db, rb, 1e-2, "win_attn_bias_bwd dbias")      # per-window dS is stored in bf16 before the sum over windows
+    _close(db, rb, 2e-3, "win_attn_bias_bwd dbias")      # per-window dS in fp32, summed over the windows in fp32
 
 
 def test_tinyvit_training_step_matches_oracle_autograd(cuda):
