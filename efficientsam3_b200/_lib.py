@@ -86,6 +86,15 @@ SIGNATURES: dict[str, list] = {
     "es3_layernorm_bwd": [_vp, _vp, _vp, _vp, _f, _vp, _ll, _i, _vp, _vp, _vp, _vp],
     "es3_win_attn_bias_bwd": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _f, _vp],
     "es3_colsum_f32": [_vp, _ll, _ll, _i, _vp, _vp, _vp],
+    # strict (fp32-class) precision mode (strict_f32.cu)
+    "es3_sgemm_f32": [_vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _vp, _i, _vp, _ll, _i, _vp],
+    "es3_im2col_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "es3_dwconv_f32": [_vp, _ll, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "es3_litemla_attn_f32": [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _f, _vp],
+    "es3_bilinear_nhwc_f32_to_nchw": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "es3_attn_few_keys_f32": [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp],
+    "es3_ln_rows_gelu_f32": [_vp, _vp, _vp, _f, _vp, _ll, _i, _vp],
+    "es3_bias_act_res_f32": [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp],
     "es3_stem_wgrad": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "es3_bilinear_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_litemla_attn_bwd_generic": [_vp, _ll, _vp, _ll, _vp, _i, _vp, _vp, _ll, _i, _i, _i, _i, _f, _vp],
@@ -101,6 +110,7 @@ SIZE_HELPERS: dict[str, list] = {
     "es3_se_bwd_ws_floats": [_i, _i, _i],
     "es3_layernorm_bwd_ws_floats": [_ll, _i],
     "es3_colsum_f32_ws_floats": [_ll, _i],
+    "es3_litemla_attn_f32_ws_floats": [_i, _i, _i, _i],
     "es3_stem_wgrad_ws_floats": [_i, _i, _i, _i],
     "es3_litemla_bwd_ws_floats": [_i, _i, _i],
     "es3_litemla_bwd_generic_ws_floats": [_i, _i, _i, _i],

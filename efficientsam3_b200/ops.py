@@ -17,6 +17,34 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ------------------------------------------------------------------------------------ precision mode
+# "bf16"  : bf16 operands / activations, fp32 accumulation on tcgen05 / mma.sync -- the fast path (3e-3 .. 1.5e-2 from fp32).
+# "strict": fp32 activations, weights and FMA accumulation on the CUDA cores (csrc/strict_f32.cu) -- the parity mode for
+#           north_star's tolerances (embeddings rtol 1e-4, mask logits rtol 1e-3, binary masks bit-exact).
+_PRECISION = "bf16"
+
+
+def precision() -> str:
+    return _PRECISION
+
+
+class strict_precision:
+    """`with ops.strict_precision():` -- modules that implement the strict mode run it inside (EfficientViT students, SAM heads, FPN
+    neck); the others raise rather than silently answering in bf16."""
+
+    def __init__(self, enabled: bool = True):
+        self.mode = "strict" if enabled else "bf16"
+
+    def __enter__(self):
+        global _PRECISION
+        self.prev, _PRECISION = _PRECISION, self.mode
+        return self
+
+    def __exit__(self, *exc):
+        global _PRECISION
+        _PRECISION = self.prev
+
+
 # ------------------------------------------------------------------------------------ accounting
 # kernels launched per C-ABI call (memsets excluded) -- bench.py reports the sum as `gpu_launches`.
 KERNELS_PER_CALL = {"es3_colsum_f32": 2, "es3_layernorm_bwd": 2, "es3_litemla_attn": 2, "es3_litemla_attn_generic": 2, "es3_fill_small_components": 4, "es3_grad_norm": 2, "es3_adamw_flat": 2, "es3_litemla_attn_tc": 2, "es3_kd_loss_fwd": 2, "es3_channel_mean": 2}
@@ -1028,3 +1056,135 @@ def litemla_attn_bwd(ms, datt, kv, heads2, eps=1e-15):
           ms.data_ptr(), ld, datt.data_ptr(), datt.shape[3], kv.data_ptr(), (HW + 511) // 512, ws.data_ptr(), dms.data_ptr(), ld,
           B, HW, heads2, float(eps), _stream())
     return dms
+
+
+# ------------------------------------------------------------------------------------ strict (fp32-class) mode ops (strict_f32.cu)
+def sgemm(a, w, *, scale=None, bias=None, act=None, residual=None, out=None, act_after_res=False):
+    """fp32 out[m,n] = act(scale[n] * sum_k a[m,k] w[n,k] + bias[n]) (+ residual); row strides allowed, unit column stride."""
+    _chk(a, torch.float32, "a"); _chk(w, torch.float32, "w")
+    _ensure_init(a)
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[1], (a.shape, w.shape)
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    assert out.dtype == torch.float32 and out.shape == (M, N) and out.stride(1) == 1
+    if residual is not None:
+        _chk(residual, torch.float32, "residual")
+        assert residual.shape == (M, N) and residual.stride(1) == 1
+    _call("es3_sgemm_f32", f"sgemm_f32[K={K},N={N}]", 4 * (M * K + M * N) + _nb(w, residual), 2 * M * N * K, a.data_ptr(), a.stride(0),
+          w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), M, N, K, _ptr(scale), _ptr(bias), ACT[act], _ptr(residual),
+          residual.stride(0) if residual is not None else 0, int(act_after_res), _stream())
+    return out
+
+
+def conv2d_f32(x, weight, stride=1, pad=0, *, scale=None, bias=None, act=None, residual=None, nchw=False):
+    """Dense nn.Conv2d in the strict mode: x NHWC fp32 [B,H,W,C] (nchw=True: the NCHW fp32 image), weight [N,C,k,k] fp32 (the
+    nn.Conv2d parameter) -> NHWC fp32 [B,Ho,Wo,N] = act(scale * conv + bias) (+ residual).  1x1 stride-1 convs are one SGEMM on the
+    pixel matrix; everything else goes through es3_im2col_f32."""
+    _chk(x, torch.float32, "x"); _chk(weight, torch.float32, "weight")
+    _ensure_init(x)
+    N, C, ks, _ = weight.shape
+    if nchw:
+        B, Cx, H, W = x.shape
+    else:
+        B, H, W, Cx = x.shape
+    assert Cx == C and x.is_contiguous(), (x.shape, weight.shape)
+    Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+    res2 = residual.reshape(B * Ho * Wo, N) if residual is not None else None
+    if ks == 1 and stride == 1 and pad == 0 and not nchw:
+        out = sgemm(x.view(-1, C), weight.reshape(N, C), scale=scale, bias=bias, act=act, residual=res2)
+        return out.view(B, Ho, Wo, N)
+    cols = torch.empty((B * Ho * Wo, ks * ks * C), device=x.device, dtype=torch.float32)
+    _call("es3_im2col_f32", "im2col_f32", _nb(x, cols), 0, x.data_ptr(), cols.data_ptr(), B, H, W, C, ks, stride, pad, int(nchw), _stream())
+    wk = weight.permute(0, 2, 3, 1).reshape(N, ks * ks * C).contiguous()          # k = (ky * ks + kx) * C + c
+    return sgemm(cols, wk, scale=scale, bias=bias, act=act, residual=res2).view(B, Ho, Wo, N)
+
+
+def dwconv_f32(x, w, scale, bias, ks, stride, act, out=None):
+    """Depthwise conv in the strict mode: x [B,H,W,C] fp32 (channel slice of a wider NHWC map allowed), w [ks*ks, C] fp32."""
+    _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w")
+    _ensure_init(x)
+    B, H, W, C = x.shape
+    assert x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1) and w.shape == (ks * ks, C) and w.is_contiguous()
+    pad = ks // 2
+    Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.float32)
+    assert out.shape == (B, Ho, Wo, C) and out.stride(3) == 1 and out.stride(1) == Wo * out.stride(2) and out.stride(0) == Ho * out.stride(1)
+    _call("es3_dwconv_f32", f"dwconv_f32[k={ks}]", 4 * (x.numel() + out.numel()), 2 * out.numel() * ks * ks, x.data_ptr(), x.stride(2),
+          w.data_ptr(), _ptr(scale), _ptr(bias), out.data_ptr(), out.stride(2), B, H, W, C, ks, stride, ACT[act], _stream())
+    return out
+
+
+def litemla_attn_f32(ms, heads, dim, eps):
+    """LiteMLA.relu_linear_att on fp32: ms [B,H,W,3*dim*heads] (head = q | k | v) -> [B,H,W,dim*heads] fp32."""
+    _chk(ms, torch.float32, "ms")
+    _ensure_init(ms)
+    assert ms.is_contiguous()
+    B, H, W, ld = ms.shape
+    assert ld == 3 * dim * heads
+    out = torch.empty((B, H, W, dim * heads), device=ms.device, dtype=torch.float32)
+    ws = _f32ws(_lib.size("es3_litemla_attn_f32_ws_floats", B, H * W, heads, dim), ms.device)
+    _call("es3_litemla_attn_f32", "litemla_attn_f32", _nb(ms, out) + _nb(ms) * 2 // 3, 4 * B * H * W * heads * dim * (dim + 1),
+          ms.data_ptr(), ld, ws.data_ptr(), out.data_ptr(), dim * heads, B, H * W, heads, dim, float(eps), _stream())
+    return out
+
+
+def bilinear_nhwc_f32_to_nchw(x, Ho, Wo):
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    assert x.is_contiguous()
+    B, Hi, Wi, C = x.shape
+    out = torch.empty((B, C, Ho, Wo), device=x.device, dtype=torch.float32)
+    _call("es3_bilinear_nhwc_f32_to_nchw", "bilinear_f32", _nb(x, out), 8 * out.numel(), x.data_ptr(), out.data_ptr(), B, Hi, Wi, C, Ho, Wo,
+          _stream())
+    return out
+
+
+def attn_few_keys_f32(q, k, v, B, heads, scale):
+    """q [B*Nq, D] fp32; k, v [B,Tk,D] fp32 -> [B*Nq, D] fp32 (libm exp)."""
+    _chk(q, torch.float32, "q"); _chk(k, torch.float32, "k"); _chk(v, torch.float32, "v")
+    _ensure_init(q)
+    D = q.shape[1]
+    Nq, Tk = q.shape[0] // B, k.shape[1]
+    assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    out = torch.empty_like(q)
+    _call("es3_attn_few_keys_f32", "attn_few_keys_f32", _nb(q, k, v, out), 4 * B * Nq * Tk * D, q.data_ptr(), D, k.data_ptr(), v.data_ptr(),
+          D, out.data_ptr(), D, B, heads, D // heads, Nq, Tk, float(scale), _stream())
+    return out
+
+
+def ln_rows_gelu_f32(x, w, b, eps):
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    assert x.dim() == 2 and x.is_contiguous()
+    M, C = x.shape
+    y = torch.empty_like(x)
+    _call("es3_ln_rows_gelu_f32", "ln_rows_gelu_f32", 2 * _nb(x), 10 * M * C, x.data_ptr(), w.data_ptr(), b.data_ptr(), float(eps),
+          y.data_ptr(), M, C, _stream())
+    return y
+
+
+def bias_act_res_f32(x, bias=None, act=None, residual=None, act_after_res=False):
+    """act(x + bias[c]) + residual (act_after_res: act(x + bias[c] + residual)); x [..., C] fp32 contiguous."""
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    assert x.is_contiguous() and (residual is None or (residual.is_contiguous() and residual.shape == x.shape and residual.dtype == torch.float32))
+    y = torch.empty_like(x)
+    _call("es3_bias_act_res_f32", "bias_act_res_f32", _nb(x, y, residual), x.numel(), x.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(),
+          x.numel(), x.shape[-1], ACT[act], int(act_after_res), _stream())
+    return y
+
+
+def convt2x2_f32(x, weight, bias=None, act=None, residual=None, act_after_res=False):
+    """nn.ConvTranspose2d(k=2, s=2) in the strict mode: x [B,H,W,Cin] fp32, weight [Cin,Cout,2,2] fp32 (the parameter) ->
+    [B,2H,2W,Cout] fp32 = act(convT + bias) (+ residual).  One SGEMM with N = 4 Cout, depth-to-space as a view permute (layout
+    plumbing), then the elementwise tail."""
+    _chk(x, torch.float32, "x"); _chk(weight, torch.float32, "weight")
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[1]
+    wt = weight.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).contiguous()          # row (dy*2+dx)*Cout + co
+    y = sgemm(x.reshape(-1, Cin), wt)                                            # [B*H*W, 4*Cout]
+    y = y.view(B, H, W, 2, 2, Cout).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, Cout).contiguous()
+    return bias_act_res_f32(y, bias, act, residual, act_after_res)

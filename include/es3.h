@@ -363,6 +363,34 @@ long long es3_litemla_bwd_ws_floats(int B, int HW, int heads2);
 int es3_litemla_attn_bwd(const void* ms, long long ld, const void* dy, long long lddy, const float* kv_part, int nchunk_f,
                          float* dkv_ws, void* dms, long long lddms, int B, int HW, int heads2, float eps, void* stream);
 
+/* ---- strict (fp32-class) precision mode (strict_f32.cu): fp32 activations / weights / FMA accumulation on the CUDA cores, the
+ * parity mode for north_star's tolerances (embeddings rtol 1e-4, mask logits rtol 1e-3, binary masks bit-exact) against the
+ * reference's PyTorch fp32 path (its LiteMLA is forced to fp32: efficientvit/nn/ops.py:586-589).  Same epilogue contract as
+ * es3_gemm_bf16: out = act(scale[n] * A W^T + bias[n]) (+ residual), the activation after the residual when act_after_res. */
+int es3_sgemm_f32(const float* A, long long lda, const float* W, long long ldw, float* out, long long ldo, long long M, int N, int K,
+                  const float* scale, const float* bias, int act, const float* residual, long long ldr, int act_after_res, void* stream);
+/* cols[(b,oy,ox)][(ky*ks+kx)*C + c] of an NHWC fp32 map (nchw != 0: of the NCHW fp32 image), zero padding: every dense, strided or
+ * image convolution (nn.Conv2d: ops.py:39-80, stage1/model.py:194-199, necks.py) becomes es3_sgemm_f32 on it. */
+int es3_im2col_f32(const float* x, float* cols, int B, int H, int W, int C, int ks, int stride, int pad, int nchw, void* stream);
+/* depthwise k x k (odd k, same padding), w [k*k][C] tap-major, y = act(scale[c] * conv + bias[c]); NHWC fp32 with pixel strides
+ * ldx / ldy floats (channel slices of a wider map). */
+int es3_dwconv_f32(const float* x, long long ldx, const float* w, const float* scale, const float* bias, float* y, long long ldy, int B,
+                   int H, int W, int C, int ks, int stride, int act, void* stream);
+/* LiteMLA.relu_linear_att (ops.py:584-621) on fp32: ms [B][HW][ld], head h = q | k | v at columns [3 dim h, 3 dim (h+1));
+ * out [B][HW][ldo], head h at columns [dim h, dim (h+1)).  ws: es3_litemla_attn_f32_ws_floats(B, HW, heads, dim) floats. */
+long long es3_litemla_attn_f32_ws_floats(int B, int HW, int heads, int dim);
+int es3_litemla_attn_f32(const float* ms, long long ld, float* ws, float* out, long long ldo, int B, int HW, int heads, int dim, float eps,
+                         void* stream);
+/* F.interpolate(bilinear, align_corners=False) NHWC fp32 -> NCHW fp32 (stage1/model.py:203-210); equal sizes = layout change. */
+int es3_bilinear_nhwc_f32_to_nchw(const float* x, float* y, int B, int Hi, int Wi, int C, int Ho, int Wo, void* stream);
+/* fp32 twins of es3_attn_few_keys / es3_ln_rows_gelu (sam/transformer.py:168-176, mask_decoder.py:59-70) and the elementwise tail
+ * y = act(x + bias[c]) + residual (act_after_res: act(x + bias[c] + residual)) of the strict ConvTranspose2d path. */
+int es3_attn_few_keys_f32(const float* q, long long ldq, const float* k, const float* v, long long ldkv, float* out, long long ldo, int B,
+                          int H, int head_dim, int Nq, int Tk, float scale, void* stream);
+int es3_ln_rows_gelu_f32(const float* x, const float* w, const float* bias, float eps, float* y, long long M, int C, void* stream);
+int es3_bias_act_res_f32(const float* x, const float* bias, const float* residual, float* y, long long total, int C, int act,
+                         int act_after_res, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
