@@ -497,6 +497,8 @@ def other_encoders(dev, S, E):
         ("efficientsam3_evm_point_prompt", lambda: efficientsam3_point_leg(dev, batch=8)),
         # A21 end to end: pinned host images -> H2D -> teacher forward -> fp16 -> D2H of the embeddings (10.6 MB / image)
         ("e2e_teacher_dump", lambda: teacher_dump_e2e_leg(dev, batch=8, steps=4, warm=1)),
+        # the strict (fp32-class) precision mode of the headline model: parity mode, CUDA-core fp32 kernels
+        ("strict_mode_evm_forward", lambda: strict_leg(dev, S, E, batch=8)),
     ]
     for name, fn in legs:
         try:
@@ -506,6 +508,25 @@ def other_encoders(dev, S, E):
             out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
     torch.cuda.empty_cache()
     return out
+
+
+def strict_leg(dev, S, E, batch):
+    from efficientsam3_b200 import ops
+    m = build_student(S, E, dev)
+    x = torch.randn(batch, 3, S, S, device=dev)
+
+    def fwd():
+        with ops.strict_precision():
+            return m(x)
+
+    ms = _time_steps(fwd, 1, 3)
+    fast = m(x)
+    strict = fwd()
+    rel = ((fast.double() - strict.double()).norm() / strict.double().norm()).item()
+    return {"images_per_s": round(batch / ms * 1e3, 1), "ms_per_step": round(ms, 2), "batch": batch, "img": S,
+            "what": "EV-M forward with fp32 activations / weights / FMA accumulation (csrc/strict_f32.cu): embeddings within rtol 1e-4 of the "
+                    "reference's fp32 output (tests/test_strict_gpu.py); the bf16 tensor-core mode is the headline",
+            "bf16_mode_rel_l2_vs_strict": float(f"{rel:.3e}")}
 
 
 def teacher_dump_e2e_leg(dev, batch, steps, warm):

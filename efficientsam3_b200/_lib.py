@@ -86,6 +86,8 @@ SIGNATURES: dict[str, list] = {
     "es3_layernorm_bwd": [_vp, _vp, _vp, _vp, _f, _vp, _ll, _i, _vp, _vp, _vp, _vp],
     "es3_win_attn_bias_bwd": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _f, _vp],
     "es3_colsum_f32": [_vp, _ll, _ll, _i, _vp, _vp, _vp],
+    "es3_pw_small_bf16": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp],
+    "es3_wgrad_tc": [_vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _vp, _ll, _vp],
     # strict (fp32-class) precision mode (strict_f32.cu)
     "es3_sgemm_f32": [_vp, _ll, _vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _vp, _i, _vp, _ll, _i, _vp],
     "es3_im2col_f32": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
@@ -110,6 +112,7 @@ SIZE_HELPERS: dict[str, list] = {
     "es3_se_bwd_ws_floats": [_i, _i, _i],
     "es3_layernorm_bwd_ws_floats": [_ll, _i],
     "es3_colsum_f32_ws_floats": [_ll, _i],
+    "es3_wgrad_tc_ws_floats": [_ll, _i, _i],
     "es3_litemla_attn_f32_ws_floats": [_i, _i, _i, _i],
     "es3_stem_wgrad_ws_floats": [_i, _i, _i, _i],
     "es3_litemla_bwd_ws_floats": [_i, _i, _i],

@@ -19,6 +19,9 @@
 //   warps 2-9: epilogue       -- tcgen05.ld 32x32b -> registers -> scale/bias/act/rope/residual -> global
 // Pipelines: full[s]/empty[s] mbarriers (TMA <-> MMA), tmem_full[2]/tmem_empty[2] (MMA <-> epilogue) over a
 // double-buffered TMEM accumulator, so the epilogue of one tile overlaps the main loop of the next.
+#include <cstdio>
+#include <cstdlib>
+
 #include "ptx.cuh"
 
 namespace es3 {
@@ -48,43 +51,108 @@ struct GemmArgs {
   // (b,h,w) / column n to output pixel (b, 2h+dy, 2w+dx), channel co (depth-to-space).  0 = off.
   int ct_cout, ct_H, ct_W;
   int act_after_res;    // apply the activation after the residual add (MaskDecoder: gelu(dc2(x) + feat_s0))
+  int dbg;              // ES3_GEMM_DBG bits (bottleneck bisection only; 0 in production): 1 no stores, 2 no tmem loads, 4 epilogue = hand-back only, 8 loads pinned to tile 0
 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 
-template <int BN, int STAGES>
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, splitting the column chunks
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
+// CPR = 16-byte chunks per row of the per-warp transposition tile (see epi_store_rows): 4 -> 32 rows x 64 B = 2 KB per warp,
+// 2 -> 32 rows x 32 B = 1 KB per warp (the deep-pipeline BN = 128 configuration, which must keep two CTAs per SM: the first
+// version of this epilogue spent 114688 B and the runtime reported ONE resident CTA -- gpurun_out/r2g_bisect.log)
+template <int BN, int STAGES, int CPR>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+  static constexpr int OFF_EPI = STAGES * STAGE_BYTES;
+  static constexpr int EPI_TILE_BYTES = 32 * 16 * CPR;
+  static constexpr int TOTAL = OFF_EPI + EPI_WARPS * EPI_TILE_BYTES;   // no alignment slack: the buffer is declared __align__(1024)
 };
 
-constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, splitting the column chunks
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
+// ---- coalescing the epilogue's global traffic ------------------------------------------------------------------------------
+// tcgen05.ld 32x32b hands lane r the 32 columns of ROW r.  Stored straight from there, one STG.128 touches 32 different rows
+// (32 cache-line wavefronts of 16 B each): ncu showed the short-K GEMMs of the students sitting on exactly that
+// (lg_throttle 3.9 / issue, 17 % of the samples on the four STG.128, profiles/r2c_*: 2048 sixteen-byte write requests per
+// 128 x 128 tile).  Each epilogue warp therefore owns a 2 KB shared-memory tile of 32 rows x 64 B: the row owner writes its four
+// 16-byte chunks (XOR-swizzled by (row >> 1) & 3: conflict-free both ways), then lane l moves chunk (l & 3) of row 8 j + (l >> 2),
+// j = 0..3 -- one instruction now covers 8 rows x 64 contiguous bytes (8 wavefronts of two full sectors).  The same tile runs
+// backwards for the residual operand.  Row offsets / validity travel by shuffle, so every row mapping (plain, implicit-GEMM conv
+// tiles, ConvTranspose depth-to-space) shares the code.
+template <int CPR>
+__device__ __forceinline__ uint8_t* epi_chunk(uint8_t* tile, int r, int c) {
+  if constexpr (CPR == 4) return tile + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+  else return tile + r * 32 + ((c ^ ((r >> 2) & 1)) << 4);
+}
+
+// `mine`: this lane's row, 64 bytes = 4 chunks; moved to global in 64 / (16 CPR) passes through the tile
+template <int CPR>
+__device__ __forceinline__ void epi_store_rows(uint8_t* tile, const uint4* mine, uint8_t* gbase, long long my_off_bytes,
+                                               bool my_valid, int lane) {
+  constexpr int RPI = 32 / CPR;           // rows per store instruction
+#pragma unroll
+  for (int p = 0; p < 4 / CPR; ++p) {
+#pragma unroll
+    for (int j = 0; j < CPR; ++j) *reinterpret_cast<uint4*>(epi_chunk<CPR>(tile, lane, j)) = mine[p * CPR + j];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < CPR; ++j) {
+      const int r = j * RPI + lane / CPR, c = lane % CPR;
+      const long long off = __shfl_sync(0xffffffffu, my_off_bytes, r);
+      const int ok = __shfl_sync(0xffffffffu, (int)my_valid, r);
+      const uint4 u = *reinterpret_cast<const uint4*>(epi_chunk<CPR>(tile, r, c));
+      if (ok) *reinterpret_cast<uint4*>(gbase + off + (p * CPR + c) * 16) = u;
+    }
+    __syncwarp();
+  }
+}
+
+template <int CPR>
+__device__ __forceinline__ void epi_load_rows(uint8_t* tile, uint4* mine, const uint8_t* gbase, long long my_off_bytes,
+                                              bool my_valid, int lane) {
+  constexpr int RPI = 32 / CPR;
+#pragma unroll
+  for (int p = 0; p < 4 / CPR; ++p) {
+#pragma unroll
+    for (int j = 0; j < CPR; ++j) {
+      const int r = j * RPI + lane / CPR, c = lane % CPR;
+      const long long off = __shfl_sync(0xffffffffu, my_off_bytes, r);
+      const int ok = __shfl_sync(0xffffffffu, (int)my_valid, r);
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (ok) u = __ldg(reinterpret_cast<const uint4*>(gbase + off + (p * CPR + c) * 16));
+      *reinterpret_cast<uint4*>(epi_chunk<CPR>(tile, r, c)) = u;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < CPR; ++j) mine[p * CPR + j] = *reinterpret_cast<const uint4*>(epi_chunk<CPR>(tile, lane, j));
+    __syncwarp();
+  }
+}
 
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so CTAs that
 // run together share the A row-block in L2).  The accumulator is double-buffered in TMEM (2 x BN columns):
 // the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
-template <int BN, int STAGES, int ACT>
+template <int BN, int STAGES, int ACT, int CPR>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const GemmArgs args, const int num_tiles) {
-  extern __shared__ uint8_t smem_raw[];
+  // (no integer round trip on the pointer: the compiler keeps shared-space addressing for the staging tiles)
+  extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_holder;
 
-  using L = GemmSmem<BN, STAGES>;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using L = GemmSmem<BN, STAGES, CPR>;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    if (ptx::smem_u32(smem) & 1023u) { printf("es3: gemm_tc dynamic smem base not 1024-byte aligned\n"); __trap(); }
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
 #pragma unroll
@@ -112,8 +180,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % args.tiles_n) * BN;
-        const int m_tile = tile / args.tiles_n;
+        const int n0 = (args.dbg & 8) ? 0 : (tile % args.tiles_n) * BN;
+        const int m_tile = (args.dbg & 8) ? 0 : tile / args.tiles_n;
         int img = 0, h0 = 0, w0 = 0;
         if (args.conv) {
           img = m_tile / per_img;
@@ -176,6 +244,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;       // which of the two warps of the quarter: interleaved column chunks
     const int r = q * 32 + lane;            // row inside the tile
+    uint8_t* epi_tile = smem + L::OFF_EPI + (warp - 2) * L::EPI_TILE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -183,6 +252,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
       const int m_tile = tile / args.tiles_n;
       bool valid;
       long long row_off;
+      const bool dbg_nostore = (args.dbg & 1) != 0;
       if (args.conv) {
         const int img = m_tile / per_img;
         const int t = m_tile % per_img;
@@ -197,14 +267,21 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
         row_off = m;
       }
 
+      if (dbg_nostore) valid = false;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
 
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
+        if (args.dbg & 4) break;
         uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-        ptx::tmem_ld_wait();
+        if (args.dbg & 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint((float)(r + j));
+        } else {
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+          ptx::tmem_ld_wait();
+        }
         const int nb = n0 + c * 32;
         if (valid && nb < args.N && nb + 32 > args.N) {
           // ragged last chunk (N % 32 != 0, N % 8 == 0): per-column path, plain GEMM epilogue only
@@ -225,7 +302,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
               else reinterpret_cast<bf16*>(args.out)[out_off + j] = __float2bfloat16(x);
             }
           }
-        } else if (valid && nb < args.N) {
+        } else if (nb + 32 <= args.N) {
+          // every lane of the warp comes through here together (nb, N are warp-uniform): the loads / stores below are
+          // cooperative; rows past M (or outside the conv tile) compute on whatever TMEM holds and are masked at the store
           float f[32];
           if (args.scale != nullptr) {
             const float4* sc4 = reinterpret_cast<const float4*>(args.scale + nb);
@@ -279,19 +358,25 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
               f[4 * j + 3] = x2 * cs.w + x3 * cs.z;
             }
           }
-          if (args.residual != nullptr && args.res_f32) {
-            const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(args.residual) + res_off);
+          if (args.residual != nullptr && args.res_f32) {     // 32 fp32 = two 64-byte halves through the staging tile
+            const uint8_t* rbase = reinterpret_cast<const uint8_t*>(args.residual);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 r4 = __ldg(rp + j);
-              f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+            for (int hf = 0; hf < 2; ++hf) {
+              uint4 rr[4];
+              epi_load_rows<CPR>(epi_tile, rr, rbase, res_off * 4 + hf * 64, valid, lane);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[hf * 16 + 4 * j + 0] += __uint_as_float(rr[j].x); f[hf * 16 + 4 * j + 1] += __uint_as_float(rr[j].y);
+                f[hf * 16 + 4 * j + 2] += __uint_as_float(rr[j].z); f[hf * 16 + 4 * j + 3] += __uint_as_float(rr[j].w);
+              }
             }
           } else if (args.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(args.residual + res_off);
+            uint4 rr[4];
+            epi_load_rows<CPR>(epi_tile, rr, reinterpret_cast<const uint8_t*>(args.residual), res_off * 2, valid, lane);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float rf[8];
-              unpack8(__ldg(rp + j), rf);
+              unpack8(rr[j], rf);
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[j * 8 + e] += rf[e];
             }
@@ -301,15 +386,22 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
             for (int j = 0; j < 32; ++j) f[j] = es3_act_t<ACT>(f[j]);
           }
           if (args.out_f32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + out_off);
+            uint8_t* obase = reinterpret_cast<uint8_t*>(args.out);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int hf = 0; hf < 2; ++hf) {
+              uint4 oo[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                oo[j] = make_uint4(__float_as_uint(f[hf * 16 + 4 * j]), __float_as_uint(f[hf * 16 + 4 * j + 1]),
+                                   __float_as_uint(f[hf * 16 + 4 * j + 2]), __float_as_uint(f[hf * 16 + 4 * j + 3]));
+              epi_store_rows<CPR>(epi_tile, oo, obase, out_off * 4 + hf * 64, valid, lane);
+            }
           } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(args.out) + out_off);
+            uint4 oo[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = pack8(f + 8 * j);
+            for (int j = 0; j < 4; ++j) oo[j] = pack8(f + 8 * j);
+            epi_store_rows<CPR>(epi_tile, oo, reinterpret_cast<uint8_t*>(args.out), out_off * 2, valid, lane);
           }
-
         }
       }
       // this warp is done reading the accumulator: hand it back to the MMA warp
@@ -367,39 +459,48 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
   return 0;
 }
 
-template <int BN, int STAGES, int ACT>
+template <int BN, int STAGES, int ACT, int CPR>
 static int launch_act(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int tiles_m,
                       cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    ES3_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        L::TOTAL));
-    configured = true;
-  }
-  const int num_tiles = tiles_m * args.tiles_n;
+  using L = GemmSmem<BN, STAGES, CPR>;
+  static int resident = 0;     // CTAs of this instantiation one SM holds (asked of the runtime: smem is sized to the last KB)
   static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
+  if (resident == 0) {
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, ACT, CPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        L::TOTAL));
+    // ask for the full shared-memory carveout: with the default preference the runtime reported ONE resident CTA even for 80 KB
+    // blocks (gpurun_out/r2h_bisect.log) and a grid sized from that left half of every SM's slots empty
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, ACT, CPR>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
+    int dev = 0, occ = 0;
     ES3_CHECK_CUDA(cudaGetDevice(&dev));
     ES3_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    ES3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_tc_kernel<BN, STAGES, ACT, CPR>, GEMM_THREADS, L::TOTAL));
+    ES3_REQUIRE(occ >= 1, "gemm_tc_kernel<%d,%d>: does not fit an SM (%d B of dynamic shared memory)", BN, STAGES, L::TOTAL);
+    // slots per SM: TMEM (2 * BN of 512 columns) and shared memory (228 KB minus 1 KB per CTA) allow two CTAs for BN <= 128;
+    // the grid is a persistent tile loop, so an over-estimate only costs a second wave
+    resident = (BN >= 256 || 2 * (L::TOTAL + 2048) > 233472) ? 1 : 2;
+    if (getenv("ES3_DEBUG_OCCUPANCY"))
+      fprintf(stderr, "es3: gemm_tc_kernel<BN=%d,STAGES=%d,ACT=%d,CPR=%d> %d B smem -> %d CTA/SM (runtime occupancy %d)\n", BN, STAGES, ACT,
+              CPR, L::TOTAL, resident, occ);
   }
-  // BN = 256 uses all 512 TMEM columns and ~193 KB of smem: one CTA per SM.  Narrower tiles fit two.
-  const int ctas = sm_count * (BN == 256 ? 1 : 2);
+  const int num_tiles = tiles_m * args.tiles_n;
+  // persistent grid: every resident slot of every SM, BN = 256 uses all 512 TMEM columns and ~209 KB of smem (one CTA per SM)
+  const int ctas = sm_count * resident;
   dim3 grid((unsigned)(num_tiles < ctas ? num_tiles : ctas));
-  gemm_tc_kernel<BN, STAGES, ACT><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, args, num_tiles);
+  gemm_tc_kernel<BN, STAGES, ACT, CPR><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, args, num_tiles);
   ES3_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CPR>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int tiles_m,
                   cudaStream_t stream) {
   switch (args.act) {
-    case ACT_NONE: return launch_act<BN, STAGES, ACT_NONE>(tmA, tmB, args, tiles_m, stream);
-    case ACT_RELU: return launch_act<BN, STAGES, ACT_RELU>(tmA, tmB, args, tiles_m, stream);
-    case ACT_HSWISH: return launch_act<BN, STAGES, ACT_HSWISH>(tmA, tmB, args, tiles_m, stream);
-    case ACT_GELU: return launch_act<BN, STAGES, ACT_GELU>(tmA, tmB, args, tiles_m, stream);
+    case ACT_NONE: return launch_act<BN, STAGES, ACT_NONE, CPR>(tmA, tmB, args, tiles_m, stream);
+    case ACT_RELU: return launch_act<BN, STAGES, ACT_RELU, CPR>(tmA, tmB, args, tiles_m, stream);
+    case ACT_HSWISH: return launch_act<BN, STAGES, ACT_HSWISH, CPR>(tmA, tmB, args, tiles_m, stream);
+    case ACT_GELU: return launch_act<BN, STAGES, ACT_GELU, CPR>(tmA, tmB, args, tiles_m, stream);
     default: set_error("gemm_tc: activation code %d not instantiated (0,1,2,3)", args.act); return 1;
   }
 }
@@ -424,10 +525,12 @@ static int pick_bn(int N, int bn_hint, int K = 1 << 30, int act = ACT_NONE) {
 static int dispatch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args, int tiles_m,
                     cudaStream_t stream) {
   switch (bn) {
-    case 256: return launch<256, 4>(tmA, tmB, args, tiles_m, stream);
-    case 128: return launch<128, 3>(tmA, tmB, args, tiles_m, stream);
-    case 64: return launch<64, 4>(tmA, tmB, args, tiles_m, stream);
-    default: return launch<32, 4>(tmA, tmB, args, tiles_m, stream);
+    // (shared memory per CTA; two CTAs per SM need <= ~110 KB each)
+    case 256: return launch<256, 4, 4>(tmA, tmB, args, tiles_m, stream);                        // 208 KB, one CTA per SM
+    case 128: return args.num_kb <= 4 ? launch<128, 2, 4>(tmA, tmB, args, tiles_m, stream)      //  80 KB: short K, a tile is <= 4 k-blocks
+                                      : launch<128, 3, 2>(tmA, tmB, args, tiles_m, stream);     // 104 KB: deep pipeline, 1 KB staging tiles
+    case 64: return launch<64, 3, 4>(tmA, tmB, args, tiles_m, stream);                          //  88 KB
+    default: return launch<32, 4, 4>(tmA, tmB, args, tiles_m, stream);                          //  96 KB
   }
 }
 
@@ -479,6 +582,7 @@ extern "C" int es3_gemm_bf16_ex(const void* A, long long lda, const void* W, lon
   }
   GemmArgs a;
   memset(&a, 0, sizeof(a));
+  { const char* e = getenv("ES3_GEMM_DBG"); if (e) a.dbg = atoi(e); }
   a.M = M; a.N = N;
   a.num_kb = ceil_div(K, BK);
   a.kb_per_tap = a.num_kb;
@@ -518,6 +622,7 @@ extern "C" int es3_conv3x3_bf16(const void* x, const void* W, void* out, int out
   }
   GemmArgs a;
   memset(&a, 0, sizeof(a));
+  { const char* e = getenv("ES3_GEMM_DBG"); if (e) a.dbg = atoi(e); }
   a.M = B * H * Wd; a.N = N;
   a.kb_per_tap = ceil_div(C, BK);
   a.num_kb = 9 * a.kb_per_tap;
@@ -560,6 +665,7 @@ extern "C" int es3_convt2x2_bf16(const void* x, const void* Wt, void* out, int o
   }
   GemmArgs a;
   memset(&a, 0, sizeof(a));
+  { const char* e = getenv("ES3_GEMM_DBG"); if (e) a.dbg = atoi(e); }
   a.M = M; a.N = N;
   a.num_kb = ceil_div(K, BK);
   a.kb_per_tap = a.num_kb;

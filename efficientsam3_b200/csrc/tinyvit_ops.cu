@@ -152,41 +152,54 @@ __global__ void win_attn_bias_kernel(const WinAttnArgs a) {
   }
 }
 
-// LayerNorm over rows of bf16, C % 8 == 0, C <= 1024.  One warp per row, values kept in registers.
-__global__ void layernorm_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      float eps, bf16* __restrict__ y, long long M, int C) {
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
+// LayerNorm over rows of bf16, C % 8 == 0, C <= 1024, values kept in registers.  A row is handled by L = min(32, pow2ceil(C / 8))
+// lanes (TinyViT's C = 128 rows are 16 vectors of 8: two rows per warp -- the one-warp-per-row version left half of every warp idle
+// on exactly the largest token maps and ran at 1.4 TB/s, profiles/r2c_table_tiny_vit_11m.md); reductions are xor-shuffles inside
+// the L-lane group.
+template <int L>
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps, bf16* __restrict__ y, long long M,
+                                                             int C) {
+  constexpr int RPW = 32 / L;                                  // rows per warp
+  const int lane = threadIdx.x & 31, sub = lane % L;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / L;
+  const bool live = row < M;
   const int nvec = C >> 3;
   float v[4][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      unpack8(*reinterpret_cast<const uint4*>(x + row * C + vi * 8), v[i]);
+    const int vi = sub + i * L;
+    if (live && vi < nvec) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + vi * 8)), v[i]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) s += v[i][e];
     }
   }
-  const float mean = warp_sum(s) / C;
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (lane + i * 32 < nvec) {
+    if (live && sub + i * L < nvec) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; q += d * d; }
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
+    const int vi = sub + i * L;
+    if (live && vi < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8) + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * gamma[vi * 8 + e] + beta[vi * 8 + e];
+      for (int e = 0; e < 8; ++e) o[e] = fmaf((v[i][e] - mean) * rstd, gg[e], bb[e]);
       *reinterpret_cast<uint4*>(y + row * C + vi * 8) = pack8(o);
     }
   }
@@ -229,7 +242,15 @@ extern "C" int es3_win_attn_bias_bf16(const void* qkv, const void* qkv_pad, cons
 extern "C" int es3_layernorm_bf16(const void* x, const float* gamma, const float* beta, float eps, void* y, long long M, int C,
                                   void* stream) {
   ES3_REQUIRE(C % 8 == 0 && C <= 1024, "es3_layernorm_bf16: C=%d must be a multiple of 8 and <= 1024", C);
-  layernorm_bf16_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, M, C);
+  ES3_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, "es3_layernorm_bf16: 16-byte alignment");
+  const int nvec = C / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nvec <= 8)
+    layernorm_bf16_kernel<8><<<(unsigned)ceil_div(M, 8 * 4), 256, 0, st>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, M, C);
+  else if (nvec <= 16)
+    layernorm_bf16_kernel<16><<<(unsigned)ceil_div(M, 8 * 2), 256, 0, st>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, M, C);
+  else
+    layernorm_bf16_kernel<32><<<(unsigned)ceil_div(M, 8), 256, 0, st>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, M, C);
   ES3_LAUNCH_CHECK("layernorm_bf16_kernel");
   return 0;
 }

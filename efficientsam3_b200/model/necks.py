@@ -62,6 +62,19 @@ class Sam3DualViTDetNeck(nn.Module, NativePlanMixin):
         return plan
 
     @staticmethod
+    def _run_branch_strict(seq, scale, x):  # x: [B,h,w,C] fp32 NHWC; strict precision mode (fp32 kernels, raw parameters)
+        f = lambda t: t.detach().float().contiguous()
+        if scale == 4.0:
+            x = ops.convt2x2_f32(x, f(seq.dconv_2x2_0.weight), f(seq.dconv_2x2_0.bias), act="gelu")
+            x = ops.convt2x2_f32(x, f(seq.dconv_2x2_1.weight), f(seq.dconv_2x2_1.bias))
+        elif scale == 2.0:
+            x = ops.convt2x2_f32(x, f(seq.dconv_2x2.weight), f(seq.dconv_2x2.bias))
+        elif scale == 0.5:
+            raise NotImplementedError("strict precision mode: the 0.5x FPN level (MaxPool) is dropped by scalp=1 and not built")
+        y = ops.conv2d_f32(x, f(seq.conv_1x1.weight), 1, 0, bias=f(seq.conv_1x1.bias))
+        return ops.conv2d_f32(y, f(seq.conv_3x3.weight), 1, 1, bias=f(seq.conv_3x3.bias))
+
+    @staticmethod
     def _run_branch(bp, x, out_dtype=torch.bfloat16):  # x: [B,h,w,C] bf16 NHWC
         s = bp["scale"]
         if s == 4.0:
@@ -80,6 +93,9 @@ class Sam3DualViTDetNeck(nn.Module, NativePlanMixin):
         """Fast path: trunk feature map [B,h,w,C] bf16 NHWC -> list of NHWC levels of one branch (bf16; fp32 for
         the levels listed in f32_levels)."""
         self._require_eval("Sam3DualViTDetNeck.forward")
+        if ops.precision() == "strict":
+            seqs = self.convs if branch == "sam3" else self.sam2_convs
+            return [self._run_branch_strict(seqs[i], self.scale_factors[i], feats_nhwc.float()) for i in levels]
         plan = self._plan()[branch]
         return [self._run_branch(plan[i], feats_nhwc, torch.float32 if i in f32_levels else torch.bfloat16) for i in levels]
 
@@ -88,8 +104,15 @@ class Sam3DualViTDetNeck(nn.Module, NativePlanMixin):
         """Reference contract (necks.py:100-125): images -> (sam3_out, sam3_pos, sam2_out, sam2_pos), NCHW fp32 maps.
         Positional encodings are returned as None (they feed the detector / tracker memory, not this path)."""
         xs = self.trunk(tensor_list)
-        x = ops.nchw_f32_to_nhwc(xs[-1])
         n = len(self.scale_factors)
+        if ops.precision() == "strict":      # fp32 NHWC stream; the 0.5x level is not built in this mode (scalp=1 drops it)
+            x = xs[-1].float().permute(0, 2, 3, 1).contiguous()
+            lv = [i for i, sc in enumerate(self.scale_factors) if sc != 0.5]
+            nchw = lambda ts: [t.permute(0, 3, 1, 2).contiguous() for t in ts]
+            s3 = nchw(self.forward_nhwc(x, "sam3", lv))
+            s2 = nchw(self.forward_nhwc(x, "sam2", lv)) if self.sam2_convs is not None else None
+            return s3, [None] * len(lv), s2, ([None] * len(lv) if s2 is not None else None)
+        x = ops.nchw_f32_to_nhwc(xs[-1])
         s3 = [ops.nhwc_to_nchw_f32(t) for t in self.forward_nhwc(x, "sam3", range(n))]
         s2 = [ops.nhwc_to_nchw_f32(t) for t in self.forward_nhwc(x, "sam2", range(n))] if self.sam2_convs is not None else None
         return s3, [None] * n, s2, ([None] * n if s2 is not None else None)

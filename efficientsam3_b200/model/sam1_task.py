@@ -59,6 +59,10 @@ class Sam3PointPromptSegmenter(nn.Module):
     def set_image_batch(self, images: torch.Tensor):
         """images [B,3,S,S] fp32 CUDA, already resized / normalised (mean 0.5, std 0.5 as Sam3Processor does)."""
         neck = self.backbone.vision_backbone
+        strict = ops.precision() == "strict"
+        if strict and hasattr(neck.trunk, "forward_tokens"):
+            raise NotImplementedError("strict precision mode covers the EfficientViT student encoder, the FPN neck and the SAM heads; "
+                                      "the SAM3 ViT trunk runs in the bf16 mode only")
         if hasattr(neck.trunk, "forward_tokens"):       # SAM3 ViT trunk: fp32 token stream -> bf16 NHWC
             tok, (B, h, w) = neck.trunk.forward_tokens(images)
             feats = ops.add_rows(tok, None, out_bf16=True, out_f32=False)[0].view(B, h, w, -1)
@@ -71,7 +75,9 @@ class Sam3PointPromptSegmenter(nn.Module):
         # image_embed = 72^2 level + no_mem_embed (sam1_task_predictor.py:157) + no_mask dense embedding (mask_decoder.py:189)
         addc = (self.no_mem_embed.detach().reshape(-1) + self.sam_prompt_encoder.no_mask_embed.weight.detach().reshape(-1)).float().contiguous()
         C = l72.shape[-1]
-        keys_b16, keys_f32 = ops.add_rows(l72.view(-1, C), addc.view(1, C), out_bf16=True, out_f32=True)
+        keys_b16, keys_f32 = ops.add_rows(l72.view(-1, C), addc.view(1, C), out_bf16=not strict, out_f32=True)
+        if strict:
+            keys_b16 = keys_f32
         # the same level with no_mem_embed only: the base a mask prompt's dense embedding is added to
         _, base_f32 = ops.add_rows(l72.view(-1, C), self.no_mem_embed.detach().reshape(1, C).float().contiguous(), out_f32=True)
         self._features = dict(B=B, h=h, w=w, keys_f32=keys_f32, keys_b16=keys_b16, base_f32=base_f32, feat_s0=feat_s0,
@@ -104,7 +110,9 @@ class Sam3PointPromptSegmenter(nn.Module):
         if mask_input is not None:
             assert mask_input.shape[0] == P and tuple(mask_input.shape[1:]) == (1, 4 * h, 4 * w), tuple(mask_input.shape)
             wts, eps = pe.mask_weights()
-            kb, kf = ops.mask_downscale_tokens(mask_input.float(), wts, f["base_f32"][sl].contiguous(), eps)
+            kb, kf = ops.mask_downscale_tokens(mask_input.float(), wts, f["base_f32"][sl].contiguous(), eps,
+                                               out_bf16=ops.precision() != "strict")
+            kb = kf if kb is None else kb
         else:
             kf = f["keys_f32"][sl].unsqueeze(0).expand(P, -1, -1).reshape(P * hw, -1)
             kb = f["keys_b16"][sl].unsqueeze(0).expand(P, -1, -1).reshape(P * hw, -1)

@@ -73,6 +73,8 @@ class ListWrapper(nn.Module):
 
     def forward_nhwc(self, x):
         """[B,3,S,S] fp32 -> [B,72,72,1024] bf16 NHWC for Sam3DualViTDetNeck.forward_nhwc."""
+        if ops.precision() == "strict":      # fp32 NHWC stream for the strict neck / heads (layout change only)
+            return self.model(x).permute(0, 2, 3, 1).contiguous()
         return ops.nchw_f32_to_nhwc(self.model(x))
 
 

@@ -79,7 +79,8 @@ class NativePlanMixin:
     """Caches packed / folded weights; rebuilds when parameters, device or mode change."""
 
     def _plan(self):
-        key = (params_fingerprint(self), self.training)
+        from . import ops
+        key = (params_fingerprint(self), self.training, ops.precision())
         if getattr(self, "_plan_key", None) != key:
             self._plan_cache = self._build_plan()
             self._plan_key = key
@@ -88,6 +89,5 @@ class NativePlanMixin:
     def _require_eval(self, what: str):
         if self.training:
             raise NotImplementedError(
-                f"{what}: the native sm_100a path implements eval-mode forward only in this round "
-                "(BatchNorm batch statistics + backward are the next scope row; see DESIGN.md). "
-                "Call .eval() first.")
+                f"{what}: this module's native sm_100a path is eval-mode only (train-mode forward / backward exist for the "
+                "stage-1 student encoders: ImageStudentEncoder; see DESIGN.md).  Call .eval() first.")

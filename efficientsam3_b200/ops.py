@@ -112,6 +112,9 @@ def _ensure_init(t: torch.Tensor):
     _lib.init(t.device.index or 0)
 
 
+PW_SMALL = True    # K, N <= 64 plain pointwise GEMMs on es3_pw_small_bf16 (CUDA cores, HBM-bound) instead of 128-row tcgen05 tiles
+
+
 def gemm(a, w, *, scale=None, bias=None, act=None, residual=None, out=None, out_dtype=torch.bfloat16, bn_hint=0,
          rope=None, act_after_res=False):
     """out[m,n] = act(scale[n]*sum_k a[m,k] w[n,k] + bias[n]) (+residual).  a: [M,K] (row stride allowed),
@@ -131,6 +134,22 @@ def gemm(a, w, *, scale=None, bias=None, act=None, residual=None, out=None, out_
         assert residual.is_cuda and residual.dtype in (torch.bfloat16, torch.float32)
         assert residual.stride(1) == 1 and residual.shape == (M, N)
         res_f32 = int(residual.dtype == torch.float32)
+    if (PW_SMALL and K <= 64 and N <= 64 and scale is None and bias is None and act in (None, "none") and rope is None
+            and out.dtype == torch.bfloat16 and (residual is None or residual.dtype == torch.bfloat16)):
+        # 16..64-channel pointwise convs of stages 0-1 (and their input gradients): one thread per pixel row (pw_small.cu)
+        global launch_count
+        prof = _profiler
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rc = _lib.call_rc("es3_pw_small_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
+                          _ptr(residual), residual.stride(0) if residual is not None else 0, M, N, K, _stream())
+        if rc == 0:
+            launch_count += 1
+            if prof is not None:
+                e1.record()
+                prof.records.append((f"pw_small[K={K},N={N}]", e0, e1, M * K * 2 + M * N * 2 + _nb(w, residual), 2 * M * N * K))
+            return out
     if rope is not None:
         tab, rcols, rH, rW, rwin = rope
         _chk(tab, torch.float32, "rope table")
@@ -835,6 +854,9 @@ def add_bf16(a, b):
     return out
 
 
+WGRAD_TC = True    # 1x1-conv weight gradients with N % 64 == 0 and K % 64 == 0 on the tcgen05 split-K kernel (es3_wgrad_tc)
+
+
 def wgrad_pw(dz, x, dW, ldn=None, ldk=1, shift=None):
     """dW[n*ldn + k*ldk] += sum_m dz[m,n] x[m,k].  dz [M,N], x [M,K] bf16 (row strides allowed); dW fp32 (flat indexing
     from its data pointer).  shift = (H, W, dy, dx): x row of pixel (b,y,x) is (b,y+dy,x+dx), zero outside the map."""
@@ -843,6 +865,22 @@ def wgrad_pw(dz, x, dW, ldn=None, ldk=1, shift=None):
     assert dz.dim() == 2 and x.dim() == 2 and dz.stride(1) == 1 and x.stride(1) == 1 and dz.shape[0] == x.shape[0]
     M, N = dz.shape
     K = x.shape[1]
+    if WGRAD_TC and shift is None and ldk == 1 and N % 64 == 0 and K % 64 == 0 and M >= 64:
+        # dense contraction over the pixel index: split-K UMMA with both operands MN-major (wgrad_tc.cu)
+        global launch_count
+        ws = _f32ws(_lib.size("es3_wgrad_tc_ws_floats", M, N, K), dz.device)
+        prof = _profiler
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rc = _lib.call_rc("es3_wgrad_tc", dz.data_ptr(), dz.stride(0), x.data_ptr(), x.stride(0), M, N, K, ws.data_ptr(), dW.data_ptr(),
+                          K if ldn is None else ldn, _stream())
+        if rc == 0:
+            launch_count += 2
+            if prof is not None:
+                e1.record()
+                prof.records.append((f"wgrad_tc[N={N},K={K}]", e0, e1, M * (N + K) * 2, 2 * M * N * K))
+            return dW
     H, W, dy, dx = shift if shift is not None else (0, 0, 0, 0)
     ws = _f32ws(_lib.size("es3_wgrad_pw_ws_floats", M, N, K), dz.device)
     _call("es3_wgrad_pw", f"wgrad_pw[N={N},K={K}]", M * (N + K) * 2, 2 * M * N * K, dz.data_ptr(), dz.stride(0), x.data_ptr(),

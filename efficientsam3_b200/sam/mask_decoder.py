@@ -74,16 +74,21 @@ class MaskDecoder(nn.Module, NativePlanMixin):
 
     def _build_plan(self):
         dc1, ln1, _, dc2, _ = self.output_upscaling
+        strict = ops.precision() == "strict"
+        wdt = torch.float32 if strict else torch.bfloat16
         return dict(
+            strict=strict,
+            dc1_raw=(dc1.weight.detach().float().contiguous(), dc1.bias.detach().float().contiguous()),
+            dc2_raw=(dc2.weight.detach().float().contiguous(), dc2.bias.detach().float().contiguous()),
             out_tok=torch.cat([self.obj_score_token.weight, self.iou_token.weight, self.mask_tokens.weight], 0).detach().float().contiguous(),
             dc1=(ops.convt2x2_weight(dc1.weight), dc1.bias.detach().float().repeat(4).contiguous()),
             ln1=(ln1.weight.detach().float().contiguous(), ln1.bias.detach().float().contiguous(), ln1.eps),
             dc2=(ops.convt2x2_weight(dc2.weight), dc2.bias.detach().float().repeat(4).contiguous()),
             hyper=[_mlp_plan(m) for m in self.output_hypernetworks_mlps], iou=_mlp_plan(self.iou_prediction_head),
             obj=_mlp_plan(self.pred_obj_score_head),
-            s0=(self.conv_s0.weight.detach().reshape(self.conv_s0.out_channels, -1).to(torch.bfloat16).contiguous(),
+            s0=(self.conv_s0.weight.detach().reshape(self.conv_s0.out_channels, -1).to(wdt).contiguous(),
                 self.conv_s0.bias.detach().float().contiguous()),
-            s1=(self.conv_s1.weight.detach().reshape(self.conv_s1.out_channels, -1).to(torch.bfloat16).contiguous(),
+            s1=(self.conv_s1.weight.detach().reshape(self.conv_s1.out_channels, -1).to(wdt).contiguous(),
                 self.conv_s1.bias.detach().float().contiguous()))
 
     @torch.no_grad()
@@ -94,7 +99,10 @@ class MaskDecoder(nn.Module, NativePlanMixin):
         out = []
         for x, (w, b) in ((feat_s0_nhwc, p["s0"]), (feat_s1_nhwc, p["s1"])):
             B, H, W, C = x.shape
-            out.append(ops.gemm(x.view(-1, C), w, bias=b, out_dtype=torch.float32).view(B, H, W, -1))
+            if p["strict"]:
+                out.append(ops.sgemm(x.float().view(-1, C), w, bias=b).view(B, H, W, -1))
+            else:
+                out.append(ops.gemm(x.view(-1, C), w, bias=b, out_dtype=torch.float32).view(B, H, W, -1))
         return out
 
     @torch.no_grad()
@@ -108,10 +116,15 @@ class MaskDecoder(nn.Module, NativePlanMixin):
         hs, kf, kb = self.transformer.run_tokens(keys_f32, keys_b16, key_pe_tokens, tokens, B)
         iou_tok = hs[:, 1].contiguous()
         mask_toks = hs[:, 2:2 + self.num_mask_tokens]
-        up1 = ops.convt2x2(kb.view(B, h, w, C), p["dc1"][0], bias4=p["dc1"][1], residual=feat_s1, out_dtype=torch.float32)
-        up1 = ops.ln_rows_gelu(up1.view(-1, C // 4), *p["ln1"]).view(B, 2 * h, 2 * w, C // 4)
-        up2 = ops.convt2x2(up1, p["dc2"][0], bias4=p["dc2"][1], act="gelu", residual=feat_s0, out_dtype=torch.float32,
-                           act_after_res=True)
+        if p["strict"]:      # fp32 image stream (kf is what run_tokens returned as kb as well)
+            up1 = ops.convt2x2_f32(kf.view(B, h, w, C), p["dc1_raw"][0], p["dc1_raw"][1], residual=feat_s1)
+            up1 = ops.ln_rows_gelu_f32(up1.view(-1, C // 4), *p["ln1"]).view(B, 2 * h, 2 * w, C // 4)
+            up2 = ops.convt2x2_f32(up1, p["dc2_raw"][0], p["dc2_raw"][1], act="gelu", residual=feat_s0, act_after_res=True)
+        else:
+            up1 = ops.convt2x2(kb.view(B, h, w, C), p["dc1"][0], bias4=p["dc1"][1], residual=feat_s1, out_dtype=torch.float32)
+            up1 = ops.ln_rows_gelu(up1.view(-1, C // 4), *p["ln1"]).view(B, 2 * h, 2 * w, C // 4)
+            up2 = ops.convt2x2(up1, p["dc2"][0], bias4=p["dc2"][1], act="gelu", residual=feat_s0, out_dtype=torch.float32,
+                               act_after_res=True)
         hyper = torch.stack([_run_mlp(p["hyper"][i], mask_toks[:, i].contiguous()) for i in range(self.num_mask_tokens)], 1)
         iou = _run_mlp(p["iou"], iou_tok)
         obj = _run_mlp(p["obj"], hs[:, 0].contiguous())

@@ -54,7 +54,18 @@ def _f32(lin: nn.Linear):
 
 
 def _b16(lin: nn.Linear):
+    """Weights of a projection over the 5184 image tokens: bf16 for the tcgen05 GEMM, fp32 in the strict precision mode."""
+    if ops.precision() == "strict":
+        return _f32(lin)
     return lin.weight.detach().to(torch.bfloat16).contiguous(), lin.bias.detach().float().contiguous()
+
+
+def _img_gemm(x, wb, **kw):
+    """Image-token projection: es3_gemm_bf16 on bf16 operands, es3_sgemm_f32 on fp32 operands (strict mode)."""
+    if wb[0].dtype == torch.float32:
+        kw.pop("out_dtype", None)
+        return ops.sgemm(x, wb[0], bias=wb[1], **kw)
+    return ops.gemm(x, wb[0], bias=wb[1], **kw)
 
 
 def _ln(n: nn.LayerNorm):
@@ -107,10 +118,19 @@ class TwoWayTransformer(nn.Module, NativePlanMixin):
         def token_to_image(a, queries, k_in_b16, keys_b16):
             qq = ops.add_rows(queries, q_pe)[1]
             q = lin(qq, a["q"]).view(B, T, -1)
-            k = ops.gemm(k_in_b16, a["k"][0], bias=a["k"][1]).view(B, HW, -1)
-            v = ops.gemm(keys_b16, a["v"][0], bias=a["v"][1]).view(B, HW, -1)
+            k = _img_gemm(k_in_b16, a["k"]).view(B, HW, -1)
+            v = _img_gemm(keys_b16, a["v"]).view(B, HW, -1)
             o = ops.attn_few_queries(q, k, v, H, a["scale"]).view(B * T, -1)
             return lin(o, a["o"], residual=queries)
+
+        strict = ops.precision() == "strict"       # fp32 image stream: the "b16" operands below ARE the fp32 tensors
+        if strict:
+            keys_b16 = keys_f32
+
+        def key_in():
+            if strict:
+                return ops.add_rows(keys_f32, key_pe)[1]
+            return ops.add_rows(keys_f32, key_pe, out_bf16=True, out_f32=False)[0]
 
         for lp in p["layers"]:
             sa = lp["sa"]
@@ -126,7 +146,7 @@ class TwoWayTransformer(nn.Module, NativePlanMixin):
             o = ops.attn_few_queries(q, k, v, H, sa["scale"]).view(B * T, -1)
             queries = ln(lin(o, sa["o"], residual=res), lp["n1"])
             # token -> image
-            k_in_b16 = ops.add_rows(keys_f32, key_pe, out_bf16=True, out_f32=False)[0]
+            k_in_b16 = key_in()
             queries = ln(token_to_image(lp["t2i"], queries, k_in_b16, keys_b16), lp["n2"])
             # mlp
             hdn = lin(queries, lp["l1"], act=lp["act"])
@@ -136,11 +156,13 @@ class TwoWayTransformer(nn.Module, NativePlanMixin):
             qq = ops.add_rows(queries, q_pe)[1]
             kt = lin(qq, a["k"]).view(B, T, -1)
             vt = lin(queries, a["v"]).view(B, T, -1)
-            qi = ops.gemm(k_in_b16, a["q"][0], bias=a["q"][1])
-            att = ops.attn_few_keys(qi, kt, vt, B, H, a["scale"])
-            kx = ops.gemm(att, a["o"][0], bias=a["o"][1], residual=keys_f32, out_dtype=torch.float32)
-            keys_b16, keys_f32 = ops.layernorm(kx, *lp["n4"], out_bf16=True, out_f32=True)
-        k_in_b16 = ops.add_rows(keys_f32, key_pe, out_bf16=True, out_f32=False)[0]
+            qi = _img_gemm(k_in_b16, a["q"])
+            att = (ops.attn_few_keys_f32 if strict else ops.attn_few_keys)(qi, kt, vt, B, H, a["scale"])
+            kx = _img_gemm(att, a["o"], residual=keys_f32, out_dtype=torch.float32)
+            keys_b16, keys_f32 = ops.layernorm(kx, *lp["n4"], out_bf16=not strict, out_f32=True)
+            if strict:
+                keys_b16 = keys_f32
+        k_in_b16 = key_in()
         queries = ln(token_to_image(p["final"], queries, k_in_b16, keys_b16), p["nf"])
         return queries.view(B, T, C), keys_f32, keys_b16
 

@@ -51,6 +51,9 @@ class ImageStudentEncoder(nn.Module, NativePlanMixin):
         if self.training:
             return self._forward_train(x)
         with torch.no_grad():
+            if ops.precision() == "strict":           # fp32 activations / weights / accumulation (strict.py, csrc/strict_f32.cu)
+                from ..strict import student_forward
+                return student_forward(self, x)
             if self._graphs is not None and x.is_cuda:
                 return self._forward_graphed(x)
             return self._forward_eval(x)
@@ -100,8 +103,8 @@ class ImageStudentEncoder(nn.Module, NativePlanMixin):
         BN modules, set_bn_state), backward on the kernels of train_bwd.cu.  Built for all nine students (EfficientViT b0 / b1 / b2, RepViT m0_9 / m1_1 / m2_3, TinyViT 5m / 11m / 21m)."""
         if not isinstance(self.backbone, (EfficientViTAdapter, RepViTAdapter, TinyViTAdapter)):
             raise NotImplementedError(
-                "train-mode forward/backward is built for the EfficientViT, RepViT and TinyViT "
-                f"students; {type(self.backbone).__name__} is eval-only (see DESIGN.md).  Call .eval() first.")
+                "train-mode forward / backward is built for the nine students of the reference builder (EfficientViT, RepViT, "
+                f"TinyViT adapters); {type(self.backbone).__name__} is eval-only.  Call .eval() first.")
         params = [p for p in self.parameters()]
         return StudentTrainFunction.apply(self, x, *params)
 

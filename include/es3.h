@@ -363,6 +363,18 @@ long long es3_litemla_bwd_ws_floats(int B, int HW, int heads2);
 int es3_litemla_attn_bwd(const void* ms, long long ld, const void* dy, long long lddy, const float* kv_part, int nchunk_f,
                          float* dkv_ws, void* dms, long long lddms, int B, int HW, int heads2, float eps, void* stream);
 
+/* Narrow pointwise conv / its input gradient on the CUDA cores (pw_small.cu): out[m][n] = sum_k a[m][k] w[n][k] (+ residual), bf16 in /
+ * out, fp32 accumulation, K, N in {16, 32, 64} (not both 64).  Returns -1 without setting an error for any other shape / alignment:
+ * callers fall back to es3_gemm_bf16 (efficientvit/nn/ops.py:273-367, the 16..64-channel 1x1 convs of stages 0-1). */
+int es3_pw_small_bf16(const void* a, long long lda, const void* w, long long ldw, void* out, long long ldo, const void* residual,
+                      long long ldr, long long M, int N, int K, void* stream);
+/* Weight gradient of pointwise convs / linears on tcgen05 (wgrad_tc.cu): dW[n * ldn + k] += sum_m dz[m * lddz + n] * x[m * ldx + k]
+ * as a split-K UMMA with both operands MN-major (TMA tiles of [64 px][64 ch] are the transposed operand layout), deterministic
+ * two-stage sum.  Returns -1 without setting an error for shapes it does not take (N or K not multiples of 64, M < 64, unaligned
+ * strides): callers fall back to es3_wgrad_pw.  ws: es3_wgrad_tc_ws_floats(M, N, K) floats. */
+long long es3_wgrad_tc_ws_floats(long long M, int N, int K);
+int es3_wgrad_tc(const void* dz, long long lddz, const void* x, long long ldx, long long M, int N, int K, float* ws, float* dW,
+                 long long ldn, void* stream);
 /* ---- strict (fp32-class) precision mode (strict_f32.cu): fp32 activations / weights / FMA accumulation on the CUDA cores, the
  * parity mode for north_star's tolerances (embeddings rtol 1e-4, mask logits rtol 1e-3, binary masks bit-exact) against the
  * reference's PyTorch fp32 path (its LiteMLA is forced to fp32: efficientvit/nn/ops.py:586-589).  Same epilogue contract as

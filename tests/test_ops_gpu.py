@@ -76,6 +76,29 @@ def test_gemm_tc(cuda, M, N, K, act, res, out_f32, bn):
     _close(out2, ref, 2e-3, "gemm_simt")
 
 
+@pytest.mark.parametrize("K,N", [(16, 16), (16, 32), (16, 64), (32, 16), (32, 32), (32, 64), (64, 16), (64, 32)])
+@pytest.mark.parametrize("M,res", [(1, False), (4099, True), (70000, False)])
+def test_pw_small(cuda, K, N, M, res):
+    """Narrow pointwise GEMMs (K, N <= 64) on es3_pw_small_bf16: against fp32, and against the tcgen05 kernel on the same operands."""
+    from efficientsam3_b200 import ops
+    g = torch.Generator().manual_seed(M + 3 * K + N)
+    big = _bf(torch.randn(M, K + 8, generator=g)).to(cuda)
+    a = big[:, :K]                                                  # row-strided operand view
+    w = _bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda)
+    r = _bf(torch.randn(M, N, generator=g)).to(cuda) if res else None
+    n0 = ops.launch_count
+    out = ops.gemm(a, w, residual=r)
+    assert ops.launch_count == n0 + 1
+    ref = a.float() @ w.float().t() + (r.float() if res else 0)
+    _close(out, ref, 1e-2, f"pw_small {M}x{N}x{K}")
+    ops.PW_SMALL = False
+    try:
+        tc = ops.gemm(a, w, residual=r)
+    finally:
+        ops.PW_SMALL = True
+    assert (out.float() - tc.float()).abs().max().item() <= 2 ** -7 * ref.abs().max().item()      # same rounding points: <= 1 bf16 ulp apart
+
+
 def test_gemm_strided_views(cuda):
     """A is a channel slice of a wider buffer; out is written into a slice (the LiteMLA qkv layout)."""
     from efficientsam3_b200 import ops

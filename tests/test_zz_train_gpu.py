@@ -128,6 +128,34 @@ def test_wgrad_pw(cuda, M, N, K):
     _close(dW, dW_ref, 2e-3, f"wgrad_pw {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("M,N,K,ldz,ldx", [(64, 64, 64, 64, 64), (5000, 128, 64, 128, 64), (4099, 256, 512, 256, 512), (20000, 1024, 256, 1024, 256),
+                                           (3000, 64, 256, 200, 264), (777, 192, 320, 192, 320), (100000, 384, 128, 768, 128), (1500, 512, 1024, 512, 1024)])
+def test_wgrad_tc(cuda, M, N, K, ldz, ldx):
+    """The tcgen05 split-K weight-gradient kernel (both operands MN-major) against the fp32 statement, incl. strided operand views,
+    ragged pixel counts, tiles wider than the matrix, accumulation into a pre-filled dW, and bit-reproducibility."""
+    from efficientsam3_b200 import ops, _lib
+    g = _g(M + N + K)
+    dzb, xb = _bf(torch.randn(M, ldz, generator=g)), _bf(torch.randn(M, ldx, generator=g))
+    dz, x = dzb[:, ldz - N:], xb[:, :K]
+    ref = torch.full((N, K), 0.25)
+    E.wgrad_pw(dz, x, ref)
+    outs = []
+    for _ in range(2):
+        dW = torch.full((N, K), 0.25, device=cuda)
+        dzd, xd = dzb.to(cuda)[:, ldz - N:], xb.to(cuda)[:, :K]
+        ws = torch.empty(_lib.size("es3_wgrad_tc_ws_floats", M, N, K), device=cuda)
+        rc = _lib.call_rc("es3_wgrad_tc", dzd.data_ptr(), dzd.stride(0), xd.data_ptr(), xd.stride(0), M, N, K, ws.data_ptr(), dW.data_ptr(), K,
+                          torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        outs.append(dW)
+    _close(outs[0], ref, 2e-3, f"wgrad_tc {M}x{N}x{K}")
+    assert torch.equal(outs[0], outs[1])
+    # and the same shapes through the public op (which routes here)
+    dW = torch.full((N, K), 0.25, device=cuda)
+    ops.wgrad_pw(dzb.to(cuda)[:, ldz - N:], xb.to(cuda)[:, :K], dW)
+    assert torch.equal(dW, outs[0])
+
+
 def test_wgrad_pw_strided_operands(cuda):
     """dz is a channel slice of the LiteMLA gradient buffer (row stride 2*c3)."""
     from efficientsam3_b200 import ops
