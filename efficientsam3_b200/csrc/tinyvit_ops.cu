@@ -5,6 +5,8 @@
 //     head_dim 32, N = ws*ws in {49, 196}.  One CTA per (window, head): S = QK^T on mma.sync with the whole
 //     score row block in registers, + bias, softmax, PV on mma.sync.
 //   * LayerNorm over bf16 rows with arbitrary C % 8 == 0 (C = 448 is not a multiple of 128).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace es3 {
@@ -39,19 +41,36 @@ struct WinAttnArgs {
 // NT16 = ceil(N / 16): number of 16-row tiles (4 for N=49, 13 for N=196).  The query tiles of a window are split over
 // gridDim.z CTAs of blockDim/32 warps each (the 26x4 score registers per thread cap a CTA at ~7 warps); every CTA
 // stages the whole window's K / V.
-template <int NT16>
-__global__ void win_attn_bias_kernel(const WinAttnArgs a) {
+//
+// PERSIST (the 14 x 14 windows, N = 196): round 1 launched one CTA per (window, head, half of the query tiles) and every thread
+// fetched its 104 + 104 bias values with scalar loads -- 88 KB of L2 traffic and ~26 dependent load batches per CTA, 1.14 ms per
+// launch at 23 TFLOP/s (profiles/r2c_table_tiny_vit_11m.md).  Here a CTA of NT16 warps keeps ONE head: the head's bias table sits in
+// shared memory as fp16 (196 rows x 200: the pad makes the (row g, column pair t4) reads conflict-free; fp16 keeps 11 bits of a
+// |b| < 8 table, finer than the bf16 rounding of P that follows), loaded once, and the CTA walks the windows
+// blockIdx.x, blockIdx.x + gridDim.x, ...
+constexpr int WA_BLD = 200;     // fp16 elements per bias row in shared memory
+
+template <int NT16, bool PERSIST>
+__global__ void __launch_bounds__(NT16 * 32 > 256 ? NT16 * 32 : 256) win_attn_bias_kernel(const WinAttnArgs a, const int total_windows) {
   constexpr int NP = NT16 * 16;
   extern __shared__ __align__(16) uint8_t smem[];
   uint8_t* s_q = smem;
   uint8_t* s_k = s_q + NP * WA_RS;
   uint8_t* s_v = s_k + NP * WA_RS;
+  const __half* s_bias = reinterpret_cast<const __half*>(s_v + NP * WA_RS);      // PERSIST only: [N][WA_BLD]
   const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = blockIdx.z * (blockDim.x >> 5) + (tid >> 5);   // query tile handled by this warp
+  const int warp = PERSIST ? (tid >> 5) : blockIdx.z * (blockDim.x >> 5) + (tid >> 5);   // query tile handled by this warp
   const int head = blockIdx.y;
-  const int b = blockIdx.x / a.nWin, wi = blockIdx.x % a.nWin;
-  const int wy = wi / a.nWx, wx = wi % a.nWx;
   const int ld = 3 * a.C;
+  if (PERSIST) {
+    __half* sb = const_cast<__half*>(s_bias);
+    const float* src = a.bias + (long long)head * a.N * a.N;
+    for (int i = tid; i < a.N * a.N; i += blockDim.x) sb[(i / a.N) * WA_BLD + (i % a.N)] = __float2half_rn(src[i]);
+  }
+  for (int win = blockIdx.x; win < total_windows; win += (PERSIST ? (int)gridDim.x : total_windows)) {
+  if (PERSIST) __syncthreads();        // the previous window's tiles are no longer read (and the bias table is complete)
+  const int b = win / a.nWin, wi = win % a.nWin;
+  const int wy = wi / a.nWx, wx = wi % a.nWx;
   // ---- gather q, k, v rows of this window / head (4 x 16-byte chunks each); rows >= N are zero
   for (int i = tid; i < NP * 12; i += blockDim.x) {
     const int c = i % 12, r = i / 12;         // c: 0..3 q, 4..7 k, 8..11 v
@@ -65,7 +84,7 @@ __global__ void win_attn_bias_kernel(const WinAttnArgs a) {
     *reinterpret_cast<uint4*>(dst) = val;
   }
   __syncthreads();
-  if (warp >= NT16) return;
+  if (warp >= NT16) { if (PERSIST) continue; else return; }
   const uint32_t u_q = static_cast<uint32_t>(__cvta_generic_to_shared(s_q));
   const uint32_t u_k = static_cast<uint32_t>(__cvta_generic_to_shared(s_k));
   const uint32_t u_v = static_cast<uint32_t>(__cvta_generic_to_shared(s_v));
@@ -96,15 +115,27 @@ __global__ void win_attn_bias_kernel(const WinAttnArgs a) {
   const int r0 = warp * 16 + g, r1 = r0 + 8;
   const float* bias0 = a.bias + ((long long)head * a.N + min(r0, a.N - 1)) * a.N;
   const float* bias1 = a.bias + ((long long)head * a.N + min(r1, a.N - 1)) * a.N;
+  const __half* sb0 = s_bias + min(r0, a.N - 1) * WA_BLD;
+  const __half* sb1 = s_bias + min(r1, a.N - 1) * WA_BLD;
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int nt = 0; nt < 2 * NT16; ++nt) {
+    const int c0 = nt * 8 + t4 * 2;
+    float2 bb0 = make_float2(0.f, 0.f), bb1 = make_float2(0.f, 0.f);
+    if (c0 < a.N) {
+      if (PERSIST) {
+        bb0 = __half22float2(*reinterpret_cast<const __half2*>(sb0 + c0));
+        bb1 = __half22float2(*reinterpret_cast<const __half2*>(sb1 + c0));
+      } else {       // N = 49: rows are 196 B apart (4-byte aligned only) and the last column pair is half outside
+        bb0.x = __ldg(bias0 + c0); bb1.x = __ldg(bias1 + c0);
+        if (c0 + 1 < a.N) { bb0.y = __ldg(bias0 + c0 + 1); bb1.y = __ldg(bias1 + c0 + 1); }
+      }
+    }
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int col = nt * 8 + t4 * 2 + e;
-      const bool ok = col < a.N;
-      const float v0 = ok ? fmaf(s[nt][e], a.scale, __ldg(bias0 + col)) : -INFINITY;
-      const float v1 = ok ? fmaf(s[nt][2 + e], a.scale, __ldg(bias1 + col)) : -INFINITY;
+      const bool ok = c0 + e < a.N;
+      const float v0 = ok ? fmaf(s[nt][e], a.scale, e ? bb0.y : bb0.x) : -INFINITY;
+      const float v1 = ok ? fmaf(s[nt][2 + e], a.scale, e ? bb1.y : bb1.x) : -INFINITY;
       s[nt][e] = v0; s[nt][2 + e] = v1;
       mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
     }
@@ -150,6 +181,7 @@ __global__ void win_attn_bias_kernel(const WinAttnArgs a) {
     for (int nt = 0; nt < 4; ++nt)
       *reinterpret_cast<uint32_t*>(dst + nt * 8 + t4 * 2) = pack_bf16x2(o[nt][half * 2] * inv, o[nt][half * 2 + 1] * inv);
   }
+  }   // windows
 }
 
 // LayerNorm over rows of bf16, C % 8 == 0, C <= 1024, values kept in registers.  A row is handled by L = min(32, pow2ceil(C / 8))
@@ -224,16 +256,20 @@ extern "C" int es3_win_attn_bias_bf16(const void* qkv, const void* qkv_pad, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (N == 49) {
     const size_t smem = (size_t)3 * 64 * WA_RS;
-    win_attn_bias_kernel<4><<<grid, 4 * 32, smem, st>>>(a);
+    win_attn_bias_kernel<4, false><<<grid, 4 * 32, smem, st>>>(a, B * a.nWin);
   } else {
-    const size_t smem = (size_t)3 * 208 * WA_RS;
-    static bool configured = false;
-    if (!configured) {
-      ES3_CHECK_CUDA(cudaFuncSetAttribute(win_attn_bias_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
+    const size_t smem = (size_t)3 * 208 * WA_RS + (size_t)N * WA_BLD * sizeof(__half);       // 49920 + 78400 B
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(win_attn_bias_kernel<13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int sm_count = 0;
+    if (sm_count == 0) {
+      int dev = 0;
+      ES3_CHECK_CUDA(cudaGetDevice(&dev));
+      ES3_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    grid.z = 2;
-    win_attn_bias_kernel<13><<<grid, 7 * 32, smem, st>>>(a);
+    int per_head = sm_count / num_heads;             // one CTA per SM (128 KB of shared memory), every CTA pinned to one head
+    if (per_head < 1) per_head = 1;
+    if (per_head > B * a.nWin) per_head = B * a.nWin;
+    win_attn_bias_kernel<13, true><<<dim3(per_head, num_heads), 13 * 32, smem, st>>>(a, B * a.nWin);
   }
   ES3_LAUNCH_CHECK("win_attn_bias_kernel");
   return 0;

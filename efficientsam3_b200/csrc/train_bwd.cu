@@ -951,6 +951,21 @@ __device__ __forceinline__ void sum_kv_partials(const float* __restrict__ src, i
   }
 }
 
+// The partial KV / dKV sums are reduced ONCE per (image, head) by this kernel (fixed chunk order); round 1 had every CTA of the two
+// kernels below re-sum all chunks from global memory (43 KB of L2 reads per CTA, 0.7 GB per launch at stage 3).
+__global__ void __launch_bounds__(288) litemla_sum_partials_kernel(const float* __restrict__ src, int nchunk, float* __restrict__ dst) {
+  const int i = threadIdx.x;
+  if (i >= 17 * 16) return;
+  const float* p = src + (long long)blockIdx.x * nchunk * 17 * 16 + i;
+  float a = 0.f;
+  for (int c = 0; c < nchunk; ++c) a += p[(long long)c * 17 * 16];
+  dst[(long long)blockIdx.x * 17 * 16 + i] = a;
+}
+
+__device__ __forceinline__ void load_kv_sum(const float* __restrict__ src, float* s_dst, int tid, int nthr) {
+  for (int i = tid; i < 17 * 16; i += nthr) s_dst[i] = src[i];
+}
+
 // do[0..16] for one token from q' (fp32, already relu'd), dy and KV
 __device__ __forceinline__ void token_do(const float* skv, const float* q, const float* dy, float eps, float* dof) {
   float o[17];
@@ -958,7 +973,10 @@ __device__ __forceinline__ void token_do(const float* skv, const float* q, const
   for (int j = 0; j < 17; ++j) {
     float a = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) a = fmaf(skv[j * 16 + i], q[i], a);
+    for (int i4 = 0; i4 < 4; ++i4) {       // warp-uniform 16-byte reads: one LDS.128 broadcast per four FMAs
+      const float4 w = *reinterpret_cast<const float4*>(skv + j * 16 + i4 * 4);
+      a = fmaf(w.x, q[i4 * 4], a); a = fmaf(w.y, q[i4 * 4 + 1], a); a = fmaf(w.z, q[i4 * 4 + 2], a); a = fmaf(w.w, q[i4 * 4 + 3], a);
+    }
     o[j] = a;
   }
   const float r = 1.f / (o[16] + eps);
@@ -975,12 +993,13 @@ __device__ __forceinline__ void token_do(const float* skv, const float* q, const
 __global__ void __launch_bounds__(288) litemla_dkv_kernel(const bf16* __restrict__ ms, long long ld, const bf16* __restrict__ dy,
                                                           long long lddy, const float* __restrict__ kv_part, int nchunk_f,
                                                           float* __restrict__ dkv_part, int HW, float eps) {
-  __shared__ float skv[17 * 16];
+  __shared__ __align__(16) float skv[17 * 16];
   __shared__ float s_q[LB_PX][17];
   __shared__ float s_do[LB_PX][17];
   const int tid = threadIdx.x;
   const int h = blockIdx.y, b = blockIdx.z, heads2 = gridDim.y;
-  sum_kv_partials(kv_part + ((long long)b * heads2 + h) * nchunk_f * 17 * 16, nchunk_f, skv, tid, 288);
+  load_kv_sum(kv_part + ((long long)b * heads2 + h) * 17 * 16, skv, tid, 288);       // kv_part: already summed over the chunks
+  (void)nchunk_f;
   __syncthreads();
   if (tid < LB_PX) {
     const int n = blockIdx.x * LB_PX + tid;
@@ -1017,41 +1036,61 @@ __global__ void __launch_bounds__(128) litemla_dqkv_kernel(const bf16* __restric
                                                            long long lddy, const float* __restrict__ kv_part, int nchunk_f,
                                                            const float* __restrict__ dkv_part, int nchunk_b, bf16* __restrict__ dms,
                                                            long long lddms, int HW, float eps) {
-  __shared__ float skv[17 * 16];
-  __shared__ float sdkv[17 * 16];
+  __shared__ __align__(16) float skv[17 * 16];      // KV [j][i]
+  __shared__ __align__(16) float sdkv[17 * 16];     // dKV [j][i]
+  __shared__ __align__(16) float skvT[16 * 20];     // KV^T [i][j], j padded 17 -> 20
+  __shared__ __align__(16) float sdkvT[16 * 20];    // dKV^T [i][j]
   const int tid = threadIdx.x;
   const int h = blockIdx.y, b = blockIdx.z, heads2 = gridDim.y;
-  sum_kv_partials(kv_part + ((long long)b * heads2 + h) * nchunk_f * 17 * 16, nchunk_f, skv, tid, 128);
-  sum_kv_partials(dkv_part + ((long long)b * heads2 + h) * nchunk_b * 17 * 16, nchunk_b, sdkv, tid, 128);
+  load_kv_sum(kv_part + ((long long)b * heads2 + h) * 17 * 16, skv, tid, 128);       // both already summed over their chunks
+  load_kv_sum(dkv_part + ((long long)b * heads2 + h) * 17 * 16, sdkv, tid, 128);
+  (void)nchunk_f; (void)nchunk_b;
+  __syncthreads();
+  for (int t = tid; t < 16 * 20; t += 128) {
+    const int i = t / 20, j = t % 20;
+    skvT[t] = j < 17 ? skv[j * 16 + i] : 0.f;
+    sdkvT[t] = j < 17 ? sdkv[j * 16 + i] : 0.f;
+  }
   __syncthreads();
   const int n = blockIdx.x * LB_PX + tid;
   if (n >= HW) return;
   const bf16* row = ms + ((long long)b * HW + n) * ld + h * 48;
-  float q[16], k[16], v[16], dyv[16], dof[17], qr[16];
+  float q[16], k[16], v[20], dyv[16], dof[20], qr[16];
   load16(row, q);
   load16(row + 16, k);
   load16(row + 32, v);
+  v[16] = 1.f; v[17] = v[18] = v[19] = 0.f;          // vpad = [v, 1] (+ zero pad to a multiple of 4)
   load16(dy + ((long long)b * HW + n) * lddy + h * 16, dyv);
 #pragma unroll
   for (int i = 0; i < 16; ++i) qr[i] = fmaxf(q[i], 0.f);
   token_do(skv, qr, dyv, eps, dof);
+  dof[17] = dof[18] = dof[19] = 0.f;
   float dq[16], dk[16], dv[16];
+  // every shared-memory operand below is one warp-uniform LDS.128 per four FMAs (round 1: one LDS.32 per FMA)
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    float a = 0.f;
+    float a = 0.f, c = 0.f;
 #pragma unroll
-    for (int j = 0; j < 17; ++j) a = fmaf(skv[j * 16 + i], dof[j], a);
+    for (int j4 = 0; j4 < 5; ++j4) {
+      const float4 w = *reinterpret_cast<const float4*>(skvT + i * 20 + j4 * 4);
+      const float4 d = *reinterpret_cast<const float4*>(sdkvT + i * 20 + j4 * 4);
+      a = fmaf(w.x, dof[j4 * 4], a); a = fmaf(w.y, dof[j4 * 4 + 1], a); a = fmaf(w.z, dof[j4 * 4 + 2], a); a = fmaf(w.w, dof[j4 * 4 + 3], a);
+      c = fmaf(d.x, v[j4 * 4], c); c = fmaf(d.y, v[j4 * 4 + 1], c); c = fmaf(d.z, v[j4 * 4 + 2], c); c = fmaf(d.w, v[j4 * 4 + 3], c);
+    }
     dq[i] = q[i] > 0.f ? a : 0.f;
-    float c = sdkv[16 * 16 + i];               // vpad[16] = 1
-#pragma unroll
-    for (int j = 0; j < 16; ++j) c = fmaf(v[j], sdkv[j * 16 + i], c);
     dk[i] = k[i] > 0.f ? c : 0.f;
   }
+  float kr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) kr[i] = fmaxf(k[i], 0.f);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     float a = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) a = fmaf(sdkv[j * 16 + i], fmaxf(k[i], 0.f), a);
+    for (int i4 = 0; i4 < 4; ++i4) {
+      const float4 d = *reinterpret_cast<const float4*>(sdkv + j * 16 + i4 * 4);
+      a = fmaf(d.x, kr[i4 * 4], a); a = fmaf(d.y, kr[i4 * 4 + 1], a); a = fmaf(d.z, kr[i4 * 4 + 2], a); a = fmaf(d.w, kr[i4 * 4 + 3], a);
+    }
     dv[j] = a;
   }
   uint4* o = reinterpret_cast<uint4*>(dms + ((long long)b * HW + n) * lddms + h * 48);
@@ -1442,7 +1481,8 @@ extern "C" int es3_bilinear_bwd(const float* dout, void* din, int B, int Hi, int
 }
 
 extern "C" long long es3_litemla_bwd_ws_floats(int B, int HW, int heads2) {
-  return (long long)B * heads2 * ceil_div(HW, LB_PX) * 17 * 16;
+  // dKV partials per 128-pixel chunk + the two chunk-summed tables (KV, dKV)
+  return (long long)B * heads2 * (ceil_div(HW, LB_PX) + 2) * 17 * 16;
 }
 
 /* kv_part: the [B][heads2][nchunk_f][17][16] partial KV sums es3_litemla_attn[_tc] left in its workspace
@@ -1456,9 +1496,17 @@ extern "C" int es3_litemla_attn_bwd(const void* ms, long long ld, const void* dy
   cudaStream_t st = (cudaStream_t)stream;
   const int nchunk_b = ceil_div(HW, LB_PX);
   dim3 grid(nchunk_b, heads2, B);
-  litemla_dkv_kernel<<<grid, 288, 0, st>>>((const bf16*)ms, ld, (const bf16*)dy, lddy, kv_part, nchunk_f, dkv_ws, HW, eps);
+  const int BH = B * heads2;
+  float* dkv_part = dkv_ws;
+  float* kv_sum = dkv_ws + (long long)BH * nchunk_b * 17 * 16;
+  float* dkv_sum = kv_sum + (long long)BH * 17 * 16;
+  litemla_sum_partials_kernel<<<BH, 288, 0, st>>>(kv_part, nchunk_f, kv_sum);
+  ES3_LAUNCH_CHECK("litemla_sum_partials_kernel");
+  litemla_dkv_kernel<<<grid, 288, 0, st>>>((const bf16*)ms, ld, (const bf16*)dy, lddy, kv_sum, nchunk_f, dkv_part, HW, eps);
   ES3_LAUNCH_CHECK("litemla_dkv_kernel");
-  litemla_dqkv_kernel<<<grid, 128, 0, st>>>((const bf16*)ms, ld, (const bf16*)dy, lddy, kv_part, nchunk_f, dkv_ws, nchunk_b, (bf16*)dms,
+  litemla_sum_partials_kernel<<<BH, 288, 0, st>>>(dkv_part, nchunk_b, dkv_sum);
+  ES3_LAUNCH_CHECK("litemla_sum_partials_kernel");
+  litemla_dqkv_kernel<<<grid, 128, 0, st>>>((const bf16*)ms, ld, (const bf16*)dy, lddy, kv_sum, nchunk_f, dkv_sum, nchunk_b, (bf16*)dms,
                                             lddms, HW, eps);
   ES3_LAUNCH_CHECK("litemla_dqkv_kernel");
   return 0;

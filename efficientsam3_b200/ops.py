@@ -777,7 +777,7 @@ def win_attn_bias(qkv, qkv_pad, bias, B, H, W, C, heads, ws, scale):
 # ------------------------------------------------------------------------------------ student backward (train_bwd.cu)
 BN_MODE = {"none": 0, "eval": 1, "batch": 2}
 KERNELS_PER_CALL.update({"es3_bn_stats": 2, "es3_bn_act_bwd_reduce": 2, "es3_wgrad_pw": 2, "es3_dwconv_wgrad": 2,
-                         "es3_stem_wgrad": 2, "es3_litemla_attn_bwd": 2, "es3_dwconv_wgrad_tiled": 2, "es3_se_bwd_dgate": 2,
+                         "es3_stem_wgrad": 2, "es3_litemla_attn_bwd": 4, "es3_dwconv_wgrad_tiled": 2, "es3_se_bwd_dgate": 2,
                          "es3_litemla_attn_bwd_generic": 2})
 
 
