@@ -254,7 +254,7 @@ class LiteMLAUnit:
 class LiteMLAGenericUnit:
     """x + LiteMLA(x) for head dims other than 16 (efficientvit_b2: 32), on the route the inference plan takes for them:
     depthwise 5x5 (es3_dwconv) + the grouped 1x1 as a block-diagonal tcgen05 GEMM + es3_litemla_attn_generic; backward through
-    es3_litemla_attn_bwd_generic.  (That backward kernel has had no GPU run yet -- litemla_bwd_generic.cu.)"""
+    es3_litemla_attn_bwd_generic (litemla_bwd_generic.cu)."""
 
     def __init__(self, m: LiteMLA):
         if m.dim not in (16, 32):

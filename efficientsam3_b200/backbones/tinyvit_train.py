@@ -12,7 +12,7 @@ by stage1.model.StudentTrainFunction.  Tokens [B, L, C] and NHWC maps [B, H, W, 
                                                       d attention_biases = scatter-add of the [heads, N, N] bias gradient over attention_bias_idxs
   DropPath (timm, tiny_vit.py:56-64)                  per-sample Bernoulli gate through es3_scale_channels (forward and backward)
 
-es3_layernorm_bwd and es3_win_attn_bias_bwd have had no GPU run yet (tinyvit_bwd.cu); the graph logic is checked in fp64 on CPU.
+GPU parity of the whole training step and of es3_layernorm_bwd / es3_win_attn_bias_bwd: tests/test_zz_train_gpu.py (green on a B200 since round 2); the graph logic is also checked in fp64 on CPU.
 """
 from __future__ import annotations
 

@@ -134,8 +134,10 @@ __device__ __forceinline__ void epi_load_rows(uint8_t* tile, uint4* mine, const 
 // Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so CTAs that
 // run together share the A row-block in L2).  The accumulator is double-buffered in TMEM (2 x BN columns):
 // the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
+// (min 2 CTAs/SM for BN <= 128: the GELU instantiations grew to 130-138 registers with the staged epilogue and silently dropped to one
+//  resident CTA -- TinyViT's fc1 GEMMs lost 13-30 %, gpurun_out/r2k_table_tvm.md)
 template <int BN, int STAGES, int ACT, int CPR>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(GEMM_THREADS, BN >= 256 ? 1 : 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const GemmArgs args, const int num_tiles) {
   // (no integer round trip on the pointer: the compiler keeps shared-space addressing for the staging tiles)

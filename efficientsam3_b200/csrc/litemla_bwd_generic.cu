@@ -4,8 +4,8 @@
 //   q' = relu(q), k' = relu(k), vpad = [v, 1];  KV[j][i] = sum_n vpad[n][j] k'[n][i];  o[n][j] = sum_i KV[j][i] q'[n][i];
 //   y[n][j] = o[n][j] / (o[n][DIM] + eps).   With r = 1 / (o[DIM] + eps):  do[j] = dy[j] r,  do[DIM] = -r sum_j dy[j] y[j];
 //   dKV[j][i] = sum_n do[n][j] q'[n][i];  dq'[i] = sum_j KV[j][i] do[j];  dv[j] = sum_i dKV[j][i] k'[i];  dk'[i] = sum_j vpad[j] dKV[j][i].
-// Thread per token, fp32, two-stage deterministic dKV reduction.  Written after the round-1 GPU budget was spent: no GPU run yet
-// (the efficientvit_b2 training graph that uses it is checked on CPU against the same formulas, tests/test_train_cpu.py).
+// Thread per token, fp32, two-stage deterministic dKV reduction.  GPU parity: tests/test_zz_train_gpu.py
+// (test_litemla_attn_bwd_generic, the efficientvit_b2 training step), green on a B200 since round 2.
 #include "common.cuh"
 
 namespace es3 {

@@ -4,10 +4,10 @@
 //                            gradient), dgamma += sum dy xhat, dbeta += sum dy
 //   es3_win_attn_bias_bwd    backward of es3_win_attn_bias_bf16 (Attention.forward :264-293 on window partitions) on a token map
 //                            whose extent is a multiple of the window: dqkv in the forward's [q|k|v]-per-head layout and the
-//                            per-window score gradients dS (bf16); the bias gradient is the column sum of dS over the windows
-// Correctness-first CUDA-core formulations (thread per row / per key, fixed-order reductions, no atomics).  Written after the
-// round-1 GPU budget was spent: the TinyViT training graph that uses them is exact on CPU against the same formulas
-// (tests/test_train_cpu.py), the kernels themselves have had no GPU run yet.
+//                            per-window score gradients dS (fp32); the bias gradient is the column sum of dS over the windows
+//                            (es3_colsum_f32, fixed order)
+// Correctness-first CUDA-core formulations (thread per row / per key, fixed-order reductions, no atomics).  GPU parity:
+// tests/test_zz_train_gpu.py (test_layernorm_bwd, test_win_attn_bias_bwd, the TinyViT training step), green on a B200 since round 2.
 #include "common.cuh"
 
 namespace es3 {

@@ -649,8 +649,8 @@ __global__ void __launch_bounds__(256) dw_wgrad_strip_kernel(const bf16* __restr
   }
 }
 
-// Shared-memory tiled version for stride 1, C % 32 == 0 (NOT the default path yet: written after the round's GPU budget was
-// spent, selected only through es3_dwconv_wgrad_tiled; see profiles/r1_next_steps.md).  A CTA owns a 32-channel slab and walks
+// Shared-memory tiled version for stride 1, C % 32 == 0 (the default route for these shapes since round 2, ops.DW_WGRAD_TILED;
+// GPU parity: test_dwconv_wgrad_tiled).  A CTA owns a 32-channel slab and walks
 // 8 x 32 output-pixel tiles: the dz tile and the haloed x tile are staged once with cp.async (zero fill outside the map), a
 // half-warp = the 16 channel pairs of one pixel, so every shared-memory read is 64 contiguous bytes and the KS*KS taps of a pixel
 // re-use the staged tile instead of L1.  acc[KS*KS][2] per thread (<= 50 registers) -> full occupancy.
@@ -883,41 +883,69 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const bf16* __restri
 // dout [B,C,Ho,Wo] fp32 NCHW -> din [B,Hi,Wi,C] bf16 NHWC, adjoint of bilinear_nhwc_to_nchw_kernel (same source-index
 // arithmetic).  grid (C/32, Hi, B), block 256: 32 channels x one input row; the result goes through shared memory so
 // the NHWC store is 64-byte contiguous per pixel.
-constexpr int BB_CB = 32;
+constexpr int BB_CB = 32, BB_MAXT = 12;    // channels per block; candidate outputs per input pixel and axis (up-scaling by <= 4)
 __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ din, int Hi, int Wi, int C,
                                                            int Ho, int Wo, float sy, float sx) {
-  extern __shared__ float bb_tile[];   // [Wi][BB_CB + 1]
+  extern __shared__ float bb_tile[];   // [Wi][BB_CB + 1] | wx table [Wi][BB_MAXT] | ox0 [Wi] | wy [BB_MAXT]
+  float* s_wx = bb_tile + Wi * (BB_CB + 1);
+  int* s_ox0 = reinterpret_cast<int*>(s_wx + Wi * BB_MAXT);
+  float* s_wy = reinterpret_cast<float*>(s_ox0 + Wi);
   const int c0 = blockIdx.x * BB_CB, iy = blockIdx.y, b = blockIdx.z;
   // candidate output rows: every oy whose source interval [y0, y1] can contain iy
   int oy_lo = (int)floorf(((float)iy - 1.f + 0.5f) / sy - 0.5f) - 1;
   int oy_hi = (int)ceilf(((float)iy + 1.f + 0.5f) / sy - 0.5f) + 1;
   oy_lo = max(oy_lo, 0);
   oy_hi = min(oy_hi, Ho - 1);
+  if (oy_hi - oy_lo + 1 > BB_MAXT) oy_hi = oy_lo + BB_MAXT - 1;      // (host checks the scale: never taken)
+  // The interpolation weights depend on (iy, oy) and (ix, ox) only -- not on the channel: they are built once per block (round 1
+  // recomputed floorf / ceilf / the clamped source index for every (channel, ix, oy, ox) candidate: 1.49 ms for a 537 MB read).
+  for (int t = threadIdx.x; t <= oy_hi - oy_lo; t += 256) {
+    const int oy = oy_lo + t;
+    float fy = (oy + 0.5f) * sy - 0.5f;
+    if (fy < 0.f) fy = 0.f;
+    const int y0 = min((int)fy, Hi - 1), y1 = min(y0 + 1, Hi - 1);
+    const float ly = fy - (float)y0, hy = 1.f - ly;
+    s_wy[t] = (y0 == iy ? hy : 0.f) + (y1 == iy ? ly : 0.f);
+  }
+  for (int ix = threadIdx.x; ix < Wi; ix += 256) {
+    int ox_lo = (int)floorf(((float)ix - 1.f + 0.5f) / sx - 0.5f) - 1;
+    int ox_hi = (int)ceilf(((float)ix + 1.f + 0.5f) / sx - 0.5f) + 1;
+    ox_lo = max(ox_lo, 0);
+    ox_hi = min(ox_hi, Wo - 1);
+    s_ox0[ix] = ox_lo;
+    for (int t = 0; t < BB_MAXT; ++t) {
+      const int ox = ox_lo + t;
+      float wx = 0.f;
+      if (ox <= ox_hi) {
+        float fx = (ox + 0.5f) * sx - 0.5f;
+        if (fx < 0.f) fx = 0.f;
+        const int x0 = min((int)fx, Wi - 1), x1 = min(x0 + 1, Wi - 1);
+        const float lx = fx - (float)x0, hx = 1.f - lx;
+        wx = (x0 == ix ? hx : 0.f) + (x1 == ix ? lx : 0.f);
+      }
+      s_wx[ix * BB_MAXT + t] = wx;
+    }
+  }
+  __syncthreads();
+  const int ny = oy_hi - oy_lo + 1;
   for (int idx = threadIdx.x; idx < BB_CB * Wi; idx += 256) {
     const int ix = idx % Wi, cl = idx / Wi;
     const int c = c0 + cl;
     float acc = 0.f;
     if (c < C) {
-      int ox_lo = (int)floorf(((float)ix - 1.f + 0.5f) / sx - 0.5f) - 1;
-      int ox_hi = (int)ceilf(((float)ix + 1.f + 0.5f) / sx - 0.5f) + 1;
-      ox_lo = max(ox_lo, 0);
-      ox_hi = min(ox_hi, Wo - 1);
+      const int ox_lo = s_ox0[ix];
       const float* plane = dout + ((long long)b * C + c) * Ho * Wo;
-      for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-        float fy = (oy + 0.5f) * sy - 0.5f;
-        if (fy < 0.f) fy = 0.f;
-        const int y0 = min((int)fy, Hi - 1), y1 = min(y0 + 1, Hi - 1);
-        const float ly = fy - (float)y0, hy = 1.f - ly;
-        const float wy = (y0 == iy ? hy : 0.f) + (y1 == iy ? ly : 0.f);
+      for (int t = 0; t < ny; ++t) {
+        const float wy = s_wy[t];
         if (wy == 0.f) continue;
-        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-          float fx = (ox + 0.5f) * sx - 0.5f;
-          if (fx < 0.f) fx = 0.f;
-          const int x0 = min((int)fx, Wi - 1), x1 = min(x0 + 1, Wi - 1);
-          const float lx = fx - (float)x0, hx = 1.f - lx;
-          const float wx = (x0 == ix ? hx : 0.f) + (x1 == ix ? lx : 0.f);
-          if (wx != 0.f) acc = fmaf(wy * wx, __ldg(plane + (long long)oy * Wo + ox), acc);
+        const float* rowp = plane + (long long)(oy_lo + t) * Wo + ox_lo;
+        float ra = 0.f;
+#pragma unroll
+        for (int u = 0; u < BB_MAXT; ++u) {
+          const float wx = s_wx[ix * BB_MAXT + u];
+          if (wx != 0.f) ra = fmaf(wx, __ldg(rowp + u), ra);       // wx == 0 also covers ox beyond the row
         }
+        acc = fmaf(wy, ra, acc);
       }
     }
     bb_tile[ix * (BB_CB + 1) + cl] = acc;
@@ -1472,8 +1500,11 @@ extern "C" int es3_accumulate_strided(const float* src, long long n, int inner, 
 
 extern "C" int es3_bilinear_bwd(const float* dout, void* din, int B, int Hi, int Wi, int C, int Ho, int Wo, void* stream) {
   ES3_REQUIRE(B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0, "es3_bilinear_bwd: bad shape");
-  const int smem = Wi * (BB_CB + 1) * (int)sizeof(float);
+  const int smem = (Wi * (BB_CB + 1) + Wi * BB_MAXT + Wi + BB_MAXT) * (int)sizeof(float);
   ES3_REQUIRE(smem <= 48 * 1024, "es3_bilinear_bwd: Wi=%d too wide for the row tile", Wi);
+  // candidates per input pixel and axis: outputs whose 2-tap source interval can contain it, <= 2 * (out / in) + 4
+  ES3_REQUIRE(2.f * Ho / Hi + 4.f <= BB_MAXT && 2.f * Wo / Wi + 4.f <= BB_MAXT,
+              "es3_bilinear_bwd: up-scaling %dx%d -> %dx%d exceeds the %d-candidate tables", Hi, Wi, Ho, Wo, BB_MAXT);
   bilinear_bwd_kernel<<<dim3(ceil_div(C, BB_CB), Hi, B), 256, smem, (cudaStream_t)stream>>>(dout, (bf16*)din, Hi, Wi, C, Ho, Wo,
                                                                                           (float)Hi / (float)Ho, (float)Wi / (float)Wo);
   ES3_LAUNCH_CHECK("bilinear_bwd_kernel");

@@ -923,7 +923,8 @@ def conv3x3_wgrad(dy, a, gw):
         aT = transpose_pad(a, Wp, kx - 1)
         for ky in range(3):
             lo = Wp + (ky - 1) * Wp
-            gemm(dyT[:, Wp:Mp - Wp], aT[:, lo:lo + Mp - 2 * Wp], out=full)
+            # 64-wide tiles: 8 x 16 = 128 CTAs instead of 64 on 148 SMs (the contraction runs over ~43 K pixels: MMA-bound per tile)
+            gemm(dyT[:, Wp:Mp - Wp], aT[:, lo:lo + Mp - 2 * Wp], out=full, bn_hint=64 if full.shape[1] >= 512 else 0)
             accumulate_strided(full, flat[ky * 3 + kx:], C, 9 * C, 9)
     return gw
 

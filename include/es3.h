@@ -322,8 +322,7 @@ long long es3_dwconv_wgrad_ws_floats(int B, int H, int W, int C, int ks, int str
 int es3_dwconv_wgrad(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, int stride, float* ws,
                      float* dW, void* stream);
 /* Backward of es3_litemla_attn_generic (head dim 16 | 32; efficientvit_b2 uses 32): same contract as es3_litemla_attn_bwd with
- * kv_part = the workspace es3_litemla_attn_generic filled (nchunk_f = ceil(HW / 128)).  No GPU run yet (written after the
- * round-1 GPU budget was spent). */
+ * kv_part = the workspace es3_litemla_attn_generic filled (nchunk_f = ceil(HW / 128)).  GPU parity: test_litemla_attn_bwd_generic. */
 long long es3_litemla_bwd_generic_ws_floats(int B, int HW, int heads2, int dim);
 int es3_litemla_attn_bwd_generic(const void* ms, long long ld, const void* dy, long long lddy, const float* kv_part, int nchunk_f,
                                  float* dkv_ws, void* dms, long long lddms, int B, int HW, int heads2, int dim, float eps, void* stream);
@@ -339,8 +338,8 @@ int es3_win_attn_bias_bwd(const void* qkv, const void* dout, const float* bias, 
                           int C, int num_heads, int ws, float scale, void* stream);
 long long es3_colsum_f32_ws_floats(long long M, int L);
 int es3_colsum_f32(const float* src, long long ld, long long M, int L, float* ws, float* out, void* stream);
-/* Shared-memory tiled variant of es3_dwconv_wgrad for stride 1 and C % 32 == 0 (same result contract).  Written after the round-1
- * GPU budget was spent: NOT on the default path until it has a GPU parity run (profiles/r1_next_steps.md). */
+/* Shared-memory tiled variant of es3_dwconv_wgrad for stride 1 and C % 32 == 0 (same result contract).  The default
+ * route for these shapes since round 2 (GPU parity: test_dwconv_wgrad_tiled). */
 long long es3_dwconv_wgrad_tiled_ws_floats(int B, int H, int W, int C, int ks);
 int es3_dwconv_wgrad_tiled(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, float* ws, float* dW,
                            void* stream);
