@@ -12,6 +12,8 @@
 //                      then exp2), P written back to TMEM with tcgen05.st, per-tile Ot read from TMEM and folded
 //                      into the fp32 running output in registers (o = o * corr + Ot), so O is never rescaled in TMEM.
 // TMEM map (512 columns): slot q at q*256: S [0,128) fp32 | P [128,192) packed bf16x2 | Ot [192,256) fp32.
+#include <cstdlib>
+
 #include "ptx.cuh"
 
 namespace es3 {
@@ -294,6 +296,183 @@ __global__ void __launch_bounds__((3 + 4 * NS) * 32, NS == 1 ? 2 : 1) attn_tc_ke
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ 24 x 24 windows, whole window resident
+// The windowed blocks of the trunk (28 of 32: L = 576 keys, 4.5 query tiles) ran attn_tc_kernel<96, 1>: one CTA per QUERY TILE, so
+// each (window, head) gathered its K and V five times, lived for only six key tiles and had no second slot to overlap softmax with
+// the MMAs (round-1 table: 222-260 TFLOP/s against 430 for the global blocks).  Here one CTA owns a (window, head): Q (5 tiles,
+// the last half empty), K and V (6 tiles of 96 rows each) are gathered ONCE into 224 KB of shared memory by all warps, then the
+// five query tiles run through the two ping-ponged slots (pairs (0,1), (2,3), (4)) against the resident K / V -- no producer warps,
+// no ring, the same S / P / Ot protocol with per-slot iteration counters as barrier phases.
+constexpr int FW_L = 576, FW_BN = 96, FW_NKT = 6, FW_NQT = 5, FW_KT_BYTES = FW_BN * 128;   // 12288 B per K / V tile (12 atoms)
+constexpr int FW_THREADS = 10 * 32;
+constexpr int FW_SMEM = 1024 + FW_NQT * FA_TILE_BYTES + 2 * FW_NKT * FW_KT_BYTES;          // 1 KB + 80 KB + 144 KB
+
+__global__ void __launch_bounds__(FW_THREADS, 1) attn_win24_tc_kernel(const FaArgs a) {
+  extern __shared__ uint8_t fa_raw[];
+  __shared__ __align__(8) uint64_t s_full[2], p_full[2], ot_full[2], ot_free[2];
+  __shared__ uint32_t tmem_holder;
+  const uint32_t smem0 = (ptx::smem_u32(fa_raw) + 1023u) & ~1023u;
+  const uint32_t u_q = smem0;                                   // [5][128 x 128 B]
+  const uint32_t u_k = smem0 + FW_NQT * FA_TILE_BYTES;          // [6][96 x 128 B]
+  const uint32_t u_v = u_k + FW_NKT * FW_KT_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z / a.nwin, wi = blockIdx.z % a.nwin;
+  const int ld = 3 * a.C;
+  const bf16* qbase = a.qkv + head * FA_D;
+
+  if (tid == 0) {
+    for (int q = 0; q < 2; ++q) {
+      ptx::mbar_init(&s_full[q], 1); ptx::mbar_init(&p_full[q], 4);
+      ptx::mbar_init(&ot_full[q], 1); ptx::mbar_init(&ot_free[q], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(&tmem_holder, 512);
+  // ---- gather the whole window once: Q rows 0..639 (>= 576: zero), K and V rows 0..575; 16-byte chunks, 128B-swizzled tiles
+  for (int i = tid; i < (FW_NQT * FA_BM + 2 * FW_L) * 8; i += FW_THREADS) {
+    const int c = i & 7, r = i >> 3;
+    if (r < FW_NQT * FA_BM) {
+      const bool ok = r < FW_L;
+      const long long row = ok ? fa_token_row(a, b, wi, r) : 0;
+      fa_cp16(fa_sw(u_q + (r >> 7) * FA_TILE_BYTES, r & 127, c), qbase + row * ld + c * 8, ok);
+    } else {
+      const int rr = r - FW_NQT * FA_BM;
+      const int isv = rr >= FW_L;
+      const int l = isv ? rr - FW_L : rr;
+      const long long row = fa_token_row(a, b, wi, l);
+      const int t = l / FW_BN, lr = l % FW_BN;
+      fa_cp16(fa_sw((isv ? u_v : u_k) + t * FW_KT_BYTES, lr, c), qbase + (isv ? 2 : 1) * a.C + row * ld + c * 8, true);
+    }
+  }
+  fa_cp_wait_all();
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_holder;
+  constexpr int NPAIR = (FW_NQT + 1) / 2;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16_f32(128, FW_BN);
+      constexpr uint32_t idesc_o = ptx::make_idesc_bf16_f32(128, 64) | (1u << 16);  // B is MN-major
+      auto issue_s = [&](int q, int qt, int kt) {
+        const uint64_t dq = ptx::make_desc_sw128(u_q + qt * FA_TILE_BYTES);
+        const uint64_t dk = ptx::make_desc_sw128(u_k + kt * FW_KT_BYTES);
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k) ptx::umma_f16(tmem + q * 256, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k != 0);
+        ptx::umma_commit(&s_full[q]);
+      };
+      uint32_t it[2] = {0u, 0u};                     // tiles processed per slot: the phase of its four barriers
+      for (int pr = 0; pr < NPAIR; ++pr) {
+        const int nslots = (2 * pr + 1 < FW_NQT) ? 2 : 1;
+        for (int q = 0; q < nslots; ++q) issue_s(q, 2 * pr + q, 0);
+        for (int j = 0; j < FW_NKT; ++j) {
+          for (int q = 0; q < nslots; ++q) {
+            ptx::mbar_wait(&p_full[q], it[q] & 1u);            // P_q written, S_q consumed
+            ptx::mbar_wait(&ot_free[q], (it[q] & 1u) ^ 1u);     // previous Ot_q folded into registers
+            ptx::tc_fence_after();
+            const uint64_t dv = fa_desc_mn(u_v + j * FW_KT_BYTES);
+#pragma unroll
+            for (int k = 0; k < FW_BN / 16; ++k)
+              umma_f16_ts(tmem + q * 256 + 192, tmem + q * 256 + 128 + k * 8, dv + (uint64_t)(k * 128), idesc_o, k != 0);
+            ptx::umma_commit(&ot_full[q]);
+            if (j + 1 < FW_NKT) issue_s(q, 2 * pr + q, j + 1);
+            ++it[q];
+          }
+        }
+      }
+    }
+  } else if (warp >= 2) {
+    const int q = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_s = tmem + q * 256 + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t t_p = t_s + 128, t_o = t_s + 192;
+    uint32_t it = 0u;
+    for (int pr = 0; pr < NPAIR; ++pr) {
+      const int qt = 2 * pr + q;
+      if (qt >= FW_NQT) break;
+      float o_reg[FA_D];
+#pragma unroll
+      for (int d = 0; d < FA_D; ++d) o_reg[d] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < FW_NKT; ++j, ++it) {
+        const uint32_t jp = it & 1u;
+        ptx::mbar_wait(&s_full[q], jp);
+        ptx::tc_fence_after();
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < FW_BN / 32; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_s + c * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+        }
+        const float m_new = fmaxf(m_run, mx * a.scale_log2);
+        const float corr = fa_exp2(m_run - m_new);
+        float rs = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < FW_BN / 32; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_s + c * 32, v);
+          ptx::tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float p0 = fa_exp2(fmaf(__uint_as_float(v[2 * e]), a.scale_log2, -m_new));
+            const float p1 = fa_exp2(fmaf(__uint_as_float(v[2 * e + 1]), a.scale_log2, -m_new));
+            rs += p0 + p1;
+            pk[e] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x16(t_p + c * 16, pk);
+        }
+        tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[q]);
+        l_run = l_run * corr + rs;
+        m_run = m_new;
+        ptx::mbar_wait(&ot_full[q], jp);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_o + c * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o_reg[c * 32 + e] = fmaf(o_reg[c * 32 + e], corr, __uint_as_float(v[e]));
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ot_free[q]);
+      }
+      const int l = qt * FA_BM + row;
+      if (l < FW_L) {
+        const float inv = 1.f / l_run;
+        bf16* op = a.out + fa_token_row(a, b, wi, l) * a.C + head * FA_D;
+#pragma unroll
+        for (int d = 0; d < FA_D; d += 8) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = o_reg[d + e] * inv;
+          *reinterpret_cast<uint4*>(op + d) = pack8(f);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
 }  // namespace es3
 
 using namespace es3;
@@ -321,8 +500,18 @@ extern "C" int es3_attention_tc_bf16(const void* qkv, void* out, int B, int H, i
     ES3_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<96, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
     configured = true;
   }
-  dim3 grid(ceil_div(a.L, ns * FA_BM), num_heads, B * a.nwin);
   cudaStream_t st = (cudaStream_t)stream;
+  if (win == 24 && a.L == FW_L && !getenv("ES3_ATTN_WIN_TILED")) {     // the trunk's windowed blocks: whole window resident
+    static bool cfg_win = false;
+    if (!cfg_win) {
+      ES3_CHECK_CUDA(cudaFuncSetAttribute(attn_win24_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
+      cfg_win = true;
+    }
+    attn_win24_tc_kernel<<<dim3(1, num_heads, B * a.nwin), FW_THREADS, FW_SMEM, st>>>(a);
+    ES3_LAUNCH_CHECK("attn_win24_tc_kernel");
+    return 0;
+  }
+  dim3 grid(ceil_div(a.L, ns * FA_BM), num_heads, B * a.nwin);
   // 24x24 windows (L = 576 = 6 x 96) and other multiples of 96 that are not multiples of 128: 96-key tiles, no padding
   const bool bn96 = a.L % 96 == 0 && a.L % 128 != 0;
   if (ns == 1) {
