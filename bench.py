@@ -765,6 +765,11 @@ def cpu_oracle_throughput(S, E, batch, steps, warmup):
     x = torch.randn(batch, 3, S, S, generator=torch.Generator().manual_seed(1))
     prev = torch.get_num_threads()
     cores = min(_physical_cores(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 1 << 30)
+    if os.environ.get("ES3_CPU_THREADS"):
+        cores = int(os.environ["ES3_CPU_THREADS"])
+    if os.environ.get("ES3_CPU_CUDA_INIT") == "1" and torch.cuda.is_available():
+        torch.cuda.init()
+        torch.zeros(1, device="cuda")
     torch.set_num_threads(cores)
     try:
         with torch.no_grad():

@@ -72,7 +72,7 @@ __device__ __forceinline__ void mma16816(float* d, const uint32_t* a, uint32_t b
 constexpr int CR_THREADS = 256;
 
 template <int ACT, bool STATS>
-__global__ void __launch_bounds__(CR_THREADS) col_reduce_kernel(const bf16* __restrict__ z, const bf16* __restrict__ da,
+__global__ void __launch_bounds__(CR_THREADS, 3) col_reduce_kernel(const bf16* __restrict__ z, const bf16* __restrict__ da,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                                                 long long M, int C, int CVB, long long rows_per_block,
                                                                 float* __restrict__ part) {
@@ -96,28 +96,30 @@ __global__ void __launch_bounds__(CR_THREADS) col_reduce_kernel(const bf16* __re
     if constexpr (STATS) unpack8(__ldg(reinterpret_cast<const uint4*>(z + cv * 8)), piv);
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = min(M, r0 + rows_per_block);
-    // two rows per iteration: both loads (four in the backward form) are issued before any arithmetic
-    for (long long r = r0 + pl; r < r1; r += 2 * lanes) {
-      const long long rb = r + lanes;
-      const bool two = rb < r1;
-      const uint4 uza = __ldg(reinterpret_cast<const uint4*>(z + r * C + cv * 8));
-      const uint4 uzb = two ? __ldg(reinterpret_cast<const uint4*>(z + rb * C + cv * 8)) : make_uint4(0, 0, 0, 0);
-      uint4 uda = make_uint4(0, 0, 0, 0), udb = make_uint4(0, 0, 0, 0);
-      if constexpr (!STATS) {
-        uda = __ldg(reinterpret_cast<const uint4*>(da + r * C + cv * 8));
-        if (two) udb = __ldg(reinterpret_cast<const uint4*>(da + rb * C + cv * 8));
+    // CR_ROWS rows per iteration: all loads (twice as many in the backward form) are issued before any arithmetic -- the kernel is
+    // a pure stream, its speed is the number of 16-byte loads in flight per SM (two rows: 2.2 / 2.9 TB/s, profiles/r2n_train_step_table.md)
+    constexpr int CR_ROWS = 4;
+    for (long long r = r0 + pl; r < r1; r += (long long)CR_ROWS * lanes) {
+      uint4 uz[CR_ROWS], ud[CR_ROWS];
+      bool ok[CR_ROWS];
+#pragma unroll
+      for (int h = 0; h < CR_ROWS; ++h) {
+        const long long rr = r + (long long)h * lanes;
+        ok[h] = rr < r1;
+        uz[h] = ok[h] ? __ldg(reinterpret_cast<const uint4*>(z + rr * C + cv * 8)) : make_uint4(0, 0, 0, 0);
+        if constexpr (!STATS) ud[h] = ok[h] ? __ldg(reinterpret_cast<const uint4*>(da + rr * C + cv * 8)) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h == 1 && !two) break;
+      for (int h = 0; h < CR_ROWS; ++h) {
+        if (!ok[h]) break;
         float fz[8];
-        unpack8(h ? uzb : uza, fz);
+        unpack8(uz[h], fz);
         if constexpr (STATS) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) { const float d = fz[i] - piv[i]; s0[i] += d; s1[i] = fmaf(d, d, s1[i]); }
         } else {
           float fd[8];
-          unpack8(h ? udb : uda, fd);
+          unpack8(ud[h], fd);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float g = fd[i] * act_grad_t<ACT>(fmaf(sc[i], fz[i], sh[i]));
