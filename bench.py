@@ -752,6 +752,22 @@ def _physical_cores():
     return max(1, (os.cpu_count() or 2) // 2)
 
 
+def _keep_malloc_off_mmap():
+    """glibc serves every allocation above its mmap threshold (<= 32 MB) with a fresh mmap and returns it with munmap: the
+    oracle's intermediates (up to 268 MB each) are then page-faulted in on EVERY pass.  Measured on the GPU box's host
+    (scripts/cpu_arm_probe.sh, profiles/r2q_cpu_probe.log): 1.5 img/s in a fresh process vs 6.7 img/s with the heap kept
+    (and 5 img/s at the end of the native run, whose heap had grown) -- the bimodal CPU arm of round 1.  mallopt() is the
+    in-process form of MALLOC_MMAP_MAX_=0 MALLOC_TRIM_THRESHOLD_=big; it only ever makes the CPU baseline faster."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL("libc.so.6")
+        M_TRIM_THRESHOLD, M_TOP_PAD, M_MMAP_MAX = -1, -2, -4
+        ok = libc.mallopt(M_MMAP_MAX, 0) and libc.mallopt(M_TRIM_THRESHOLD, 2 ** 31 - 1) and libc.mallopt(M_TOP_PAD, 1 << 28)
+        return bool(ok)
+    except Exception:
+        return False
+
+
 def cpu_oracle_throughput(S, E, batch, steps, warmup):
     """Times the CPU oracle port (oracle/efficientvit.py; pinned to the reference by tests/golden) on the host's physical cores.
     The only place the native arm touches oracle/ besides the eager-GPU arm -- as a baseline, never as the product path.
@@ -763,6 +779,7 @@ def cpu_oracle_throughput(S, E, batch, steps, warmup):
     cfg = NS(MODEL=NS(BACKBONE="efficientvit_b1"), DATA=NS(IMG_SIZE=S), DISTILL=NS(EMBED_DIM=1024, EMBED_SIZE=E))
     sd = fill_state_dict(build_image_student_model(cfg).state_dict(), 7)
     x = torch.randn(batch, 3, S, S, generator=torch.Generator().manual_seed(1))
+    heap_kept = _keep_malloc_off_mmap()
     prev = torch.get_num_threads()
     cores = min(_physical_cores(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 1 << 30)
     if os.environ.get("ES3_CPU_THREADS"):
@@ -786,7 +803,7 @@ def cpu_oracle_throughput(S, E, batch, steps, warmup):
     return {"value": round(batch / sec, 3), "unit": UNIT, "cores": cores, "kind": "port",
             "min_median_max": [round(batch / max(ts), 3), round(batch / sec, 3), round(batch / min(ts), 3)],
             "sample": f"{steps} timed passes of batch {batch} x 3x{S}x{S} after {warmup} warm-up (median), PyTorch-CPU fp32 eager oracle port, "
-                      f"torch threads = {cores} physical cores"}
+                      f"torch threads = {cores} physical cores, glibc heap kept off mmap = {heap_kept}"}
 
 
 def run_reference(args):

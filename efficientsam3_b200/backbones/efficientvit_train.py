@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..nn_utils import dw_weight, pw_weight
+from ..nn_utils import cached_pack, dw_weight, dw_weight_rot, pw_weight, pw_weight_t
 from .efficientvit import (ConvLayer, DSConv, EfficientViTBlock, LiteMLA, MBConv, ResidualBlock)
 
 __all__ = ["EfficientViTTrainGraph", "HeadTrainUnit", "GradSink"]
@@ -78,7 +78,7 @@ class ConvUnit:
             self.w = dw_weight(conv, None)                                      # [k*k, C] fp32
             return ops.dwconv(x, self.w, None, self.ks, self.stride, None)
         cout = conv.out_channels
-        w27 = conv.weight.detach().float().reshape(cout, 27).t().contiguous()   # [27, Cout], 27 = ci*9 + ky*3 + kx
+        w27 = cached_pack(conv, "w27", conv.weight, lambda: conv.weight.detach().float().reshape(cout, 27).t().contiguous())   # [27, Cout]
         return ops.stem_conv3x3_s2(x, w27, None, None)
 
     def forward(self, x, residual=None):
@@ -126,7 +126,7 @@ class ConvUnit:
                 ops.wgrad_pw(dz2, x2, gw)
             if not need_dx:
                 return None
-            wt = self.w.t().contiguous()                                        # [K, N] bf16
+            wt = pw_weight_t(conv)                                              # [K, N] bf16 (cached per optimiser step)
             res = dx_residual.reshape(-1, K) if dx_residual is not None else None
             return ops.gemm(dz2, wt, residual=res).view(B, H, W, K)
         if self.kind == "dw":
@@ -136,7 +136,7 @@ class ConvUnit:
             if not need_dx:
                 return None
             if self.stride == 1:   # correlation with the 180-degree rotated taps: the forward kernel itself
-                dx = ops.dwconv(dz, self.w.flip(0).contiguous(), None, self.ks, 1, None)
+                dx = ops.dwconv(dz, dw_weight_rot(conv), None, self.ks, 1, None)
             else:
                 dx = ops.dwconv_bwd_data(dz, self.w, H, W, self.ks, self.stride)
             if dx_residual is not None:
@@ -236,19 +236,19 @@ class LiteMLAUnit:
             ops.wgrad_pw(d_y2, t.view(-1, c3), full)
             idx = torch.arange(G, device=x.device)
             g_pw += full.view(G, 16, G, 16)[idx, :, idx, :].reshape(pwc.weight.shape)
-        wbd_t = torch.block_diag(*wp.view(G, 16, 16).transpose(1, 2)).contiguous()   # [16g+i][16g+n] bf16
+        wbd_t = cached_pack(pwc, "wbd_t", pwc.weight, lambda: torch.block_diag(*wp.view(G, 16, 16).transpose(1, 2)).contiguous())   # [16g+i][16g+n] bf16
         d_t = ops.gemm(d_y2, wbd_t).view(B, H, W, c3)
         # depthwise 5x5 (aggreg[0][0]) on qkv
         g_dw = _grad_of(grads, dwc.weight)
         if g_dw is not None:
             ops.dwconv_wgrad(d_t, ms[..., :c3], g_dw, 5, 1)
-        d_q1 = ops.dwconv(d_t, agg_dw.flip(0).contiguous(), None, 5, 1, None)
+        d_q1 = ops.dwconv(d_t, cached_pack(dwc, "agg_rot", dwc.weight, lambda: agg_dw.flip(0).contiguous()), None, 5, 1, None)
         d_qkv = ops.add_bf16(dms2[:, :c3], d_q1.view(-1, c3))
         # qkv 1x1
         g_qkv = _grad_of(grads, m.qkv.conv.weight)
         if g_qkv is not None:
             ops.wgrad_pw(d_qkv, x.view(-1, C), g_qkv)
-        return ops.gemm(d_qkv, qkv_w.t().contiguous(), residual=dy.reshape(-1, C)).view(B, H, W, C)
+        return ops.gemm(d_qkv, pw_weight_t(m.qkv.conv), residual=dy.reshape(-1, C)).view(B, H, W, C)
 
 
 class LiteMLAGenericUnit:
@@ -316,7 +316,7 @@ class LiteMLAGenericUnit:
         g_qkv = _grad_of(grads, m.qkv.conv.weight)
         if g_qkv is not None:
             ops.wgrad_pw(d_qkv, x.view(-1, C), g_qkv)
-        return ops.gemm(d_qkv, qkv_w.t().contiguous(), residual=dy.reshape(-1, C)).view(B, H, W, C)
+        return ops.gemm(d_qkv, pw_weight_t(m.qkv.conv), residual=dy.reshape(-1, C)).view(B, H, W, C)
 
 
 class EfficientViTTrainGraph:
@@ -370,7 +370,7 @@ class HeadTrainUnit:
         a1 = self.c0.forward(feats)                                              # [B,h,w,1024] bf16
         w = self.conv3.weight.detach()
         n, c = w.shape[:2]
-        w9 = w.permute(0, 2, 3, 1).reshape(n, 9 * c).to(torch.bfloat16).contiguous()
+        w9 = cached_pack(self.conv3, "w9", self.conv3.weight, lambda: w.permute(0, 2, 3, 1).reshape(n, 9 * c).to(torch.bfloat16).contiguous())
         y = ops.conv3x3(a1, w9, bias=self.conv3.bias.detach().float().contiguous())
         B, h, wd, _ = y.shape
         self.saved = (a1, h, wd)
@@ -398,6 +398,7 @@ class HeadTrainUnit:
                 for kx in range(3):
                     ops.wgrad_pw(dy2, a2, flat[ky * 3 + kx:], ldn=9 * c, ldk=9, shift=(h, wd, ky - 1, kx - 1))
         # input gradient: 3x3 conv of dy with the rotated, in/out-transposed kernel
-        wt9 = conv3.weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(c, 9 * n).to(torch.bfloat16).contiguous()
+        wt9 = cached_pack(conv3, "wt9", conv3.weight,
+                          lambda: conv3.weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(c, 9 * n).to(torch.bfloat16).contiguous())
         da1 = ops.conv3x3(dy, wt9)
         return self.c0.backward(da1, grads)

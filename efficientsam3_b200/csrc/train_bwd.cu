@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(CR_THREADS, 3) col_reduce_kernel(const bf16* _
     const long long r1 = min(M, r0 + rows_per_block);
     // CR_ROWS rows per iteration: all loads (twice as many in the backward form) are issued before any arithmetic -- the kernel is
     // a pure stream, its speed is the number of 16-byte loads in flight per SM (two rows: 2.2 / 2.9 TB/s, profiles/r2n_train_step_table.md)
-    constexpr int CR_ROWS = 4;
+    constexpr int CR_ROWS = STATS ? 4 : 2;     // (four rows in the backward form cost registers / resident CTAs: 5.4 -> 5.8 ms, reverted)
     for (long long r = r0 + pl; r < r1; r += (long long)CR_ROWS * lanes) {
       uint4 uz[CR_ROWS], ud[CR_ROWS];
       bool ok[CR_ROWS];
@@ -1334,11 +1334,65 @@ extern "C" int es3_wgrad_pw(const void* dz, long long lddz, const void* x, long 
   return 0;
 }
 
+// 3x3, stride 2 (the stage openers: 4 launches, 2 GB of dx per EV-M step): one thread per 2 x 2 block of input pixels and 8 channels.
+// With z(oy,ox) = sum w[ky][kx] x(2 oy - 1 + ky, 2 ox - 1 + kx) the block (2m + a, 2n + b) reads only dz(m..m+1, n..n+1):
+//   dx(2m  ,2n  ) = w11 dz00                      dx(2m  ,2n+1) = w12 dz00 + w10 dz01
+//   dx(2m+1,2n  ) = w21 dz00 + w01 dz10           dx(2m+1,2n+1) = w22 dz00 + w20 dz01 + w02 dz10 + w00 dz11
+// four 16-byte loads and four 16-byte stores per thread (the generic kernel above walked nine taps with a modulo test per tap and
+// re-read the weights from global memory for every tap: 0.86 TB/s).
+__global__ void __launch_bounds__(256) dw_bwd_data_s2k3_kernel(const bf16* __restrict__ dz, const float* __restrict__ w,
+                                                               bf16* __restrict__ dxo, int B, int H, int W, int C, int Ho, int Wo) {
+  const int CV = C >> 3;
+  const int Hb = (H + 1) >> 1, Wb = (W + 1) >> 1;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Hb * Wb * CV) return;
+  const int cv = (int)(i % CV);
+  const long long p = i / CV;
+  const int n = (int)(p % Wb), m = (int)((p / Wb) % Hb), b = (int)(p / ((long long)Wb * Hb));
+  float d[4][8];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int oy = m + (t >> 1), ox = n + (t & 1);
+    if (oy < Ho && ox < Wo) unpack8(__ldg(reinterpret_cast<const uint4*>(dz + (((long long)b * Ho + oy) * Wo + ox) * C + cv * 8)), d[t]);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[t][e] = 0.f;
+    }
+  }
+  float wk[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (long long)t * C + cv * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (long long)t * C + cv * 8 + 4));
+    wk[t][0] = w0.x; wk[t][1] = w0.y; wk[t][2] = w0.z; wk[t][3] = w0.w; wk[t][4] = w1.x; wk[t][5] = w1.y; wk[t][6] = w1.z; wk[t][7] = w1.w;
+  }
+  float o[4][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    o[0][e] = wk[4][e] * d[0][e];
+    o[1][e] = fmaf(wk[5][e], d[0][e], wk[3][e] * d[1][e]);
+    o[2][e] = fmaf(wk[7][e], d[0][e], wk[1][e] * d[2][e]);
+    o[3][e] = fmaf(wk[8][e], d[0][e], fmaf(wk[6][e], d[1][e], fmaf(wk[2][e], d[2][e], wk[0][e] * d[3][e])));
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int iy = 2 * m + (t >> 1), ix = 2 * n + (t & 1);
+    if (iy < H && ix < W) *reinterpret_cast<uint4*>(dxo + (((long long)b * H + iy) * W + ix) * C + cv * 8) = pack8(o[t]);
+  }
+}
+
 extern "C" int es3_dwconv_bwd_data(const void* dz, const float* w, void* dx, int B, int H, int W, int C, int ks, int stride,
                                    void* stream) {
   ES3_REQUIRE(C % 8 == 0 && (ks == 3 || ks == 5) && (stride == 1 || stride == 2), "es3_dwconv_bwd_data: unsupported C=%d ks=%d stride=%d", C, ks, stride);
   const int pad = ks / 2;
   const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
+  if (ks == 3 && stride == 2) {
+    const long long blocks = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+    dw_bwd_data_s2k3_kernel<<<(unsigned)ceil_div(blocks, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dz, w, (bf16*)dx, B, H, W, C, Ho,
+                                                                                              Wo);
+    ES3_LAUNCH_CHECK("dw_bwd_data_s2k3_kernel");
+    return 0;
+  }
   const long long total = (long long)B * H * W * (C / 8);
   dw_bwd_data_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dz, w, (bf16*)dx, B, H, W, C, Ho, Wo,
                                                                                        ks, stride);

@@ -23,19 +23,62 @@ def bn_scale_bias(norm: nn.BatchNorm2d | None, conv_bias: torch.Tensor | None, c
     return s.contiguous(), b.contiguous()
 
 
-def pw_weight(conv: nn.Conv2d) -> torch.Tensor:
-    """1x1 conv weight [N,C,1,1] -> bf16 [N,C] (K-major GEMM B operand)."""
+# Packed / re-laid-out copies of a parameter are cached on the module that owns it and rebuilt when the parameter changes:
+# (data_ptr, _version) catches torch-side writes, WEIGHTS_EPOCH the fused AdamW kernel, which moves the parameters through raw
+# pointers (stage1.optim.FlatAdamW.step bumps it).  The training graphs re-derive ~150 such tensors per iteration (bf16 casts,
+# transposes for the input-gradient GEMMs, rotated depthwise taps): with the cache they are built once per optimiser step.
+WEIGHTS_EPOCH = 0
+
+
+def bump_weights_epoch():
+    global WEIGHTS_EPOCH
+    WEIGHTS_EPOCH += 1
+
+
+def cached_pack(owner: nn.Module, name: str, src: torch.Tensor, fn):
+    key = (src.data_ptr(), src._version, src.device, WEIGHTS_EPOCH)
+    cache = owner.__dict__.setdefault("_es3_pack_cache", {})
+    ent = cache.get(name)
+    if ent is None or ent[0] != key:
+        with torch.no_grad():
+            ent = (key, fn())
+        cache[name] = ent
+    return ent[1]
+
+
+def _pw_weight(conv):
     w = conv.weight.detach()
     return w.reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
 
 
-def dw_weight(conv: nn.Conv2d, scale: torch.Tensor | None) -> torch.Tensor:
-    """depthwise weight [C,1,k,k] (x folded BN scale) -> fp32 [k*k, C] tap-major."""
+def pw_weight(conv: nn.Conv2d) -> torch.Tensor:
+    """1x1 conv weight [N,C,1,1] -> bf16 [N,C] (K-major GEMM B operand)."""
+    return cached_pack(conv, "pw", conv.weight, lambda: _pw_weight(conv))
+
+
+def pw_weight_t(conv: nn.Conv2d) -> torch.Tensor:
+    """bf16 [C,N]: the transposed 1x1 weight, B operand of the input-gradient GEMM dx = dz . W."""
+    return cached_pack(conv, "pw_t", conv.weight, lambda: _pw_weight(conv).t().contiguous())
+
+
+def _dw_weight(conv, scale):
     w = conv.weight.detach().float()
     c, _, k, _ = w.shape
     if scale is not None:
         w = w * scale.view(-1, 1, 1, 1)
     return w.reshape(c, k * k).t().contiguous()
+
+
+def dw_weight(conv: nn.Conv2d, scale: torch.Tensor | None) -> torch.Tensor:
+    """depthwise weight [C,1,k,k] (x folded BN scale) -> fp32 [k*k, C] tap-major."""
+    if scale is not None:
+        return _dw_weight(conv, scale)
+    return cached_pack(conv, "dw", conv.weight, lambda: _dw_weight(conv, None))
+
+
+def dw_weight_rot(conv: nn.Conv2d) -> torch.Tensor:
+    """fp32 [k*k, C] with the taps rotated by 180 degrees: the stride-1 input gradient is the forward kernel on these."""
+    return cached_pack(conv, "dw_rot", conv.weight, lambda: _dw_weight(conv, None).flip(0).contiguous())
 
 
 def pack_patch_embed(w0: torch.Tensor, s0, b0, w1: torch.Tensor):

@@ -162,6 +162,8 @@ class FlatAdamW:
             self._plan_holders = [mod for mod in self._model.modules() if hasattr(mod, "_plan_key")]
         for mod in self._plan_holders:
             mod._plan_key = None
+        from ..nn_utils import bump_weights_epoch
+        bump_weights_epoch()                     # packed training-graph weights (nn_utils.cached_pack) are stale as well
         ops.grad_norm(self.flat_grad, self._part_ws, self._norm_ws)
         ops.adamw_flat(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.n_decay, self.lr, self.betas,
                        self.eps, self.weight_decay, max_norm, 1.0 / world_size, self._norm_ws, self.state,

@@ -79,3 +79,24 @@ def test_state_dict_round_trips_through_torch_adamw():
         sl = slice(o, o + p_.numel())
         assert torch.equal(opt2.exp_avg[sl], opt.exp_avg[sl]) and torch.equal(opt2.exp_avg_sq[sl], opt.exp_avg_sq[sl])
     assert opt2.lr == 3e-4 and float(opt2.state[0]) == 1024.0 and float(opt2.state[2]) == 7.0
+
+
+def test_packed_weight_cache_follows_the_parameter():
+    """nn_utils.cached_pack: one packed copy per parameter state -- rebuilt after a torch-side write (version counter), after the fused
+    AdamW kernel moved the parameters through raw pointers (WEIGHTS_EPOCH), and after the parameter moved (data_ptr)."""
+    import torch
+    from efficientsam3_b200 import nn_utils as U
+    conv = torch.nn.Conv2d(8, 16, 1, bias=False)
+    a = U.pw_weight(conv)
+    assert U.pw_weight(conv) is a and U.pw_weight_t(conv).shape == (8, 16)
+    with torch.no_grad():
+        conv.weight.mul_(2.0)
+    b = U.pw_weight(conv)
+    assert b is not a and torch.equal(b.float(), (conv.weight.detach().reshape(16, 8)).to(torch.bfloat16).float())
+    conv.weight.data.view(-1)[0] = 123.0           # a raw write: the version counter of `.data` is not the parameter's
+    U.bump_weights_epoch()                          # ... which is why FlatAdamW.step bumps the epoch
+    c = U.pw_weight(conv)
+    assert c is not b and float(c[0, 0]) == 123.0
+    dw = torch.nn.Conv2d(8, 8, 3, padding=1, groups=8, bias=False)
+    r = U.dw_weight_rot(dw)
+    assert torch.equal(r, U.dw_weight(dw, None).flip(0)) and U.dw_weight_rot(dw) is r
