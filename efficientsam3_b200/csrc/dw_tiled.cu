@@ -22,6 +22,8 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, b
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 template <int KS, int STRIDE, int CG, int TH, int TW>
 struct DwTile {
@@ -31,56 +33,90 @@ struct DwTile {
   static constexpr int TILE_BYTES = IH * IW * PIX_BYTES;
   static constexpr int W_FLOATS = KS * KS * CG;
   static constexpr int GPW_FLOATS = (CG / 8) * (8 * 16 + 4);  // grouped-1x1 weights, padded per 8-ch group
-  static constexpr int SMEM = TILE_BYTES + (W_FLOATS + CG + GPW_FLOATS) * 4;
+  static constexpr int WB_FLOATS = W_FLOATS + CG;                      // one (tap weights, bias) set
+  static constexpr int SMEM = 2 * TILE_BYTES + (2 * WB_FLOATS + GPW_FLOATS) * 4;   // double-buffered tile + weights (persistent CTAs)
 };
 
 // x: [B,H,W,*] bf16 with pixel stride ldx, channel window [c_in0, c_in0 + C) ; out likewise (ldo, c_out0).
 // w: [KS*KS][C] fp32 tap-major (scale folded); bias [C] or null.
 // GROUP_PW: after the depthwise, apply a grouped 1x1 with 16-channel groups, wpw [C][16] fp32, no bias.
+// Persistent CTAs over work items (tile, channel group, image): while the strips of item i are computed from one shared-memory
+// buffer, the haloed tile (cp.async) and the weights of item i + gridDim.x stream into the other -- the one-item-per-CTA version was
+// a load -> wait -> compute -> store sequence with nothing overlapped inside a CTA and ran at 1.7-1.9 TB/s with three CTAs per SM
+// (profiles/r2l_table_repvit_m1_1.md).
 template <int KS, int STRIDE, int CG, int TH, int TW, int ACT, bool GROUP_PW>
 __global__ void __launch_bounds__(256) dw_tiled_kernel(const bf16* x, long long ldx, const float* __restrict__ w,
                                                        const float* __restrict__ bias,
                                                        const float* __restrict__ wpw, bf16* out, long long ldo,
-                                                       int H, int W, int C, int Ho, int Wo, int tiles_x) {
+                                                       int H, int W, int C, int Ho, int Wo, int tiles_x, int tiles_per_img,
+                                                       int n_cg, int total_items) {
   using T = DwTile<KS, STRIDE, CG, TH, TW>;
   extern __shared__ __align__(16) uint8_t smem[];
-  uint8_t* s_tile = smem;
-  float* s_w = reinterpret_cast<float*>(smem + T::TILE_BYTES);
-  float* s_b = s_w + T::W_FLOATS;
-  float* s_g = s_b + CG;
+  float* s_wb = reinterpret_cast<float*>(smem + 2 * T::TILE_BYTES);     // [2][W_FLOATS + CG]
+  float* s_g = s_wb + 2 * T::WB_FLOATS;
   constexpr int PAD = KS / 2;
   constexpr int NV = CG / 8;  // 16-byte vectors per pixel
 
-  const int tile = blockIdx.x;
-  const int ty = tile / tiles_x, tx = tile % tiles_x;
-  const int c0 = blockIdx.y * CG;
-  const int b = blockIdx.z;
-  const int oy0 = ty * TH, ox0 = tx * TW;
-  const int iy0 = oy0 * STRIDE - PAD, ix0 = ox0 * STRIDE - PAD;
-
-  // ---- stage the haloed input tile (zero outside the image) and the weights
-  const bf16* xb = x + (long long)b * H * W * ldx + c0;
-  for (int i = threadIdx.x; i < T::IH * T::IW * NV; i += 256) {
-    const int v = i % NV, p = i / NV;
-    const int py = p / T::IW, px = p % T::IW;
-    const int iy = iy0 + py, ix = ix0 + px;
-    const bool ok = (iy >= 0 && iy < H && ix >= 0 && ix < W);
-    const bf16* src = ok ? xb + ((long long)iy * W + ix) * ldx + v * 8 : xb;
-    cp_async16_zfill(s_tile + p * T::PIX_BYTES + v * 16, src, ok);
-  }
-  for (int i = threadIdx.x; i < T::W_FLOATS; i += 256) {
-    const int tap = i / CG, c = i % CG;
-    s_w[i] = w[(long long)tap * C + c0 + c];
-  }
-  for (int i = threadIdx.x; i < CG; i += 256) s_b[i] = bias ? bias[c0 + i] : 0.f;
-  if (GROUP_PW) {
-    for (int i = threadIdx.x; i < CG * 16; i += 256) {
-      const int c = i / 16, k = i % 16;  // output channel c (within block), input k within its 16-group
-      s_g[(c / 8) * (8 * 16 + 4) + (c % 8) * 16 + k] = wpw[(long long)(c0 + c) * 16 + k];
+  // item -> (tile, channel group, image); channel group fastest so that neighbouring CTAs share the input tile in L2
+  auto decode = [&](int item, int& tile, int& c0, int& b) {
+    const int cg = item % n_cg;
+    const int r = item / n_cg;
+    tile = r % tiles_per_img;
+    b = r / tiles_per_img;
+    c0 = cg * CG;
+  };
+  auto stage = [&](int item, int buf) {
+    int tile, c0, b;
+    decode(item, tile, c0, b);
+    const int ty = tile / tiles_x, tx = tile % tiles_x;
+    const int iy0 = ty * TH * STRIDE - PAD, ix0 = tx * TW * STRIDE - PAD;
+    uint8_t* s_tile = smem + buf * T::TILE_BYTES;
+    const bf16* xb = x + (long long)b * H * W * ldx + c0;
+    for (int i = threadIdx.x; i < T::IH * T::IW * NV; i += 256) {
+      const int v = i % NV, p = i / NV;
+      const int py = p / T::IW, px = p % T::IW;
+      const int iy = iy0 + py, ix = ix0 + px;
+      const bool ok = (iy >= 0 && iy < H && ix >= 0 && ix < W);
+      const bf16* src = ok ? xb + ((long long)iy * W + ix) * ldx + v * 8 : xb;
+      cp_async16_zfill(s_tile + p * T::PIX_BYTES + v * 16, src, ok);
     }
-  }
-  cp_async_wait_all();
-  __syncthreads();
+    float* s_w = s_wb + buf * T::WB_FLOATS;
+    for (int i = threadIdx.x; i < T::W_FLOATS; i += 256) {
+      const int tap = i / CG, c = i % CG;
+      s_w[i] = w[(long long)tap * C + c0 + c];
+    }
+    for (int i = threadIdx.x; i < CG; i += 256) s_w[T::W_FLOATS + i] = bias ? bias[c0 + i] : 0.f;
+    cp_async_commit();
+  };
+
+  int item = blockIdx.x;
+  if (item >= total_items) return;
+  int gpw_c0 = -1;
+  stage(item, 0);
+  int buf = 0;
+  for (; item < total_items; item += gridDim.x, buf ^= 1) {
+    const int next = item + gridDim.x;
+    if (next < total_items) {
+      stage(next, buf ^ 1);      // the other buffer was released by the __syncthreads that ended the previous iteration
+      cp_async_wait_1();         // everything but the group just committed: this item's tile has landed
+    } else {
+      cp_async_wait_all();
+    }
+    int tile, c0, b;
+    decode(item, tile, c0, b);
+    if (GROUP_PW && c0 != gpw_c0) {
+      for (int i = threadIdx.x; i < CG * 16; i += 256) {
+        const int c = i / 16, k = i % 16;  // output channel c (within block), input k within its 16-group
+        s_g[(c / 8) * (8 * 16 + 4) + (c % 8) * 16 + k] = wpw[(long long)(c0 + c) * 16 + k];
+      }
+      gpw_c0 = c0;
+    }
+    __syncthreads();
+    const uint8_t* s_tile = smem + buf * T::TILE_BYTES;
+    const float* s_w = s_wb + buf * T::WB_FLOATS;
+    const float* s_b = s_w + T::W_FLOATS;
+    const int ty = tile / tiles_x, tx = tile % tiles_x;
+    const int oy0 = ty * TH, ox0 = tx * TW;
 
   // ---- compute: item = (strip of 4 outputs along x, 8-channel group)
   constexpr int STRIPS_X = TW / 4;
@@ -155,6 +191,8 @@ __global__ void __launch_bounds__(256) dw_tiled_kernel(const bf16* x, long long 
         *reinterpret_cast<uint4*>(out + (((long long)b * Ho + oy) * Wo + ox) * ldo + c0 + v * 8) = pack8(o);
     }
   }
+    __syncthreads();     // every strip of this item is done with the buffer before the next iteration refills it
+  }
 }
 
 template <int KS, int STRIDE, int CG, int TH, int TW, int ACT, bool GROUP_PW>
@@ -168,8 +206,19 @@ static int launch_dw_tiled(const bf16* x, long long ldx, const float* w, const f
     configured = true;
   }
   const int tiles_x = ceil_div(Wo, TW), tiles_y = ceil_div(Ho, TH);
-  dim3 grid(tiles_x * tiles_y, C / CG, B);
-  kern<<<grid, 256, T::SMEM, st>>>(x, ldx, w, bias, wpw, out, ldo, H, W, C, Ho, Wo, tiles_x);
+  const int n_cg = C / CG;
+  const long long total = (long long)tiles_x * tiles_y * n_cg * B;
+  ES3_REQUIRE(total < (1LL << 31), "dw_tiled: too many work items");
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    ES3_CHECK_CUDA(cudaGetDevice(&dev));
+    ES3_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int per_sm = 2 * (T::SMEM + 1024) <= 227 * 1024 ? 2 : 1;       // resident CTAs (shared memory: two buffers each)
+  const long long ctas = (long long)sm_count * per_sm;
+  kern<<<(unsigned)(total < ctas ? total : ctas), 256, T::SMEM, st>>>(x, ldx, w, bias, wpw, out, ldo, H, W, C, Ho, Wo, tiles_x,
+                                                                      tiles_x * tiles_y, n_cg, (int)total);
   ES3_LAUNCH_CHECK("dw_tiled_kernel");
   return 0;
 }
