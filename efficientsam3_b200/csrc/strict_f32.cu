@@ -301,6 +301,118 @@ __global__ void bias_act_res_f32_kernel(const float* __restrict__ x, const float
   if (act_after_res) v = es3_act(v, act);
   y[i] = v;
 }
+
+// 2-D axial RoPE of the q and k heads, in place on fp32 qkv rows (vitdet.py:68-90 apply_rotary_enc): columns [0, rope_cols) are heads
+// of 64 dims = 32 complex pairs (2 i, 2 i + 1); table [positions][32] (cos, sin); position = window-local index when win > 0.
+__global__ void rope_f32_kernel(float* __restrict__ qkv, long long ld, const float2* __restrict__ table, int rope_cols, int H, int W,
+                                int win, long long total_pairs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_pairs) return;
+  const int ppr = rope_cols >> 1;                    // pairs per row
+  const long long row = i / ppr;
+  const int pr = (int)(i - row * ppr);
+  const int t = (int)(row % ((long long)H * W));
+  const int h = t / W, w = t - h * W;
+  const int pidx = win ? (h % win) * win + (w % win) : t;
+  const float2 cs = table[(long long)pidx * 32 + (pr & 31)];
+  float* p = qkv + row * ld + 2 * pr;
+  const float x0 = p[0], x1 = p[1];
+  p[0] = x0 * cs.x - x1 * cs.y;
+  p[1] = x0 * cs.y + x1 * cs.x;
+}
+
+// softmax(q k^T scale + bias) v in fp32 over (optionally windowed) token grids.  Rows of `qkv` are tokens [B*H*W][ld]; head h reads
+// q / k / v at columns q_off + h * head_stride (k_off, v_off alike) -- the ViT trunk's q | k | v blocks (head_stride = D) and TinyViT's
+// per-head (q, k, v) triples (head_stride = 3 D) are both this.  win > 0: win x win windows gathered in place; a window that
+// overhangs the grid takes `pad_row` (one qkv row, the projection of a zero-padded token) for the missing tokens, whose outputs are
+// dropped (tiny_vit.py:352-372).  bias [heads][L][L] optional.  Thread = one query: q and the running output in registers, keys /
+// values staged 64 at a time in shared memory, online softmax with libm expf.
+template <int D>
+__global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, const float* __restrict__ bias,
+                                                       const float* __restrict__ pad_row, int H, int W, int ld, int ldo, int q_off, int k_off,
+                                                       int v_off, int head_stride, int win, int nwx, int nwin, int L, float scale) {
+  __shared__ __align__(16) float s_k[64][D];
+  __shared__ __align__(16) float s_v[64][D];
+  const int head = blockIdx.y;
+  const int b = blockIdx.z / nwin, wi = blockIdx.z % nwin;
+  auto token_row = [&](int l) -> long long {          // -1: a padded position of an overhanging window
+    if (win == 0) return (long long)b * H * W + l;
+    const int wy = wi / nwx, wx = wi % nwx;
+    const int y = wy * win + l / win, x = wx * win + l % win;
+    if (y >= H || x >= W) return -1;
+    return (long long)b * H * W + (long long)y * W + x;
+  };
+  const int lq = blockIdx.x * 128 + threadIdx.x;
+  const long long row_q = lq < L ? token_row(lq) : -1;
+  const bool live = row_q >= 0;
+  float q[D], o[D];
+  {
+    const float* qp = live ? qkv + row_q * ld + q_off + head * head_stride : nullptr;
+#pragma unroll
+    for (int d = 0; d < D; ++d) q[d] = live ? qp[d] * scale : 0.f;
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) o[d] = 0.f;
+  float m = -INFINITY, lsum = 0.f;
+  const float* brow = (bias && lq < L) ? bias + ((long long)head * L + lq) * L : nullptr;
+  for (int k0 = 0; k0 < L; k0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * (D / 4); i += 128) {
+      const int r = i / (D / 4), c4 = i % (D / 4);
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+      if (k0 + r < L) {
+        const long long tr = token_row(k0 + r);
+        const float* base = (tr >= 0 ? qkv + tr * ld : pad_row) + head * head_stride + c4 * 4;
+        kk = *reinterpret_cast<const float4*>(base + k_off);
+        vv = *reinterpret_cast<const float4*>(base + v_off);
+      }
+      *reinterpret_cast<float4*>(&s_k[r][c4 * 4]) = kk;
+      *reinterpret_cast<float4*>(&s_v[r][c4 * 4]) = vv;
+    }
+    __syncthreads();
+    const int nk = min(64, L - k0);
+    for (int j = 0; j < nk; ++j) {
+      float sc = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&s_k[j][d4 * 4]);
+        sc = fmaf(q[d4 * 4], kk.x, sc); sc = fmaf(q[d4 * 4 + 1], kk.y, sc); sc = fmaf(q[d4 * 4 + 2], kk.z, sc); sc = fmaf(q[d4 * 4 + 3], kk.w, sc);
+      }
+      if (brow) sc += brow[k0 + j];
+      if (sc > m) {                                   // new running maximum: rescale what has been accumulated
+        const float corr = expf(m - sc);
+        lsum *= corr;
+#pragma unroll
+        for (int d = 0; d < D; ++d) o[d] *= corr;
+        m = sc;
+      }
+      const float p = expf(sc - m);
+      lsum += p;
+#pragma unroll
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 vv = *reinterpret_cast<const float4*>(&s_v[j][d4 * 4]);
+        o[d4 * 4] = fmaf(p, vv.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(p, vv.y, o[d4 * 4 + 1]);
+        o[d4 * 4 + 2] = fmaf(p, vv.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(p, vv.w, o[d4 * 4 + 3]);
+      }
+    }
+  }
+  if (live) {
+    const float inv = 1.f / lsum;
+    float* op = out + row_q * ldo + head * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) op[d] = o[d] * inv;
+  }
+}
+
+// per-(image, channel) gate: y[b][p][c] = x[b][p][c] * gate[b][c]   (SqueezeExcite excitation, fp32)
+__global__ void scale_channels_f32_kernel(const float* __restrict__ x, const float* __restrict__ gate, float* __restrict__ y, long long HW,
+                                          int C, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long b = i / ((long long)HW * C);
+  y[i] = x[i] * gate[b * C + c];
+}
 }  // namespace
 }  // namespace es3
 
@@ -407,5 +519,47 @@ extern "C" int es3_bias_act_res_f32(const float* x, const float* bias, const flo
   bias_act_res_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, bias, residual, y, total, C, act,
                                                                                             act_after_res);
   ES3_LAUNCH_CHECK("bias_act_res_f32_kernel");
+  return 0;
+}
+
+/* In-place 2-D axial RoPE on columns [0, rope_cols) of fp32 rows (q | k heads of 64 dims); table [positions][32][2] = (cos, sin). */
+extern "C" int es3_rope_f32(float* qkv, long long ld, long long rows, const float* table, int rope_cols, int H, int W, int win, void* stream) {
+  ES3_REQUIRE(rows > 0 && rope_cols % 64 == 0 && H > 0 && W > 0 && rows % ((long long)H * W) == 0, "es3_rope_f32: bad arguments");
+  const long long total = rows * (rope_cols / 2);
+  rope_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(qkv, ld, reinterpret_cast<const float2*>(table),
+                                                                                    rope_cols, H, W, win, total);
+  ES3_LAUNCH_CHECK("rope_f32_kernel");
+  return 0;
+}
+
+/* fp32 softmax attention over token rows (see attn_f32_kernel): ViT trunk = (q_off 0, k_off C, v_off 2C, head_stride D),
+ * TinyViT = (0, D, 2D, 3D) with bias [heads][win^2][win^2] and pad_row; out [B*H*W][heads*D]. */
+extern "C" int es3_attention_f32(const float* qkv, float* out, const float* bias, const float* pad_row, int B, int H, int W, int ld,
+                                 int num_heads, int head_dim, int q_off, int k_off, int v_off, int head_stride, int win, float scale,
+                                 void* stream) {
+  ES3_REQUIRE(head_dim == 32 || head_dim == 64, "es3_attention_f32: head_dim must be 32 or 64 (got %d)", head_dim);
+  ES3_REQUIRE(B > 0 && H > 0 && W > 0 && ld % 4 == 0 && q_off % 4 == 0 && k_off % 4 == 0 && v_off % 4 == 0 && head_stride % 4 == 0,
+              "es3_attention_f32: bad layout");
+  ES3_REQUIRE(win >= 0 && (win == 0 || (H % win == 0 && W % win == 0) || pad_row != nullptr),
+              "es3_attention_f32: windows overhang the %dx%d grid and no pad_row was given", H, W);
+  const int nwx = win ? ceil_div(W, win) : 1, nwin = win ? ceil_div(H, win) * nwx : 1;
+  const int L = win ? win * win : H * W;
+  const dim3 grid(ceil_div(L, 128), num_heads, B * nwin);
+  const int ldo = num_heads * head_dim;
+  if (head_dim == 64)
+    attn_f32_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>(qkv, out, bias, pad_row, H, W, ld, ldo, q_off, k_off, v_off, head_stride,
+                                                                 win, nwx, nwin, L, scale);
+  else
+    attn_f32_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>(qkv, out, bias, pad_row, H, W, ld, ldo, q_off, k_off, v_off, head_stride,
+                                                                 win, nwx, nwin, L, scale);
+  ES3_LAUNCH_CHECK("attn_f32_kernel");
+  return 0;
+}
+
+extern "C" int es3_scale_channels_f32(const float* x, const float* gate, float* y, int B, long long HW, int C, void* stream) {
+  ES3_REQUIRE(B > 0 && HW > 0 && C > 0, "es3_scale_channels_f32: bad shape");
+  const long long total = (long long)B * HW * C;
+  scale_channels_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, gate, y, HW, C, total);
+  ES3_LAUNCH_CHECK("scale_channels_f32_kernel");
   return 0;
 }

@@ -1166,8 +1166,9 @@ __global__ void __launch_bounds__(128) litemla_dqkv_kernel(const bf16* __restric
 }
 
 static int pick_blocks(long long rows, int lanes, int max_blocks) {
-  // enough blocks to fill the GPU, but at least ~64 rows per lane and block so the per-block tail stays small
-  long long want = (rows + (long long)lanes * 64 - 1) / ((long long)lanes * 64);
+  // enough blocks to fill the GPU, but at least ~16 rows per lane and block.  (64 rows per lane made every deep-stage reduction a
+  // 32-iteration dependent load chain on 8..128 CTAs: 39..47 us for 4..67 MB, profiles/r2s_ncu_train_step.md rows 9-57.)
+  long long want = (rows + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
   if (want < 1) want = 1;
   if (want > max_blocks) want = max_blocks;
   return (int)want;

@@ -60,12 +60,9 @@ class Sam3PointPromptSegmenter(nn.Module):
         """images [B,3,S,S] fp32 CUDA, already resized / normalised (mean 0.5, std 0.5 as Sam3Processor does)."""
         neck = self.backbone.vision_backbone
         strict = ops.precision() == "strict"
-        if strict and hasattr(neck.trunk, "forward_tokens"):
-            raise NotImplementedError("strict precision mode covers the EfficientViT student encoder, the FPN neck and the SAM heads; "
-                                      "the SAM3 ViT trunk runs in the bf16 mode only")
-        if hasattr(neck.trunk, "forward_tokens"):       # SAM3 ViT trunk: fp32 token stream -> bf16 NHWC
+        if hasattr(neck.trunk, "forward_tokens"):       # SAM3 ViT trunk: fp32 token stream -> bf16 NHWC (strict: stays fp32)
             tok, (B, h, w) = neck.trunk.forward_tokens(images)
-            feats = ops.add_rows(tok, None, out_bf16=True, out_f32=False)[0].view(B, h, w, -1)
+            feats = (tok if strict else ops.add_rows(tok, None, out_bf16=True, out_f32=False)[0]).view(B, h, w, -1)
         else:                                           # EfficientSAM3 student encoder (model_builder.ListWrapper)
             feats = neck.trunk.forward_nhwc(images)
             B, h, w, _ = feats.shape

@@ -162,6 +162,9 @@ class ViT(nn.Module, NativePlanMixin):
         h = w = S // self.patch_size
         # the reference asserts on the RoPE table shape for any other size (vitdet.py:60-65)
         assert h == self.img_size // self.patch_size, f"ViT built for {self.img_size}px inputs, got {S}"
+        if ops.precision() == "strict":               # fp32 operands / accumulation end to end (strict.py, csrc/strict_f32.cu)
+            from ..strict import vit_tokens
+            return vit_tokens(self, x)
         p = self._plan()
         C, heads = self.embed_dim, self.num_heads
         cols = ops.im2col_patch(x, self.patch_size, p["kp"])

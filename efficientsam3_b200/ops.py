@@ -1227,3 +1227,47 @@ def convt2x2_f32(x, weight, bias=None, act=None, residual=None, act_after_res=Fa
     y = sgemm(x.reshape(-1, Cin), wt)                                            # [B*H*W, 4*Cout]
     y = y.view(B, H, W, 2, 2, Cout).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, Cout).contiguous()
     return bias_act_res_f32(y, bias, act, residual, act_after_res)
+
+
+def rope_f32(qkv, table, rope_cols, H, W, win):
+    """In-place 2-D axial RoPE on columns [0, rope_cols) of fp32 rows; table [positions, 32, 2] fp32 (cos, sin)."""
+    _chk(qkv, torch.float32, "qkv"); _chk(table, torch.float32, "table")
+    _ensure_init(qkv)
+    assert qkv.dim() == 2 and qkv.stride(1) == 1 and table.is_contiguous() and table.shape[1:] == (32, 2)
+    _call("es3_rope_f32", "rope_f32", 2 * qkv.shape[0] * rope_cols * 4, 6 * qkv.shape[0] * rope_cols // 2, qkv.data_ptr(), qkv.stride(0),
+          qkv.shape[0], table.data_ptr(), rope_cols, H, W, win, _stream())
+    return qkv
+
+
+def attention_f32(qkv, B, H, W, heads, head_dim, win, scale, *, layout="blocks", bias=None, pad_row=None):
+    """fp32 softmax attention over token rows qkv [B*H*W, ld] fp32 -> [B*H*W, heads*head_dim] fp32.  layout "blocks": q | k | v column
+    blocks of heads*head_dim (the ViT trunk); "per_head": (q, k, v) triples per head (TinyViT).  win = 0: global; bias [heads, L, L];
+    pad_row [ld] stands in for the tokens an overhanging window lacks."""
+    _chk(qkv, torch.float32, "qkv")
+    _ensure_init(qkv)
+    C = heads * head_dim
+    assert qkv.is_contiguous() and qkv.shape == (B * H * W, 3 * C), (qkv.shape, B, H, W, C)
+    offs = (0, C, 2 * C, head_dim) if layout == "blocks" else (0, head_dim, 2 * head_dim, 3 * head_dim)
+    L = win * win if win else H * W
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+        assert bias.is_contiguous() and bias.shape == (heads, L, L)
+    if pad_row is not None:
+        _chk(pad_row, torch.float32, "pad_row")
+        assert pad_row.is_contiguous() and pad_row.numel() == 3 * C
+    out = torch.empty((B * H * W, C), device=qkv.device, dtype=torch.float32)
+    _call("es3_attention_f32", f"attention_f32[L={L}]", _nb(qkv, out), 4 * B * H * W * L * C, qkv.data_ptr(), out.data_ptr(), _ptr(bias),
+          _ptr(pad_row), B, H, W, 3 * C, heads, head_dim, *offs, win, float(scale), _stream())
+    return out
+
+
+def scale_channels_f32(x, gate):
+    """x [B,H,W,C] fp32 * gate [B,C] fp32."""
+    _chk(x, torch.float32, "x"); _chk(gate, torch.float32, "gate")
+    _ensure_init(x)
+    assert x.is_contiguous() and gate.is_contiguous()
+    B, H, W, C = x.shape
+    y = torch.empty_like(x)
+    _call("es3_scale_channels_f32", "scale_channels_f32", 2 * _nb(x), x.numel(), x.data_ptr(), gate.data_ptr(), y.data_ptr(), B, H * W, C,
+          _stream())
+    return y

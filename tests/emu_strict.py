@@ -105,8 +105,67 @@ def convt2x2_f32(x, weight, bias=None, act=None, residual=None, act_after_res=Fa
     return bias_act_res_f32(v, bias, act, residual, act_after_res)
 
 
+def layernorm(x, gamma, beta, eps=1e-5, *, pos=None, pos_size=0, H=0, W=0, out_bf16=True, out_f32=False):
+    """The fp32-output form of ops.layernorm (the strict graphs never ask for bf16): optional tiled abs-pos add, then LayerNorm."""
+    assert out_f32 and not out_bf16
+    v = x
+    if pos is not None:
+        C = x.shape[1]
+        hh, ww = torch.arange(H).view(H, 1).expand(H, W) % pos_size, torch.arange(W).view(1, W).expand(H, W) % pos_size
+        v = (x.view(-1, H * W, C) + pos[(hh * pos_size + ww).reshape(-1)].to(x.dtype)).view(-1, C)
+    return None, F.layer_norm(v, (v.shape[1],), gamma.to(v.dtype), beta.to(v.dtype), eps)
+
+
+def rope_f32(qkv, table, rope_cols, H, W, win):
+    M = qkv.shape[0]
+    hh, ww = torch.arange(H).view(H, 1).expand(H, W), torch.arange(W).view(1, W).expand(H, W)
+    idx = ((hh % win) * win + (ww % win)) if win else (hh * W + ww)
+    c = torch.view_as_complex(table.to(qkv.dtype).contiguous())[idx.reshape(-1)]            # [HW, 32]
+    t = qkv[:, :rope_cols].reshape(M // (H * W), H * W, rope_cols // 64, 32, 2).contiguous()
+    r = torch.view_as_real(torch.view_as_complex(t) * c.view(1, H * W, 1, 32))
+    qkv[:, :rope_cols] = r.reshape(M, rope_cols)
+    return qkv
+
+
+def attention_f32(qkv, B, H, W, heads, head_dim, win, scale, *, layout="blocks", bias=None, pad_row=None):
+    C = heads * head_dim
+    t = qkv.view(B, H, W, 3 * C)
+    ws = win if win else max(H, W)
+    Hp, Wp = (-(-H // win) * win, -(-W // win) * win) if win else (H, W)
+    if (Hp, Wp) != (H, W):
+        full = pad_row.to(qkv.dtype).view(1, 1, 1, -1).expand(B, Hp, Wp, 3 * C).clone()
+        full[:, :H, :W] = t
+        t = full
+    if win:
+        nh, nw = Hp // win, Wp // win
+        t = t.view(B, nh, win, nw, win, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(B * nh * nw, win * win, 3 * C)
+    else:
+        t = t.reshape(B, H * W, 3 * C)
+    if layout == "blocks":
+        q, k, v = (t[..., i * C:(i + 1) * C].reshape(t.shape[0], t.shape[1], heads, head_dim).transpose(1, 2) for i in range(3))
+    else:
+        u = t.reshape(t.shape[0], t.shape[1], heads, 3 * head_dim).transpose(1, 2)
+        q, k, v = u[..., :head_dim], u[..., head_dim:2 * head_dim], u[..., 2 * head_dim:]
+    a = q @ k.transpose(-1, -2) * scale
+    if bias is not None:
+        a = a + bias.to(a.dtype)
+    o = (torch.softmax(a, dim=-1) @ v).transpose(1, 2).reshape(t.shape[0], t.shape[1], C)
+    if win:
+        o = o.view(B, nh, nw, win, win, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, C)[:, :H, :W]
+    return o.reshape(B * H * W, C).contiguous()
+
+
+def scale_channels_f32(x, gate):
+    return x * gate.view(gate.shape[0], 1, 1, -1)
+
+
+def colsum_f32(src, out):
+    out += src.sum(0)
+    return out
+
+
 PATCHED = ["sgemm", "conv2d_f32", "dwconv_f32", "litemla_attn_f32", "bilinear_nhwc_f32_to_nchw", "attn_few_keys_f32", "ln_rows_gelu_f32",
-           "bias_act_res_f32", "convt2x2_f32"]
+           "bias_act_res_f32", "convt2x2_f32", "layernorm", "rope_f32", "attention_f32", "scale_channels_f32", "colsum_f32"]
 
 
 def install(monkeypatch):

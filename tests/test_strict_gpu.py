@@ -114,6 +114,47 @@ def test_decoder_twins_f32(cuda):
     _close(got, E.convt2x2_f32(xt.double(), wt.double(), bt.double(), act="gelu", residual=r.double(), act_after_res=True).float(), 3e-6, "convt2x2_f32")
 
 
+@pytest.mark.parametrize("B,H,W,heads,hd,win,layout,with_bias", [
+    (2, 16, 16, 4, 64, 8, "blocks", False),        # ViT trunk: windowed block
+    (1, 24, 24, 2, 64, 0, "blocks", False),        # ViT trunk: global block (L = 576: several key chunks and query tiles)
+    (2, 14, 14, 3, 32, 7, "per_head", True),       # TinyViT: exact windows + relative bias
+    (2, 10, 10, 2, 32, 7, "per_head", True),       # TinyViT: overhanging windows -> pad_row
+    (1, 5, 5, 5, 32, 7, "per_head", True),         # TinyViT: one window larger than the grid
+])
+def test_attention_f32(cuda, B, H, W, heads, hd, win, layout, with_bias):
+    from efficientsam3_b200 import ops
+    g = _g(B * 100 + H + heads)
+    C = heads * hd
+    L = win * win if win else H * W
+    qkv = torch.randn(B * H * W, 3 * C, generator=g)
+    bias = torch.randn(heads, L, L, generator=g) if with_bias else None
+    pad = torch.randn(3 * C, generator=g) if (win and (H % win or W % win)) else None
+    scale = hd ** -0.5
+    got = ops.attention_f32(qkv.to(cuda), B, H, W, heads, hd, win, scale, layout=layout, bias=None if bias is None else bias.to(cuda),
+                            pad_row=None if pad is None else pad.to(cuda))
+    ref = E.attention_f32(qkv.double(), B, H, W, heads, hd, win, scale, layout=layout, bias=None if bias is None else bias.double(),
+                          pad_row=None if pad is None else pad.double()).float()
+    _close(got, ref, 3e-6, f"attention_f32 {layout} win={win}")
+
+
+@pytest.mark.parametrize("win", [0, 4])
+def test_rope_and_scale_channels_f32(cuda, win):
+    from efficientsam3_b200 import ops
+    from efficientsam3_b200.model.vitdet import compute_axial_cis
+    g = _g(17 + win)
+    B, H, W, heads = 2, 8, 8, 3
+    C = heads * 64
+    qkv = torch.randn(B * H * W, 3 * C, generator=g)
+    end = win if win else H
+    table = torch.view_as_real(compute_axial_cis(64, end, end)).float().contiguous()
+    got = ops.rope_f32(qkv.clone().to(cuda), table.to(cuda), 2 * C, H, W, win)
+    ref = E.rope_f32(qkv.double().clone(), table.double(), 2 * C, H, W, win).float()
+    _close(got, ref, 1e-6, "rope_f32")
+    assert torch.equal(got[:, 2 * C:].cpu(), qkv[:, 2 * C:])              # the v block is untouched
+    x, gate = torch.randn(2, 5, 7, 48, generator=g), torch.rand(2, 48, generator=g)
+    assert torch.equal(ops.scale_channels_f32(x.to(cuda), gate.to(cuda)).cpu(), E.scale_channels_f32(x, gate))
+
+
 # ------------------------------------------------------------------------------------------------ student encoders
 def _student(name, img, embed, sd, dev):
     from efficientsam3_b200.stage1.model import build_image_student_model
@@ -123,7 +164,12 @@ def _student(name, img, embed, sd, dev):
     return m.to(dev).eval()
 
 
-@pytest.mark.parametrize("fixture,name", [("evm_160", "efficientvit_b1"), ("ev_b0_160", "efficientvit_b0"), ("ev_b2_192", "efficientvit_b2")])
+STUDENTS = [("evm_160", "efficientvit_b1"), ("ev_b0_160", "efficientvit_b0"), ("ev_b2_192", "efficientvit_b2"), ("rvm_160", "repvit_m1_1"),
+            ("rv_m0_9_128", "repvit_m0_9"), ("rv_m2_3_128", "repvit_m2_3"), ("tvm_160", "tiny_vit_11m"), ("tv_5m_160", "tiny_vit_5m"),
+            ("tv_21m_160", "tiny_vit_21m")]
+
+
+@pytest.mark.parametrize("fixture,name", STUDENTS)
 def test_strict_student_matches_reference_fixture(cuda, fixture, name):
     from efficientsam3_b200 import ops
     g = load_golden(fixture)
@@ -141,6 +187,50 @@ def test_strict_student_matches_reference_fixture(cuda, fixture, name):
     assert out.shape == ref.shape and l2 <= EMB_TOL and mx <= EMB_TOL, (l2, mx)
     assert torch.equal(out, again)                           # bit-reproducible
     assert rel_l2(fast.cpu(), ref) > 10 * l2                 # and the mode switch really switched
+
+
+def test_strict_vit_trunk_matches_reference_fixture(cuda):
+    """The SAM3 ViT trunk (the teacher) in the strict mode: RoPE, windowed + global attention, abs-pos tiling, all fp32."""
+    from efficientsam3_b200 import ops
+    from efficientsam3_b200.model.vitdet import create_sam3_vit_backbone
+    g = load_golden("vit_small_112")
+    cfg = eval(str(g["cfg"]))
+    m = create_sam3_vit_backbone(**cfg)
+    m.load_state_dict(sd_from_keys(g["keys"], int(g["seed_w"])), strict=False)
+    m = m.to(cuda).eval()
+    x = torch.randn(int(g["batch"]), 3, cfg["img_size"], cfg["img_size"], generator=_g(int(g["seed_x"]))).to(cuda)
+    with ops.strict_precision():
+        out = m(x)[-1]
+        again = m(x)[-1]
+    fast = m(x)[-1]
+    ref = torch.as_tensor(g["out"])
+    l2, mx = rel_l2(out.cpu(), ref), max_err_over_scale(out.cpu(), ref)
+    print(f"vit_small_112: strict rel-L2 {l2:.3e} max/scale {mx:.3e}   (bf16 mode rel-L2 {rel_l2(fast.cpu(), ref):.3e})")
+    assert out.shape == ref.shape and l2 <= EMB_TOL and mx <= EMB_TOL, (l2, mx)
+    assert torch.equal(out, again) and rel_l2(fast.cpu(), ref) > 10 * l2
+
+
+def test_strict_teacher_geometry_vs_oracle(cuda):
+    """Full-width teacher geometry (1008 px, 72 x 72 tokens, 24-windows, dim 1024, 16 heads; depth 3 so the CPU oracle takes seconds)
+    through SAM3ImageTeacherEncoder in the strict mode."""
+    from efficientsam3_b200 import ops
+    from efficientsam3_b200.stage1.model import SAM3ImageTeacherEncoder
+    from oracle import vitdet as O
+    from oracle.weights import fill_state_dict
+    over = dict(depth=3, global_att_blocks=(2,))
+    t = SAM3ImageTeacherEncoder(embed_size=72, vit_overrides=over)
+    vit = t.sam3.backbone.vision_backbone.trunk
+    sd = {k: v for k, v in fill_state_dict(vit.state_dict(), 35).items() if not v.is_complex()}
+    vit.load_state_dict(sd, strict=False)
+    x = torch.randn(1, 3, 1008, 1008, generator=_g(10))
+    from efficientsam3_b200.model.vitdet import SAM3_VIT_KWARGS
+    with torch.no_grad():
+        ref = O.vit_trunk(sd, "", x, dict(SAM3_VIT_KWARGS, **over))
+    with ops.strict_precision():
+        out = t.to(cuda)(x.to(cuda)).cpu()
+    l2, mx = rel_l2(out, ref), max_err_over_scale(out, ref)
+    print(f"teacher geometry (depth 3): strict rel-L2 {l2:.3e} max/scale {mx:.3e}")
+    assert out.shape == ref.shape and l2 <= EMB_TOL and mx <= EMB_TOL, (l2, mx)
 
 
 def test_strict_evm_at_the_headline_shape_vs_oracle(cuda):

@@ -285,15 +285,23 @@ def _student(name, img, embed, seed=3):
     return m
 
 
-def _oracle_grads(sd0, x, teacher, img, sizes, variant, embed, bn_train):
+def _oracle_grads(sd0, x, teacher, img, sizes, variant, embed, bn_train, device="cpu", autocast=None):
+    """Autograd of the oracle: fp32 on the CPU (the reference), or -- device="cuda", autocast=dtype -- the same graph the way the
+    reference trains it (torch.autocast around the student forward, train_image_encoder_stage1.py:199-203), as a yardstick for what
+    reduced-precision activations alone do to these gradients."""
+    import contextlib
     from oracle import efficientvit as O
     from oracle.kd_loss import kd_loss
-    sd = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v.clone()) for k, v in sd0.items()}
-    if bn_train:
-        with O.bn_batch_stats():
+    sd = {k: (v.clone().to(device).requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v.clone().to(device))
+          for k, v in sd0.items()}
+    x, teacher = x.to(device), teacher.to(device)
+    with (torch.autocast("cuda", dtype=autocast) if autocast is not None else contextlib.nullcontext()):
+        if bn_train:
+            with O.bn_batch_stats():
+                out = O.image_student_encoder(sd, x, embed, variant)
+        else:
             out = O.image_student_encoder(sd, x, embed, variant)
-    else:
-        out = O.image_student_encoder(sd, x, embed, variant)
+    out = out.float()
     loss, _, _ = kd_loss(out, teacher, img, sizes, 1.0)
     loss.backward()
     return out.detach(), loss.item(), sd
@@ -334,6 +342,17 @@ def test_student_training_step_matches_oracle_autograd(cuda, name, variant, bn_t
     print(f"{name} bn_train={bn_train}: out rel-L2 {rel_out:.3e}, loss {loss.item():.5f} vs {ref_loss:.5f}, all-gradient rel-L2 {rel_all:.3e}")
     assert rel_out < tol_out, rel_out
     assert rel_all < tol_all, rel_all
+    if bn_train:
+        # yardstick: the SAME fp32 oracle graph under torch.autocast (how the reference itself trains) against the fp32 oracle.  The
+        # batch-statistics gradients of this random-weight fixture move by a comparable amount from reduced-precision activations
+        # alone, i.e. the distance above is the precision class, not a graph error (the graph is exact in fp64: tests/test_train_cpu.py)
+        for dt in (torch.bfloat16, torch.float16):
+            _, _, sda = _oracle_grads(sd0, x, teacher, img, sizes, variant, embed, True, device=cuda, autocast=dt)
+            n = sum((sda[k].grad.cpu().double() - sd[k].grad.double()).pow(2).sum().item() for k, _ in m.named_parameters())
+            rel_auto = (n / den) ** 0.5
+            print(f"  torch.autocast({dt}) oracle vs fp32 oracle: all-gradient rel-L2 {rel_auto:.3e}")
+            if dt is torch.bfloat16:
+                assert rel_all < max(3.0 * rel_auto, 0.1), (rel_all, rel_auto)
     if bn_train:
         for k, v in m.state_dict().items():
             if k.endswith("num_batches_tracked"):
