@@ -97,6 +97,7 @@ SIGNATURES: dict[str, list] = {
     "es3_attn_few_keys_f32": [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp],
     "es3_ln_rows_gelu_f32": [_vp, _vp, _vp, _f, _vp, _ll, _i, _vp],
     "es3_bias_act_res_f32": [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp],
+    "es3_ln_rows_f32": [_vp, _vp, _vp, _f, _vp, _ll, _i, _vp],
     "es3_rope_f32": [_vp, _ll, _ll, _vp, _i, _i, _i, _i, _vp],
     "es3_attention_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
     "es3_scale_channels_f32": [_vp, _vp, _vp, _i, _ll, _i, _vp],

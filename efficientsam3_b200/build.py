@@ -64,7 +64,9 @@ def build(verbose: bool = False, force: bool = False) -> Path:
         list(ex.map(run, jobs))
     objs = [str(OBJ / (s.stem + ".o")) for s in srcs]
     if jobs or force or not LIB.exists():
-        run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs, "-lcudart"])
+        tmp = LIB.with_suffix(".so.tmp")     # link beside the target, then rename: a reader never sees a half-written library
+        run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *objs, "-lcudart"])
+        os.replace(tmp, LIB)
     return LIB
 
 

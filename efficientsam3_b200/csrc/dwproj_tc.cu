@@ -154,7 +154,8 @@ dwproj_tc_kernel(const __grid_constant__ CUtensorMap tm_mid, const __grid_consta
       for (int c = 0; c < NC; ++c, ++g) {
         ptx::mbar_wait(bar_a + (g & 1), (uint32_t)((g >> 1) & 1));
         const uint32_t u_a = ptx::smem_u32(s_a + (g & 1) * L::A_STAGE);
-        // ---- depthwise 3x3: warp -> channel group cg (16 ch), m-tiles (tile rows) hsel, hsel + 2, ...
+        // ---- depthwise 3x3: warp -> channel group cg (16 ch), four CONSECUTIVE tile rows hsel*4 .. hsel*4+3: per kx the six
+        // input-row fragments are loaded once and shared by the three ky taps of each output row (18 ldmatrix.x4 per chunk, was 36)
         const int cg = q;
         const bf16* wd = s_wdw + c * 9 * 64 + cg * 16 + g4;
         float dacc[4][2][4];
@@ -163,19 +164,22 @@ dwproj_tc_kernel(const __grid_constant__ CUtensorMap tm_mid, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 2; ++i) { dacc[m][i][0] = dacc[m][i][1] = dacc[m][i][2] = dacc[m][i][3] = 0.f; }
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+        for (int kx = 0; kx < 3; ++kx) {
+          uint32_t af[6][4];
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
+          for (int r = 0; r < 6; ++r) {
+            const int row = (hsel * 4 + r) * DP_HW + a_row + kx;                // pixel row of the swizzled tile
+            ldsm_x4(u_a + row * 128 + (((cg * 2 + a_kh) ^ (row & 7)) << 4), af[r][0], af[r][1], af[r][2], af[r][3]);
+          }
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
             const uint32_t w_lo = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * 64]);
             const uint32_t w_hi = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * 64 + 8]);
             const uint32_t b_lo = dvalid ? (w_lo << dshift) : 0u, b_hi = dvalid ? (w_hi << dshift) : 0u;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-              const int row = (hsel + 2 * m + ky) * DP_HW + a_row + kx;         // pixel row of the swizzled tile
-              uint32_t af[4];
-              ldsm_x4(u_a + row * 128 + (((cg * 2 + a_kh) ^ (row & 7)) << 4), af[0], af[1], af[2], af[3]);
-              mma_1688(dacc[m][0], af[0], af[1], b_lo);
-              mma_1688(dacc[m][1], af[2], af[3], b_hi);
+              mma_1688(dacc[m][0], af[m + ky][0], af[m + ky][1], b_lo);
+              mma_1688(dacc[m][1], af[m + ky][2], af[m + ky][3], b_hi);
             }
           }
         }
@@ -183,7 +187,7 @@ dwproj_tc_kernel(const __grid_constant__ CUtensorMap tm_mid, const __grid_consta
         const float* b2 = s_b2 + c * DP_MC;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          const int mt = hsel + 2 * m;
+          const int mt = hsel * 4 + m;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const int p = mt * DP_TW + g4 + half * 8;

@@ -129,7 +129,7 @@ __device__ __forceinline__ void mma1688(float* d, uint32_t a0, uint32_t a1, uint
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(b0));
 }
-__global__ void __launch_bounds__(256) litemla_aggreg_dwpw_kernel(const bf16* ms_in, bf16* ms_out, long long ld,
+__global__ void __launch_bounds__(256, 3) litemla_aggreg_dwpw_kernel(const bf16* ms_in, bf16* ms_out, long long ld,
                                                                   const bf16* __restrict__ wdw, const bf16* __restrict__ wpw,
                                                                   int H, int W, int tiles_x) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -166,20 +166,25 @@ __global__ void __launch_bounds__(256) litemla_aggreg_dwpw_kernel(const bf16* ms
 #pragma unroll
     for (int n = 0; n < 2; ++n) { acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f; }
 
+  // warp -> x-half xh (16 pixels) and four CONSECUTIVE output rows y0 .. y0+3: per kx the eight input-row fragments are loaded
+  // once and shared by the five ky taps of each output row -- 40 ldmatrix.x4 per warp instead of 100 (the shared-memory pipe was
+  // this kernel's busiest unit at 70 %, profiles/r2s_ncu_evm_forward.md)
+  const int xh = warp & 1, y0 = (warp >> 1) * 4;
 #pragma unroll 1
-  for (int ky = 0; ky < 5; ++ky) {
+  for (int kx = 0; kx < 5; ++kx) {
+    uint32_t af[8][4];
 #pragma unroll
-    for (int kx = 0; kx < 5; ++kx) {
+    for (int r = 0; r < 8; ++r)
+      ldsm4(u_tile + ((y0 + r) * AG_IW + xh * 16 + a_row + kx) * AG_PS + a_kh * 16, af[r][0], af[r][1], af[r][2], af[r][3]);
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
       const uint32_t w_lo = (uint32_t)__bfloat16_as_ushort(s_wd[(ky * 5 + kx) * 16 + g]);
       const uint32_t w_hi = (uint32_t)__bfloat16_as_ushort(s_wd[(ky * 5 + kx) * 16 + 8 + g]);
       const uint32_t b_lo = dvalid ? (w_lo << dshift) : 0u, b_hi = dvalid ? (w_hi << dshift) : 0u;
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const int y = warp * 2 + (m >> 1), x0 = (m & 1) * 16;
-        uint32_t af[4];
-        ldsm4(u_tile + ((y + ky) * AG_IW + x0 + a_row + kx) * AG_PS + a_kh * 16, af[0], af[1], af[2], af[3]);
-        mma1688(acc[m][0], af[0], af[1], b_lo);
-        mma1688(acc[m][1], af[2], af[3], b_hi);
+        mma1688(acc[m][0], af[m + ky][0], af[m + ky][1], b_lo);
+        mma1688(acc[m][1], af[m + ky][2], af[m + ky][3], b_hi);
       }
     }
   }
@@ -194,11 +199,11 @@ __global__ void __launch_bounds__(256) litemla_aggreg_dwpw_kernel(const bf16* ms
     float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     mma16816(o[0], pa, p0, p1);
     mma16816(o[1], pa, p2, p3);
-    const int oy = oy0 + warp * 2 + (m >> 1);
+    const int oy = oy0 + y0 + m;
     if (oy >= H) continue;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      const int ox = ox0 + (m & 1) * 16 + g + half * 8;
+      const int ox = ox0 + xh * 16 + g + half * 8;
       if (ox >= W) continue;
       bf16* dst = ob + ((long long)oy * W + ox) * ld + t4 * 2;
       *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(o[0][half * 2], o[0][half * 2 + 1]);

@@ -264,7 +264,10 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         compute_bar_sync();                              // s_mid complete
         if (c > 0) ptx::mbar_wait(bar_proj, (uint32_t)((gc - 1) & 1));   // project(gc-1) has finished reading s_dw
 
-        // ---- depthwise 3x3 on tensor cores (diagonal-B MMAs): warp -> channel group cg (16 ch), m-tiles hsel, hsel+2, ...
+        // ---- depthwise 3x3 on tensor cores (diagonal-B MMAs): warp -> channel group cg (16 ch), output rows hsel*4 .. hsel*4+3.
+        // Four CONSECUTIVE output rows share their input rows: per kx the warp loads the 6 input-row fragments once and feeds
+        // them to the 3 ky taps of each output row -- 18 ldmatrix.x4 per chunk instead of 36 (the kernel's busiest unit is the
+        // shared-memory pipe, 54 % LSU + 9 % UMMA wavefronts, profiles/r2s_ncu_evm_forward.md; ldmatrix was 2/3 of its loads).
         {
           const int cg = q;
           const bf16* wd = s_wdw + c * 9 * 64 + cg * 16 + g;
@@ -274,26 +277,27 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 2; ++i) { dacc[m][i][0] = dacc[m][i][1] = dacc[m][i][2] = dacc[m][i][3] = 0.f; }
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
+          for (int kx = 0; kx < 3; ++kx) {
+            uint32_t af[6][4];
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
+            for (int r = 0; r < 6; ++r)
+              ldsm_x4(u_mid + ((hsel * 4 + r) * MT_HW + a_row + kx) * MT_RS_MID + (cg * 16 + a_kh * 8) * 2, af[r][0], af[r][1], af[r][2], af[r][3]);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
               const uint32_t w_lo = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * 64]);
               const uint32_t w_hi = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * 64 + 8]);
               const uint32_t b_lo = dvalid ? (w_lo << dshift) : 0u, b_hi = dvalid ? (w_hi << dshift) : 0u;
 #pragma unroll
               for (int m = 0; m < 4; ++m) {
-                const int mt = hsel + 2 * m;
-                uint32_t af[4];
-                ldsm_x4(u_mid + ((mt + ky) * MT_HW + a_row + kx) * MT_RS_MID + (cg * 16 + a_kh * 8) * 2, af[0], af[1], af[2], af[3]);
-                mma_1688(dacc[m][0], af[0], af[1], b_lo);   // channels cg*16 + 0..7
-                mma_1688(dacc[m][1], af[2], af[3], b_hi);   // channels cg*16 + 8..15
+                mma_1688(dacc[m][0], af[m + ky][0], af[m + ky][1], b_lo);   // channels cg*16 + 0..7
+                mma_1688(dacc[m][1], af[m + ky][2], af[m + ky][3], b_hi);   // channels cg*16 + 8..15
               }
             }
           }
           const float* b2 = s_b2 + c * MT_MC;
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
-            const int mt = hsel + 2 * m;
+            const int mt = hsel * 4 + m;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const int p = mt * MT_TW + g + half * 8;     // output pixel = A-operand row of the project UMMA

@@ -33,6 +33,11 @@ constexpr int S2_IH = 2 * S2_TH + 1, S2_IW = 2 * S2_TW + 1;  // 9 x 33 input pix
 constexpr int S2_PIN = S2_IH * S2_IW;                      // 297
 constexpr int S2_MC = 32;                                  // expanded-channel chunk
 constexpr int S2_RS_MID = S2_MC * 2 + 16;                  // 80-byte rows: conflict-free 16-byte stores / ldmatrix
+// s_mid keeps the EVEN and ODD input columns of every input row in separate planes (even column 2j -> slot j, odd column 2j+1 ->
+// slot S2_ODD + j).  A stride-2 tap then walks CONSECUTIVE 80-byte rows (8 rows -> 8 distinct 4-bank groups); walking every other
+// row of an interleaved tile (160-byte stride) made every ldmatrix 2-way conflicted: 25.8 M of 78 M load wavefronts at 16->64->32
+// (profiles/r2s_ncu/r2s_fwd_raw.csv.gz).  S2_ODD = 20 also keeps the expand epilogue's 16-byte stores (lanes alternate planes) apart.
+constexpr int S2_ODD = 20, S2_PW = S2_ODD + S2_TW;           // slots per input row: 17 even | 3 unused | 16 odd
 constexpr int S2_THREADS = 288;
 
 template <int MID, int COUT, int WSTAGES>
@@ -41,7 +46,7 @@ struct S2Smem {
   static constexpr int W1 = 2 * S2_MC * 128;
   static constexpr int W3_STAGE = COUT * 128;
   static constexpr int OFF_W1 = IN, OFF_W3 = OFF_W1 + W1, OFF_DW = OFF_W3 + WSTAGES * W3_STAGE, OFF_MID = OFF_DW + 128 * 128;
-  static constexpr int OFF_WDW = OFF_MID + (S2_PIN * S2_RS_MID + 15) / 16 * 16;   // bf16 [MID/32][9][32]
+  static constexpr int OFF_WDW = OFF_MID + (S2_IH * S2_PW * S2_RS_MID + 15) / 16 * 16;   // bf16 [MID/32][9][32]
   static constexpr int OFF_PAR = OFF_WDW + 9 * MID * 2;
   static constexpr int OFF_BAR = OFF_PAR + (3 * MID + 2 * COUT) * 4;
   static constexpr int TOTAL = OFF_BAR + 128;
@@ -218,7 +223,8 @@ mbconv_tc_s2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
             const bool in = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
             const float4* sc = reinterpret_cast<const float4*>(s_s1 + c * S2_MC);
             const float4* bi = reinterpret_cast<const float4*>(s_b1 + c * S2_MC);
-            uint4* dst = reinterpret_cast<uint4*>(s_mid + row * S2_RS_MID);
+            const int lx = row % S2_IW;
+            uint4* dst = reinterpret_cast<uint4*>(s_mid + ((row / S2_IW) * S2_PW + ((lx & 1) ? S2_ODD + (lx >> 1) : (lx >> 1))) * S2_RS_MID);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 s0 = sc[2 * j], s1v = sc[2 * j + 1], b0 = bi[2 * j], b1v = bi[2 * j + 1];
@@ -253,7 +259,9 @@ mbconv_tc_s2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
               const uint32_t w_hi = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * S2_MC + 8]);
               const uint32_t b_lo = dvalid ? (w_lo << dshift) : 0u, b_hi = dvalid ? (w_hi << dshift) : 0u;
               uint32_t af[4];
-              ldsm_x4(u_mid + ((2 * mt + ky) * S2_IW + 2 * a_row + kx) * S2_RS_MID + (cg * 16 + a_kh * 8) * 2, af[0], af[1], af[2], af[3]);
+              // input column 2 * a_row + kx: kx = 0 / 2 -> even slots a_row / a_row + 1, kx = 1 -> odd slot a_row
+              ldsm_x4(u_mid + ((2 * mt + ky) * S2_PW + a_row + (kx == 1 ? S2_ODD : (kx >> 1))) * S2_RS_MID + (cg * 16 + a_kh * 8) * 2,
+                      af[0], af[1], af[2], af[3]);
               mma_1688(dacc[0], af[0], af[1], b_lo);
               mma_1688(dacc[1], af[2], af[3], b_hi);
             }

@@ -289,6 +289,24 @@ __global__ void ln_rows_gelu_f32_kernel(const float* __restrict__ x, const float
   }
 }
 
+// y = LayerNorm(x) * w + b over rows of any width C, fp32 in / out, two-pass (mean, then centred variance) per row: warp = row.
+// nn.LayerNorm of the strict TinyViT walk (tiny_vit.py:235, 259: C = 64 .. 576, not multiples of 128).
+__global__ void ln_rows_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float eps,
+                                   float* __restrict__ y, long long M, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* xr = x + row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / C;
+  float qv = 0.f;
+  for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; qv = fmaf(d, d, qv); }
+  const float rstd = 1.f / sqrtf(warp_sum(qv) / C + eps);
+  float* yr = y + row * C;
+  for (int c = lane; c < C; c += 32) yr[c] = (xr[c] - mean) * rstd * w[c] + bias[c];
+}
+
 // y[m][c] = act(x[m][c] + bias[c]) + residual  |  act(x + bias + residual)   (elementwise tail of the strict ConvTranspose path)
 __global__ void bias_act_res_f32_kernel(const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ residual,
                                         float* __restrict__ y, long long total, int C, int act, int act_after_res) {
@@ -510,6 +528,13 @@ extern "C" int es3_ln_rows_gelu_f32(const float* x, const float* w, const float*
   ES3_REQUIRE(C % 32 == 0 && C <= 128, "es3_ln_rows_gelu_f32: C=%d must be a multiple of 32 and <= 128", C);
   ln_rows_gelu_f32_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(x, w, bias, eps, y, M, C);
   ES3_LAUNCH_CHECK("ln_rows_gelu_f32_kernel");
+  return 0;
+}
+
+extern "C" int es3_ln_rows_f32(const float* x, const float* w, const float* bias, float eps, float* y, long long M, int C, void* stream) {
+  ES3_REQUIRE(M > 0 && C > 0, "es3_ln_rows_f32: bad shape");
+  ln_rows_f32_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(x, w, bias, eps, y, M, C);
+  ES3_LAUNCH_CHECK("ln_rows_f32_kernel");
   return 0;
 }
 

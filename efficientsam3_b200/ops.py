@@ -1229,6 +1229,18 @@ def convt2x2_f32(x, weight, bias=None, act=None, residual=None, act_after_res=Fa
     return bias_act_res_f32(y, bias, act, residual, act_after_res)
 
 
+def ln_rows_f32(x, w, b, eps):
+    """nn.LayerNorm over the rows of an fp32 matrix of any width."""
+    _chk(x, torch.float32, "x")
+    _ensure_init(x)
+    assert x.dim() == 2 and x.is_contiguous()
+    M, C = x.shape
+    y = torch.empty_like(x)
+    _call("es3_ln_rows_f32", "ln_rows_f32", 2 * _nb(x), 8 * M * C, x.data_ptr(), w.data_ptr(), b.data_ptr(), float(eps), y.data_ptr(), M, C,
+          _stream())
+    return y
+
+
 def rope_f32(qkv, table, rope_cols, H, W, win):
     """In-place 2-D axial RoPE on columns [0, rope_cols) of fp32 rows; table [positions, 32, 2] fp32 (cos, sin)."""
     _chk(qkv, torch.float32, "qkv"); _chk(table, torch.float32, "table")

@@ -163,8 +163,7 @@ def repvit_backbone(rv, x):
 
 # ------------------------------------------------------------------------------------------------ TinyViT
 def _ln(x2, norm):
-    return ops.layernorm(x2, norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous(), norm.eps, out_bf16=False,
-                         out_f32=True)[1]
+    return ops.ln_rows_f32(x2, norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous(), norm.eps)
 
 
 def _linear(l, x2, act=None, residual=None):

@@ -402,8 +402,9 @@ int es3_ln_rows_gelu_f32(const float* x, const float* w, const float* bias, floa
 int es3_bias_act_res_f32(const float* x, const float* bias, const float* residual, float* y, long long total, int C, int act,
                          int act_after_res, void* stream);
 
-/* More of the strict mode: in-place 2-D axial RoPE on fp32 q | k heads (vitdet.py:68-90), fp32 softmax attention on the ViT qkv layout
+/* More of the strict mode: nn.LayerNorm over rows of any width (tiny_vit.py:235, 259), in-place 2-D axial RoPE on fp32 q | k heads (vitdet.py:68-90), fp32 softmax attention on the ViT qkv layout
  * (windows gathered in place, vitdet.py:93-139, 466-515; TinyViT's biased, zero-padded windows, tiny_vit.py:258-287, 352-372), SqueezeExcite gating y = x * gate[b][c] (timm SqueezeExcite, repvit.py:23,136). */
+int es3_ln_rows_f32(const float* x, const float* w, const float* bias, float eps, float* y, long long M, int C, void* stream);
 int es3_rope_f32(float* qkv, long long ld, long long rows, const float* table, int rope_cols, int H, int W, int win, void* stream);
 int es3_attention_f32(const float* qkv, float* out, const float* bias, const float* pad_row, int B, int H, int W, int ld, int num_heads,
                       int head_dim, int q_off, int k_off, int v_off, int head_stride, int win, float scale, void* stream);

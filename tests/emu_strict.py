@@ -116,6 +116,10 @@ def layernorm(x, gamma, beta, eps=1e-5, *, pos=None, pos_size=0, H=0, W=0, out_b
     return None, F.layer_norm(v, (v.shape[1],), gamma.to(v.dtype), beta.to(v.dtype), eps)
 
 
+def ln_rows_f32(x, w, b, eps):
+    return F.layer_norm(x, (x.shape[-1],), w.to(x.dtype), b.to(x.dtype), eps)
+
+
 def rope_f32(qkv, table, rope_cols, H, W, win):
     M = qkv.shape[0]
     hh, ww = torch.arange(H).view(H, 1).expand(H, W), torch.arange(W).view(1, W).expand(H, W)
@@ -165,7 +169,7 @@ def colsum_f32(src, out):
 
 
 PATCHED = ["sgemm", "conv2d_f32", "dwconv_f32", "litemla_attn_f32", "bilinear_nhwc_f32_to_nchw", "attn_few_keys_f32", "ln_rows_gelu_f32",
-           "bias_act_res_f32", "convt2x2_f32", "layernorm", "rope_f32", "attention_f32", "scale_channels_f32", "colsum_f32"]
+           "bias_act_res_f32", "convt2x2_f32", "layernorm", "ln_rows_f32", "rope_f32", "attention_f32", "scale_channels_f32", "colsum_f32"]
 
 
 def install(monkeypatch):

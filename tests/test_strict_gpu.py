@@ -151,6 +151,10 @@ def test_rope_and_scale_channels_f32(cuda, win):
     ref = E.rope_f32(qkv.double().clone(), table.double(), 2 * C, H, W, win).float()
     _close(got, ref, 1e-6, "rope_f32")
     assert torch.equal(got[:, 2 * C:].cpu(), qkv[:, 2 * C:])              # the v block is untouched
+    for C in (64, 160, 576):
+        xl, wl, bl = torch.randn(77, C, generator=g) * 3 + 1, torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+        _close(ops.ln_rows_f32(xl.to(cuda), wl.to(cuda), bl.to(cuda), 1e-5), E.ln_rows_f32(xl.double(), wl.double(), bl.double(), 1e-5).float(),
+               2e-6, f"ln_rows_f32 C={C}")
     x, gate = torch.randn(2, 5, 7, 48, generator=g), torch.rand(2, 48, generator=g)
     assert torch.equal(ops.scale_channels_f32(x.to(cuda), gate.to(cuda)).cpu(), E.scale_channels_f32(x, gate))
 
