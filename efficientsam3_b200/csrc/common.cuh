@@ -121,6 +121,35 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return u;
 }
 
+// Packed fp32x2 arithmetic (sm_100a FFMA2 / FMUL2 / FADD2): one instruction, two IEEE fp32 results -- bit-identical to the scalar
+// forms, half the issue slots and half the fma-pipe cycles (scripts/ffma2_bench.cu measures the rates).  The compiler does not form
+// these from scalar code; the operands have to be 64-bit register pairs.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ void unpack8_2(const uint4& u, float2* f) {
+  f[0] = unpack_bf16x2(u.x); f[1] = unpack_bf16x2(u.y); f[2] = unpack_bf16x2(u.z); f[3] = unpack_bf16x2(u.w);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -10,6 +10,8 @@
 //
 // Block: 256 threads.  Tile: TH x TW outputs x CG channels.  smem pixel stride = CG*2 + 16 bytes
 // (the pad keeps 16-byte accesses of 8 consecutive pixels on distinct bank groups).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace es3 {
@@ -45,7 +47,7 @@ struct DwTile {
 // a load -> wait -> compute -> store sequence with nothing overlapped inside a CTA and ran at 1.7-1.9 TB/s with three CTAs per SM
 // (profiles/r2l_table_repvit_m1_1.md).
 template <int KS, int STRIDE, int CG, int TH, int TW, int ACT, bool GROUP_PW>
-__global__ void __launch_bounds__(256) dw_tiled_kernel(const bf16* x, long long ldx, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, (2 * (DwTile<KS, STRIDE, CG, TH, TW>::SMEM + 1024) <= 227 * 1024) ? 2 : 1) dw_tiled_kernel(const bf16* x, long long ldx, const float* __restrict__ w,
                                                        const float* __restrict__ bias,
                                                        const float* __restrict__ wpw, bf16* out, long long ldo,
                                                        int H, int W, int C, int Ho, int Wo, int tiles_x, int tiles_per_img,
@@ -123,36 +125,42 @@ __global__ void __launch_bounds__(256) dw_tiled_kernel(const bf16* x, long long 
   constexpr int ITEMS = TH * STRIPS_X * NV;
   constexpr int WIN = 3 * STRIDE + KS;  // input columns covering 4 outputs
   static_assert(!GROUP_PW || (ITEMS % 256 == 0 && NV % 2 == 0), "GROUP_PW needs full warps (shuffle pairing)");
+  // (unroll 1: with ITEMS = 2 x 256 the compiler fused both iterations into one 150 .. 255-register body -- one resident CTA per SM,
+  //  spills in the 5x5 variants)
+#pragma unroll 1
   for (int it = threadIdx.x; it < ITEMS; it += 256) {
     const int v = it % NV;
     const int sidx = it / NV;
     const int sy = sidx / STRIPS_X, sx = sidx % STRIPS_X;
-    float acc[4][8];
+    // accumulators, taps and inputs as channel PAIRS: every multiply-add below is one FFMA2 (two fp32 FMAs per issue slot; the
+    // scalar version spent 288 of its ~500 instructions per strip on FFMA and sat on the fma pipe)
+    float2 acc[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[j][e] = s_b[v * 8 + e];
-#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = *reinterpret_cast<const float2*>(s_b + v * 8 + 2 * e);
+    // (5x5: rows not unrolled -- the unrolled form hoisted all 25 x 8 tap weights into registers: 255 registers and spills)
+#pragma unroll(KS == 3 ? 3 : 1)
     for (int ky = 0; ky < KS; ++ky) {
-      float wk[KS][8];
+      float2 wk[KS][4];
 #pragma unroll
       for (int kx = 0; kx < KS; ++kx) {
         const float4 a = *reinterpret_cast<const float4*>(s_w + (ky * KS + kx) * CG + v * 8);
         const float4 c = *reinterpret_cast<const float4*>(s_w + (ky * KS + kx) * CG + v * 8 + 4);
-        wk[kx][0] = a.x; wk[kx][1] = a.y; wk[kx][2] = a.z; wk[kx][3] = a.w;
-        wk[kx][4] = c.x; wk[kx][5] = c.y; wk[kx][6] = c.z; wk[kx][7] = c.w;
+        wk[kx][0] = make_float2(a.x, a.y); wk[kx][1] = make_float2(a.z, a.w);
+        wk[kx][2] = make_float2(c.x, c.y); wk[kx][3] = make_float2(c.z, c.w);
       }
       const uint8_t* rowp = s_tile + ((sy * STRIDE + ky) * T::IW + sx * 4 * STRIDE) * T::PIX_BYTES + v * 16;
 #pragma unroll
       for (int col = 0; col < WIN; ++col) {
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(rowp + col * T::PIX_BYTES), f);
+        float2 f[4];
+        unpack8_2(*reinterpret_cast<const uint4*>(rowp + col * T::PIX_BYTES), f);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int kx = col - j * STRIDE;
           if (kx >= 0 && kx < KS) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(f[e], wk[kx][e], acc[j][e]);
+            for (int e = 0; e < 4; ++e) acc[j][e] = ffma2(f[e], wk[kx][e], acc[j][e]);
           }
         }
       }
@@ -162,7 +170,7 @@ __global__ void __launch_bounds__(256) dw_tiled_kernel(const bf16* x, long long 
     for (int j = 0; j < 4; ++j) {
       float o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = es3_act_t<ACT>(acc[j][e]);
+      for (int e = 0; e < 4; ++e) { o[2 * e] = es3_act_t<ACT>(acc[j][e].x); o[2 * e + 1] = es3_act_t<ACT>(acc[j][e].y); }
       if (GROUP_PW) {
         // materialise the depthwise output in bf16 (as the unfused reference path does), then the
         // 16x16 group product: this thread owns 8 of the group's 16 channels, lane^1 owns the rest.
@@ -251,7 +259,10 @@ extern "C" int es3_dwconv_tiled_bf16(const void* x, long long ldx, const float* 
   } else if (ks == 3 && stride == 2) {
     ES3_DW_CASE(3, 2, 32, 4, 32)
   } else if (ks == 5 && stride == 1) {
-    if (C % 64 == 0) { ES3_DW_CASE(5, 1, 64, 8, 32) } else { ES3_DW_CASE(5, 1, 32, 8, 32) }
+    // 32-channel groups: two double-buffered 35 KB tiles -> two CTAs per SM (the 64-channel tile needs 124 KB: one CTA, 8 warps per SM);
+    // ES3_DW5_CG64=1 selects the wide variant for A/B timing (scripts/dw_bench.py)
+    static const bool wide = [] { const char* e = getenv("ES3_DW5_CG64"); return e && e[0] == '1'; }();
+    if (wide && C % 64 == 0) { ES3_DW_CASE(5, 1, 64, 8, 32) } else { ES3_DW_CASE(5, 1, 32, 8, 32) }
   }
 #undef ES3_DW_CASE
   ES3_REQUIRE(false, "es3_dwconv_tiled_bf16: unsupported ks=%d stride=%d", ks, stride);

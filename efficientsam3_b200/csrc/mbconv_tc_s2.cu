@@ -225,18 +225,20 @@ mbconv_tc_s2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
             const float4* bi = reinterpret_cast<const float4*>(s_b1 + c * S2_MC);
             const int lx = row % S2_IW;
             uint4* dst = reinterpret_cast<uint4*>(s_mid + ((row / S2_IW) * S2_PW + ((lx & 1) ? S2_ODD + (lx >> 1) : (lx >> 1))) * S2_RS_MID);
+            if (in) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 s0 = sc[2 * j], s1v = sc[2 * j + 1], b0 = bi[2 * j], b1v = bi[2 * j + 1];
-              const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1v.x, s1v.y, s1v.z, s1v.w};
-              const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
-              float f[8];
+              for (int j = 0; j < 4; ++j) {
+                const float4 s0 = sc[2 * j], s1v = sc[2 * j + 1], b0 = bi[2 * j], b1v = bi[2 * j + 1];
+                const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1v.x, s1v.y, s1v.z, s1v.w};
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
+                float f[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float x = es3_act_t<ACT>(fmaf(__uint_as_float(v[j * 8 + e]), sv[e], bv[e]));
-                f[e] = in ? x : 0.f;
+                for (int e = 0; e < 8; ++e) f[e] = es3_act_t<ACT>(fmaf(__uint_as_float(v[j * 8 + e]), sv[e], bv[e]));
+                dst[j] = pack8(f);
               }
-              dst[j] = pack8(f);
+            } else {                                       // outside the image: the depthwise's zero padding (border tiles only,
+#pragma unroll                                             // so interior tiles carry no per-element select)
+              for (int j = 0; j < 4; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
             }
           }
         }
