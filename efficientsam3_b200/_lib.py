@@ -80,6 +80,8 @@ SIGNATURES: dict[str, list] = {
     "es3_accumulate_strided": [_vp, _ll, _i, _ll, _ll, _vp, _vp],
     "es3_dwconv_bwd_data": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_dwconv_wgrad": [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "es3_dwconv_tc_bf16": [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp],
+    "es3_dwconv_wgrad_win": [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "es3_dwconv_wgrad_tiled": [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "es3_se_bwd_dgate": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "es3_se_bwd_apply": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
@@ -112,6 +114,7 @@ SIZE_HELPERS: dict[str, list] = {
     "es3_col_reduce_ws_floats": [_ll, _i],
     "es3_wgrad_pw_ws_floats": [_ll, _i, _i],
     "es3_dwconv_wgrad_ws_floats": [_i, _i, _i, _i, _i, _i],
+    "es3_dwconv_wgrad_win_ws_floats": [_i, _i, _i, _i, _i, _i],
     "es3_dwconv_wgrad_tiled_ws_floats": [_i, _i, _i, _i, _i],
     "es3_se_bwd_ws_floats": [_i, _i, _i],
     "es3_layernorm_bwd_ws_floats": [_ll, _i],

@@ -21,6 +21,12 @@ __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
+__device__ __forceinline__ void mma_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void mma_1688(float* d, uint32_t a0, uint32_t a1, uint32_t b0) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
@@ -171,16 +177,23 @@ dwproj_tc_kernel(const __grid_constant__ CUtensorMap tm_mid, const __grid_consta
             const int row = (hsel * 4 + r) * DP_HW + a_row + kx;                // pixel row of the swizzled tile
             ldsm_x4(u_a + row * 128 + (((cg * 2 + a_kh) ^ (row & 7)) << 4), af[r][0], af[r][1], af[r][2], af[r][3]);
           }
+          // taps (0, kx) and (1, kx) in one m16n8k16 (same issue rate as m16n8k8), (2, kx) as a k8 MMA: 12 MMAs per m-tile instead of 18
+          uint32_t b_lo[3], b_hi[3];
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
             const uint32_t w_lo = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * 64]);
             const uint32_t w_hi = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * 64 + 8]);
-            const uint32_t b_lo = dvalid ? (w_lo << dshift) : 0u, b_hi = dvalid ? (w_hi << dshift) : 0u;
+            b_lo[ky] = dvalid ? (w_lo << dshift) : 0u;
+            b_hi[ky] = dvalid ? (w_hi << dshift) : 0u;
+          }
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              mma_1688(dacc[m][0], af[m + ky][0], af[m + ky][1], b_lo);
-              mma_1688(dacc[m][1], af[m + ky][2], af[m + ky][3], b_hi);
-            }
+          for (int m = 0; m < 4; ++m) {
+            const uint32_t a_lo[4] = {af[m][0], af[m][1], af[m + 1][0], af[m + 1][1]};
+            const uint32_t a_hi[4] = {af[m][2], af[m][3], af[m + 1][2], af[m + 1][3]};
+            mma_16816(dacc[m][0], a_lo, b_lo[0], b_lo[1]);
+            mma_16816(dacc[m][1], a_hi, b_hi[0], b_hi[1]);
+            mma_1688(dacc[m][0], af[m + 2][0], af[m + 2][1], b_lo[2]);
+            mma_1688(dacc[m][1], af[m + 2][2], af[m + 2][3], b_hi[2]);
           }
         }
         if (g > 0) ptx::mbar_wait(bar_proj, (uint32_t)((g - 1) & 1));   // project(g-1) has finished reading s_dw

@@ -176,16 +176,27 @@ __global__ void __launch_bounds__(256, 3) litemla_aggreg_dwpw_kernel(const bf16*
 #pragma unroll
     for (int r = 0; r < 8; ++r)
       ldsm4(u_tile + ((y0 + r) * AG_IW + xh * 16 + a_row + kx) * AG_PS + a_kh * 16, af[r][0], af[r][1], af[r][2], af[r][3]);
+    // two taps per MMA (m16n8k16 issues at the rate of m16n8k8): (0, kx)+(1, kx), (2, kx)+(3, kx) as k16, (4, kx) as k8 -- 30 MMAs per
+    // m-tile instead of 50; the legacy-MMA pipe was this kernel's limiter (60 % busy)
+    uint32_t b_lo[5], b_hi[5];
 #pragma unroll
     for (int ky = 0; ky < 5; ++ky) {
       const uint32_t w_lo = (uint32_t)__bfloat16_as_ushort(s_wd[(ky * 5 + kx) * 16 + g]);
       const uint32_t w_hi = (uint32_t)__bfloat16_as_ushort(s_wd[(ky * 5 + kx) * 16 + 8 + g]);
-      const uint32_t b_lo = dvalid ? (w_lo << dshift) : 0u, b_hi = dvalid ? (w_hi << dshift) : 0u;
+      b_lo[ky] = dvalid ? (w_lo << dshift) : 0u;
+      b_hi[ky] = dvalid ? (w_hi << dshift) : 0u;
+    }
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        mma1688(acc[m][0], af[m + ky][0], af[m + ky][1], b_lo);
-        mma1688(acc[m][1], af[m + ky][2], af[m + ky][3], b_hi);
+    for (int m = 0; m < 4; ++m) {
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {
+        const uint32_t a_lo[4] = {af[m + 2 * kp][0], af[m + 2 * kp][1], af[m + 2 * kp + 1][0], af[m + 2 * kp + 1][1]};
+        const uint32_t a_hi[4] = {af[m + 2 * kp][2], af[m + 2 * kp][3], af[m + 2 * kp + 1][2], af[m + 2 * kp + 1][3]};
+        mma16816(acc[m][0], a_lo, b_lo[2 * kp], b_lo[2 * kp + 1]);
+        mma16816(acc[m][1], a_hi, b_hi[2 * kp], b_hi[2 * kp + 1]);
       }
+      mma1688(acc[m][0], af[m + 4][0], af[m + 4][1], b_lo[4]);
+      mma1688(acc[m][1], af[m + 4][2], af[m + 4][3], b_hi[4]);
     }
   }
   uint32_t p0, p1, p2, p3;

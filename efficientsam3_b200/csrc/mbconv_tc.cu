@@ -284,16 +284,25 @@ mbconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
 #pragma unroll
             for (int r = 0; r < 6; ++r)
               ldsm_x4(u_mid + ((hsel * 4 + r) * MT_HW + a_row + kx) * MT_RS_MID + (cg * 16 + a_kh * 8) * 2, af[r][0], af[r][1], af[r][2], af[r][3]);
+            // two taps per MMA: m16n8k16 issues at the rate of m16n8k8 (0.46 / clk / SM, scripts/mma_bench.cu), so the taps (0, kx) and
+            // (1, kx) share one instruction -- A = [tap-0 fragment | tap-1 fragment] along k, B = [diag(w0) ; diag(w1)] -- and (2, kx)
+            // stays a k8 MMA: 12 MMAs per 16 pixels x 16 channels instead of 18
+            uint32_t b_lo[3], b_hi[3];
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
               const uint32_t w_lo = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * 64]);
               const uint32_t w_hi = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * 64 + 8]);
-              const uint32_t b_lo = dvalid ? (w_lo << dshift) : 0u, b_hi = dvalid ? (w_hi << dshift) : 0u;
+              b_lo[ky] = dvalid ? (w_lo << dshift) : 0u;
+              b_hi[ky] = dvalid ? (w_hi << dshift) : 0u;
+            }
 #pragma unroll
-              for (int m = 0; m < 4; ++m) {
-                mma_1688(dacc[m][0], af[m + ky][0], af[m + ky][1], b_lo);   // channels cg*16 + 0..7
-                mma_1688(dacc[m][1], af[m + ky][2], af[m + ky][3], b_hi);   // channels cg*16 + 8..15
-              }
+            for (int m = 0; m < 4; ++m) {
+              const uint32_t a_lo[4] = {af[m][0], af[m][1], af[m + 1][0], af[m + 1][1]};
+              const uint32_t a_hi[4] = {af[m][2], af[m][3], af[m + 1][2], af[m + 1][3]};
+              mma_16816(dacc[m][0], a_lo, b_lo[0], b_lo[1]);                   // channels cg*16 + 0..7, taps ky = 0, 1
+              mma_16816(dacc[m][1], a_hi, b_hi[0], b_hi[1]);                   // channels cg*16 + 8..15
+              mma_1688(dacc[m][0], af[m + 2][0], af[m + 2][1], b_lo[2]);       // tap ky = 2
+              mma_1688(dacc[m][1], af[m + 2][2], af[m + 2][3], b_hi[2]);
             }
           }
           const float* b2 = s_b2 + c * MT_MC;

@@ -19,6 +19,12 @@ __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
+__device__ __forceinline__ void mma_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void mma_1688(float* d, uint32_t a0, uint32_t a1, uint32_t b0) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
@@ -253,20 +259,35 @@ mbconv_tc_s2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
           const int cg = warp & 1, mt = warp >> 1;
           const bf16* wd = s_wdw + c * 9 * S2_MC + cg * 16 + g4;
           float dacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+          // taps in pairs (0,1) (2,3) (4,5) (6,7) as m16n8k16 MMAs -- A = [tap-a fragment | tap-b fragment] along k, B = [diag(wa) ; diag(wb)]
+          // -- and tap 8 as m16n8k8: 10 MMAs instead of 18 (k16 issues at the rate of k8, scripts/mma_bench.cu)
+          auto frag = [&](int tap, uint32_t* af) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            // input column 2 * a_row + kx: kx = 0 / 2 -> even slots a_row / a_row + 1, kx = 1 -> odd slot a_row
+            ldsm_x4(u_mid + ((2 * mt + ky) * S2_PW + a_row + (kx == 1 ? S2_ODD : (kx >> 1))) * S2_RS_MID + (cg * 16 + a_kh * 8) * 2,
+                    af[0], af[1], af[2], af[3]);
+          };
+          auto bfrag = [&](int tap, uint32_t& b_lo, uint32_t& b_hi) {
+            const uint32_t w_lo = (uint32_t)__bfloat16_as_ushort(wd[tap * S2_MC]);
+            const uint32_t w_hi = (uint32_t)__bfloat16_as_ushort(wd[tap * S2_MC + 8]);
+            b_lo = dvalid ? (w_lo << dshift) : 0u;
+            b_hi = dvalid ? (w_hi << dshift) : 0u;
+          };
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const uint32_t w_lo = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * S2_MC]);
-              const uint32_t w_hi = (uint32_t)__bfloat16_as_ushort(wd[(ky * 3 + kx) * S2_MC + 8]);
-              const uint32_t b_lo = dvalid ? (w_lo << dshift) : 0u, b_hi = dvalid ? (w_hi << dshift) : 0u;
-              uint32_t af[4];
-              // input column 2 * a_row + kx: kx = 0 / 2 -> even slots a_row / a_row + 1, kx = 1 -> odd slot a_row
-              ldsm_x4(u_mid + ((2 * mt + ky) * S2_PW + a_row + (kx == 1 ? S2_ODD : (kx >> 1))) * S2_RS_MID + (cg * 16 + a_kh * 8) * 2,
-                      af[0], af[1], af[2], af[3]);
-              mma_1688(dacc[0], af[0], af[1], b_lo);
-              mma_1688(dacc[1], af[2], af[3], b_hi);
-            }
+          for (int tp = 0; tp < 4; ++tp) {
+            uint32_t fa[4], fb[4], la, ha, lb, hb;
+            frag(2 * tp, fa); frag(2 * tp + 1, fb);
+            bfrag(2 * tp, la, ha); bfrag(2 * tp + 1, lb, hb);
+            const uint32_t a_lo[4] = {fa[0], fa[1], fb[0], fb[1]};
+            const uint32_t a_hi[4] = {fa[2], fa[3], fb[2], fb[3]};
+            mma_16816(dacc[0], a_lo, la, lb);
+            mma_16816(dacc[1], a_hi, ha, hb);
+          }
+          {
+            uint32_t fa[4], la, ha;
+            frag(8, fa); bfrag(8, la, ha);
+            mma_1688(dacc[0], fa[0], fa[1], la);
+            mma_1688(dacc[1], fa[2], fa[3], ha);
           }
           const float* b2 = s_b2 + c * S2_MC;
 #pragma unroll

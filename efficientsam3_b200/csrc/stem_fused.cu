@@ -191,15 +191,27 @@ __global__ void __launch_bounds__(256) stem_fused_kernel(const StemArgs a) {
     for (int mt = warp; mt < SF_TH * (SF_TW / 16); mt += 8) {
       const int ry = mt >> 1, rx0 = (mt & 1) * 16;   // output row / first column inside the tile
       float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      // taps in pairs as m16n8k16 MMAs (A = [tap-a fragment | tap-b fragment] along k, B = [diag(wa) ; diag(wb)]; k16 issues at the rate
+      // of k8), tap 8 as m16n8k8: 10 MMAs per m-tile instead of 18
+      auto frag = [&](int tap, uint32_t* af) {
+        const int ky = tap / 3, kx = tap - ky * 3;
+        ldsm4(u_x + ((ry + ky) * SF_XW + rx0 + a_row + kx) * SF_XRS + a_kh * 16, af[0], af[1], af[2], af[3]);
+      };
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          uint32_t af[4];
-          ldsm4(u_x + ((ry + ky) * SF_XW + rx0 + a_row + kx) * SF_XRS + a_kh * 16, af[0], af[1], af[2], af[3]);
-          mma1688(d[0], af[0], af[1], dlo[ky * 3 + kx]);   // diagonal 8x8 B: no structural zeros multiplied
-          mma1688(d[1], af[2], af[3], dhi[ky * 3 + kx]);
-        }
+      for (int tp = 0; tp < 4; ++tp) {
+        uint32_t fa[4], fb[4];
+        frag(2 * tp, fa); frag(2 * tp + 1, fb);
+        const uint32_t a_lo[4] = {fa[0], fa[1], fb[0], fb[1]};
+        const uint32_t a_hi[4] = {fa[2], fa[3], fb[2], fb[3]};
+        mma16816(d[0], a_lo, dlo[2 * tp], dlo[2 * tp + 1]);
+        mma16816(d[1], a_hi, dhi[2 * tp], dhi[2 * tp + 1]);
+      }
+      {
+        uint32_t fa[4];
+        frag(8, fa);
+        mma1688(d[0], fa[0], fa[1], dlo[8]);
+        mma1688(d[1], fa[2], fa[3], dhi[8]);
+      }
       // hswish(dw + bias) -> A fragment of the pointwise MMA (C-fragment layout == A-fragment layout)
       uint32_t pa[4];
 #pragma unroll

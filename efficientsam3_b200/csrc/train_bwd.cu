@@ -740,6 +740,111 @@ __global__ void __launch_bounds__(256) dw_wgrad_tiled_kernel(const bf16* __restr
   }
 }
 
+// Sliding-window version (stride 1 | 2, C % 32 == 0; the default route since round 2, ops.DW_WGRAD_WIN).  Same staging as the tiled
+// kernel above, different walk: a thread owns one channel pair and a 16-pixel run of ONE output row, keeps the KS x KS input window
+// of the current pixel in registers (as channel-pair float2s) and slides it along x -- STRIDE new columns (KS x STRIDE shared-memory
+// reads) per pixel instead of KS x KS, every multiply-add a packed FFMA2.  Per pixel and channel pair: 3x3 s1  4 LDS + 9 FFMA2 (was
+// 10 LDS + 18 FFMA), 5x5 s1  6 + 25 (was 26 + 50), 3x3 s2  7 + 9 (the per-pixel global-memory kernel ran at 1.2 TB/s).
+// The two half-warps of a warp walk output rows py and py + 1: the row strides are padded so that their reads fall into opposite
+// 64-byte halves of the 128-byte bank window.
+constexpr int DWW_TH = 8, DWW_TW = 32, DWW_CS = 32;
+constexpr int dww_pad(int rs0, int stride) {
+  for (int p = 0; p < 128; p += 16)
+    if ((stride * (rs0 + p)) % 128 == 64) return p;
+  return 0;
+}
+template <int KS, int STRIDE>
+struct DwwCfg {
+  static constexpr int IH = (DWW_TH - 1) * STRIDE + KS, IW = (DWW_TW - 1) * STRIDE + KS;
+  static constexpr int X_RS = IW * 64 + dww_pad(IW * 64, STRIDE);      // bytes per staged input row (64 B per pixel = 32 channels)
+  static constexpr int DZ_RS = DWW_TW * 64 + dww_pad(DWW_TW * 64, 1);
+  static constexpr int X_BYTES = IH * X_RS, DZ_BYTES = DWW_TH * DZ_RS;
+  static constexpr int RED_BYTES = 8 * KS * KS * DWW_CS * 4;
+  static constexpr int SMEM = (X_BYTES + DZ_BYTES > RED_BYTES) ? X_BYTES + DZ_BYTES : RED_BYTES;
+  static_assert((STRIDE * X_RS) % 128 == 64 && DZ_RS % 128 == 64 && X_RS % 16 == 0, "row strides must split the half-warps across the banks");
+};
+
+template <int KS, int STRIDE>
+__global__ void __launch_bounds__(256, (2 * (DwwCfg<KS, STRIDE>::SMEM + 1024) <= 227 * 1024) ? 2 : 1)
+dw_wgrad_win_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ x, long long ldx, int B, int H, int W, int C, int Ho, int Wo,
+                    int tiles_x, int tiles_y, float* __restrict__ part) {
+  using Cfg = DwwCfg<KS, STRIDE>;
+  constexpr int KK = KS * KS, PAD = KS / 2;
+  extern __shared__ __align__(16) uint8_t dww_smem[];
+  const uint32_t u_x = static_cast<uint32_t>(__cvta_generic_to_shared(dww_smem));
+  const uint32_t u_dz = u_x + Cfg::X_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cp = lane & 15, half = lane >> 4;
+  const int py = (warp >> 1) * 2 + half, x0 = (warp & 1) * 16;   // this thread's output row and first output column inside the tile
+  const int c0 = blockIdx.y * DWW_CS;
+  float2 acc[KK];
+#pragma unroll
+  for (int t = 0; t < KK; ++t) acc[t] = make_float2(0.f, 0.f);
+  const long long ntiles = (long long)B * tiles_y * tiles_x;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y), b = (int)(tile / ((long long)tiles_x * tiles_y));
+    const int oy0 = ty * DWW_TH, ox0 = tx * DWW_TW;
+    __syncthreads();                                         // previous tile fully consumed
+    for (int i = tid; i < Cfg::IH * Cfg::IW * 4; i += 256) {
+      const int v = i & 3, pix = i >> 2;
+      const int ly = pix / Cfg::IW, lx = pix - ly * Cfg::IW;
+      const int iy = oy0 * STRIDE - PAD + ly, ix = ox0 * STRIDE - PAD + lx;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      cpa16(u_x + ly * Cfg::X_RS + lx * 64 + v * 16, ok ? x + (((long long)b * H + iy) * W + ix) * ldx + c0 + v * 8 : x, ok);
+    }
+    for (int i = tid; i < DWW_TH * DWW_TW * 4; i += 256) {
+      const int v = i & 3, pix = i >> 2;
+      const int ly = pix / DWW_TW, lx = pix % DWW_TW;
+      const int oy = oy0 + ly, ox = ox0 + lx;
+      const bool ok = oy < Ho && ox < Wo;
+      cpa16(u_dz + ly * Cfg::DZ_RS + lx * 64 + v * 16, ok ? dz + (((long long)b * Ho + oy) * Wo + ox) * C + c0 + v * 8 : dz, ok);
+    }
+    cpa_wait_all();
+    __syncthreads();
+    const uint8_t* xrow = dww_smem + (py * STRIDE) * Cfg::X_RS + (x0 * STRIDE) * 64 + cp * 4;
+    const uint8_t* grow = dww_smem + Cfg::X_BYTES + py * Cfg::DZ_RS + x0 * 64 + cp * 4;
+    float2 win[KS][KS];                                      // input column c of the run lives in slot c % KS
+#pragma unroll
+    for (int c = 0; c < KS - STRIDE; ++c)
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky) win[ky][c % KS] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xrow + ky * Cfg::X_RS + c * 64));
+#pragma unroll
+    for (int px = 0; px < 16; ++px) {
+#pragma unroll
+      for (int n = 0; n < STRIDE; ++n) {
+        const int c = px * STRIDE + KS - STRIDE + n;
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) win[ky][c % KS] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xrow + ky * Cfg::X_RS + c * 64));
+      }
+      const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(grow + px * 64));
+#pragma unroll
+      for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) acc[ky * KS + kx] = ffma2(g, win[ky][(px * STRIDE + kx) % KS], acc[ky * KS + kx]);
+    }
+  }
+  // the two half-warps (same channel pair, different rows), then the 8 warps through shared memory: red[warp][tap][32 channels]
+#pragma unroll
+  for (int t = 0; t < KK; ++t) {
+    acc[t].x += __shfl_xor_sync(0xffffffffu, acc[t].x, 16);
+    acc[t].y += __shfl_xor_sync(0xffffffffu, acc[t].y, 16);
+  }
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(dww_smem);
+  if (half == 0) {
+#pragma unroll
+    for (int t = 0; t < KK; ++t) *reinterpret_cast<float2*>(red + (warp * KK + t) * DWW_CS + cp * 2) = acc[t];
+  }
+  __syncthreads();
+  for (int i = tid; i < KK * DWW_CS; i += 256) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w * KK * DWW_CS + i];
+    const int t = i / DWW_CS, c = i % DWW_CS;
+    part[((long long)blockIdx.x * KK + t) * C + c0 + c] = sum;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ SqueezeExcite backward (batched)
 // Per-image column reductions / per-image affine of the SqueezeExcite backward in ONE launch each (the training graph's first
 // version loops over the batch with es3_bn_act_bwd_reduce / es3_affine_act: ~100 launches per SE block at batch 32).
@@ -1496,6 +1601,58 @@ extern "C" int es3_dwconv_wgrad_tiled(const void* dz, const void* x, long long l
   ES3_LAUNCH_CHECK("dw_wgrad_tiled_kernel");
   const long long n = (long long)ks * ks * C;
   sum_partials_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, st>>>(ws, nblk, n, C, 1, (long long)ks * ks, dW);
+  ES3_LAUNCH_CHECK("sum_partials_kernel");
+  return 0;
+}
+
+static int dww_blocks(int B, int Ho, int Wo, int C) {
+  const long long ntiles = (long long)B * ceil_div(Ho, DWW_TH) * ceil_div(Wo, DWW_TW);
+  long long want = (2LL * 148 + C / DWW_CS - 1) / (C / DWW_CS);      // two resident CTAs per SM over all channel slabs
+  if (want > ntiles) want = ntiles;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+extern "C" long long es3_dwconv_wgrad_win_ws_floats(int B, int H, int W, int C, int ks, int stride) {
+  const int pad = ks / 2;
+  const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
+  return (long long)dww_blocks(B, Ho, Wo, C) * ks * ks * C;
+}
+
+template <int KS, int STRIDE>
+static int launch_dw_wgrad_win(const bf16* dz, const bf16* x, long long ldx, int B, int H, int W, int C, int Ho, int Wo, float* ws, cudaStream_t st) {
+  using Cfg = DwwCfg<KS, STRIDE>;
+  static bool configured = false;
+  if (!configured) {
+    ES3_CHECK_CUDA(cudaFuncSetAttribute(dw_wgrad_win_kernel<KS, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    configured = true;
+  }
+  const int nblk = dww_blocks(B, Ho, Wo, C);
+  dw_wgrad_win_kernel<KS, STRIDE><<<dim3(nblk, C / DWW_CS), 256, Cfg::SMEM, st>>>(dz, x, ldx, B, H, W, C, Ho, Wo, ceil_div(Wo, DWW_TW),
+                                                                                  ceil_div(Ho, DWW_TH), ws);
+  ES3_LAUNCH_CHECK("dw_wgrad_win_kernel");
+  return 0;
+}
+
+/* Same contract as es3_dwconv_wgrad for C % 32 == 0 (stride 1 | 2, ks 3 | 5): register sliding window over shared-memory tiles. */
+extern "C" int es3_dwconv_wgrad_win(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, int stride, float* ws,
+                                    float* dW, void* stream) {
+  ES3_REQUIRE(C % DWW_CS == 0 && ldx % 8 == 0 && (ks == 3 || ks == 5) && (stride == 1 || stride == 2),
+              "es3_dwconv_wgrad_win: need C %% 32 == 0, ks 3|5, stride 1|2 (C=%d ks=%d stride=%d)", C, ks, stride);
+  ES3_REQUIRE(((uintptr_t)dz & 15) == 0 && ((uintptr_t)x & 15) == 0, "es3_dwconv_wgrad_win: operands must be 16-byte aligned");
+  const int pad = ks / 2;
+  const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bf16* dzp = (const bf16*)dz;
+  const bf16* xp = (const bf16*)x;
+  int rc;
+  if (ks == 3 && stride == 1) rc = launch_dw_wgrad_win<3, 1>(dzp, xp, ldx, B, H, W, C, Ho, Wo, ws, st);
+  else if (ks == 3) rc = launch_dw_wgrad_win<3, 2>(dzp, xp, ldx, B, H, W, C, Ho, Wo, ws, st);
+  else if (stride == 1) rc = launch_dw_wgrad_win<5, 1>(dzp, xp, ldx, B, H, W, C, Ho, Wo, ws, st);
+  else rc = launch_dw_wgrad_win<5, 2>(dzp, xp, ldx, B, H, W, C, Ho, Wo, ws, st);
+  if (rc) return rc;
+  const long long n = (long long)ks * ks * C;
+  sum_partials_kernel<<<(unsigned)ceil_div(n, 32), 256, 0, st>>>(ws, dww_blocks(B, Ho, Wo, C), n, C, 1, (long long)ks * ks, dW);
   ES3_LAUNCH_CHECK("sum_partials_kernel");
   return 0;
 }

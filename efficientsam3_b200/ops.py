@@ -208,8 +208,12 @@ def stem_conv3x3_s2(x, w27, bias, act):
     return out
 
 
-def dwconv(x, w, bias, ks, stride, act, out=None, force_simple=False):
-    """x: [B,H,W,C] bf16 (channel-sliced views allowed); w: [ks*ks, C] fp32."""
+DW_TC = True   # stride-1 3x3 / 5x5 depthwise convs with C % 32 == 0 on the tensor-core kernel (csrc/dw_tc.cu; GPU parity: test_dwconv_tc)
+
+
+def dwconv(x, w, bias, ks, stride, act, out=None, force_simple=False, impl=None):
+    """x: [B,H,W,C] bf16 (channel-sliced views allowed); w: [ks*ks, C] fp32.  impl: None (default routing), "tc" (tensor-core kernel,
+    stride 1), "tiled" (CUDA-core shared-memory kernel)."""
     _chk(x, torch.bfloat16, "x")
     _ensure_init(x)
     B, H, W, Cc = x.shape
@@ -218,6 +222,10 @@ def dwconv(x, w, bias, ks, stride, act, out=None, force_simple=False):
     Ho, Wo = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
     if out is None:
         out = torch.empty((B, Ho, Wo, Cc), device=x.device, dtype=torch.bfloat16)
+    if DW_TC and stride == 1 and ks in (3, 5) and Cc % 32 == 0 and not force_simple and impl in (None, "tc"):
+        _call("es3_dwconv_tc_bf16", f"dwconv_tc{ks}x{ks}", B * H * W * Cc * 2 + B * Ho * Wo * Cc * 2, 2 * B * Ho * Wo * Cc * ks * ks,
+              x.data_ptr(), x.stride(2), w.data_ptr(), _ptr(bias), out.data_ptr(), out.stride(2), B, H, W, Cc, ks, ACT[act], _stream())
+        return out
     fn = "es3_dwconv_tiled_bf16" if (Cc % 32 == 0 and not force_simple) else "es3_dwconv_bf16"
     _call(fn, f"dwconv{ks}x{ks}s{stride}", B * H * W * Cc * 2 + B * Ho * Wo * Cc * 2, 2 * B * Ho * Wo * Cc * ks * ks,
           x.data_ptr(), x.stride(2), w.data_ptr(), _ptr(bias), out.data_ptr(), out.stride(2),
@@ -943,18 +951,26 @@ def dwconv_bwd_data(dz, w, H, W, ks, stride):
     return dx
 
 
+DW_WGRAD_WIN = True      # route C % 32 == 0 weight gradients (stride 1 | 2) to es3_dwconv_wgrad_win (GPU parity: test_dwconv_wgrad_win)
 DW_WGRAD_TILED = True    # route stride-1, C % 32 == 0 weight gradients to es3_dwconv_wgrad_tiled (GPU parity: test_dwconv_wgrad_tiled, r2)
 
 
 def dwconv_wgrad(dz, x, dW, ks, stride, impl=None):
     """dW [C,1,ks,ks] fp32 += depthwise weight gradient; dz [B,Ho,Wo,C] bf16 contiguous, x [B,H,W,C] bf16 (channel slice ok).
-    impl="tiled" forces the shared-memory tiled kernel (stride 1, C % 32 == 0)."""
+    impl="win": register sliding window over shared-memory tiles (C % 32 == 0; the default for such shapes); impl="tiled": the first
+    shared-memory tiled kernel (stride 1, C % 32 == 0); impl="direct": the global-memory kernels."""
     _chk(dz, torch.bfloat16, "dz"); _chk(x, torch.bfloat16, "x"); _chk(dW, torch.float32, "dW")
     _ensure_init(dz)
     B, H, W, C = x.shape
     assert dz.is_contiguous() and dW.is_contiguous() and dW.numel() == C * ks * ks and dz.shape[3] == C
     assert x.stride(3) == 1 and x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1)
-    if impl == "tiled" or (impl is None and DW_WGRAD_TILED and stride == 1 and C % 32 == 0):
+    if impl == "win" or (impl is None and DW_WGRAD_WIN and C % 32 == 0):
+        assert C % 32 == 0
+        ws = _f32ws(_lib.size("es3_dwconv_wgrad_win_ws_floats", B, H, W, C, ks, stride), dz.device)
+        _call("es3_dwconv_wgrad_win", f"dwconv_wgrad_win{ks}x{ks}s{stride}", _nb(dz) + B * H * W * C * 2, 2 * dz.numel() * ks * ks,
+              dz.data_ptr(), x.data_ptr(), x.stride(2), B, H, W, C, ks, stride, ws.data_ptr(), dW.data_ptr(), _stream())
+        return dW
+    if impl == "tiled" or (impl is None and DW_WGRAD_TILED and stride == 1 and C % 32 == 0):   # (impl="direct" falls through)
         assert stride == 1 and C % 32 == 0
         ws = _f32ws(_lib.size("es3_dwconv_wgrad_tiled_ws_floats", B, H, W, C, ks), dz.device)
         _call("es3_dwconv_wgrad_tiled", f"dwconv_wgrad_tiled{ks}x{ks}", _nb(dz) + B * H * W * C * 2, 2 * dz.numel() * ks * ks,

@@ -340,6 +340,17 @@ long long es3_colsum_f32_ws_floats(long long M, int L);
 int es3_colsum_f32(const float* src, long long ld, long long M, int L, float* ws, float* out, void* stream);
 /* Shared-memory tiled variant of es3_dwconv_wgrad for stride 1 and C % 32 == 0 (same result contract).  The default
  * route for these shapes since round 2 (GPU parity: test_dwconv_wgrad_tiled). */
+/* Stride-1 depthwise conv (ks 3 | 5, pad ks/2, C % 32 == 0) on mma.sync with diagonal tap operands: same contract as
+ * es3_dwconv_tiled_bf16 at stride 1, taps rounded to bf16 (nn.Conv2d(groups=C): efficientvit/nn/ops.py:39-80, repvit.py:84-122,
+ * tiny_vit.py:97-133; also the backward-data pass of those layers, on flipped taps). */
+int es3_dwconv_tc_bf16(const void* x, long long ldx, const float* w, const float* bias, void* out, long long ldo, int B, int H, int W, int C,
+                       int ks, int act, void* stream);
+
+/* Register sliding-window depthwise weight gradient over shared-memory tiles: same contract as es3_dwconv_wgrad for C % 32 == 0
+ * (stride 1 | 2, ks 3 | 5); the route ops.dwconv_wgrad takes for such shapes (autograd of nn.Conv2d(groups=C), ops.py:39-80). */
+long long es3_dwconv_wgrad_win_ws_floats(int B, int H, int W, int C, int ks, int stride);
+int es3_dwconv_wgrad_win(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, int stride, float* ws, float* dW,
+                         void* stream);
 long long es3_dwconv_wgrad_tiled_ws_floats(int B, int H, int W, int C, int ks);
 int es3_dwconv_wgrad_tiled(const void* dz, const void* x, long long ldx, int B, int H, int W, int C, int ks, float* ws, float* dW,
                            void* stream);

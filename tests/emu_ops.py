@@ -78,7 +78,7 @@ def _dw(x4, w, ks, stride):
     return F.conv2d(x4, w.t().reshape(C, 1, ks, ks), None, stride=stride, padding=ks // 2, groups=C)
 
 
-def dwconv(x, w, bias, ks, stride, act, out=None, force_simple=False):
+def dwconv(x, w, bias, ks, stride, act, out=None, force_simple=False, impl=None):
     v = _dw(_nchw(x), w.to(CD), ks, stride)
     if bias is not None:
         v = v + bias.view(1, -1, 1, 1)

@@ -154,6 +154,32 @@ def test_dwconv(cuda, ks, stride, H, W, C, simple):
     _close(out, ref, 1e-2, "dwconv")
 
 
+@pytest.mark.parametrize("ks,H,W,C,act,sliced", [(3, 20, 20, 64, "hswish", False), (3, 64, 64, 128, None, False), (3, 7, 5, 32, "gelu", False),
+                                                 (5, 33, 70, 96, None, True), (5, 16, 16, 32, "relu", False), (3, 40, 37, 96, None, True),
+                                                 (3, 9, 100, 256, "hswish", False), (5, 64, 64, 384, None, True)])
+def test_dwconv_tc(cuda, ks, H, W, C, act, sliced):
+    """Tensor-core depthwise kernel (diagonal tap operands, two taps per m16n8k16): against torch at the bf16-rounded taps it computes
+    with, and against the CUDA-core tiled kernel; `sliced`: input and output are channel windows of wider NHWC buffers."""
+    from efficientsam3_b200 import ops
+    g = torch.Generator().manual_seed(ks * 100 + C + H)
+    B = 2
+    wide = _bf(torch.randn(B, H, W, 2 * C if sliced else C, generator=g)).to(cuda)
+    x = wide[..., :C]
+    w = (torch.randn(C, 1, ks, ks, generator=g) / ks).to(cuda)
+    b = torch.randn(C, generator=g).to(cuda) if act != "relu" else None
+    wt = w.reshape(C, ks * ks).t().contiguous()
+    obuf = torch.zeros(B, H, W, 2 * C if sliced else C, device=cuda, dtype=torch.bfloat16)
+    out = ops.dwconv(x, wt, b, ks, 1, act, out=obuf[..., C:] if sliced else obuf, impl="tc")
+    wr = w.to(torch.bfloat16).float()
+    pre = F.conv2d(x.float().permute(0, 3, 1, 2), wr, b, stride=1, padding=ks // 2, groups=C)
+    ref = {None: lambda t: t, "hswish": F.hardswish, "gelu": F.gelu, "relu": F.relu}[act](pre).permute(0, 2, 3, 1)
+    _close(out, ref, 6e-3, "dwconv_tc vs torch (bf16 taps)")
+    tiled = ops.dwconv(x, wt, b, ks, 1, act, impl="tiled")
+    _close(out, tiled.float(), 1e-2, "dwconv_tc vs tiled")
+    if sliced:
+        assert torch.count_nonzero(obuf[..., :C]) == 0       # the neighbouring channel window is untouched
+
+
 def test_dsconv_res(cuda):
     from efficientsam3_b200 import ops
     g = torch.Generator().manual_seed(3)

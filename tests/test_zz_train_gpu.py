@@ -530,6 +530,26 @@ def test_dwconv_wgrad_tiled(cuda, B, H, W, C, ks):
     _close(got, ref, 2e-3, "dwconv_wgrad tiled")
 
 
+@pytest.mark.parametrize("B,H,W,C,ks,stride", [(2, 16, 16, 32, 3, 1), (1, 9, 11, 96, 5, 1), (2, 64, 64, 384, 5, 1), (2, 40, 37, 512, 3, 1),
+                                               (1, 7, 5, 64, 5, 1), (2, 64, 64, 64, 3, 2), (1, 37, 51, 128, 3, 2), (3, 18, 70, 32, 3, 2),
+                                               (1, 33, 33, 64, 5, 2), (2, 8, 100, 96, 3, 1)])
+def test_dwconv_wgrad_win(cuda, B, H, W, C, ks, stride):
+    """Sliding-window weight gradient (the default for C % 32 == 0) against the torch statement and against the direct kernels."""
+    from efficientsam3_b200 import ops
+    g = _g(B * H + C + ks + stride)
+    ms = _bf(torch.randn(B, H, W, 2 * C, generator=g))
+    Ho, Wo = (H + 2 * (ks // 2) - ks) // stride + 1, (W + 2 * (ks // 2) - ks) // stride + 1
+    dz = _bf(torch.randn(B, Ho, Wo, C, generator=g))
+    ref = torch.full((C, 1, ks, ks), 0.125)
+    E.dwconv_wgrad(dz, ms[..., :C], ref, ks, stride)
+    got = torch.full((C, 1, ks, ks), 0.125, device=cuda)
+    ops.dwconv_wgrad(dz.to(cuda), ms.to(cuda)[..., :C], got, ks, stride, impl="win")
+    _close(got, ref, 2e-3, "dwconv_wgrad win")
+    direct = torch.full((C, 1, ks, ks), 0.125, device=cuda)
+    ops.dwconv_wgrad(dz.to(cuda), ms.to(cuda)[..., :C], direct, ks, stride, impl="direct")
+    _close(got, direct.cpu(), 1e-4, "dwconv_wgrad win vs direct")
+
+
 @pytest.mark.parametrize("B,H,W,C", [(3, 16, 16, 64), (2, 9, 7, 128), (4, 32, 32, 256), (2, 5, 5, 2560)])
 def test_se_bwd_batched(cuda, B, H, W, C):
     from efficientsam3_b200 import ops
