@@ -80,6 +80,7 @@ SIGNATURES: dict[str, list] = {
     "es3_accumulate_strided": [_vp, _ll, _i, _ll, _ll, _vp, _vp],
     "es3_dwconv_bwd_data": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "es3_dwconv_wgrad": [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "es3_round_taps_sum_bf16": [_vp, _vp, _i, _i, _vp],
     "es3_dwconv_tc_bf16": [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp],
     "es3_dwconv_wgrad_win": [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "es3_dwconv_wgrad_tiled": [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp],

@@ -8,8 +8,15 @@
 // (profiles/r2w_dw_tiled_ncu_raw.csv.gz).  Here the taps are DIAGONAL B operands of mma.sync: ldmatrix delivers the bf16 pixels
 // straight into A fragments (no unpacking), two taps share one m16n8k16 (A = [tap-a | tap-b] along k, B = [diag(wa) ; diag(wb)]; k16
 // issues at the rate of k8, scripts/mma_bench.cu), input rows are shared by the taps of neighbouring output rows.  Per 16 pixels x 16
-// channels: 3x3 = 4.5 ldmatrix.x4 + 12 MMAs, 5x5 = 10 ldmatrix.x4 + 30 MMAs, fp32 accumulation.  The tap weights are rounded to
-// bf16 (as in the fused kernels); bias / activation epilogue in fp32.
+// channels: 3x3 = 4.5 ldmatrix.x4 + 12 MMAs, 5x5 = 10 ldmatrix.x4 + 30 MMAs, fp32 accumulation; bias / activation epilogue in fp32.
+//
+// The taps are bf16 operands.  Rounding each fp32 tap to nearest moved tiny_vit_5m's embedding from 1.5e-2 to 2.7e-2 of the fp32
+// reference (tolerance 2e-2): on smooth feature maps the output is ~ mean(x) * sum(taps), so the error that matters is the error of the
+// tap SUM.  es3_round_taps_sum_bf16 therefore picks, per channel, bf16 taps whose sum stays (nearly) the fp32 sum -- nearest rounding,
+// then up to four one-ulp moves of the taps with the largest same-sign rounding error.  CPU oracle experiment (tiny_vit_5m, 512^2):
+// nearest 1.9e-2, sum-preserving 3.2e-3 output rel-L2 from the taps alone.  A two-term (hi + lo) split of the taps inside one k16
+// MMA was also built and measured: exact, but 450 us instead of 392 us at 32 x 256^2 x 128 and slower than the CUDA-core kernel for
+// 5x5 (profiles/r2ac_dw_tc_split.md) -- not kept.
 //
 // CTA: 256 threads, persistent over (8 x 32 pixel tile, channel group, image) items, haloed tile double-buffered with cp.async
 // (zero fill = the convolution's padding).  Warp -> (16-channel sub-group, half of the tile's rows).
@@ -178,6 +185,51 @@ dw_tc_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict_
   }
 }
 
+// One thread per channel: out[tap][c] = bf16-representable taps (stored as fp32) with sum_c(out) ~ sum_c(w).
+__global__ void round_taps_sum_bf16_kernel(const float* __restrict__ w, float* __restrict__ out, int KK, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t[25], r[25];
+  float sum_w = 0.f, sum_r = 0.f;
+#pragma unroll
+  for (int i = 0; i < 25; ++i) {
+    if (i < KK) {
+      t[i] = w[(long long)i * C + c];
+      r[i] = __bfloat162float(__float2bfloat16(t[i]));
+      sum_w += t[i];
+      sum_r += r[i];
+    }
+  }
+  for (int it = 0; it < 4; ++it) {
+    const float res = sum_w - sum_r;
+    if (res == 0.f) break;
+    const float sgn = res > 0.f ? 1.f : -1.f;
+    int best = 0;
+    float best_score = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 25; ++i) {
+      if (i < KK) {
+        const float score = (t[i] - r[i]) * sgn;
+        if (score > best_score) { best_score = score; best = i; }
+      }
+    }
+    float rb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 25; ++i) if (i == best) rb = r[i];
+    const float ulp = __uint_as_float(__float_as_uint(rb) & 0x7f800000u) * 0.0078125f;     // 2^(exponent - 7): one bf16 step at rb
+    if (ulp == 0.f) break;
+    const float cand = __bfloat162float(__float2bfloat16(rb + sgn * ulp));
+    const float new_sum = sum_r - rb + cand;
+    if (fabsf(sum_w - new_sum) >= fabsf(res)) break;
+#pragma unroll
+    for (int i = 0; i < 25; ++i) if (i == best) r[i] = cand;
+    sum_r = new_sum;
+  }
+#pragma unroll
+  for (int i = 0; i < 25; ++i)
+    if (i < KK) out[(long long)i * C + c] = r[i];
+}
+
 template <int KS, int CG, int ACT>
 static int launch_dw_tc(const bf16* x, long long ldx, const float* w, const float* bias, bf16* out, long long ldo, int B, int H, int W, int C,
                         cudaStream_t st) {
@@ -211,7 +263,8 @@ static int launch_dw_tc(const bf16* x, long long ldx, const float* w, const floa
 using namespace es3;
 
 /* Stride-1 depthwise ks x ks (3 | 5), pad ks/2, C % 32 == 0, on mma.sync with diagonal tap operands.  Same contract as
- * es3_dwconv_tiled_bf16 with stride = 1 (the taps are rounded to bf16). */
+ * es3_dwconv_tiled_bf16 with stride = 1; the taps are bf16 operands (nearest rounding of what is passed: pass taps prepared by
+ * es3_round_taps_sum_bf16 to keep the tap sums, as ops.dwconv does). */
 extern "C" int es3_dwconv_tc_bf16(const void* x, long long ldx, const float* w, const float* bias, void* out, long long ldo, int B, int H,
                                   int W, int C, int ks, int act, void* stream) {
   ES3_REQUIRE(C % 32 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && (ks == 3 || ks == 5), "es3_dwconv_tc_bf16: need C %% 32 == 0, ks 3|5 (C=%d ks=%d)", C, ks);
@@ -234,4 +287,13 @@ extern "C" int es3_dwconv_tc_bf16(const void* x, long long ldx, const float* w, 
   }
 #undef ES3_DTC_CASE
   return 1;
+}
+
+/* Per channel, bf16-representable depthwise taps (written as fp32) whose sum stays as close as possible to the fp32 tap sum: w, out
+ * [KK][C] tap-major, KK <= 25.  Feed the result to es3_dwconv_tc_bf16 (whose nearest rounding is then the identity). */
+extern "C" int es3_round_taps_sum_bf16(const float* w, float* out, int KK, int C, void* stream) {
+  ES3_REQUIRE(KK > 0 && KK <= 25 && C > 0, "es3_round_taps_sum_bf16: bad shape (KK=%d C=%d)", KK, C);
+  round_taps_sum_bf16_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(w, out, KK, C);
+  ES3_LAUNCH_CHECK("round_taps_sum_bf16_kernel");
+  return 0;
 }

@@ -208,6 +208,25 @@ def stem_conv3x3_s2(x, w27, bias, act):
     return out
 
 
+def round_taps_sum_bf16(w):
+    """w [taps, C] fp32 -> fp32 tensor of bf16-representable taps whose per-channel sum stays (nearly) the fp32 sum."""
+    _chk(w, torch.float32, "w")
+    _ensure_init(w)
+    assert w.dim() == 2 and w.is_contiguous() and w.shape[0] <= 25
+    out = torch.empty_like(w)
+    _call("es3_round_taps_sum_bf16", "round_taps", 2 * _nb(w), w.numel(), w.data_ptr(), out.data_ptr(), w.shape[0], w.shape[1], _stream())
+    return out
+
+
+def _tc_taps(w):
+    """The tensor-core kernel's tap operand of `w`, computed once per (tensor object, version)."""
+    c = getattr(w, "_es3_tc_taps", None)
+    if c is None or c[0] != w._version:
+        c = (w._version, round_taps_sum_bf16(w))
+        w._es3_tc_taps = c
+    return c[1]
+
+
 DW_TC = True   # stride-1 3x3 / 5x5 depthwise convs with C % 32 == 0 on the tensor-core kernel (csrc/dw_tc.cu; GPU parity: test_dwconv_tc)
 
 
@@ -224,7 +243,7 @@ def dwconv(x, w, bias, ks, stride, act, out=None, force_simple=False, impl=None)
         out = torch.empty((B, Ho, Wo, Cc), device=x.device, dtype=torch.bfloat16)
     if DW_TC and stride == 1 and ks in (3, 5) and Cc % 32 == 0 and not force_simple and impl in (None, "tc"):
         _call("es3_dwconv_tc_bf16", f"dwconv_tc{ks}x{ks}", B * H * W * Cc * 2 + B * Ho * Wo * Cc * 2, 2 * B * Ho * Wo * Cc * ks * ks,
-              x.data_ptr(), x.stride(2), w.data_ptr(), _ptr(bias), out.data_ptr(), out.stride(2), B, H, W, Cc, ks, ACT[act], _stream())
+              x.data_ptr(), x.stride(2), _tc_taps(w).data_ptr(), _ptr(bias), out.data_ptr(), out.stride(2), B, H, W, Cc, ks, ACT[act], _stream())
         return out
     fn = "es3_dwconv_tiled_bf16" if (Cc % 32 == 0 and not force_simple) else "es3_dwconv_bf16"
     _call(fn, f"dwconv{ks}x{ks}s{stride}", B * H * W * Cc * 2 + B * Ho * Wo * Cc * 2, 2 * B * Ho * Wo * Cc * ks * ks,
@@ -253,7 +272,7 @@ def stem_fused_c16(x, w0, s0, b0, wdw, bdw, wpw, spw, bpw):
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     out = torch.empty((B, Ho, Wo, 16), device=x.device, dtype=torch.bfloat16)
     _call("es3_stem_fused_c16", "stem_fused_c16", _nb(x, out), 2 * B * Ho * Wo * 16 * (27 + 9 + 16),
-          x.data_ptr(), w0.data_ptr(), s0.data_ptr(), b0.data_ptr(), wdw.data_ptr(), bdw.data_ptr(), wpw.data_ptr(),
+          x.data_ptr(), w0.data_ptr(), s0.data_ptr(), b0.data_ptr(), _tc_taps(wdw).data_ptr(), bdw.data_ptr(), wpw.data_ptr(),
           spw.data_ptr(), bpw.data_ptr(), out.data_ptr(), B, H, W, _stream())
     return out
 
@@ -322,7 +341,7 @@ def litemla_aggreg_tc(ms, wcomb, C3):
 def litemla_dwpw_weights(wdw, wpw):
     """wdw [25, C3] fp32 (tap-major), wpw [C3, 16] fp32 -> ([C3/16, 25, 16] bf16, [C3, 16] bf16) for es3_litemla_aggreg_dwpw."""
     C3 = wpw.shape[0]
-    d = wdw.reshape(25, C3 // 16, 16).permute(1, 0, 2)
+    d = round_taps_sum_bf16(wdw.contiguous()).reshape(25, C3 // 16, 16).permute(1, 0, 2)      # bf16 taps with the fp32 tap sums
     return d.to(torch.bfloat16).contiguous(), wpw.to(torch.bfloat16).contiguous()
 
 
@@ -380,6 +399,7 @@ def mbconv_fused(x, w1, s1, b1, wdw, b2, w3, s3, b3, stride, residual, act, impl
     Mid, Cout = w1.shape[0], w3.shape[0]
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     y = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.bfloat16)
+    wdw = _tc_taps(wdw)     # the fused kernels multiply bf16 taps: per-channel tap sums kept (es3_round_taps_sum_bf16), cached on the tensor
     args = (x.data_ptr(), y.data_ptr(), w1.data_ptr(), s1.data_ptr(), b1.data_ptr(), wdw.data_ptr(), b2.data_ptr(),
             w3.data_ptr(), s3.data_ptr(), b3.data_ptr(), B, H, W, Cin, Mid, Cout, stride, int(residual), ACT[act],
             _stream())
@@ -421,7 +441,7 @@ def dwproj(mid, wdw, b2, w3, s3, b3, residual=None, act="hswish"):
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = _lib.call_rc("es3_dwproj_tc_bf16", mid.data_ptr(), wdw.data_ptr(), b2.data_ptr(), w3.data_ptr(), s3.data_ptr(),
+    rc = _lib.call_rc("es3_dwproj_tc_bf16", mid.data_ptr(), _tc_taps(wdw).data_ptr(), b2.data_ptr(), w3.data_ptr(), s3.data_ptr(),
                       b3.data_ptr(), _ptr(residual), y.data_ptr(), B, H, W, Mid, Cout, ACT[act], _stream())
     if rc < 0:
         return None

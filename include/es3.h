@@ -345,6 +345,9 @@ int es3_colsum_f32(const float* src, long long ld, long long M, int L, float* ws
  * tiny_vit.py:97-133; also the backward-data pass of those layers, on flipped taps). */
 int es3_dwconv_tc_bf16(const void* x, long long ldx, const float* w, const float* bias, void* out, long long ldo, int B, int H, int W, int C,
                        int ks, int act, void* stream);
+/* bf16-representable taps (as fp32, [KK][C] tap-major) whose per-channel SUM stays at the fp32 tap sum: the operand preparation of
+ * es3_dwconv_tc_bf16 (nearest rounding alone costs TinyViT 1e-2 of embedding accuracy, csrc/dw_tc.cu). */
+int es3_round_taps_sum_bf16(const float* w, float* out, int KK, int C, void* stream);
 
 /* Register sliding-window depthwise weight gradient over shared-memory tiles: same contract as es3_dwconv_wgrad for C % 32 == 0
  * (stride 1 | 2, ks 3 | 5); the route ops.dwconv_wgrad takes for such shapes (autograd of nn.Conv2d(groups=C), ops.py:39-80). */

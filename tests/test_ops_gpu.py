@@ -158,8 +158,9 @@ def test_dwconv(cuda, ks, stride, H, W, C, simple):
                                                  (5, 33, 70, 96, None, True), (5, 16, 16, 32, "relu", False), (3, 40, 37, 96, None, True),
                                                  (3, 9, 100, 256, "hswish", False), (5, 64, 64, 384, None, True)])
 def test_dwconv_tc(cuda, ks, H, W, C, act, sliced):
-    """Tensor-core depthwise kernel (diagonal tap operands, two taps per m16n8k16): against torch at the bf16-rounded taps it computes
-    with, and against the CUDA-core tiled kernel; `sliced`: input and output are channel windows of wider NHWC buffers."""
+    """Tensor-core depthwise kernel (diagonal bf16 tap operands, two taps per m16n8k16, tap sums preserved by es3_round_taps_sum_bf16):
+    against torch at exactly the taps it computes with, against torch with the fp32 taps, and against the CUDA-core tiled kernel;
+    `sliced`: input and output are channel windows of wider NHWC buffers."""
     from efficientsam3_b200 import ops
     g = torch.Generator().manual_seed(ks * 100 + C + H)
     B = 2
@@ -170,10 +171,17 @@ def test_dwconv_tc(cuda, ks, H, W, C, act, sliced):
     wt = w.reshape(C, ks * ks).t().contiguous()
     obuf = torch.zeros(B, H, W, 2 * C if sliced else C, device=cuda, dtype=torch.bfloat16)
     out = ops.dwconv(x, wt, b, ks, 1, act, out=obuf[..., C:] if sliced else obuf, impl="tc")
-    wr = w.to(torch.bfloat16).float()
-    pre = F.conv2d(x.float().permute(0, 3, 1, 2), wr, b, stride=1, padding=ks // 2, groups=C)
-    ref = {None: lambda t: t, "hswish": F.hardswish, "gelu": F.gelu, "relu": F.relu}[act](pre).permute(0, 2, 3, 1)
-    _close(out, ref, 6e-3, "dwconv_tc vs torch (bf16 taps)")
+    fn = {None: lambda t: t, "hswish": F.hardswish, "gelu": F.gelu, "relu": F.relu}[act]
+    taps = ops.round_taps_sum_bf16(wt)                                           # [ks*ks, C]: what the kernel multiplies with
+    assert torch.equal(taps, taps.to(torch.bfloat16).float())                   # bf16-representable ...
+    near = wt.to(torch.bfloat16).float()
+    assert ((taps - near).abs() <= 1.01 * near.abs() * 2.0 ** -7).all()         # ... at most one bf16 step from nearest rounding ...
+    assert ((taps.sum(0) - wt.sum(0)).abs() <= (near.sum(0) - wt.sum(0)).abs() + 1e-7).all()   # ... with a tap sum at least as good
+    wr = taps.t().reshape(C, 1, ks, ks)
+    ref_taps = fn(F.conv2d(x.float().permute(0, 3, 1, 2), wr, b, stride=1, padding=ks // 2, groups=C)).permute(0, 2, 3, 1)
+    _close(out, ref_taps, 4e-3, "dwconv_tc vs torch at the kernel's taps")
+    ref = fn(F.conv2d(x.float().permute(0, 3, 1, 2), w, b, stride=1, padding=ks // 2, groups=C)).permute(0, 2, 3, 1)
+    _close(out, ref, 8e-3, "dwconv_tc vs torch (fp32 taps)")
     tiled = ops.dwconv(x, wt, b, ks, 1, act, impl="tiled")
     _close(out, tiled.float(), 1e-2, "dwconv_tc vs tiled")
     if sliced:
