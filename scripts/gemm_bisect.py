@@ -3,7 +3,8 @@ epilogue math / operand loads bounds a tile.  Numbers are for diagnosis only (th
 import math, os, sys, torch
 sys.path.insert(0, "/root/repo")
 from efficientsam3_b200 import ops
-shapes = [(131072, 512, 128, "hswish", True), (131072, 384, 128, None, False), (32768, 1024, 256, None, True), (2097152, 128, 64, None, True),
+shapes = [(131072, 512, 256, "gelu", True), (131072, 512, 256, None, True), (131072, 512, 256, None, False), (2097152, 128, 64, "gelu", True),
+          (2097152, 128, 64, None, True), (41472, 4736, 1024, "gelu", True), (41472, 4736, 1024, None, True), (131072, 512, 128, "hswish", True), (131072, 384, 128, None, False), (32768, 1024, 256, None, True), (2097152, 128, 64, None, True),
           (131072, 256, 512, None, True), (41472, 1024, 1024, None, True)]
 DBG = [(0, "full"), (1, "no stores"), (4, "epilogue = hand-back only")]
 for M, N, K, act, sb in shapes:
