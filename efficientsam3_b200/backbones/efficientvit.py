@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..nn_utils import NativePlanMixin, bn_scale_bias, dw_weight, pw_weight
+from ..nn_utils import NativePlanMixin, bn_scale_bias, dw_weight, pw_weight, pw_weight_scaled
 
 __all__ = ["EfficientViTBackbone", "efficientvit_backbone_b0", "efficientvit_backbone_b1", "efficientvit_backbone_b2"]
 
@@ -132,12 +132,13 @@ class _PW:
     """Packed pointwise conv: bf16 [N,K] weight + fp32 scale/bias + act."""
 
     def __init__(self, layer: ConvLayer, device):
-        self.w = pw_weight(layer.conv)
+        self.w = pw_weight(layer.conv)                        # unscaled: the fused MBConv kernels take (w, scale, bias) separately
         self.scale, self.bias = _fold(layer, device)
+        self.wf = pw_weight_scaled(layer.conv, self.scale)    # BN scale folded before the bf16 rounding: bias-only GEMM epilogue
         self.act = layer.act
 
     def __call__(self, x2d, residual=None, out=None):
-        return ops.gemm(x2d, self.w, scale=self.scale, bias=self.bias, act=self.act, residual=residual, out=out)
+        return ops.gemm(x2d, self.wf, bias=self.bias, act=self.act, residual=residual, out=out)
 
 
 class _DW:

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..nn_utils import NativePlanMixin, bn_scale_bias, dw_weight, pack_patch_embed, pw_weight
+from ..nn_utils import NativePlanMixin, bn_scale_bias, dw_weight, pack_patch_embed, pw_weight, pw_weight_scaled
 
 
 def _make_divisible(v, divisor, min_value=None):
@@ -111,14 +111,14 @@ class _SEPlan:
 
 class _PW:
     def __init__(self, cb: Conv2d_BN, act, dev):
-        self.w = pw_weight(cb.c)
         self.s, self.b = _fold_cb(cb, dev)
+        self.w = pw_weight_scaled(cb.c, self.s)               # BN scale folded before the bf16 rounding: bias-only GEMM epilogue
         self.act = act
 
     def __call__(self, x, residual=None):
         B, H, W, C = x.shape
         r = residual.view(-1, residual.shape[-1]) if residual is not None else None
-        return ops.gemm(x.view(-1, C), self.w, scale=self.s, bias=self.b, act=self.act, residual=r).view(B, H, W, -1)
+        return ops.gemm(x.view(-1, C), self.w, bias=self.b, act=self.act, residual=r).view(B, H, W, -1)
 
 
 class _BlockPlan:

@@ -139,6 +139,8 @@ def _cb(cb: Conv2d_BN, dev):
 
 class _PW:
     def __init__(self, cb, act, dev):
+        # (TinyViT keeps the BN scale in the fp32 epilogue: folding it into the bf16 weights bought 0.4 % and moved tiny_vit_5m from 1.46e-2
+        #  to 1.78e-2 of the reference, against a 2e-2 tolerance -- profiles/r2af_tests.log; RepViT / EfficientViT fold it)
         self.w = pw_weight(cb.c)
         self.s, self.b = _cb(cb, dev)
         self.act = act

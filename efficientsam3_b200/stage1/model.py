@@ -17,7 +17,7 @@ import torch.nn as nn
 from .. import ops
 from ..backbones.efficientvit import (efficientvit_backbone_b0, efficientvit_backbone_b1,
                                       efficientvit_backbone_b2)
-from ..nn_utils import NativePlanMixin, bn_scale_bias, conv3x3_weight, params_fingerprint, pw_weight
+from ..nn_utils import NativePlanMixin, bn_scale_bias, conv3x3_weight, params_fingerprint, pw_weight, pw_weight_scaled
 
 
 def build_image_student_model(config):
@@ -44,7 +44,7 @@ class ImageStudentEncoder(nn.Module, NativePlanMixin):
     def _build_plan(self):
         dev = self.head[0].weight.device
         s, b = bn_scale_bias(self.head[1], None, self.head[0].out_channels, dev)
-        return dict(w0=pw_weight(self.head[0]), s0=s, b0=b, w3=conv3x3_weight(self.head[3]),
+        return dict(w0=pw_weight_scaled(self.head[0], s), b0=b, w3=conv3x3_weight(self.head[3]),
                     b3=self.head[3].bias.detach().float().contiguous())
 
     def forward(self, x):
@@ -116,7 +116,7 @@ class ImageStudentEncoder(nn.Module, NativePlanMixin):
         feats = self.backbone.forward_nhwc(x)          # [B,h,w,Cin] bf16
         p = self._plan()
         B, h, w, cin = feats.shape
-        y = ops.gemm(feats.view(-1, cin), p["w0"], scale=p["s0"], bias=p["b0"], act="gelu")
+        y = ops.gemm(feats.view(-1, cin), p["w0"], bias=p["b0"], act="gelu")       # BN scale folded into w0 (nn_utils.pw_weight_scaled)
         y = ops.conv3x3(y.view(B, h, w, -1), p["w3"], bias=p["b3"])
         if h != self.embed_size or w != self.embed_size:
             return ops.bilinear_nhwc_to_nchw(y, self.embed_size, self.embed_size)
