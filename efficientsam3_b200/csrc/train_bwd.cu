@@ -150,6 +150,94 @@ __global__ void __launch_bounds__(CR_THREADS, 3) col_reduce_kernel(const bf16* _
   }
 }
 
+// The same reduction with the loads DECOUPLED from the registers: every thread streams its rows through a private ring of CRR_STAGES
+// 16-byte shared-memory slots per tensor with cp.async (it reads back only what it copied itself, so no barrier is involved) and keeps
+// CRR_STAGES - 1 rows in flight whatever the register pressure of the arithmetic.  The register-fed version above had two (backward
+// form) or four (statistics) rows in flight per thread and ran at 2.7 - 3.1 TB/s of 6.5 (profiles/r2x_train_step.json); with three
+// resident CTAs this one keeps 3 x 256 x 5 x 32 B = 120 KB per SM in flight.  part / geometry identical to col_reduce_kernel.
+constexpr int CRR_STAGES = 6;
+template <int ACT, bool STATS>
+__global__ void __launch_bounds__(CR_THREADS, 3) col_reduce_ring_kernel(const bf16* __restrict__ z, const bf16* __restrict__ da,
+                                                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                     long long M, int C, int CVB, long long rows_per_block,
+                                                                     float* __restrict__ part) {
+  __shared__ float red[CR_THREADS][17];
+  extern __shared__ __align__(16) uint4 crr_ring[];          // [CRR_STAGES][STATS ? 1 : 2][CR_THREADS]
+  constexpr int NT = STATS ? 1 : 2;
+  const int tid = threadIdx.x;
+  const int lanes = CR_THREADS / CVB;
+  const int cvl = tid % CVB, pl = tid / CVB;
+  const int cv = blockIdx.y * CVB + cvl;
+  const bool active = pl < lanes && cv * 8 < C;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s0[i] = s1[i] = 0.f;
+  if (active) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = (!STATS && scale) ? scale[cv * 8 + i] : 1.f;
+      sh[i] = (!STATS && shift) ? shift[cv * 8 + i] : 0.f;
+    }
+    float piv[8];
+    if constexpr (STATS) unpack8(__ldg(reinterpret_cast<const uint4*>(z + cv * 8)), piv);
+    const long long r0 = (long long)blockIdx.x * rows_per_block + pl;
+    const long long r1 = min(M, (long long)blockIdx.x * rows_per_block + rows_per_block);
+    const long long n = r0 < r1 ? (r1 - r0 + lanes - 1) / lanes : 0;      // rows of this thread: r0, r0 + lanes, ...
+    const uint32_t u_ring = static_cast<uint32_t>(__cvta_generic_to_shared(crr_ring)) + tid * 16;
+    auto issue = [&](long long k) {
+      if (k < n) {
+        const long long off = (r0 + k * lanes) * C + cv * 8;
+        const uint32_t slot = u_ring + (uint32_t)((k % CRR_STAGES) * NT) * (CR_THREADS * 16);
+        cpa16(slot, z + off, true);
+        if constexpr (!STATS) cpa16(slot + CR_THREADS * 16, da + off, true);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");       // one group per row slot, empty past the end: the wait count stays fixed
+    };
+#pragma unroll
+    for (int k = 0; k < CRR_STAGES - 1; ++k) issue(k);
+    for (long long k = 0; k < n; ++k) {
+      issue(k + CRR_STAGES - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(CRR_STAGES - 1) : "memory");
+      const uint4* slot = crr_ring + (size_t)((k % CRR_STAGES) * NT) * CR_THREADS + tid;
+      float fz[8];
+      unpack8(slot[0], fz);
+      if constexpr (STATS) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = fz[i] - piv[i]; s0[i] += d; s1[i] = fmaf(d, d, s1[i]); }
+      } else {
+        float fd[8];
+        unpack8(slot[CR_THREADS], fd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float g = fd[i] * act_grad_t<ACT>(fmaf(sc[i], fz[i], sh[i]));
+          s0[i] += g;
+          s1[i] = fmaf(g, fz[i], s1[i]);
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[tid][i] = s0[i]; red[tid][8 + i] = s1[i]; }
+  __syncthreads();
+  int top = 1;
+  while (top < lanes) top <<= 1;
+  for (int stride = top >> 1; stride > 0; stride >>= 1) {
+    if (pl < stride && pl + stride < lanes) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) red[tid][i] += red[tid + stride * CVB][i];
+    }
+    __syncthreads();
+  }
+  if (pl == 0 && cv * 8 < C) {
+    float* p0 = part + ((long long)blockIdx.x * 2) * C + cv * 8;
+    float* p1 = p0 + C;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { p0[i] = red[tid][i]; p1[i] = red[tid][8 + i]; }
+  }
+}
+
 // Second stage of the column reductions.  block 256 = 8 channels x 32 lanes: lane l adds partials l, l + 32, ... (double),
 // the 32 lanes are then summed in a fixed order.  (One thread per channel walking all <= 1184 partials serially cost
 // ~0.1 ms per BatchNorm layer -- 35 + 54 launches per step, profiles/r1_train_step_b.md.)
@@ -1291,6 +1379,12 @@ extern "C" long long es3_col_reduce_ws_floats(long long M, int C) {
   return (long long)nblk * 2 * C;
 }
 
+// ES3_COL_REDUCE_RING=0 selects the register-fed kernels (A/B timing); default: the cp.async ring
+static bool col_reduce_use_ring() {
+  static const bool on = [] { const char* e = getenv("ES3_COL_REDUCE_RING"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 static int col_reduce_geometry(long long M, int C, int* CVB, int* nblk, long long* rpb, int* gy) {
   const int CV = C / 8;
   *CVB = CV < CR_THREADS ? CV : CR_THREADS;
@@ -1323,7 +1417,12 @@ extern "C" int es3_bn_stats(const void* z, long long M, int C, float eps, float 
   long long rpb;
   col_reduce_geometry(M, C, &CVB, &nblk, &rpb, &gy);
   cudaStream_t st = (cudaStream_t)stream;
-  col_reduce_kernel<ACT_NONE, true><<<dim3(nblk, gy), CR_THREADS, 0, st>>>((const bf16*)z, nullptr, nullptr, nullptr, M, C, CVB, rpb, ws);
+  if (col_reduce_use_ring()) {
+    constexpr int RING = CRR_STAGES * 1 * CR_THREADS * 16;
+    col_reduce_ring_kernel<ACT_NONE, true><<<dim3(nblk, gy), CR_THREADS, RING, st>>>((const bf16*)z, nullptr, nullptr, nullptr, M, C, CVB, rpb, ws);
+  } else {
+    col_reduce_kernel<ACT_NONE, true><<<dim3(nblk, gy), CR_THREADS, 0, st>>>((const bf16*)z, nullptr, nullptr, nullptr, M, C, CVB, rpb, ws);
+  }
   ES3_LAUNCH_CHECK("col_reduce_kernel<stats>");
   bn_stats_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>((const bf16*)z, ws, nblk, C, M, eps, momentum, gamma, beta, mean, invstd, scale, shift,
                                                             running_mean, running_var, num_batches_tracked);
@@ -1355,8 +1454,19 @@ extern "C" int es3_bn_act_bwd_reduce(const void* da, const void* z, const float*
   long long rpb;
   col_reduce_geometry(M, C, &CVB, &nblk, &rpb, &gy);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool ring = col_reduce_use_ring();
   ES3_DISPATCH_ACT_BWD(act, A, {
-    col_reduce_kernel<A, false><<<dim3(nblk, gy), CR_THREADS, 0, st>>>((const bf16*)z, (const bf16*)da, scale, shift, M, C, CVB, rpb, ws);
+    if (ring) {
+      constexpr int RING = CRR_STAGES * 2 * CR_THREADS * 16;                     // 48 KB: needs the opt-in above the default 48 KB with `red`
+      static bool configured = false;
+      if (!configured) {
+        ES3_CHECK_CUDA(cudaFuncSetAttribute(col_reduce_ring_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RING));
+        configured = true;
+      }
+      col_reduce_ring_kernel<A, false><<<dim3(nblk, gy), CR_THREADS, RING, st>>>((const bf16*)z, (const bf16*)da, scale, shift, M, C, CVB, rpb, ws);
+    } else {
+      col_reduce_kernel<A, false><<<dim3(nblk, gy), CR_THREADS, 0, st>>>((const bf16*)z, (const bf16*)da, scale, shift, M, C, CVB, rpb, ws);
+    }
   })
   ES3_LAUNCH_CHECK("col_reduce_kernel<bwd>");
   bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(ws, nblk, C, M, mode, scale, mean, invstd, coef, dgamma, dbeta);
