@@ -100,3 +100,36 @@ def test_packed_weight_cache_follows_the_parameter():
     dw = torch.nn.Conv2d(8, 8, 3, padding=1, groups=8, bias=False)
     r = U.dw_weight_rot(dw)
     assert torch.equal(r, U.dw_weight(dw, None).flip(0)) and U.dw_weight_rot(dw) is r
+
+
+def test_folded_pointwise_weight_is_the_scaled_weight_rounded_once():
+    """nn_utils.pw_weight_scaled: W * s in fp32, then ONE bf16 rounding (not bf16(W) * s, which would round twice)."""
+    from efficientsam3_b200.nn_utils import pw_weight, pw_weight_scaled
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(24, 40, 1, bias=False)
+    s = torch.rand(40) * 3 + 0.1
+    wf = pw_weight_scaled(conv, s)
+    assert wf.dtype == torch.bfloat16 and wf.shape == (40, 24) and wf.is_contiguous()
+    exact = conv.weight.detach().reshape(40, 24) * s.view(-1, 1)
+    assert torch.equal(wf, exact.to(torch.bfloat16))
+    assert ((wf.float() - exact).abs() <= exact.abs() * 2.0 ** -8).all()
+    assert torch.equal(pw_weight_scaled(conv, None), pw_weight(conv))
+
+
+def test_tensor_core_tap_operand_is_cached_per_tensor_and_version(monkeypatch):
+    """ops._tc_taps: the sum-preserving bf16 taps are computed once per weight tensor object and recomputed after an in-place update."""
+    from efficientsam3_b200 import ops
+    calls = []
+
+    def fake_round(w):
+        calls.append(w._version)
+        return w.to(torch.bfloat16).float()
+    monkeypatch.setattr(ops, "round_taps_sum_bf16", fake_round)
+    w = torch.randn(9, 32)
+    a = ops._tc_taps(w)
+    b = ops._tc_taps(w)
+    assert a is b and len(calls) == 1
+    w.mul_(2.0)                                   # an optimiser step on the flat arena bumps the version of its views
+    c = ops._tc_taps(w)
+    assert c is not a and len(calls) == 2 and torch.equal(c, w.to(torch.bfloat16).float())
+    assert ops._tc_taps(torch.randn(9, 32)) is not c and len(calls) == 3
